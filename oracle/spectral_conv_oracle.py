@@ -1,0 +1,419 @@
+"""CPU oracle for the SpectralConv hot path.  TEST INFRASTRUCTURE -- NOT PRODUCT CODE.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU legs (`cpu_baseline`, `--impl reference`)
+may import this module.  The product package `neuraloperator_b200` never does, and has no CPU path.
+
+What it restates (reference = neuraloperator @ 93d3f06, paths relative to /root/reference):
+
+  * `kept_mode_plan`        <- neuralop/layers/spectral_convolution.py:404-415 (last-dim halving),
+                               :465-489 (weight slice when n_modes < max_n_modes),
+                               :500-519 (centred block in fft-shifted coordinates)
+  * `contract_*`            <- :21-46 dense, :55-73 CP, :76-103 Tucker, :106-132 TT (einsum strings)
+  * `spectral_conv_forward` <- :417-570 (rfftn -> shift -> slice -> contract -> scatter -> unshift ->
+                               ifftn(leading) -> zero Im of DC/Nyquist columns -> irfft(last) -> +bias)
+  * backward                <- whatever torch.autograd records for the above (the reference has no
+                               hand-written backward); `spectral_conv_backward_closed_form_f64` is the
+                               independent SURVEY.md App. A.3 statement used to cross-check it.
+
+Two independent statements live here on purpose:
+  (1) `spectral_conv_forward` -- torch.fft on CPU in fp32, i.e. the same library calls the reference makes
+      on its CPU path, written in gather/scatter form (no fftshift copies; the shift is index arithmetic).
+      This is the arm timed as the CPU baseline.
+  (2) `spectral_conv_forward_f64` -- explicit truncated DFT sums in float64 numpy (small sizes only).
+
+Pinning: `tests/test_oracle.py` checks (1) against golden vectors minted by `oracle/make_golden.py` from
+the UNMODIFIED reference module imported in the build container (`oracle/load_reference.py`), and, when
+/root/reference is present, against the live reference (`tests/test_oracle_vs_reference.py`).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+EINSUM_SYMBOLS = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"
+
+
+# --------------------------------------------------------------------------------------------------
+# index math
+# --------------------------------------------------------------------------------------------------
+def stored_n_modes(n_modes, complex_data: bool = False) -> List[int]:
+    """`SpectralConv.n_modes` setter, spectral_convolution.py:404-415."""
+    n = [n_modes] if isinstance(n_modes, int) else list(n_modes)
+    if not complex_data:
+        n[-1] = n[-1] // 2 + 1
+    return n
+
+
+@dataclass
+class DimPlan:
+    grid: int            # N_j, spatial size of the input along this dim
+    spec: int            # F_j, spectrum length (N_j, or N_j//2+1 for the last dim)
+    kept: int            # k'_j = min(F_j, n_modes_j)
+    in_bins: List[int]   # unshifted spectrum bin of the input read by kept slot t (len kept)
+    w_index: List[int]   # index along this dim of the (un-sliced) weight used by kept slot t
+    freqs: List[int]     # signed frequency of slot t (leading dims) / bin (last dim)
+
+
+def kept_mode_plan(grid: Sequence[int], n_modes_stored: Sequence[int],
+                   max_n_modes: Optional[Sequence[int]] = None) -> List[DimPlan]:
+    """Which spectrum bins are read, in which order, against which weight rows.
+
+    spectral_convolution.py:429-434 (fft_size), :465-489 (starts / slices_w), :500-519 (slices_x).
+    """
+    d = len(grid)
+    if max_n_modes is None:
+        max_n_modes = list(n_modes_stored)
+    plans = []
+    for j in range(d):
+        last = j == d - 1
+        N = int(grid[j])
+        F = N // 2 + 1 if last else N
+        k = min(F, int(n_modes_stored[j]))
+        start = int(max_n_modes[j]) - k
+        if start < 0:
+            raise ValueError("n_modes exceeds max_n_modes")
+        if last:
+            bins = list(range(k))                      # slice(None, k)  (:514-517)
+            w_idx = list(range(k))                     # slice(None, -start)  (:486)
+            freqs = list(range(k))
+        else:
+            centre = F // 2
+            neg, pos = k // 2, k // 2 + k % 2
+            shifted = list(range(centre - neg, centre + pos))           # (:507-512)
+            bins = [(s - F // 2) % F for s in shifted]                   # undo fftshift (roll by F//2)
+            freqs = [s - centre for s in shifted]
+            w0 = start // 2 if start else 0                             # slice(start//2, -start//2) (:476-485)
+            w_idx = list(range(w0, w0 + k))
+        plans.append(DimPlan(N, F, k, bins, w_idx, freqs))
+    return plans
+
+
+def resolve_output_grid(grid, resolution_scaling_factor=None, output_shape=None):
+    """spectral_convolution.py:524-528."""
+    if output_shape is not None:
+        return [int(s) for s in output_shape]
+    if resolution_scaling_factor is not None:
+        return [round(s * r) for s, r in zip(grid, resolution_scaling_factor)]
+    return [int(s) for s in grid]
+
+
+# --------------------------------------------------------------------------------------------------
+# contractions (einsum strings restated from spectral_convolution.py:21-132)
+# --------------------------------------------------------------------------------------------------
+def contract_dense(xm: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    order = xm.ndim
+    xs = EINSUM_SYMBOLS[:order]
+    o = EINSUM_SYMBOLS[order]
+    ws = xs[1] + o + xs[2:]
+    out = xs[0] + o + xs[2:]
+    return torch.einsum(f"{xs},{ws}->{out}", xm, w)
+
+
+def contract_tucker(xm: torch.Tensor, core: torch.Tensor, factors: Sequence[torch.Tensor]) -> torch.Tensor:
+    order = xm.ndim
+    xs = EINSUM_SYMBOLS[:order]
+    o = EINSUM_SYMBOLS[order]
+    cs = EINSUM_SYMBOLS[order + 1: 2 * order + 1]
+    fs = [xs[1] + cs[0], o + cs[1]] + [a + r for a, r in zip(xs[2:], cs[2:])]
+    out = xs[0] + o + xs[2:]
+    return torch.einsum(f"{xs},{cs},{','.join(fs)}->{out}", xm, core, *factors)
+
+
+def contract_cp(xm: torch.Tensor, weights: torch.Tensor, factors: Sequence[torch.Tensor]) -> torch.Tensor:
+    order = xm.ndim
+    xs = EINSUM_SYMBOLS[:order]
+    r = EINSUM_SYMBOLS[order]
+    o = EINSUM_SYMBOLS[order + 1]
+    fs = [xs[1] + r, o + r] + [a + r for a in xs[2:]]
+    out = xs[0] + o + xs[2:]
+    return torch.einsum(f"{xs},{r},{','.join(fs)}->{out}", xm, weights, *factors)
+
+
+def contract_tt(xm: torch.Tensor, cores: Sequence[torch.Tensor]) -> torch.Tensor:
+    order = xm.ndim
+    xs = list(EINSUM_SYMBOLS[:order])
+    ws = xs[1:]
+    ws.insert(1, EINSUM_SYMBOLS[order])
+    out = [xs[0]] + ws[1:]
+    rs = EINSUM_SYMBOLS[order + 1:]
+    tts = [rs[i] + s + rs[i + 1] for i, s in enumerate(ws)]
+    return torch.einsum("".join(xs) + "," + ",".join(tts) + "->" + "".join(out), xm, *cores)
+
+
+def tucker_to_dense(core, factors):
+    n = len(factors)
+    cs = EINSUM_SYMBOLS[:n]
+    os_ = EINSUM_SYMBOLS[n:2 * n]
+    return torch.einsum(cs + "," + ",".join(o + c for o, c in zip(os_, cs)) + "->" + os_, core, *factors)
+
+
+def cp_to_dense(weights, factors):
+    n = len(factors)
+    return torch.einsum("Z," + ",".join(s + "Z" for s in EINSUM_SYMBOLS[:n]) + "->" + EINSUM_SYMBOLS[:n],
+                        weights, *factors)
+
+
+@dataclass
+class Weight:
+    """kind in {"dense","tucker","cp","tt"}; tensors laid out as the reference's tltorch factors."""
+    kind: str
+    tensor: Optional[torch.Tensor] = None         # dense (Ci, Co, *max_n_modes)
+    core: Optional[torch.Tensor] = None           # tucker (r_i, r_o, r_1..r_d)
+    weights: Optional[torch.Tensor] = None        # cp (R,)
+    factors: Optional[List[torch.Tensor]] = None  # tucker/cp (dim_k, r_k) ; tt (r_k, dim_k, r_k+1)
+
+    def params(self):
+        if self.kind == "dense":
+            return [self.tensor]
+        if self.kind == "tucker":
+            return [self.core, *self.factors]
+        if self.kind == "cp":
+            return [self.weights, *self.factors]
+        return list(self.factors)
+
+    def sliced(self, plans: Sequence[DimPlan]) -> "Weight":
+        """`self.weight[slices_w]` (:489): a view for dense, sliced factors for Tucker/CP/TT."""
+        if self.kind == "dense":
+            t = self.tensor
+            for j, p in enumerate(plans):
+                t = t.narrow(2 + j, p.w_index[0], p.kept)
+            return Weight("dense", tensor=t)
+        fs = list(self.factors)
+        for j, p in enumerate(plans):
+            if self.kind == "tt":
+                fs[2 + j] = fs[2 + j][:, p.w_index[0]: p.w_index[0] + p.kept, :]
+            else:
+                fs[2 + j] = fs[2 + j][p.w_index[0]: p.w_index[0] + p.kept, :]
+        return Weight(self.kind, core=self.core, weights=self.weights, factors=fs)
+
+    def contract(self, xm):
+        if self.kind == "dense":
+            return contract_dense(xm, self.tensor)
+        if self.kind == "tucker":
+            return contract_tucker(xm, self.core, self.factors)
+        if self.kind == "cp":
+            return contract_cp(xm, self.weights, self.factors)
+        if self.kind == "tt":
+            return contract_tt(xm, self.factors)
+        raise ValueError(self.kind)
+
+    def to_dense(self):
+        if self.kind == "dense":
+            return self.tensor
+        if self.kind == "tucker":
+            return tucker_to_dense(self.core, self.factors)
+        if self.kind == "cp":
+            return cp_to_dense(self.weights, self.factors)
+        out = self.factors[0]
+        for f in self.factors[1:]:
+            out = torch.tensordot(out, f, dims=([-1], [0]))
+        return out.squeeze(0).squeeze(-1)
+
+
+# --------------------------------------------------------------------------------------------------
+# (1) torch.fft restatement -- fp32, CPU; this is the timed CPU baseline
+# --------------------------------------------------------------------------------------------------
+def _gather(x, dim, idx):
+    return x.index_select(dim, torch.as_tensor(idx, dtype=torch.long, device=x.device))
+
+
+def spectral_conv_forward(x: torch.Tensor, weight: Weight, bias: Optional[torch.Tensor],
+                          n_modes: Sequence[int], max_n_modes: Optional[Sequence[int]] = None,
+                          output_shape: Optional[Sequence[int]] = None,
+                          resolution_scaling_factor: Optional[Sequence[float]] = None,
+                          fft_norm: str = "forward", return_modes: bool = False):
+    """`SpectralConv.forward` for real data, full precision (spectral_convolution.py:417-570).
+
+    `n_modes` are the USER modes (the last one is halved here exactly as the setter does).
+    """
+    B, Ci, *grid = x.shape
+    d = len(grid)
+    stored = stored_n_modes(n_modes)
+    if max_n_modes is None:
+        max_n_modes = stored
+    plans = kept_mode_plan(grid, stored, max_n_modes)
+    dims = list(range(-d, 0))
+
+    spec = torch.fft.rfftn(x, norm=fft_norm, dim=dims)                  # :443
+    xm = spec
+    for j, p in enumerate(plans):                                        # :449 + :500-519 as a gather
+        xm = _gather(xm, 2 + j, p.in_bins)
+    w = weight.sliced(plans)                                             # :489
+    ym = w.contract(xm.to(torch.cfloat))                                 # :520-522
+
+    out_grid = resolve_output_grid(grid, resolution_scaling_factor, output_shape)   # :524-528
+    Co = ym.shape[1]
+    out_spec = torch.zeros([B, Co] + [p.spec for p in plans], dtype=torch.cfloat, device=x.device)  # :460-462
+    index = [torch.arange(B).view(-1, *[1] * (d + 1)), torch.arange(Co).view(1, -1, *[1] * d)]
+    for j, p in enumerate(plans):
+        shape = [1] * (d + 2)
+        shape[2 + j] = -1
+        index.append(torch.as_tensor(p.in_bins, dtype=torch.long).view(shape))
+    out_spec[tuple(index)] = ym                                          # scatter (:520) + ifftshift (:532)
+
+    if d > 1:                                                            # :548
+        out_spec = torch.fft.ifftn(out_spec, s=out_grid[:-1], dim=dims[:-1], norm=fft_norm)
+    out_spec[..., 0].imag.zero_()                                        # :552
+    if out_grid[-1] % 2 == 0:                                            # :555-556
+        out_spec[..., -1].imag.zero_()
+    y = torch.fft.irfft(out_spec, n=out_grid[-1], dim=-1, norm=fft_norm)  # :559
+    if bias is not None:
+        y = y + bias                                                     # :567-568
+    if return_modes:
+        return y, xm, ym
+    return y
+
+
+def spectral_conv_fwd_bwd(x, weight: Weight, bias, grad_y, n_modes, **kw):
+    """Forward + the backward torch.autograd records for it. Returns y, dx, [dparams...], dbias."""
+    x = x.detach().clone().requires_grad_(True)
+    params = [p.detach().clone().requires_grad_(True) for p in weight.params()]
+    if weight.kind == "dense":
+        w = Weight("dense", tensor=params[0])
+    elif weight.kind == "tucker":
+        w = Weight("tucker", core=params[0], factors=params[1:])
+    elif weight.kind == "cp":
+        w = Weight("cp", weights=params[0], factors=params[1:])
+    else:
+        w = Weight("tt", factors=params)
+    b = bias.detach().clone().requires_grad_(True) if bias is not None else None
+    y = spectral_conv_forward(x, w, b, n_modes, **kw)
+    y.backward(grad_y)
+    return y.detach(), x.grad, [p.grad for p in params], (b.grad if b is not None else None)
+
+
+# --------------------------------------------------------------------------------------------------
+# (2) closed-form float64 statement -- small sizes only
+# --------------------------------------------------------------------------------------------------
+def _norm_scales(grid, out_grid, fft_norm):
+    n_in, n_out = math.prod(grid), math.prod(out_grid)
+    if fft_norm == "forward":
+        return 1.0 / n_in, 1.0
+    if fft_norm == "backward":
+        return 1.0, 1.0 / n_out
+    if fft_norm == "ortho":
+        return 1.0 / math.sqrt(n_in), 1.0 / math.sqrt(n_out)
+    raise ValueError(fft_norm)
+
+
+def analysis_matrices_f64(plans: Sequence[DimPlan]):
+    """Per dim: complex matrix A_j[t, n] = exp(-2 pi i bin_t n / N_j)  (kept x grid)."""
+    mats = []
+    for p in plans:
+        n = np.arange(p.grid)[None, :]
+        b = np.asarray(p.in_bins)[:, None]
+        mats.append(np.exp(-2j * np.pi * b * n / p.grid))
+    return mats
+
+
+def synthesis_matrices_f64(plans: Sequence[DimPlan], out_grid: Sequence[int]):
+    """Leading dims: S_j[n, t] = exp(+2 pi i bin_t n / M_j) if bin_t < M_j else 0 (ifftn's crop/pad of the
+    unshifted spectrum, :548).  Last dim: returns (Sre, Sim) real matrices so that
+    y[n] = sum_t Sre[n,t] Re(Y_t) + Sim[n,t] Im(Y_t)  -- C2R with the Hermitian rules (:552-559)."""
+    d = len(plans)
+    lead = []
+    for j in range(d - 1):
+        p, M = plans[j], out_grid[j]
+        n = np.arange(M)[:, None]
+        b = np.asarray(p.in_bins)[None, :]
+        S = np.exp(2j * np.pi * b * n / M)
+        S = S * (b < M)
+        lead.append(S)
+    p, M = plans[-1], out_grid[-1]
+    n = np.arange(M)[:, None]
+    q = np.asarray(p.in_bins)[None, :]
+    used = q < (M // 2 + 1)
+    c = np.where((q == 0) | ((M % 2 == 0) & (q == M // 2)), 1.0, 2.0)
+    im_dead = (q == 0) | ((M % 2 == 0) & ((q == M // 2) | (q == p.spec - 1)))
+    Sre = c * np.cos(2 * np.pi * q * n / M) * used
+    Sim = -c * np.sin(2 * np.pi * q * n / M) * used * (~im_dead)
+    return lead, Sre, Sim
+
+
+def spectral_conv_forward_f64(x, w_dense_sliced, bias, plans, out_grid, fft_norm="forward"):
+    """x (B,Ci,*grid) float64 ndarray; w (Ci,Co,*kept) complex128, ALREADY sliced to the kept block."""
+    d = len(plans)
+    grid = [p.grid for p in plans]
+    s_fwd, s_inv = _norm_scales(grid, out_grid, fft_norm)
+    xm = x.astype(np.complex128)
+    for j, A in enumerate(analysis_matrices_f64(plans)):
+        xm = np.moveaxis(np.tensordot(A, xm, axes=([1], [2 + j])), 0, 2 + j)
+    xm = xm * s_fwd
+    letters = "xyzw"[:d]
+    ym = np.einsum(f"bi{letters},io{letters}->bo{letters}", xm, w_dense_sliced)
+    lead, Sre, Sim = synthesis_matrices_f64(plans, out_grid)
+    t = ym
+    for j, S in enumerate(lead):
+        t = np.moveaxis(np.tensordot(S, t, axes=([1], [2 + j])), 0, 2 + j)
+    y = np.tensordot(t.real, Sre, axes=([t.ndim - 1], [1])) + np.tensordot(t.imag, Sim, axes=([t.ndim - 1], [1]))
+    y = y * s_inv
+    if bias is not None:
+        y = y + bias
+    return y, xm, ym
+
+
+def spectral_conv_backward_closed_form_f64(x, w_dense_sliced, grad_y, plans, out_grid, fft_norm="forward"):
+    """SURVEY.md App. A.3 generalised to output resampling: adjoints of the synthesis / analysis maps.
+    Returns dx (real), dW (complex, PyTorch conj convention, kept block only), db."""
+    d = len(plans)
+    grid = [p.grid for p in plans]
+    s_fwd, s_inv = _norm_scales(grid, out_grid, fft_norm)
+    _, xm, _ = spectral_conv_forward_f64(x, w_dense_sliced, None, plans, out_grid, fft_norm)
+    lead, Sre, Sim = synthesis_matrices_f64(plans, out_grid)
+    g = grad_y * s_inv
+    gre = np.tensordot(g, Sre, axes=([g.ndim - 1], [0]))
+    gim = np.tensordot(g, Sim, axes=([g.ndim - 1], [0]))
+    gm = gre + 1j * gim                              # dL/dRe + i dL/dIm of the last-dim-synthesis input
+    for j, S in enumerate(lead):
+        gm = np.moveaxis(np.tensordot(S.conj().T, gm, axes=([1], [2 + j])), 0, 2 + j)
+    letters = "xyzw"[:d]
+    dW = np.einsum(f"bi{letters},bo{letters}->io{letters}", xm.conj(), gm)
+    dxm = np.einsum(f"bo{letters},io{letters}->bi{letters}", gm, w_dense_sliced.conj()) * s_fwd
+    t = dxm
+    for j, A in enumerate(analysis_matrices_f64(plans)):
+        t = np.moveaxis(np.tensordot(A.conj().T, t, axes=([1], [2 + j])), 0, 2 + j)
+    dx = t.real
+    db = grad_y.sum(axis=tuple([0] + list(range(2, grad_y.ndim))))
+    return dx, dW, db
+
+
+# --------------------------------------------------------------------------------------------------
+# deterministic synthetic inputs shared by tests / smoke / bench
+# --------------------------------------------------------------------------------------------------
+def make_inputs(B, Ci, Co, grid, n_modes, seed=0, kind="dense", ranks=None, max_n_modes=None,
+                out_grid=None, dtype=torch.float32):
+    gen = torch.Generator().manual_seed(seed)
+    std = (2.0 / (Ci + Co)) ** 0.5
+    stored = stored_n_modes(n_modes)
+    wshape = list(max_n_modes) if max_n_modes is not None else stored
+
+    def crandn(*shape, scale=1.0):
+        re = torch.randn(*shape, generator=gen, dtype=dtype)
+        im = torch.randn(*shape, generator=gen, dtype=dtype)
+        return torch.complex(re, im) * (scale / math.sqrt(2.0))
+
+    x = torch.randn(B, Ci, *grid, generator=gen, dtype=dtype)
+    og = list(out_grid) if out_grid is not None else list(grid)
+    gy = torch.randn(B, Co, *og, generator=gen, dtype=dtype)
+    bias = torch.randn(Co, *([1] * len(grid)), generator=gen, dtype=dtype) * std
+    full = [Ci, Co] + wshape
+    if kind == "dense":
+        w = Weight("dense", tensor=crandn(*full, scale=std))
+    elif kind == "tucker":
+        ranks = list(ranks)
+        # every entry of the reconstructed tensor has variance prod(r) * v^(n+1): choose v to land on std^2
+        s = ((std * std) / math.prod(ranks)) ** (0.5 / (len(full) + 1))
+        w = Weight("tucker", core=crandn(*ranks, scale=s),
+                   factors=[crandn(n, r, scale=s) for n, r in zip(full, ranks)])
+    elif kind == "cp":
+        R = int(ranks)
+        s = ((std * std) / R) ** (0.5 / len(full))
+        cdt = torch.cfloat if dtype == torch.float32 else torch.cdouble
+        w = Weight("cp", weights=torch.ones(R, dtype=cdt), factors=[crandn(n, R, scale=s) for n in full])
+    else:
+        raise ValueError(kind)
+    return x, w, bias, gy

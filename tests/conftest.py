@@ -1,0 +1,83 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_index():
+    with open(os.path.join(GOLDEN_DIR, "index.json")) as f:
+        return json.load(f)["cases"]
+
+
+def load_golden(name):
+    meta = golden_index()[name]
+    data = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return meta, {k: torch.from_numpy(data[k]) for k in data.files}
+
+
+def golden_weight(meta, arrays):
+    """Builds the oracle's Weight from a golden file's parameter tensors."""
+    from oracle.spectral_conv_oracle import Weight
+    kind = meta["weight_kind"]
+    p = {k[3:].replace("__", "."): v for k, v in arrays.items() if k.startswith("p__")}
+    nf = len([k for k in p if k.startswith("weight.factors.")])
+    factors = [p[f"weight.factors.{i}"] for i in range(nf)]
+    if kind == "dense":
+        return Weight("dense", tensor=p["weight.tensor"])
+    if kind == "tucker":
+        return Weight("tucker", core=p["weight.core"], factors=factors)
+    if kind == "cp":
+        return Weight("cp", weights=p["weight.weights"], factors=factors)
+    if kind == "tt":
+        return Weight("tt", factors=factors)
+    raise ValueError(kind)
+
+
+def golden_grads(meta, arrays):
+    g = {k[3:].replace("__", "."): v for k, v in arrays.items() if k.startswith("g__")}
+    kind = meta["weight_kind"]
+    nf = len([k for k in g if k.startswith("weight.factors.")])
+    factors = [g[f"weight.factors.{i}"] for i in range(nf)]
+    if kind == "dense":
+        w = [g["weight.tensor"]]
+    elif kind == "tucker":
+        w = [g["weight.core"], *factors]
+    elif kind == "cp":
+        w = [g["weight.weights"], *factors]
+    else:
+        w = factors
+    return w, g.get("bias")
+
+
+def forward_kwargs(meta):
+    kw = {}
+    ctor = meta["ctor"]
+    if "max_n_modes" in ctor:
+        kw["max_n_modes"] = ctor["max_n_modes"]
+    if "resolution_scaling_factor" in ctor:
+        kw["resolution_scaling_factor"] = [float(ctor["resolution_scaling_factor"])] * len(meta["grid"])
+    if "fft_norm" in ctor:
+        kw["fft_norm"] = ctor["fft_norm"]
+    if "output_shape" in meta["forward"]:
+        kw["output_shape"] = meta["forward"]["output_shape"]
+    return kw
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")

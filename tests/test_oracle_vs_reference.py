@@ -1,0 +1,38 @@
+"""When the reference tree is present (build container only), the oracle must reproduce the
+UNMODIFIED reference module bit-for-bit on CPU. Skipped on the GPU box (no /root/reference there)."""
+import pytest
+import torch
+
+from oracle import spectral_conv_oracle as O
+from oracle.load_reference import load_reference_spectral_conv, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("grid,modes,kw", [
+    ((64,), (16,), {}),
+    ((32, 32), (16, 16), {}),
+    ((16, 16, 16), (8, 8, 8), {}),
+    ((9, 11), (5, 4), {}),
+    ((16, 12), (5, 4), {"max_n_modes": (8, 6)}),
+    ((12, 12), (10, 8), {"resolution_scaling_factor": 2}),
+])
+def test_live_reference_bit_exact(grid, modes, kw):
+    ref = load_reference_spectral_conv()
+    torch.manual_seed(7)
+    conv = ref.SpectralConv(4, 6, modes, **kw)
+    x = torch.randn(2, 4, *grid, requires_grad=True)
+    y = conv(x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    okw = {}
+    if "max_n_modes" in kw:
+        okw["max_n_modes"] = conv.max_n_modes
+    if "resolution_scaling_factor" in kw:
+        okw["resolution_scaling_factor"] = [float(kw["resolution_scaling_factor"])] * len(grid)
+    w = O.Weight("dense", tensor=conv.weight.tensor.detach())
+    y2, dx2, dws, db = O.spectral_conv_fwd_bwd(x.detach(), w, conv.bias.detach(), g, modes, **okw)
+    assert torch.equal(y.detach(), y2)
+    assert torch.equal(x.grad, dx2)
+    assert torch.equal(conv.weight.tensor.grad, dws[0])
+    assert torch.equal(conv.bias.grad, db)
