@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- SpectralConv fwd+bwd samples/sec at (B,C,H,W)=(32,64,128,128), modes=(32,32)  (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 50 --warmup 10              # our sm_100a path, one JSON line
+    python bench.py --impl reference --steps 5 --warmup 1        # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...        # batch-sharded, one NCCL gradient all-reduce/step
+
+One "step" = y = conv(x); y.backward(g) producing dx, dweight, dbias for one batch of synthetic input
+(weak scaling: every rank owns a full batch of 32).  `value` is measured with inputs resident in HBM;
+`e2e` is the same step through the nn.Module with pinned HOST buffers, copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SpectralConv fwd+bwd samples/sec at (B,C,H,W)=(32,64,128,128) modes=(32,32)"
+UNIT = "samples/s"
+B, C, H, W = 32, 64, 128, 128
+MODES = (32, 32)
+WORKLOAD = "FNO2d Darcy dense SpectralConv fwd+bwd, (B,C,H,W)=(32,64,128,128) per GPU, n_modes=(32,32) [BASELINE configs[1]]"
+
+
+def algorithmic_bytes_step(b=B, ci=C, co=C, grid=(H, W), kept=(32, 17)):
+    """16*B*C*S + 24*Ci*Co*M + 16*B*C*M bytes per fwd+bwd step."""
+    s = 1
+    for g in grid:
+        s *= g
+    m = 1
+    for k in kept:
+        m *= k
+    return 16 * b * ci * s + 24 * ci * co * m + 16 * b * ci * m
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_step_time(steps, warmup, max_seconds=None):
+    """The reference's CPU path (oracle port: the same torch.fft / einsum calls) on all host cores."""
+    import torch
+    from oracle import spectral_conv_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x, w, bias, gy = O.make_inputs(B, C, C, (H, W), MODES, seed=0)
+    times = []
+    t_start = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.spectral_conv_fwd_bwd(x, w, bias, gy, MODES)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if max_seconds is not None and i >= warmup and time.perf_counter() - t_start > max_seconds:
+            break
+    return times, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    times, cores = cpu_oracle_step_time(args.steps, args.warmup)
+    total = sum(times)
+    value = B * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "arm": "reference CPU path (torch.fft + einsum, oracle port of "
+                   "neuralop/layers/spectral_convolution.py:417-570 + autograd backward)", "host_threads": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} full steps of batch {B} (whole workload per step)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import neuraloperator_b200 as nb
+    from neuraloperator_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world:
+        args.gpus = world
+
+    torch.manual_seed(rank)
+    conv = nb.SpectralConv(C, C, MODES).to(dev)
+    x = torch.randn(B, C, H, W, device=dev, requires_grad=True)
+    g = torch.randn(B, C, H, W, device=dev)
+    reducer = nb.GradientAllReducer(conv.parameters()) if world > 1 else None
+
+    def step():
+        conv.weight.tensor.grad = None
+        conv.bias.grad = None
+        x.grad = None
+        y = conv(x)
+        y.backward(g)
+        if reducer is not None:
+            reducer.start()
+            reducer.finish()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = t.item()
+    ms_per_step = ms_max / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel: the forward analysis transform chain (x -> kept modes) ------------
+    plan = nb.get_plan(dev, (H, W), (H, W), conv.n_modes, conv.max_n_modes)
+    xd = x.detach()
+    for _ in range(3):
+        nb.analyze(plan, xd)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    reps = 20
+    # y/dy-sized buffers are touched between repetitions by the surrounding step in real use; here the 134 MB input
+    # itself exceeds the 126 MB L2
+    k0.record()
+    for _ in range(reps):
+        nb.analyze(plan, xd)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    analyze_ms = k0.elapsed_time(k1) / reps
+    kept = plan.kept
+    m_tot = kept[0] * kept[1]
+    analyze_bytes = 4 * B * C * H * W + 8 * B * C * m_tot
+    peak, peak_src = measured_peaks()
+    achieved = analyze_bytes / (analyze_ms * 1e-3) / 1e9
+    step_bytes = algorithmic_bytes_step(kept=kept)
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: same step through the nn.Module with pinned host buffers -------------------------------------
+    e2e = None
+    cpu_base = None
+    if True:
+        xh = torch.randn(B, C, H, W).pin_memory()
+        gh = torch.randn(B, C, H, W).pin_memory()
+        yh = torch.empty(B, C, H, W).pin_memory()
+        dxh = torch.empty(B, C, H, W).pin_memory()
+        dwh = torch.empty(conv.weight.tensor.shape, dtype=torch.complex64).pin_memory()
+        dbh = torch.empty(conv.bias.shape).pin_memory()
+
+        def e2e_step():
+            conv.weight.tensor.grad = None
+            conv.bias.grad = None
+            xd2 = xh.to(dev, non_blocking=True).requires_grad_(True)
+            gd2 = gh.to(dev, non_blocking=True)
+            y = conv(xd2)
+            y.backward(gd2)
+            if reducer is not None:
+                reducer.start()
+                reducer.finish()
+            yh.copy_(y.detach(), non_blocking=True)
+            dxh.copy_(xd2.grad, non_blocking=True)
+            dwh.copy_(conv.weight.tensor.grad, non_blocking=True)
+            dbh.copy_(conv.bias.grad, non_blocking=True)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        n_e2e = max(5, min(args.steps, 20))
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        a1.record()
+        barrier()
+        t2 = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = t2.item() / n_e2e
+        h2d = xh.numel() * 4 + gh.numel() * 4
+        d2h = yh.numel() * 4 + dxh.numel() * 4 + dwh.numel() * 8 + dbh.numel() * 4
+        e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": e2e_ms, "steps": n_e2e}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, cores = cpu_oracle_step_time(steps=10, warmup=1, max_seconds=12.0)
+        cpu_v = B * len(times) / sum(times)
+        cpu_base = {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{len(times)} full steps of batch {B} after 1 warm-up (oracle port of the reference's "
+                              "torch.fft/einsum CPU path)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "no flush: x, g, y, dx are 134 MB each (537 MB touched per step) > 126 MB L2",
+                       "fast_path_mask": plan.uses_fast_path()},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "forward analysis chain (x -> kept modes): " +
+                         ("fused tcgen05 kernel" if plan.uses_fast_path() & 1 else "k_real_table_gemm + k_complex_table_gemm"),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "bytes_per_launch": analyze_bytes, "ms_per_launch": analyze_ms, "traffic": None,
+                         "step": {"bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak}},
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        args.steps = 5 if args.steps is None else args.steps
+        args.warmup = 1 if args.warmup is None else args.warmup
+        return run_reference(args)
+    args.steps = 50 if args.steps is None else args.steps
+    args.warmup = 10 if args.warmup is None else args.warmup
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,112 @@
+/*
+ * spectral_conv_b200.h -- C ABI of the B200-native SpectralConv hot path (libspectral_conv_b200.so).
+ *
+ * Drop-in boundary for ONE reference method and the backward PyTorch records for it:
+ *
+ *     neuralop/layers/spectral_convolution.py:417-570   SpectralConv.forward (real data, full precision)
+ *
+ * Plain pointers and sizes only: no torch / pybind types cross this boundary.  All `float*` / `sc_complex*`
+ * arguments are DEVICE pointers on the device that was current when the plan was created; the caller
+ * (neuraloperator_b200/spectral_conv.py on the Python side) owns every buffer, allocates outputs and
+ * workspace through its own allocator (torch's caching allocator) and passes the CUDA stream to launch on.
+ * Every entry point returns 0 on success, non-zero on failure (sc_last_error() describes it); there is
+ * no CPU fallback behind any of them.
+ *
+ * Layouts (all contiguous, row-major):
+ *   x, dx      float  (B, Ci, N_1..N_d)            input / its gradient
+ *   y, gy      float  (B, Co, M_1..M_d)            output / upstream gradient (M = N unless resampled)
+ *   modes      sc_complex (B, C, k_1..k_d)         kept-mode block, ordered exactly like the reference's
+ *                                                  x[slices_x] (:500-519): leading dims by increasing signed
+ *                                                  frequency, last dim bins 0..k_d-1
+ *   weight     sc_complex (Ci, Co, max_1..max_d)   dense weight as stored by the module (:354-369)
+ *   bias       float  (Co)                         bias (Co,1,..,1) flattened (:376-379)
+ */
+#ifndef SPECTRAL_CONV_B200_H
+#define SPECTRAL_CONV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_MAX_DIMS 4
+
+typedef struct { float re, im; } sc_complex;   /* bit-compatible with torch.complex64 / cuFloatComplex */
+typedef struct sc_plan sc_plan;                /* opaque; owns the device-resident twiddle tables */
+typedef void* sc_stream;                       /* cudaStream_t */
+
+enum { SC_NORM_FORWARD = 0, SC_NORM_BACKWARD = 1, SC_NORM_ORTHO = 2 };   /* fft_norm, :303,:342 */
+
+/* What SpectralConv.forward derives from its arguments before touching data (:429-434, :465-528). */
+typedef struct {
+  int32_t ndim;                       /* 1..4 spatial dims ("order", :318)                                   */
+  int32_t grid[SC_MAX_DIMS];          /* N_j : x.shape[2:]                                                   */
+  int32_t out_grid[SC_MAX_DIMS];      /* M_j : output_shape / round(N_j * resolution_scaling_factor) (:524-528) */
+  int32_t n_modes[SC_MAX_DIMS];       /* SpectralConv.n_modes as STORED (last already n//2+1, :404-415)       */
+  int32_t max_n_modes[SC_MAX_DIMS];   /* SpectralConv.max_n_modes = weight extents along the mode dims (:317-321) */
+  int32_t fft_norm;                   /* SC_NORM_*                                                           */
+} sc_problem;
+
+/* ---- plan: kept-mode index set + twiddle tables (replaces the slices built at :465-519) ---------------- */
+int  sc_plan_create(const sc_problem* problem, sc_plan** plan_out);
+void sc_plan_destroy(sc_plan* plan);
+/* kept modes per dim k'_j = min(F_j, n_modes_j) (:466); returns ndim */
+int  sc_plan_kept_modes(const sc_plan* plan, int32_t* kept_out);
+/* unshifted spectrum bin read by kept slot t of dim `dim`, and the weight row it is multiplied with
+ * (the content of slices_x after undoing fftshift, and of slices_w; :476-519).  Each array has kept[dim] entries. */
+int  sc_plan_mode_bins(const sc_plan* plan, int dim, int32_t* in_bins_out, int32_t* weight_rows_out);
+/* scratch the transform entry points need for `batch_times_channels` images (max over Ci, Co) */
+size_t sc_workspace_bytes(const sc_plan* plan, int64_t batch_times_channels);
+/* 0 = generic SIMT kernels only, 1 = tcgen05/TMA fused path where the shape qualifies (default) */
+int  sc_plan_set_fast_path(sc_plan* plan, int enable);
+int  sc_plan_uses_fast_path(const sc_plan* plan);
+
+/* ---- the two transforms ------------------------------------------------------------------------------- */
+/* Truncated analysis:  images (n_images, grid..) real  ->  modes (n_images, k_1..k_d).
+ *   adjoint == 0 : rfftn(norm) + fftshift + x[slices_x]                      (:443-449, :500-519)  on `grid`
+ *   adjoint == 1 : the adjoint of sc_synthesize (what autograd applies to gy): images live on `out_grid`.   */
+int sc_analyze(const sc_plan* plan, const float* images, int64_t n_images, sc_complex* modes_out,
+               int adjoint, void* workspace, size_t workspace_bytes, sc_stream stream);
+/* Zero-padded synthesis: modes (n_images, k_1..k_d) -> images real.
+ *   adjoint == 0 : scatter + ifftshift + ifftn(leading) + Hermitian fix + irfft(last) + bias   (:460-462,:520-568)
+ *                  onto `out_grid`; bias (n_channels) may be NULL; image n uses bias[n % n_channels].
+ *   adjoint == 1 : the adjoint of sc_analyze (produces dx on `grid`); bias must be NULL.                    */
+int sc_synthesize(const sc_plan* plan, const sc_complex* modes_in, int64_t n_images, int32_t n_channels,
+                  const float* bias, float* images_out, int adjoint,
+                  void* workspace, size_t workspace_bytes, sc_stream stream);
+
+/* ---- dense mode-wise contraction (_contract_dense, :21-46) and its backward ------------------------------ */
+/* ym[b,o,m] = sum_i xm[b,i,m] * weight[i,o,w(m)] */
+int sc_contract_dense(const sc_plan* plan, const sc_complex* xm, const sc_complex* weight, sc_complex* ym,
+                      int32_t batch, int32_t in_channels, int32_t out_channels, sc_stream stream);
+/* dxm[b,i,m] = sum_o gm[b,o,m] * conj(weight[i,o,w(m)])                 (dxm may be NULL)
+ * dweight[i,o,w(m)] = sum_b conj(xm[b,i,m]) * gm[b,o,m], zero elsewhere  (dweight may be NULL; full weight shape)
+ * dbias[o] = sum_{b,n} gy[b,o,n], read off the DC slot of gm             (dbias may be NULL) */
+int sc_contract_dense_backward(const sc_plan* plan, const sc_complex* xm, const sc_complex* gm,
+                               const sc_complex* weight, sc_complex* dxm, sc_complex* dweight, float* dbias,
+                               int32_t batch, int32_t in_channels, int32_t out_channels, sc_stream stream);
+/* dbias alone (used by the factorized paths): dbias[o] = sum_b Re(gm[b,o,DC]) / synthesis scale */
+int sc_bias_grad(const sc_plan* plan, const sc_complex* gm, float* dbias, int32_t batch, int32_t out_channels,
+                 sc_stream stream);
+
+/* ---- whole forward / backward for a dense weight (one call per autograd.Function.forward/backward) ------ */
+/* y = SpectralConv.forward(x); xm_saved (B,Ci,k..) is the only activation kept for backward. */
+int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weight, const float* bias,
+                     float* y, sc_complex* xm_saved, int32_t batch, int32_t in_channels, int32_t out_channels,
+                     void* workspace, size_t workspace_bytes, sc_stream stream);
+int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* weight, const sc_complex* xm_saved,
+                      float* dx, sc_complex* dweight, float* dbias,
+                      int32_t batch, int32_t in_channels, int32_t out_channels,
+                      void* workspace, size_t workspace_bytes, sc_stream stream);
+
+/* ---- diagnostics --------------------------------------------------------------------------------------- */
+const char* sc_last_error(void);          /* thread-local description of the last failure */
+uint64_t    sc_kernel_launch_count(void); /* kernels this library has launched so far (process-wide) */
+const char* sc_build_info(void);          /* "sm_100a nvcc <ver> ..." */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRAL_CONV_B200_H */

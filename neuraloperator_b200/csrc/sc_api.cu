@@ -1,0 +1,466 @@
+// C ABI of libspectral_conv_b200.so: plan construction (kept-mode index set + twiddle tables) and the
+// orchestration of the transform / contraction kernels.  See include/spectral_conv_b200.h for the contract
+// and the reference lines each entry point replaces.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "sc_plan.h"
+#include "sc_fast.h"
+
+namespace sc {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return false;
+}
+
+template <typename T>
+static bool upload(Plan* p, const std::vector<T>& host, T** dev) {
+  void* d = nullptr;
+  const size_t bytes = host.size() * sizeof(T);
+  if (!cuda_ok(cudaMalloc(&d, bytes ? bytes : sizeof(T)), "cudaMalloc(table)")) return false;
+  p->owned.push_back(d);
+  if (bytes && !cuda_ok(cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice), "cudaMemcpy(table)")) return false;
+  *dev = static_cast<T*>(d);
+  return true;
+}
+
+static const double kTwoPi = 6.283185307179586476925286766559;
+
+// exp(sign * 2 pi i * (a*b mod n) / n) with the angle reduced in integers first
+static inline void unit(long long a, long long b, long long n, int sign, double* re, double* im) {
+  const long long r = ((a % n) * (b % n)) % n;
+  const double ang = kTwoPi * (double)r / (double)n;
+  *re = std::cos(ang);
+  *im = sign * std::sin(ang);
+}
+
+static bool build_plan(const sc_problem& pr, Plan* p) {
+  p->prob = pr;
+  p->d = pr.ndim;
+  const int d = p->d;
+  if (d < 1 || d > SC_MAX_DIMS) { set_error("ndim must be in 1..4"); return false; }
+  if (pr.fft_norm < 0 || pr.fft_norm > 2) { set_error("unknown fft_norm"); return false; }
+  if (!cuda_ok(cudaGetDevice(&p->device), "cudaGetDevice")) return false;
+
+  p->n_modes_total = p->grid_points = p->out_points = p->weight_elems_per_io = 1;
+  p->weight_block_is_whole = true;
+  for (int j = 0; j < d; ++j) {
+    DimTables& t = p->dim[j];
+    const bool last = (j == d - 1);
+    t.N = pr.grid[j];
+    t.M = pr.out_grid[j];
+    if (t.N < 1 || t.M < 1) { set_error("grid sizes must be >= 1"); return false; }
+    if (pr.n_modes[j] < 1) { set_error("n_modes must be >= 1 along every dim"); return false; }
+    t.F = last ? t.N / 2 + 1 : t.N;
+    t.k = pr.n_modes[j] < t.F ? pr.n_modes[j] : t.F;                      // min(size, n_mode)   (:466)
+    const int start = pr.max_n_modes[j] - t.k;                            // (:465-468)
+    if (start < 0) { set_error("n_modes exceeds max_n_modes (weight too small for the requested modes)"); return false; }
+    t.in_bins.resize(t.k);
+    if (last) {
+      t.w0 = 0;                                                           // slice(None, -start)  (:486)
+      for (int s = 0; s < t.k; ++s) t.in_bins[s] = s;                      // slice(None, k)       (:514-517)
+    } else {
+      t.w0 = start ? start / 2 : 0;                                       // slice(start//2, -start//2) (:476-485)
+      const int centre = t.F / 2, neg = t.k / 2;                          // (:507-512)
+      for (int s = 0; s < t.k; ++s) {
+        const int shifted = centre - neg + s;
+        t.in_bins[s] = ((shifted - t.F / 2) % t.F + t.F) % t.F;           // undo fftshift = roll by F//2 (:449)
+      }
+    }
+    if (start != 0) p->weight_block_is_whole = false;
+    p->n_modes_total *= t.k;
+    p->grid_points *= t.N;
+    p->out_points *= t.M;
+    p->weight_elems_per_io *= pr.max_n_modes[j];
+  }
+  if (p->weight_elems_per_io * 1.0 > 2.0e9 || p->n_modes_total > (1ll << 30)) { set_error("mode block too large"); return false; }
+  switch (pr.fft_norm) {
+    case SC_NORM_FORWARD:  p->s_fwd = 1.0 / (double)p->grid_points; p->s_inv = 1.0; break;
+    case SC_NORM_BACKWARD: p->s_fwd = 1.0; p->s_inv = 1.0 / (double)p->out_points; break;
+    default: p->s_fwd = 1.0 / std::sqrt((double)p->grid_points); p->s_inv = 1.0 / std::sqrt((double)p->out_points);
+  }
+
+  // ---- leading dims: complex tables
+  for (int j = 0; j + 1 < d; ++j) {
+    DimTables& t = p->dim[j];
+    std::vector<float2> A((size_t)t.k * t.N), AH((size_t)t.N * t.k), S((size_t)t.M * t.k), SH((size_t)t.k * t.M);
+    for (int s = 0; s < t.k; ++s) {
+      const int b = t.in_bins[s];
+      for (int n = 0; n < t.N; ++n) {
+        double re, im;
+        unit(b, n, t.N, -1, &re, &im);
+        A[(size_t)s * t.N + n] = make_float2((float)re, (float)im);
+        AH[(size_t)n * t.k + s] = make_float2((float)re, (float)-im);
+      }
+      for (int n = 0; n < t.M; ++n) {
+        double re = 0.0, im = 0.0;
+        if (b < t.M) unit(b, n, t.M, +1, &re, &im);       // ifftn(s=M) crops / zero-pads the UNSHIFTED spectrum (:548)
+        S[(size_t)n * t.k + s] = make_float2((float)re, (float)im);
+        SH[(size_t)s * t.M + n] = make_float2((float)re, (float)-im);
+      }
+    }
+    if (!upload(p, A, &t.d_A) || !upload(p, AH, &t.d_AH) || !upload(p, S, &t.d_S) || !upload(p, SH, &t.d_SH)) return false;
+  }
+  // ---- last dim: real tables
+  {
+    DimTables& t = p->dim[d - 1];
+    const int k2 = 2 * t.k;
+    p->ldTA = k2; p->ldTAT = t.N; p->ldTS = t.M; p->ldTST = k2;
+    std::vector<float> TA((size_t)t.N * k2), TAT((size_t)k2 * t.N), TS((size_t)k2 * t.M), TST((size_t)t.M * k2);
+    for (int s = 0; s < t.k; ++s) {
+      const int q = t.in_bins[s];
+      for (int n = 0; n < t.N; ++n) {
+        double re, im;
+        unit(q, n, t.N, -1, &re, &im);
+        const float c = (float)(p->s_fwd * re), sn = (float)(p->s_fwd * im);
+        TA[(size_t)n * k2 + 2 * s] = c;      TA[(size_t)n * k2 + 2 * s + 1] = sn;
+        TAT[(size_t)(2 * s) * t.N + n] = c;  TAT[(size_t)(2 * s + 1) * t.N + n] = sn;
+      }
+      // C2R rules: irfft(n=M) reads bins q < M/2+1; DC and (M even) Nyquist count once and ignore Im;
+      // the reference also zeroes Im of the LAST bin of the input-sized spectrum when M is even (:552-559)
+      const bool used = q < t.M / 2 + 1;
+      const bool edge = (q == 0) || (t.M % 2 == 0 && q == t.M / 2);
+      const bool im_dead = edge || (t.M % 2 == 0 && q == t.F - 1);
+      const double cq = edge ? 1.0 : 2.0;
+      for (int n = 0; n < t.M; ++n) {
+        double re = 0.0, im = 0.0;
+        if (used) unit(q, n, t.M, +1, &re, &im);
+        const float c = (float)(p->s_inv * cq * re);
+        const float sn = im_dead ? 0.f : (float)(-p->s_inv * cq * im);
+        TS[(size_t)(2 * s) * t.M + n] = c;   TS[(size_t)(2 * s + 1) * t.M + n] = sn;
+        TST[(size_t)n * k2 + 2 * s] = c;     TST[(size_t)n * k2 + 2 * s + 1] = sn;
+      }
+    }
+    if (!upload(p, TA, &p->d_TA) || !upload(p, TAT, &p->d_TAT) || !upload(p, TS, &p->d_TS) || !upload(p, TST, &p->d_TST)) return false;
+  }
+  // ---- weight offsets of the kept block + DC slot
+  {
+    std::vector<int32_t> woff((size_t)p->n_modes_total);
+    int64_t wstride[SC_MAX_DIMS];
+    int64_t acc = 1;
+    for (int j = d - 1; j >= 0; --j) { wstride[j] = acc; acc *= pr.max_n_modes[j]; }
+    std::vector<int> idx(d, 0);
+    for (int64_t m = 0; m < p->n_modes_total; ++m) {
+      int64_t off = 0;
+      for (int j = 0; j < d; ++j) off += (int64_t)(p->dim[j].w0 + idx[j]) * wstride[j];
+      woff[(size_t)m] = (int32_t)off;
+      for (int j = d - 1; j >= 0; --j) { if (++idx[j] < p->dim[j].k) break; idx[j] = 0; }
+    }
+    if (!upload(p, woff, &p->d_woff)) return false;
+    int64_t dc = 0;
+    for (int j = 0; j < d; ++j) dc = dc * p->dim[j].k + (j == d - 1 ? 0 : p->dim[j].k / 2);
+    p->dc_slot = (int)dc;
+  }
+  return fast_plan_init(p);
+}
+
+static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// largest intermediate of a transform chain over `n_images` images, in complex elements
+static int64_t chain_elems(const Plan* p, int64_t n_images) {
+  const int d = p->d;
+  if (d == 1) return 0;
+  int64_t best = 0;
+  for (int variant = 0; variant < 2; ++variant) {
+    int64_t lead = 1;
+    for (int j = 0; j + 1 < d; ++j) lead *= variant ? p->dim[j].M : p->dim[j].N;
+    const int64_t e = n_images * lead * p->dim[d - 1].k;
+    if (e > best) best = e;
+  }
+  return best;
+}
+
+struct Workspace {
+  float2* buf[2];
+  float2* modes[2];
+};
+
+static bool carve(const Plan* p, int64_t n_images, void* ws, size_t ws_bytes, Workspace* out) {
+  const size_t chain = align256((size_t)chain_elems(p, n_images) * sizeof(float2));
+  const size_t modes = align256((size_t)(n_images * p->n_modes_total) * sizeof(float2));
+  const size_t need = 2 * chain + 2 * modes;
+  if (need > 0 && (ws == nullptr || ws_bytes < need)) { set_error("workspace too small (see sc_workspace_bytes)"); return false; }
+  char* base = static_cast<char*>(ws);
+  out->buf[0] = reinterpret_cast<float2*>(base);
+  out->buf[1] = reinterpret_cast<float2*>(base + chain);
+  out->modes[0] = reinterpret_cast<float2*>(base + 2 * chain);
+  out->modes[1] = reinterpret_cast<float2*>(base + 2 * chain + modes);
+  return true;
+}
+
+// ---- generic transform chains ---------------------------------------------------------------------------
+static bool analyze_generic(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint,
+                            float2* b0, float2* b1, cudaStream_t st) {
+  const int d = p->d;
+  const DimTables& L = p->dim[d - 1];
+  int64_t lead = 1;
+  for (int j = 0; j + 1 < d; ++j) lead *= adjoint ? p->dim[j].M : p->dim[j].N;
+  const int64_t rows = n_images * lead;
+  float2* cur = (d == 1) ? modes_out : b0;
+  float2* nxt = b1;
+  if (!launch_real_table_gemm(images, adjoint ? p->d_TST : p->d_TA, adjoint ? p->ldTST : p->ldTA,
+                              reinterpret_cast<float*>(cur), nullptr, rows, adjoint ? L.M : L.N, 2 * L.k, 1, 1, st))
+    return false;
+  int64_t inner = L.k;
+  for (int j = d - 2; j >= 0; --j) {
+    const DimTables& t = p->dim[j];
+    const int Q = adjoint ? t.M : t.N;
+    lead /= Q;
+    float2* dst = (j == 0) ? modes_out : nxt;
+    if (!launch_complex_table_gemm(adjoint ? t.d_SH : t.d_A, cur, dst, n_images * lead, t.k, Q, (int)inner, st)) return false;
+    inner *= t.k;
+    nxt = cur; cur = dst;
+  }
+  return true;
+}
+
+static bool synthesize_generic(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels,
+                               const float* bias, float* images_out, bool adjoint, float2* b0, float2* b1,
+                               cudaStream_t st) {
+  const int d = p->d;
+  const DimTables& L = p->dim[d - 1];
+  const float2* cur = modes_in;
+  float2* bufs[2] = {b0, b1};
+  int which = 0;
+  int64_t lead = 1;
+  int64_t inner = p->n_modes_total;
+  for (int j = 0; j + 1 < d; ++j) {
+    const DimTables& t = p->dim[j];
+    const int P = adjoint ? t.N : t.M;
+    inner /= t.k;
+    float2* dst = bufs[which];
+    if (!launch_complex_table_gemm(adjoint ? t.d_AH : t.d_S, cur, dst, n_images * lead, P, t.k, (int)inner, st)) return false;
+    lead *= P;
+    cur = dst; which ^= 1;
+  }
+  const int64_t rows = n_images * lead;
+  return launch_real_table_gemm(reinterpret_cast<const float*>(cur), adjoint ? p->d_TAT : p->d_TS,
+                                adjoint ? p->ldTAT : p->ldTS, images_out, bias, rows, 2 * L.k, adjoint ? L.N : L.M,
+                                lead, n_channels > 0 ? n_channels : 1, st);
+}
+
+static bool analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint,
+                    float2* b0, float2* b1, cudaStream_t st) {
+  if (n_images <= 0) return true;
+  if (p->fast_enabled && fast_can_analyze(p, adjoint)) return fast_analyze(p, images, n_images, modes_out, adjoint, st);
+  return analyze_generic(p, images, n_images, modes_out, adjoint, b0, b1, st);
+}
+
+static bool synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
+                       float* images_out, bool adjoint, float2* b0, float2* b1, cudaStream_t st) {
+  if (n_images <= 0) return true;
+  if (p->fast_enabled && fast_can_synthesize(p, adjoint))
+    return fast_synthesize(p, modes_in, n_images, n_channels, bias, images_out, adjoint, st);
+  return synthesize_generic(p, modes_in, n_images, n_channels, bias, images_out, adjoint, b0, b1, st);
+}
+
+static bool contract_fwd(const Plan* p, const float2* xm, const float2* w, float2* ym, int B, int Ci, int Co,
+                         cudaStream_t st) {
+  const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
+  ModeGemmOperand a{xm, (int64_t)Ci * Mt, Mt, nullptr};
+  ModeGemmOperand b{w, (int64_t)Co * Wp, Wp, p->d_woff};
+  ModeGemmOperand o{ym, (int64_t)Co * Mt, Mt, nullptr};
+  return launch_mode_gemm(a, false, b, false, o, B, Co, Ci, Mt, st);
+}
+
+static bool contract_bwd(const Plan* p, const float2* xm, const float2* gm, const float2* w, float2* dxm,
+                         float2* dw, float* dbias, int B, int Ci, int Co, cudaStream_t st) {
+  const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
+  if (dw != nullptr) {
+    if (!p->weight_block_is_whole &&
+        !cuda_ok(cudaMemsetAsync(dw, 0, (size_t)Ci * Co * Wp * sizeof(float2), st), "cudaMemsetAsync(dweight)"))
+      return false;
+    ModeGemmOperand a{xm, Mt, (int64_t)Ci * Mt, nullptr};          // r = i, k = b
+    ModeGemmOperand b{gm, (int64_t)Co * Mt, Mt, nullptr};          // k = b, c = o
+    ModeGemmOperand o{dw, (int64_t)Co * Wp, Wp, p->d_woff};
+    if (!launch_mode_gemm(a, true, b, false, o, Ci, Co, B, Mt, st)) return false;
+  }
+  if (dbias != nullptr &&
+      !launch_bias_grad(gm, dbias, B, Co, Mt, p->dc_slot, (float)(1.0 / p->s_inv), st))
+    return false;
+  if (dxm != nullptr) {
+    ModeGemmOperand a{gm, (int64_t)Co * Mt, Mt, nullptr};          // r = b, k = o
+    ModeGemmOperand b{w, Wp, (int64_t)Co * Wp, p->d_woff};         // k = o, c = i  (conjugated)
+    ModeGemmOperand o{dxm, (int64_t)Ci * Mt, Mt, nullptr};
+    if (!launch_mode_gemm(a, false, b, true, o, B, Ci, Co, Mt, st)) return false;
+  }
+  return true;
+}
+
+}  // namespace sc
+
+using namespace sc;
+
+#define SC_TRY(expr) do { if (!(expr)) return 1; } while (0)
+#define SC_REQUIRE(cond, msg) do { if (!(cond)) { set_error(msg); return 1; } } while (0)
+
+extern "C" {
+
+int sc_plan_create(const sc_problem* problem, sc_plan** plan_out) {
+  SC_REQUIRE(problem != nullptr && plan_out != nullptr, "sc_plan_create: null argument");
+  Plan* p = new (std::nothrow) Plan();
+  SC_REQUIRE(p != nullptr, "sc_plan_create: out of host memory");
+  if (!build_plan(*problem, p)) {
+    for (void* d : p->owned) cudaFree(d);
+    delete p;
+    return 1;
+  }
+  *plan_out = reinterpret_cast<sc_plan*>(p);
+  return 0;
+}
+
+void sc_plan_destroy(sc_plan* plan) {
+  if (plan == nullptr) return;
+  Plan* p = reinterpret_cast<Plan*>(plan);
+  fast_plan_destroy(p);
+  for (void* d : p->owned) cudaFree(d);
+  delete p;
+}
+
+int sc_plan_kept_modes(const sc_plan* plan, int32_t* kept_out) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  if (p == nullptr || kept_out == nullptr) return 0;
+  for (int j = 0; j < p->d; ++j) kept_out[j] = p->dim[j].k;
+  return p->d;
+}
+
+int sc_plan_mode_bins(const sc_plan* plan, int dim, int32_t* in_bins_out, int32_t* weight_rows_out) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && dim >= 0 && dim < p->d, "sc_plan_mode_bins: bad argument");
+  for (int s = 0; s < p->dim[dim].k; ++s) {
+    if (in_bins_out) in_bins_out[s] = p->dim[dim].in_bins[s];
+    if (weight_rows_out) weight_rows_out[s] = p->dim[dim].w0 + s;
+  }
+  return 0;
+}
+
+size_t sc_workspace_bytes(const sc_plan* plan, int64_t n_images) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  if (p == nullptr || n_images <= 0) return 0;
+  return 2 * align256((size_t)chain_elems(p, n_images) * sizeof(float2)) +
+         2 * align256((size_t)(n_images * p->n_modes_total) * sizeof(float2));
+}
+
+int sc_plan_set_fast_path(sc_plan* plan, int enable) {
+  SC_REQUIRE(plan != nullptr, "sc_plan_set_fast_path: null plan");
+  reinterpret_cast<Plan*>(plan)->fast_enabled = enable != 0;
+  return 0;
+}
+
+int sc_plan_uses_fast_path(const sc_plan* plan) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  if (p == nullptr || !p->fast_enabled) return 0;
+  return (fast_can_analyze(p, false) ? 1 : 0) | (fast_can_synthesize(p, false) ? 2 : 0) |
+         (fast_can_analyze(p, true) ? 4 : 0) | (fast_can_synthesize(p, true) ? 8 : 0);
+}
+
+int sc_analyze(const sc_plan* plan, const float* images, int64_t n_images, sc_complex* modes_out, int adjoint,
+               void* workspace, size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && images != nullptr && modes_out != nullptr, "sc_analyze: null argument");
+  Workspace w{};
+  SC_TRY(carve(p, n_images, workspace, workspace_bytes, &w));
+  SC_TRY(analyze(p, images, n_images, reinterpret_cast<float2*>(modes_out), adjoint != 0, w.buf[0], w.buf[1],
+                 static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_synthesize(const sc_plan* plan, const sc_complex* modes_in, int64_t n_images, int32_t n_channels,
+                  const float* bias, float* images_out, int adjoint, void* workspace, size_t workspace_bytes,
+                  sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && modes_in != nullptr && images_out != nullptr, "sc_synthesize: null argument");
+  SC_REQUIRE(!(adjoint && bias != nullptr), "sc_synthesize: bias is only valid for the forward synthesis");
+  SC_REQUIRE(bias == nullptr || n_channels > 0, "sc_synthesize: n_channels must be > 0 with a bias");
+  Workspace w{};
+  SC_TRY(carve(p, n_images, workspace, workspace_bytes, &w));
+  SC_TRY(synthesize(p, reinterpret_cast<const float2*>(modes_in), n_images, n_channels, bias, images_out,
+                    adjoint != 0, w.buf[0], w.buf[1], static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_contract_dense(const sc_plan* plan, const sc_complex* xm, const sc_complex* weight, sc_complex* ym,
+                      int32_t batch, int32_t in_channels, int32_t out_channels, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && xm != nullptr && weight != nullptr && ym != nullptr, "sc_contract_dense: null argument");
+  SC_TRY(contract_fwd(p, reinterpret_cast<const float2*>(xm), reinterpret_cast<const float2*>(weight),
+                      reinterpret_cast<float2*>(ym), batch, in_channels, out_channels, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_contract_dense_backward(const sc_plan* plan, const sc_complex* xm, const sc_complex* gm,
+                               const sc_complex* weight, sc_complex* dxm, sc_complex* dweight, float* dbias,
+                               int32_t batch, int32_t in_channels, int32_t out_channels, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && gm != nullptr, "sc_contract_dense_backward: null argument");
+  SC_REQUIRE(dweight == nullptr || xm != nullptr, "sc_contract_dense_backward: dweight needs xm");
+  SC_REQUIRE(dxm == nullptr || weight != nullptr, "sc_contract_dense_backward: dxm needs weight");
+  SC_TRY(contract_bwd(p, reinterpret_cast<const float2*>(xm), reinterpret_cast<const float2*>(gm),
+                      reinterpret_cast<const float2*>(weight), reinterpret_cast<float2*>(dxm),
+                      reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels,
+                      static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_bias_grad(const sc_plan* plan, const sc_complex* gm, float* dbias, int32_t batch, int32_t out_channels,
+                 sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && gm != nullptr && dbias != nullptr, "sc_bias_grad: null argument");
+  SC_TRY(launch_bias_grad(reinterpret_cast<const float2*>(gm), dbias, batch, out_channels, p->n_modes_total,
+                          p->dc_slot, (float)(1.0 / p->s_inv), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weight, const float* bias, float* y,
+                     sc_complex* xm_saved, int32_t batch, int32_t in_channels, int32_t out_channels,
+                     void* workspace, size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && x != nullptr && weight != nullptr && y != nullptr && xm_saved != nullptr,
+             "sc_forward_dense: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)batch * (in_channels > out_channels ? in_channels : out_channels);
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, workspace_bytes, &w));
+  float2* xm = reinterpret_cast<float2*>(xm_saved);
+  float2* ym = w.modes[0];
+  SC_TRY(analyze(p, x, (int64_t)batch * in_channels, xm, false, w.buf[0], w.buf[1], st));
+  SC_TRY(contract_fwd(p, xm, reinterpret_cast<const float2*>(weight), ym, batch, in_channels, out_channels, st));
+  SC_TRY(synthesize(p, ym, (int64_t)batch * out_channels, out_channels, bias, y, false, w.buf[0], w.buf[1], st));
+  return 0;
+}
+
+int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* weight, const sc_complex* xm_saved,
+                      float* dx, sc_complex* dweight, float* dbias, int32_t batch, int32_t in_channels,
+                      int32_t out_channels, void* workspace, size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && gy != nullptr && weight != nullptr, "sc_backward_dense: null argument");
+  SC_REQUIRE(dweight == nullptr || xm_saved != nullptr, "sc_backward_dense: dweight needs the saved modes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)batch * (in_channels > out_channels ? in_channels : out_channels);
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, workspace_bytes, &w));
+  float2* gm = w.modes[0];
+  float2* dxm = dx != nullptr ? w.modes[1] : nullptr;
+  SC_TRY(analyze(p, gy, (int64_t)batch * out_channels, gm, true, w.buf[0], w.buf[1], st));
+  SC_TRY(contract_bwd(p, reinterpret_cast<const float2*>(xm_saved), gm, reinterpret_cast<const float2*>(weight), dxm,
+                      reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels, st));
+  if (dx != nullptr)
+    SC_TRY(synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+  return 0;
+}
+
+const char* sc_last_error(void) { return t_error.c_str(); }
+uint64_t sc_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* sc_build_info(void) {
+  return "libspectral_conv_b200 sm_100a nvcc " SC_STR(__CUDACC_VER_MAJOR__) "." SC_STR(__CUDACC_VER_MINOR__);
+}
+
+}  // extern "C"

@@ -1,0 +1,316 @@
+// Generic (any grid size, any mode count, 1..4-D) SIMT fp32 kernels of the SpectralConv path.
+//
+// The truncated transforms are expressed as products with small precomputed twiddle tables, so odd grids,
+// odd mode counts, resampled outputs and the Hermitian rules of the reference's C2R step
+// (spectral_convolution.py:552-559) are all properties of the table, not of the kernel.  The tcgen05/TMA
+// path (sc_fast_*.cu) covers the large power-of-two shapes; this file is the path every other shape takes
+// and the cross-check for the fast one.  Compiled for sm_100a only.
+#include "sc_plan.h"
+
+namespace sc {
+
+// =====================================================================================================
+// 1. real table GEMM:   C[R x Nc] = A[R x Kc] * T[Kc x ldt]   (+ per-channel bias)
+//    analysis of the last dim  (Kc = N_d,  Nc = 2 k_d)   and   synthesis of the last dim (Kc = 2 k_d, Nc = M_d)
+// =====================================================================================================
+constexpr int RG_BM = 128;      // rows per CTA
+constexpr int RG_BK = 32;       // k-chunk
+constexpr int RG_THREADS = 256; // 8 column-groups x 32 row-groups, 4 rows x TN cols per thread
+
+template <int TN>
+__device__ __forceinline__ void rg_step(float (&acc)[4][TN], const float (&As)[RG_BM][RG_BK + 1],
+                                        const float (&Ts)[RG_BK][8 * TN], int ty, int tx, int k) {
+  float a[4], t[TN];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) a[m] = As[ty * 4 + m][k];
+#pragma unroll
+  for (int n = 0; n < TN; ++n) t[n] = Ts[k][tx * TN + n];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) acc[m][n] = fmaf(a[m], t[n], acc[m][n]);
+}
+
+template <int TN>
+__global__ void __launch_bounds__(RG_THREADS)
+k_real_table_gemm(const float* __restrict__ A, const float* __restrict__ T, int ldt, float* __restrict__ C,
+                  const float* __restrict__ bias, long long R, int Kc, int Nc, long long rows_per_image,
+                  int n_channels) {
+  constexpr int BN = 8 * TN;
+  __shared__ float As[RG_BM][RG_BK + 1];
+  __shared__ float Ts[RG_BK][BN];
+  const int tx = threadIdx.x & 7;
+  const int ty = threadIdx.x >> 3;
+  const long long row0 = (long long)blockIdx.x * RG_BM;
+  const int col0 = blockIdx.y * BN;
+
+  float acc[4][TN];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) acc[m][n] = 0.f;
+
+  for (int k0 = 0; k0 < Kc; k0 += RG_BK) {
+    // A tile: a warp reads 32 consecutive floats of one row (128 B, coalesced)
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < RG_BM * RG_BK; idx += RG_THREADS) {
+      const int r = idx / RG_BK, k = idx % RG_BK;
+      const long long gr = row0 + r;
+      float v = 0.f;
+      if (gr < R && k0 + k < Kc) v = __ldg(A + gr * (long long)Kc + k0 + k);
+      As[r][k] = v;
+    }
+    for (int idx = threadIdx.x; idx < RG_BK * BN; idx += RG_THREADS) {
+      const int k = idx / BN, c = idx % BN;
+      float v = 0.f;
+      if (k0 + k < Kc && col0 + c < ldt) v = __ldg(T + (long long)(k0 + k) * ldt + col0 + c);
+      Ts[k][c] = v;
+    }
+    __syncthreads();
+    if (k0 + RG_BK <= Kc) {
+#pragma unroll
+      for (int k = 0; k < RG_BK; ++k) rg_step<TN>(acc, As, Ts, ty, tx, k);
+    } else {   // ragged tail of the contraction (e.g. Kc = 2 k_d = 34): do not multiply the zero padding
+      const int kmax = Kc - k0;
+#pragma unroll 2
+      for (int k = 0; k < kmax; ++k) rg_step<TN>(acc, As, Ts, ty, tx, k);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const long long gr = row0 + ty * 4 + m;
+    if (gr >= R) continue;
+    float b = 0.f;
+    if (bias != nullptr) b = __ldg(bias + (gr / rows_per_image) % n_channels);
+#pragma unroll
+    for (int n = 0; n < TN; ++n) {
+      const int gc = col0 + tx * TN + n;
+      if (gc < Nc) C[gr * (long long)Nc + gc] = acc[m][n] + b;
+    }
+  }
+}
+
+template <int TN>
+static void launch_rg(const float* A, const float* T, int ldt, float* C, const float* bias, int64_t R, int Kc,
+                      int Nc, int64_t rows_per_image, int n_channels, int n_tiles, cudaStream_t st) {
+  dim3 grid((unsigned)((R + RG_BM - 1) / RG_BM), (unsigned)n_tiles);
+  k_real_table_gemm<TN><<<grid, RG_THREADS, 0, st>>>(A, T, ldt, C, bias, (long long)R, Kc, Nc,
+                                                      (long long)rows_per_image, n_channels);
+}
+
+bool launch_real_table_gemm(const float* A, const float* T, int ldt, float* C, const float* bias, int64_t R,
+                            int Kc, int Nc, int64_t rows_per_image, int n_channels, cudaStream_t st) {
+  if (R <= 0 || Nc <= 0) return true;
+  // split Nc into equal column tiles of at most 96 columns, 8 column-groups of TN each
+  const int n_tiles = (Nc + 95) / 96;
+  const int per_tile = (Nc + n_tiles - 1) / n_tiles;
+  const int tn = (per_tile + 7) / 8;
+#define SC_RG_CASE(N) \
+  case N: launch_rg<N>(A, T, ldt, C, bias, R, Kc, Nc, rows_per_image, n_channels, (Nc + 8 * N - 1) / (8 * N), st); break;
+  switch (tn) {
+    SC_RG_CASE(1) SC_RG_CASE(2) SC_RG_CASE(3) SC_RG_CASE(4) SC_RG_CASE(5) SC_RG_CASE(6)
+    SC_RG_CASE(7) SC_RG_CASE(8) SC_RG_CASE(9) SC_RG_CASE(10) SC_RG_CASE(11) SC_RG_CASE(12)
+    default: set_error("real_table_gemm: internal tile selection failed"); return false;
+  }
+#undef SC_RG_CASE
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_real_table_gemm launch");
+}
+
+// =====================================================================================================
+// 2. complex table GEMM over a middle axis:   out[o, p, i] = sum_q T[p, q] * in[o, q, i]
+//    (leading-dim analysis: Q = N_j, P = k_j;   leading-dim synthesis: Q = k_j, P = M_j)
+//    lanes run over the flattened (o, i) columns, each thread owns CT_TP output rows of one column.
+// =====================================================================================================
+constexpr int CT_COLS = 128;   // columns per CTA (threadIdx.x)
+constexpr int CT_TP = 16;      // output rows per thread
+constexpr int CT_PG = 2;       // row groups per CTA (threadIdx.y)
+constexpr int CT_QC = 32;      // q-chunk held in shared memory
+
+__global__ void __launch_bounds__(CT_COLS* CT_PG)
+k_complex_table_gemm(const float2* __restrict__ T, const float2* __restrict__ in, float2* __restrict__ out,
+                     long long O, int P, int Q, int I) {
+  __shared__ float2 s_in[CT_QC][CT_COLS];
+  __shared__ __align__(16) float2 s_T[CT_QC][CT_PG * CT_TP];
+  const long long ncols = O * (long long)I;
+  const long long col = (long long)blockIdx.x * CT_COLS + threadIdx.x;
+  const bool col_ok = col < ncols;
+  const long long o = col_ok ? col / I : 0;
+  const int i = col_ok ? (int)(col - o * I) : 0;
+  const int p_base = blockIdx.y * (CT_PG * CT_TP);
+  const int tid = threadIdx.y * CT_COLS + threadIdx.x;
+
+  float2 acc[CT_TP];
+#pragma unroll
+  for (int t = 0; t < CT_TP; ++t) acc[t] = make_float2(0.f, 0.f);
+
+  const float2* in_col = in + (o * Q) * (long long)I + i;
+  for (int q0 = 0; q0 < Q; q0 += CT_QC) {
+    for (int qq = threadIdx.y; qq < CT_QC; qq += CT_PG) {
+      float2 v = make_float2(0.f, 0.f);
+      if (col_ok && q0 + qq < Q) v = __ldg(in_col + (long long)(q0 + qq) * I);
+      s_in[qq][threadIdx.x] = v;
+    }
+    for (int idx = tid; idx < CT_QC * CT_PG * CT_TP; idx += CT_COLS * CT_PG) {
+      const int pp = idx / CT_QC, qq = idx % CT_QC;   // consecutive threads walk q: contiguous in T
+      float2 v = make_float2(0.f, 0.f);
+      if (p_base + pp < P && q0 + qq < Q) v = __ldg(T + (long long)(p_base + pp) * Q + q0 + qq);
+      s_T[qq][pp] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int qq = 0; qq < CT_QC; ++qq) {
+      const float2 v = s_in[qq][threadIdx.x];
+      const float4* trow = reinterpret_cast<const float4*>(&s_T[qq][threadIdx.y * CT_TP]);
+#pragma unroll
+      for (int t = 0; t < CT_TP / 2; ++t) {
+        const float4 w = trow[t];   // two twiddles, warp-uniform address -> broadcast
+        acc[2 * t].x = fmaf(w.x, v.x, acc[2 * t].x);
+        acc[2 * t].x = fmaf(-w.y, v.y, acc[2 * t].x);
+        acc[2 * t].y = fmaf(w.x, v.y, acc[2 * t].y);
+        acc[2 * t].y = fmaf(w.y, v.x, acc[2 * t].y);
+        acc[2 * t + 1].x = fmaf(w.z, v.x, acc[2 * t + 1].x);
+        acc[2 * t + 1].x = fmaf(-w.w, v.y, acc[2 * t + 1].x);
+        acc[2 * t + 1].y = fmaf(w.z, v.y, acc[2 * t + 1].y);
+        acc[2 * t + 1].y = fmaf(w.w, v.x, acc[2 * t + 1].y);
+      }
+    }
+    __syncthreads();
+  }
+  if (!col_ok) return;
+  float2* out_col = out + (o * P) * (long long)I + i;
+#pragma unroll
+  for (int t = 0; t < CT_TP; ++t) {
+    const int p = p_base + threadIdx.y * CT_TP + t;
+    if (p < P) out_col[(long long)p * I] = acc[t];
+  }
+}
+
+bool launch_complex_table_gemm(const float2* T, const float2* in, float2* out, int64_t O, int P, int Q, int I,
+                               cudaStream_t st) {
+  const int64_t ncols = O * (int64_t)I;
+  if (ncols <= 0 || P <= 0) return true;
+  dim3 grid((unsigned)((ncols + CT_COLS - 1) / CT_COLS), (unsigned)((P + CT_PG * CT_TP - 1) / (CT_PG * CT_TP)));
+  dim3 block(CT_COLS, CT_PG);
+  k_complex_table_gemm<<<grid, block, 0, st>>>(T, in, out, (long long)O, P, Q, I);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_complex_table_gemm launch");
+}
+
+// =====================================================================================================
+// 3. mode-wise complex GEMM:  out[r, c, m] = sum_k opA(A[r, k, m]) * opB(B[k, c, m])
+//    forward  : r=b c=o k=i   A = xm            B = weight
+//    dxm      : r=b c=i k=o   A = gm            B = conj(weight) (strides swapped)
+//    dweight  : r=i c=o k=b   A = conj(xm)      B = gm
+//    lanes run over modes (the contiguous axis of every operand); a warp owns a TR x TC tile.
+// =====================================================================================================
+constexpr int MG_TR = 4;
+constexpr int MG_TC = 8;
+constexpr int MG_WARPS = 8;
+
+struct MgOp {
+  const float2* ptr;
+  long long s_outer, s_inner;
+  const int* off;
+};
+
+template <bool CONJ_A, bool CONJ_B>
+__global__ void __launch_bounds__(32 * MG_WARPS)
+k_mode_gemm(MgOp A, MgOp B, float2* __restrict__ outp, long long so_r, long long so_c, const int* __restrict__ out_off,
+            int nR, int nC, int nK, long long nModes) {
+  const long long m = (long long)blockIdx.x * 32 + threadIdx.x;
+  const int tiles_r = (nR + MG_TR - 1) / MG_TR;
+  const int tiles_c = (nC + MG_TC - 1) / MG_TC;
+  const int tile = blockIdx.y * MG_WARPS + threadIdx.y;   // r-tiles fastest: warps of a CTA share the B tile
+  if (tile >= tiles_r * tiles_c || m >= nModes) return;
+  const int r0 = (tile % tiles_r) * MG_TR;
+  const int c0 = (tile / tiles_r) * MG_TC;
+  const long long ma = A.off ? (long long)__ldg(A.off + m) : m;
+  const long long mb = B.off ? (long long)__ldg(B.off + m) : m;
+  const long long mo = out_off ? (long long)__ldg(out_off + m) : m;
+
+  float2 acc[MG_TR][MG_TC];
+#pragma unroll
+  for (int r = 0; r < MG_TR; ++r)
+#pragma unroll
+    for (int c = 0; c < MG_TC; ++c) acc[r][c] = make_float2(0.f, 0.f);
+
+  const float2* pa = A.ptr + ma;
+  const float2* pb = B.ptr + mb;
+#pragma unroll 2
+  for (int k = 0; k < nK; ++k) {
+    float2 a[MG_TR], b[MG_TC];
+#pragma unroll
+    for (int r = 0; r < MG_TR; ++r) {
+      a[r] = (r0 + r < nR) ? __ldg(pa + (long long)(r0 + r) * A.s_outer + (long long)k * A.s_inner)
+                           : make_float2(0.f, 0.f);
+      if (CONJ_A) a[r].y = -a[r].y;
+    }
+#pragma unroll
+    for (int c = 0; c < MG_TC; ++c) {
+      b[c] = (c0 + c < nC) ? __ldg(pb + (long long)k * B.s_outer + (long long)(c0 + c) * B.s_inner)
+                           : make_float2(0.f, 0.f);
+      if (CONJ_B) b[c].y = -b[c].y;
+    }
+#pragma unroll
+    for (int r = 0; r < MG_TR; ++r)
+#pragma unroll
+      for (int c = 0; c < MG_TC; ++c) {
+        acc[r][c].x = fmaf(a[r].x, b[c].x, acc[r][c].x);
+        acc[r][c].x = fmaf(-a[r].y, b[c].y, acc[r][c].x);
+        acc[r][c].y = fmaf(a[r].x, b[c].y, acc[r][c].y);
+        acc[r][c].y = fmaf(a[r].y, b[c].x, acc[r][c].y);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < MG_TR; ++r)
+#pragma unroll
+    for (int c = 0; c < MG_TC; ++c)
+      if (r0 + r < nR && c0 + c < nC) outp[mo + (long long)(r0 + r) * so_r + (long long)(c0 + c) * so_c] = acc[r][c];
+}
+
+bool launch_mode_gemm(ModeGemmOperand A, bool conjA, ModeGemmOperand B, bool conjB, ModeGemmOperand Out, int nR,
+                      int nC, int nK, int64_t nModes, cudaStream_t st) {
+  if (nR <= 0 || nC <= 0 || nModes <= 0) return true;
+  const int tiles = ((nR + MG_TR - 1) / MG_TR) * ((nC + MG_TC - 1) / MG_TC);
+  dim3 grid((unsigned)((nModes + 31) / 32), (unsigned)((tiles + MG_WARPS - 1) / MG_WARPS));
+  dim3 block(32, MG_WARPS);
+  MgOp a{(const float2*)A.ptr, (long long)A.s_outer, (long long)A.s_inner, A.mode_off};
+  MgOp b{(const float2*)B.ptr, (long long)B.s_outer, (long long)B.s_inner, B.mode_off};
+  float2* o = (float2*)Out.ptr;
+  if (conjA && !conjB)
+    k_mode_gemm<true, false><<<grid, block, 0, st>>>(a, b, o, Out.s_outer, Out.s_inner, Out.mode_off, nR, nC, nK, nModes);
+  else if (!conjA && conjB)
+    k_mode_gemm<false, true><<<grid, block, 0, st>>>(a, b, o, Out.s_outer, Out.s_inner, Out.mode_off, nR, nC, nK, nModes);
+  else if (!conjA && !conjB)
+    k_mode_gemm<false, false><<<grid, block, 0, st>>>(a, b, o, Out.s_outer, Out.s_inner, Out.mode_off, nR, nC, nK, nModes);
+  else
+    k_mode_gemm<true, true><<<grid, block, 0, st>>>(a, b, o, Out.s_outer, Out.s_inner, Out.mode_off, nR, nC, nK, nModes);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_mode_gemm launch");
+}
+
+// =====================================================================================================
+// 4. bias gradient from the DC slot of gm:  dbias[o] = inv_scale * sum_b Re(gm[b, o, dc])
+// =====================================================================================================
+__global__ void k_bias_grad(const float2* __restrict__ gm, float* __restrict__ dbias, int batch, int out_channels,
+                            long long n_modes, int dc_slot, float inv_scale) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= out_channels) return;
+  float s = 0.f;
+  for (int b = 0; b < batch; ++b) s += gm[((long long)b * out_channels + o) * n_modes + dc_slot].x;
+  dbias[o] = s * inv_scale;
+}
+
+bool launch_bias_grad(const float2* gm, float* dbias, int batch, int out_channels, int64_t n_modes, int dc_slot,
+                      float inv_scale, cudaStream_t st) {
+  if (out_channels <= 0) return true;
+  k_bias_grad<<<(out_channels + 127) / 128, 128, 0, st>>>(gm, dbias, batch, out_channels, (long long)n_modes,
+                                                          dc_slot, inv_scale);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_bias_grad launch");
+}
+
+}  // namespace sc

@@ -1,0 +1,102 @@
+"""CPU tests of the boundary: the shared object loads, exports every symbol the header declares, and the
+host-side module mirrors the reference's constructor / attribute contract. No kernel is launched here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import neuraloperator_b200 as nb
+from neuraloperator_b200 import _lib
+from neuraloperator_b200.build import LIB_PATH, build_library
+from neuraloperator_b200.factorized import FactorizedWeight, tucker_ranks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build_library()
+    return _lib.load()
+
+
+def test_header_symbols_are_exported(lib):
+    header = open(os.path.join(ROOT, "include", "spectral_conv_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sc_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 15
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    raw = ctypes.CDLL(LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} not exported"
+    assert b"sm_100a" in lib.sc_build_info()
+
+
+def test_problem_struct_matches_header():
+    # int32 ndim + 4 arrays of SC_MAX_DIMS int32 + int32 fft_norm
+    assert ctypes.sizeof(_lib.ScProblem) == 4 * (1 + 4 * _lib.SC_MAX_DIMS + 1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_plan_create_fails_loudly_without_gpu(lib):
+    prob = _lib.ScProblem()
+    prob.ndim = 1
+    prob.grid[0] = prob.out_grid[0] = 16
+    prob.n_modes[0] = prob.max_n_modes[0] = 5
+    handle = ctypes.c_void_p()
+    assert lib.sc_plan_create(ctypes.byref(prob), ctypes.byref(handle)) != 0
+    assert lib.sc_last_error()
+
+
+def test_module_contract_dense():
+    conv = nb.SpectralConv(4, 6, (8, 6))
+    assert conv.n_modes == [8, 4] and conv.max_n_modes == [8, 4] and conv.order == 2
+    assert tuple(conv.weight.shape) == (4, 6, 8, 4) and conv.weight.tensor.dtype == torch.complex64
+    assert tuple(conv.bias.shape) == (6, 1, 1)
+    assert sorted(conv.state_dict().keys()) == ["bias", "weight.tensor"]
+    conv.n_modes = (6, 4)           # mutable, halves the last dim (reference :404-415)
+    assert conv.n_modes == [6, 3]
+    x = torch.randn(2, 4, 16, 16)
+    assert conv.transform(x) is x
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        conv(x)
+    with pytest.raises(NotImplementedError):
+        nb.SpectralConv(4, 4, (8, 8), complex_data=True)
+    with pytest.raises(NotImplementedError):
+        nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half")
+    with pytest.raises(ValueError):
+        nb.SpectralConv(4, 4, (8, 8), implementation="nope")
+
+
+def test_module_contract_factorized():
+    conv = nb.SpectralConv(6, 5, (8, 6), factorization="tucker", rank=[4, 3, 5, 3], implementation="factorized")
+    keys = sorted(conv.state_dict().keys())
+    assert keys == ["bias", "weight.core"] + [f"weight.factors.factor_{i}" for i in range(4)]
+    assert conv.weight.name.lower().endswith("tucker")
+    assert tuple(conv.weight.to_tensor().shape) == (6, 5, 8, 4)
+    sub = conv.weight[:, :, 1:5, :3]
+    assert tuple(sub.shape) == (6, 5, 4, 3)
+    assert torch.allclose(sub.to_tensor(), conv.weight.to_tensor()[:, :, 1:5, :3], atol=1e-6)
+    cp = nb.SpectralConv(6, 5, (8, 6), factorization="cp", rank=7)
+    assert sorted(cp.state_dict().keys()) == ["bias"] + [f"weight.factors.factor_{i}" for i in range(4)] + ["weight.weights"]
+    tt = nb.SpectralConv(6, 5, (8, 6), factorization="tt", rank=[1, 3, 4, 3, 1])
+    assert tuple(tt.weight.to_tensor().shape) == (6, 5, 8, 4)
+    assert torch.is_complex(conv.weight) and torch.is_complex(cp.weight)
+
+
+def test_tucker_rank_rule():
+    # (64,64,32,17) @ 0.1 -> (36,36,18,10)
+    assert tucker_ranks((64, 64, 32, 17), 0.1) == [36, 36, 18, 10]
+    w = FactorizedWeight.new((4, 4, 6, 4), rank=0.5, factorization="Tucker")
+    assert w.name.lower().endswith("tucker")
+
+
+def test_factorized_reconstruction_matches_oracle_layout():
+    from oracle import spectral_conv_oracle as O
+    torch.manual_seed(0)
+    conv = nb.SpectralConv(6, 5, (8, 6), factorization="tucker", rank=[4, 3, 5, 3])
+    w = O.Weight("tucker", core=conv.weight.core.detach(), factors=[f.detach() for f in conv.weight.factors])
+    assert torch.allclose(w.to_dense(), conv.weight.to_tensor().detach(), atol=1e-6)
+    xm = torch.randn(2, 6, 8, 4, dtype=torch.cfloat)
+    assert torch.allclose(w.contract(xm), O.contract_dense(xm, w.to_dense()), atol=1e-5)

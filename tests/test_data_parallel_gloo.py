@@ -1,0 +1,46 @@
+"""world_size-2 gloo test of the one collective on the path: the gradient all-reduce (CPU tensors)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from neuraloperator_b200.data_parallel import GradientAllReducer
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)
+    w = torch.nn.Parameter(torch.zeros(3, 4, 5, dtype=torch.cfloat))
+    b = torch.nn.Parameter(torch.zeros(4, 1, 1))
+    w.grad = torch.randn(3, 4, 5, dtype=torch.cfloat)
+    b.grad = torch.randn(4, 1, 1)
+    local = (w.grad.clone(), b.grad.clone())
+    red = GradientAllReducer([w, b])
+    red.start()
+    red.finish()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    mean_w = sum(g[0] for g in gathered) / world
+    mean_b = sum(g[1] for g in gathered) / world
+    ok = torch.allclose(w.grad, mean_w, atol=1e-6) and torch.allclose(b.grad, mean_b, atol=1e-6)
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world2():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        assert out[0] and out[1]
