@@ -164,16 +164,18 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
 
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-// largest intermediate of a transform chain over `n_images` images, in complex elements
+// largest intermediate of a transform chain over `n_images` images, in complex elements.  A chain state is
+// "dims < s still on the grid (N for the forward pair, M for the adjoint pair), dims >= s already in mode space".
 static int64_t chain_elems(const Plan* p, int64_t n_images) {
   const int d = p->d;
-  if (d == 1) return 0;
   int64_t best = 0;
   for (int variant = 0; variant < 2; ++variant) {
-    int64_t lead = 1;
-    for (int j = 0; j + 1 < d; ++j) lead *= variant ? p->dim[j].M : p->dim[j].N;
-    const int64_t e = n_images * lead * p->dim[d - 1].k;
-    if (e > best) best = e;
+    for (int s = 1; s < d; ++s) {
+      int64_t e = n_images;
+      for (int j = 0; j < s; ++j) e *= variant ? p->dim[j].M : p->dim[j].N;
+      for (int j = s; j < d; ++j) e *= p->dim[j].k;
+      if (e > best) best = e;
+    }
   }
   return best;
 }

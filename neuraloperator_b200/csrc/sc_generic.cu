@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(CT_COLS* CT_PG)
 k_complex_table_gemm(const float2* __restrict__ T, const float2* __restrict__ in, float2* __restrict__ out,
                      long long O, int P, int Q, int I) {
   __shared__ float2 s_in[CT_QC][CT_COLS];
-  __shared__ __align__(16) float2 s_T[CT_QC][CT_PG * CT_TP];
+  __shared__ __align__(16) float2 s_T[CT_QC][CT_PG * CT_TP + 2];   // +2: keeps rows 16-B aligned, spreads banks
   const long long ncols = O * (long long)I;
   const long long col = (long long)blockIdx.x * CT_COLS + threadIdx.x;
   const bool col_ok = col < ncols;
@@ -217,7 +217,7 @@ struct MgOp {
 };
 
 template <bool CONJ_A, bool CONJ_B>
-__global__ void __launch_bounds__(32 * MG_WARPS)
+__global__ void __launch_bounds__(32 * MG_WARPS, 2)
 k_mode_gemm(MgOp A, MgOp B, float2* __restrict__ outp, long long so_r, long long so_c, const int* __restrict__ out_off,
             int nR, int nC, int nK, long long nModes) {
   const long long m = (long long)blockIdx.x * 32 + threadIdx.x;
