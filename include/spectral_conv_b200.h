@@ -105,6 +105,9 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
 const char* sc_last_error(void);          /* thread-local description of the last failure */
 uint64_t    sc_kernel_launch_count(void); /* kernels this library has launched so far (process-wide) */
 const char* sc_build_info(void);          /* "sm_100a nvcc <ver> ..." */
+/* tcgen05 bring-up check: d[128 x n] = bf16(a[128 x k]) * bf16(b[n x k])^T accumulated in FP32 in TMEM, through the
+ * same operand staging / descriptors / TMEM read-back the fused transform kernels use (device pointers, fp32). */
+int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream);
 
 #ifdef __cplusplus
 }

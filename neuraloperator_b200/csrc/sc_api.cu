@@ -91,7 +91,9 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
   // ---- leading dims: complex tables
   for (int j = 0; j + 1 < d; ++j) {
     DimTables& t = p->dim[j];
-    std::vector<float2> A((size_t)t.k * t.N), AH((size_t)t.N * t.k), S((size_t)t.M * t.k), SH((size_t)t.k * t.M);
+    std::vector<float2>&A = t.h_A, &AH = t.h_AH, &S = t.h_S, &SH = t.h_SH;
+    A.assign((size_t)t.k * t.N, make_float2(0.f, 0.f));  AH.assign((size_t)t.N * t.k, make_float2(0.f, 0.f));
+    S.assign((size_t)t.M * t.k, make_float2(0.f, 0.f));  SH.assign((size_t)t.k * t.M, make_float2(0.f, 0.f));
     for (int s = 0; s < t.k; ++s) {
       const int b = t.in_bins[s];
       for (int n = 0; n < t.N; ++n) {
@@ -114,7 +116,9 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
     DimTables& t = p->dim[d - 1];
     const int k2 = 2 * t.k;
     p->ldTA = k2; p->ldTAT = t.N; p->ldTS = t.M; p->ldTST = k2;
-    std::vector<float> TA((size_t)t.N * k2), TAT((size_t)k2 * t.N), TS((size_t)k2 * t.M), TST((size_t)t.M * k2);
+    std::vector<float>&TA = p->h_TA, &TAT = p->h_TAT, &TS = p->h_TS, &TST = p->h_TST;
+    TA.assign((size_t)t.N * k2, 0.f);  TAT.assign((size_t)k2 * t.N, 0.f);
+    TS.assign((size_t)k2 * t.M, 0.f);  TST.assign((size_t)t.M * k2, 0.f);
     for (int s = 0; s < t.k; ++s) {
       const int q = t.in_bins[s];
       for (int n = 0; n < t.N; ++n) {
@@ -456,6 +460,12 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
                       reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels, st));
   if (dx != nullptr)
     SC_TRY(synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+  return 0;
+}
+
+int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream) {
+  SC_REQUIRE(a != nullptr && b != nullptr && d != nullptr, "sc_selftest_umma: null argument");
+  SC_TRY(umma_selftest(a, b, d, n, k, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -1,19 +1,472 @@
-// tcgen05 / TMA fused transform path.  (Being brought up: until the kernels land every shape reports
-// "not supported" and the generic SIMT kernels in sc_generic.cu run instead.)
+// tcgen05 fused transform path (sm_100a).  See DESIGN.md "fast path" for the derivation.
+//
+// Both transforms are chains of two small GEMMs per 128-row tile, executed on the 5th-generation tensor cores
+// with BF16 operands and FP32 accumulation in TMEM.  FP32 accuracy is kept by splitting every operand into
+// two bf16 terms (x = x_hi + x_lo, table = T1 + T2) and accumulating the three significant products
+// x_hi*T1 + x_lo*T1 + x_hi*T2 ("bf16x3", relative error ~1e-5).
+#include <cstring>
+#include <vector>
+
 #include "sc_fast.h"
+#include "sc_umma.cuh"
 
 namespace sc {
 
-bool fast_plan_init(Plan*) { return true; }
-void fast_plan_destroy(Plan*) {}
-bool fast_can_analyze(const Plan*, bool) { return false; }
-bool fast_can_synthesize(const Plan*, bool) { return false; }
-bool fast_analyze(const Plan*, const float*, int64_t, float2*, bool, cudaStream_t) {
-  set_error("fast path not available for this shape");
-  return false;
+using namespace umma;
+
+// =====================================================================================================
+// self-test: D[128 x N] = A[128 x K] * B[N x K]^T with bf16-rounded operands -- exercises the swizzled operand
+// stores, the shared-memory / instruction descriptors, TMEM allocation, tcgen05.mma, commit and tcgen05.ld
+// exactly the way the transform kernels use them.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__ A, const float* __restrict__ B,
+                                                        float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 128 * K * 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_base, 128);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+  for (int idx = tid; idx < 128 * K; idx += 128) {
+    const int r = idx / K, k = idx % K;
+    *reinterpret_cast<__nv_bfloat16*>(sA + sw128_offset(r, k, 128)) = __float2bfloat16_rn(A[idx]);
+  }
+  for (int idx = tid; idx < N * K; idx += 128) {
+    const int r = idx / K, k = idx % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + sw128_offset(r, k, N)) = __float2bfloat16_rn(B[idx]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16(128, N);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const int slab = ks >> 2, kk = ks & 3;
+      const uint64_t da = smem_desc_sw128(smem_u32(sA) + slab * 128 * 128 + kk * 32);
+      const uint64_t db = smem_desc_sw128(smem_u32(sB) + slab * N * 128 + kk * 32);
+      mma_bf16_ss(tmem, da, db, idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  for (int c = 0; c < N; c += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)(warp * 32 + lane) * N + c + i] = v[i];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
 }
+
+bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaStream_t st) {
+  if (N < 16 || N > 128 || N % 16 != 0 || K < 64 || K > 256 || K % 64 != 0) {
+    set_error("umma selftest: need N in 16..128 step 16 and K in 64..256 step 64");
+    return false;
+  }
+  const size_t smem = (size_t)(128 + N) * K * 2 + 1024;
+  if (!cuda_ok(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "cudaFuncSetAttribute(selftest)"))
+    return false;
+  k_umma_selftest<<<1, 128, smem, st>>>(A, B, D, N, K);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_umma_selftest launch");
+}
+
+// =====================================================================================================
+// fused analysis:  tile of 128 image rows  ->  kept modes of the G = 128/H images the tile holds
+//
+//   stage 1 (last dim)    D1[h, j]   = sum_w x[h, w] * TA[w, j]                 M=128 (rows)  N=2*N1  K=W
+//   stage 2 (leading dim) D2[i', n]  = sum_{p,h} A2[i', (p,h)] * R_p[h, n]      M=128         N=N1    K=256
+//
+//   warps 0-3  epilogue  (TMEM -> registers; D1 -> bf16 hi/lo B-operand of stage 2;  D2 -> global modes)
+//   warp  4    MMA issuer (one thread) + TMEM allocation
+//   warps 5-12 loaders   (LDG.128 -> bf16 hi/lo split -> swizzled STS into the slab ring)
+// =====================================================================================================
+constexpr int FA_LOADER_WARPS = 8;
+constexpr int FA_THREADS = (4 + 1 + FA_LOADER_WARPS) * 32;   // 416
+constexpr int FA_SLAB_BYTES = 128 * 128;                      // one [128 x 64] bf16 slab
+constexpr int FA_STAGE_BYTES = 2 * FA_SLAB_BYTES;             // hi + lo
+
+struct AnaParams {
+  const float* x;
+  float2* out;
+  const uint8_t* b1_img;   // [2*N1 x W] bf16, canonical K-major SW128 image (T1 rows then T2 rows)
+  const uint8_t* a2_img;   // [128 x 256] bf16 image of the real-embedded leading-dim table (T1 rows 0-63, T2 rows 64-127)
+  int n_tiles, W, slabs, N1, KX, QROWS, n_stages, tmem_cols;
+  uint32_t off_b1, off_a2, off_b2, off_scratch;
+};
+
+template <int N1>
+__global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
+  __shared__ uint64_t bar_full[4], bar_empty[4], bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_d2_full;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = P.n_stages;
+  uint8_t* s_b1 = smem + P.off_b1;
+  uint8_t* s_a2 = smem + P.off_a2;
+  uint8_t* s_b2 = smem + P.off_b2;
+  float* s_scr = reinterpret_cast<float*>(smem + P.off_scratch);
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], FA_LOADER_WARPS); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_d1_full[i], 1); mbar_init(&bar_d1_empty[i], 128); }
+    mbar_init(&bar_b2_full, 128);
+    mbar_init(&bar_d2_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 4) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+  // constant operand images: global -> shared, byte for byte
+  {
+    const int b1_vec = (2 * N1 * P.W * 2) / 16, a2_vec = (128 * 256 * 2) / 16;
+    const uint4* g1 = reinterpret_cast<const uint4*>(P.b1_img);
+    const uint4* g2 = reinterpret_cast<const uint4*>(P.a2_img);
+    uint4* d1 = reinterpret_cast<uint4*>(s_b1);
+    uint4* d2 = reinterpret_cast<uint4*>(s_a2);
+    for (int i = tid; i < b1_vec; i += FA_THREADS) d1[i] = __ldg(g1 + i);
+    for (int i = tid; i < a2_vec; i += FA_THREADS) d2[i] = __ldg(g2 + i);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tm_d1[2] = {tmem, tmem + (uint32_t)(2 * N1)};
+  const uint32_t tm_d2 = tmem + (uint32_t)(4 * N1);
+
+  const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ loaders
+    const int lt = tid - 5 * 32;                 // 0..255
+    const int rbase = lt >> 4, c4 = lt & 15;     // 16 float4 per 64-float row segment; 16 rows per pass
+    uint32_t g = 0;                              // running slab counter
+    float4 v[8];
+    auto issue = [&](int tile, int slab) {
+      const float* src = P.x + ((size_t)tile * 128) * P.W + slab * 64 + c4 * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) v[it] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(rbase + it * 16) * P.W));
+    };
+    const int total = n_local * P.slabs;
+    if (total > 0) issue((int)blockIdx.x, 0);
+    for (int idx = 0; idx < total; ++idx, ++g) {
+      const int slot = (int)(g % (uint32_t)NS);
+      const uint32_t ph = (g / (uint32_t)NS) & 1u;
+      float4 cur[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) cur[it] = v[it];
+      if (idx + 1 < total) {                     // keep the next slab's loads in flight while this one is converted
+        const int nidx = idx + 1;
+        issue((int)blockIdx.x + (nidx / P.slabs) * (int)gridDim.x, nidx % P.slabs);
+      }
+      mbar_wait(&bar_empty[slot], ph ^ 1u);
+      uint8_t* hi = smem + (size_t)slot * FA_STAGE_BYTES;
+      uint8_t* lo = hi + FA_SLAB_BYTES;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = rbase + it * 16;
+        float h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(cur[it].x, h0, l0); split_bf16(cur[it].y, h1, l1);
+        split_bf16(cur[it].z, h2, l2); split_bf16(cur[it].w, h3, l3);
+        const uint32_t off = sw128_offset(r, c4 * 4, 128);
+        *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+        *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[slot]);
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_p1 = idesc_bf16(128, 2 * N1), idesc_p2 = idesc_bf16(128, N1);
+      const uint32_t a_b1 = smem_u32(s_b1), a_a2 = smem_u32(s_a2), a_b2 = smem_u32(s_b2);
+      uint32_t g = 0;
+      auto stage2 = [&](int j) {   // leading-dim pass of local tile j
+        mbar_wait(&bar_b2_full, (uint32_t)(j & 1));
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int ks = 0; ks < 16; ++ks) {
+          const int slab = ks >> 2, kk = ks & 3;
+          mma_bf16_ss(tm_d2, smem_desc_sw128(a_a2 + slab * (128 * 128) + kk * 32),
+                      smem_desc_sw128(a_b2 + slab * (N1 * 128) + kk * 32), idesc_p2, ks > 0);
+        }
+        mma_commit(&bar_d2_full);
+      };
+      for (int i = 0; i < n_local; ++i) {
+        const int buf = i & 1;
+        mbar_wait(&bar_d1_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+        tc_fence_after_sync();
+        for (int s = 0; s < P.slabs; ++s, ++g) {
+          const int slot = (int)(g % (uint32_t)NS);
+          mbar_wait(&bar_full[slot], (g / (uint32_t)NS) & 1u);
+          tc_fence_after_sync();
+          const uint32_t a_hi = smem_u32(smem + (size_t)slot * FA_STAGE_BYTES), a_lo = a_hi + FA_SLAB_BYTES;
+          const uint32_t b_sl = a_b1 + s * (2 * N1 * 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            mma_bf16_ss(tm_d1[buf], smem_desc_sw128(a_hi + kk * 32), smem_desc_sw128(b_sl + kk * 32), idesc_p1, (s | kk) != 0);
+            mma_bf16_ss(tm_d1[buf], smem_desc_sw128(a_lo + kk * 32), smem_desc_sw128(b_sl + kk * 32), idesc_p2, true);
+          }
+          mma_commit(&bar_empty[slot]);
+        }
+        mma_commit(&bar_d1_full[buf]);
+        if (i >= 1) stage2(i - 1);
+      }
+      if (n_local >= 1) stage2(n_local - 1);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-3 = TMEM lane quarters)
+    const int row = warp * 32 + lane;                       // TMEM lane == tile row h (stage 1) / output row i' (stage 2)
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int KX = P.KX;
+    constexpr int half = N1 / 2;
+    auto epi2 = [&](int j) {   // D2 -> modes of local tile j
+      mbar_wait(&bar_d2_full, (uint32_t)(j & 1));
+      tc_fence_after_sync();
+      float acc[N1 / 2];
+#pragma unroll
+      for (int c = 0; c < N1; c += 16) {
+        float t[16];
+        tmem_ld16(tm_d2 + lane_sel + c, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = c + e;                 // hi block [0, half), lo block [half, N1)
+          if (col < half) acc[col] = t[e];
+          else acc[col - half] += t[e];
+        }
+      }
+      tc_fence_before_sync();
+      // T2 rows (warps 2,3) hand their partial sums to the matching T1 rows (warps 0,1)
+      if (warp >= 2) {
+        float* dst = s_scr + (row - 64) * (KX + 1);
+#pragma unroll
+        for (int kx = 0; kx < N1 / 2; ++kx) if (kx < KX) dst[kx] = acc[kx];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp < 2) {
+        const float* src = s_scr + row * (KX + 1);
+        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+        const int q = row >> 1, part = row & 1;
+        const bool live = q < P.QROWS;
+        float2* dst = P.out + ((size_t)tile * P.QROWS + q) * KX;
+#pragma unroll
+        for (int kx = 0; kx < N1 / 2; ++kx) {
+          if (kx < KX) {                         // warp-uniform
+            const float mine = acc[kx] + src[kx];
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            if (live && part == 0) dst[kx] = make_float2(mine, other);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    for (int i = 0; i < n_local; ++i) {
+      if (i >= 1) epi2(i - 1);
+      const int buf = i & 1;
+      mbar_wait(&bar_d1_full[buf], (uint32_t)((i >> 1) & 1));
+      tc_fence_after_sync();
+      float r[N1];             // R[h, j] = T1 block + T2 block
+#pragma unroll
+      for (int c = 0; c < 2 * N1; c += 16) {
+        float t[16];
+        tmem_ld16(tm_d1[buf] + lane_sel + c, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = c + e;
+          if (col < N1) r[col] = t[e];
+          else r[col - N1] += t[e];
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bar_d1_empty[buf]);
+      // B operand of stage 2: row n = kx (hi) / half + kx (lo), column k2 = part*128 + h, K-major SW128, N1 rows per slab
+#pragma unroll
+      for (int j = 0; j < N1; ++j) {
+        if (j < 2 * KX) {
+          const int kx = j >> 1, part = j & 1;
+          float hi_f, lo_f;
+          split_bf16(r[j], hi_f, lo_f);
+          const int k2 = part * 128 + row;
+          *reinterpret_cast<__nv_bfloat16*>(s_b2 + sw128_offset(kx, k2, N1)) = __float2bfloat16_rn(hi_f);
+          *reinterpret_cast<__nv_bfloat16*>(s_b2 + sw128_offset(half + kx, k2, N1)) = __float2bfloat16_rn(lo_f);
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_b2_full);
+    }
+    if (n_local >= 1) epi2(n_local - 1);
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: operand images and dispatch
+// ---------------------------------------------------------------------------------------------------------
+struct FusedAnalysisTables {
+  bool ok = false;
+  int W = 0, H = 0, G = 0, N1 = 0, KX = 0, KY = 0, slabs = 0, n_stages = 0, tmem_cols = 0;
+  uint8_t* d_b1 = nullptr;
+  uint8_t* d_a2 = nullptr;
+  uint32_t off_b1 = 0, off_a2 = 0, off_b2 = 0, off_scratch = 0, smem_bytes = 0;
+};
+
+struct FastTables {
+  FusedAnalysisTables ana[2];   // [0] forward analysis on `grid`, [1] adjoint-of-synthesis analysis on `out_grid`
+  int sm_count = 0;
+};
+
+static inline uint16_t bf16_bits(float f) {   // round to nearest even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+static inline float bf16_to_float(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline size_t host_sw128_offset(int r, int k, int rows) {
+  const int slab = k >> 6, kk = k & 63;
+  return (size_t)slab * rows * 128 + (size_t)r * 128 + ((((kk >> 3) ^ r) & 7) << 4) + ((kk & 7) << 1);
+}
+// writes v as T1 (row r1) and T2 (row r2) of a [rows x K] K-major SW128 bf16 image
+static inline void put_split(std::vector<uint8_t>& img, int rows, int r1, int r2, int k, float v) {
+  const uint16_t t1 = bf16_bits(v);
+  const uint16_t t2 = bf16_bits(v - bf16_to_float(t1));
+  memcpy(&img[host_sw128_offset(r1, k, rows)], &t1, 2);
+  memcpy(&img[host_sw128_offset(r2, k, rows)], &t2, 2);
+}
+
+template <typename T>
+static bool upload_bytes(Plan* p, const std::vector<T>& host, uint8_t** dev) {
+  void* d = nullptr;
+  if (!cuda_ok(cudaMalloc(&d, host.size() * sizeof(T)), "cudaMalloc(fast table)")) return false;
+  p->owned.push_back(d);
+  if (!cuda_ok(cudaMemcpy(d, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice), "cudaMemcpy(fast table)")) return false;
+  *dev = static_cast<uint8_t*>(d);
+  return true;
+}
+
+// last-dim table `tab` is [W x 2KX] (row stride 2KX); leading-dim table `lead` is [KY x H] complex
+static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, int KY, int KX, const std::vector<float>& tab,
+                                 const std::vector<float2>& lead) {
+  t->ok = false;
+  if (W % 64 != 0 || W > 128 || H < 16 || 128 % H != 0) return true;
+  const int G = 128 / H;
+  const int N1 = ((2 * KX + 15) / 16) * 16;
+  if (N1 > 96 || G * KY > 32 || KX < 1 || KY < 1) return true;
+  t->W = W; t->H = H; t->G = G; t->N1 = N1; t->KX = KX; t->KY = KY; t->slabs = W / 64;
+  t->tmem_cols = 5 * N1 <= 256 ? 256 : 512;
+  // ---- B1: [2*N1 x W]
+  std::vector<uint8_t> b1((size_t)2 * N1 * W * 2, 0);
+  for (int j = 0; j < 2 * KX; ++j)
+    for (int w = 0; w < W; ++w) put_split(b1, 2 * N1, j, N1 + j, w, tab[(size_t)w * 2 * KX + j]);
+  // ---- A2: [128 x 256]; row i' = 2*(g*KY + ky) + p_out (T1), 64 + i' (T2); column k2 = p_in*128 + g*H + h
+  std::vector<uint8_t> a2((size_t)128 * 256 * 2, 0);
+  for (int g = 0; g < G; ++g)
+    for (int ky = 0; ky < KY; ++ky)
+      for (int h = 0; h < H; ++h) {
+        const float2 f = lead[(size_t)ky * H + h];
+        const int q = g * KY + ky, hl = g * H + h;
+        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 0 * 128 + hl, f.x);
+        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 1 * 128 + hl, -f.y);
+        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 0 * 128 + hl, f.y);
+        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 1 * 128 + hl, f.x);
+      }
+  if (!upload_bytes(p, b1, &t->d_b1) || !upload_bytes(p, a2, &t->d_a2)) return false;
+  // ---- shared-memory carve-up
+  const uint32_t fixed = (uint32_t)b1.size() + 65536u + (uint32_t)N1 * 512u + ((64u * (KX + 1) * 4u + 1023u) & ~1023u);
+  int stages = (int)((227u * 1024u - 4096u - fixed) / FA_STAGE_BYTES);
+  if (stages > 4) stages = 4;
+  if (stages < 2) return true;
+  t->n_stages = stages;
+  t->off_b1 = (uint32_t)stages * FA_STAGE_BYTES;
+  t->off_a2 = t->off_b1 + (uint32_t)b1.size();
+  t->off_b2 = t->off_a2 + 65536u;
+  t->off_scratch = t->off_b2 + (uint32_t)N1 * 512u;
+  t->smem_bytes = t->off_scratch + ((64u * (KX + 1) * 4u + 1023u) & ~1023u) + 1024u;
+  t->ok = true;
+  return true;
+}
+
+bool fast_plan_init(Plan* p) {
+  p->fast = nullptr;
+  if (p->d < 2) return true;
+  cudaDeviceProp prop{};
+  if (!cuda_ok(cudaGetDeviceProperties(&prop, p->device), "cudaGetDeviceProperties")) return false;
+  if (prop.major != 10) return true;   // tcgen05 path is sm_100-only
+  FastTables* f = new FastTables();
+  f->sm_count = prop.multiProcessorCount;
+  const DimTables& L = p->dim[p->d - 1];
+  const DimTables& Y = p->dim[p->d - 2];
+  bool good = build_fused_analysis(p, &f->ana[0], Y.N, L.N, Y.k, L.k, p->h_TA, Y.h_A) &&
+              build_fused_analysis(p, &f->ana[1], Y.M, L.M, Y.k, L.k, p->h_TST, Y.h_SH);
+  if (!good) { delete f; return false; }
+  p->fast = f;
+  return true;
+}
+
+void fast_plan_destroy(Plan* p) {
+  delete p->fast;
+  p->fast = nullptr;
+}
+
+bool fast_can_analyze(const Plan* p, bool adjoint) {
+  return p->fast != nullptr && p->d == 2 && p->fast->ana[adjoint ? 1 : 0].ok;
+}
+bool fast_can_synthesize(const Plan*, bool) { return false; }
+
+bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint, cudaStream_t st) {
+  const FusedAnalysisTables& t = p->fast->ana[adjoint ? 1 : 0];
+  if (n_images % t.G != 0) { set_error("fast_analyze: image count not a multiple of the tile group"); return false; }
+  AnaParams P{};
+  P.x = images; P.out = modes_out; P.b1_img = t.d_b1; P.a2_img = t.d_a2;
+  P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.slabs = t.slabs; P.N1 = t.N1; P.KX = t.KX; P.QROWS = t.G * t.KY;
+  P.n_stages = t.n_stages; P.tmem_cols = t.tmem_cols;
+  P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch;
+  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  switch (t.N1) {
+#define SC_FA_CASE(N)                                                                                            \
+  case N: {                                                                                                      \
+    static uint32_t attr_bytes = 0;                                                                              \
+    if (attr_bytes < t.smem_bytes) {                                                                             \
+      if (!cuda_ok(cudaFuncSetAttribute(k_fused_analysis<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                        (int)t.smem_bytes), "cudaFuncSetAttribute(k_fused_analysis)"))          \
+        return false;                                                                                            \
+      attr_bytes = t.smem_bytes;                                                                                 \
+    }                                                                                                            \
+    k_fused_analysis<N><<<grid, FA_THREADS, t.smem_bytes, st>>>(P);                                              \
+  } break;
+    SC_FA_CASE(16) SC_FA_CASE(32) SC_FA_CASE(48) SC_FA_CASE(64) SC_FA_CASE(80) SC_FA_CASE(96)
+#undef SC_FA_CASE
+    default: set_error("fast_analyze: unsupported N1"); return false;
+  }
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_fused_analysis launch");
+}
+
 bool fast_synthesize(const Plan*, const float2*, int64_t, int, const float*, float*, bool, cudaStream_t) {
-  set_error("fast path not available for this shape");
+  set_error("fast synthesis not available for this shape");
   return false;
 }
 

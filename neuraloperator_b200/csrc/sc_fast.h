@@ -16,4 +16,6 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
 bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
                      float* images_out, bool adjoint, cudaStream_t st);
 
+bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
+
 }  // namespace sc

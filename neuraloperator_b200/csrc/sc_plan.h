@@ -25,7 +25,10 @@ struct DimTables {
   float2* d_AH = nullptr;   // its adjoint       [N x k]
   float2* d_S = nullptr;    // synthesis         [M x k]   exp(+2 pi i b n / M) * [b < M]
   float2* d_SH = nullptr;   // its adjoint       [k x M]
+  std::vector<float2> h_A, h_AH, h_S, h_SH;   // host copies (the fast path derives its bf16 operand images from them)
 };
+
+struct FastTables;   // sc_fast.cu
 
 struct Plan {
   sc_problem prob{};
@@ -46,6 +49,8 @@ struct Plan {
   int64_t weight_elems_per_io = 1;         // prod max_n_modes
   bool weight_block_is_whole = true;       // kept block == whole weight tensor
   bool fast_enabled = true;
+  std::vector<float> h_TA, h_TAT, h_TS, h_TST;   // host copies of the last-dim tables
+  FastTables* fast = nullptr;              // tcgen05 path state (nullptr when the shape does not qualify)
   std::vector<void*> owned;                // every cudaMalloc made for this plan
 };
 
