@@ -316,6 +316,239 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
   if (warp == 4) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
 }
 
+// =====================================================================================================
+// fused synthesis:  kept modes of the G images of a tile  ->  128 image rows (+ bias)
+//
+//   stage A (leading dim) DA[hl, n] = sum_k AA[hl, k] * BA[n, k]      M=128 (rows)  N=2*N1  K=128 (T1 | T2 halves)
+//   stage B (last dim)    DB[hl, w] = sum_j U[hl, j] * TS[j, w]       M=128         N=W     K=N1 x 3 bf16 products
+//
+//   warps 0-3  epilogue B (TMEM -> +bias -> 256-bit global stores of the image rows)
+//   warps 4-7  epilogue A (TMEM -> U -> bf16 hi/lo A-operand of stage B)
+//   warp  8    MMA issuer + TMEM allocation
+//   warps 9-12 prep      (modes -> bf16 hi/lo real-embedded B-operand of stage A)
+// =====================================================================================================
+constexpr int FS_THREADS = 13 * 32;
+
+struct SynParams {
+  const float2* modes;
+  float* out;
+  const float* bias;       // may be null
+  const uint8_t* aa_img;   // [128 x 128] bf16 image: leading-dim table, columns (2q+s | 64+2q+s)
+  const uint8_t* bb_img;   // two [W x 64] bf16 images: T1 then T2 of the last-dim table (rows = w, K = j)
+  int n_tiles, W, KX, QROWS, H, n_channels, tmem_cols;
+  uint32_t off_aa, off_ba, off_u, off_bb;
+};
+
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+template <int N1>
+__global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_ba_full[2], bar_ba_empty[2], bar_da_full[2], bar_da_empty[2];
+  __shared__ uint64_t bar_u_full[2], bar_u_empty[2], bar_db_full[2], bar_db_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  constexpr int BA_BYTES = 2 * N1 * 256;    // [2*N1 x 128] bf16 = two slabs of 2*N1 rows
+  constexpr int U_BYTES = 2 * FA_SLAB_BYTES;  // hi slab + lo slab, [128 x 64] bf16 each
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W = P.W, KX = P.KX;
+  uint8_t* s_aa = smem + P.off_aa;
+  uint8_t* s_ba = smem + P.off_ba;
+  uint8_t* s_u = smem + P.off_u;
+  uint8_t* s_bb = smem + P.off_bb;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_ba_full[i], 4);  mbar_init(&bar_ba_empty[i], 1);
+      mbar_init(&bar_da_full[i], 1);  mbar_init(&bar_da_empty[i], 128);
+      mbar_init(&bar_u_full[i], 128); mbar_init(&bar_u_empty[i], 1);
+      mbar_init(&bar_db_full[i], 1);  mbar_init(&bar_db_empty[i], 128);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+  {
+    const uint4* g1 = reinterpret_cast<const uint4*>(P.aa_img);
+    const uint4* g2 = reinterpret_cast<const uint4*>(P.bb_img);
+    uint4* d1 = reinterpret_cast<uint4*>(s_aa);
+    uint4* d2 = reinterpret_cast<uint4*>(s_bb);
+    for (int i = tid; i < (128 * 128 * 2) / 16; i += FS_THREADS) d1[i] = __ldg(g1 + i);
+    for (int i = tid; i < (2 * W * 128) / 16; i += FS_THREADS) d2[i] = __ldg(g2 + i);
+    uint4* z1 = reinterpret_cast<uint4*>(s_ba);     // zero both BA buffers and both U buffers once: padding rows /
+    for (int i = tid; i < (2 * BA_BYTES) / 16; i += FS_THREADS) z1[i] = make_uint4(0, 0, 0, 0);   // columns stay zero
+    uint4* z2 = reinterpret_cast<uint4*>(s_u);
+    for (int i = tid; i < (2 * U_BYTES) / 16; i += FS_THREADS) z2[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tm_da[2] = {tmem, tmem + (uint32_t)(2 * N1)};
+  const uint32_t tm_db[2] = {tmem + (uint32_t)(4 * N1), tmem + (uint32_t)(4 * N1 + W)};
+  const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp >= 9) {
+    // ------------------------------------------------------------------ prep: modes -> BA
+    const int pt = tid - 9 * 32;   // 0..127
+    const int n_el = P.QROWS * KX;
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      const float2* src = P.modes + (size_t)tile * n_el;
+      mbar_wait(&bar_ba_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+      uint8_t* ba = s_ba + buf * BA_BYTES;
+      for (int e = pt; e < n_el; e += 128) {
+        const float2 y = __ldg(src + e);
+        const int q = e / KX, kx = e - q * KX;
+        float rh, rl, ih, il;
+        split_bf16(y.x, rh, rl);
+        split_bf16(y.y, ih, il);
+        const uint32_t re_row_hi = pack_bf16(rh, -ih), im_row_hi = pack_bf16(ih, rh);
+        const uint32_t re_row_lo = pack_bf16(rl, -il), im_row_lo = pack_bf16(il, rl);
+        const int n0 = 2 * kx, n1 = 2 * kx + 1, k = 2 * q;
+        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, k, 2 * N1)) = re_row_hi;        // hi * T1
+        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, k, 2 * N1)) = im_row_hi;
+        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, 64 + k, 2 * N1)) = re_row_hi;   // hi * T2
+        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, 64 + k, 2 * N1)) = im_row_hi;
+        *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n0, k, 2 * N1)) = re_row_lo;   // lo * T1
+        *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n1, k, 2 * N1)) = im_row_lo;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ba_full[buf]);
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_a = idesc_bf16(128, 2 * N1), idesc_b = idesc_bf16(128, W);
+      const uint32_t a_aa = smem_u32(s_aa), a_ba = smem_u32(s_ba), a_u = smem_u32(s_u), a_bb = smem_u32(s_bb);
+      auto stage_b = [&](int j) {
+        const int buf = j & 1;
+        const uint32_t ph = (uint32_t)((j >> 1) & 1);
+        mbar_wait(&bar_u_full[buf], ph);
+        mbar_wait(&bar_db_empty[buf], ph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t u_hi = a_u + buf * U_BYTES, u_lo = u_hi + FA_SLAB_BYTES;
+        const uint32_t t1 = a_bb, t2 = a_bb + (uint32_t)W * 128;
+#pragma unroll
+        for (int ks = 0; ks < N1 / 16; ++ks) {
+          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, ks > 0);
+          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_lo + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, true);
+          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t2 + ks * 32), idesc_b, true);
+        }
+        mma_commit(&bar_u_empty[buf]);
+        mma_commit(&bar_db_full[buf]);
+      };
+      for (int i = 0; i < n_local; ++i) {
+        const int buf = i & 1;
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        mbar_wait(&bar_ba_full[buf], ph);
+        mbar_wait(&bar_da_empty[buf], ph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t ba = a_ba + buf * BA_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const int slab = ks >> 2, kk = ks & 3;
+          mma_bf16_ss(tm_da[buf], smem_desc_sw128(a_aa + slab * (128 * 128) + kk * 32),
+                      smem_desc_sw128(ba + slab * (2 * N1 * 128) + kk * 32), idesc_a, ks > 0);
+        }
+        mma_commit(&bar_ba_empty[buf]);
+        mma_commit(&bar_da_full[buf]);
+        if (i >= 1) stage_b(i - 1);
+      }
+      if (n_local >= 1) stage_b(n_local - 1);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue A: DA -> U (hi / lo)
+    const int q4 = warp - 4;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      mbar_wait(&bar_da_full[buf], ph);
+      tc_fence_after_sync();
+      float u[N1];
+#pragma unroll
+      for (int c = 0; c < 2 * N1; c += 16) {
+        float t[16];
+        tmem_ld16(tm_da[buf] + lane_sel + c, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = c + e;
+          if (col < N1) u[col] = t[e];
+          else u[col - N1] += t[e];
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bar_da_empty[buf]);
+      mbar_wait(&bar_u_empty[buf], ph ^ 1u);
+      uint8_t* uhi = s_u + buf * U_BYTES;
+      uint8_t* ulo = uhi + FA_SLAB_BYTES;
+#pragma unroll
+      for (int c = 0; c < N1 / 8; ++c) {          // one 16-byte chunk = 8 consecutive j
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float h0, l0, h1, l1;
+          split_bf16(u[c * 8 + 2 * e], h0, l0);
+          split_bf16(u[c * 8 + 2 * e + 1], h1, l1);
+          hw[e] = pack_bf16(h0, h1);
+          lw[e] = pack_bf16(l0, l1);
+        }
+        const uint32_t off = (uint32_t)(row * 128 + (((c ^ row) & 7) << 4));
+        *reinterpret_cast<uint4*>(uhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(ulo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_u_full[buf]);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue B: DB -> image rows
+    const int row = warp * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      float b = 0.f;
+      if (P.bias != nullptr) {
+        const long long image = (long long)tile * (128 / P.H) + row / P.H;
+        b = __ldg(P.bias + (int)(image % P.n_channels));
+      }
+      float* dst = P.out + ((size_t)tile * 128 + row) * W;
+      mbar_wait(&bar_db_full[buf], ph);
+      tc_fence_after_sync();
+      for (int c = 0; c < W; c += 32) {
+        float t0[16], t1[16];
+        tmem_ld16(tm_db[buf] + lane_sel + c, t0);
+        tmem_ld16(tm_db[buf] + lane_sel + c + 16, t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { t0[e] += b; t1[e] += b; }
+        st_global_v8(dst + c, t0);
+        st_global_v8(dst + c + 8, t0 + 8);
+        st_global_v8(dst + c + 16, t1);
+        st_global_v8(dst + c + 24, t1 + 8);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bar_db_empty[buf]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: operand images and dispatch
 // ---------------------------------------------------------------------------------------------------------
@@ -327,8 +560,17 @@ struct FusedAnalysisTables {
   uint32_t off_b1 = 0, off_a2 = 0, off_b2 = 0, off_scratch = 0, smem_bytes = 0;
 };
 
+struct FusedSynthesisTables {
+  bool ok = false;
+  int W = 0, H = 0, G = 0, N1 = 0, KX = 0, KY = 0, tmem_cols = 0;
+  uint8_t* d_aa = nullptr;
+  uint8_t* d_bb = nullptr;
+  uint32_t off_aa = 0, off_ba = 0, off_u = 0, off_bb = 0, smem_bytes = 0;
+};
+
 struct FastTables {
   FusedAnalysisTables ana[2];   // [0] forward analysis on `grid`, [1] adjoint-of-synthesis analysis on `out_grid`
+  FusedSynthesisTables syn[2];  // [0] forward synthesis onto `out_grid`, [1] adjoint-of-analysis synthesis onto `grid`
   int sm_count = 0;
 };
 
@@ -409,6 +651,55 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   return true;
 }
 
+// last-dim table `tab` is [2KX x W] (row stride W); leading-dim table `lead` is [H x KY] complex
+static bool build_fused_synthesis(Plan* p, FusedSynthesisTables* t, int H, int W, int KY, int KX, const std::vector<float>& tab,
+                                  const std::vector<float2>& lead) {
+  t->ok = false;
+  if (W % 64 != 0 || W > 256 || H < 16 || 128 % H != 0) return true;
+  const int G = 128 / H;
+  const int N1 = ((2 * KX + 15) / 16) * 16;
+  if (N1 > 64 || G * KY > 32 || KX < 1 || KY < 1 || 4 * N1 + 2 * W > 512) return true;
+  t->W = W; t->H = H; t->G = G; t->N1 = N1; t->KX = KX; t->KY = KY;
+  t->tmem_cols = 4 * N1 + 2 * W <= 256 ? 256 : 512;
+  // ---- AA: [128 x 128]; row hl = g*H + h; columns 2q+s (T1) and 64+2q+s (T2), q = g*KY + ky, s: 0 = Re, 1 = Im of the table
+  std::vector<uint8_t> aa((size_t)128 * 128 * 2, 0);
+  {
+    // T1 and T2 of the same coefficient live in the SAME row at columns k and 64 + k
+    for (int g = 0; g < G; ++g)
+      for (int h = 0; h < H; ++h)
+        for (int ky = 0; ky < KY; ++ky) {
+          const float2 f = lead[(size_t)h * KY + ky];
+          const int hl = g * H + h, q = g * KY + ky;
+          const float vals[2] = {f.x, f.y};
+          for (int sgn = 0; sgn < 2; ++sgn) {
+            const uint16_t t1 = bf16_bits(vals[sgn]);
+            const uint16_t t2 = bf16_bits(vals[sgn] - bf16_to_float(t1));
+            memcpy(&aa[host_sw128_offset(hl, 2 * q + sgn, 128)], &t1, 2);
+            memcpy(&aa[host_sw128_offset(hl, 64 + 2 * q + sgn, 128)], &t2, 2);
+          }
+        }
+  }
+  // ---- BB: T1 image then T2 image, each [W x 64]: row w, column j
+  std::vector<uint8_t> bb((size_t)2 * W * 128, 0);
+  for (int j = 0; j < 2 * KX; ++j)
+    for (int w = 0; w < W; ++w) {
+      const float v = tab[(size_t)j * W + w];
+      const uint16_t t1 = bf16_bits(v);
+      const uint16_t t2 = bf16_bits(v - bf16_to_float(t1));
+      memcpy(&bb[host_sw128_offset(w, j, W)], &t1, 2);
+      memcpy(&bb[(size_t)W * 128 + host_sw128_offset(w, j, W)], &t2, 2);
+    }
+  if (!upload_bytes(p, aa, &t->d_aa) || !upload_bytes(p, bb, &t->d_bb)) return false;
+  t->off_aa = 0;
+  t->off_ba = 32768u;
+  t->off_u = t->off_ba + 2u * (uint32_t)(2 * N1 * 256);
+  t->off_bb = t->off_u + 2u * (uint32_t)(2 * FA_SLAB_BYTES);
+  t->smem_bytes = t->off_bb + (uint32_t)bb.size() + 1024u;
+  if (t->smem_bytes > 227u * 1024u - 4096u) return true;
+  t->ok = true;
+  return true;
+}
+
 bool fast_plan_init(Plan* p) {
   p->fast = nullptr;
   if (p->d < 2) return true;
@@ -420,7 +711,9 @@ bool fast_plan_init(Plan* p) {
   const DimTables& L = p->dim[p->d - 1];
   const DimTables& Y = p->dim[p->d - 2];
   bool good = build_fused_analysis(p, &f->ana[0], Y.N, L.N, Y.k, L.k, p->h_TA, Y.h_A) &&
-              build_fused_analysis(p, &f->ana[1], Y.M, L.M, Y.k, L.k, p->h_TST, Y.h_SH);
+              build_fused_analysis(p, &f->ana[1], Y.M, L.M, Y.k, L.k, p->h_TST, Y.h_SH) &&
+              build_fused_synthesis(p, &f->syn[0], Y.M, L.M, Y.k, L.k, p->h_TS, Y.h_S) &&
+              build_fused_synthesis(p, &f->syn[1], Y.N, L.N, Y.k, L.k, p->h_TAT, Y.h_AH);
   if (!good) { delete f; return false; }
   p->fast = f;
   return true;
@@ -434,7 +727,9 @@ void fast_plan_destroy(Plan* p) {
 bool fast_can_analyze(const Plan* p, bool adjoint) {
   return p->fast != nullptr && p->d == 2 && p->fast->ana[adjoint ? 1 : 0].ok;
 }
-bool fast_can_synthesize(const Plan*, bool) { return false; }
+bool fast_can_synthesize(const Plan* p, bool adjoint) {
+  return p->fast != nullptr && p->d == 2 && p->fast->syn[adjoint ? 1 : 0].ok;
+}
 
 bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint, cudaStream_t st) {
   const FusedAnalysisTables& t = p->fast->ana[adjoint ? 1 : 0];
@@ -465,9 +760,34 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   return cuda_ok(cudaGetLastError(), "k_fused_analysis launch");
 }
 
-bool fast_synthesize(const Plan*, const float2*, int64_t, int, const float*, float*, bool, cudaStream_t) {
-  set_error("fast synthesis not available for this shape");
-  return false;
+bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
+                     float* images_out, bool adjoint, cudaStream_t st) {
+  const FusedSynthesisTables& t = p->fast->syn[adjoint ? 1 : 0];
+  if (n_images % t.G != 0) { set_error("fast_synthesize: image count not a multiple of the tile group"); return false; }
+  SynParams P{};
+  P.modes = modes_in; P.out = images_out; P.bias = bias; P.aa_img = t.d_aa; P.bb_img = t.d_bb;
+  P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.KX = t.KX; P.QROWS = t.G * t.KY; P.H = t.H;
+  P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
+  P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb;
+  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  switch (t.N1) {
+#define SC_FS_CASE(N)                                                                                            \
+  case N: {                                                                                                      \
+    static uint32_t attr_bytes = 0;                                                                              \
+    if (attr_bytes < t.smem_bytes) {                                                                             \
+      if (!cuda_ok(cudaFuncSetAttribute(k_fused_synthesis<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                        (int)t.smem_bytes), "cudaFuncSetAttribute(k_fused_synthesis)"))         \
+        return false;                                                                                            \
+      attr_bytes = t.smem_bytes;                                                                                 \
+    }                                                                                                            \
+    k_fused_synthesis<N><<<grid, FS_THREADS, t.smem_bytes, st>>>(P);                                             \
+  } break;
+    SC_FS_CASE(16) SC_FS_CASE(32) SC_FS_CASE(48) SC_FS_CASE(64)
+#undef SC_FS_CASE
+    default: set_error("fast_synthesize: unsupported N1"); return false;
+  }
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_fused_synthesis launch");
 }
 
 }  // namespace sc

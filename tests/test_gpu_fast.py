@@ -64,3 +64,32 @@ def test_fast_analysis_matches_generic_and_fp64(cuda_device, grid, modes, n0, n1
         for j, p in enumerate(plans):
             ref = ref.index_select(2 + j, torch.tensor(p.in_bins))
         assert _rel(torch.view_as_real(fast.cpu().to(torch.complex128)), torch.view_as_real(ref)) < 5e-5
+
+
+@pytest.mark.parametrize("grid,modes,n0,n1", [
+    ((128, 128), (32, 32), 2, 5),
+    ((128, 128), (32, 32), 32, 64),
+    ((128, 64), (16, 16), 3, 4),
+    ((64, 64), (16, 16), 2, 6),
+    ((128, 128), (12, 20), 1, 3),
+    ((32, 128), (8, 32), 2, 4),
+])
+@pytest.mark.parametrize("adjoint", [False, True])
+def test_fast_synthesis_matches_generic(cuda_device, grid, modes, n0, n1, adjoint):
+    from oracle import spectral_conv_oracle as O
+    stored = O.stored_n_modes(modes)
+    plan = nb.get_plan(cuda_device, grid, grid, stored, stored)
+    mask = plan.uses_fast_path()
+    assert mask & (8 if adjoint else 2), f"fast synthesis not selected for {grid} (mask {mask})"
+    torch.manual_seed(9)
+    ym = torch.randn(n0, n1, *plan.kept, dtype=torch.cfloat, device=cuda_device)
+    bias = None if adjoint else torch.randn(n1, device=cuda_device)
+    fast = nb.synthesize(plan, ym, bias, adjoint=adjoint)
+    plan.set_fast_path(False)
+    try:
+        slow = nb.synthesize(plan, ym, bias, adjoint=adjoint)
+    finally:
+        plan.set_fast_path(True)
+    torch.cuda.synchronize()
+    assert torch.isfinite(fast).all()
+    assert _rel(fast, slow) < 1e-4
