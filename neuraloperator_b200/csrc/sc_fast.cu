@@ -84,16 +84,20 @@ bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaS
 // fused analysis:  tile of 128 image rows  ->  kept modes of the G = 128/H images the tile holds
 //
 //   stage 1 (last dim)    D1[h, j]   = sum_w x[h, w] * TA[w, j]                 M=128 (rows)  N=2*N1  K=W
-//   stage 2 (leading dim) D2[i', n]  = sum_{p,h} A2[i', (p,h)] * R_p[h, n]      M=128         N=N1    K=256
+//   stage 2 (leading dim) D2[i', n]  = sum_{h,p} A2[i', (h,p)] * R_p[h, n]      M=128         N=N1    K=256
 //
-//   warps 0-3  epilogue  (TMEM -> registers; D1 -> bf16 hi/lo B-operand of stage 2;  D2 -> global modes)
-//   warp  4    MMA issuer (one thread) + TMEM allocation
-//   warps 5-12 loaders   (LDG.128 -> bf16 hi/lo split -> swizzled STS into the slab ring)
+//   Every role is its own pipeline stage with double buffers in between:
+//   warps 10-17 loaders   LDG.128 -> bf16 hi/lo split -> swizzled STS into the slab ring
+//   warp  8     stage-1 MMA issuer (+ TMEM allocation)          ring slab -> D1[2]
+//   warps 4-7   epilogue 1: D1 -> R -> bf16 hi/lo B operand of stage 2 (B2, single buffer)
+//   warp  9     stage-2 MMA issuer                                B2 -> D2[2]
+//   warps 0-3   epilogue 2: D2 -> kept modes in global memory
 // =====================================================================================================
 constexpr int FA_LOADER_WARPS = 8;
-constexpr int FA_THREADS = (4 + 1 + FA_LOADER_WARPS) * 32;   // 416
-constexpr int FA_SLAB_BYTES = 128 * 128;                      // one [128 x 64] bf16 slab
-constexpr int FA_STAGE_BYTES = 2 * FA_SLAB_BYTES;             // hi + lo
+constexpr int FA_LOADER_WARP0 = 10;
+constexpr int FA_THREADS = (FA_LOADER_WARP0 + FA_LOADER_WARPS) * 32;   // 576
+constexpr int FA_SLAB_BYTES = 128 * 128;                                // one [128 x 64] bf16 slab
+constexpr int FA_STAGE_BYTES = 2 * FA_SLAB_BYTES;                       // hi + lo
 
 struct AnaParams {
   const float* x;
@@ -108,8 +112,10 @@ template <int N1>
 __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
-  __shared__ uint64_t bar_full[4], bar_empty[4], bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_d2_full;
+  __shared__ uint64_t bar_full[4], bar_empty[4], bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_b2_empty,
+      bar_d2_full[2], bar_d2_empty[2];
   __shared__ uint32_t tmem_base_slot;
+  constexpr int half = N1 / 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = P.n_stages;
@@ -120,21 +126,20 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], FA_LOADER_WARPS); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_d1_full[i], 1); mbar_init(&bar_d1_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_d1_full[i], 1); mbar_init(&bar_d1_empty[i], 128);
+      mbar_init(&bar_d2_full[i], 1); mbar_init(&bar_d2_empty[i], 128);
+    }
     mbar_init(&bar_b2_full, 128);
-    mbar_init(&bar_d2_full, 1);
+    mbar_init(&bar_b2_empty, 1);
     mbar_init_fence();
   }
-  if (warp == 4) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
-  // constant operand images: global -> shared, byte for byte
+  if (warp == 8) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+  copy_image(s_b1, P.b1_img, (2 * N1 * P.W * 2) / 16, tid, FA_THREADS);
+  copy_image(s_a2, P.a2_img, (128 * 256 * 2) / 16, tid, FA_THREADS);
   {
-    const int b1_vec = (2 * N1 * P.W * 2) / 16, a2_vec = (128 * 256 * 2) / 16;
-    const uint4* g1 = reinterpret_cast<const uint4*>(P.b1_img);
-    const uint4* g2 = reinterpret_cast<const uint4*>(P.a2_img);
-    uint4* d1 = reinterpret_cast<uint4*>(s_b1);
-    uint4* d2 = reinterpret_cast<uint4*>(s_a2);
-    for (int i = tid; i < b1_vec; i += FA_THREADS) d1[i] = __ldg(g1 + i);
-    for (int i = tid; i < a2_vec; i += FA_THREADS) d2[i] = __ldg(g2 + i);
+    uint4* z = reinterpret_cast<uint4*>(s_b2);   // padding rows of B2 (kx >= KX) stay zero for the whole kernel
+    for (int i = tid; i < (N1 * 512) / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async_smem();
   tc_fence_before_sync();
@@ -142,13 +147,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_slot;
   const uint32_t tm_d1[2] = {tmem, tmem + (uint32_t)(2 * N1)};
-  const uint32_t tm_d2 = tmem + (uint32_t)(4 * N1);
+  const uint32_t tm_d2[2] = {tmem + (uint32_t)(4 * N1), tmem + (uint32_t)(5 * N1)};
 
   const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 5) {
+  if (warp >= FA_LOADER_WARP0) {
     // ------------------------------------------------------------------ loaders
-    const int lt = tid - 5 * 32;                 // 0..255
+    const int lt = tid - FA_LOADER_WARP0 * 32;   // 0..255
     const int rbase = lt >> 4, c4 = lt & 15;     // 16 float4 per 64-float row segment; 16 rows per pass
     uint32_t g = 0;                              // running slab counter
     float4 v[8];
@@ -162,47 +167,35 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     for (int idx = 0; idx < total; ++idx, ++g) {
       const int slot = (int)(g % (uint32_t)NS);
       const uint32_t ph = (g / (uint32_t)NS) & 1u;
-      float4 cur[8];
+      uint2 hi[8], lo[8];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) cur[it] = v[it];
-      if (idx + 1 < total) {                     // keep the next slab's loads in flight while this one is converted
+      for (int it = 0; it < 8; ++it) {
+        split2_bf16(v[it].x, v[it].y, hi[it].x, lo[it].x);
+        split2_bf16(v[it].z, v[it].w, hi[it].y, lo[it].y);
+      }
+      if (idx + 1 < total) {                     // next slab's loads are in flight while this one waits for its slot
         const int nidx = idx + 1;
         issue((int)blockIdx.x + (nidx / P.slabs) * (int)gridDim.x, nidx % P.slabs);
       }
       mbar_wait(&bar_empty[slot], ph ^ 1u);
-      uint8_t* hi = smem + (size_t)slot * FA_STAGE_BYTES;
-      uint8_t* lo = hi + FA_SLAB_BYTES;
+      uint8_t* shi = smem + (size_t)slot * FA_STAGE_BYTES;
+      uint8_t* slo = shi + FA_SLAB_BYTES;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const int r = rbase + it * 16;
-        float h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(cur[it].x, h0, l0); split_bf16(cur[it].y, h1, l1);
-        split_bf16(cur[it].z, h2, l2); split_bf16(cur[it].w, h3, l3);
-        const uint32_t off = sw128_offset(r, c4 * 4, 128);
-        *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-        *reinterpret_cast<uint2*>(lo + off) = make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+        const uint32_t off = sw128_offset(rbase + it * 16, c4 * 4, 128);
+        *reinterpret_cast<uint2*>(shi + off) = hi[it];
+        *reinterpret_cast<uint2*>(slo + off) = lo[it];
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full[slot]);
     }
-  } else if (warp == 4) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ stage-1 MMA issuer
     if (lane == 0) {
       const uint32_t idesc_p1 = idesc_bf16(128, 2 * N1), idesc_p2 = idesc_bf16(128, N1);
-      const uint32_t a_b1 = smem_u32(s_b1), a_a2 = smem_u32(s_a2), a_b2 = smem_u32(s_b2);
+      const uint32_t a_b1 = smem_u32(s_b1);
       uint32_t g = 0;
-      auto stage2 = [&](int j) {   // leading-dim pass of local tile j
-        mbar_wait(&bar_b2_full, (uint32_t)(j & 1));
-        tc_fence_after_sync();
-#pragma unroll 1
-        for (int ks = 0; ks < 16; ++ks) {
-          const int slab = ks >> 2, kk = ks & 3;
-          mma_bf16_ss(tm_d2, smem_desc_sw128(a_a2 + slab * (128 * 128) + kk * 32),
-                      smem_desc_sw128(a_b2 + slab * (N1 * 128) + kk * 32), idesc_p2, ks > 0);
-        }
-        mma_commit(&bar_d2_full);
-      };
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         mbar_wait(&bar_d1_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
@@ -221,99 +214,109 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
           mma_commit(&bar_empty[slot]);
         }
         mma_commit(&bar_d1_full[buf]);
-        if (i >= 1) stage2(i - 1);
       }
-      if (n_local >= 1) stage2(n_local - 1);
     }
     __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 0-3 = TMEM lane quarters)
-    const int row = warp * 32 + lane;                       // TMEM lane == tile row h (stage 1) / output row i' (stage 2)
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ stage-2 MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_p2 = idesc_bf16(128, N1);
+      const uint32_t a_a2 = smem_u32(s_a2), a_b2 = smem_u32(s_b2);
+      for (int i = 0; i < n_local; ++i) {
+        const int buf = i & 1;
+        mbar_wait(&bar_b2_full, (uint32_t)(i & 1));
+        mbar_wait(&bar_d2_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+        tc_fence_after_sync();
+#pragma unroll 4
+        for (int ks = 0; ks < 16; ++ks) {
+          const int slab = ks >> 2, kk = ks & 3;
+          mma_bf16_ss(tm_d2[buf], smem_desc_sw128(a_a2 + slab * (128 * 128) + kk * 32),
+                      smem_desc_sw128(a_b2 + slab * (N1 * 128) + kk * 32), idesc_p2, ks > 0);
+        }
+        mma_commit(&bar_b2_empty);
+        mma_commit(&bar_d2_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue 1: D1 -> B operand of stage 2
+    const int q4 = warp - 4;                                  // TMEM lane quarter; tile row h = q4*32 + lane
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const int KX = P.KX;
-    constexpr int half = N1 / 2;
-    auto epi2 = [&](int j) {   // D2 -> modes of local tile j
-      mbar_wait(&bar_d2_full, (uint32_t)(j & 1));
+    // B2[n][k2], k2 = 2*h + part: row h owns 4 bytes of every row n, inside K-slab q4 (64 columns = 32 rows h)
+    uint8_t* b2_mine = s_b2 + q4 * (N1 * 128) + (lane & 3) * 4;
+    const int chunk = lane >> 2;
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      mbar_wait(&bar_d1_full[buf], (uint32_t)((i >> 1) & 1));
+      mbar_wait(&bar_b2_empty, (uint32_t)((i & 1) ^ 1));
       tc_fence_after_sync();
-      float acc[N1 / 2];
 #pragma unroll
       for (int c = 0; c < N1; c += 16) {
-        float t[16];
-        tmem_ld16(tm_d2 + lane_sel + c, t);
+        float t1[16], t2[16];
+        tmem_ld16(tm_d1[buf] + lane_sel + c, t1);        // x_hi*T1 + x_lo*T1
+        tmem_ld16(tm_d1[buf] + lane_sel + N1 + c, t2);   // x_hi*T2
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int col = c + e;                 // hi block [0, half), lo block [half, N1)
-          if (col < half) acc[col] = t[e];
-          else acc[col - half] += t[e];
+        for (int e = 0; e < 8; ++e) {
+          const int kx = c / 2 + e;                       // compile-time
+          if (kx < KX) {                                  // warp-uniform
+            uint32_t hi, lo;
+            split2_bf16(t1[2 * e] + t2[2 * e], t1[2 * e + 1] + t2[2 * e + 1], hi, lo);
+            *reinterpret_cast<uint32_t*>(b2_mine + kx * 128 + ((chunk ^ (kx & 7)) << 4)) = hi;
+            *reinterpret_cast<uint32_t*>(b2_mine + (half + kx) * 128 + ((chunk ^ ((half + kx) & 7)) << 4)) = lo;
+          }
         }
       }
       tc_fence_before_sync();
-      // T2 rows (warps 2,3) hand their partial sums to the matching T1 rows (warps 0,1)
+      mbar_arrive(&bar_d1_empty[buf]);
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_b2_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue 2: D2 -> kept modes
+    const int row = warp * 32 + lane;                        // output row i' (0-63: T1 rows, 64-127: T2 rows)
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int KX = P.KX;
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      mbar_wait(&bar_d2_full[buf], (uint32_t)((i >> 1) & 1));
+      tc_fence_after_sync();
+      float d[N1];
+#pragma unroll
+      for (int c = 0; c < N1; c += 16) tmem_ld16(tm_d2[buf] + lane_sel + c, *reinterpret_cast<float(*)[16]>(&d[c]));
+      tmem_ld_wait();
+      tc_fence_before_sync();
+      mbar_arrive(&bar_d2_empty[buf]);
+      // T2 rows (warps 2,3) hand hi+lo sums to the matching T1 rows (warps 0,1)
       if (warp >= 2) {
         float* dst = s_scr + (row - 64) * (KX + 1);
 #pragma unroll
-        for (int kx = 0; kx < N1 / 2; ++kx) if (kx < KX) dst[kx] = acc[kx];
+        for (int kx = 0; kx < half; ++kx) if (kx < KX) dst[kx] = d[kx] + d[half + kx];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp < 2) {
         const float* src = s_scr + row * (KX + 1);
-        const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int q = row >> 1, part = row & 1;
         const bool live = q < P.QROWS;
         float2* dst = P.out + ((size_t)tile * P.QROWS + q) * KX;
 #pragma unroll
-        for (int kx = 0; kx < N1 / 2; ++kx) {
+        for (int kx = 0; kx < half; ++kx) {
           if (kx < KX) {                         // warp-uniform
-            const float mine = acc[kx] + src[kx];
+            const float mine = d[kx] + d[half + kx] + src[kx];
             const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
             if (live && part == 0) dst[kx] = make_float2(mine, other);
           }
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-    };
-    for (int i = 0; i < n_local; ++i) {
-      if (i >= 1) epi2(i - 1);
-      const int buf = i & 1;
-      mbar_wait(&bar_d1_full[buf], (uint32_t)((i >> 1) & 1));
-      tc_fence_after_sync();
-      float r[N1];             // R[h, j] = T1 block + T2 block
-#pragma unroll
-      for (int c = 0; c < 2 * N1; c += 16) {
-        float t[16];
-        tmem_ld16(tm_d1[buf] + lane_sel + c, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int col = c + e;
-          if (col < N1) r[col] = t[e];
-          else r[col - N1] += t[e];
-        }
-      }
-      tc_fence_before_sync();
-      mbar_arrive(&bar_d1_empty[buf]);
-      // B operand of stage 2: row n = kx (hi) / half + kx (lo), column k2 = part*128 + h, K-major SW128, N1 rows per slab
-#pragma unroll
-      for (int j = 0; j < N1; ++j) {
-        if (j < 2 * KX) {
-          const int kx = j >> 1, part = j & 1;
-          float hi_f, lo_f;
-          split_bf16(r[j], hi_f, lo_f);
-          const int k2 = part * 128 + row;
-          *reinterpret_cast<__nv_bfloat16*>(s_b2 + sw128_offset(kx, k2, N1)) = __float2bfloat16_rn(hi_f);
-          *reinterpret_cast<__nv_bfloat16*>(s_b2 + sw128_offset(half + kx, k2, N1)) = __float2bfloat16_rn(lo_f);
-        }
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(&bar_b2_full);
     }
-    if (n_local >= 1) epi2(n_local - 1);
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
+  if (warp == 8) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
 }
 
 // =====================================================================================================
@@ -322,12 +325,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 //   stage A (leading dim) DA[hl, n] = sum_k AA[hl, k] * BA[n, k]      M=128 (rows)  N=2*N1  K=128 (T1 | T2 halves)
 //   stage B (last dim)    DB[hl, w] = sum_j U[hl, j] * TS[j, w]       M=128         N=W     K=N1 x 3 bf16 products
 //
-//   warps 0-3  epilogue B (TMEM -> +bias -> 256-bit global stores of the image rows)
-//   warps 4-7  epilogue A (TMEM -> U -> bf16 hi/lo A-operand of stage B)
-//   warp  8    MMA issuer + TMEM allocation
-//   warps 9-12 prep      (modes -> bf16 hi/lo real-embedded B-operand of stage A)
+//   warps 10-13 prep       modes -> bf16 hi/lo real-embedded B operand of stage A (BA[2])
+//   warp  8     stage-A MMA issuer (+ TMEM allocation)   BA -> DA[2]
+//   warps 4-7   epilogue A: DA -> U -> bf16 hi/lo A operand of stage B (U[2])
+//   warp  9     stage-B MMA issuer                        U -> DB[2]
+//   warps 0-3   epilogue B: DB -> + bias -> 256-bit global stores of the image rows
 // =====================================================================================================
-constexpr int FS_THREADS = 13 * 32;
+constexpr int FS_THREADS = 14 * 32;
 
 struct SynParams {
   const float2* modes;
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
   __shared__ uint64_t bar_ba_full[2], bar_ba_empty[2], bar_da_full[2], bar_da_empty[2];
   __shared__ uint64_t bar_u_full[2], bar_u_empty[2], bar_db_full[2], bar_db_empty[2];
   __shared__ uint32_t tmem_base_slot;
-  constexpr int BA_BYTES = 2 * N1 * 256;    // [2*N1 x 128] bf16 = two slabs of 2*N1 rows
+  constexpr int BA_BYTES = 2 * N1 * 256;      // [2*N1 x 128] bf16 = two slabs of 2*N1 rows
   constexpr int U_BYTES = 2 * FA_SLAB_BYTES;  // hi slab + lo slab, [128 x 64] bf16 each
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -372,13 +376,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     mbar_init_fence();
   }
   if (warp == 8) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+  copy_image(s_aa, P.aa_img, (128 * 128 * 2) / 16, tid, FS_THREADS);
+  copy_image(s_bb, P.bb_img, (2 * W * 128) / 16, tid, FS_THREADS);
   {
-    const uint4* g1 = reinterpret_cast<const uint4*>(P.aa_img);
-    const uint4* g2 = reinterpret_cast<const uint4*>(P.bb_img);
-    uint4* d1 = reinterpret_cast<uint4*>(s_aa);
-    uint4* d2 = reinterpret_cast<uint4*>(s_bb);
-    for (int i = tid; i < (128 * 128 * 2) / 16; i += FS_THREADS) d1[i] = __ldg(g1 + i);
-    for (int i = tid; i < (2 * W * 128) / 16; i += FS_THREADS) d2[i] = __ldg(g2 + i);
     uint4* z1 = reinterpret_cast<uint4*>(s_ba);     // zero both BA buffers and both U buffers once: padding rows /
     for (int i = tid; i < (2 * BA_BYTES) / 16; i += FS_THREADS) z1[i] = make_uint4(0, 0, 0, 0);   // columns stay zero
     uint4* z2 = reinterpret_cast<uint4*>(s_u);
@@ -393,58 +393,48 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
   const uint32_t tm_db[2] = {tmem + (uint32_t)(4 * N1), tmem + (uint32_t)(4 * N1 + W)};
   const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 9) {
+  if (warp >= 10) {
     // ------------------------------------------------------------------ prep: modes -> BA
-    const int pt = tid - 9 * 32;   // 0..127
+    const int pt = tid - 10 * 32;   // 0..127
     const int n_el = P.QROWS * KX;
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const float2* src = P.modes + (size_t)tile * n_el;
+      float2 y[5];                                   // n_el <= 32 * 48 / ... : QROWS*KX <= 32*32 -> <= 8 per thread
       mbar_wait(&bar_ba_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
       uint8_t* ba = s_ba + buf * BA_BYTES;
-      for (int e = pt; e < n_el; e += 128) {
-        const float2 y = __ldg(src + e);
-        const int q = e / KX, kx = e - q * KX;
-        float rh, rl, ih, il;
-        split_bf16(y.x, rh, rl);
-        split_bf16(y.y, ih, il);
-        const uint32_t re_row_hi = pack_bf16(rh, -ih), im_row_hi = pack_bf16(ih, rh);
-        const uint32_t re_row_lo = pack_bf16(rl, -il), im_row_lo = pack_bf16(il, rl);
-        const int n0 = 2 * kx, n1 = 2 * kx + 1, k = 2 * q;
-        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, k, 2 * N1)) = re_row_hi;        // hi * T1
-        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, k, 2 * N1)) = im_row_hi;
-        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, 64 + k, 2 * N1)) = re_row_hi;   // hi * T2
-        *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, 64 + k, 2 * N1)) = im_row_hi;
-        *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n0, k, 2 * N1)) = re_row_lo;   // lo * T1
-        *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n1, k, 2 * N1)) = im_row_lo;
+      for (int e0 = pt; e0 < n_el; e0 += 5 * 128) {
+#pragma unroll
+        for (int u = 0; u < 5; ++u) if (e0 + u * 128 < n_el) y[u] = __ldg(src + e0 + u * 128);
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int e = e0 + u * 128;
+          if (e < n_el) {
+            const int q = e / KX, kx = e - q * KX;
+            uint32_t hi, lo;                         // (re | im << 16)
+            split2_bf16(y[u].x, y[u].y, hi, lo);
+            const uint32_t re_row_hi = hi ^ 0x80000000u, im_row_hi = __byte_perm(hi, 0, 0x1032);   // (re, -im) ; (im, re)
+            const uint32_t re_row_lo = lo ^ 0x80000000u, im_row_lo = __byte_perm(lo, 0, 0x1032);
+            const int n0 = 2 * kx, n1 = 2 * kx + 1, k = 2 * q;
+            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, k, 2 * N1)) = re_row_hi;        // hi * T1
+            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, k, 2 * N1)) = im_row_hi;
+            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, 64 + k, 2 * N1)) = re_row_hi;   // hi * T2
+            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, 64 + k, 2 * N1)) = im_row_hi;
+            *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n0, k, 2 * N1)) = re_row_lo;   // lo * T1
+            *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n1, k, 2 * N1)) = im_row_lo;
+          }
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_ba_full[buf]);
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ MMA issuer
+    // ------------------------------------------------------------------ stage-A MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_a = idesc_bf16(128, 2 * N1), idesc_b = idesc_bf16(128, W);
-      const uint32_t a_aa = smem_u32(s_aa), a_ba = smem_u32(s_ba), a_u = smem_u32(s_u), a_bb = smem_u32(s_bb);
-      auto stage_b = [&](int j) {
-        const int buf = j & 1;
-        const uint32_t ph = (uint32_t)((j >> 1) & 1);
-        mbar_wait(&bar_u_full[buf], ph);
-        mbar_wait(&bar_db_empty[buf], ph ^ 1u);
-        tc_fence_after_sync();
-        const uint32_t u_hi = a_u + buf * U_BYTES, u_lo = u_hi + FA_SLAB_BYTES;
-        const uint32_t t1 = a_bb, t2 = a_bb + (uint32_t)W * 128;
-#pragma unroll
-        for (int ks = 0; ks < N1 / 16; ++ks) {
-          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, ks > 0);
-          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_lo + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, true);
-          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t2 + ks * 32), idesc_b, true);
-        }
-        mma_commit(&bar_u_empty[buf]);
-        mma_commit(&bar_db_full[buf]);
-      };
+      const uint32_t idesc_a = idesc_bf16(128, 2 * N1);
+      const uint32_t a_aa = smem_u32(s_aa), a_ba = smem_u32(s_ba);
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
@@ -460,9 +450,31 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
         }
         mma_commit(&bar_ba_empty[buf]);
         mma_commit(&bar_da_full[buf]);
-        if (i >= 1) stage_b(i - 1);
       }
-      if (n_local >= 1) stage_b(n_local - 1);
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ stage-B MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_b = idesc_bf16(128, W);
+      const uint32_t a_u = smem_u32(s_u), a_bb = smem_u32(s_bb);
+      const uint32_t t1 = a_bb, t2 = a_bb + (uint32_t)W * 128;
+      for (int i = 0; i < n_local; ++i) {
+        const int buf = i & 1;
+        const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        mbar_wait(&bar_u_full[buf], ph);
+        mbar_wait(&bar_db_empty[buf], ph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t u_hi = a_u + buf * U_BYTES, u_lo = u_hi + FA_SLAB_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < N1 / 16; ++ks) {
+          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, ks > 0);
+          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_lo + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, true);
+          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t2 + ks * 32), idesc_b, true);
+        }
+        mma_commit(&bar_u_empty[buf]);
+        mma_commit(&bar_db_full[buf]);
+      }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -474,40 +486,27 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       const int buf = i & 1;
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
       mbar_wait(&bar_da_full[buf], ph);
+      mbar_wait(&bar_u_empty[buf], ph ^ 1u);
       tc_fence_after_sync();
-      float u[N1];
+      uint8_t* uhi = s_u + buf * U_BYTES + row * 128;
+      uint8_t* ulo = uhi + FA_SLAB_BYTES;
 #pragma unroll
-      for (int c = 0; c < 2 * N1; c += 16) {
-        float t[16];
-        tmem_ld16(tm_da[buf] + lane_sel + c, t);
+      for (int c = 0; c < N1; c += 16) {
+        float t1[16], t2[16];
+        tmem_ld16(tm_da[buf] + lane_sel + c, t1);
+        tmem_ld16(tm_da[buf] + lane_sel + N1 + c, t2);
         tmem_ld_wait();
+        uint32_t hw[8], lw[8];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int col = c + e;
-          if (col < N1) u[col] = t[e];
-          else u[col - N1] += t[e];
-        }
+        for (int e = 0; e < 8; ++e) split2_bf16(t1[2 * e] + t2[2 * e], t1[2 * e + 1] + t2[2 * e + 1], hw[e], lw[e]);
+        const int c0 = c / 8;                          // two 16-byte chunks of 8 consecutive j
+        *reinterpret_cast<uint4*>(uhi + (((c0 ^ row) & 7) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(uhi + ((((c0 + 1) ^ row) & 7) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        *reinterpret_cast<uint4*>(ulo + (((c0 ^ row) & 7) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        *reinterpret_cast<uint4*>(ulo + ((((c0 + 1) ^ row) & 7) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
       }
       tc_fence_before_sync();
       mbar_arrive(&bar_da_empty[buf]);
-      mbar_wait(&bar_u_empty[buf], ph ^ 1u);
-      uint8_t* uhi = s_u + buf * U_BYTES;
-      uint8_t* ulo = uhi + FA_SLAB_BYTES;
-#pragma unroll
-      for (int c = 0; c < N1 / 8; ++c) {          // one 16-byte chunk = 8 consecutive j
-        uint32_t hw[4], lw[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float h0, l0, h1, l1;
-          split_bf16(u[c * 8 + 2 * e], h0, l0);
-          split_bf16(u[c * 8 + 2 * e + 1], h1, l1);
-          hw[e] = pack_bf16(h0, h1);
-          lw[e] = pack_bf16(l0, l1);
-        }
-        const uint32_t off = (uint32_t)(row * 128 + (((c ^ row) & 7) << 4));
-        *reinterpret_cast<uint4*>(uhi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(ulo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      }
       fence_proxy_async_smem();
       mbar_arrive(&bar_u_full[buf]);
     }
@@ -527,17 +526,18 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       float* dst = P.out + ((size_t)tile * 128 + row) * W;
       mbar_wait(&bar_db_full[buf], ph);
       tc_fence_after_sync();
-      for (int c = 0; c < W; c += 32) {
-        float t0[16], t1[16];
-        tmem_ld16(tm_db[buf] + lane_sel + c, t0);
-        tmem_ld16(tm_db[buf] + lane_sel + c + 16, t1);
+      for (int c = 0; c < W; c += 64) {
+        float t[4][16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tmem_ld16(tm_db[buf] + lane_sel + c + 16 * u, t[u]);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) { t0[e] += b; t1[e] += b; }
-        st_global_v8(dst + c, t0);
-        st_global_v8(dst + c + 8, t0 + 8);
-        st_global_v8(dst + c + 16, t1);
-        st_global_v8(dst + c + 24, t1 + 8);
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) t[u][e] += b;
+          st_global_v8(dst + c + 16 * u, t[u]);
+          st_global_v8(dst + c + 16 * u + 8, t[u] + 8);
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(&bar_db_empty[buf]);
@@ -616,24 +616,24 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   if (W % 64 != 0 || W > 128 || H < 16 || 128 % H != 0) return true;
   const int G = 128 / H;
   const int N1 = ((2 * KX + 15) / 16) * 16;
-  if (N1 > 96 || G * KY > 32 || KX < 1 || KY < 1) return true;
+  if (N1 > 80 || G * KY > 32 || KX < 1 || KY < 1) return true;
   t->W = W; t->H = H; t->G = G; t->N1 = N1; t->KX = KX; t->KY = KY; t->slabs = W / 64;
-  t->tmem_cols = 5 * N1 <= 256 ? 256 : 512;
+  t->tmem_cols = 6 * N1 <= 256 ? 256 : 512;
   // ---- B1: [2*N1 x W]
   std::vector<uint8_t> b1((size_t)2 * N1 * W * 2, 0);
   for (int j = 0; j < 2 * KX; ++j)
     for (int w = 0; w < W; ++w) put_split(b1, 2 * N1, j, N1 + j, w, tab[(size_t)w * 2 * KX + j]);
-  // ---- A2: [128 x 256]; row i' = 2*(g*KY + ky) + p_out (T1), 64 + i' (T2); column k2 = p_in*128 + g*H + h
+  // ---- A2: [128 x 256]; row i' = 2*(g*KY + ky) + p_out (T1), 64 + i' (T2); column k2 = 2*(g*H + h) + p_in
   std::vector<uint8_t> a2((size_t)128 * 256 * 2, 0);
   for (int g = 0; g < G; ++g)
     for (int ky = 0; ky < KY; ++ky)
       for (int h = 0; h < H; ++h) {
         const float2 f = lead[(size_t)ky * H + h];
         const int q = g * KY + ky, hl = g * H + h;
-        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 0 * 128 + hl, f.x);
-        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 1 * 128 + hl, -f.y);
-        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 0 * 128 + hl, f.y);
-        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 1 * 128 + hl, f.x);
+        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 2 * hl + 0, f.x);
+        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 2 * hl + 1, -f.y);
+        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 2 * hl + 0, f.y);
+        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 2 * hl + 1, f.x);
       }
   if (!upload_bytes(p, b1, &t->d_b1) || !upload_bytes(p, a2, &t->d_a2)) return false;
   // ---- shared-memory carve-up
@@ -752,7 +752,7 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
     }                                                                                                            \
     k_fused_analysis<N><<<grid, FA_THREADS, t.smem_bytes, st>>>(P);                                              \
   } break;
-    SC_FA_CASE(16) SC_FA_CASE(32) SC_FA_CASE(48) SC_FA_CASE(64) SC_FA_CASE(80) SC_FA_CASE(96)
+    SC_FA_CASE(16) SC_FA_CASE(32) SC_FA_CASE(48) SC_FA_CASE(64) SC_FA_CASE(80)
 #undef SC_FA_CASE
     default: set_error("fast_analyze: unsupported N1"); return false;
   }

@@ -131,5 +131,24 @@ __device__ __forceinline__ void split_bf16(float x, float& hi_f, float& lo_f) {
   lo_f = x - hi_f;
 }
 
+// (x0, x1) -> packed bf16 pairs hi = (hi0 | hi1 << 16), lo likewise, with x = hi + lo + O(2^-17 |x|)
+__device__ __forceinline__ void split2_bf16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16(x0, x1);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  lo = pack_bf16(x0 - h0, x1 - h1);
+}
+
+// global -> shared byte copy of a constant operand image (16-byte units), 4 independent loads in flight per thread
+__device__ __forceinline__ void copy_image(uint8_t* dst, const uint8_t* src, int n_vec, int tid, int nthreads) {
+  const uint4* g = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  int i = tid;
+  for (; i + 3 * nthreads < n_vec; i += 4 * nthreads) {
+    const uint4 a = __ldg(g + i), b = __ldg(g + i + nthreads), c = __ldg(g + i + 2 * nthreads), e = __ldg(g + i + 3 * nthreads);
+    d[i] = a; d[i + nthreads] = b; d[i + 2 * nthreads] = c; d[i + 3 * nthreads] = e;
+  }
+  for (; i < n_vec; i += nthreads) d[i] = __ldg(g + i);
+}
+
 }  // namespace umma
 }  // namespace sc
