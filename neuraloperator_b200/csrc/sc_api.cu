@@ -271,6 +271,9 @@ static bool synthesize(const Plan* p, const float2* modes_in, int64_t n_images, 
 static bool contract_fwd(const Plan* p, const float2* xm, const float2* w, float2* ym, int B, int Ci, int Co,
                          cudaStream_t st) {
   const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
+  if (p->fast_enabled && fast_can_contract(p, B, Ci, Co))   // ym^T[o, b] = sum_i w[i, o] * xm[b, i]
+    return launch_mode_gemm_tc(p, w, Wp, (long long)Co * Wp, p->d_woff, false, xm, (long long)Ci * Mt, Mt, nullptr, ym, Mt,
+                               (long long)Co * Mt, nullptr, Co, B, Ci, Mt, st);
   ModeGemmOperand a{xm, (int64_t)Ci * Mt, Mt, nullptr};
   ModeGemmOperand b{w, (int64_t)Co * Wp, Wp, p->d_woff};
   ModeGemmOperand o{ym, (int64_t)Co * Mt, Mt, nullptr};
@@ -280,10 +283,25 @@ static bool contract_fwd(const Plan* p, const float2* xm, const float2* w, float
 static bool contract_bwd(const Plan* p, const float2* xm, const float2* gm, const float2* w, float2* dxm,
                          float2* dw, float* dbias, int B, int Ci, int Co, cudaStream_t st) {
   const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
-  if (dw != nullptr) {
-    if (!p->weight_block_is_whole &&
-        !cuda_ok(cudaMemsetAsync(dw, 0, (size_t)Ci * Co * Wp * sizeof(float2), st), "cudaMemsetAsync(dweight)"))
+  const bool tc = p->fast_enabled && fast_can_contract(p, B, Ci, Co);
+  if (dw != nullptr && !p->weight_block_is_whole &&
+      !cuda_ok(cudaMemsetAsync(dw, 0, (size_t)Ci * Co * Wp * sizeof(float2), st), "cudaMemsetAsync(dweight)"))
+    return false;
+  if (tc) {
+    // dweight[i, o] = sum_b conj(xm[b, i]) * gm[b, o]
+    if (dw != nullptr &&
+        !launch_mode_gemm_tc(p, xm, Mt, (long long)Ci * Mt, nullptr, true, gm, Mt, (long long)Co * Mt, nullptr, dw,
+                             (long long)Co * Wp, Wp, p->d_woff, Ci, Co, B, Mt, st))
       return false;
+    if (dbias != nullptr && !launch_bias_grad(gm, dbias, B, Co, Mt, p->dc_slot, (float)(1.0 / p->s_inv), st)) return false;
+    // dxm^T[i, b] = sum_o conj(w[i, o]) * gm[b, o]
+    if (dxm != nullptr &&
+        !launch_mode_gemm_tc(p, w, (long long)Co * Wp, Wp, p->d_woff, true, gm, (long long)Co * Mt, Mt, nullptr, dxm, Mt,
+                             (long long)Ci * Mt, nullptr, Ci, B, Co, Mt, st))
+      return false;
+    return true;
+  }
+  if (dw != nullptr) {
     ModeGemmOperand a{xm, Mt, (int64_t)Ci * Mt, nullptr};          // r = i, k = b
     ModeGemmOperand b{gm, (int64_t)Co * Mt, Mt, nullptr};          // k = b, c = o
     ModeGemmOperand o{dw, (int64_t)Co * Wp, Wp, p->d_woff};

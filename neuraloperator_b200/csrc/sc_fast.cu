@@ -549,6 +549,227 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
   if (warp == 8) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
 }
 
+// =====================================================================================================
+// mode-wise complex GEMM on tcgen05 (dense contraction and its two backward products)
+//
+//   out[R, n] = sum_k a(R, k) * b(n, k)   (complex), one independent product per kept mode m.
+//   The complex product is a real GEMM with the 2x2 embedding on the A side:
+//     rows (R, re|im) x K (k, re|im):   [ ar  -ai ]        B rows n, K (k, re|im) = (br, bi) as stored
+//                                       [ ai   ar ]
+//   A = A_hi + A_lo and B = B_hi + B_lo in bf16; D = A_hi*[B_hi ; B_lo] + A_lo*B_hi  (FP32 in TMEM).
+//   warps 0-3 epilogue, warp 4 MMA issuer (+TMEM), warps 5-12 gather/split loaders.
+// =====================================================================================================
+constexpr int MG2_THREADS = 13 * 32;
+constexpr int MG2_LOADERS = 256;
+
+struct ModeGemmTcParams {
+  const float2* a; const float2* b; float2* out;
+  long long sAR, sAK, sBN, sBK, sOR, sON;          // complex-element strides
+  const int* offA; const int* offB; const int* offO;   // per-mode offsets (nullptr -> m)
+  int MR, NB, KC;                                   // complex rows of A (<= 64), rows of B (<= 64), contraction length
+  int NBp;                                          // NB rounded up to a multiple of 16
+  int Kreal;                                        // 2 * KC rounded up to a multiple of 64
+  int conjA;
+  int n_modes;
+  uint32_t stage_bytes, off_alo, off_b;
+};
+
+__global__ void __launch_bounds__(MG2_THREADS, 1) k_mode_gemm_tc(const ModeGemmTcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_full[2], bar_empty[2], bar_d_full[2], bar_d_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_full[i], 8); mbar_init(&bar_empty[i], 1);
+      mbar_init(&bar_d_full[i], 1); mbar_init(&bar_d_empty[i], 128);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 4) tmem_alloc(&tmem_base_slot, 256);
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);      // padding rows / columns of both stages stay zero
+    for (int i = tid; i < (int)(2 * P.stage_bytes / 16); i += MG2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const int n_local = (P.n_modes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int rowsB = 2 * P.NBp;
+
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ gather + split loaders
+    const int lt = tid - 5 * 32;
+    const int nA = P.MR * P.KC, nB = P.NB * P.KC;
+    for (int it = 0; it < n_local; ++it) {
+      const int m = (int)blockIdx.x + it * (int)gridDim.x;
+      const int st = it & 1;
+      const long long ma = P.offA ? (long long)__ldg(P.offA + m) : m;
+      const long long mb = P.offB ? (long long)__ldg(P.offB + m) : m;
+      uint8_t* a_hi = smem + (size_t)st * P.stage_bytes;
+      uint8_t* a_lo = a_hi + P.off_alo;
+      uint8_t* b_op = a_hi + P.off_b;
+      mbar_wait(&bar_empty[st], (uint32_t)(((it >> 1) & 1) ^ 1));
+      // A operand
+      for (int e0 = lt; e0 < nA; e0 += 8 * MG2_LOADERS) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * MG2_LOADERS;
+          if (e < nA) { const int R = e / P.KC, k = e - R * P.KC; v[u] = __ldg(P.a + ma + R * P.sAR + k * P.sAK); }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * MG2_LOADERS;
+          if (e < nA) {
+            const int R = e / P.KC, k = e - R * P.KC;
+            uint32_t hi, lo;
+            split2_bf16(v[u].x, v[u].y, hi, lo);                 // (re | im << 16)
+            uint32_t r0h, r1h, r0l, r1l;
+            if (P.conjA) {   // a = conj(v): row re = (vr, vi), row im = (-vi, vr)
+              r0h = hi; r1h = __byte_perm(hi, 0, 0x1032) ^ 0x00008000u;
+              r0l = lo; r1l = __byte_perm(lo, 0, 0x1032) ^ 0x00008000u;
+            } else {         // a = v:       row re = (vr, -vi), row im = (vi, vr)
+              r0h = hi ^ 0x80000000u; r1h = __byte_perm(hi, 0, 0x1032);
+              r0l = lo ^ 0x80000000u; r1l = __byte_perm(lo, 0, 0x1032);
+            }
+            const uint32_t o0 = sw128_offset(2 * R, 2 * k, 128), o1 = sw128_offset(2 * R + 1, 2 * k, 128);
+            *reinterpret_cast<uint32_t*>(a_hi + o0) = r0h; *reinterpret_cast<uint32_t*>(a_hi + o1) = r1h;
+            *reinterpret_cast<uint32_t*>(a_lo + o0) = r0l; *reinterpret_cast<uint32_t*>(a_lo + o1) = r1l;
+          }
+        }
+      }
+      // B operand: rows n (hi) and NBp + n (lo)
+      for (int e0 = lt; e0 < nB; e0 += 8 * MG2_LOADERS) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * MG2_LOADERS;
+          if (e < nB) { const int n = e / P.KC, k = e - n * P.KC; v[u] = __ldg(P.b + mb + n * P.sBN + k * P.sBK); }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * MG2_LOADERS;
+          if (e < nB) {
+            const int n = e / P.KC, k = e - n * P.KC;
+            uint32_t hi, lo;
+            split2_bf16(v[u].x, v[u].y, hi, lo);
+            *reinterpret_cast<uint32_t*>(b_op + sw128_offset(n, 2 * k, rowsB)) = hi;
+            *reinterpret_cast<uint32_t*>(b_op + sw128_offset(P.NBp + n, 2 * k, rowsB)) = lo;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[st]);
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc1 = idesc_bf16(128, rowsB), idesc2 = idesc_bf16(128, P.NBp);
+      for (int it = 0; it < n_local; ++it) {
+        const int st = it & 1;
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&bar_full[st], ph);
+        mbar_wait(&bar_d_empty[st], ph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t a_hi = smem_u32(smem + (size_t)st * P.stage_bytes), a_lo = a_hi + P.off_alo, b_op = a_hi + P.off_b;
+        const uint32_t d = tmem + (uint32_t)(st * 128);
+        const int ksteps = P.Kreal / 16;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const int slab = ks >> 2, kk = ks & 3;
+          const uint64_t db = smem_desc_sw128(b_op + slab * (rowsB * 128) + kk * 32);
+          mma_bf16_ss(d, smem_desc_sw128(a_hi + slab * (128 * 128) + kk * 32), db, idesc1, ks > 0);
+          mma_bf16_ss(d, smem_desc_sw128(a_lo + slab * (128 * 128) + kk * 32), db, idesc2, true);
+        }
+        mma_commit(&bar_empty[st]);
+        mma_commit(&bar_d_full[st]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int row = warp * 32 + lane;                // real row (R, part)
+    const int R = row >> 1, part = row & 1;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    for (int it = 0; it < n_local; ++it) {
+      const int m = (int)blockIdx.x + it * (int)gridDim.x;
+      const int st = it & 1;
+      const long long mo = P.offO ? (long long)__ldg(P.offO + m) : m;
+      mbar_wait(&bar_d_full[st], (uint32_t)((it >> 1) & 1));
+      tc_fence_after_sync();
+      const uint32_t d = tmem + (uint32_t)(st * 128) + lane_sel;
+      float2* dst = P.out + mo + (long long)R * P.sOR;
+      for (int c = 0; c < P.NBp; c += 8) {           // hi block [0, NBp), lo block [NBp, 2*NBp)
+        float t1[8], t2[8];
+        tmem_ld8(d + c, t1);
+        tmem_ld8(d + P.NBp + c, t2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int n = c + e;
+          const float mine = t1[e] + t2[e];
+          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          if (part == 0 && R < P.MR && n < P.NB) dst[(long long)n * P.sON] = make_float2(mine, other);
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bar_d_empty[st]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, 256);
+}
+
+static int fast_sm_count(const Plan* p);   // defined with FastTables below
+
+static bool mode_gemm_tc_supported(int MR, int NB, int KC) {
+  return MR >= 1 && MR <= 64 && NB >= 1 && NB <= 64 && KC >= 1 && KC <= 64;
+}
+
+bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long long sAK, const int* offA, bool conjA,
+                         const float2* b, long long sBN, long long sBK, const int* offB, float2* out, long long sOR,
+                         long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st) {
+  ModeGemmTcParams P{};
+  P.a = a; P.b = b; P.out = out;
+  P.sAR = sAR; P.sAK = sAK; P.sBN = sBN; P.sBK = sBK; P.sOR = sOR; P.sON = sON;
+  P.offA = offA; P.offB = offB; P.offO = offO;
+  P.MR = MR; P.NB = NB; P.KC = KC;
+  P.NBp = (NB + 15) / 16 * 16;   // N of an M=128 MMA must be a multiple of 16
+  P.Kreal = (2 * KC + 63) / 64 * 64;
+  P.conjA = conjA ? 1 : 0;
+  P.n_modes = (int)n_modes;
+  const uint32_t a_bytes = 128u * (uint32_t)P.Kreal * 2u;
+  const uint32_t b_bytes = 2u * (uint32_t)P.NBp * (uint32_t)P.Kreal * 2u;
+  P.off_alo = a_bytes;
+  P.off_b = 2 * a_bytes;
+  P.stage_bytes = (2 * a_bytes + b_bytes + 1023u) & ~1023u;
+  const uint32_t smem_bytes = 2 * P.stage_bytes + 1024u;
+  static uint32_t attr_bytes = 0;
+  if (attr_bytes < smem_bytes) {
+    if (!cuda_ok(cudaFuncSetAttribute(k_mode_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                 "cudaFuncSetAttribute(k_mode_gemm_tc)"))
+      return false;
+    attr_bytes = smem_bytes;
+  }
+  const int sms = fast_sm_count(p);
+  const int grid = n_modes < sms ? (int)n_modes : sms;
+  k_mode_gemm_tc<<<grid, MG2_THREADS, smem_bytes, st>>>(P);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_mode_gemm_tc launch");
+}
+
+bool fast_can_contract(const Plan* p, int B, int Ci, int Co) {
+  return p->fast != nullptr && mode_gemm_tc_supported(Co, B, Ci) && mode_gemm_tc_supported(Ci, B, Co) &&
+         mode_gemm_tc_supported(Ci, Co, B);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: operand images and dispatch
 // ---------------------------------------------------------------------------------------------------------
@@ -573,6 +794,8 @@ struct FastTables {
   FusedSynthesisTables syn[2];  // [0] forward synthesis onto `out_grid`, [1] adjoint-of-analysis synthesis onto `grid`
   int sm_count = 0;
 };
+
+static int fast_sm_count(const Plan* p) { return p->fast->sm_count; }
 
 static inline uint16_t bf16_bits(float f) {   // round to nearest even
   uint32_t u;
@@ -702,12 +925,12 @@ static bool build_fused_synthesis(Plan* p, FusedSynthesisTables* t, int H, int W
 
 bool fast_plan_init(Plan* p) {
   p->fast = nullptr;
-  if (p->d < 2) return true;
   cudaDeviceProp prop{};
   if (!cuda_ok(cudaGetDeviceProperties(&prop, p->device), "cudaGetDeviceProperties")) return false;
   if (prop.major != 10) return true;   // tcgen05 path is sm_100-only
   FastTables* f = new FastTables();
   f->sm_count = prop.multiProcessorCount;
+  if (p->d < 2) { p->fast = f; return true; }   // only the tensor-core contraction applies to 1-D problems
   const DimTables& L = p->dim[p->d - 1];
   const DimTables& Y = p->dim[p->d - 2];
   bool good = build_fused_analysis(p, &f->ana[0], Y.N, L.N, Y.k, L.k, p->h_TA, Y.h_A) &&

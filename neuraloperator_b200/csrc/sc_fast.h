@@ -16,6 +16,11 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
 bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
                      float* images_out, bool adjoint, cudaStream_t st);
 
+bool fast_can_contract(const Plan* p, int B, int Ci, int Co);
+// out[R, n] (+ per-mode offset) = sum_k a(R, k) * b(n, k), complex, one product per kept mode, on tcgen05 (bf16x3)
+bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long long sAK, const int* offA, bool conjA,
+                         const float2* b, long long sBN, long long sBK, const int* offB, float2* out, long long sOR,
+                         long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st);
 bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
 
 }  // namespace sc
