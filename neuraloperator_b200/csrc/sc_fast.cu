@@ -135,16 +135,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     mbar_init_fence();
   }
   if (warp == 8) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
-  copy_image(s_b1, P.b1_img, (2 * N1 * P.W * 2) / 16, tid, FA_THREADS);
-  copy_image(s_a2, P.a2_img, (128 * 256 * 2) / 16, tid, FA_THREADS);
-  {
-    uint4* z = reinterpret_cast<uint4*>(s_b2);   // padding rows of B2 (kx >= KX) stay zero for the whole kernel
-    for (int i = tid; i < (N1 * 512) / 16; i += FA_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-  }
-  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if (warp < FA_LOADER_WARP0) {
+    // constant operand images are staged by the consumer-side warps only; the loaders start streaming x at once
+    constexpr int NT = FA_LOADER_WARP0 * 32;
+    copy_image(s_b1, P.b1_img, (2 * N1 * P.W * 2) / 16, tid, NT);
+    copy_image(s_a2, P.a2_img, (128 * 256 * 2) / 16, tid, NT);
+    uint4* z = reinterpret_cast<uint4*>(s_b2);   // padding rows of B2 (kx >= KX) stay zero for the whole kernel
+    for (int i = tid; i < (N1 * 512) / 16; i += NT) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+  }
   const uint32_t tmem = tmem_base_slot;
   const uint32_t tm_d1[2] = {tmem, tmem + (uint32_t)(2 * N1)};
   const uint32_t tm_d2[2] = {tmem + (uint32_t)(4 * N1), tmem + (uint32_t)(5 * N1)};
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // ------------------------------------------------------------------ stage-1 MMA issuer
     if (lane == 0) {
       const uint32_t idesc_p1 = idesc_bf16(128, 2 * N1), idesc_p2 = idesc_bf16(128, N1);
-      const uint32_t a_b1 = smem_u32(s_b1);
+      const uint32_t b1_lo = desc_lo(smem_u32(s_b1)), ring_lo = desc_lo(smem_u32(smem));
       uint32_t g = 0;
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
@@ -204,12 +207,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
           const int slot = (int)(g % (uint32_t)NS);
           mbar_wait(&bar_full[slot], (g / (uint32_t)NS) & 1u);
           tc_fence_after_sync();
-          const uint32_t a_hi = smem_u32(smem + (size_t)slot * FA_STAGE_BYTES), a_lo = a_hi + FA_SLAB_BYTES;
-          const uint32_t b_sl = a_b1 + s * (2 * N1 * 128);
+          const uint32_t d_hi = ring_lo + (uint32_t)slot * (FA_STAGE_BYTES >> 4), d_lo = d_hi + (FA_SLAB_BYTES >> 4);
+          const uint32_t d_b = b1_lo + (uint32_t)s * ((2 * N1 * 128) >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            mma_bf16_ss(tm_d1[buf], smem_desc_sw128(a_hi + kk * 32), smem_desc_sw128(b_sl + kk * 32), idesc_p1, (s | kk) != 0);
-            mma_bf16_ss(tm_d1[buf], smem_desc_sw128(a_lo + kk * 32), smem_desc_sw128(b_sl + kk * 32), idesc_p2, true);
+            mma_bf16_ss(tm_d1[buf], desc_from_lo(d_hi + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p1, (s | kk) != 0);
+            mma_bf16_ss(tm_d1[buf], desc_from_lo(d_lo + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p2, true);
           }
           mma_commit(&bar_empty[slot]);
         }
@@ -221,17 +224,17 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // ------------------------------------------------------------------ stage-2 MMA issuer
     if (lane == 0) {
       const uint32_t idesc_p2 = idesc_bf16(128, N1);
-      const uint32_t a_a2 = smem_u32(s_a2), a_b2 = smem_u32(s_b2);
+      const uint32_t a2_lo = desc_lo(smem_u32(s_a2)), b2_lo = desc_lo(smem_u32(s_b2));
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         mbar_wait(&bar_b2_full, (uint32_t)(i & 1));
         mbar_wait(&bar_d2_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
         tc_fence_after_sync();
-#pragma unroll 4
+#pragma unroll
         for (int ks = 0; ks < 16; ++ks) {
           const int slab = ks >> 2, kk = ks & 3;
-          mma_bf16_ss(tm_d2[buf], smem_desc_sw128(a_a2 + slab * (128 * 128) + kk * 32),
-                      smem_desc_sw128(a_b2 + slab * (N1 * 128) + kk * 32), idesc_p2, ks > 0);
+          mma_bf16_ss(tm_d2[buf], desc_from_lo(a2_lo + slab * ((128 * 128) >> 4) + 2 * kk),
+                      desc_from_lo(b2_lo + slab * ((N1 * 128) >> 4) + 2 * kk), idesc_p2, ks > 0);
         }
         mma_commit(&bar_b2_empty);
         mma_commit(&bar_d2_full[buf]);
@@ -434,19 +437,19 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     // ------------------------------------------------------------------ stage-A MMA issuer
     if (lane == 0) {
       const uint32_t idesc_a = idesc_bf16(128, 2 * N1);
-      const uint32_t a_aa = smem_u32(s_aa), a_ba = smem_u32(s_ba);
+      const uint32_t aa_lo = desc_lo(smem_u32(s_aa)), ba_lo0 = desc_lo(smem_u32(s_ba));
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
         mbar_wait(&bar_ba_full[buf], ph);
         mbar_wait(&bar_da_empty[buf], ph ^ 1u);
         tc_fence_after_sync();
-        const uint32_t ba = a_ba + buf * BA_BYTES;
+        const uint32_t ba_lo = ba_lo0 + (uint32_t)buf * (BA_BYTES >> 4);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           const int slab = ks >> 2, kk = ks & 3;
-          mma_bf16_ss(tm_da[buf], smem_desc_sw128(a_aa + slab * (128 * 128) + kk * 32),
-                      smem_desc_sw128(ba + slab * (2 * N1 * 128) + kk * 32), idesc_a, ks > 0);
+          mma_bf16_ss(tm_da[buf], desc_from_lo(aa_lo + slab * ((128 * 128) >> 4) + 2 * kk),
+                      desc_from_lo(ba_lo + slab * ((2 * N1 * 128) >> 4) + 2 * kk), idesc_a, ks > 0);
         }
         mma_commit(&bar_ba_empty[buf]);
         mma_commit(&bar_da_full[buf]);
@@ -457,20 +460,20 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     // ------------------------------------------------------------------ stage-B MMA issuer
     if (lane == 0) {
       const uint32_t idesc_b = idesc_bf16(128, W);
-      const uint32_t a_u = smem_u32(s_u), a_bb = smem_u32(s_bb);
-      const uint32_t t1 = a_bb, t2 = a_bb + (uint32_t)W * 128;
+      const uint32_t u_lo0 = desc_lo(smem_u32(s_u));
+      const uint32_t t1 = desc_lo(smem_u32(s_bb)), t2 = t1 + (((uint32_t)W * 128) >> 4);
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
         mbar_wait(&bar_u_full[buf], ph);
         mbar_wait(&bar_db_empty[buf], ph ^ 1u);
         tc_fence_after_sync();
-        const uint32_t u_hi = a_u + buf * U_BYTES, u_lo = u_hi + FA_SLAB_BYTES;
+        const uint32_t u_hi = u_lo0 + (uint32_t)buf * (U_BYTES >> 4), u_lo = u_hi + (FA_SLAB_BYTES >> 4);
 #pragma unroll
         for (int ks = 0; ks < N1 / 16; ++ks) {
-          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, ks > 0);
-          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_lo + ks * 32), smem_desc_sw128(t1 + ks * 32), idesc_b, true);
-          mma_bf16_ss(tm_db[buf], smem_desc_sw128(u_hi + ks * 32), smem_desc_sw128(t2 + ks * 32), idesc_b, true);
+          mma_bf16_ss(tm_db[buf], desc_from_lo(u_hi + 2 * ks), desc_from_lo(t1 + 2 * ks), idesc_b, ks > 0);
+          mma_bf16_ss(tm_db[buf], desc_from_lo(u_lo + 2 * ks), desc_from_lo(t1 + 2 * ks), idesc_b, true);
+          mma_bf16_ss(tm_db[buf], desc_from_lo(u_hi + 2 * ks), desc_from_lo(t2 + 2 * ks), idesc_b, true);
         }
         mma_commit(&bar_u_empty[buf]);
         mma_commit(&bar_db_full[buf]);
@@ -557,10 +560,13 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
 //     rows (R, re|im) x K (k, re|im):   [ ar  -ai ]        B rows n, K (k, re|im) = (br, bi) as stored
 //                                       [ ai   ar ]
 //   A = A_hi + A_lo and B = B_hi + B_lo in bf16; D = A_hi*[B_hi ; B_lo] + A_lo*B_hi  (FP32 in TMEM).
-//   warps 0-3 epilogue, warp 4 MMA issuer (+TMEM), warps 5-12 gather/split loaders.
+//   warps 0-3 epilogue, warp 4 MMA issuer (+TMEM), warps 5-20 gather/split loaders.
+//   A CTA owns a CONTIGUOUS range of modes: the 8-byte gathers of 4 consecutive modes share 32-byte sectors, so the
+//   sectors fetched for the first mode of a range are L2 hits for the next three.
 // =====================================================================================================
-constexpr int MG2_THREADS = 13 * 32;
-constexpr int MG2_LOADERS = 256;
+constexpr int MG2_LOADER_WARPS = 16;
+constexpr int MG2_THREADS = (5 + MG2_LOADER_WARPS) * 32;
+constexpr int MG2_LOADERS = MG2_LOADER_WARPS * 32;
 
 struct ModeGemmTcParams {
   const float2* a; const float2* b; float2* out;
@@ -569,8 +575,9 @@ struct ModeGemmTcParams {
   int MR, NB, KC;                                   // complex rows of A (<= 64), rows of B (<= 64), contraction length
   int NBp;                                          // NB rounded up to a multiple of 16
   int Kreal;                                        // 2 * KC rounded up to a multiple of 64
+  int KCp, kshift;                                  // KC rounded up to a power of two (>= 8), and its log2
   int conjA;
-  int n_modes;
+  int n_modes, modes_per_cta;
   uint32_t stage_bytes, off_alo, off_b;
 };
 
@@ -583,7 +590,7 @@ __global__ void __launch_bounds__(MG2_THREADS, 1) k_mode_gemm_tc(const ModeGemmT
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_full[i], 8); mbar_init(&bar_empty[i], 1);
+      mbar_init(&bar_full[i], MG2_LOADER_WARPS); mbar_init(&bar_empty[i], 1);
       mbar_init(&bar_d_full[i], 1); mbar_init(&bar_d_empty[i], 128);
     }
     mbar_init_fence();
@@ -598,69 +605,67 @@ __global__ void __launch_bounds__(MG2_THREADS, 1) k_mode_gemm_tc(const ModeGemmT
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_slot;
-  const int n_local = (P.n_modes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int m_begin = (int)blockIdx.x * P.modes_per_cta;
+  const int n_local = min(P.modes_per_cta, P.n_modes - m_begin);
   const int rowsB = 2 * P.NBp;
 
   if (warp >= 5) {
     // ------------------------------------------------------------------ gather + split loaders
+    // thread -> fixed contraction index k, rows r0, r0 + step, ...: all index math is hoisted out of the mode loop and the
+    // per-element work is one 8-byte gather, one bf16 hi/lo split and four (A) / two (B) 4-byte swizzled stores.
     const int lt = tid - 5 * 32;
-    const int nA = P.MR * P.KC, nB = P.NB * P.KC;
+    const int k = lt & (P.KCp - 1);
+    const int r0 = lt >> P.kshift;
+    const int step = MG2_LOADERS >> P.kshift;          // 8, 16, 32 or 64 rows between a thread's elements
+    const bool k_ok = k < P.KC;
+    const long long a_elem0 = (long long)r0 * P.sAR + (long long)k * P.sAK, a_estep = (long long)step * P.sAR;
+    const long long b_elem0 = (long long)r0 * P.sBN + (long long)k * P.sBK, b_estep = (long long)step * P.sBN;
+    // step is a multiple of 8, so (row & 7) -- the swizzle phase -- is the same for all of a thread's rows
+    const uint32_t a_s0 = sw128_offset(2 * r0, 2 * k, 128), a_s1 = sw128_offset(2 * r0 + 1, 2 * k, 128);
+    const uint32_t a_sstep = (uint32_t)step * 256u;
+    const uint32_t b_s0 = sw128_offset(r0, 2 * k, rowsB), b_sstep = (uint32_t)step * 128u, b_lo = (uint32_t)P.NBp * 128u;
     for (int it = 0; it < n_local; ++it) {
-      const int m = (int)blockIdx.x + it * (int)gridDim.x;
+      const int m = m_begin + it;
       const int st = it & 1;
-      const long long ma = P.offA ? (long long)__ldg(P.offA + m) : m;
-      const long long mb = P.offB ? (long long)__ldg(P.offB + m) : m;
+      const float2* pa = P.a + (P.offA ? (long long)__ldg(P.offA + m) : (long long)m) + a_elem0;
+      const float2* pb = P.b + (P.offB ? (long long)__ldg(P.offB + m) : (long long)m) + b_elem0;
       uint8_t* a_hi = smem + (size_t)st * P.stage_bytes;
       uint8_t* a_lo = a_hi + P.off_alo;
       uint8_t* b_op = a_hi + P.off_b;
+      float2 v[8], w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k_ok && r0 + u * step < P.MR) v[u] = __ldg(pa + u * a_estep);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k_ok && r0 + u * step < P.NB) w[u] = __ldg(pb + u * b_estep);
       mbar_wait(&bar_empty[st], (uint32_t)(((it >> 1) & 1) ^ 1));
-      // A operand
-      for (int e0 = lt; e0 < nA; e0 += 8 * MG2_LOADERS) {
-        float2 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * MG2_LOADERS;
-          if (e < nA) { const int R = e / P.KC, k = e - R * P.KC; v[u] = __ldg(P.a + ma + R * P.sAR + k * P.sAK); }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * MG2_LOADERS;
-          if (e < nA) {
-            const int R = e / P.KC, k = e - R * P.KC;
-            uint32_t hi, lo;
-            split2_bf16(v[u].x, v[u].y, hi, lo);                 // (re | im << 16)
-            uint32_t r0h, r1h, r0l, r1l;
-            if (P.conjA) {   // a = conj(v): row re = (vr, vi), row im = (-vi, vr)
-              r0h = hi; r1h = __byte_perm(hi, 0, 0x1032) ^ 0x00008000u;
-              r0l = lo; r1l = __byte_perm(lo, 0, 0x1032) ^ 0x00008000u;
-            } else {         // a = v:       row re = (vr, -vi), row im = (vi, vr)
-              r0h = hi ^ 0x80000000u; r1h = __byte_perm(hi, 0, 0x1032);
-              r0l = lo ^ 0x80000000u; r1l = __byte_perm(lo, 0, 0x1032);
-            }
-            const uint32_t o0 = sw128_offset(2 * R, 2 * k, 128), o1 = sw128_offset(2 * R + 1, 2 * k, 128);
-            *reinterpret_cast<uint32_t*>(a_hi + o0) = r0h; *reinterpret_cast<uint32_t*>(a_hi + o1) = r1h;
-            *reinterpret_cast<uint32_t*>(a_lo + o0) = r0l; *reinterpret_cast<uint32_t*>(a_lo + o1) = r1l;
+      for (int u = 0; u < 8; ++u) {
+        if (k_ok && r0 + u * step < P.MR) {
+          uint32_t hi, lo;
+          split2_bf16(v[u].x, v[u].y, hi, lo);                 // (re | im << 16)
+          uint32_t r0h, r1h, r0l, r1l;
+          if (P.conjA) {   // a = conj(v): row re = (vr, vi), row im = (-vi, vr)
+            r0h = hi; r1h = __byte_perm(hi, 0, 0x1032) ^ 0x00008000u;
+            r0l = lo; r1l = __byte_perm(lo, 0, 0x1032) ^ 0x00008000u;
+          } else {         // a = v:       row re = (vr, -vi), row im = (vi, vr)
+            r0h = hi ^ 0x80000000u; r1h = __byte_perm(hi, 0, 0x1032);
+            r0l = lo ^ 0x80000000u; r1l = __byte_perm(lo, 0, 0x1032);
           }
+          *reinterpret_cast<uint32_t*>(a_hi + a_s0 + u * a_sstep) = r0h;
+          *reinterpret_cast<uint32_t*>(a_hi + a_s1 + u * a_sstep) = r1h;
+          *reinterpret_cast<uint32_t*>(a_lo + a_s0 + u * a_sstep) = r0l;
+          *reinterpret_cast<uint32_t*>(a_lo + a_s1 + u * a_sstep) = r1l;
         }
       }
-      // B operand: rows n (hi) and NBp + n (lo)
-      for (int e0 = lt; e0 < nB; e0 += 8 * MG2_LOADERS) {
-        float2 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * MG2_LOADERS;
-          if (e < nB) { const int n = e / P.KC, k = e - n * P.KC; v[u] = __ldg(P.b + mb + n * P.sBN + k * P.sBK); }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * MG2_LOADERS;
-          if (e < nB) {
-            const int n = e / P.KC, k = e - n * P.KC;
-            uint32_t hi, lo;
-            split2_bf16(v[u].x, v[u].y, hi, lo);
-            *reinterpret_cast<uint32_t*>(b_op + sw128_offset(n, 2 * k, rowsB)) = hi;
-            *reinterpret_cast<uint32_t*>(b_op + sw128_offset(P.NBp + n, 2 * k, rowsB)) = lo;
-          }
+      for (int u = 0; u < 8; ++u) {
+        if (k_ok && r0 + u * step < P.NB) {
+          uint32_t hi, lo;
+          split2_bf16(w[u].x, w[u].y, hi, lo);
+          *reinterpret_cast<uint32_t*>(b_op + b_s0 + u * b_sstep) = hi;          // row n        (hi)
+          *reinterpret_cast<uint32_t*>(b_op + b_s0 + u * b_sstep + b_lo) = lo;   // row NBp + n  (lo)
         }
       }
       fence_proxy_async_smem();
@@ -677,14 +682,17 @@ __global__ void __launch_bounds__(MG2_THREADS, 1) k_mode_gemm_tc(const ModeGemmT
         mbar_wait(&bar_full[st], ph);
         mbar_wait(&bar_d_empty[st], ph ^ 1u);
         tc_fence_after_sync();
-        const uint32_t a_hi = smem_u32(smem + (size_t)st * P.stage_bytes), a_lo = a_hi + P.off_alo, b_op = a_hi + P.off_b;
+        const uint32_t a_hi = desc_lo(smem_u32(smem + (size_t)st * P.stage_bytes)), a_lo = a_hi + (P.off_alo >> 4),
+                       b_op = a_hi + (P.off_b >> 4);
         const uint32_t d = tmem + (uint32_t)(st * 128);
-        const int ksteps = P.Kreal / 16;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int slab = ks >> 2, kk = ks & 3;
-          const uint64_t db = smem_desc_sw128(b_op + slab * (rowsB * 128) + kk * 32);
-          mma_bf16_ss(d, smem_desc_sw128(a_hi + slab * (128 * 128) + kk * 32), db, idesc1, ks > 0);
-          mma_bf16_ss(d, smem_desc_sw128(a_lo + slab * (128 * 128) + kk * 32), db, idesc2, true);
+        const int slabs = P.Kreal / 64;
+        for (int slab = 0; slab < slabs; ++slab) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t db = desc_from_lo(b_op + slab * ((rowsB * 128) >> 4) + 2 * kk);
+            mma_bf16_ss(d, desc_from_lo(a_hi + slab * ((128 * 128) >> 4) + 2 * kk), db, idesc1, (slab | kk) != 0);
+            mma_bf16_ss(d, desc_from_lo(a_lo + slab * ((128 * 128) >> 4) + 2 * kk), db, idesc2, true);
+          }
         }
         mma_commit(&bar_empty[st]);
         mma_commit(&bar_d_full[st]);
@@ -697,7 +705,7 @@ __global__ void __launch_bounds__(MG2_THREADS, 1) k_mode_gemm_tc(const ModeGemmT
     const int R = row >> 1, part = row & 1;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     for (int it = 0; it < n_local; ++it) {
-      const int m = (int)blockIdx.x + it * (int)gridDim.x;
+      const int m = m_begin + it;
       const int st = it & 1;
       const long long mo = P.offO ? (long long)__ldg(P.offO + m) : m;
       mbar_wait(&bar_d_full[st], (uint32_t)((it >> 1) & 1));
@@ -743,6 +751,8 @@ bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long lon
   P.MR = MR; P.NB = NB; P.KC = KC;
   P.NBp = (NB + 15) / 16 * 16;   // N of an M=128 MMA must be a multiple of 16
   P.Kreal = (2 * KC + 63) / 64 * 64;
+  P.KCp = 8; P.kshift = 3;
+  while (P.KCp < KC) { P.KCp *= 2; ++P.kshift; }
   P.conjA = conjA ? 1 : 0;
   P.n_modes = (int)n_modes;
   const uint32_t a_bytes = 128u * (uint32_t)P.Kreal * 2u;
@@ -759,7 +769,11 @@ bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long lon
     attr_bytes = smem_bytes;
   }
   const int sms = fast_sm_count(p);
-  const int grid = n_modes < sms ? (int)n_modes : sms;
+  // contiguous mode ranges, a multiple of 4 modes (one 32-byte sector of complex64) per CTA
+  int per = (int)((n_modes + sms - 1) / sms);
+  per = (per + 3) / 4 * 4;
+  P.modes_per_cta = per;
+  const int grid = (int)((n_modes + per - 1) / per);
   k_mode_gemm_tc<<<grid, MG2_THREADS, smem_bytes, st>>>(P);
   count_launch();
   return cuda_ok(cudaGetLastError(), "k_mode_gemm_tc launch");

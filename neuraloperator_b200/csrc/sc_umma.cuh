@@ -103,6 +103,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// The single MMA-issuing thread is a serial instruction stream, so descriptor arithmetic is kept to 32-bit adds:
+// only the low word (start address >> 4, LBO) changes between MMAs; the high word is a constant.
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_from_lo(uint32_t lo) { return ((uint64_t)kDescHiSw128 << 32) | lo; }
 // Instruction descriptor for kind::f16 with BF16 operands, FP32 accumulate, both operands K-major:
 //   [4,6) D format = 1 (F32) | [7,10) A format = 1 (BF16) | [10,13) B format = 1 (BF16) | [15] A major = 0 (K)
 //   | [16] B major = 0 (K) | [17,23) N >> 3 | [24,29) M >> 4
