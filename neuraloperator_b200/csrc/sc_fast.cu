@@ -735,15 +735,231 @@ __global__ void __launch_bounds__(MG2_THREADS, 1) k_mode_gemm_tc(const ModeGemmT
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
+// =====================================================================================================
+// mode-wise complex GEMM, four consecutive modes per CTA  ("quad" variant)
+//
+//   Every operand stores the mode index innermost, so the values of 4 consecutive modes of one (row, k) element
+//   are one aligned 32-byte sector: the loaders fetch them with ONE 256-bit load and scatter them into the four
+//   per-mode operand tiles; the epilogue gathers the four per-mode results and writes ONE 32-byte sector.
+//   Global traffic is therefore sector-exact (the single-mode kernel above touches every sector four times).
+//   K (<= 128 real) is consumed in rounds of one 64-wide slab; the four accumulators live side by side in TMEM.
+// =====================================================================================================
+constexpr int MGQ_THREADS = (4 + MG2_LOADER_WARPS) * 32;   // warps 0-3: MMA issue (warp 0) + epilogue, warps 4-19: loaders
+
+struct ModeGemmQuadParams {
+  const float2* a; const float2* b; float2* out;
+  long long sAR, sAK, sBN, sBK, sOR, sON;
+  int MR, NB, KC, NBp, KCp, kshift, conjA, n_groups, rounds, zero_fill;
+};
+// fixed per-mode tile layout (compile-time offsets keep the scatter stores on immediate addressing):
+//   [A_hi 16 KB | A_lo 16 KB | B (hi rows, lo rows) up to 16 KB]
+constexpr uint32_t MGQ_MODE_BYTES = 49152, MGQ_OFF_ALO = 16384, MGQ_OFF_B = 32768;
+
+__device__ __forceinline__ void ld_global_v8(const float2* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
+__global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGemmQuadParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_full, bar_empty, bar_d_full;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rowsB = 2 * P.NBp;
+
+  if (tid == 0) {
+    mbar_init(&bar_full, MG2_LOADER_WARPS);
+    mbar_init(&bar_empty, 1);
+    mbar_init(&bar_d_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
+  if (P.zero_fill) {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < (int)(4 * MGQ_MODE_BYTES / 16); i += MGQ_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const long long m0 = (long long)blockIdx.x * 4;      // first mode of this CTA's quad
+
+  if (warp >= 4) {
+    // ------------------------------------------------------------------ loaders
+    const int lt = tid - 4 * 32;
+    const int kq = lt & (P.KCp - 1);                   // k within the 32-complex slab handled per round (KCp <= 32 here)
+    const int r0 = lt >> P.kshift;
+    const int step = MG2_LOADERS >> P.kshift;          // 16, 32 or 64 rows between a thread's elements
+    const uint32_t a_s0 = sw128_offset(2 * r0, 2 * kq, 128), a_s1 = sw128_offset(2 * r0 + 1, 2 * kq, 128);
+    const uint32_t a_sstep = (uint32_t)step * 256u;
+    const uint32_t b_s0 = sw128_offset(r0, 2 * kq, rowsB), b_sstep = (uint32_t)step * 128u, b_lo = (uint32_t)P.NBp * 128u;
+    for (int rd = 0; rd < P.rounds; ++rd) {
+      const int k = rd * 32 + kq;
+      const bool k_ok = kq < 32 && k < P.KC;
+      const float2* pa = P.a + m0 + (long long)r0 * P.sAR + (long long)k * P.sAK;
+      const float2* pb = P.b + m0 + (long long)r0 * P.sBN + (long long)k * P.sBK;
+      float v[4][8];                                   // <= 4 rows per thread and operand (64 rows / step 16), 4 modes each
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k_ok && r0 + u * step < P.MR) ld_global_v8(pa + (long long)u * step * P.sAR, v[u]);
+      if (rd > 0) mbar_wait(&bar_empty, (uint32_t)((rd - 1) & 1));   // MMAs of the previous round have read the tiles
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k_ok && r0 + u * step < P.MR) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint8_t* a_hi = smem + j * MGQ_MODE_BYTES;
+            uint8_t* a_lo = a_hi + MGQ_OFF_ALO;
+            uint32_t hi, lo;
+            split2_bf16(v[u][2 * j], v[u][2 * j + 1], hi, lo);
+            uint32_t r0h, r1h, r0l, r1l;
+            if (P.conjA) {
+              r0h = hi; r1h = __byte_perm(hi, 0, 0x1032) ^ 0x00008000u;
+              r0l = lo; r1l = __byte_perm(lo, 0, 0x1032) ^ 0x00008000u;
+            } else {
+              r0h = hi ^ 0x80000000u; r1h = __byte_perm(hi, 0, 0x1032);
+              r0l = lo ^ 0x80000000u; r1l = __byte_perm(lo, 0, 0x1032);
+            }
+            *reinterpret_cast<uint32_t*>(a_hi + a_s0 + u * a_sstep) = r0h;
+            *reinterpret_cast<uint32_t*>(a_hi + a_s1 + u * a_sstep) = r1h;
+            *reinterpret_cast<uint32_t*>(a_lo + a_s0 + u * a_sstep) = r0l;
+            *reinterpret_cast<uint32_t*>(a_lo + a_s1 + u * a_sstep) = r1l;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k_ok && r0 + u * step < P.NB) ld_global_v8(pb + (long long)u * step * P.sBN, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k_ok && r0 + u * step < P.NB) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint8_t* b_op = smem + j * MGQ_MODE_BYTES + MGQ_OFF_B;
+            uint32_t hi, lo;
+            split2_bf16(v[u][2 * j], v[u][2 * j + 1], hi, lo);
+            *reinterpret_cast<uint32_t*>(b_op + b_s0 + u * b_sstep) = hi;
+            *reinterpret_cast<uint32_t*>(b_op + b_s0 + u * b_sstep + b_lo) = lo;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issue (warp 0, one thread), then epilogue
+    if (warp == 0 && lane == 0) {
+      const uint32_t idesc1 = idesc_bf16(128, rowsB), idesc2 = idesc_bf16(128, P.NBp);
+      const uint32_t base_lo = desc_lo(smem_u32(smem));
+      for (int rd = 0; rd < P.rounds; ++rd) {
+        mbar_wait(&bar_full, (uint32_t)(rd & 1));
+        tc_fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a_hi = base_lo + (uint32_t)j * (MGQ_MODE_BYTES >> 4), a_lo = a_hi + (MGQ_OFF_ALO >> 4), b_op = a_hi + (MGQ_OFF_B >> 4);
+          const uint32_t d = tmem + (uint32_t)(j * 128);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            mma_bf16_ss(d, desc_from_lo(a_hi + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc1, (rd | kk) != 0);
+            mma_bf16_ss(d, desc_from_lo(a_lo + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc2, true);
+          }
+        }
+        mma_commit(&bar_empty);
+      }
+      mma_commit(&bar_d_full);
+    }
+    __syncwarp();
+    // epilogue: four modes -> one 32-byte store
+    const int row = warp * 32 + lane;
+    const int R = row >> 1, part = row & 1;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    mbar_wait(&bar_d_full, 0);
+    tc_fence_after_sync();
+    float2* dst = P.out + m0 + (long long)R * P.sOR;
+    for (int c = 0; c < P.NBp; c += 8) {
+      float acc[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t1[8], t2[8];
+        tmem_ld8(tmem + lane_sel + (uint32_t)(j * 128 + c), t1);
+        tmem_ld8(tmem + lane_sel + (uint32_t)(j * 128 + P.NBp + c), t2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[j][e] = t1[e] + t2[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mine = acc[j][e];
+          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          o[2 * j] = mine; o[2 * j + 1] = other;      // (re, im) on even lanes
+        }
+        const int n = c + e;
+        if (part == 0 && R < P.MR && n < P.NB) st_global_v8(reinterpret_cast<float*>(dst + (long long)n * P.sON), o);
+      }
+    }
+    tc_fence_before_sync();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 static int fast_sm_count(const Plan* p);   // defined with FastTables below
 
 static bool mode_gemm_tc_supported(int MR, int NB, int KC) {
   return MR >= 1 && MR <= 64 && NB >= 1 && NB <= 64 && KC >= 1 && KC <= 64;
 }
 
+static bool launch_mode_gemm_quad(const Plan* p, const float2* a, long long sAR, long long sAK, bool conjA, const float2* b,
+                                  long long sBN, long long sBK, float2* out, long long sOR, long long sON, int MR, int NB,
+                                  int KC, int64_t n_modes, cudaStream_t st) {
+  ModeGemmQuadParams P{};
+  P.a = a; P.b = b; P.out = out;
+  P.sAR = sAR; P.sAK = sAK; P.sBN = sBN; P.sBK = sBK; P.sOR = sOR; P.sON = sON;
+  P.MR = MR; P.NB = NB; P.KC = KC;
+  P.NBp = (NB + 15) / 16 * 16;
+  P.rounds = (KC + 31) / 32;
+  P.KCp = 8; P.kshift = 3;
+  const int kc_round = KC < 32 ? KC : 32;
+  while (P.KCp < kc_round) { P.KCp *= 2; ++P.kshift; }
+  P.conjA = conjA ? 1 : 0;
+  P.n_groups = (int)(n_modes / 4);
+  P.zero_fill = (MR < 64 || NB < P.NBp || (KC % 32) != 0) ? 1 : 0;
+  const uint32_t smem_bytes = 4 * MGQ_MODE_BYTES + 1024u;
+  static uint32_t attr_bytes = 0;
+  if (attr_bytes < smem_bytes) {
+    if (!cuda_ok(cudaFuncSetAttribute(k_mode_gemm_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                 "cudaFuncSetAttribute(k_mode_gemm_quad)"))
+      return false;
+    attr_bytes = smem_bytes;
+  }
+  k_mode_gemm_quad<<<P.n_groups, MGQ_THREADS, smem_bytes, st>>>(P);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_mode_gemm_quad launch");
+}
+
+static inline bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31u) == 0; }
+
 bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long long sAK, const int* offA, bool conjA,
                          const float2* b, long long sBN, long long sBK, const int* offB, float2* out, long long sOR,
                          long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st) {
+  // Quad variant: modes contiguous in every operand (no sliced weight block), every stride a multiple of 4 complex
+  // elements and 32-byte aligned bases, so that 4 consecutive modes are exactly one sector.
+  const bool contiguous = (offA == nullptr || p->weight_block_is_whole) && (offB == nullptr || p->weight_block_is_whole) &&
+                          (offO == nullptr || p->weight_block_is_whole);
+  const bool strides4 = ((sAR | sAK | sBN | sBK | sOR | sON) & 3) == 0;
+  if (contiguous && strides4 && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out) && MR <= 64 && NB <= 64 &&
+      KC <= 64) {
+    return launch_mode_gemm_quad(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, st);
+  }
   ModeGemmTcParams P{};
   P.a = a; P.b = b; P.out = out;
   P.sAR = sAR; P.sAK = sAK; P.sBN = sBN; P.sBK = sBK; P.sOR = sOR; P.sON = sON;
