@@ -4,6 +4,9 @@
 // with BF16 operands and FP32 accumulation in TMEM.  FP32 accuracy is kept by splitting every operand into
 // two bf16 terms (x = x_hi + x_lo, table = T1 + T2) and accumulating the three significant products
 // x_hi*T1 + x_lo*T1 + x_hi*T2 ("bf16x3", relative error ~1e-5).
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
+
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -93,6 +96,13 @@ bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaS
 //   warp  9     stage-2 MMA issuer                                B2 -> D2[2]
 //   warps 0-3   epilogue 2: D2 -> kept modes in global memory
 // =====================================================================================================
+// debug timeline: role r, tile i, phase ph (0 = iteration start, 1 = inputs ready, 2 = work done) of CTA 0
+#define SC_TRACE(P, role, i, ph)                                                                        \
+  do {                                                                                                  \
+    if ((P).trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (i) < 16)                \
+      (P).trace[(((role) * 16 + (i)) * 4 + (ph))] = clock64();                                          \
+  } while (0)
+
 constexpr int FA_LOADER_WARPS = 8;
 constexpr int FA_LOADER_WARP0 = 10;
 constexpr int FA_THREADS = (FA_LOADER_WARP0 + FA_LOADER_WARPS) * 32;   // 576
@@ -105,7 +115,8 @@ struct AnaParams {
   const uint8_t* b1_img;   // [2*N1 x W] bf16, canonical K-major SW128 image (T1 rows then T2 rows)
   const uint8_t* a2_img;   // [128 x 256] bf16 image of the real-embedded leading-dim table (T1 rows 0-63, T2 rows 64-127)
   int n_tiles, W, slabs, N1, KX, QROWS, n_stages, tmem_cols;
-  uint32_t off_b1, off_a2, off_b2, off_scratch;
+  uint32_t off_b1, off_a2, off_b2, off_scratch, stage_off;   // stage_off: output staging, relative to off_scratch
+  long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
 
 template <int N1>
@@ -170,6 +181,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     for (int idx = 0; idx < total; ++idx, ++g) {
       const int slot = (int)(g % (uint32_t)NS);
       const uint32_t ph = (g / (uint32_t)NS) & 1u;
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 0);
       uint2 hi[8], lo[8];
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -180,7 +192,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
         const int nidx = idx + 1;
         issue((int)blockIdx.x + (nidx / P.slabs) * (int)gridDim.x, nidx % P.slabs);
       }
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 1);
       mbar_wait(&bar_empty[slot], ph ^ 1u);
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 2);
       uint8_t* shi = smem + (size_t)slot * FA_STAGE_BYTES;
       uint8_t* slo = shi + FA_SLAB_BYTES;
 #pragma unroll
@@ -194,50 +208,63 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
       if (lane == 0) mbar_arrive(&bar_full[slot]);
     }
   } else if (warp == 8) {
-    // ------------------------------------------------------------------ stage-1 MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ stage-1 MMA issuer (warp-uniform, one elected lane issues)
+    {
       const uint32_t idesc_p1 = idesc_bf16(128, 2 * N1), idesc_p2 = idesc_bf16(128, N1);
       const uint32_t b1_lo = desc_lo(smem_u32(s_b1)), ring_lo = desc_lo(smem_u32(smem));
       uint32_t g = 0;
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
+        SC_TRACE(P, 1, i, 0);
         mbar_wait(&bar_d1_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
         tc_fence_after_sync();
+        SC_TRACE(P, 1, i, 1);
         for (int s = 0; s < P.slabs; ++s, ++g) {
           const int slot = (int)(g % (uint32_t)NS);
           mbar_wait(&bar_full[slot], (g / (uint32_t)NS) & 1u);
           tc_fence_after_sync();
           const uint32_t d_hi = ring_lo + (uint32_t)slot * (FA_STAGE_BYTES >> 4), d_lo = d_hi + (FA_SLAB_BYTES >> 4);
           const uint32_t d_b = b1_lo + (uint32_t)s * ((2 * N1 * 128) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            mma_bf16_ss(tm_d1[buf], desc_from_lo(d_hi + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p1, (s | kk) != 0);
-            mma_bf16_ss(tm_d1[buf], desc_from_lo(d_lo + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p2, true);
+            for (int kk = 0; kk < 4; ++kk) {
+              mma_bf16_ss(tm_d1[buf], desc_from_lo(d_hi + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p1, (s | kk) != 0);
+              mma_bf16_ss(tm_d1[buf], desc_from_lo(d_lo + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p2, true);
+            }
+            mma_commit(&bar_empty[slot]);
           }
-          mma_commit(&bar_empty[slot]);
+          __syncwarp();
         }
-        mma_commit(&bar_d1_full[buf]);
+        if (elect_one()) mma_commit(&bar_d1_full[buf]);
+        __syncwarp();
+        SC_TRACE(P, 1, i, 2);
       }
     }
     __syncwarp();
   } else if (warp == 9) {
     // ------------------------------------------------------------------ stage-2 MMA issuer
-    if (lane == 0) {
+    {
       const uint32_t idesc_p2 = idesc_bf16(128, N1);
       const uint32_t a2_lo = desc_lo(smem_u32(s_a2)), b2_lo = desc_lo(smem_u32(s_b2));
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
+        SC_TRACE(P, 3, i, 0);
         mbar_wait(&bar_b2_full, (uint32_t)(i & 1));
         mbar_wait(&bar_d2_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
         tc_fence_after_sync();
+        SC_TRACE(P, 3, i, 1);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 16; ++ks) {
-          const int slab = ks >> 2, kk = ks & 3;
-          mma_bf16_ss(tm_d2[buf], desc_from_lo(a2_lo + slab * ((128 * 128) >> 4) + 2 * kk),
-                      desc_from_lo(b2_lo + slab * ((N1 * 128) >> 4) + 2 * kk), idesc_p2, ks > 0);
+          for (int ks = 0; ks < 16; ++ks) {
+            const int slab = ks >> 2, kk = ks & 3;
+            mma_bf16_ss(tm_d2[buf], desc_from_lo(a2_lo + slab * ((128 * 128) >> 4) + 2 * kk),
+                        desc_from_lo(b2_lo + slab * ((N1 * 128) >> 4) + 2 * kk), idesc_p2, ks > 0);
+          }
+          mma_commit(&bar_b2_empty);
+          mma_commit(&bar_d2_full[buf]);
         }
-        mma_commit(&bar_b2_empty);
-        mma_commit(&bar_d2_full[buf]);
+        __syncwarp();
+        SC_TRACE(P, 3, i, 2);
       }
     }
     __syncwarp();
@@ -251,9 +278,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     const int chunk = lane >> 2;
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
+      if (warp == 4) SC_TRACE(P, 2, i, 0);
       mbar_wait(&bar_d1_full[buf], (uint32_t)((i >> 1) & 1));
       mbar_wait(&bar_b2_empty, (uint32_t)((i & 1) ^ 1));
       tc_fence_after_sync();
+      if (warp == 4) SC_TRACE(P, 2, i, 1);
 #pragma unroll
       for (int c = 0; c < N1; c += 16) {
         float t1[16], t2[16];
@@ -275,6 +304,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
       mbar_arrive(&bar_d1_empty[buf]);
       fence_proxy_async_smem();
       mbar_arrive(&bar_b2_full);
+      if (warp == 4) SC_TRACE(P, 2, i, 2);
     }
   } else {
     // ------------------------------------------------------------------ epilogue 2: D2 -> kept modes
@@ -283,8 +313,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     const int KX = P.KX;
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
+      if (warp == 0) SC_TRACE(P, 4, i, 0);
       mbar_wait(&bar_d2_full[buf], (uint32_t)((i >> 1) & 1));
       tc_fence_after_sync();
+      if (warp == 0) SC_TRACE(P, 4, i, 1);
       float d[N1];
 #pragma unroll
       for (int c = 0; c < N1; c += 16) tmem_ld16(tm_d2[buf] + lane_sel + c, *reinterpret_cast<float(*)[16]>(&d[c]));
@@ -297,24 +329,33 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 #pragma unroll
         for (int kx = 0; kx < half; ++kx) if (kx < KX) dst[kx] = d[kx] + d[half + kx];
       }
+      if (tid == 0) bulk_wait_read_1();            // the block stored two tiles ago has left its staging buffer
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      // the tile's modes are ONE contiguous block of QROWS*KX complex numbers: stage it, then a single bulk async store
+      float2* stage = reinterpret_cast<float2*>(smem + P.off_scratch + P.stage_off) + (i & 1) * (P.QROWS * KX);
       if (warp < 2) {
         const float* src = s_scr + row * (KX + 1);
-        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int q = row >> 1, part = row & 1;
         const bool live = q < P.QROWS;
-        float2* dst = P.out + ((size_t)tile * P.QROWS + q) * KX;
 #pragma unroll
         for (int kx = 0; kx < half; ++kx) {
           if (kx < KX) {                         // warp-uniform
             const float mine = d[kx] + d[half + kx] + src[kx];
             const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-            if (live && part == 0) dst[kx] = make_float2(mine, other);
+            if (live && part == 0) stage[q * KX + kx] = make_float2(mine, other);
           }
         }
       }
+      fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 0) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        bulk_store(P.out + (size_t)tile * P.QROWS * KX, stage, (uint32_t)(P.QROWS * KX * 8));
+        bulk_commit();
+      }
+      if (warp == 0) SC_TRACE(P, 4, i, 2);
     }
+    if (tid == 0) bulk_wait_all();
   }
 
   tc_fence_before_sync();
@@ -335,6 +376,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 //   warps 0-3   epilogue B: DB -> + bias -> 256-bit global stores of the image rows
 // =====================================================================================================
 constexpr int FS_THREADS = 14 * 32;
+constexpr int FS_STAGE_BYTES = 4 * 2 * 4096;   // per warp two [32 rows x 32 floats] TMA store boxes
 
 struct SynParams {
   const float2* modes;
@@ -343,7 +385,8 @@ struct SynParams {
   const uint8_t* aa_img;   // [128 x 128] bf16 image: leading-dim table, columns (2q+s | 64+2q+s)
   const uint8_t* bb_img;   // two [W x 64] bf16 images: T1 then T2 of the last-dim table (rows = w, K = j)
   int n_tiles, W, KX, QROWS, H, n_channels, tmem_cols;
-  uint32_t off_aa, off_ba, off_u, off_bb;
+  uint32_t off_aa, off_ba, off_u, off_bb, off_stage;
+  long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
 
 __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
@@ -353,7 +396,7 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
 }
 
 template <int N1>
-__global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynParams P) {
+__global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynParams P, const __grid_constant__ CUtensorMap out_map) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t bar_ba_full[2], bar_ba_empty[2], bar_da_full[2], bar_da_empty[2];
@@ -398,85 +441,104 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
 
   if (warp >= 10) {
     // ------------------------------------------------------------------ prep: modes -> BA
+    // thread -> fixed mode row q (0..31) and columns kx = kx0 + 4u: every swizzled store address is a per-thread base plus
+    // a compile-time multiple of 1024 bytes (8 operand rows), so the per-element work is one 8-byte load, one split, six stores
     const int pt = tid - 10 * 32;   // 0..127
-    const int n_el = P.QROWS * KX;
+    const int q = pt >> 2, kx0 = pt & 3;
+    const bool q_ok = q < P.QROWS;
+    const uint32_t o_re = sw128_offset(2 * kx0, 2 * q, 2 * N1), o_im = sw128_offset(2 * kx0 + 1, 2 * q, 2 * N1);
+    constexpr uint32_t T2 = 2 * N1 * 128;    // second K-slab (columns 64 + k): hi * T2
+    constexpr uint32_t LO = N1 * 128;        // rows N1 + n: lo * T1
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-      const float2* src = P.modes + (size_t)tile * n_el;
-      float2 y[5];                                   // n_el <= 32 * 48 / ... : QROWS*KX <= 32*32 -> <= 8 per thread
+      const float2* src = P.modes + ((size_t)tile * P.QROWS + q) * KX + kx0;
+      float2 y[8];
+      if (warp == 10) SC_TRACE(P, 0, i, 0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (q_ok && kx0 + 4 * u < KX) y[u] = __ldg(src + 4 * u);
       mbar_wait(&bar_ba_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+      if (warp == 10) SC_TRACE(P, 0, i, 1);
       uint8_t* ba = s_ba + buf * BA_BYTES;
-      for (int e0 = pt; e0 < n_el; e0 += 5 * 128) {
 #pragma unroll
-        for (int u = 0; u < 5; ++u) if (e0 + u * 128 < n_el) y[u] = __ldg(src + e0 + u * 128);
-#pragma unroll
-        for (int u = 0; u < 5; ++u) {
-          const int e = e0 + u * 128;
-          if (e < n_el) {
-            const int q = e / KX, kx = e - q * KX;
-            uint32_t hi, lo;                         // (re | im << 16)
-            split2_bf16(y[u].x, y[u].y, hi, lo);
-            const uint32_t re_row_hi = hi ^ 0x80000000u, im_row_hi = __byte_perm(hi, 0, 0x1032);   // (re, -im) ; (im, re)
-            const uint32_t re_row_lo = lo ^ 0x80000000u, im_row_lo = __byte_perm(lo, 0, 0x1032);
-            const int n0 = 2 * kx, n1 = 2 * kx + 1, k = 2 * q;
-            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, k, 2 * N1)) = re_row_hi;        // hi * T1
-            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, k, 2 * N1)) = im_row_hi;
-            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n0, 64 + k, 2 * N1)) = re_row_hi;   // hi * T2
-            *reinterpret_cast<uint32_t*>(ba + sw128_offset(n1, 64 + k, 2 * N1)) = im_row_hi;
-            *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n0, k, 2 * N1)) = re_row_lo;   // lo * T1
-            *reinterpret_cast<uint32_t*>(ba + sw128_offset(N1 + n1, k, 2 * N1)) = im_row_lo;
-          }
+      for (int u = 0; u < 8; ++u) {
+        if (q_ok && kx0 + 4 * u < KX) {
+          uint32_t hi, lo;                         // (re | im << 16)
+          split2_bf16(y[u].x, y[u].y, hi, lo);
+          const uint32_t re_row_hi = hi ^ 0x80000000u, im_row_hi = __byte_perm(hi, 0, 0x1032);   // (re, -im) ; (im, re)
+          const uint32_t re_row_lo = lo ^ 0x80000000u, im_row_lo = __byte_perm(lo, 0, 0x1032);
+          uint8_t* pr = ba + o_re + u * 1024;      // rows 2*kx advance by 8 per u
+          uint8_t* pi = ba + o_im + u * 1024;
+          *reinterpret_cast<uint32_t*>(pr) = re_row_hi;             // hi * T1
+          *reinterpret_cast<uint32_t*>(pi) = im_row_hi;
+          *reinterpret_cast<uint32_t*>(pr + T2) = re_row_hi;        // hi * T2
+          *reinterpret_cast<uint32_t*>(pi + T2) = im_row_hi;
+          *reinterpret_cast<uint32_t*>(pr + LO) = re_row_lo;        // lo * T1
+          *reinterpret_cast<uint32_t*>(pi + LO) = im_row_lo;
         }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_ba_full[buf]);
+      if (warp == 10) SC_TRACE(P, 0, i, 2);
     }
   } else if (warp == 8) {
     // ------------------------------------------------------------------ stage-A MMA issuer
-    if (lane == 0) {
+    {
       const uint32_t idesc_a = idesc_bf16(128, 2 * N1);
       const uint32_t aa_lo = desc_lo(smem_u32(s_aa)), ba_lo0 = desc_lo(smem_u32(s_ba));
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        SC_TRACE(P, 1, i, 0);
         mbar_wait(&bar_ba_full[buf], ph);
         mbar_wait(&bar_da_empty[buf], ph ^ 1u);
         tc_fence_after_sync();
+        SC_TRACE(P, 1, i, 1);
         const uint32_t ba_lo = ba_lo0 + (uint32_t)buf * (BA_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const int slab = ks >> 2, kk = ks & 3;
-          mma_bf16_ss(tm_da[buf], desc_from_lo(aa_lo + slab * ((128 * 128) >> 4) + 2 * kk),
-                      desc_from_lo(ba_lo + slab * ((2 * N1 * 128) >> 4) + 2 * kk), idesc_a, ks > 0);
+          for (int ks = 0; ks < 8; ++ks) {
+            const int slab = ks >> 2, kk = ks & 3;
+            mma_bf16_ss(tm_da[buf], desc_from_lo(aa_lo + slab * ((128 * 128) >> 4) + 2 * kk),
+                        desc_from_lo(ba_lo + slab * ((2 * N1 * 128) >> 4) + 2 * kk), idesc_a, ks > 0);
+          }
+          mma_commit(&bar_ba_empty[buf]);
+          mma_commit(&bar_da_full[buf]);
         }
-        mma_commit(&bar_ba_empty[buf]);
-        mma_commit(&bar_da_full[buf]);
+        __syncwarp();
+        SC_TRACE(P, 1, i, 2);
       }
     }
     __syncwarp();
   } else if (warp == 9) {
     // ------------------------------------------------------------------ stage-B MMA issuer
-    if (lane == 0) {
+    {
       const uint32_t idesc_b = idesc_bf16(128, W);
       const uint32_t u_lo0 = desc_lo(smem_u32(s_u));
       const uint32_t t1 = desc_lo(smem_u32(s_bb)), t2 = t1 + (((uint32_t)W * 128) >> 4);
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         const uint32_t ph = (uint32_t)((i >> 1) & 1);
+        SC_TRACE(P, 3, i, 0);
         mbar_wait(&bar_u_full[buf], ph);
         mbar_wait(&bar_db_empty[buf], ph ^ 1u);
         tc_fence_after_sync();
+        SC_TRACE(P, 3, i, 1);
         const uint32_t u_hi = u_lo0 + (uint32_t)buf * (U_BYTES >> 4), u_lo = u_hi + (FA_SLAB_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < N1 / 16; ++ks) {
-          mma_bf16_ss(tm_db[buf], desc_from_lo(u_hi + 2 * ks), desc_from_lo(t1 + 2 * ks), idesc_b, ks > 0);
-          mma_bf16_ss(tm_db[buf], desc_from_lo(u_lo + 2 * ks), desc_from_lo(t1 + 2 * ks), idesc_b, true);
-          mma_bf16_ss(tm_db[buf], desc_from_lo(u_hi + 2 * ks), desc_from_lo(t2 + 2 * ks), idesc_b, true);
+          for (int ks = 0; ks < N1 / 16; ++ks) {
+            mma_bf16_ss(tm_db[buf], desc_from_lo(u_hi + 2 * ks), desc_from_lo(t1 + 2 * ks), idesc_b, ks > 0);
+            mma_bf16_ss(tm_db[buf], desc_from_lo(u_lo + 2 * ks), desc_from_lo(t1 + 2 * ks), idesc_b, true);
+            mma_bf16_ss(tm_db[buf], desc_from_lo(u_hi + 2 * ks), desc_from_lo(t2 + 2 * ks), idesc_b, true);
+          }
+          mma_commit(&bar_u_empty[buf]);
+          mma_commit(&bar_db_full[buf]);
         }
-        mma_commit(&bar_u_empty[buf]);
-        mma_commit(&bar_db_full[buf]);
+        __syncwarp();
+        SC_TRACE(P, 3, i, 2);
       }
     }
     __syncwarp();
@@ -488,35 +550,51 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
+      if (warp == 4) SC_TRACE(P, 2, i, 0);
       mbar_wait(&bar_da_full[buf], ph);
       mbar_wait(&bar_u_empty[buf], ph ^ 1u);
       tc_fence_after_sync();
+      if (warp == 4) SC_TRACE(P, 2, i, 1);
       uint8_t* uhi = s_u + buf * U_BYTES + row * 128;
       uint8_t* ulo = uhi + FA_SLAB_BYTES;
 #pragma unroll
-      for (int c = 0; c < N1; c += 16) {
-        float t1[16], t2[16];
-        tmem_ld16(tm_da[buf] + lane_sel + c, t1);
-        tmem_ld16(tm_da[buf] + lane_sel + N1 + c, t2);
-        tmem_ld_wait();
-        uint32_t hw[8], lw[8];
+      for (int c = 0; c < N1; c += 32) {            // two 16-column chunks (4 TMEM loads) per wait
+        float t1[2][16], t2[2][16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) split2_bf16(t1[2 * e] + t2[2 * e], t1[2 * e + 1] + t2[2 * e + 1], hw[e], lw[e]);
-        const int c0 = c / 8;                          // two 16-byte chunks of 8 consecutive j
-        *reinterpret_cast<uint4*>(uhi + (((c0 ^ row) & 7) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(uhi + ((((c0 + 1) ^ row) & 7) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-        *reinterpret_cast<uint4*>(ulo + (((c0 ^ row) & 7) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        *reinterpret_cast<uint4*>(ulo + ((((c0 + 1) ^ row) & 7) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+        for (int h = 0; h < 2; ++h) {
+          if (c + 16 * h < N1) {
+            tmem_ld16(tm_da[buf] + lane_sel + c + 16 * h, t1[h]);
+            tmem_ld16(tm_da[buf] + lane_sel + N1 + c + 16 * h, t2[h]);
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (c + 16 * h < N1) {
+            uint32_t hw[8], lw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              split2_bf16(t1[h][2 * e] + t2[h][2 * e], t1[h][2 * e + 1] + t2[h][2 * e + 1], hw[e], lw[e]);
+            const int c0 = (c + 16 * h) / 8;          // two 16-byte chunks of 8 consecutive j
+            *reinterpret_cast<uint4*>(uhi + (((c0 ^ row) & 7) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(uhi + ((((c0 + 1) ^ row) & 7) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+            *reinterpret_cast<uint4*>(ulo + (((c0 ^ row) & 7) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            *reinterpret_cast<uint4*>(ulo + ((((c0 + 1) ^ row) & 7) << 4)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+          }
+        }
       }
       tc_fence_before_sync();
       mbar_arrive(&bar_da_empty[buf]);
       fence_proxy_async_smem();
       mbar_arrive(&bar_u_full[buf]);
+      if (warp == 4) SC_TRACE(P, 2, i, 2);
     }
   } else {
     // ------------------------------------------------------------------ epilogue B: DB -> image rows
     const int row = warp * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    uint8_t* my_stage = smem + P.off_stage + warp * 8192;   // two [32 x 128 B] boxes per warp
+    uint32_t chunk_ctr = 0;
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
@@ -527,24 +605,43 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
         b = __ldg(P.bias + (int)(image % P.n_channels));
       }
       float* dst = P.out + ((size_t)tile * 128 + row) * W;
+      if (warp == 0) SC_TRACE(P, 4, i, 0);
       mbar_wait(&bar_db_full[buf], ph);
       tc_fence_after_sync();
-      for (int c = 0; c < W; c += 64) {
-        float t[4][16];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) tmem_ld16(tm_db[buf] + lane_sel + c + 16 * u, t[u]);
+      if (warp == 0) SC_TRACE(P, 4, i, 1);
+      // 32 columns at a time: TMEM -> registers (+bias) -> this warp's [32 rows x 128 B] staging box in the tensor map's
+      // 128-byte swizzle -> ONE TMA tensor store per warp and box (direct per-thread row stores touch 32 different
+      // 128-byte lines per warp instruction and serialise in the LSU).
+      for (int c = 0; c < W; c += 32) {
+        float t[2][16];
+        tmem_ld16(tm_db[buf] + lane_sel + c, t[0]);
+        tmem_ld16(tm_db[buf] + lane_sel + c + 16, t[1]);
+        uint8_t* box = my_stage + (chunk_ctr & 1) * 4096;
+        if (lane == 0) bulk_wait_read_1();          // the store issued two boxes ago has finished reading this buffer
+        __syncwarp();
         tmem_ld_wait();
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u)
 #pragma unroll
-          for (int e = 0; e < 16; ++e) t[u][e] += b;
-          st_global_v8(dst + c + 16 * u, t[u]);
-          st_global_v8(dst + c + 16 * u + 8, t[u] + 8);
+          for (int e = 0; e < 16; e += 4) {
+            const int ch = (16 * u + e) >> 2;        // 16-byte chunk index within the 128-byte row
+            *reinterpret_cast<float4*>(box + lane * 128 + (((ch ^ lane) & 7) << 4)) =
+                make_float4(t[u][e] + b, t[u][e + 1] + b, t[u][e + 2] + b, t[u][e + 3] + b);
+          }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&out_map, box, c, tile * 128 + warp * 32);
+          bulk_commit();
         }
+        ++chunk_ctr;
       }
       tc_fence_before_sync();
       mbar_arrive(&bar_db_empty[buf]);
+      if (warp == 0) SC_TRACE(P, 4, i, 2);
     }
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
   }
 
   tc_fence_before_sync();
@@ -1008,7 +1105,7 @@ struct FusedAnalysisTables {
   int W = 0, H = 0, G = 0, N1 = 0, KX = 0, KY = 0, slabs = 0, n_stages = 0, tmem_cols = 0;
   uint8_t* d_b1 = nullptr;
   uint8_t* d_a2 = nullptr;
-  uint32_t off_b1 = 0, off_a2 = 0, off_b2 = 0, off_scratch = 0, smem_bytes = 0;
+  uint32_t off_b1 = 0, off_a2 = 0, off_b2 = 0, off_scratch = 0, stage_off = 0, smem_bytes = 0;
 };
 
 struct FusedSynthesisTables {
@@ -1016,7 +1113,7 @@ struct FusedSynthesisTables {
   int W = 0, H = 0, G = 0, N1 = 0, KX = 0, KY = 0, tmem_cols = 0;
   uint8_t* d_aa = nullptr;
   uint8_t* d_bb = nullptr;
-  uint32_t off_aa = 0, off_ba = 0, off_u = 0, off_bb = 0, smem_bytes = 0;
+  uint32_t off_aa = 0, off_ba = 0, off_u = 0, off_bb = 0, off_stage = 0, smem_bytes = 0;
 };
 
 struct FastTables {
@@ -1090,7 +1187,11 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
       }
   if (!upload_bytes(p, b1, &t->d_b1) || !upload_bytes(p, a2, &t->d_a2)) return false;
   // ---- shared-memory carve-up
-  const uint32_t fixed = (uint32_t)b1.size() + 65536u + (uint32_t)N1 * 512u + ((64u * (KX + 1) * 4u + 1023u) & ~1023u);
+  if ((G * KY * KX) % 2 != 0) return true;   // the per-tile mode block is stored with one 16-byte-granular bulk copy
+  const uint32_t scr_bytes = (64u * (KX + 1) * 4u + 15u) & ~15u;
+  const uint32_t scratch_total = (scr_bytes + 2u * (uint32_t)(G * KY * KX) * 8u + 1023u) & ~1023u;
+  t->stage_off = scr_bytes;
+  const uint32_t fixed = (uint32_t)b1.size() + 65536u + (uint32_t)N1 * 512u + scratch_total;
   int stages = (int)((227u * 1024u - 4096u - fixed) / FA_STAGE_BYTES);
   if (stages > 4) stages = 4;
   if (stages < 2) return true;
@@ -1099,7 +1200,7 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   t->off_a2 = t->off_b1 + (uint32_t)b1.size();
   t->off_b2 = t->off_a2 + 65536u;
   t->off_scratch = t->off_b2 + (uint32_t)N1 * 512u;
-  t->smem_bytes = t->off_scratch + ((64u * (KX + 1) * 4u + 1023u) & ~1023u) + 1024u;
+  t->smem_bytes = t->off_scratch + scratch_total + 1024u;
   t->ok = true;
   return true;
 }
@@ -1147,7 +1248,9 @@ static bool build_fused_synthesis(Plan* p, FusedSynthesisTables* t, int H, int W
   t->off_ba = 32768u;
   t->off_u = t->off_ba + 2u * (uint32_t)(2 * N1 * 256);
   t->off_bb = t->off_u + 2u * (uint32_t)(2 * FA_SLAB_BYTES);
-  t->smem_bytes = t->off_bb + (uint32_t)bb.size() + 1024u;
+  t->off_stage = t->off_bb + (uint32_t)bb.size();
+  t->off_stage = (t->off_stage + 1023u) & ~1023u;
+  t->smem_bytes = t->off_stage + FS_STAGE_BYTES + 1024u;
   if (t->smem_bytes > 227u * 1024u - 4096u) return true;
   t->ok = true;
   return true;
@@ -1184,6 +1287,57 @@ bool fast_can_synthesize(const Plan* p, bool adjoint) {
   return p->fast != nullptr && p->d == 2 && p->fast->syn[adjoint ? 1 : 0].ok;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// fp32 matrix [rows x W] (row-major), boxes of [32 rows x 32 floats], 128-byte swizzle
+static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint64_t W) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  const cuuint64_t dims[2] = {W, rows};
+  const cuuint64_t strides[1] = {W * sizeof(float)};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed"); return false; }
+  return true;
+}
+
+// SC_TRACE_FILE=<path>: record the per-role timeline of CTA 0 of every fused transform launch (debug only; synchronises)
+static long long* trace_begin() {
+  if (getenv("SC_TRACE_FILE") == nullptr) return nullptr;
+  long long* d = nullptr;
+  if (cudaMalloc(&d, 5 * 16 * 4 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemset(d, 0, 5 * 16 * 4 * sizeof(long long));
+  return d;
+}
+static void trace_end(long long* d, const char* what) {
+  if (d == nullptr) return;
+  std::vector<long long> h(5 * 16 * 4);
+  cudaDeviceSynchronize();
+  cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  FILE* f = fopen(getenv("SC_TRACE_FILE"), "a");
+  if (f == nullptr) return;
+  fprintf(f, "# %s\n", what);
+  for (int r = 0; r < 5; ++r)
+    for (int i = 0; i < 16; ++i)
+      fprintf(f, "%d %d %lld %lld %lld\n", r, i, h[(r * 16 + i) * 4], h[(r * 16 + i) * 4 + 1], h[(r * 16 + i) * 4 + 2]);
+  fclose(f);
+}
+
 bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint, cudaStream_t st) {
   const FusedAnalysisTables& t = p->fast->ana[adjoint ? 1 : 0];
   if (n_images % t.G != 0) { set_error("fast_analyze: image count not a multiple of the tile group"); return false; }
@@ -1191,7 +1345,8 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   P.x = images; P.out = modes_out; P.b1_img = t.d_b1; P.a2_img = t.d_a2;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.slabs = t.slabs; P.N1 = t.N1; P.KX = t.KX; P.QROWS = t.G * t.KY;
   P.n_stages = t.n_stages; P.tmem_cols = t.tmem_cols;
-  P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch;
+  P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch; P.stage_off = t.stage_off;
+  P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
   switch (t.N1) {
 #define SC_FA_CASE(N)                                                                                            \
@@ -1210,6 +1365,7 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
     default: set_error("fast_analyze: unsupported N1"); return false;
   }
   count_launch();
+  trace_end(P.trace, "analysis");
   return cuda_ok(cudaGetLastError(), "k_fused_analysis launch");
 }
 
@@ -1221,8 +1377,11 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   P.modes = modes_in; P.out = images_out; P.bias = bias; P.aa_img = t.d_aa; P.bb_img = t.d_bb;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.KX = t.KX; P.QROWS = t.G * t.KY; P.H = t.H;
   P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
-  P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb;
+  P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb; P.off_stage = t.off_stage;
+  P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  CUtensorMap out_map;
+  if (!make_row_tile_map(&out_map, images_out, (uint64_t)P.n_tiles * 128, (uint64_t)t.W)) return false;
   switch (t.N1) {
 #define SC_FS_CASE(N)                                                                                            \
   case N: {                                                                                                      \
@@ -1233,13 +1392,14 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
         return false;                                                                                            \
       attr_bytes = t.smem_bytes;                                                                                 \
     }                                                                                                            \
-    k_fused_synthesis<N><<<grid, FS_THREADS, t.smem_bytes, st>>>(P);                                             \
+    k_fused_synthesis<N><<<grid, FS_THREADS, t.smem_bytes, st>>>(P, out_map);                                             \
   } break;
     SC_FS_CASE(16) SC_FS_CASE(32) SC_FS_CASE(48) SC_FS_CASE(64)
 #undef SC_FS_CASE
     default: set_error("fast_synthesize: unsupported N1"); return false;
   }
   count_launch();
+  trace_end(P.trace, "synthesis");
   return cuda_ok(cudaGetLastError(), "k_fused_synthesis launch");
 }
 

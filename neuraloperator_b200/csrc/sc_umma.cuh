@@ -129,6 +129,29 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of the (converged) warp is elected; the rest of the issuing code stays warp-uniform so that descriptor math
+// runs on the uniform datapath instead of being funnelled through a divergent single-lane branch
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// bulk asynchronous shared -> global copy (TMA engine, no LSU wavefronts); sizes / addresses multiples of 16 bytes
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA store shared -> global through a tensor map (box laid out in the map's swizzle mode)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* ssrc, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_u32(ssrc)),
+               "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- canonical K-major / SWIZZLE_128B addressing for bf16 tiles ---------------------------------------------
 // A tile [rows x K] is stored as K/64 slabs of [rows x 64]; byte offset of element (r, k) inside the tile:
 __device__ __forceinline__ uint32_t sw128_offset(int r, int k, int rows) {
