@@ -291,13 +291,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const int kx = c / 2 + e;                       // compile-time
-          if (kx < KX) {                                  // warp-uniform
-            uint32_t hi, lo;
-            split2_bf16(t1[2 * e] + t2[2 * e], t1[2 * e + 1] + t2[2 * e + 1], hi, lo);
-            *reinterpret_cast<uint32_t*>(b2_mine + kx * 128 + ((chunk ^ (kx & 7)) << 4)) = hi;
-            *reinterpret_cast<uint32_t*>(b2_mine + (half + kx) * 128 + ((chunk ^ ((half + kx) & 7)) << 4)) = lo;
-          }
+          const int kx = c / 2 + e;                       // compile-time; slots kx >= KX hold exact zeros (zero table rows)
+          uint32_t hi, lo;
+          split2_bf16(t1[2 * e] + t2[2 * e], t1[2 * e + 1] + t2[2 * e + 1], hi, lo);
+          *reinterpret_cast<uint32_t*>(b2_mine + kx * 128 + ((chunk ^ (kx & 7)) << 4)) = hi;
+          *reinterpret_cast<uint32_t*>(b2_mine + (half + kx) * 128 + ((chunk ^ ((half + kx) & 7)) << 4)) = lo;
         }
       }
       tc_fence_before_sync();
@@ -321,33 +319,42 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 #pragma unroll
       for (int c = 0; c < N1; c += 16) tmem_ld16(tm_d2[buf] + lane_sel + c, *reinterpret_cast<float(*)[16]>(&d[c]));
       tmem_ld_wait();
+      if (warp == 0) SC_TRACE(P, 5, i, 0);
       tc_fence_before_sync();
       mbar_arrive(&bar_d2_empty[buf]);
-      // T2 rows (warps 2,3) hand hi+lo sums to the matching T1 rows (warps 0,1)
+      if (warp == 0) SC_TRACE(P, 5, i, 1);
+      // T2 rows (warps 2,3) hand hi+lo sums to the matching T1 rows (warps 0,1).  Straight-line code over all N1/2 column
+      // slots (padding slots carry exact zeros): runtime bounds checks here turn into a serial LDS->FADD->SHFL->STS chain.
+      constexpr int SP = half + 1;                 // scratch row pitch in floats
       if (warp >= 2) {
-        float* dst = s_scr + (row - 64) * (KX + 1);
+        float* dst = s_scr + (row - 64) * SP;
 #pragma unroll
-        for (int kx = 0; kx < half; ++kx) if (kx < KX) dst[kx] = d[kx] + d[half + kx];
+        for (int kx = 0; kx < half; ++kx) dst[kx] = d[kx] + d[half + kx];
       }
       if (tid == 0) bulk_wait_read_1();            // the block stored two tiles ago has left its staging buffer
+      if (warp == 0) SC_TRACE(P, 5, i, 2);
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0) SC_TRACE(P, 6, i, 0);
       // the tile's modes are ONE contiguous block of QROWS*KX complex numbers: stage it, then a single bulk async store
       float2* stage = reinterpret_cast<float2*>(smem + P.off_scratch + P.stage_off) + (i & 1) * (P.QROWS * KX);
       if (warp < 2) {
-        const float* src = s_scr + row * (KX + 1);
+        const float* src = s_scr + row * SP;
         const int q = row >> 1, part = row & 1;
-        const bool live = q < P.QROWS;
+        const bool live = q < P.QROWS && part == 0;
+        float mine[half], other[half];
 #pragma unroll
-        for (int kx = 0; kx < half; ++kx) {
-          if (kx < KX) {                         // warp-uniform
-            const float mine = d[kx] + d[half + kx] + src[kx];
-            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-            if (live && part == 0) stage[q * KX + kx] = make_float2(mine, other);
-          }
-        }
+        for (int kx = 0; kx < half; ++kx) mine[kx] = d[kx] + d[half + kx] + src[kx];
+#pragma unroll
+        for (int kx = 0; kx < half; ++kx) other[kx] = __shfl_xor_sync(0xffffffffu, mine[kx], 1);
+        float2* my = stage + q * KX;
+#pragma unroll
+        for (int kx = 0; kx < half; ++kx)
+          if (live && kx < KX) my[kx] = make_float2(mine[kx], other[kx]);
       }
+      if (warp == 0) SC_TRACE(P, 6, i, 1);
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0) SC_TRACE(P, 6, i, 2);
       if (tid == 0) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         bulk_store(P.out + (size_t)tile * P.QROWS * KX, stage, (uint32_t)(P.QROWS * KX * 8));
@@ -1188,7 +1195,7 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   if (!upload_bytes(p, b1, &t->d_b1) || !upload_bytes(p, a2, &t->d_a2)) return false;
   // ---- shared-memory carve-up
   if ((G * KY * KX) % 2 != 0) return true;   // the per-tile mode block is stored with one 16-byte-granular bulk copy
-  const uint32_t scr_bytes = (64u * (KX + 1) * 4u + 15u) & ~15u;
+  const uint32_t scr_bytes = (64u * (uint32_t)(N1 / 2 + 1) * 4u + 15u) & ~15u;
   const uint32_t scratch_total = (scr_bytes + 2u * (uint32_t)(G * KY * KX) * 8u + 1023u) & ~1023u;
   t->stage_off = scr_bytes;
   const uint32_t fixed = (uint32_t)b1.size() + 65536u + (uint32_t)N1 * 512u + scratch_total;
@@ -1319,20 +1326,20 @@ static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint
 static long long* trace_begin() {
   if (getenv("SC_TRACE_FILE") == nullptr) return nullptr;
   long long* d = nullptr;
-  if (cudaMalloc(&d, 5 * 16 * 4 * sizeof(long long)) != cudaSuccess) return nullptr;
-  cudaMemset(d, 0, 5 * 16 * 4 * sizeof(long long));
+  if (cudaMalloc(&d, 8 * 16 * 4 * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemset(d, 0, 8 * 16 * 4 * sizeof(long long));
   return d;
 }
 static void trace_end(long long* d, const char* what) {
   if (d == nullptr) return;
-  std::vector<long long> h(5 * 16 * 4);
+  std::vector<long long> h(8 * 16 * 4);
   cudaDeviceSynchronize();
   cudaMemcpy(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaFree(d);
   FILE* f = fopen(getenv("SC_TRACE_FILE"), "a");
   if (f == nullptr) return;
   fprintf(f, "# %s\n", what);
-  for (int r = 0; r < 5; ++r)
+  for (int r = 0; r < 8; ++r)
     for (int i = 0; i < 16; ++i)
       fprintf(f, "%d %d %lld %lld %lld\n", r, i, h[(r * 16 + i) * 4], h[(r * 16 + i) * 4 + 1], h[(r * 16 + i) * 4 + 2]);
   fclose(f);

@@ -10,7 +10,7 @@ for name in ('analysis','synthesis'):
     sec=secs[-1][1]
     t0=min(v[0] for v in sec.values() if v[0]>0)
     print('==',name,'(role: 0 loader/prep 1 S1/SA 2 epi1/epiA 3 S2/SB 4 epi2/epiB)  i:[start wWAIT xWORK]')
-    for r in range(5):
+    for r in range(8):
         row=[]
         for i in range(2,10):
             a,b,c=sec.get((r,i),(0,0,0))
