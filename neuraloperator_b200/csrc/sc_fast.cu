@@ -115,7 +115,7 @@ struct AnaParams {
   const uint8_t* b1_img;   // [2*N1 x W] bf16, canonical K-major SW128 image (T1 rows then T2 rows)
   const uint8_t* a2_img;   // [128 x 256] bf16 image of the real-embedded leading-dim table (T1 rows 0-63, T2 rows 64-127)
   int n_tiles, W, slabs, N1, KX, QROWS, n_stages, tmem_cols;
-  uint32_t off_b1, off_a2, off_b2, off_scratch, stage_off;   // stage_off: output staging, relative to off_scratch
+  uint32_t off_f32, off_ring, off_b1, off_a2, off_b2, off_scratch, stage_off;   // stage_off: output staging, relative to off_scratch
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
 
@@ -167,35 +167,44 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 
   if (warp >= FA_LOADER_WARP0) {
     // ------------------------------------------------------------------ loaders
+    // x streams through a two-deep fp32 staging ring with cp.async (64 KB in flight per SM at no register cost); each
+    // thread later converts exactly the 16-byte pieces it copied itself, so cp.async.wait_group is the only hand-off.
     const int lt = tid - FA_LOADER_WARP0 * 32;   // 0..255
     const int rbase = lt >> 4, c4 = lt & 15;     // 16 float4 per 64-float row segment; 16 rows per pass
+    uint8_t* f32_stage = smem + P.off_f32;       // two [128 x 64] fp32 slabs, row pitch 256 B
+    const uint32_t my_f32 = (uint32_t)(rbase * 256 + c4 * 16);
     uint32_t g = 0;                              // running slab counter
-    float4 v[8];
-    auto issue = [&](int tile, int slab) {
-      const float* src = P.x + ((size_t)tile * 128) * P.W + slab * 64 + c4 * 4;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) v[it] = __ldg(reinterpret_cast<const float4*>(src + (size_t)(rbase + it * 16) * P.W));
-    };
     const int total = n_local * P.slabs;
-    if (total > 0) issue((int)blockIdx.x, 0);
+    auto issue = [&](int idx) {                  // slab idx -> staging buffer idx & 1
+      const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
+      const float* src = P.x + ((size_t)tile * 128) * P.W + slab * 64 + c4 * 4;
+      uint8_t* dst = f32_stage + (idx & 1) * 32768 + my_f32;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) cp_async16(dst + it * 16 * 256, src + (size_t)(rbase + it * 16) * P.W);
+    };
+    if (total > 0) issue(0);
+    cp_async_commit();
+    if (total > 1) issue(1);
+    cp_async_commit();
     for (int idx = 0; idx < total; ++idx, ++g) {
       const int slot = (int)(g % (uint32_t)NS);
       const uint32_t ph = (g / (uint32_t)NS) & 1u;
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 0);
+      cp_async_wait<1>();                        // slab idx has landed (one younger group may still be in flight)
       uint2 hi[8], lo[8];
+      const uint8_t* fsrc = f32_stage + (idx & 1) * 32768 + my_f32;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        split2_bf16(v[it].x, v[it].y, hi[it].x, lo[it].x);
-        split2_bf16(v[it].z, v[it].w, hi[it].y, lo[it].y);
+        const float4 v = *reinterpret_cast<const float4*>(fsrc + it * 16 * 256);
+        split2_bf16(v.x, v.y, hi[it].x, lo[it].x);
+        split2_bf16(v.z, v.w, hi[it].y, lo[it].y);
       }
-      if (idx + 1 < total) {                     // next slab's loads are in flight while this one waits for its slot
-        const int nidx = idx + 1;
-        issue((int)blockIdx.x + (nidx / P.slabs) * (int)gridDim.x, nidx % P.slabs);
-      }
+      if (idx + 2 < total) issue(idx + 2);       // this thread has consumed its pieces of the buffer: refill it
+      cp_async_commit();
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 1);
       mbar_wait(&bar_empty[slot], ph ^ 1u);
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 2);
-      uint8_t* shi = smem + (size_t)slot * FA_STAGE_BYTES;
+      uint8_t* shi = smem + P.off_ring + (size_t)slot * FA_STAGE_BYTES;
       uint8_t* slo = shi + FA_SLAB_BYTES;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // ------------------------------------------------------------------ stage-1 MMA issuer (warp-uniform, one elected lane issues)
     {
       const uint32_t idesc_p1 = idesc_bf16(128, 2 * N1), idesc_p2 = idesc_bf16(128, N1);
-      const uint32_t b1_lo = desc_lo(smem_u32(s_b1)), ring_lo = desc_lo(smem_u32(smem));
+      const uint32_t b1_lo = desc_lo(smem_u32(s_b1)), ring_lo = desc_lo(smem_u32(smem + P.off_ring));
       uint32_t g = 0;
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
@@ -1112,7 +1121,7 @@ struct FusedAnalysisTables {
   int W = 0, H = 0, G = 0, N1 = 0, KX = 0, KY = 0, slabs = 0, n_stages = 0, tmem_cols = 0;
   uint8_t* d_b1 = nullptr;
   uint8_t* d_a2 = nullptr;
-  uint32_t off_b1 = 0, off_a2 = 0, off_b2 = 0, off_scratch = 0, stage_off = 0, smem_bytes = 0;
+  uint32_t off_f32 = 0, off_ring = 0, off_b1 = 0, off_a2 = 0, off_b2 = 0, off_scratch = 0, stage_off = 0, smem_bytes = 0;
 };
 
 struct FusedSynthesisTables {
@@ -1199,11 +1208,15 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   const uint32_t scratch_total = (scr_bytes + 2u * (uint32_t)(G * KY * KX) * 8u + 1023u) & ~1023u;
   t->stage_off = scr_bytes;
   const uint32_t fixed = (uint32_t)b1.size() + 65536u + (uint32_t)N1 * 512u + scratch_total;
-  int stages = (int)((227u * 1024u - 4096u - fixed) / FA_STAGE_BYTES);
+  // [fp32 staging: 2 slabs x 32 KB][bf16 hi/lo ring: `stages` x 32 KB][B1][A2][B2][scratch]
+  int stages = (int)(((227u * 1024u - 4096u - fixed) - 65536u) / FA_STAGE_BYTES);
+  if (227u * 1024u - 4096u < fixed + 65536u + FA_STAGE_BYTES) return true;
   if (stages > 4) stages = 4;
-  if (stages < 2) return true;
+  if (stages < 1) return true;
   t->n_stages = stages;
-  t->off_b1 = (uint32_t)stages * FA_STAGE_BYTES;
+  t->off_f32 = 0;
+  t->off_ring = 65536u;
+  t->off_b1 = t->off_ring + (uint32_t)stages * FA_STAGE_BYTES;
   t->off_a2 = t->off_b1 + (uint32_t)b1.size();
   t->off_b2 = t->off_a2 + 65536u;
   t->off_scratch = t->off_b2 + (uint32_t)N1 * 512u;
@@ -1352,6 +1365,7 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   P.x = images; P.out = modes_out; P.b1_img = t.d_b1; P.a2_img = t.d_a2;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.slabs = t.slabs; P.N1 = t.N1; P.KX = t.KX; P.QROWS = t.G * t.KY;
   P.n_stages = t.n_stages; P.tmem_cols = t.tmem_cols;
+  P.off_f32 = t.off_f32; P.off_ring = t.off_ring;
   P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch; P.stage_off = t.stage_off;
   P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
