@@ -166,12 +166,42 @@ def run_ours(args):
     g = torch.randn(B, C, H, W, device=dev)
     reducer = nb.GradientAllReducer(conv.parameters()) if world > 1 else None
 
-    def step():
+    def step_body():
         conv.weight.tensor.grad = None
         conv.bias.grad = None
         x.grad = None
         y = conv(x)
         y.backward(g)
+
+    # The step is 8 kernel launches of 20-40 us each: capture it once in a CUDA graph so that the timed loop is not bound
+    # by Python / autograd dispatch (the eager path is what `e2e` measures).
+    graph = None
+    c0 = _lib.launch_count()
+    step_body()
+    launches_per_step = _lib.launch_count() - c0       # kernels this library launches for one fwd+bwd
+    torch.cuda.synchronize(dev)
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step_body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_body()
+        except Exception as exc:  # pragma: no cover - reported in the JSON line
+            graph = None
+            graph_error = repr(exc)
+            torch.cuda.synchronize(dev)
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_body()
         if reducer is not None:
             reducer.start()
             reducer.finish()
@@ -197,6 +227,8 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
+    if graph is not None:
+        launches = launches_per_step * args.steps      # replayed by the graph: the library's own counter does not see them
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -288,7 +320,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "no flush: x, g, y, dx are 134 MB each (537 MB touched per step) > 126 MB L2",
-                       "fast_path_mask": plan.uses_fast_path()},
+                       "fast_path_mask": plan.uses_fast_path(), "cuda_graph": graph is not None},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
@@ -312,6 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager autograd path instead of a captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps

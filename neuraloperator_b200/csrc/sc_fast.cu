@@ -8,6 +8,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "sc_fast.h"
@@ -90,7 +91,8 @@ bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaS
 //   stage 2 (leading dim) D2[i', n]  = sum_{h,p} A2[i', (h,p)] * R_p[h, n]      M=128         N=N1    K=256
 //
 //   Every role is its own pipeline stage with double buffers in between:
-//   warps 10-17 loaders   LDG.128 -> bf16 hi/lo split -> swizzled STS into the slab ring
+//   warp  18    TMA producer: x slabs [128 rows x 64 fp32] -> two-deep fp32 staging ring (one tensor load per slab)
+//   warps 10-17 converters: staging -> bf16 hi/lo split -> swizzled STS into the operand slab
 //   warp  8     stage-1 MMA issuer (+ TMEM allocation)          ring slab -> D1[2]
 //   warps 4-7   epilogue 1: D1 -> R -> bf16 hi/lo B operand of stage 2 (B2, single buffer)
 //   warp  9     stage-2 MMA issuer                                B2 -> D2[2]
@@ -104,8 +106,10 @@ bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaS
   } while (0)
 
 constexpr int FA_LOADER_WARPS = 8;
+constexpr int FA_LOADER_ITERS = 128 / (FA_LOADER_WARPS * 2);   // row passes per slab: a loader warp covers 2 rows x 64 floats
 constexpr int FA_LOADER_WARP0 = 10;
-constexpr int FA_THREADS = (FA_LOADER_WARP0 + FA_LOADER_WARPS) * 32;   // 576
+constexpr int FA_TMA_WARP = FA_LOADER_WARP0 + FA_LOADER_WARPS;          // one extra warp streams x with TMA loads
+constexpr int FA_THREADS = (FA_TMA_WARP + 1) * 32;                     // 608
 constexpr int FA_SLAB_BYTES = 128 * 128;                                // one [128 x 64] bf16 slab
 constexpr int FA_STAGE_BYTES = 2 * FA_SLAB_BYTES;                       // hi + lo
 
@@ -120,11 +124,11 @@ struct AnaParams {
 };
 
 template <int N1>
-__global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParams P) {
+__global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParams P, const __grid_constant__ CUtensorMap x_map) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
   __shared__ uint64_t bar_full[4], bar_empty[4], bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_b2_empty,
-      bar_d2_full[2], bar_d2_empty[2];
+      bar_d2_full[2], bar_d2_empty[2], bar_f32_full[2], bar_f32_empty[2];
   __shared__ uint32_t tmem_base_slot;
   constexpr int half = N1 / 2;
 
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_d1_full[i], 1); mbar_init(&bar_d1_empty[i], 128);
       mbar_init(&bar_d2_full[i], 1); mbar_init(&bar_d2_empty[i], 128);
+      mbar_init(&bar_f32_full[i], 1); mbar_init(&bar_f32_empty[i], FA_LOADER_WARPS);
     }
     mbar_init(&bar_b2_full, 128);
     mbar_init(&bar_b2_empty, 1);
@@ -165,50 +170,56 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 
   const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= FA_LOADER_WARP0) {
-    // ------------------------------------------------------------------ loaders
-    // x streams through a two-deep fp32 staging ring with cp.async (64 KB in flight per SM at no register cost); each
-    // thread later converts exactly the 16-byte pieces it copied itself, so cp.async.wait_group is the only hand-off.
-    const int lt = tid - FA_LOADER_WARP0 * 32;   // 0..255
-    const int rbase = lt >> 4, c4 = lt & 15;     // 16 float4 per 64-float row segment; 16 rows per pass
+  if (warp == FA_TMA_WARP) {
+    // ------------------------------------------------------------------ TMA producer: one tensor load per 32 KB slab
+    const int total = n_local * P.slabs;
+    uint8_t* f32_stage = smem + P.off_f32;
+    for (int idx = 0; idx < total; ++idx) {
+      const int sb = idx & 1;
+      mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx >> 1) & 1) ^ 1));
+      if (elect_one()) {
+        const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
+        mbar_arrive_expect_tx(&bar_f32_full[sb], 32768u);
+        tma_load_2d(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= FA_LOADER_WARP0) {
+    // ------------------------------------------------------------------ converters
+    // x arrives in a two-deep fp32 staging ring ([128 x 64] fp32 per slab, written by the TMA engine: 64 KB in flight per
+    // SM, no registers, no LSU issue slots); each thread splits its 16-byte pieces into bf16 hi/lo operand tiles.
+    const int lt = tid - FA_LOADER_WARP0 * 32;
+    constexpr int RP = FA_LOADER_WARPS * 2;      // rows covered per pass
+    const int rbase = lt >> 4, c4 = lt & 15;     // 16 float4 per 64-float row segment
     uint8_t* f32_stage = smem + P.off_f32;       // two [128 x 64] fp32 slabs, row pitch 256 B
     const uint32_t my_f32 = (uint32_t)(rbase * 256 + c4 * 16);
     uint32_t g = 0;                              // running slab counter
     const int total = n_local * P.slabs;
-    auto issue = [&](int idx) {                  // slab idx -> staging buffer idx & 1
-      const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
-      const float* src = P.x + ((size_t)tile * 128) * P.W + slab * 64 + c4 * 4;
-      uint8_t* dst = f32_stage + (idx & 1) * 32768 + my_f32;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) cp_async16(dst + it * 16 * 256, src + (size_t)(rbase + it * 16) * P.W);
-    };
-    if (total > 0) issue(0);
-    cp_async_commit();
-    if (total > 1) issue(1);
-    cp_async_commit();
     for (int idx = 0; idx < total; ++idx, ++g) {
       const int slot = (int)(g % (uint32_t)NS);
       const uint32_t ph = (g / (uint32_t)NS) & 1u;
+      const int sb = idx & 1;
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 0);
-      cp_async_wait<1>();                        // slab idx has landed (one younger group may still be in flight)
-      uint2 hi[8], lo[8];
-      const uint8_t* fsrc = f32_stage + (idx & 1) * 32768 + my_f32;
+      mbar_wait(&bar_f32_full[sb], (uint32_t)((idx >> 1) & 1));
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 7, idx, 0);
+      uint2 hi[FA_LOADER_ITERS], lo[FA_LOADER_ITERS];
+      const uint8_t* fsrc = f32_stage + sb * 32768 + my_f32;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const float4 v = *reinterpret_cast<const float4*>(fsrc + it * 16 * 256);
+      for (int it = 0; it < FA_LOADER_ITERS; ++it) {
+        const float4 v = *reinterpret_cast<const float4*>(fsrc + it * RP * 256);
         split2_bf16(v.x, v.y, hi[it].x, lo[it].x);
         split2_bf16(v.z, v.w, hi[it].y, lo[it].y);
       }
-      if (idx + 2 < total) issue(idx + 2);       // this thread has consumed its pieces of the buffer: refill it
-      cp_async_commit();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_f32_empty[sb]);   // this warp has consumed its pieces of the staging buffer
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 1);
       mbar_wait(&bar_empty[slot], ph ^ 1u);
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 2);
       uint8_t* shi = smem + P.off_ring + (size_t)slot * FA_STAGE_BYTES;
       uint8_t* slo = shi + FA_SLAB_BYTES;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const uint32_t off = sw128_offset(rbase + it * 16, c4 * 4, 128);
+      for (int it = 0; it < FA_LOADER_ITERS; ++it) {
+        const uint32_t off = sw128_offset(rbase + it * RP, c4 * 4, 128);
         *reinterpret_cast<uint2*>(shi + off) = hi[it];
         *reinterpret_cast<uint2*>(slo + off) = lo[it];
       }
@@ -1132,13 +1143,37 @@ struct FusedSynthesisTables {
   uint32_t off_aa = 0, off_ba = 0, off_u = 0, off_bb = 0, off_stage = 0, smem_bytes = 0;
 };
 
+// Encoding a CUtensorMap costs tens of microseconds on the host; training loops hand the same buffers (PyTorch's caching
+// allocator) to the same plan step after step, so encoded maps are kept in a small per-plan cache.
+struct TensorMapCacheEntry { const void* base; uint64_t rows, W; int kind; CUtensorMap map; };
+
 struct FastTables {
+  std::vector<TensorMapCacheEntry> map_cache;
+  std::mutex map_mutex;
   FusedAnalysisTables ana[2];   // [0] forward analysis on `grid`, [1] adjoint-of-synthesis analysis on `out_grid`
   FusedSynthesisTables syn[2];  // [0] forward synthesis onto `out_grid`, [1] adjoint-of-analysis synthesis onto `grid`
   int sm_count = 0;
 };
 
 static int fast_sm_count(const Plan* p) { return p->fast->sm_count; }
+
+static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t W);
+static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint64_t W);
+// kind 0: x slab loads, kind 1: image row-tile stores
+static bool cached_map(const Plan* p, int kind, const void* base, uint64_t rows, uint64_t W, CUtensorMap* out) {
+  FastTables* f = p->fast;
+  std::lock_guard<std::mutex> lock(f->map_mutex);
+  for (const TensorMapCacheEntry& e : f->map_cache)
+    if (e.base == base && e.rows == rows && e.W == W && e.kind == kind) { *out = e.map; return true; }
+  TensorMapCacheEntry e{base, rows, W, kind, {}};
+  const bool ok = kind == 0 ? make_slab_load_map(&e.map, static_cast<const float*>(base), rows, W)
+                            : make_row_tile_map(&e.map, static_cast<float*>(const_cast<void*>(base)), rows, W);
+  if (!ok) return false;
+  if (f->map_cache.size() >= 32) f->map_cache.erase(f->map_cache.begin());
+  f->map_cache.push_back(e);
+  *out = e.map;
+  return true;
+}
 
 static inline uint16_t bf16_bits(float f) {   // round to nearest even
   uint32_t u;
@@ -1335,6 +1370,21 @@ static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint
   return true;
 }
 
+// fp32 matrix [rows x W] (row-major), boxes of [128 rows x 64 floats], no swizzle (the converters read 16-byte pieces)
+static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t W) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  const cuuint64_t dims[2] = {W, rows};
+  const cuuint64_t strides[1] = {W * sizeof(float)};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (x slabs) failed"); return false; }
+  return true;
+}
+
 // SC_TRACE_FILE=<path>: record the per-role timeline of CTA 0 of every fused transform launch (debug only; synchronises)
 static long long* trace_begin() {
   if (getenv("SC_TRACE_FILE") == nullptr) return nullptr;
@@ -1369,6 +1419,8 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch; P.stage_off = t.stage_off;
   P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  CUtensorMap x_map;
+  if (!cached_map(p, 0, images, (uint64_t)P.n_tiles * 128, (uint64_t)t.W, &x_map)) return false;
   switch (t.N1) {
 #define SC_FA_CASE(N)                                                                                            \
   case N: {                                                                                                      \
@@ -1379,7 +1431,7 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
         return false;                                                                                            \
       attr_bytes = t.smem_bytes;                                                                                 \
     }                                                                                                            \
-    k_fused_analysis<N><<<grid, FA_THREADS, t.smem_bytes, st>>>(P);                                              \
+    k_fused_analysis<N><<<grid, FA_THREADS, t.smem_bytes, st>>>(P, x_map);                                              \
   } break;
     SC_FA_CASE(16) SC_FA_CASE(32) SC_FA_CASE(48) SC_FA_CASE(64) SC_FA_CASE(80)
 #undef SC_FA_CASE
@@ -1402,7 +1454,7 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
   CUtensorMap out_map;
-  if (!make_row_tile_map(&out_map, images_out, (uint64_t)P.n_tiles * 128, (uint64_t)t.W)) return false;
+  if (!cached_map(p, 1, images_out, (uint64_t)P.n_tiles * 128, (uint64_t)t.W, &out_map)) return false;
   switch (t.N1) {
 #define SC_FS_CASE(N)                                                                                            \
   case N: {                                                                                                      \

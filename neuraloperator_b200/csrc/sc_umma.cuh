@@ -149,6 +149,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// 2-D tiled TMA load global -> shared; completion (bytes) is signalled on an mbarrier armed with arrive.expect_tx
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* sdst, const void* tmap, uint64_t* bar, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                   smem_u32(sdst)),
+               "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y)
+               : "memory");
+}
+
 // 2-D tiled TMA store shared -> global through a tensor map (box laid out in the map's swizzle mode)
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* ssrc, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_u32(ssrc)),
