@@ -36,3 +36,20 @@ def test_live_reference_bit_exact(grid, modes, kw):
     assert torch.equal(x.grad, dx2)
     assert torch.equal(conv.weight.tensor.grad, dws[0])
     assert torch.equal(conv.bias.grad, db)
+
+
+def test_reference_fno_blocks_accept_the_plugin_class():
+    """`FNOBlocks(conv_module=neuraloperator_b200.SpectralConv)` constructs (reference fno_block.py:210-240) and the
+    host-side attribute traffic it performs (n_modes setter, :460-464) works. No forward here: that needs the GPU."""
+    import importlib
+    import neuraloperator_b200 as nb
+    load_reference_spectral_conv()
+    fno_block = importlib.import_module("neuralop.layers.fno_block")
+    blocks = fno_block.FNOBlocks(8, 8, (12, 12), n_layers=2, conv_module=nb.SpectralConv)
+    assert all(isinstance(c, nb.SpectralConv) for c in blocks.convs)
+    assert blocks.convs[0].n_modes == [12, 7]
+    blocks.n_modes = (8, 8)
+    assert blocks.convs[1].n_modes == [8, 5]
+    tf = fno_block.FNOBlocks(8, 8, (12, 12), n_layers=1, conv_module=nb.SpectralConv, factorization="tucker", rank=0.5,
+                             implementation="factorized")
+    assert tf.convs[0].weight.name.lower().endswith("tucker")
