@@ -48,6 +48,23 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(plan):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused analysis kernel from the committed
+    `ncu --set full` capture of this same command (profiles/r01_final_ana.txt); None when the generic kernels run."""
+    if not plan.uses_fast_path() & 1:
+        return None
+    path = os.path.join(ROOT, "profiles", "r01_final_ana.txt")
+    try:
+        vals = {}
+        for line in open(path):
+            if line.startswith("dram__bytes_read.sum =") or line.startswith("dram__bytes_write.sum ="):
+                k, v = line.split("=")
+                vals[k.strip()] = float(v) * 1e6          # ncu prints Mbyte
+        return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -327,7 +344,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "forward analysis chain (x -> kept modes): " +
                          ("fused tcgen05 kernel" if plan.uses_fast_path() & 1 else "k_real_table_gemm + k_complex_table_gemm"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "bytes_per_launch": analyze_bytes, "ms_per_launch": analyze_ms, "traffic": None,
+                         "bytes_per_launch": analyze_bytes, "ms_per_launch": analyze_ms, "traffic": ncu_traffic(plan),
                          "step": {"bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak}},
             "cpu_baseline": cpu_base,
         }
