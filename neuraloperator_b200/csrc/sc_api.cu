@@ -256,15 +256,41 @@ static bool synthesize_generic(const Plan* p, const float2* modes_in, int64_t n_
 static bool analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint,
                     float2* b0, float2* b1, cudaStream_t st) {
   if (n_images <= 0) return true;
-  if (p->fast_enabled && fast_can_analyze(p, adjoint)) return fast_analyze(p, images, n_images, modes_out, adjoint, st);
+  if (p->fast_enabled && fast_can_analyze(p, adjoint)) {
+    if (p->d == 2) {
+      if (n_images % fast_tile_group(p, false, adjoint) == 0)
+        return fast_analyze(p, images, n_images, modes_out, adjoint, st);
+    } else {   // d == 3: fused last two dims per (image, z) slice, then dim 0 on the truncated data
+      const DimTables& Z = p->dim[0];
+      const int64_t slices = n_images * (adjoint ? Z.M : Z.N);
+      if (slices % fast_tile_group(p, false, adjoint) == 0) {
+        if (!fast_analyze(p, images, slices, b0, adjoint, st)) return false;
+        const int64_t inner = (int64_t)p->dim[1].k * p->dim[2].k;
+        return launch_complex_table_gemm(adjoint ? Z.d_SH : Z.d_A, b0, modes_out, n_images, Z.k, adjoint ? Z.M : Z.N, (int)inner, st);
+      }
+    }
+  }
   return analyze_generic(p, images, n_images, modes_out, adjoint, b0, b1, st);
 }
 
 static bool synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
                        float* images_out, bool adjoint, float2* b0, float2* b1, cudaStream_t st) {
   if (n_images <= 0) return true;
-  if (p->fast_enabled && fast_can_synthesize(p, adjoint))
-    return fast_synthesize(p, modes_in, n_images, n_channels, bias, images_out, adjoint, st);
+  if (p->fast_enabled && fast_can_synthesize(p, adjoint)) {
+    if (p->d == 2) {
+      if (n_images % fast_tile_group(p, true, adjoint) == 0)
+        return fast_synthesize(p, modes_in, n_images, n_channels, bias, images_out, adjoint, 1, st);
+    } else {
+      const DimTables& Z = p->dim[0];
+      const int P0 = adjoint ? Z.N : Z.M;
+      const int64_t slices = n_images * P0;
+      if (slices % fast_tile_group(p, true, adjoint) == 0) {
+        const int64_t inner = (int64_t)p->dim[1].k * p->dim[2].k;
+        if (!launch_complex_table_gemm(adjoint ? Z.d_AH : Z.d_S, modes_in, b0, n_images, P0, Z.k, (int)inner, st)) return false;
+        return fast_synthesize(p, b0, slices, n_channels, bias, images_out, adjoint, P0, st);
+      }
+    }
+  }
   return synthesize_generic(p, modes_in, n_images, n_channels, bias, images_out, adjoint, b0, b1, st);
 }
 

@@ -412,6 +412,7 @@ struct SynParams {
   const uint8_t* aa_img;   // [128 x 128] bf16 image: leading-dim table, columns (2q+s | 64+2q+s)
   const uint8_t* bb_img;   // two [W x 64] bf16 images: T1 then T2 of the last-dim table (rows = w, K = j)
   int n_tiles, W, KX, QROWS, H, n_channels, tmem_cols;
+  int slices_per_image;    // 3-D: the fused kernel sees (image, z) slices; bias channel = (slice / slices_per_image) % n_channels
   uint32_t off_aa, off_ba, off_u, off_bb, off_stage;
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
@@ -628,8 +629,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       float b = 0.f;
       if (P.bias != nullptr) {
-        const long long image = (long long)tile * (128 / P.H) + row / P.H;
-        b = __ldg(P.bias + (int)(image % P.n_channels));
+        const long long slice = (long long)tile * (128 / P.H) + row / P.H;
+        b = __ldg(P.bias + (int)((slice / P.slices_per_image) % P.n_channels));
       }
       float* dst = P.out + ((size_t)tile * 128 + row) * W;
       if (warp == 0) SC_TRACE(P, 4, i, 0);
@@ -1335,11 +1336,16 @@ void fast_plan_destroy(Plan* p) {
   p->fast = nullptr;
 }
 
+// d == 2: the fused kernels are the whole transform.  d == 3: they handle the last two dims of every (image, z) slice and
+// the generic complex table kernel handles dim 0 on the already-truncated data (sc_api.cu).
 bool fast_can_analyze(const Plan* p, bool adjoint) {
-  return p->fast != nullptr && p->d == 2 && p->fast->ana[adjoint ? 1 : 0].ok;
+  return p->fast != nullptr && (p->d == 2 || p->d == 3) && p->fast->ana[adjoint ? 1 : 0].ok;
 }
 bool fast_can_synthesize(const Plan* p, bool adjoint) {
-  return p->fast != nullptr && p->d == 2 && p->fast->syn[adjoint ? 1 : 0].ok;
+  return p->fast != nullptr && (p->d == 2 || p->d == 3) && p->fast->syn[adjoint ? 1 : 0].ok;
+}
+int fast_tile_group(const Plan* p, bool synthesis, bool adjoint) {
+  return synthesis ? p->fast->syn[adjoint ? 1 : 0].G : p->fast->ana[adjoint ? 1 : 0].G;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1443,13 +1449,14 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
 }
 
 bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
-                     float* images_out, bool adjoint, cudaStream_t st) {
+                     float* images_out, bool adjoint, int slices_per_image, cudaStream_t st) {
   const FusedSynthesisTables& t = p->fast->syn[adjoint ? 1 : 0];
   if (n_images % t.G != 0) { set_error("fast_synthesize: image count not a multiple of the tile group"); return false; }
   SynParams P{};
   P.modes = modes_in; P.out = images_out; P.bias = bias; P.aa_img = t.d_aa; P.bb_img = t.d_bb;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.KX = t.KX; P.QROWS = t.G * t.KY; P.H = t.H;
   P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
+  P.slices_per_image = slices_per_image > 0 ? slices_per_image : 1;
   P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb; P.off_stage = t.off_stage;
   P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;

@@ -13,8 +13,10 @@ bool fast_can_analyze(const Plan* p, bool adjoint);
 bool fast_can_synthesize(const Plan* p, bool adjoint);
 bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint,
                   cudaStream_t st);
+// n_images counts the 2-D slices the fused kernel sees (images x dim-0 extent for 3-D problems)
 bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
-                     float* images_out, bool adjoint, cudaStream_t st);
+                     float* images_out, bool adjoint, int slices_per_image, cudaStream_t st);
+int fast_tile_group(const Plan* p, bool synthesis, bool adjoint);   // slices per 128-row tile
 
 bool fast_can_contract(const Plan* p, int B, int Ci, int Co);
 // out[R, n] (+ per-mode offset) = sum_k a(R, k) * b(n, k), complex, one product per kept mode, on tcgen05 (bf16x3)

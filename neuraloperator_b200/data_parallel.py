@@ -1,11 +1,11 @@
 """Batch-sharded data parallelism for the spectral conv: ONE gradient all-reduce per step.
 
-The reference wraps the model in DDP (neuralop/training/trainer.py:203-205): samples are independent in the
-forward pass and in dx; only dweight / dbias sum over the batch.  `GradientAllReducer` does the same thing for
-the parameters it is given -- averages `.grad` across ranks with a single all-reduce on one flat float32
-buffer (complex64 grads travel as (re, im) float pairs) -- issued on a side stream so that it overlaps
-whatever the caller launches next (the dx inverse transforms, the previous layer's backward).
-Backend: NCCL over NVLink/NVSwitch on the B200 box, gloo in the CPU tests.
+The reference wraps the model in DDP (neuralop/training/trainer.py:203-205): samples are independent in the forward pass and
+in dx; only dweight / dbias sum over the batch.  `GradientAllReducer` averages gradient tensors across ranks on a side
+stream (complex64 grads travel as (re, im) float pairs, in place, no packing copy), so that the collective overlaps whatever
+the caller launches next.  Attached to a `SpectralConv` (`conv.gradient_reducer = reducer`) the backward pass itself starts
+the all-reduce of dweight / dbias as soon as the contraction backward has produced them, i.e. underneath the dx synthesis
+kernel -- the DDP overlap, for a single layer.  Backend: NCCL over NVLink/NVSwitch on the B200 box, gloo in the CPU tests.
 """
 from typing import Iterable, List, Optional
 
@@ -14,71 +14,78 @@ import torch.distributed as dist
 
 
 class GradientAllReducer:
-    def __init__(self, params: Iterable[torch.nn.Parameter], process_group=None, average: bool = True):
+    def __init__(self, params: Iterable[torch.nn.Parameter] = (), process_group=None, average: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = process_group
         self.average = average
-        self._flat: Optional[torch.Tensor] = None
         self._stream: Optional[torch.cuda.Stream] = None
-        self._work = None
+        self._pending = []          # (work, tensor) pairs of the collectives in flight
+        self._early = False         # True once a backward pass has already started this step's collectives
 
     @staticmethod
     def _as_real(t: torch.Tensor) -> torch.Tensor:
         return torch.view_as_real(t) if t.is_complex() else t
 
-    def _numel(self) -> int:
-        return sum(self._as_real(p).numel() for p in self.params)
-
-    def _ensure_buffer(self, device):
-        n = self._numel()
-        if self._flat is None or self._flat.numel() != n or self._flat.device != device:
-            self._flat = torch.empty(n, dtype=torch.float32, device=device)
-        if device.type == "cuda" and self._stream is None:
-            self._stream = torch.cuda.Stream(device=device)
-
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
-    def start(self):
-        """Pack the grads and launch the all-reduce (non-blocking on CUDA). No-op for a single rank."""
-        if self.world_size() == 1 or not self.params:
+    def _backend_has_avg(self) -> bool:
+        return dist.get_backend(self.group) == "nccl"
+
+    def start_tensors(self, tensors: Iterable[torch.Tensor]):
+        """Launch the all-reduce of `tensors` (in place). On CUDA it runs on a side stream that first waits for the work
+        already queued on the current stream (the kernels that produced the tensors)."""
+        tensors = [t for t in tensors if t is not None]
+        if self.world_size() == 1 or not tensors:
             return
-        device = self.params[0].grad.device
-        self._ensure_buffer(device)
+        device = tensors[0].device
+        op = dist.ReduceOp.AVG if (self.average and self._backend_has_avg()) else dist.ReduceOp.SUM
         if device.type == "cuda":
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=device)
             self._stream.wait_stream(torch.cuda.current_stream(device))
-            ctx = torch.cuda.stream(self._stream)
+            with torch.cuda.stream(self._stream):
+                for t in tensors:
+                    r = self._as_real(t)
+                    r.record_stream(self._stream)
+                    self._pending.append((dist.all_reduce(r, op=op, group=self.group, async_op=True), r, op))
         else:
-            ctx = torch.autograd.profiler.record_function("grad_allreduce")
-        with ctx:
-            off = 0
-            for p in self.params:
-                g = self._as_real(p.grad).reshape(-1)
-                self._flat[off:off + g.numel()].copy_(g)
-                off += g.numel()
-            self._work = dist.all_reduce(self._flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            for t in tensors:
+                r = self._as_real(t)
+                self._pending.append((dist.all_reduce(r, op=op, group=self.group, async_op=True), r, op))
+
+    def start_early(self, tensors):
+        """Called from inside a backward pass (SpectralConv with a reducer attached)."""
+        self._early = True
+        self.start_tensors(tensors)
+
+    def start(self):
+        """All-reduce the `.grad` of the registered parameters, unless a backward pass already did it for this step."""
+        if self._early:
+            return
+        self.start_tensors([p.grad for p in self.params if p.grad is not None])
 
     def finish(self):
-        """Wait for the all-reduce and scatter the averaged values back into `.grad`."""
-        if self._work is None:
+        """Wait for the collectives; the current stream then sees the averaged gradients."""
+        if not self._pending:
+            self._early = False
             return
-        device = self._flat.device
+        device = self._pending[0][1].device
+        scale = 1.0 / self.world_size()
         if device.type == "cuda":
-            ctx = torch.cuda.stream(self._stream)
-        else:
-            ctx = torch.autograd.profiler.record_function("grad_allreduce_unpack")
-        with ctx:
-            self._work.wait()
-            scale = 1.0 / self.world_size() if self.average else 1.0
-            off = 0
-            for p in self.params:
-                g = self._as_real(p.grad)
-                n = g.numel()
-                g.copy_((self._flat[off:off + n] * scale).view_as(g))
-                off += n
-        if device.type == "cuda":
+            with torch.cuda.stream(self._stream):
+                for work, r, op in self._pending:
+                    work.wait()
+                    if self.average and op == dist.ReduceOp.SUM:
+                        r.mul_(scale)
             torch.cuda.current_stream(device).wait_stream(self._stream)
-        self._work = None
+        else:
+            for work, r, op in self._pending:
+                work.wait()
+                if self.average and op == dist.ReduceOp.SUM:
+                    r.mul_(scale)
+        self._pending = []
+        self._early = False
 
     def all_reduce(self):
         self.start()

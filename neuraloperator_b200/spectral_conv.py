@@ -177,7 +177,7 @@ class _SpectralConvDense(torch.autograd.Function):
     """y = SpectralConv.forward(x) with a dense weight; saves only the kept input modes (B,Ci,*kept)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, plan: Plan):
+    def forward(ctx, x, weight, bias, plan: Plan, reducer=None):
         lib = _lib.load()
         B, Ci = x.shape[:2]
         Co = weight.shape[1]
@@ -191,6 +191,7 @@ class _SpectralConvDense(torch.autograd.Function):
             _lib.check(lib.sc_forward_dense(plan.handle, _ptr(x), _ptr(weight), _ptr(b), _ptr(y), _ptr(xm), B, Ci, Co,
                                             _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_forward_dense")
         ctx.plan = plan
+        ctx.reducer = reducer
         ctx.has_bias = bias is not None
         ctx.bias_shape = bias.shape if bias is not None else None
         ctx.save_for_backward(xm, weight)
@@ -212,16 +213,31 @@ class _SpectralConvDense(torch.autograd.Function):
         dw = torch.empty_like(weight) if need_dw else None
         db = torch.empty(Co, dtype=torch.float32, device=dev) if need_db else None
         ws = _workspace(plan, B * max(Ci, Co), dev)
+        reducer = ctx.reducer
         with torch.cuda.device(dev):
-            _lib.check(lib.sc_backward_dense(plan.handle, _ptr(gy), _ptr(weight), _ptr(xm), _ptr(dx), _ptr(dw), _ptr(db),
-                                             B, Ci, Co, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_backward_dense")
+            if reducer is None or reducer.world_size() == 1:
+                _lib.check(lib.sc_backward_dense(plan.handle, _ptr(gy), _ptr(weight), _ptr(xm), _ptr(dx), _ptr(dw), _ptr(db),
+                                                 B, Ci, Co, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_backward_dense")
+            else:
+                # data parallel: same kernels, but the gradient all-reduce of dweight / dbias is launched on the reducer's
+                # side stream right after the contraction backward, underneath the dx synthesis kernel
+                st = _stream_ptr(dev)
+                gm = torch.empty((B, Co, *plan.kept), dtype=torch.complex64, device=dev)
+                dxm = torch.empty((B, Ci, *plan.kept), dtype=torch.complex64, device=dev) if need_dx else None
+                _lib.check(lib.sc_analyze(plan.handle, _ptr(gy), B * Co, _ptr(gm), 1, _ptr(ws), ws.numel(), st), "sc_analyze")
+                _lib.check(lib.sc_contract_dense_backward(plan.handle, _ptr(xm), _ptr(gm), _ptr(weight), _ptr(dxm), _ptr(dw),
+                                                          _ptr(db), B, Ci, Co, st), "sc_contract_dense_backward")
+                reducer.start_early([dw, db])
+                if need_dx:
+                    _lib.check(lib.sc_synthesize(plan.handle, _ptr(dxm), B * Ci, 0, _ptr(None), _ptr(dx), 1, _ptr(ws),
+                                                 ws.numel(), st), "sc_synthesize")
         if db is not None:
             db = db.reshape(ctx.bias_shape)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def spectral_conv_dense(x, weight, bias, plan: Plan):
-    return _SpectralConvDense.apply(x, weight, bias, plan)
+def spectral_conv_dense(x, weight, bias, plan: Plan, reducer=None):
+    return _SpectralConvDense.apply(x, weight, bias, plan, reducer)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -317,6 +333,8 @@ class SpectralConv(BaseSpectralConv):
             fixed_rank_modes = [0] if fixed_rank_modes else None
         self.fft_norm = fft_norm
         self.separable = separable
+        # optional neuraloperator_b200.GradientAllReducer: backward then overlaps the dweight/dbias all-reduce with dx
+        self.gradient_reducer = None
 
         weight_shape = (in_channels, out_channels, *self.max_n_modes)
         tensor_kwargs = decomposition_kwargs if decomposition_kwargs is not None else {}
@@ -374,4 +392,4 @@ class SpectralConv(BaseSpectralConv):
         w = self.weight.to_tensor()
         if not w.is_contiguous():
             w = w.contiguous()
-        return spectral_conv_dense(x, w, self.bias, plan)
+        return spectral_conv_dense(x, w, self.bias, plan, self.gradient_reducer if self.factorization is None else None)

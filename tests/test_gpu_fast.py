@@ -93,3 +93,26 @@ def test_fast_synthesis_matches_generic(cuda_device, grid, modes, n0, n1, adjoin
     torch.cuda.synchronize()
     assert torch.isfinite(fast).all()
     assert _rel(fast, slow) < 1e-4
+
+
+@pytest.mark.parametrize("grid,modes,n0,n1", [((64, 64, 64), (16, 16, 16), 2, 4), ((8, 128, 128), (4, 32, 32), 1, 3), ((10, 64, 64), (6, 12, 14), 2, 2)])
+def test_fast_3d_matches_generic(cuda_device, grid, modes, n0, n1):
+    """3-D: fused tcgen05 kernels on the last two dims + the generic complex table kernel on dim 0."""
+    from oracle import spectral_conv_oracle as O
+    stored = O.stored_n_modes(modes)
+    plan = nb.get_plan(cuda_device, grid, grid, stored, stored)
+    assert plan.uses_fast_path() == 15, plan.uses_fast_path()
+    torch.manual_seed(21)
+    x = torch.randn(n0, n1, *grid, device=cuda_device)
+    ym = torch.randn(n0, n1, *plan.kept, dtype=torch.cfloat, device=cuda_device)
+    bias = torch.randn(n1, device=cuda_device)
+    fast = [nb.analyze(plan, x), nb.analyze(plan, x, adjoint=True), nb.synthesize(plan, ym, bias), nb.synthesize(plan, ym, adjoint=True)]
+    plan.set_fast_path(False)
+    try:
+        slow = [nb.analyze(plan, x), nb.analyze(plan, x, adjoint=True), nb.synthesize(plan, ym, bias), nb.synthesize(plan, ym, adjoint=True)]
+    finally:
+        plan.set_fast_path(True)
+    for f, s_ in zip(fast, slow):
+        f = torch.view_as_real(f) if f.is_complex() else f
+        s_ = torch.view_as_real(s_) if s_.is_complex() else s_
+        assert _rel(f, s_) < 1e-4
