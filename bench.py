@@ -182,17 +182,15 @@ def run_ours(args):
     x = torch.randn(B, C, H, W, device=dev, requires_grad=True)
     g = torch.randn(B, C, H, W, device=dev)
     reducer = nb.GradientAllReducer(conv.parameters()) if world > 1 else None
-    conv.gradient_reducer = reducer      # backward starts the all-reduce of dW/db underneath the dx synthesis kernel
+    if args.no_graph:
+        conv.gradient_reducer = reducer  # eager path: backward starts the all-reduce of dW/db underneath the dx synthesis kernel
 
     def step_body():
         conv.weight.tensor.grad = None
         conv.bias.grad = None
         x.grad = None
         y = conv(x)
-        y.backward(g)                      # data parallel: starts the dW/db all-reduce underneath the dx kernel
-        if reducer is not None:
-            reducer.start()                # no-op when backward already started it
-            reducer.finish()               # joins the side stream: the step ends with averaged gradients
+        y.backward(g)
 
     # The step is 8 kernel launches of 20-40 us each: capture it once in a CUDA graph so that the timed loop is not bound
     # by Python / autograd dispatch (the eager path is what `e2e` measures).
@@ -223,6 +221,9 @@ def run_ours(args):
             graph.replay()
         else:
             step_body()
+        if reducer is not None:            # one in-place NCCL all-reduce (AVG) of dW and db per step, outside the captured graph
+            reducer.start()                # (capturing the collective inside the graph dead-locked on this stack; no-op if the
+            reducer.finish()               #  eager backward already started it)
 
     def barrier():
         if world > 1:
