@@ -91,6 +91,18 @@ int sc_contract_dense_backward(const sc_plan* plan, const sc_complex* xm, const 
 int sc_bias_grad(const sc_plan* plan, const sc_complex* gm, float* dbias, int32_t batch, int32_t out_channels,
                  sc_stream stream);
 
+/* ---- building blocks of the factorized (Tucker) contraction, _contract_tucker :76-103, and of its backward --------- */
+/* out[o, p, i] = sum_q op(table[p, q]) * in[o, q, i]   (complex; table element (p,q) at table[p*stride_p + q*stride_q];
+ * op = conj when conj_table != 0).  Applies one factor matrix along one axis of a tensor: channel mixing with U_in / U_out
+ * (i = flattened modes) and the expansion of the core along a mode axis with the (kept rows of the) mode factors. */
+int sc_table_contract(const sc_complex* table, int64_t table_stride_p, int64_t table_stride_q, int conj_table,
+                      const sc_complex* in, sc_complex* out, int64_t n_outer, int32_t P, int32_t Q, int32_t n_inner,
+                      sc_stream stream);
+/* out[p*out_stride_p + q*out_stride_q] = sum_{o, i} conj(a[o, p, i]) * b[o, q, i]   (a: [n_outer x P x n_inner],
+ * b: [n_outer x Q x n_inner]): gradient of a factor matrix in PyTorch's conjugate convention (warp-shuffle reductions). */
+int sc_pair_reduce(const sc_complex* a, const sc_complex* b, sc_complex* out, int64_t out_stride_p, int64_t out_stride_q,
+                   int64_t n_outer, int32_t P, int32_t Q, int32_t n_inner, sc_stream stream);
+
 /* ---- whole forward / backward for a dense weight (one call per autograd.Function.forward/backward) ------ */
 /* y = SpectralConv.forward(x); xm_saved (B,Ci,k..) is the only activation kept for backward. */
 int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weight, const float* bias,

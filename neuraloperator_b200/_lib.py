@@ -50,6 +50,8 @@ SIGNATURES = {
                                  c_void_p, c_size_t, c_void_p]),
     "sc_backward_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                                   c_i32, c_void_p, c_size_t, c_void_p]),
+    "sc_table_contract": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p]),
+    "sc_pair_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_void_p]),
     "sc_last_error": (ctypes.c_char_p, []),
     "sc_kernel_launch_count": (ctypes.c_uint64, []),
     "sc_build_info": (ctypes.c_char_p, []),

@@ -507,6 +507,24 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
   return 0;
 }
 
+int sc_table_contract(const sc_complex* table, int64_t table_stride_p, int64_t table_stride_q, int conj_table,
+                      const sc_complex* in, sc_complex* out, int64_t n_outer, int32_t P, int32_t Q, int32_t n_inner,
+                      sc_stream stream) {
+  SC_REQUIRE(table != nullptr && in != nullptr && out != nullptr, "sc_table_contract: null argument");
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(table), table_stride_p, table_stride_q, conj_table != 0,
+                                           reinterpret_cast<const float2*>(in), reinterpret_cast<float2*>(out), n_outer, P, Q,
+                                           n_inner, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_pair_reduce(const sc_complex* a, const sc_complex* b, sc_complex* out, int64_t out_stride_p, int64_t out_stride_q,
+                   int64_t n_outer, int32_t P, int32_t Q, int32_t n_inner, sc_stream stream) {
+  SC_REQUIRE(a != nullptr && b != nullptr && out != nullptr, "sc_pair_reduce: null argument");
+  SC_TRY(launch_pair_reduce(reinterpret_cast<const float2*>(a), reinterpret_cast<const float2*>(b), reinterpret_cast<float2*>(out),
+                            out_stride_p, out_stride_q, n_outer, P, Q, n_inner, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream) {
   SC_REQUIRE(a != nullptr && b != nullptr && d != nullptr, "sc_selftest_umma: null argument");
   SC_TRY(umma_selftest(a, b, d, n, k, static_cast<cudaStream_t>(stream)));

@@ -880,6 +880,8 @@ struct ModeGemmQuadParams {
 //   [A_hi 16 KB | A_lo 16 KB | B (hi rows, lo rows) up to 16 KB]
 constexpr uint32_t MGQ_MODE_BYTES = 49152, MGQ_OFF_ALO = 16384, MGQ_OFF_B = 32768;
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void ld_global_v8(const float2* p, float (&v)[8]) {
   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
@@ -930,6 +932,17 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (k_ok && r0 + u * step < P.MR) ld_global_v8(pa + (long long)u * step * P.sAR, v[u]);
+      // pull the sectors this thread needs next (B of this round, A and B of the next round) into L2 while A is in flight
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k_ok && r0 + u * step < P.NB) prefetch_l2(pb + (long long)u * step * P.sBN);
+      if (rd + 1 < P.rounds && kq < 32 && k + 32 < P.KC) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (r0 + u * step < P.MR) prefetch_l2(pa + 32 * P.sAK + (long long)u * step * P.sAR);
+          if (r0 + u * step < P.NB) prefetch_l2(pb + 32 * P.sBK + (long long)u * step * P.sBN);
+        }
+      }
       if (rd > 0) mbar_wait(&bar_empty, (uint32_t)((rd - 1) & 1));   // MMAs of the previous round have read the tiles
 #pragma unroll
       for (int u = 0; u < 4; ++u) {

@@ -129,9 +129,10 @@ constexpr int CT_TP = 16;      // output rows per thread
 constexpr int CT_PG = 2;       // row groups per CTA (threadIdx.y)
 constexpr int CT_QC = 32;      // q-chunk held in shared memory
 
+template <bool CONJ_T>
 __global__ void __launch_bounds__(CT_COLS* CT_PG)
-k_complex_table_gemm(const float2* __restrict__ T, const float2* __restrict__ in, float2* __restrict__ out,
-                     long long O, int P, int Q, int I) {
+k_complex_table_gemm(const float2* __restrict__ T, long long sTp, long long sTq, const float2* __restrict__ in,
+                     float2* __restrict__ out, long long O, int P, int Q, int I) {
   __shared__ float2 s_in[CT_QC][CT_COLS];
   __shared__ __align__(16) float2 s_T[CT_QC][CT_PG * CT_TP + 2];   // +2: keeps rows 16-B aligned, spreads banks
   const long long ncols = O * (long long)I;
@@ -156,7 +157,8 @@ k_complex_table_gemm(const float2* __restrict__ T, const float2* __restrict__ in
     for (int idx = tid; idx < CT_QC * CT_PG * CT_TP; idx += CT_COLS * CT_PG) {
       const int pp = idx / CT_QC, qq = idx % CT_QC;   // consecutive threads walk q: contiguous in T
       float2 v = make_float2(0.f, 0.f);
-      if (p_base + pp < P && q0 + qq < Q) v = __ldg(T + (long long)(p_base + pp) * Q + q0 + qq);
+      if (p_base + pp < P && q0 + qq < Q) v = __ldg(T + (long long)(p_base + pp) * sTp + (long long)(q0 + qq) * sTq);
+      if (CONJ_T) v.y = -v.y;
       s_T[qq][pp] = v;
     }
     __syncthreads();
@@ -188,15 +190,95 @@ k_complex_table_gemm(const float2* __restrict__ T, const float2* __restrict__ in
   }
 }
 
-bool launch_complex_table_gemm(const float2* T, const float2* in, float2* out, int64_t O, int P, int Q, int I,
-                               cudaStream_t st) {
+bool launch_complex_table_gemm_strided(const float2* T, int64_t sTp, int64_t sTq, bool conjT, const float2* in, float2* out,
+                                       int64_t O, int P, int Q, int I, cudaStream_t st) {
   const int64_t ncols = O * (int64_t)I;
   if (ncols <= 0 || P <= 0) return true;
   dim3 grid((unsigned)((ncols + CT_COLS - 1) / CT_COLS), (unsigned)((P + CT_PG * CT_TP - 1) / (CT_PG * CT_TP)));
   dim3 block(CT_COLS, CT_PG);
-  k_complex_table_gemm<<<grid, block, 0, st>>>(T, in, out, (long long)O, P, Q, I);
+  if (conjT)
+    k_complex_table_gemm<true><<<grid, block, 0, st>>>(T, (long long)sTp, (long long)sTq, in, out, (long long)O, P, Q, I);
+  else
+    k_complex_table_gemm<false><<<grid, block, 0, st>>>(T, (long long)sTp, (long long)sTq, in, out, (long long)O, P, Q, I);
   count_launch();
   return cuda_ok(cudaGetLastError(), "k_complex_table_gemm launch");
+}
+
+bool launch_complex_table_gemm(const float2* T, const float2* in, float2* out, int64_t O, int P, int Q, int I,
+                               cudaStream_t st) {
+  return launch_complex_table_gemm_strided(T, Q, 1, false, in, out, O, P, Q, I, st);
+}
+
+// =====================================================================================================
+// 2b. pair reduction (factor gradients of the factorized contractions):
+//     out[p, q] = sum_{o, i} conj(A[o, p, i]) * B[o, q, i]        A: [O x P x I], B: [O x Q x I], out: P x Q (strided)
+//     One CTA owns a 4 x 4 tile of `out`; its 256 threads stride over the flattened (o, i) reduction axis (consecutive
+//     threads -> consecutive i: coalesced), then a warp-shuffle tree and a cross-warp pass in shared memory finish the sum.
+// =====================================================================================================
+constexpr int PR_T = 4;
+constexpr int PR_THREADS = 256;
+
+__global__ void __launch_bounds__(PR_THREADS)
+k_pair_reduce(const float2* __restrict__ A, const float2* __restrict__ B, float2* __restrict__ out, long long sOp,
+              long long sOq, long long O, int P, int Q, int I) {
+  __shared__ float2 s_part[PR_THREADS / 32][PR_T * PR_T];
+  const int p0 = blockIdx.x * PR_T, q0 = blockIdx.y * PR_T;
+  const long long R = O * (long long)I;
+  float2 acc[PR_T][PR_T];
+#pragma unroll
+  for (int a = 0; a < PR_T; ++a)
+#pragma unroll
+    for (int b = 0; b < PR_T; ++b) acc[a][b] = make_float2(0.f, 0.f);
+  for (long long r = threadIdx.x; r < R; r += PR_THREADS) {
+    const long long o = r / I;
+    const int i = (int)(r - o * I);
+    float2 av[PR_T], bv[PR_T];
+#pragma unroll
+    for (int a = 0; a < PR_T; ++a)
+      av[a] = (p0 + a < P) ? __ldg(A + (o * P + p0 + a) * (long long)I + i) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int b = 0; b < PR_T; ++b)
+      bv[b] = (q0 + b < Q) ? __ldg(B + (o * Q + q0 + b) * (long long)I + i) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < PR_T; ++a)
+#pragma unroll
+      for (int b = 0; b < PR_T; ++b) {   // conj(a) * b
+        acc[a][b].x = fmaf(av[a].x, bv[b].x, acc[a][b].x);
+        acc[a][b].x = fmaf(av[a].y, bv[b].y, acc[a][b].x);
+        acc[a][b].y = fmaf(av[a].x, bv[b].y, acc[a][b].y);
+        acc[a][b].y = fmaf(-av[a].y, bv[b].x, acc[a][b].y);
+      }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < PR_T; ++a)
+#pragma unroll
+    for (int b = 0; b < PR_T; ++b) {
+      float2 v = acc[a][b];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+      }
+      if (lane == 0) s_part[warp][a * PR_T + b] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < PR_T * PR_T) {
+    float2 v = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < PR_THREADS / 32; ++w) { v.x += s_part[w][threadIdx.x].x; v.y += s_part[w][threadIdx.x].y; }
+    const int a = threadIdx.x / PR_T, b = threadIdx.x % PR_T;
+    if (p0 + a < P && q0 + b < Q) out[(long long)(p0 + a) * sOp + (long long)(q0 + b) * sOq] = v;
+  }
+}
+
+bool launch_pair_reduce(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q,
+                        int I, cudaStream_t st) {
+  if (P <= 0 || Q <= 0) return true;
+  dim3 grid((unsigned)((P + PR_T - 1) / PR_T), (unsigned)((Q + PR_T - 1) / PR_T));
+  k_pair_reduce<<<grid, PR_THREADS, 0, st>>>(A, B, out, (long long)sOp, (long long)sOq, (long long)O, P, Q, I);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_pair_reduce launch");
 }
 
 // =====================================================================================================
@@ -297,18 +379,21 @@ bool launch_mode_gemm(ModeGemmOperand A, bool conjA, ModeGemmOperand B, bool con
 // =====================================================================================================
 __global__ void k_bias_grad(const float2* __restrict__ gm, float* __restrict__ dbias, int batch, int out_channels,
                             long long n_modes, int dc_slot, float inv_scale) {
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per output channel, lanes over the batch: the loads are independent (one L2 round trip), then a shuffle tree
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (o >= out_channels) return;
   float s = 0.f;
-  for (int b = 0; b < batch; ++b) s += gm[((long long)b * out_channels + o) * n_modes + dc_slot].x;
-  dbias[o] = s * inv_scale;
+  for (int b = lane; b < batch; b += 32) s += __ldg(&gm[((long long)b * out_channels + o) * n_modes + dc_slot].x);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) dbias[o] = s * inv_scale;
 }
 
 bool launch_bias_grad(const float2* gm, float* dbias, int batch, int out_channels, int64_t n_modes, int dc_slot,
                       float inv_scale, cudaStream_t st) {
   if (out_channels <= 0) return true;
-  k_bias_grad<<<(out_channels + 127) / 128, 128, 0, st>>>(gm, dbias, batch, out_channels, (long long)n_modes,
-                                                          dc_slot, inv_scale);
+  k_bias_grad<<<(out_channels + 3) / 4, 128, 0, st>>>(gm, dbias, batch, out_channels, (long long)n_modes, dc_slot, inv_scale);
   count_launch();
   return cuda_ok(cudaGetLastError(), "k_bias_grad launch");
 }

@@ -66,6 +66,11 @@ bool launch_real_table_gemm(const float* A, const float* T, int ldt, float* C, c
 // out[o, p, i] = sum_q T[p, q] * in[o, q, i]   (complex; T is [P x Q] row-major)
 bool launch_complex_table_gemm(const float2* T, const float2* in, float2* out, int64_t O, int P, int Q, int I,
                                cudaStream_t st);
+bool launch_complex_table_gemm_strided(const float2* T, int64_t sTp, int64_t sTq, bool conjT, const float2* in, float2* out,
+                                       int64_t O, int P, int Q, int I, cudaStream_t st);
+// out[p, q] (strided) = sum_{o,i} conj(A[o,p,i]) * B[o,q,i]
+bool launch_pair_reduce(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I,
+                        cudaStream_t st);
 // out[r, c, m] = sum_k opA(A[r,k,m]) * opB(B[k,c,m]); per-operand element strides, optional mode-offset tables
 struct ModeGemmOperand {
   const void* ptr; int64_t s_outer; int64_t s_inner; const int32_t* mode_off;  // mode_off == nullptr -> m itself

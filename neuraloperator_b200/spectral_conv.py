@@ -241,6 +241,116 @@ def spectral_conv_dense(x, weight, bias, plan: Plan, reducer=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# Tucker-factorized contraction without reconstructing the weight (reference `_contract_tucker`, :76-103)
+# --------------------------------------------------------------------------------------------------
+def _table_contract(table, s_p, s_q, conj, src, n_outer, P, Q, n_inner):
+    """out[o, p, i] = sum_q op(table[p, q]) * src[o, q, i]; table element (p, q) at table.flat[p * s_p + q * s_q]."""
+    lib = _lib.load()
+    out = torch.empty(n_outer * P * n_inner, dtype=torch.complex64, device=src.device)
+    _lib.check(lib.sc_table_contract(_ptr(table), s_p, s_q, int(conj), _ptr(src), _ptr(out), n_outer, P, Q, n_inner,
+                                     _stream_ptr(src.device)), "sc_table_contract")
+    return out
+
+
+def _pair_reduce(a, b, out, s_p, s_q, n_outer, P, Q, n_inner):
+    """out.flat[p * s_p + q * s_q] = sum_{o,i} conj(a[o,p,i]) * b[o,q,i]."""
+    lib = _lib.load()
+    _lib.check(lib.sc_pair_reduce(_ptr(a), _ptr(b), _ptr(out), s_p, s_q, n_outer, P, Q, n_inner, _stream_ptr(a.device)),
+               "sc_pair_reduce")
+    return out
+
+
+class _SpectralConvTucker(torch.autograd.Function):
+    """y = SpectralConv.forward(x) with a Tucker weight, contracted factor by factor (einsum `abcd,fghi,bf,eg,ch,di->aecd`,
+    reference :86-98):  xm -> U_in -> (core expanded along the mode axes with the kept rows of the mode factors) -> U_out.
+    Inputs: x, core (r_in, r_out, r_1..r_d), U_in (Ci, r_in), U_out (Co, r_out), mode factors ALREADY sliced to the kept rows
+    (k_j, r_j) -- autograd handles the slicing --, bias.  `plan_kept` is a plan whose weight extents equal the kept modes."""
+
+    @staticmethod
+    def forward(ctx, x, bias, plan, plan_kept, core, u_in, u_out, *u_modes):
+        lib = _lib.load()
+        dev = x.device
+        B, Ci = x.shape[:2]
+        Co, rg = u_out.shape
+        rf = u_in.shape[1]
+        d = plan.ndim
+        kept = plan.kept
+        M = plan.n_modes_total
+        ranks = list(core.shape[2:])
+        with torch.cuda.device(dev):
+            xm = analyze(plan, x)                                                   # (B, Ci, *kept)
+            # expand the core along the mode axes, last axis first: A_d = core, A_{j-1} = U_j x_j A_j
+            chain = [core.contiguous()]
+            for j in range(d - 1, -1, -1):
+                outer = rf * rg
+                for l in range(j):
+                    outer *= ranks[l]
+                inner = 1
+                for l in range(j + 1, d):
+                    inner *= kept[l]
+                uj = u_modes[j]
+                chain.append(_table_contract(uj, uj.shape[1], 1, False, chain[-1], outer, kept[j], ranks[j], inner))
+            wc = chain[-1]                                                          # (rf, rg, *kept)
+            t1 = _table_contract(u_in, 1, rf, False, xm, B, rf, Ci, M)              # T[p=f, q=i] = U_in[i, f]
+            t2 = contract_dense(plan_kept, t1.view(B, rf, *kept), wc.view(rf, rg, *kept))
+            ym = _table_contract(u_out, rg, 1, False, t2, B, Co, rg, M)             # T[p=o, q=g] = U_out[o, g]
+            y = synthesize(plan, ym.view(B, Co, *kept), bias)
+        ctx.plan, ctx.plan_kept, ctx.d = plan, plan_kept, d
+        ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.dims = (B, Ci, Co, rf, rg, M, ranks)
+        ctx.save_for_backward(xm, t1, t2, wc, u_in, u_out, *u_modes, *chain[:-1])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        plan, plan_kept, d = ctx.plan, ctx.plan_kept, ctx.d
+        B, Ci, Co, rf, rg, M, ranks = ctx.dims
+        kept = plan.kept
+        saved = ctx.saved_tensors
+        xm, t1, t2, wc, u_in, u_out = saved[:6]
+        u_modes = saved[6:6 + d]
+        chain = saved[6 + d:]                    # A_d (= core), A_{d-1}, ..., A_1
+        dev = gy.device
+        gy = gy.contiguous()
+        cplx = dict(dtype=torch.complex64, device=dev)
+        with torch.cuda.device(dev):
+            gm = analyze(plan, gy, adjoint=True)                                    # (B, Co, *kept)
+            db = None
+            if ctx.bias_shape is not None:
+                db = torch.empty(Co, dtype=torch.float32, device=dev)
+                _lib.check(lib.sc_bias_grad(plan.handle, _ptr(gm), _ptr(db), B, Co, _stream_ptr(dev)), "sc_bias_grad")
+                db = db.reshape(ctx.bias_shape)
+            # out side
+            g2 = _table_contract(u_out, 1, rg, True, gm, B, rg, Co, M)              # T[p=g, q=o] = conj(U_out[o, g])
+            d_u_out = _pair_reduce(t2, gm, torch.empty(Co, rg, **cplx), 1, rg, B, rg, Co, M)      # out[(g,o)] -> dU_out[o, g]
+            # core side: the same two mode GEMMs as the dense backward, on rank channels
+            g1, d_wc, _ = contract_dense_backward(plan_kept, t1.view(B, rf, *kept), g2.view(B, rg, *kept),
+                                                  wc.view(rf, rg, *kept), need_dbias=False)
+            # in side
+            d_u_in = _pair_reduce(xm, g1, torch.empty(Ci, rf, **cplx), rf, 1, B, Ci, rf, M)       # out[(i,f)] -> dU_in[i, f]
+            dxm = _table_contract(u_in, rf, 1, True, g1, B, Ci, rf, M)              # T[p=i, q=f] = conj(U_in[i, f])
+            dx = synthesize(plan, dxm.view(B, Ci, *kept), adjoint=True)
+            # mode factors and core: undo the expansion chain, first axis first
+            d_modes = [None] * d
+            d_a = d_wc.reshape(-1)
+            for j in range(d):
+                a_j = chain[d - 1 - j]                                               # A_{j+1} in 1-based terms: before axis j was expanded
+                outer = rf * rg
+                for l in range(j):
+                    outer *= ranks[l]
+                inner = 1
+                for l in range(j + 1, d):
+                    inner *= kept[l]
+                uj = u_modes[j]
+                d_modes[j] = _pair_reduce(a_j, d_a, torch.empty(kept[j], ranks[j], **cplx), 1, ranks[j], outer, ranks[j],
+                                          kept[j], inner)                           # out[(h,m)] -> dU_j[m, h]
+                d_a = _table_contract(uj, 1, ranks[j], True, d_a, outer, ranks[j], kept[j], inner)   # T[p=h, q=m] = conj(U_j[m, h])
+            d_core = d_a.view(rf, rg, *ranks)
+        return (dx, db, None, None, d_core, d_u_in, d_u_out, *d_modes)
+
+
+# --------------------------------------------------------------------------------------------------
 # the module
 # --------------------------------------------------------------------------------------------------
 def _validate_scaling_factor(factor, n_dim) -> Optional[List[float]]:
@@ -375,6 +485,18 @@ class SpectralConv(BaseSpectralConv):
         raise NotImplementedError("SpectralConv.transform with a resolution change needs the reference's "
                                   "`resample` (neuralop/layers/resample.py), which is outside the spectral-conv path")
 
+    def _forward_tucker(self, x, plan: Plan):
+        """Factor-by-factor contraction (reference implementation="factorized", `_contract_tucker` :76-103)."""
+        w = self.weight
+        factors = list(w.factors)
+        u_in, u_out = factors[0].contiguous(), factors[1].contiguous()
+        u_modes = []
+        for j in range(self.order):                      # rows of the mode factors the kept block uses (`weight[slices_w]`, :489)
+            _, rows = plan.mode_bins(j)
+            u_modes.append(factors[2 + j][rows[0]:rows[0] + len(rows)].contiguous())
+        plan_kept = get_plan(x.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
+        return _SpectralConvTucker.apply(x, self.bias, plan, plan_kept, w.core, u_in, u_out, *u_modes)
+
     def forward(self, x: torch.Tensor, output_shape: Optional[Tuple[int]] = None):
         if x.ndim != self.order + 2:
             raise ValueError(f"expected input of shape (batch, channels, {self.order} spatial dims), got {tuple(x.shape)}")
@@ -388,7 +510,10 @@ class SpectralConv(BaseSpectralConv):
         out_grid = self._output_grid(grid, output_shape)
         plan = get_plan(x.device, grid, out_grid, self.n_modes, self.max_n_modes, self.fft_norm)
         x = x.contiguous()
-        # dense weight goes straight to the kernels; a factorized one is reconstructed first (differentiably)
+        if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "tucker" and \
+                self.in_channels <= 64 and self.out_channels <= 64:
+            return self._forward_tucker(x, plan)
+        # dense weight goes straight to the kernels; other factorized forms are reconstructed first (differentiably)
         w = self.weight.to_tensor()
         if not w.is_contiguous():
             w = w.contiguous()
