@@ -66,55 +66,51 @@ def ncu_traffic(plan):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons WHILE the timed region runs.  The timed region is only ~10 ms (50 steps of
+    0.2 ms), far below nvidia-smi's sampling period, so NVML is polled directly from a thread (about every millisecond)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index=0):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.mask = 0
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._nvml = None
+            return
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        self._thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self._nvml is None or self._thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self._stop.set()
+        self._thread.join(timeout=2)
+        sm = sorted(self.samples)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm), "reasons": reasons}
 
 
 def cpu_oracle_step_time(steps, warmup, max_seconds=None):
@@ -291,29 +287,60 @@ def run_ours(args):
         dwh = torch.empty(conv.weight.tensor.shape, dtype=torch.complex64).pin_memory()
         dbh = torch.empty(conv.bias.shape).pin_memory()
 
+        # Host buffers in, host buffers out, every step.  The three legs run on their own streams (H2D of step i+1 and D2H
+        # of step i-1 overlap the kernels of step i; PCIe is full duplex), double-buffered on the device side.
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        xd_buf = [torch.empty(B, C, H, W, device=dev) for _ in range(2)]
+        gd_buf = [torch.empty(B, C, H, W, device=dev) for _ in range(2)]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        for e in ev_free:
+            e.record(main)
+        state = {"i": 0}
+
         def e2e_step():
+            i = state["i"]; state["i"] += 1
+            sb = i & 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_free[sb])                       # the kernels that last read this buffer pair are done
+                xd_buf[sb].copy_(xh, non_blocking=True)
+                gd_buf[sb].copy_(gh, non_blocking=True)
+                ev_in[sb].record(s_in)
+            main.wait_event(ev_in[sb])
             conv.weight.tensor.grad = None
             conv.bias.grad = None
-            xd2 = xh.to(dev, non_blocking=True).requires_grad_(True)
-            gd2 = gh.to(dev, non_blocking=True)
+            xd2 = xd_buf[sb].detach().requires_grad_(True)    # fresh leaf over the same storage
             y = conv(xd2)
-            y.backward(gd2)
+            y.backward(gd_buf[sb])
             if reducer is not None:
                 reducer.start()
                 reducer.finish()
-            yh.copy_(y.detach(), non_blocking=True)
-            dxh.copy_(xd2.grad, non_blocking=True)
-            dwh.copy_(conv.weight.tensor.grad, non_blocking=True)
-            dbh.copy_(conv.bias.grad, non_blocking=True)
+            ev_free[sb].record(main)
+            outs = (y.detach(), xd2.grad, conv.weight.tensor.grad, conv.bias.grad)
+            s_out.wait_stream(main)
+            with torch.cuda.stream(s_out):
+                for t in outs:
+                    t.record_stream(s_out)
+                yh.copy_(outs[0], non_blocking=True)
+                dxh.copy_(outs[1], non_blocking=True)
+                dwh.copy_(outs[2], non_blocking=True)
+                dbh.copy_(outs[3], non_blocking=True)
+
+        def e2e_join():
+            main.wait_stream(s_in)
+            main.wait_stream(s_out)
 
         for _ in range(3):
             e2e_step()
+        e2e_join()
         barrier()
         n_e2e = max(5, min(args.steps, 20))
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for _ in range(n_e2e):
             e2e_step()
+        e2e_join()
         a1.record()
         barrier()
         t2 = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
