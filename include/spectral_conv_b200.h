@@ -120,6 +120,8 @@ const char* sc_build_info(void);          /* "sm_100a nvcc <ver> ..." */
 /* tcgen05 bring-up check: d[128 x n] = bf16(a[128 x k]) * bf16(b[n x k])^T accumulated in FP32 in TMEM, through the
  * same operand staging / descriptors / TMEM read-back the fused transform kernels use (device pointers, fp32). */
 int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream);
+/* the same product with the A operand resident in tensor memory (tcgen05.st + TMEM-A tcgen05.mma) */
+int sc_selftest_umma_ts(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream);
 
 #ifdef __cplusplus
 }

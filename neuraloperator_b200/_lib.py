@@ -56,6 +56,7 @@ SIGNATURES = {
     "sc_kernel_launch_count": (ctypes.c_uint64, []),
     "sc_build_info": (ctypes.c_char_p, []),
     "sc_selftest_umma": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
+    "sc_selftest_umma_ts": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
 }
 
 _lock = threading.Lock()

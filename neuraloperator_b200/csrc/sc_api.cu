@@ -531,6 +531,12 @@ int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_
   return 0;
 }
 
+int sc_selftest_umma_ts(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream) {
+  SC_REQUIRE(a != nullptr && b != nullptr && d != nullptr, "sc_selftest_umma_ts: null argument");
+  SC_TRY(umma_selftest_ts(a, b, d, n, k, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 const char* sc_last_error(void) { return t_error.c_str(); }
 uint64_t sc_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* sc_build_info(void) {

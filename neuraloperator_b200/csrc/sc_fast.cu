@@ -70,6 +70,75 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+// same product with the A operand resident in TENSOR MEMORY (tcgen05.st, then tcgen05.mma with a TMEM A operand)
+__global__ void __launch_bounds__(128) k_umma_selftest_ts(const float* __restrict__ A, const float* __restrict__ B,
+                                                           float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  uint8_t* sB = smem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) tmem_alloc(&tmem_base, 256);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+  for (int idx = tid; idx < N * K; idx += 128) {
+    const int r = idx / K, k = idx % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + sw128_offset(r, k, N)) = __float2bfloat16_rn(B[idx]);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t tm_a = tmem + 128;                          // A: columns 128 .. 128 + K/2
+  {
+    const int row = warp * 32 + lane;
+    for (int c = 0; c < K / 2; c += 16) {
+      uint32_t w[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) w[e] = pack_bf16(A[(size_t)row * K + 2 * (c + e)], A[(size_t)row * K + 2 * (c + e) + 1]);
+      tmem_st16(tm_a + ((uint32_t)(warp * 32) << 16) + c, w);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (tid == 0) {
+    const uint32_t idesc = idesc_bf16(128, N);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const int slab = ks >> 2, kk = ks & 3;
+      mma_bf16_ts(tmem, tm_a + ks * 8, smem_desc_sw128(smem_u32(sB) + slab * N * 128 + kk * 32), idesc, ks > 0);
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after_sync();
+  for (int c = 0; c < N; c += 16) {
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[(size_t)(warp * 32 + lane) * N + c + i] = v[i];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+bool umma_selftest_ts(const float* A, const float* B, float* D, int N, int K, cudaStream_t st) {
+  if (N < 16 || N > 128 || N % 16 != 0 || K < 64 || K > 256 || K % 64 != 0) {
+    set_error("umma selftest: need N in 16..128 step 16 and K in 64..256 step 64");
+    return false;
+  }
+  const size_t smem = (size_t)N * K * 2 + 1024;
+  if (!cuda_ok(cudaFuncSetAttribute(k_umma_selftest_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "cudaFuncSetAttribute(selftest_ts)"))
+    return false;
+  k_umma_selftest_ts<<<1, 128, smem, st>>>(A, B, D, N, K);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_umma_selftest_ts launch");
+}
+
 bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaStream_t st) {
   if (N < 16 || N > 128 || N % 16 != 0 || K < 64 || K > 256 || K % 64 != 0) {
     set_error("umma selftest: need N in 16..128 step 16 and K in 64..256 step 64");
@@ -117,7 +186,8 @@ struct AnaParams {
   const float* x;
   float2* out;
   const uint8_t* b1_img;   // [2*N1 x W] bf16, canonical K-major SW128 image (T1 rows then T2 rows)
-  const uint8_t* a2_img;   // [128 x 256] bf16 image of the real-embedded leading-dim table (T1 rows 0-63, T2 rows 64-127)
+  const uint8_t* a2_img;   // [128 x 256] bf16, plain row-major: real-embedded leading-dim table (T1 rows 0-63, T2 rows 64-127);
+                           // copied once into TENSOR MEMORY and used as the TMEM A operand of every stage-2 MMA
   int n_tiles, W, slabs, N1, KX, QROWS, n_stages, tmem_cols;
   uint32_t off_f32, off_ring, off_b1, off_a2, off_b2, off_scratch, stage_off;   // stage_off: output staging, relative to off_scratch
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
@@ -135,7 +205,6 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = P.n_stages;
   uint8_t* s_b1 = smem + P.off_b1;
-  uint8_t* s_a2 = smem + P.off_a2;
   uint8_t* s_b2 = smem + P.off_b2;
   float* s_scr = reinterpret_cast<float*>(smem + P.off_scratch);
 
@@ -158,7 +227,22 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // constant operand images are staged by the consumer-side warps only; the loaders start streaming x at once
     constexpr int NT = FA_LOADER_WARP0 * 32;
     copy_image(s_b1, P.b1_img, (2 * N1 * P.W * 2) / 16, tid, NT);
-    copy_image(s_a2, P.a2_img, (128 * 256 * 2) / 16, tid, NT);
+    if (warp < 4) {   // leading-dim table -> tensor memory: lane = table row, two bf16 K-elements per 32-bit column
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(P.a2_img) + (size_t)(warp * 32 + lane) * 128;
+      const uint32_t tm_a2_w = tmem_base_slot + (uint32_t)(6 * N1) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 2
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t w[16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + c + e));
+          w[e] = v.x; w[e + 1] = v.y; w[e + 2] = v.z; w[e + 3] = v.w;
+        }
+        tmem_st16(tm_a2_w + c, w);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+    }
     uint4* z = reinterpret_cast<uint4*>(s_b2);   // padding rows of B2 (kx >= KX) stay zero for the whole kernel
     for (int i = tid; i < (N1 * 512) / 16; i += NT) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
@@ -167,6 +251,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
   const uint32_t tmem = tmem_base_slot;
   const uint32_t tm_d1[2] = {tmem, tmem + (uint32_t)(2 * N1)};
   const uint32_t tm_d2[2] = {tmem + (uint32_t)(4 * N1), tmem + (uint32_t)(5 * N1)};
+  const uint32_t tm_a2 = tmem + (uint32_t)(6 * N1);
 
   const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -265,7 +350,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // ------------------------------------------------------------------ stage-2 MMA issuer
     {
       const uint32_t idesc_p2 = idesc_bf16(128, N1);
-      const uint32_t a2_lo = desc_lo(smem_u32(s_a2)), b2_lo = desc_lo(smem_u32(s_b2));
+      const uint32_t b2_lo = desc_lo(smem_u32(s_b2));
       for (int i = 0; i < n_local; ++i) {
         const int buf = i & 1;
         SC_TRACE(P, 3, i, 0);
@@ -277,8 +362,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 #pragma unroll
           for (int ks = 0; ks < 16; ++ks) {
             const int slab = ks >> 2, kk = ks & 3;
-            mma_bf16_ss(tm_d2[buf], desc_from_lo(a2_lo + slab * ((128 * 128) >> 4) + 2 * kk),
-                        desc_from_lo(b2_lo + slab * ((N1 * 128) >> 4) + 2 * kk), idesc_p2, ks > 0);
+            mma_bf16_ts(tm_d2[buf], tm_a2 + ks * 8, desc_from_lo(b2_lo + slab * ((N1 * 128) >> 4) + 2 * kk), idesc_p2, ks > 0);
           }
           mma_commit(&bar_b2_empty);
           mma_commit(&bar_d2_full[buf]);
@@ -1231,24 +1315,29 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   if (W % 64 != 0 || W > 128 || H < 16 || 128 % H != 0) return true;
   const int G = 128 / H;
   const int N1 = ((2 * KX + 15) / 16) * 16;
-  if (N1 > 80 || G * KY > 32 || KX < 1 || KY < 1) return true;
+  if (N1 > 64 || G * KY > 32 || KX < 1 || KY < 1) return true;   // TMEM: D1[2] + D2[2] + the 128-column table = 6*N1 + 128 <= 512
   t->W = W; t->H = H; t->G = G; t->N1 = N1; t->KX = KX; t->KY = KY; t->slabs = W / 64;
-  t->tmem_cols = 6 * N1 <= 256 ? 256 : 512;
+  t->tmem_cols = 6 * N1 + 128 <= 256 ? 256 : 512;
   // ---- B1: [2*N1 x W]
   std::vector<uint8_t> b1((size_t)2 * N1 * W * 2, 0);
   for (int j = 0; j < 2 * KX; ++j)
     for (int w = 0; w < W; ++w) put_split(b1, 2 * N1, j, N1 + j, w, tab[(size_t)w * 2 * KX + j]);
   // ---- A2: [128 x 256]; row i' = 2*(g*KY + ky) + p_out (T1), 64 + i' (T2); column k2 = 2*(g*H + h) + p_in
-  std::vector<uint8_t> a2((size_t)128 * 256 * 2, 0);
+  std::vector<uint16_t> a2((size_t)128 * 256, 0);   // plain row-major [row][k2]
+  auto put_plain = [&](int r1, int r2, int k, float v) {
+    const uint16_t t1 = bf16_bits(v);
+    a2[(size_t)r1 * 256 + k] = t1;
+    a2[(size_t)r2 * 256 + k] = bf16_bits(v - bf16_to_float(t1));
+  };
   for (int g = 0; g < G; ++g)
     for (int ky = 0; ky < KY; ++ky)
       for (int h = 0; h < H; ++h) {
         const float2 f = lead[(size_t)ky * H + h];
         const int q = g * KY + ky, hl = g * H + h;
-        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 2 * hl + 0, f.x);
-        put_split(a2, 128, 2 * q + 0, 64 + 2 * q + 0, 2 * hl + 1, -f.y);
-        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 2 * hl + 0, f.y);
-        put_split(a2, 128, 2 * q + 1, 64 + 2 * q + 1, 2 * hl + 1, f.x);
+        put_plain(2 * q + 0, 64 + 2 * q + 0, 2 * hl + 0, f.x);
+        put_plain(2 * q + 0, 64 + 2 * q + 0, 2 * hl + 1, -f.y);
+        put_plain(2 * q + 1, 64 + 2 * q + 1, 2 * hl + 0, f.y);
+        put_plain(2 * q + 1, 64 + 2 * q + 1, 2 * hl + 1, f.x);
       }
   if (!upload_bytes(p, b1, &t->d_b1) || !upload_bytes(p, a2, &t->d_a2)) return false;
   // ---- shared-memory carve-up
@@ -1256,7 +1345,7 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   const uint32_t scr_bytes = (64u * (uint32_t)(N1 / 2 + 1) * 4u + 15u) & ~15u;
   const uint32_t scratch_total = (scr_bytes + 2u * (uint32_t)(G * KY * KX) * 8u + 1023u) & ~1023u;
   t->stage_off = scr_bytes;
-  const uint32_t fixed = (uint32_t)b1.size() + 65536u + (uint32_t)N1 * 512u + scratch_total;
+  const uint32_t fixed = (uint32_t)b1.size() + (uint32_t)N1 * 512u + scratch_total;   // B1 + B2 + scratch (the leading-dim table lives in TMEM)
   // [fp32 staging: 2 slabs x 32 KB][bf16 hi/lo ring: `stages` x 32 KB][B1][A2][B2][scratch]
   int stages = (int)(((227u * 1024u - 4096u - fixed) - 65536u) / FA_STAGE_BYTES);
   if (227u * 1024u - 4096u < fixed + 65536u + FA_STAGE_BYTES) return true;
@@ -1267,7 +1356,7 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   t->off_ring = 65536u;
   t->off_b1 = t->off_ring + (uint32_t)stages * FA_STAGE_BYTES;
   t->off_a2 = t->off_b1 + (uint32_t)b1.size();
-  t->off_b2 = t->off_a2 + 65536u;
+  t->off_b2 = t->off_a2;
   t->off_scratch = t->off_b2 + (uint32_t)N1 * 512u;
   t->smem_bytes = t->off_scratch + scratch_total + 1024u;
   t->ok = true;
@@ -1452,7 +1541,7 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
     }                                                                                                            \
     k_fused_analysis<N><<<grid, FA_THREADS, t.smem_bytes, st>>>(P, x_map);                                              \
   } break;
-    SC_FA_CASE(16) SC_FA_CASE(32) SC_FA_CASE(48) SC_FA_CASE(64) SC_FA_CASE(80)
+    SC_FA_CASE(16) SC_FA_CASE(32) SC_FA_CASE(48) SC_FA_CASE(64)
 #undef SC_FA_CASE
     default: set_error("fast_analyze: unsupported N1"); return false;
   }

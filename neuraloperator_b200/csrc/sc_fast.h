@@ -23,6 +23,7 @@ bool fast_can_contract(const Plan* p, int B, int Ci, int Co);
 bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long long sAK, const int* offA, bool conjA,
                          const float2* b, long long sBN, long long sBK, const int* offB, float2* out, long long sOR,
                          long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st);
+bool umma_selftest_ts(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
 bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
 
 }  // namespace sc

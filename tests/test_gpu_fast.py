@@ -10,6 +10,23 @@ from neuraloperator_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("N,K", [(48, 64), (48, 256), (96, 128)])
+def test_umma_selftest_tmem_a_operand(cuda_device, N, K):
+    """A operand written to tensor memory with tcgen05.st and consumed by a TMEM-A tcgen05.mma."""
+    lib = _lib.load()
+    torch.manual_seed(N * 1000 + K + 1)
+    a = torch.randn(128, K, device=cuda_device)
+    b = torch.randn(N, K, device=cuda_device)
+    d = torch.full((128, N), float("nan"), device=cuda_device)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(cuda_device).cuda_stream)
+    _lib.check(lib.sc_selftest_umma_ts(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                                       ctypes.c_void_p(d.data_ptr()), N, K, stream), "sc_selftest_umma_ts")
+    torch.cuda.synchronize()
+    ref = a.bfloat16().double() @ b.bfloat16().double().T
+    err = (d.double() - ref).abs().max().item()
+    assert err < 1e-3 * max(ref.abs().max().item(), 1.0), f"max err {err}"
+
+
 @pytest.mark.parametrize("N,K", [(16, 64), (48, 64), (96, 128), (128, 128), (48, 256)])
 def test_umma_selftest(cuda_device, N, K):
     """tcgen05.mma with hand-swizzled bf16 operands, FP32 accumulation in TMEM, tcgen05.ld read-back."""
