@@ -174,6 +174,7 @@ bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaS
       (P).trace[(((role) * 16 + (i)) * 4 + (ph))] = clock64();                                          \
   } while (0)
 
+constexpr int FA_F32_STAGES = 3;   // depth of the fp32 TMA staging ring (32 KB slabs): covers the HBM latency under load
 constexpr int FA_LOADER_WARPS = 8;
 constexpr int FA_LOADER_ITERS = 128 / (FA_LOADER_WARPS * 2);   // row passes per slab: a loader warp covers 2 rows x 64 floats
 constexpr int FA_LOADER_WARP0 = 10;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
   __shared__ uint64_t bar_full[4], bar_empty[4], bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_b2_empty,
-      bar_d2_full[2], bar_d2_empty[2], bar_f32_full[2], bar_f32_empty[2];
+      bar_d2_full[2], bar_d2_empty[2], bar_f32_full[FA_F32_STAGES], bar_f32_empty[FA_F32_STAGES];
   __shared__ uint32_t tmem_base_slot;
   constexpr int half = N1 / 2;
 
@@ -213,8 +214,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_d1_full[i], 1); mbar_init(&bar_d1_empty[i], 128);
       mbar_init(&bar_d2_full[i], 1); mbar_init(&bar_d2_empty[i], 128);
-      mbar_init(&bar_f32_full[i], 1); mbar_init(&bar_f32_empty[i], FA_LOADER_WARPS);
     }
+    for (int i = 0; i < FA_F32_STAGES; ++i) { mbar_init(&bar_f32_full[i], 1); mbar_init(&bar_f32_empty[i], FA_LOADER_WARPS); }
     mbar_init(&bar_b2_full, 128);
     mbar_init(&bar_b2_empty, 1);
     mbar_init_fence();
@@ -260,8 +261,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     const int total = n_local * P.slabs;
     uint8_t* f32_stage = smem + P.off_f32;
     for (int idx = 0; idx < total; ++idx) {
-      const int sb = idx & 1;
-      mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx >> 1) & 1) ^ 1));
+      const int sb = idx % FA_F32_STAGES;
+      mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx / FA_F32_STAGES) & 1) ^ 1));
       if (elect_one()) {
         const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
         mbar_arrive_expect_tx(&bar_f32_full[sb], 32768u);
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     }
   } else if (warp >= FA_LOADER_WARP0) {
     // ------------------------------------------------------------------ converters
-    // x arrives in a two-deep fp32 staging ring ([128 x 64] fp32 per slab, written by the TMA engine: 64 KB in flight per
+    // x arrives in a FA_F32_STAGES-deep fp32 staging ring ([128 x 64] fp32 per slab, written by the TMA engine: 64 KB in flight per
     // SM, no registers, no LSU issue slots); each thread splits its 16-byte pieces into bf16 hi/lo operand tiles.
     const int lt = tid - FA_LOADER_WARP0 * 32;
     constexpr int RP = FA_LOADER_WARPS * 2;      // rows covered per pass
@@ -283,9 +284,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     for (int idx = 0; idx < total; ++idx, ++g) {
       const int slot = (int)(g % (uint32_t)NS);
       const uint32_t ph = (g / (uint32_t)NS) & 1u;
-      const int sb = idx & 1;
+      const int sb = idx % FA_F32_STAGES;
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 0);
-      mbar_wait(&bar_f32_full[sb], (uint32_t)((idx >> 1) & 1));
+      mbar_wait(&bar_f32_full[sb], (uint32_t)((idx / FA_F32_STAGES) & 1));
       if (warp == FA_LOADER_WARP0) SC_TRACE(P, 7, idx, 0);
       uint2 hi[FA_LOADER_ITERS], lo[FA_LOADER_ITERS];
       const uint8_t* fsrc = f32_stage + sb * 32768 + my_f32;
@@ -1346,14 +1347,15 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   const uint32_t scratch_total = (scr_bytes + 2u * (uint32_t)(G * KY * KX) * 8u + 1023u) & ~1023u;
   t->stage_off = scr_bytes;
   const uint32_t fixed = (uint32_t)b1.size() + (uint32_t)N1 * 512u + scratch_total;   // B1 + B2 + scratch (the leading-dim table lives in TMEM)
-  // [fp32 staging: 2 slabs x 32 KB][bf16 hi/lo ring: `stages` x 32 KB][B1][A2][B2][scratch]
-  int stages = (int)(((227u * 1024u - 4096u - fixed) - 65536u) / FA_STAGE_BYTES);
-  if (227u * 1024u - 4096u < fixed + 65536u + FA_STAGE_BYTES) return true;
+  // [fp32 staging: FA_F32_STAGES slabs x 32 KB][bf16 hi/lo ring: `stages` x 32 KB][B1][B2][scratch]
+  const uint32_t f32_bytes = (uint32_t)FA_F32_STAGES * 32768u;
+  int stages = (int)(((227u * 1024u - 4096u - fixed) - f32_bytes) / FA_STAGE_BYTES);
+  if (227u * 1024u - 4096u < fixed + f32_bytes + FA_STAGE_BYTES) return true;
   if (stages > 4) stages = 4;
   if (stages < 1) return true;
   t->n_stages = stages;
   t->off_f32 = 0;
-  t->off_ring = 65536u;
+  t->off_ring = f32_bytes;
   t->off_b1 = t->off_ring + (uint32_t)stages * FA_STAGE_BYTES;
   t->off_a2 = t->off_b1 + (uint32_t)b1.size();
   t->off_b2 = t->off_a2;
