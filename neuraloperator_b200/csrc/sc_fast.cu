@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = P.n_stages;
+  pdl_launch_dependents();   // the next kernel may take over each SM as soon as this CTA leaves it
   uint8_t* s_b1 = smem + P.off_b1;
   uint8_t* s_b2 = smem + P.off_b2;
   float* s_scr = reinterpret_cast<float*>(smem + P.off_scratch);
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // ------------------------------------------------------------------ TMA producer: one tensor load per 32 KB slab
     const int total = n_local * P.slabs;
     uint8_t* f32_stage = smem + P.off_f32;
+    pdl_wait();                                  // x is produced by the previous kernel of the stream
     for (int idx = 0; idx < total; ++idx) {
       const int sb = idx % FA_F32_STAGES;
       mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx / FA_F32_STAGES) & 1) ^ 1));
@@ -414,6 +416,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     const int row = warp * 32 + lane;                        // output row i' (0-63: T1 rows, 64-127: T2 rows)
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     const int KX = P.KX;
+    pdl_wait();                                              // the mode buffer may still be read by the previous kernel
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       if (warp == 0) SC_TRACE(P, 4, i, 0);
@@ -520,6 +523,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W = P.W, KX = P.KX;
+  pdl_launch_dependents();
   uint8_t* s_aa = smem + P.off_aa;
   uint8_t* s_ba = smem + P.off_ba;
   uint8_t* s_u = smem + P.off_u;
@@ -562,6 +566,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     const uint32_t o_re = sw128_offset(2 * kx0, 2 * q, 2 * N1), o_im = sw128_offset(2 * kx0 + 1, 2 * q, 2 * N1);
     constexpr uint32_t T2 = 2 * N1 * 128;    // second K-slab (columns 64 + k): hi * T2
     constexpr uint32_t LO = N1 * 128;        // rows N1 + n: lo * T1
+    pdl_wait();                              // the modes are produced by the previous kernel of the stream
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -708,6 +713,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     uint8_t* my_stage = smem + P.off_stage + warp * 8192;   // two [32 x 128 B] boxes per warp
     uint32_t chunk_ctr = 0;
+    pdl_wait();                                             // the output image may still be read by the previous kernel
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       const uint32_t ph = (uint32_t)((i >> 1) & 1);
@@ -980,6 +986,7 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   __shared__ uint32_t tmem_base_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rowsB = 2 * P.NBp;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     mbar_init(&bar_full, MG2_LOADER_WARPS);
@@ -998,6 +1005,7 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_slot;
   const long long m0 = (long long)blockIdx.x * 4;      // first mode of this CTA's quad
+  pdl_wait();                                          // operands come from / the output goes to buffers of the previous kernel
 
   if (warp >= 4) {
     // ------------------------------------------------------------------ loaders
@@ -1136,6 +1144,7 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
 }
 
 static int fast_sm_count(const Plan* p);   // defined with FastTables below
+static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args);
 
 static bool mode_gemm_tc_supported(int MR, int NB, int KC) {
   return MR >= 1 && MR <= 64 && NB >= 1 && NB <= 64 && KC >= 1 && KC <= 64;
@@ -1164,9 +1173,10 @@ static bool launch_mode_gemm_quad(const Plan* p, const float2* a, long long sAR,
       return false;
     attr_bytes = smem_bytes;
   }
-  k_mode_gemm_quad<<<P.n_groups, MGQ_THREADS, smem_bytes, st>>>(P);
   count_launch();
-  return cuda_ok(cudaGetLastError(), "k_mode_gemm_quad launch");
+  void* args[] = {(void*)&P};
+  return cuda_ok(launch_pdl((const void*)k_mode_gemm_quad, dim3(P.n_groups), dim3(MGQ_THREADS), smem_bytes, st, args),
+                 "k_mode_gemm_quad launch");
 }
 
 static inline bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31u) == 0; }
@@ -1495,6 +1505,18 @@ static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t row
   return true;
 }
 
+// launch with programmatic stream serialization: the kernel may begin (prologue only; see pdl_wait) before the previous
+// kernel of the stream has drained
+static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelExC(&cfg, func, args);
+}
+
 // SC_TRACE_FILE=<path>: record the per-role timeline of CTA 0 of every fused transform launch (debug only; synchronises)
 static long long* trace_begin() {
   if (getenv("SC_TRACE_FILE") == nullptr) return nullptr;
@@ -1541,7 +1563,9 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
         return false;                                                                                            \
       attr_bytes = t.smem_bytes;                                                                                 \
     }                                                                                                            \
-    k_fused_analysis<N><<<grid, FA_THREADS, t.smem_bytes, st>>>(P, x_map);                                              \
+    { void* args[] = {(void*)&P, (void*)&x_map};                                                               \
+      if (!cuda_ok(launch_pdl((const void*)k_fused_analysis<N>, dim3(grid), dim3(FA_THREADS), t.smem_bytes, st, args), \
+                   "k_fused_analysis launch")) return false; }                                              \
   } break;
     SC_FA_CASE(16) SC_FA_CASE(32) SC_FA_CASE(48) SC_FA_CASE(64)
 #undef SC_FA_CASE
@@ -1576,7 +1600,9 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
         return false;                                                                                            \
       attr_bytes = t.smem_bytes;                                                                                 \
     }                                                                                                            \
-    k_fused_synthesis<N><<<grid, FS_THREADS, t.smem_bytes, st>>>(P, out_map);                                             \
+    { void* args[] = {(void*)&P, (void*)&out_map};                                                             \
+      if (!cuda_ok(launch_pdl((const void*)k_fused_synthesis<N>, dim3(grid), dim3(FS_THREADS), t.smem_bytes, st, args), \
+                   "k_fused_synthesis launch")) return false; }                                             \
   } break;
     SC_FS_CASE(16) SC_FS_CASE(32) SC_FS_CASE(48) SC_FS_CASE(64)
 #undef SC_FS_CASE

@@ -192,6 +192,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// Programmatic dependent launch: the next kernel of the stream may start its prologue on SMs this grid has already left;
+// `pdl_wait` blocks until every prerequisite grid has completed and its memory operations are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- canonical K-major / SWIZZLE_128B addressing for bf16 tiles ---------------------------------------------
 // A tile [rows x K] is stored as K/64 slabs of [rows x 64]; byte offset of element (r, k) inside the tile:
 __device__ __forceinline__ uint32_t sw128_offset(int r, int k, int rows) {

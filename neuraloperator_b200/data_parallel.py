@@ -26,6 +26,30 @@ class GradientAllReducer:
     def _as_real(t: torch.Tensor) -> torch.Tensor:
         return torch.view_as_real(t) if t.is_complex() else t
 
+    @staticmethod
+    def _coalesce(tensors):
+        """Merge float32 tensors that sit back to back in one storage (SpectralConv.backward lays dweight and dbias out
+        that way) into single flat views: one collective instead of one per tensor."""
+        out, i = [], 0
+        while i < len(tensors):
+            t = tensors[i]
+            j = i
+            end = t.data_ptr() + t.numel() * t.element_size()
+            total = t.numel()
+            while (j + 1 < len(tensors) and t.is_contiguous() and tensors[j + 1].is_contiguous()
+                   and tensors[j + 1].dtype == t.dtype and tensors[j + 1].device == t.device
+                   and tensors[j + 1].untyped_storage().data_ptr() == t.untyped_storage().data_ptr()
+                   and tensors[j + 1].data_ptr() == end):
+                j += 1
+                end += tensors[j].numel() * tensors[j].element_size()
+                total += tensors[j].numel()
+            if j > i:
+                out.append(torch.as_strided(t, (total,), (1,), storage_offset=t.storage_offset()))
+            else:
+                out.append(t)
+            i = j + 1
+        return out
+
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -35,7 +59,7 @@ class GradientAllReducer:
     def start_tensors(self, tensors: Iterable[torch.Tensor]):
         """Launch the all-reduce of `tensors` (in place). On CUDA it runs on a side stream that first waits for the work
         already queued on the current stream (the kernels that produced the tensors)."""
-        tensors = [t for t in tensors if t is not None]
+        tensors = self._coalesce([self._as_real(t) for t in tensors if t is not None])
         if self.world_size() == 1 or not tensors:
             return
         device = tensors[0].device

@@ -210,8 +210,15 @@ class _SpectralConvDense(torch.autograd.Function):
         Co = weight.shape[1]
         dev = gy.device
         dx = torch.empty((B, Ci, *plan.grid), dtype=torch.float32, device=dev) if need_dx else None
-        dw = torch.empty_like(weight) if need_dw else None
-        db = torch.empty(Co, dtype=torch.float32, device=dev) if need_db else None
+        if need_dw and need_db:
+            # dweight and dbias share one allocation so that a data-parallel reducer moves them with ONE collective
+            n_w = weight.numel() * 2
+            flat = torch.empty(n_w + Co, dtype=torch.float32, device=dev)
+            dw = torch.view_as_complex(flat[:n_w].view(*weight.shape, 2))
+            db = flat[n_w:]
+        else:
+            dw = torch.empty_like(weight) if need_dw else None
+            db = torch.empty(Co, dtype=torch.float32, device=dev) if need_db else None
         ws = _workspace(plan, B * max(Ci, Co), dev)
         reducer = ctx.reducer
         with torch.cuda.device(dev):
