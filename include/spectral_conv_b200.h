@@ -103,6 +103,20 @@ int sc_table_contract(const sc_complex* table, int64_t table_stride_p, int64_t t
 int sc_pair_reduce(const sc_complex* a, const sc_complex* b, sc_complex* out, int64_t out_stride_p, int64_t out_stride_q,
                    int64_t n_outer, int32_t P, int32_t Q, int32_t n_inner, sc_stream stream);
 
+/* ---- building blocks of the CP contraction, _contract_cp :55-73: out = U_out ( (x U_in) * scale ),  -------------------
+ *      scale[e, m] = lambda[e] * prod_j U_j[m_j, e]  (mode_factors[j]: kept rows of factor j, [kept[j] x rank] row-major) */
+int sc_cp_scale(const sc_complex* const* mode_factors, const int32_t* kept, int32_t ndim, const sc_complex* lambda,
+                sc_complex* scale, int32_t rank, sc_stream stream);
+/* out[a, e, m] = in[a, e, m] * op(scale[e, m])  (per_batch = rank * n_modes) */
+int sc_cp_apply(const sc_complex* in, const sc_complex* scale, sc_complex* out, int conj_scale, int32_t batch,
+                int64_t per_batch, sc_stream stream);
+/* dscale[e, m] = sum_a conj(t[a, e, m]) * g[a, e, m] */
+int sc_cp_dscale(const sc_complex* t, const sc_complex* g, sc_complex* dscale, int32_t batch, int64_t per_batch,
+                 sc_stream stream);
+/* gradient of lambda (which = -1, out[rank]) or of mode factor `which` (out[kept[which] x rank]) from dscale */
+int sc_cp_factor_grad(const sc_complex* const* mode_factors, const int32_t* kept, int32_t ndim, const sc_complex* lambda,
+                      const sc_complex* dscale, sc_complex* out, int32_t which, int32_t rank, sc_stream stream);
+
 /* ---- whole forward / backward for a dense weight (one call per autograd.Function.forward/backward) ------ */
 /* y = SpectralConv.forward(x); xm_saved (B,Ci,k..) is the only activation kept for backward. */
 int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weight, const float* bias,

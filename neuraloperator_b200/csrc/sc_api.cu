@@ -525,6 +525,49 @@ int sc_pair_reduce(const sc_complex* a, const sc_complex* b, sc_complex* out, in
   return 0;
 }
 
+static bool cp_args(const sc_complex* const* factors, const int32_t* kept, int32_t ndim, const float2** u, int* k) {
+  if (factors == nullptr || kept == nullptr || ndim < 1 || ndim > SC_MAX_DIMS) { set_error("cp: bad factor arguments"); return false; }
+  for (int j = 0; j < ndim; ++j) { u[j] = reinterpret_cast<const float2*>(factors[j]); k[j] = kept[j]; }
+  return true;
+}
+
+int sc_cp_scale(const sc_complex* const* mode_factors, const int32_t* kept, int32_t ndim, const sc_complex* lambda,
+                sc_complex* scale, int32_t rank, sc_stream stream) {
+  const float2* u[SC_MAX_DIMS]; int k[SC_MAX_DIMS];
+  SC_TRY(cp_args(mode_factors, kept, ndim, u, k));
+  int64_t M = 1; for (int j = 0; j < ndim; ++j) M *= k[j];
+  SC_TRY(launch_cp_scale(u, k, ndim, reinterpret_cast<const float2*>(lambda), reinterpret_cast<float2*>(scale), rank, M,
+                         static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_cp_apply(const sc_complex* in, const sc_complex* scale, sc_complex* out, int conj_scale, int32_t batch,
+                int64_t per_batch, sc_stream stream) {
+  SC_REQUIRE(in != nullptr && scale != nullptr && out != nullptr, "sc_cp_apply: null argument");
+  SC_TRY(launch_cp_apply(reinterpret_cast<const float2*>(in), reinterpret_cast<const float2*>(scale), reinterpret_cast<float2*>(out),
+                         conj_scale != 0, batch, per_batch, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_cp_dscale(const sc_complex* t, const sc_complex* g, sc_complex* dscale, int32_t batch, int64_t per_batch,
+                 sc_stream stream) {
+  SC_REQUIRE(t != nullptr && g != nullptr && dscale != nullptr, "sc_cp_dscale: null argument");
+  SC_TRY(launch_cp_dscale(reinterpret_cast<const float2*>(t), reinterpret_cast<const float2*>(g), reinterpret_cast<float2*>(dscale),
+                          batch, per_batch, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_cp_factor_grad(const sc_complex* const* mode_factors, const int32_t* kept, int32_t ndim, const sc_complex* lambda,
+                      const sc_complex* dscale, sc_complex* out, int32_t which, int32_t rank, sc_stream stream) {
+  const float2* u[SC_MAX_DIMS]; int k[SC_MAX_DIMS];
+  SC_TRY(cp_args(mode_factors, kept, ndim, u, k));
+  SC_REQUIRE(which >= -1 && which < ndim, "sc_cp_factor_grad: bad factor index");
+  int64_t M = 1; for (int j = 0; j < ndim; ++j) M *= k[j];
+  SC_TRY(launch_cp_factor_grad(u, k, ndim, reinterpret_cast<const float2*>(lambda), reinterpret_cast<const float2*>(dscale),
+                               reinterpret_cast<float2*>(out), which, rank, M, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream) {
   SC_REQUIRE(a != nullptr && b != nullptr && d != nullptr, "sc_selftest_umma: null argument");
   SC_TRY(umma_selftest(a, b, d, n, k, static_cast<cudaStream_t>(stream)));

@@ -282,6 +282,147 @@ bool launch_pair_reduce(const float2* A, const float2* B, float2* out, int64_t s
 }
 
 // =====================================================================================================
+// 2c. CP (canonical polyadic) pieces, reference `_contract_cp` :55-73.
+//     scale[e, m] = lambda_e * prod_j U_j[m_j, e]   (Khatri-Rao rows of the kept mode-factor rows)
+//     apply:  out[a, e, m] = in[a, e, m] * op(scale[e, m])
+//     dscale[e, m] = sum_a conj(t[a, e, m]) * g[a, e, m]
+//     factor gradients from dscale (warp per output element, shuffle reduction over the other mode indices)
+// =====================================================================================================
+struct CpFactors {
+  const float2* u[SC_MAX_DIMS];   // [k_j x R] row-major, kept rows only
+  int k[SC_MAX_DIMS];
+  int d;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cmul_conj_a(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x); }
+
+// product over the mode factors except `skip` (skip = -1: all) for rank e and flat mode index m
+__device__ __forceinline__ float2 cp_mode_product(const CpFactors& F, int R, int e, long long m, int skip) {
+  float2 p = make_float2(1.f, 0.f);
+  for (int j = F.d - 1; j >= 0; --j) {
+    const int mj = (int)(m % F.k[j]);
+    m /= F.k[j];
+    if (j != skip) p = cmul(p, __ldg(F.u[j] + (long long)mj * R + e));
+  }
+  return p;
+}
+
+__global__ void k_cp_scale(CpFactors F, const float2* __restrict__ lambda, float2* __restrict__ scale, int R, long long M) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)R * M) return;
+  const int e = (int)(idx / M);
+  const long long m = idx - (long long)e * M;
+  scale[idx] = cmul(__ldg(lambda + e), cp_mode_product(F, R, e, m, -1));
+}
+
+template <bool CONJ>
+__global__ void k_cp_apply(const float2* __restrict__ in, const float2* __restrict__ scale, float2* __restrict__ out,
+                           long long per_batch, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float2 s = __ldg(scale + idx % per_batch);
+  if (CONJ) s.y = -s.y;
+  out[idx] = cmul(__ldg(in + idx), s);
+}
+
+__global__ void k_cp_dscale(const float2* __restrict__ t, const float2* __restrict__ g, float2* __restrict__ dscale,
+                            int batch, long long per_batch) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_batch) return;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int a = 0; a < batch; ++a) {
+    const float2 v = cmul_conj_a(__ldg(t + a * per_batch + idx), __ldg(g + a * per_batch + idx));
+    acc.x += v.x; acc.y += v.y;
+  }
+  dscale[idx] = acc;
+}
+
+// which == -1: dlambda[e] = sum_m conj(prod_j U_j) dscale[e,m]
+// which == j : dU_j[r, e] = sum_{m : m_j == r} conj(lambda_e prod_{l != j} U_l) dscale[e,m]
+// one warp per output element
+__global__ void k_cp_factor_grad(CpFactors F, const float2* __restrict__ lambda, const float2* __restrict__ dscale,
+                                 float2* __restrict__ out, int which, int R, long long M) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long n_out = which < 0 ? R : (long long)F.k[which] * R;
+  if (w >= n_out) return;
+  const int e = (int)(w % R);
+  const int r = (int)(w / R);
+  float2 acc = make_float2(0.f, 0.f);
+  if (which < 0) {
+    for (long long m = lane; m < M; m += 32) {
+      const float2 v = cmul_conj_a(cp_mode_product(F, R, e, m, -1), __ldg(dscale + (long long)e * M + m));
+      acc.x += v.x; acc.y += v.y;
+    }
+  } else {
+    // enumerate the modes whose index along `which` equals r: m = (outer * k_which + r) * inner + i
+    long long inner = 1, outer = 1;
+    for (int j = which + 1; j < F.d; ++j) inner *= F.k[j];
+    for (int j = 0; j < which; ++j) outer *= F.k[j];
+    const float2 lam = __ldg(lambda + e);
+    for (long long t = lane; t < outer * inner; t += 32) {
+      const long long o = t / inner, i = t - o * inner;
+      const long long m = (o * F.k[which] + r) * inner + i;
+      const float2 coef = cmul(lam, cp_mode_product(F, R, e, m, which));
+      const float2 v = cmul_conj_a(coef, __ldg(dscale + (long long)e * M + m));
+      acc.x += v.x; acc.y += v.y;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+  }
+  if (lane == 0) out[w] = acc;
+}
+
+static CpFactors make_cp_factors(const float2* const* u, const int* k, int d) {
+  CpFactors F{};
+  F.d = d;
+  for (int j = 0; j < d; ++j) { F.u[j] = u[j]; F.k[j] = k[j]; }
+  return F;
+}
+
+bool launch_cp_scale(const float2* const* u, const int* k, int d, const float2* lambda, float2* scale, int R, int64_t M,
+                     cudaStream_t st) {
+  const long long total = (long long)R * M;
+  if (total <= 0) return true;
+  k_cp_scale<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(make_cp_factors(u, k, d), lambda, scale, R, (long long)M);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_cp_scale launch");
+}
+
+bool launch_cp_apply(const float2* in, const float2* scale, float2* out, bool conj_scale, int batch, int64_t per_batch,
+                     cudaStream_t st) {
+  const long long total = (long long)batch * per_batch;
+  if (total <= 0) return true;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (conj_scale) k_cp_apply<true><<<grid, 256, 0, st>>>(in, scale, out, (long long)per_batch, total);
+  else k_cp_apply<false><<<grid, 256, 0, st>>>(in, scale, out, (long long)per_batch, total);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_cp_apply launch");
+}
+
+bool launch_cp_dscale(const float2* t, const float2* g, float2* dscale, int batch, int64_t per_batch, cudaStream_t st) {
+  if (per_batch <= 0) return true;
+  k_cp_dscale<<<(unsigned)((per_batch + 255) / 256), 256, 0, st>>>(t, g, dscale, batch, (long long)per_batch);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_cp_dscale launch");
+}
+
+bool launch_cp_factor_grad(const float2* const* u, const int* k, int d, const float2* lambda, const float2* dscale,
+                           float2* out, int which, int R, int64_t M, cudaStream_t st) {
+  const long long n_out = which < 0 ? R : (long long)k[which] * R;
+  if (n_out <= 0) return true;
+  const long long threads = n_out * 32;
+  k_cp_factor_grad<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(make_cp_factors(u, k, d), lambda, dscale, out, which, R,
+                                                                      (long long)M);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_cp_factor_grad launch");
+}
+
+// =====================================================================================================
 // 3. mode-wise complex GEMM:  out[r, c, m] = sum_k opA(A[r, k, m]) * opB(B[k, c, m])
 //    forward  : r=b c=o k=i   A = xm            B = weight
 //    dxm      : r=b c=i k=o   A = gm            B = conj(weight) (strides swapped)

@@ -71,6 +71,12 @@ bool launch_complex_table_gemm_strided(const float2* T, int64_t sTp, int64_t sTq
 // out[p, q] (strided) = sum_{o,i} conj(A[o,p,i]) * B[o,q,i]
 bool launch_pair_reduce(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I,
                         cudaStream_t st);
+// CP pieces (sc_generic.cu, section 2c)
+bool launch_cp_scale(const float2* const* u, const int* k, int d, const float2* lambda, float2* scale, int R, int64_t M, cudaStream_t st);
+bool launch_cp_apply(const float2* in, const float2* scale, float2* out, bool conj_scale, int batch, int64_t per_batch, cudaStream_t st);
+bool launch_cp_dscale(const float2* t, const float2* g, float2* dscale, int batch, int64_t per_batch, cudaStream_t st);
+bool launch_cp_factor_grad(const float2* const* u, const int* k, int d, const float2* lambda, const float2* dscale, float2* out,
+                           int which, int R, int64_t M, cudaStream_t st);
 // out[r, c, m] = sum_k opA(A[r,k,m]) * opB(B[k,c,m]); per-operand element strides, optional mode-offset tables
 struct ModeGemmOperand {
   const void* ptr; int64_t s_outer; int64_t s_inner; const int32_t* mode_off;  // mode_off == nullptr -> m itself

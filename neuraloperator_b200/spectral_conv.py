@@ -358,6 +358,160 @@ class _SpectralConvTucker(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# CP-factorized contraction without reconstructing the weight (reference `_contract_cp`, :55-73)
+# --------------------------------------------------------------------------------------------------
+def _cp_factor_args(u_modes, kept):
+    d = len(u_modes)
+    ptrs = (ctypes.c_void_p * d)(*[u.data_ptr() for u in u_modes])      # host array of device pointers
+    ks = (ctypes.c_int32 * d)(*[int(k) for k in kept])
+    return ptrs, ks, d
+
+
+class _SpectralConvCP(torch.autograd.Function):
+    """y = SpectralConv.forward(x) with a CP weight (einsum `abcd,e,be,fe,ce,de->afcd`, reference :58-71):
+    xm -> U_in -> pointwise scale[e, m] = lambda_e prod_j U_j[m_j, e] -> U_out.  Mode factors arrive already sliced to the
+    kept rows (k_j, R)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, plan, lam, u_in, u_out, *u_modes):
+        lib = _lib.load()
+        dev = x.device
+        B, Ci = x.shape[:2]
+        Co, R = u_out.shape
+        kept = plan.kept
+        M = plan.n_modes_total
+        st = _stream_ptr(dev)
+        with torch.cuda.device(dev):
+            xm = analyze(plan, x)
+            ptrs, ks, d = _cp_factor_args(u_modes, kept)
+            scale = torch.empty(R * M, dtype=torch.complex64, device=dev)
+            _lib.check(lib.sc_cp_scale(ptrs, ks, d, _ptr(lam), _ptr(scale), R, st), "sc_cp_scale")
+            t1 = _table_contract(u_in, 1, R, False, xm, B, R, Ci, M)                # T[p=e, q=i] = U_in[i, e]
+            t2 = torch.empty_like(t1)
+            _lib.check(lib.sc_cp_apply(_ptr(t1), _ptr(scale), _ptr(t2), 0, B, R * M, st), "sc_cp_apply")
+            ym = _table_contract(u_out, R, 1, False, t2, B, Co, R, M)               # T[p=o, q=e] = U_out[o, e]
+            y = synthesize(plan, ym.view(B, Co, *kept), bias)
+        ctx.plan = plan
+        ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.dims = (B, Ci, Co, R, M)
+        ctx.save_for_backward(xm, t1, t2, scale, lam, u_in, u_out, *u_modes)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        plan = ctx.plan
+        B, Ci, Co, R, M = ctx.dims
+        kept = plan.kept
+        xm, t1, t2, scale, lam, u_in, u_out = ctx.saved_tensors[:7]
+        u_modes = ctx.saved_tensors[7:]
+        dev = gy.device
+        gy = gy.contiguous()
+        cplx = dict(dtype=torch.complex64, device=dev)
+        st = _stream_ptr(dev)
+        with torch.cuda.device(dev):
+            gm = analyze(plan, gy, adjoint=True)
+            db = None
+            if ctx.bias_shape is not None:
+                db = torch.empty(Co, dtype=torch.float32, device=dev)
+                _lib.check(lib.sc_bias_grad(plan.handle, _ptr(gm), _ptr(db), B, Co, st), "sc_bias_grad")
+                db = db.reshape(ctx.bias_shape)
+            g2 = _table_contract(u_out, 1, R, True, gm, B, R, Co, M)                # T[p=e, q=o] = conj(U_out[o, e])
+            d_u_out = _pair_reduce(t2, gm, torch.empty(Co, R, **cplx), 1, R, B, R, Co, M)
+            dscale = torch.empty(R * M, **cplx)
+            _lib.check(lib.sc_cp_dscale(_ptr(t1), _ptr(g2), _ptr(dscale), B, R * M, st), "sc_cp_dscale")
+            g1 = torch.empty_like(g2)
+            _lib.check(lib.sc_cp_apply(_ptr(g2), _ptr(scale), _ptr(g1), 1, B, R * M, st), "sc_cp_apply")
+            d_u_in = _pair_reduce(xm, g1, torch.empty(Ci, R, **cplx), R, 1, B, Ci, R, M)
+            dxm = _table_contract(u_in, R, 1, True, g1, B, Ci, R, M)                # T[p=i, q=e] = conj(U_in[i, e])
+            dx = synthesize(plan, dxm.view(B, Ci, *kept), adjoint=True)
+            ptrs, ks, d = _cp_factor_args(u_modes, kept)
+            d_lam = torch.empty(R, **cplx)
+            _lib.check(lib.sc_cp_factor_grad(ptrs, ks, d, _ptr(lam), _ptr(dscale), _ptr(d_lam), -1, R, st), "sc_cp_factor_grad")
+            d_modes = []
+            for j in range(d):
+                g = torch.empty(kept[j], R, **cplx)
+                _lib.check(lib.sc_cp_factor_grad(ptrs, ks, d, _ptr(lam), _ptr(dscale), _ptr(g), j, R, st), "sc_cp_factor_grad")
+                d_modes.append(g)
+        return (dx, db, None, d_lam, d_u_in, d_u_out, *d_modes)
+
+
+# --------------------------------------------------------------------------------------------------
+# TT-factorized contraction without reconstructing the weight (reference `_contract_tt`, :106-127)
+# --------------------------------------------------------------------------------------------------
+class _SpectralConvTT(torch.autograd.Function):
+    """y = SpectralConv.forward(x) with a tensor-train weight  W[i,o,m] = G0[0,i,:] G1[:,o,:] G2[:,m_1,:] .. G_{d+1}[:,m_d,0].
+    The mode cores (already sliced to the kept rows) are multiplied right to left into V[r2, m]; G1 V gives a rank-r1
+    weight block (r1, Co, modes) that the dense mode GEMM applies to xm G0."""
+
+    @staticmethod
+    def forward(ctx, x, bias, plan, plan_kept, g0, g1c, *cores):
+        dev = x.device
+        B, Ci = x.shape[:2]
+        r1, Co, r2 = g1c.shape
+        kept = plan.kept
+        M = plan.n_modes_total
+        d = plan.ndim
+        with torch.cuda.device(dev):
+            xm = analyze(plan, x)
+            chain = [cores[d - 1].contiguous()]                                      # A_{d-1}: (ra, k_{d-1}) since rb = 1
+            inner = kept[d - 1]
+            for j in range(d - 2, -1, -1):
+                ra, kj, rb = cores[j].shape
+                chain.append(_table_contract(cores[j], rb, 1, False, chain[-1], 1, ra * kj, rb, inner))
+                inner *= kj
+            v = chain[-1]                                                            # (r2, M)
+            wc = _table_contract(g1c, r2, 1, False, v, 1, r1 * Co, r2, M)            # (r1, Co, M)
+            t1 = _table_contract(g0, 1, r1, False, xm, B, r1, Ci, M)                 # T[p=r, q=i] = G0[0, i, r]
+            ym = contract_dense(plan_kept, t1.view(B, r1, *kept), wc.view(r1, Co, *kept))
+            y = synthesize(plan, ym, bias)
+        ctx.plan, ctx.plan_kept, ctx.d = plan, plan_kept, d
+        ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.dims = (B, Ci, Co, r1, r2, M)
+        ctx.save_for_backward(xm, t1, wc, g0, g1c, *cores, *chain)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        plan, plan_kept, d = ctx.plan, ctx.plan_kept, ctx.d
+        B, Ci, Co, r1, r2, M = ctx.dims
+        kept = plan.kept
+        saved = ctx.saved_tensors
+        xm, t1, wc, g0, g1c = saved[:5]
+        cores = saved[5:5 + d]
+        chain = saved[5 + d:]                     # A_{d-1}, A_{d-2}, ..., A_0 (= V)
+        dev = gy.device
+        gy = gy.contiguous()
+        cplx = dict(dtype=torch.complex64, device=dev)
+        with torch.cuda.device(dev):
+            gm = analyze(plan, gy, adjoint=True)
+            db = None
+            if ctx.bias_shape is not None:
+                db = torch.empty(Co, dtype=torch.float32, device=dev)
+                _lib.check(lib.sc_bias_grad(plan.handle, _ptr(gm), _ptr(db), B, Co, _stream_ptr(dev)), "sc_bias_grad")
+                db = db.reshape(ctx.bias_shape)
+            g1, d_wc, _ = contract_dense_backward(plan_kept, t1.view(B, r1, *kept), gm, wc.view(r1, Co, *kept),
+                                                  need_dbias=False)
+            d_g0 = _pair_reduce(xm, g1, torch.empty(1, Ci, r1, **cplx), r1, 1, B, Ci, r1, M)
+            dxm = _table_contract(g0, r1, 1, True, g1, B, Ci, r1, M)                 # T[p=i, q=r] = conj(G0[0, i, r])
+            dx = synthesize(plan, dxm.view(B, Ci, *kept), adjoint=True)
+            v = chain[-1]
+            d_g1 = _pair_reduce(v, d_wc, torch.empty(r1, Co, r2, **cplx), 1, r2, 1, r2, r1 * Co, M)
+            d_a = _table_contract(g1c, 1, r2, True, d_wc, 1, r2, r1 * Co, M)         # dV (r2, M)
+            d_cores = [None] * d
+            inner = M
+            for j in range(d - 1):
+                ra, kj, rb = cores[j].shape
+                inner //= kj
+                a_next = chain[d - 2 - j]                                            # A_{j+1}: (rb, inner)
+                d_cores[j] = _pair_reduce(a_next, d_a, torch.empty(ra, kj, rb, **cplx), 1, rb, 1, rb, ra * kj, inner)
+                d_a = _table_contract(cores[j], 1, rb, True, d_a, 1, rb, ra * kj, inner)
+            d_cores[d - 1] = d_a.view(cores[d - 1].shape)
+        return (dx, db, None, None, d_g0, d_g1, *d_cores)
+
+
+# --------------------------------------------------------------------------------------------------
 # the module
 # --------------------------------------------------------------------------------------------------
 def _validate_scaling_factor(factor, n_dim) -> Optional[List[float]]:
@@ -504,6 +658,27 @@ class SpectralConv(BaseSpectralConv):
         plan_kept = get_plan(x.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
         return _SpectralConvTucker.apply(x, self.bias, plan, plan_kept, w.core, u_in, u_out, *u_modes)
 
+    def _forward_cp(self, x, plan: Plan):
+        """Factor-by-factor contraction (reference implementation="factorized", `_contract_cp` :55-73)."""
+        w = self.weight
+        factors = list(w.factors)
+        u_modes = []
+        for j in range(self.order):
+            _, rows = plan.mode_bins(j)
+            u_modes.append(factors[2 + j][rows[0]:rows[0] + len(rows)].contiguous())
+        return _SpectralConvCP.apply(x, self.bias, plan, w.weights.contiguous(), factors[0].contiguous(),
+                                     factors[1].contiguous(), *u_modes)
+
+    def _forward_tt(self, x, plan: Plan):
+        """Core-by-core contraction (reference implementation="factorized", `_contract_tt` :106-127)."""
+        factors = list(self.weight.factors)
+        cores = []
+        for j in range(self.order):
+            _, rows = plan.mode_bins(j)
+            cores.append(factors[2 + j][:, rows[0]:rows[0] + len(rows), :].contiguous())
+        plan_kept = get_plan(x.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
+        return _SpectralConvTT.apply(x, self.bias, plan, plan_kept, factors[0].contiguous(), factors[1].contiguous(), *cores)
+
     def forward(self, x: torch.Tensor, output_shape: Optional[Tuple[int]] = None):
         if x.ndim != self.order + 2:
             raise ValueError(f"expected input of shape (batch, channels, {self.order} spatial dims), got {tuple(x.shape)}")
@@ -520,6 +695,10 @@ class SpectralConv(BaseSpectralConv):
         if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "tucker" and \
                 self.in_channels <= 64 and self.out_channels <= 64:
             return self._forward_tucker(x, plan)
+        if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "cp":
+            return self._forward_cp(x, plan)
+        if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "tt":
+            return self._forward_tt(x, plan)
         # dense weight goes straight to the kernels; other factorized forms are reconstructed first (differentiably)
         w = self.weight.to_tensor()
         if not w.is_contiguous():

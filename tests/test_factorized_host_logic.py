@@ -1,0 +1,152 @@
+"""Host-side logic of the factor-by-factor contractions (Tucker / CP / TT autograd functions) without a GPU.
+
+The device primitives behind the C ABI (`sc_table_contract`, `sc_pair_reduce`, `sc_cp_*`, the transforms and the dense mode
+GEMM) are replaced by small torch restatements of their documented contracts (include/spectral_conv_b200.h), so what is
+checked here is everything the Python side decides: operand strides, factor slicing, the order of the chains and which
+gradient goes where.  Reference for the numbers: the oracle's einsum restatements of `_contract_tucker/_cp/_tt`
+(neuralop/layers/spectral_convolution.py:55-127) differentiated by PyTorch.  The kernels themselves are checked on the GPU
+(tests/test_gpu_parity.py)."""
+import contextlib
+import math
+
+import pytest
+import torch
+
+from neuraloperator_b200 import spectral_conv as sc
+from oracle import spectral_conv_oracle as O
+
+
+def _table(table, s_p, s_q, conj, P, Q):
+    idx = torch.arange(P)[:, None] * s_p + torch.arange(Q)[None, :] * s_q
+    T = table.reshape(-1)[idx]
+    return T.conj() if conj else T
+
+
+def _table_contract(table, s_p, s_q, conj, src, n_outer, P, Q, n_inner):
+    return torch.einsum("pq,oqi->opi", _table(table, s_p, s_q, conj, P, Q), src.reshape(n_outer, Q, n_inner)).reshape(-1)
+
+
+def _pair_reduce(a, b, out, s_p, s_q, n_outer, P, Q, n_inner):
+    r = torch.einsum("opi,oqi->pq", a.reshape(n_outer, P, n_inner).conj(), b.reshape(n_outer, Q, n_inner))
+    idx = torch.arange(P)[:, None] * s_p + torch.arange(Q)[None, :] * s_q
+    out.view(-1)[idx.reshape(-1)] = r.reshape(-1)
+    return out
+
+
+def _cp_scale(lam, us, ks):
+    d, R = len(us), lam.shape[0]
+    s = lam.reshape(R, *[1] * d)
+    for j, u in enumerate(us):
+        shp = [R] + [1] * d
+        shp[1 + j] = ks[j]
+        s = s * u.t().reshape(shp)
+    return s.reshape(-1)
+
+
+class _Lib:
+    def sc_bias_grad(self, plan, gm, db, B, Co, st):
+        db.copy_(gm.reshape(B, Co, -1).real.sum(dim=(0, 2)))
+        return 0
+
+    def sc_cp_scale(self, us, ks, d, lam, scale, R, st):
+        scale.copy_(_cp_scale(lam, us, ks))
+        return 0
+
+    def sc_cp_apply(self, a, scale, out, conj, B, per, st):
+        out.copy_((a.reshape(B, per) * (scale.conj() if conj else scale)[None]).reshape(out.shape))
+        return 0
+
+    def sc_cp_dscale(self, t, g, ds, B, per, st):
+        ds.copy_((t.reshape(B, per).conj() * g.reshape(B, per)).sum(0))
+        return 0
+
+    def sc_cp_factor_grad(self, us, ks, d, lam, ds, out, which, R, st):
+        with torch.enable_grad():
+            lam_ = lam.detach().clone().requires_grad_(True)
+            us_ = [u.detach().clone().requires_grad_(True) for u in us]
+            _cp_scale(lam_, us_, ks).backward(ds)
+        out.copy_((lam_.grad if which < 0 else us_[which].grad).reshape(out.shape))
+        return 0
+
+
+class _Plan:
+    def __init__(self, kept):
+        self.kept, self.ndim, self.n_modes_total, self.handle = list(kept), len(kept), math.prod(kept), None
+
+
+@pytest.fixture
+def emulated(monkeypatch):
+    """analysis = real -> complex embedding, synthesis = real part (+ bias): a valid adjoint pair, so the transforms drop out."""
+    monkeypatch.setattr(sc._lib, "load", lambda: _Lib())
+    monkeypatch.setattr(sc._lib, "check", lambda rc, what: None)
+    monkeypatch.setattr(sc, "_ptr", lambda t: t)
+    monkeypatch.setattr(sc, "_stream_ptr", lambda dev: None)
+    monkeypatch.setattr(sc, "_table_contract", _table_contract)
+    monkeypatch.setattr(sc, "_pair_reduce", _pair_reduce)
+    monkeypatch.setattr(sc, "_cp_factor_args", lambda us, kept: (list(us), list(kept), len(us)))
+    monkeypatch.setattr(sc, "analyze", lambda plan, x, adjoint=False: x.to(torch.complex64))
+    monkeypatch.setattr(sc, "synthesize", lambda plan, m, bias=None, adjoint=False:
+                        (m.real + (bias.reshape(1, -1, *[1] * (m.ndim - 2)) if bias is not None else 0)).contiguous())
+    monkeypatch.setattr(sc, "contract_dense", lambda plan, xm, w: torch.einsum("bi...,io...->bo...", xm, w).contiguous())
+    monkeypatch.setattr(sc, "contract_dense_backward", lambda plan, xm, gm, w, **kw: (
+        torch.einsum("bo...,io...->bi...", gm, w.conj()).contiguous(),
+        torch.einsum("bi...,bo...->io...", xm.conj(), gm).contiguous(), None))
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _compare(fn_apply, fn_ref, params, gy):
+    p1 = [p.clone().requires_grad_(True) for p in params]
+    y1 = fn_apply(*p1)
+    y1.backward(gy)
+    p2 = [p.clone().requires_grad_(True) for p in params]
+    y2 = fn_ref(*p2)
+    y2.backward(gy)
+    assert _rel(y1, y2) < 1e-5
+    for i, (a, b) in enumerate(zip(p1, p2)):
+        assert a.grad is not None, f"input {i} got no gradient"
+        assert _rel(a.grad, b.grad) < 1e-5, f"gradient of input {i}"
+
+
+def _c(*shape):
+    return torch.randn(*shape, dtype=torch.complex64)
+
+
+KEPT = [(5,), (4, 3), (3, 4, 2), (2, 3, 2, 2)]
+
+
+@pytest.mark.parametrize("kept", KEPT)
+def test_cp_chain(emulated, kept):
+    d, B, Ci, Co, R = len(kept), 2, 3, 4, 5
+    torch.manual_seed(0)
+    params = [torch.randn(B, Ci, *kept), torch.randn(Co, *[1] * d), _c(R), _c(Ci, R), _c(Co, R), *[_c(k, R) for k in kept]]
+    _compare(lambda x, b, lam, ui, uo, *um: sc._SpectralConvCP.apply(x, b, _Plan(kept), lam, ui, uo, *um),
+             lambda x, b, lam, ui, uo, *um: O.contract_cp(x.to(torch.complex64), lam, [ui, uo, *um]).real + b,
+             params, torch.randn(B, Co, *kept))
+
+
+@pytest.mark.parametrize("kept", KEPT)
+def test_tt_chain(emulated, kept):
+    d, B, Ci, Co = len(kept), 2, 3, 4
+    torch.manual_seed(1)
+    r = [1, 3, 4] + [2 + j for j in range(d - 1)] + [1]
+    params = [torch.randn(B, Ci, *kept), torch.randn(Co, *[1] * d), _c(1, Ci, r[1]), _c(r[1], Co, r[2]),
+              *[_c(r[2 + j], kept[j], r[3 + j]) for j in range(d)]]
+    _compare(lambda x, b, *cores: sc._SpectralConvTT.apply(x, b, _Plan(kept), None, *cores),
+             lambda x, b, *cores: O.contract_tt(x.to(torch.complex64), list(cores)).real + b,
+             params, torch.randn(B, Co, *kept))
+
+
+@pytest.mark.parametrize("kept", KEPT)
+def test_tucker_chain(emulated, kept):
+    d, B, Ci, Co = len(kept), 2, 3, 4
+    torch.manual_seed(2)
+    ranks = [2, 3] + [2 + (j % 2) for j in range(d)]
+    params = [torch.randn(B, Ci, *kept), torch.randn(Co, *[1] * d), _c(*ranks), _c(Ci, ranks[0]), _c(Co, ranks[1]),
+              *[_c(k, r) for k, r in zip(kept, ranks[2:])]]
+    _compare(lambda x, b, core, ui, uo, *um: sc._SpectralConvTucker.apply(x, b, _Plan(kept), None, core, ui, uo, *um),
+             lambda x, b, core, ui, uo, *um: O.contract_tucker(x.to(torch.complex64), core, [ui, uo, *um]).real + b,
+             params, torch.randn(B, Co, *kept))

@@ -241,3 +241,41 @@ def test_fno_block_style_usage(cuda_device):
     y.square().mean().backward()
     for n, p in conv.named_parameters():
         assert p.grad is not None and torch.isfinite(torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).all(), n
+
+
+@pytest.mark.parametrize("fact,rank,Ci,Co,grid,modes,max_modes", [
+    ("cp", 9, 12, 10, (40, 36), (16, 12), None),
+    ("cp", 5, 6, 7, (64,), (20,), None),
+    ("cp", 6, 4, 5, (12, 10, 16), (6, 6, 8), None),
+    ("cp", 8, 8, 8, (32, 32), (8, 8), (16, 12)),        # kept rows are a slice of the mode factors
+    ("tt", 0.3, 12, 10, (40, 36), (16, 12), None),
+    ("tt", 0.5, 6, 7, (64,), (20,), None),
+    ("tt", 0.4, 4, 5, (12, 10, 16), (6, 6, 8), None),
+    ("tt", 0.3, 8, 8, (32, 32), (8, 8), (16, 12)),
+])
+def test_factor_by_factor_matches_reconstructed(cuda_device, fact, rank, Ci, Co, grid, modes, max_modes):
+    """implementation="factorized" (CP / TT contracted factor by factor on the device, reference :55-73 / :106-127) against
+    implementation="reconstructed" (weight rebuilt, dense kernels) on the same parameters: outputs and every gradient."""
+    dev = cuda_device
+    torch.manual_seed(11)
+    kw = dict(factorization=fact, rank=rank, max_n_modes=max_modes)
+    a = nb.SpectralConv(Ci, Co, modes, implementation="factorized", **kw).to(dev)
+    b = nb.SpectralConv(Ci, Co, modes, implementation="reconstructed", **kw).to(dev)
+    with torch.no_grad():
+        for pa, pb in zip(a.weight.decomposition(), b.weight.decomposition()):
+            pa.copy_(torch.randn_like(pa))           # O(1) entries so every factor gradient is well above rounding
+            pb.copy_(pa)
+        b.bias.copy_(a.bias.normal_())
+    B = 3
+    x = torch.randn(B, Ci, *grid, device=dev)
+    gy = torch.randn(B, Co, *grid, device=dev)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = a(xa), b(xb)
+    ya.backward(gy)
+    yb.backward(gy)
+    assert rel_err(ya, yb) < REL_TOL, "y"
+    assert rel_err(xa.grad, xb.grad) < REL_TOL, "dx"
+    assert rel_err(a.bias.grad, b.bias.grad) < REL_TOL, "dbias"
+    for i, (pa, pb) in enumerate(zip(a.weight.decomposition(), b.weight.decomposition())):
+        assert pa.grad is not None and pb.grad is not None
+        assert rel_err(pa.grad, pb.grad) < REL_TOL, f"dparam{i}"
