@@ -56,6 +56,7 @@ def build_library(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
         cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd += os.environ.get("SC_EXTRA_NVCC_FLAGS", "").split()      # e.g. -DSC_TRACE_QUAD for the debug timeline build
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

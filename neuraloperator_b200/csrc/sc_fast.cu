@@ -966,6 +966,7 @@ struct ModeGemmQuadParams {
   const float2* a; const float2* b; float2* out;
   long long sAR, sAK, sBN, sBK, sOR, sON;
   int MR, NB, KC, NBp, KCp, kshift, conjA, n_groups, rounds, zero_fill;
+  long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
 // fixed per-mode tile layout (compile-time offsets keep the scatter stores on immediate addressing):
 //   [A_hi 16 KB | A_lo 16 KB | B (hi rows, lo rows) up to 16 KB]
@@ -979,6 +980,13 @@ __device__ __forceinline__ void ld_global_v8(const float2* p, float (&v)[8]) {
                : "l"(p));
 }
 
+// timeline of the quad kernel only in -DSC_TRACE_QUAD builds (the extra live pointer costs spills in the loaders)
+#ifdef SC_TRACE_QUAD
+#define SC_QTRACE(P, role, i, ph) SC_TRACE(P, role, i, ph)
+#else
+#define SC_QTRACE(P, role, i, ph) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGemmQuadParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -987,6 +995,7 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rowsB = 2 * P.NBp;
   pdl_launch_dependents();
+  if (tid == 128) SC_QTRACE(P, 0, 0, 0);
 
   if (tid == 0) {
     mbar_init(&bar_full, MG2_LOADER_WARPS);
@@ -1005,7 +1014,7 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_slot;
   const long long m0 = (long long)blockIdx.x * 4;      // first mode of this CTA's quad
-  pdl_wait();                                          // operands come from / the output goes to buffers of the previous kernel
+  if (tid == 128) SC_QTRACE(P, 0, 0, 1);
 
   if (warp >= 4) {
     // ------------------------------------------------------------------ loaders
@@ -1016,12 +1025,15 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
     const uint32_t a_s0 = sw128_offset(2 * r0, 2 * kq, 128), a_s1 = sw128_offset(2 * r0 + 1, 2 * kq, 128);
     const uint32_t a_sstep = (uint32_t)step * 256u;
     const uint32_t b_s0 = sw128_offset(r0, 2 * kq, rowsB), b_sstep = (uint32_t)step * 128u, b_lo = (uint32_t)P.NBp * 128u;
+    pdl_wait();                                        // operands come from buffers of the previous kernel
+    if (warp == 4) SC_QTRACE(P, 0, 0, 2);
     for (int rd = 0; rd < P.rounds; ++rd) {
       const int k = rd * 32 + kq;
       const bool k_ok = kq < 32 && k < P.KC;
       const float2* pa = P.a + m0 + (long long)r0 * P.sAR + (long long)k * P.sAK;
       const float2* pb = P.b + m0 + (long long)r0 * P.sBN + (long long)k * P.sBK;
       float v[4][8];                                   // <= 4 rows per thread and operand (64 rows / step 16), 4 modes each
+      if (warp == 4) SC_QTRACE(P, 0, 1 + rd, 0);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (k_ok && r0 + u * step < P.MR) ld_global_v8(pa + (long long)u * step * P.sAR, v[u]);
@@ -1061,6 +1073,7 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
           }
         }
       }
+      if (warp == 4) SC_QTRACE(P, 0, 1 + rd, 1);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         if (k_ok && r0 + u * step < P.NB) ld_global_v8(pb + (long long)u * step * P.sBN, v[u]);
@@ -1080,38 +1093,45 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_full);
+      if (warp == 4) SC_QTRACE(P, 0, 1 + rd, 2);
     }
-  } else {
-    // ------------------------------------------------------------------ MMA issue (warp 0, one thread), then epilogue
-    if (warp == 0 && lane == 0) {
-      const uint32_t idesc1 = idesc_bf16(128, rowsB), idesc2 = idesc_bf16(128, P.NBp);
-      const uint32_t base_lo = desc_lo(smem_u32(smem));
-      for (int rd = 0; rd < P.rounds; ++rd) {
-        mbar_wait(&bar_full, (uint32_t)(rd & 1));
-        tc_fence_after_sync();
+  } else if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issue (one thread)
+    const uint32_t idesc1 = idesc_bf16(128, rowsB), idesc2 = idesc_bf16(128, P.NBp);
+    const uint32_t base_lo = desc_lo(smem_u32(smem));
+    for (int rd = 0; rd < P.rounds; ++rd) {
+      mbar_wait(&bar_full, (uint32_t)(rd & 1));
+      tc_fence_after_sync();
+      SC_QTRACE(P, 1, 1 + rd, 0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a_hi = base_lo + (uint32_t)j * (MGQ_MODE_BYTES >> 4), a_lo = a_hi + (MGQ_OFF_ALO >> 4), b_op = a_hi + (MGQ_OFF_B >> 4);
-          const uint32_t d = tmem + (uint32_t)(j * 128);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t a_hi = base_lo + (uint32_t)j * (MGQ_MODE_BYTES >> 4), a_lo = a_hi + (MGQ_OFF_ALO >> 4), b_op = a_hi + (MGQ_OFF_B >> 4);
+        const uint32_t d = tmem + (uint32_t)(j * 128);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            mma_bf16_ss(d, desc_from_lo(a_hi + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc1, (rd | kk) != 0);
-            mma_bf16_ss(d, desc_from_lo(a_lo + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc2, true);
-          }
+        for (int kk = 0; kk < 4; ++kk) {
+          mma_bf16_ss(d, desc_from_lo(a_hi + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc1, (rd | kk) != 0);
+          mma_bf16_ss(d, desc_from_lo(a_lo + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc2, true);
         }
-        mma_commit(&bar_empty);
       }
-      mma_commit(&bar_d_full);
+      mma_commit(&bar_empty);
+      SC_QTRACE(P, 1, 1 + rd, 1);
     }
-    __syncwarp();
-    // epilogue: four modes -> one 32-byte store
-    const int row = warp * 32 + lane;
+    mma_commit(&bar_d_full);
+  }
+  __syncwarp();
+  {
+    // ------------------------------------------------------------------ epilogue, ALL warps: four modes -> one 32-byte store.
+    // A warp may read the TMEM lane quarter (warp & 3); the five warps of a quarter split the 8-column chunks.
+    const int q = warp & 3, grp = warp >> 2;
+    const int row = q * 32 + lane;
     const int R = row >> 1, part = row & 1;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    if (warp < 4) pdl_wait();                          // (loaders already waited) the output buffer may still be read by the previous kernel
     mbar_wait(&bar_d_full, 0);
     tc_fence_after_sync();
+    if (warp == 0) SC_QTRACE(P, 1, 5, 0);
     float2* dst = P.out + m0 + (long long)R * P.sOR;
-    for (int c = 0; c < P.NBp; c += 8) {
+    for (int c = 8 * grp; c < P.NBp; c += 8 * (MGQ_THREADS / 128)) {
       float acc[4][8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -1136,14 +1156,18 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
       }
     }
     tc_fence_before_sync();
+    if (warp == 0) SC_QTRACE(P, 1, 5, 1);
   }
 
   tc_fence_before_sync();
   __syncthreads();
+  if (warp == 0) SC_QTRACE(P, 1, 5, 2);
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 static int fast_sm_count(const Plan* p);   // defined with FastTables below
+static long long* trace_begin();
+static void trace_end(long long* d, const char* what);
 static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args);
 
 static bool mode_gemm_tc_supported(int MR, int NB, int KC) {
@@ -1174,9 +1198,12 @@ static bool launch_mode_gemm_quad(const Plan* p, const float2* a, long long sAR,
     attr_bytes = smem_bytes;
   }
   count_launch();
+  P.trace = trace_begin();
   void* args[] = {(void*)&P};
-  return cuda_ok(launch_pdl((const void*)k_mode_gemm_quad, dim3(P.n_groups), dim3(MGQ_THREADS), smem_bytes, st, args),
-                 "k_mode_gemm_quad launch");
+  const bool ok = cuda_ok(launch_pdl((const void*)k_mode_gemm_quad, dim3(P.n_groups), dim3(MGQ_THREADS), smem_bytes, st, args),
+                          "k_mode_gemm_quad launch");
+  trace_end(P.trace, conjA ? "quad conjA" : "quad");
+  return ok;
 }
 
 static inline bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31u) == 0; }

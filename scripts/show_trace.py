@@ -17,3 +17,17 @@ for name in ('analysis','synthesis'):
             if a==0: continue
             row.append(f"{i}:[{a-t0:6d} w{b-a:5d} x{c-b:5d}]")
         print(r,' '.join(row))
+# quad contraction kernel (only in -DSC_TRACE_QUAD builds): absolute clocks relative to the kernel's first instruction
+for s in [s for s in sections if 'quad' in s[0]][-3:]:
+    sec = s[1]
+    t0 = sec.get((0, 0), (0, 0, 0))[0]
+    if t0 == 0: continue
+    print('==', s[0], ' role 0 = loader warp (i=0: start/prologue done/pdl done; i=1+rd: A issued/A scattered/B scattered),'
+          ' role 1 = MMA+epilogue (i=1+rd: tiles full/MMAs issued; i=5: D full/stores issued/all warps done)')
+    for r in range(2):
+        row = []
+        for i in range(0, 6):
+            a, b, c = sec.get((r, i), (0, 0, 0))
+            if a == 0: continue
+            row.append(f"{i}:[{a-t0:6d} {b-t0 if b else 0:6d} {c-t0 if c else 0:6d}]")
+        print(r, ' '.join(row))
