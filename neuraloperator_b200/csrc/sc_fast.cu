@@ -987,6 +987,83 @@ __device__ __forceinline__ void ld_global_v8(const float2* p, float (&v)[8]) {
 #define SC_QTRACE(P, role, i, ph) do { } while (0)
 #endif
 
+// one loader group (256 threads) of the quad kernel: streams operand A (IS_B = false) or B into the four per-mode tiles
+template <bool IS_B>
+__device__ __forceinline__ void mgq_load_operand(const ModeGemmQuadParams& P, uint8_t* smem, int lt, long long m0,
+                                                 uint64_t* bar_full, uint64_t* bar_empty) {
+  const int lane = threadIdx.x & 31;
+  const int kq = lt & (P.KCp - 1);                     // k within the 32-complex slab handled per round (KCp <= 32 here)
+  const int r0 = lt >> P.kshift;
+  const int step = (MG2_LOADERS / 2) >> P.kshift;      // 8, 16 or 32 rows between a thread's elements
+  const int n_rows = IS_B ? P.NB : P.MR;
+  const long long s_row = IS_B ? P.sBN : P.sAR, s_k = IS_B ? P.sBK : P.sAK;
+  // byte offset of this thread's first element inside a per-mode tile, and the distance between its rows
+  const uint32_t off0 = IS_B ? MGQ_OFF_B + sw128_offset(r0, 2 * kq, 2 * P.NBp) : sw128_offset(2 * r0, 2 * kq, 128);
+  const uint32_t off1 = IS_B ? off0 + (uint32_t)P.NBp * 128u : sw128_offset(2 * r0 + 1, 2 * kq, 128);
+  const uint32_t sstep = (uint32_t)step * (IS_B ? 128u : 256u);
+  const float2* base = (IS_B ? P.b : P.a) + m0 + (long long)r0 * s_row;
+  pdl_wait();                                          // operands come from buffers of the previous kernel
+  if (!IS_B && lt < 32) SC_QTRACE(P, 0, 0, 2);
+  for (int rd = 0; rd < P.rounds; ++rd) {
+    const int k = rd * 32 + kq;
+    const bool k_ok = kq < 32 && k < P.KC;
+    const float2* pk = base + (long long)k * s_k;
+    if (!IS_B && lt < 32) SC_QTRACE(P, 0, 1 + rd, 0);
+#pragma unroll
+    for (int bt = 0; bt < 2; ++bt) {
+      float v[4][8];                                   // 4 rows x 4 modes
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k_ok && r0 + (4 * bt + u) * step < n_rows) ld_global_v8(pk + (long long)(4 * bt + u) * step * s_row, v[u]);
+      if (bt == 0) {
+        // pull what this thread needs next into L2 while the batch is in flight
+#pragma unroll
+        for (int u = 4; u < 8; ++u)
+          if (k_ok && r0 + u * step < n_rows) prefetch_l2(pk + (long long)u * step * s_row);
+        if (rd + 1 < P.rounds && kq < 32 && k + 32 < P.KC) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (r0 + u * step < n_rows) prefetch_l2(pk + 32 * s_k + (long long)u * step * s_row);
+        }
+        if (rd > 0) mbar_wait(bar_empty, (uint32_t)((rd - 1) & 1));   // MMAs of the previous round have read the tiles
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k_ok && r0 + (4 * bt + u) * step < n_rows) {
+          uint8_t* t0 = smem + off0 + (4 * bt + u) * sstep;
+          uint8_t* t1 = smem + off1 + (4 * bt + u) * sstep;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t hi, lo;
+            split2_bf16(v[u][2 * j], v[u][2 * j + 1], hi, lo);
+            if (IS_B) {                                // rows (n, hi) at off0, (n, lo) NBp rows further
+              *reinterpret_cast<uint32_t*>(t0 + j * MGQ_MODE_BYTES) = hi;
+              *reinterpret_cast<uint32_t*>(t1 + j * MGQ_MODE_BYTES) = lo;
+            } else {                                   // complex row r -> real rows 2r (re, -im | conj: re, im) and 2r+1 (im, re | conj: -im... )
+              uint32_t r0h, r1h, r0l, r1l;
+              if (P.conjA) {
+                r0h = hi; r1h = __byte_perm(hi, 0, 0x1032) ^ 0x00008000u;
+                r0l = lo; r1l = __byte_perm(lo, 0, 0x1032) ^ 0x00008000u;
+              } else {
+                r0h = hi ^ 0x80000000u; r1h = __byte_perm(hi, 0, 0x1032);
+                r0l = lo ^ 0x80000000u; r1l = __byte_perm(lo, 0, 0x1032);
+              }
+              *reinterpret_cast<uint32_t*>(t0 + j * MGQ_MODE_BYTES) = r0h;
+              *reinterpret_cast<uint32_t*>(t1 + j * MGQ_MODE_BYTES) = r1h;
+              *reinterpret_cast<uint32_t*>(t0 + j * MGQ_MODE_BYTES + MGQ_OFF_ALO) = r0l;
+              *reinterpret_cast<uint32_t*>(t1 + j * MGQ_MODE_BYTES + MGQ_OFF_ALO) = r1l;
+            }
+          }
+        }
+      }
+      if (!IS_B && lt < 32) SC_QTRACE(P, 0, 1 + rd, 1 + bt);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_full);
+  }
+}
+
 __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGemmQuadParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -1017,84 +1094,10 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   if (tid == 128) SC_QTRACE(P, 0, 0, 1);
 
   if (warp >= 4) {
-    // ------------------------------------------------------------------ loaders
-    const int lt = tid - 4 * 32;
-    const int kq = lt & (P.KCp - 1);                   // k within the 32-complex slab handled per round (KCp <= 32 here)
-    const int r0 = lt >> P.kshift;
-    const int step = MG2_LOADERS >> P.kshift;          // 16, 32 or 64 rows between a thread's elements
-    const uint32_t a_s0 = sw128_offset(2 * r0, 2 * kq, 128), a_s1 = sw128_offset(2 * r0 + 1, 2 * kq, 128);
-    const uint32_t a_sstep = (uint32_t)step * 256u;
-    const uint32_t b_s0 = sw128_offset(r0, 2 * kq, rowsB), b_sstep = (uint32_t)step * 128u, b_lo = (uint32_t)P.NBp * 128u;
-    pdl_wait();                                        // operands come from buffers of the previous kernel
-    if (warp == 4) SC_QTRACE(P, 0, 0, 2);
-    for (int rd = 0; rd < P.rounds; ++rd) {
-      const int k = rd * 32 + kq;
-      const bool k_ok = kq < 32 && k < P.KC;
-      const float2* pa = P.a + m0 + (long long)r0 * P.sAR + (long long)k * P.sAK;
-      const float2* pb = P.b + m0 + (long long)r0 * P.sBN + (long long)k * P.sBK;
-      float v[4][8];                                   // <= 4 rows per thread and operand (64 rows / step 16), 4 modes each
-      if (warp == 4) SC_QTRACE(P, 0, 1 + rd, 0);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (k_ok && r0 + u * step < P.MR) ld_global_v8(pa + (long long)u * step * P.sAR, v[u]);
-      // pull the sectors this thread needs next (B of this round, A and B of the next round) into L2 while A is in flight
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (k_ok && r0 + u * step < P.NB) prefetch_l2(pb + (long long)u * step * P.sBN);
-      if (rd + 1 < P.rounds && kq < 32 && k + 32 < P.KC) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (r0 + u * step < P.MR) prefetch_l2(pa + 32 * P.sAK + (long long)u * step * P.sAR);
-          if (r0 + u * step < P.NB) prefetch_l2(pb + 32 * P.sBK + (long long)u * step * P.sBN);
-        }
-      }
-      if (rd > 0) mbar_wait(&bar_empty, (uint32_t)((rd - 1) & 1));   // MMAs of the previous round have read the tiles
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (k_ok && r0 + u * step < P.MR) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint8_t* a_hi = smem + j * MGQ_MODE_BYTES;
-            uint8_t* a_lo = a_hi + MGQ_OFF_ALO;
-            uint32_t hi, lo;
-            split2_bf16(v[u][2 * j], v[u][2 * j + 1], hi, lo);
-            uint32_t r0h, r1h, r0l, r1l;
-            if (P.conjA) {
-              r0h = hi; r1h = __byte_perm(hi, 0, 0x1032) ^ 0x00008000u;
-              r0l = lo; r1l = __byte_perm(lo, 0, 0x1032) ^ 0x00008000u;
-            } else {
-              r0h = hi ^ 0x80000000u; r1h = __byte_perm(hi, 0, 0x1032);
-              r0l = lo ^ 0x80000000u; r1l = __byte_perm(lo, 0, 0x1032);
-            }
-            *reinterpret_cast<uint32_t*>(a_hi + a_s0 + u * a_sstep) = r0h;
-            *reinterpret_cast<uint32_t*>(a_hi + a_s1 + u * a_sstep) = r1h;
-            *reinterpret_cast<uint32_t*>(a_lo + a_s0 + u * a_sstep) = r0l;
-            *reinterpret_cast<uint32_t*>(a_lo + a_s1 + u * a_sstep) = r1l;
-          }
-        }
-      }
-      if (warp == 4) SC_QTRACE(P, 0, 1 + rd, 1);
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (k_ok && r0 + u * step < P.NB) ld_global_v8(pb + (long long)u * step * P.sBN, v[u]);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (k_ok && r0 + u * step < P.NB) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint8_t* b_op = smem + j * MGQ_MODE_BYTES + MGQ_OFF_B;
-            uint32_t hi, lo;
-            split2_bf16(v[u][2 * j], v[u][2 * j + 1], hi, lo);
-            *reinterpret_cast<uint32_t*>(b_op + b_s0 + u * b_sstep) = hi;
-            *reinterpret_cast<uint32_t*>(b_op + b_s0 + u * b_sstep + b_lo) = lo;
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full);
-      if (warp == 4) SC_QTRACE(P, 0, 1 + rd, 2);
-    }
+    // ------------------------------------------------------------------ loaders: warps 4-11 own operand A, warps 12-19 operand B,
+    // so that both operands of a round are in flight at once (4 x 256-bit loads per thread and batch, <= 2 batches per round)
+    if (tid - 4 * 32 < MG2_LOADERS / 2) mgq_load_operand<false>(P, smem, tid - 4 * 32, m0, &bar_full, &bar_empty);
+    else mgq_load_operand<true>(P, smem, tid - 4 * 32 - MG2_LOADERS / 2, m0, &bar_full, &bar_empty);
   } else if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ MMA issue (one thread)
     const uint32_t idesc1 = idesc_bf16(128, rowsB), idesc2 = idesc_bf16(128, P.NBp);
