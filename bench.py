@@ -158,7 +158,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    times, cores, sample_b = cpu_oracle_step_time(args.steps, args.warmup)
+    times, cores, sample_b = cpu_oracle_step_time(args.steps, args.warmup,
+                                                  budget_seconds=float(os.environ.get("SC_BENCH_CPU_BUDGET_S", "150")))
     total = sum(times)
     value = sample_b * len(times) / total
     line = {
