@@ -1304,6 +1304,10 @@ static bool cached_map(const Plan* p, int kind, const void* base, uint64_t rows,
   std::lock_guard<std::mutex> lock(f->map_mutex);
   for (const TensorMapCacheEntry& e : f->map_cache)
     if (e.base == base && e.rows == rows && e.W == W && e.kind == kind) { *out = e.map; return true; }
+  // cuTensorMapEncodeTiled is a driver entry point: it needs the primary context bound to THIS thread.  PyTorch's autograd
+  // worker threads only get one lazily (first runtime call that needs it), and a backward whose allocations are all served
+  // from the caching allocator reaches this point before any such call -- cudaFree(0) binds it (cache misses only).
+  cudaFree(nullptr);
   TensorMapCacheEntry e{base, rows, W, kind, {}};
   const bool ok = kind == 0 ? make_slab_load_map(&e.map, static_cast<const float*>(base), rows, W)
                             : make_row_tile_map(&e.map, static_cast<float*>(const_cast<void*>(base)), rows, W);
@@ -1516,7 +1520,11 @@ static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed"); return false; }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (row tiles) failed: CUresult " + std::to_string((int)r) + ", base " +
+              std::to_string((unsigned long long)(uintptr_t)base) + ", rows " + std::to_string(rows) + ", W " + std::to_string(W));
+    return false;
+  }
   return true;
 }
 
@@ -1531,7 +1539,11 @@ static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t row
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (x slabs) failed"); return false; }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (x slabs) failed: CUresult " + std::to_string((int)r) + ", base " +
+              std::to_string((unsigned long long)(uintptr_t)base) + ", rows " + std::to_string(rows) + ", W " + std::to_string(W));
+    return false;
+  }
   return true;
 }
 
