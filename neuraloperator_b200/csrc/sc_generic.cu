@@ -216,7 +216,8 @@ bool launch_complex_table_gemm(const float2* T, const float2* in, float2* out, i
 //     threads -> consecutive i: coalesced), then a warp-shuffle tree and a cross-warp pass in shared memory finish the sum.
 // =====================================================================================================
 constexpr int PR_T = 4;
-constexpr int PR_THREADS = 256;
+constexpr int PR_THREADS = 512;
+constexpr int PR_UNROLL = 2;    // reduction elements per thread and trip: 2 x 8 independent 64-bit loads in flight
 
 __global__ void __launch_bounds__(PR_THREADS)
 k_pair_reduce(const float2* __restrict__ A, const float2* __restrict__ B, float2* __restrict__ out, long long sOp,
@@ -229,25 +230,43 @@ k_pair_reduce(const float2* __restrict__ A, const float2* __restrict__ B, float2
   for (int a = 0; a < PR_T; ++a)
 #pragma unroll
     for (int b = 0; b < PR_T; ++b) acc[a][b] = make_float2(0.f, 0.f);
-  for (long long r = threadIdx.x; r < R; r += PR_THREADS) {
-    const long long o = r / I;
-    const int i = (int)(r - o * I);
-    float2 av[PR_T], bv[PR_T];
+  // rows of the tile that exist (clamped rows re-read a valid row and are dropped at the store)
+  int pa[PR_T], qb[PR_T];
 #pragma unroll
-    for (int a = 0; a < PR_T; ++a)
-      av[a] = (p0 + a < P) ? __ldg(A + (o * P + p0 + a) * (long long)I + i) : make_float2(0.f, 0.f);
+  for (int a = 0; a < PR_T; ++a) { pa[a] = min(p0 + a, P - 1); qb[a] = min(q0 + a, Q - 1); }
+  // (o, i) of this thread's element, advanced incrementally (no 64-bit division in the loop)
+  long long o = threadIdx.x / I;
+  int i = threadIdx.x - (int)o * I;
+  const int step_o = PR_THREADS / I, step_i = PR_THREADS - step_o * I;
+  for (long long r = threadIdx.x; r < R; r += (long long)PR_THREADS * PR_UNROLL) {
+    float2 av[PR_UNROLL][PR_T], bv[PR_UNROLL][PR_T];
+    bool ok[PR_UNROLL];
 #pragma unroll
-    for (int b = 0; b < PR_T; ++b)
-      bv[b] = (q0 + b < Q) ? __ldg(B + (o * Q + q0 + b) * (long long)I + i) : make_float2(0.f, 0.f);
+    for (int u = 0; u < PR_UNROLL; ++u) {
+      ok[u] = r + (long long)u * PR_THREADS < R;
+      const long long oo = ok[u] ? o : 0;
+      const int ii = ok[u] ? i : 0;
 #pragma unroll
-    for (int a = 0; a < PR_T; ++a)
-#pragma unroll
-      for (int b = 0; b < PR_T; ++b) {   // conj(a) * b
-        acc[a][b].x = fmaf(av[a].x, bv[b].x, acc[a][b].x);
-        acc[a][b].x = fmaf(av[a].y, bv[b].y, acc[a][b].x);
-        acc[a][b].y = fmaf(av[a].x, bv[b].y, acc[a][b].y);
-        acc[a][b].y = fmaf(-av[a].y, bv[b].x, acc[a][b].y);
+      for (int a = 0; a < PR_T; ++a) {
+        av[u][a] = __ldg(A + (oo * P + pa[a]) * (long long)I + ii);
+        bv[u][a] = __ldg(B + (oo * Q + qb[a]) * (long long)I + ii);
       }
+      o += step_o; i += step_i;
+      if (i >= I) { i -= I; ++o; }
+    }
+#pragma unroll
+    for (int u = 0; u < PR_UNROLL; ++u) {
+      if (!ok[u]) continue;
+#pragma unroll
+      for (int a = 0; a < PR_T; ++a)
+#pragma unroll
+        for (int b = 0; b < PR_T; ++b) {   // conj(a) * b
+          acc[a][b].x = fmaf(av[u][a].x, bv[u][b].x, acc[a][b].x);
+          acc[a][b].x = fmaf(av[u][a].y, bv[u][b].y, acc[a][b].x);
+          acc[a][b].y = fmaf(av[u][a].x, bv[u][b].y, acc[a][b].y);
+          acc[a][b].y = fmaf(-av[u][a].y, bv[u][b].x, acc[a][b].y);
+        }
+    }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll

@@ -279,3 +279,26 @@ def test_factor_by_factor_matches_reconstructed(cuda_device, fact, rank, Ci, Co,
     for i, (pa, pb) in enumerate(zip(a.weight.decomposition(), b.weight.decomposition())):
         assert pa.grad is not None and pb.grad is not None
         assert rel_err(pa.grad, pb.grad) < REL_TOL, f"dparam{i}"
+
+
+@pytest.mark.parametrize("O_,P,Q,I", [(1, 3, 5, 1), (4, 36, 64, 544), (2, 7, 9, 600), (3, 4, 4, 1500), (5, 1, 2, 33), (32, 5, 6, 7)])
+def test_pair_reduce_and_table_contract_primitives(cuda_device, O_, P, Q, I):
+    """sc_pair_reduce / sc_table_contract against torch.einsum, including strided (transposed) tables and outputs."""
+    from neuraloperator_b200.spectral_conv import _pair_reduce, _table_contract
+    dev = cuda_device
+    torch.manual_seed(3)
+    a = torch.randn(O_, P, I, dtype=torch.complex64, device=dev)
+    b = torch.randn(O_, Q, I, dtype=torch.complex64, device=dev)
+    ref = torch.einsum("opi,oqi->pq", a.conj().to(torch.complex128), b.to(torch.complex128))
+    with torch.cuda.device(dev):
+        out = _pair_reduce(a, b, torch.empty(P, Q, dtype=torch.complex64, device=dev), Q, 1, O_, P, Q, I)
+        out_t = _pair_reduce(a, b, torch.empty(Q, P, dtype=torch.complex64, device=dev), 1, P, O_, P, Q, I)
+    assert rel_err(torch.view_as_real(out), torch.view_as_real(ref.to(torch.complex64))) < REL_TOL
+    assert rel_err(torch.view_as_real(out_t.t().contiguous()), torch.view_as_real(ref.to(torch.complex64))) < REL_TOL
+    t = torch.randn(P, Q, dtype=torch.complex64, device=dev)
+    ref2 = torch.einsum("pq,oqi->opi", t, b)
+    with torch.cuda.device(dev):
+        got2 = _table_contract(t, Q, 1, False, b, O_, P, Q, I).view(O_, P, I)
+        got3 = _table_contract(t.t().contiguous(), 1, P, True, b, O_, P, Q, I).view(O_, P, I)     # table stored transposed
+    assert rel_err(torch.view_as_real(got2), torch.view_as_real(ref2)) < REL_TOL
+    assert rel_err(torch.view_as_real(got3), torch.view_as_real(torch.einsum("pq,oqi->opi", t.conj(), b))) < REL_TOL
