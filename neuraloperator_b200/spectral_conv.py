@@ -55,9 +55,24 @@ class Plan:
         self.n_modes_total = 1
         for k in self.kept:
             self.n_modes_total *= k
+        self.max_n_modes = tuple(int(m) for m in max_n_modes)
+        self._bins = {}
+        self._ws_bytes = {}
+        self.plan_kept = None        # lazily: the same problem with weight extents == kept modes (factorized chains)
 
     def mode_bins(self, dim: int) -> Tuple[List[int], List[int]]:
         """(unshifted spectrum bins read, weight rows used) for kept slots of `dim` -- for index-set checks."""
+        if dim not in self._bins:
+            self._bins[dim] = self._mode_bins(dim)
+        b, r = self._bins[dim]
+        return list(b), list(r)
+
+    def weight_row_range(self, dim: int) -> Tuple[int, int]:
+        """[first, last+1) rows of the weight's mode axis `dim` that the kept block uses (`weight[slices_w]`, :489)."""
+        _, rows = self.mode_bins(dim)
+        return rows[0], rows[0] + len(rows)
+
+    def _mode_bins(self, dim: int) -> Tuple[List[int], List[int]]:
         k = self.kept[dim]
         bins = (ctypes.c_int32 * k)()
         rows = (ctypes.c_int32 * k)()
@@ -65,7 +80,10 @@ class Plan:
         return list(bins), list(rows)
 
     def workspace_bytes(self, n_images: int) -> int:
-        return int(self._lib.sc_workspace_bytes(self.handle, n_images))
+        b = self._ws_bytes.get(n_images)
+        if b is None:
+            b = self._ws_bytes[n_images] = int(self._lib.sc_workspace_bytes(self.handle, n_images))
+        return b
 
     def set_fast_path(self, enable: bool):
         _lib.check(self._lib.sc_plan_set_fast_path(self.handle, int(bool(enable))), "sc_plan_set_fast_path")
@@ -104,7 +122,13 @@ def get_plan(device: torch.device, grid, out_grid, n_modes_stored, max_n_modes, 
         return plan
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream_ptr(device) -> ctypes.c_void_p:
+    """cudaStream_t of PyTorch's current stream on `device` (the raw getter skips building a torch.cuda.Stream object)."""
+    if _raw_stream is not None and device.index is not None:
+        return ctypes.c_void_p(_raw_stream(device.index))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
@@ -646,38 +670,42 @@ class SpectralConv(BaseSpectralConv):
         raise NotImplementedError("SpectralConv.transform with a resolution change needs the reference's "
                                   "`resample` (neuralop/layers/resample.py), which is outside the spectral-conv path")
 
+    @staticmethod
+    def _kept_rows(factor, plan: Plan, j: int, axis: int = 0):
+        """Rows of mode factor j the kept block uses (`weight[slices_w]`, :489); the factor itself when that is all of them."""
+        lo, hi = plan.weight_row_range(j)
+        if lo == 0 and hi == factor.shape[axis]:
+            return factor if factor.is_contiguous() else factor.contiguous()
+        return factor.narrow(axis, lo, hi - lo).contiguous()
+
+    def _plan_kept(self, plan: Plan) -> Plan:
+        if plan.plan_kept is None:
+            plan.plan_kept = plan if plan.max_n_modes == plan.kept else \
+                get_plan(plan.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
+        return plan.plan_kept
+
     def _forward_tucker(self, x, plan: Plan):
         """Factor-by-factor contraction (reference implementation="factorized", `_contract_tucker` :76-103)."""
         w = self.weight
         factors = list(w.factors)
-        u_in, u_out = factors[0].contiguous(), factors[1].contiguous()
-        u_modes = []
-        for j in range(self.order):                      # rows of the mode factors the kept block uses (`weight[slices_w]`, :489)
-            _, rows = plan.mode_bins(j)
-            u_modes.append(factors[2 + j][rows[0]:rows[0] + len(rows)].contiguous())
-        plan_kept = get_plan(x.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
-        return _SpectralConvTucker.apply(x, self.bias, plan, plan_kept, w.core, u_in, u_out, *u_modes)
+        u_modes = [self._kept_rows(factors[2 + j], plan, j) for j in range(self.order)]
+        return _SpectralConvTucker.apply(x, self.bias, plan, self._plan_kept(plan), w.core, factors[0].contiguous(),
+                                         factors[1].contiguous(), *u_modes)
 
     def _forward_cp(self, x, plan: Plan):
         """Factor-by-factor contraction (reference implementation="factorized", `_contract_cp` :55-73)."""
         w = self.weight
         factors = list(w.factors)
-        u_modes = []
-        for j in range(self.order):
-            _, rows = plan.mode_bins(j)
-            u_modes.append(factors[2 + j][rows[0]:rows[0] + len(rows)].contiguous())
+        u_modes = [self._kept_rows(factors[2 + j], plan, j) for j in range(self.order)]
         return _SpectralConvCP.apply(x, self.bias, plan, w.weights.contiguous(), factors[0].contiguous(),
                                      factors[1].contiguous(), *u_modes)
 
     def _forward_tt(self, x, plan: Plan):
         """Core-by-core contraction (reference implementation="factorized", `_contract_tt` :106-127)."""
         factors = list(self.weight.factors)
-        cores = []
-        for j in range(self.order):
-            _, rows = plan.mode_bins(j)
-            cores.append(factors[2 + j][:, rows[0]:rows[0] + len(rows), :].contiguous())
-        plan_kept = get_plan(x.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
-        return _SpectralConvTT.apply(x, self.bias, plan, plan_kept, factors[0].contiguous(), factors[1].contiguous(), *cores)
+        cores = [self._kept_rows(factors[2 + j], plan, j, axis=1) for j in range(self.order)]
+        return _SpectralConvTT.apply(x, self.bias, plan, self._plan_kept(plan), factors[0].contiguous(),
+                                     factors[1].contiguous(), *cores)
 
     def forward(self, x: torch.Tensor, output_shape: Optional[Tuple[int]] = None):
         if x.ndim != self.order + 2:
