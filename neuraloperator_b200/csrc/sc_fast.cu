@@ -1168,6 +1168,17 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// The opt-in dynamic shared memory limit is a per-device property of a kernel: remember what was set per device ordinal.
+constexpr int SC_MAX_DEVICES = 64;
+struct SmemOptIn { std::atomic<uint32_t> bytes[SC_MAX_DEVICES]; };
+static bool ensure_dynamic_smem(const void* kernel, SmemOptIn& set, int device, uint32_t bytes, const char* what) {
+  const bool tracked = device >= 0 && device < SC_MAX_DEVICES;
+  if (tracked && set.bytes[device].load(std::memory_order_relaxed) >= bytes) return true;
+  if (!cuda_ok(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what)) return false;
+  if (tracked) set.bytes[device].store(bytes, std::memory_order_relaxed);
+  return true;
+}
+
 static int fast_sm_count(const Plan* p);   // defined with FastTables below
 static long long* trace_begin();
 static void trace_end(long long* d, const char* what);
@@ -1193,13 +1204,9 @@ static bool launch_mode_gemm_quad(const Plan* p, const float2* a, long long sAR,
   P.n_groups = (int)(n_modes / 4);
   P.zero_fill = (MR < 64 || NB < P.NBp || (KC % 32) != 0) ? 1 : 0;
   const uint32_t smem_bytes = 4 * MGQ_MODE_BYTES + 1024u;
-  static uint32_t attr_bytes = 0;
-  if (attr_bytes < smem_bytes) {
-    if (!cuda_ok(cudaFuncSetAttribute(k_mode_gemm_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
-                 "cudaFuncSetAttribute(k_mode_gemm_quad)"))
-      return false;
-    attr_bytes = smem_bytes;
-  }
+  static SmemOptIn opt_in;
+  if (!ensure_dynamic_smem((const void*)k_mode_gemm_quad, opt_in, p->device, smem_bytes, "cudaFuncSetAttribute(k_mode_gemm_quad)"))
+    return false;
   count_launch();
   P.trace = trace_begin();
   void* args[] = {(void*)&P};
@@ -1240,13 +1247,9 @@ bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long lon
   P.off_b = 2 * a_bytes;
   P.stage_bytes = (2 * a_bytes + b_bytes + 1023u) & ~1023u;
   const uint32_t smem_bytes = 2 * P.stage_bytes + 1024u;
-  static uint32_t attr_bytes = 0;
-  if (attr_bytes < smem_bytes) {
-    if (!cuda_ok(cudaFuncSetAttribute(k_mode_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
-                 "cudaFuncSetAttribute(k_mode_gemm_tc)"))
-      return false;
-    attr_bytes = smem_bytes;
-  }
+  static SmemOptIn opt_in;
+  if (!ensure_dynamic_smem((const void*)k_mode_gemm_tc, opt_in, p->device, smem_bytes, "cudaFuncSetAttribute(k_mode_gemm_tc)"))
+    return false;
   const int sms = fast_sm_count(p);
   // contiguous mode ranges, a multiple of 4 modes (one 32-byte sector of complex64) per CTA
   int per = (int)((n_modes + sms - 1) / sms);
@@ -1598,13 +1601,9 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   switch (t.N1) {
 #define SC_FA_CASE(N)                                                                                            \
   case N: {                                                                                                      \
-    static uint32_t attr_bytes = 0;                                                                              \
-    if (attr_bytes < t.smem_bytes) {                                                                             \
-      if (!cuda_ok(cudaFuncSetAttribute(k_fused_analysis<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                        (int)t.smem_bytes), "cudaFuncSetAttribute(k_fused_analysis)"))          \
-        return false;                                                                                            \
-      attr_bytes = t.smem_bytes;                                                                                 \
-    }                                                                                                            \
+    static SmemOptIn opt_in;                                                                                     \
+    if (!ensure_dynamic_smem((const void*)k_fused_analysis<N>, opt_in, p->device, t.smem_bytes,                  \
+                             "cudaFuncSetAttribute(k_fused_analysis)")) return false;                           \
     { void* args[] = {(void*)&P, (void*)&x_map};                                                               \
       if (!cuda_ok(launch_pdl((const void*)k_fused_analysis<N>, dim3(grid), dim3(FA_THREADS), t.smem_bytes, st, args), \
                    "k_fused_analysis launch")) return false; }                                              \
@@ -1635,13 +1634,9 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   switch (t.N1) {
 #define SC_FS_CASE(N)                                                                                            \
   case N: {                                                                                                      \
-    static uint32_t attr_bytes = 0;                                                                              \
-    if (attr_bytes < t.smem_bytes) {                                                                             \
-      if (!cuda_ok(cudaFuncSetAttribute(k_fused_synthesis<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                        (int)t.smem_bytes), "cudaFuncSetAttribute(k_fused_synthesis)"))         \
-        return false;                                                                                            \
-      attr_bytes = t.smem_bytes;                                                                                 \
-    }                                                                                                            \
+    static SmemOptIn opt_in;                                                                                     \
+    if (!ensure_dynamic_smem((const void*)k_fused_synthesis<N>, opt_in, p->device, t.smem_bytes,                 \
+                             "cudaFuncSetAttribute(k_fused_synthesis)")) return false;                          \
     { void* args[] = {(void*)&P, (void*)&out_map};                                                             \
       if (!cuda_ok(launch_pdl((const void*)k_fused_synthesis<N>, dim3(grid), dim3(FS_THREADS), t.smem_bytes, st, args), \
                    "k_fused_synthesis launch")) return false; }                                             \
