@@ -107,10 +107,11 @@ int sc_pair_reduce(const sc_complex* a, const sc_complex* b, sc_complex* out, in
  *      scale[e, m] = lambda[e] * prod_j U_j[m_j, e]  (mode_factors[j]: kept rows of factor j, [kept[j] x rank] row-major) */
 int sc_cp_scale(const sc_complex* const* mode_factors, const int32_t* kept, int32_t ndim, const sc_complex* lambda,
                 sc_complex* scale, int32_t rank, sc_stream stream);
-/* out[a, e, m] = in[a, e, m] * op(scale[e, m])  (per_batch = rank * n_modes) */
+/* out[a, e, m] = in[a, e, m] * op(scale[e, m])  (per_batch = rank * n_modes).  With e = channel and scale = the kept block of
+ * a (C, modes..) weight this is also the separable contraction, _contract_dense_separable :49-52 (conj_scale = 1: its dxm). */
 int sc_cp_apply(const sc_complex* in, const sc_complex* scale, sc_complex* out, int conj_scale, int32_t batch,
                 int64_t per_batch, sc_stream stream);
-/* dscale[e, m] = sum_a conj(t[a, e, m]) * g[a, e, m] */
+/* dscale[e, m] = sum_a conj(t[a, e, m]) * g[a, e, m]   (separable: the weight gradient) */
 int sc_cp_dscale(const sc_complex* t, const sc_complex* g, sc_complex* dscale, int32_t batch, int64_t per_batch,
                  sc_stream stream);
 /* gradient of lambda (which = -1, out[rank]) or of mode factor `which` (out[kept[which] x rank]) from dscale */

@@ -536,6 +536,54 @@ class _SpectralConvTT(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# separable (depthwise) contraction, reference `_contract_dense_separable` :49-52
+# --------------------------------------------------------------------------------------------------
+class _SpectralConvSeparable(torch.autograd.Function):
+    """y = SpectralConv.forward(x) with `separable=True`: ym[b,c,m] = xm[b,c,m] * w[c,m]  (w: (C, *kept), the kept block of the
+    weight).  Backward: dxm = gm * conj(w), dw = sum_b conj(xm) * gm, db from the DC slot."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, plan):
+        lib = _lib.load()
+        dev = x.device
+        B, C = x.shape[:2]
+        M = plan.n_modes_total
+        with torch.cuda.device(dev):
+            xm = analyze(plan, x)
+            ym = torch.empty_like(xm)
+            _lib.check(lib.sc_cp_apply(_ptr(xm), _ptr(w), _ptr(ym), 0, B, C * M, _stream_ptr(dev)), "sc_cp_apply")
+            y = synthesize(plan, ym, bias)
+        ctx.plan = plan
+        ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.save_for_backward(xm, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _lib.load()
+        plan = ctx.plan
+        xm, w = ctx.saved_tensors
+        B, C = xm.shape[:2]
+        M = plan.n_modes_total
+        dev = gy.device
+        gy = gy.contiguous()
+        st = _stream_ptr(dev)
+        with torch.cuda.device(dev):
+            gm = analyze(plan, gy, adjoint=True)
+            db = None
+            if ctx.bias_shape is not None:
+                db = torch.empty(C, dtype=torch.float32, device=dev)
+                _lib.check(lib.sc_bias_grad(plan.handle, _ptr(gm), _ptr(db), B, C, st), "sc_bias_grad")
+                db = db.reshape(ctx.bias_shape)
+            dw = torch.empty_like(w)
+            _lib.check(lib.sc_cp_dscale(_ptr(xm), _ptr(gm), _ptr(dw), B, C * M, st), "sc_cp_dscale")
+            dxm = torch.empty_like(gm)
+            _lib.check(lib.sc_cp_apply(_ptr(gm), _ptr(w), _ptr(dxm), 1, B, C * M, st), "sc_cp_apply")
+            dx = synthesize(plan, dxm, adjoint=True)
+        return dx, dw, db, None
+
+
+# --------------------------------------------------------------------------------------------------
 # the module
 # --------------------------------------------------------------------------------------------------
 def _validate_scaling_factor(factor, n_dim) -> Optional[List[float]]:
@@ -567,8 +615,7 @@ class SpectralConv(BaseSpectralConv):
     """Fourier-layer spectral convolution (real data, full precision) on hand-written sm_100a kernels.
 
     Parameters: identical to the reference class (spectral_convolution.py:183-305). Variants the kernels do
-    not cover raise `NotImplementedError` at construction: `complex_data=True`, `separable=True`,
-    `fno_block_precision != "full"`.
+    not cover raise `NotImplementedError` at construction: `complex_data=True`, `fno_block_precision != "full"`.
     """
 
     def __init__(
@@ -595,8 +642,9 @@ class SpectralConv(BaseSpectralConv):
         super().__init__(device=device)
         if complex_data:
             raise NotImplementedError("complex_data=True (C2C transforms) is not covered by the B200 kernels yet")
-        if separable:
-            raise NotImplementedError("separable=True is not covered by the B200 kernels yet")
+        if separable and in_channels != out_channels:
+            raise ValueError("To use separable Fourier Conv, in_channels must be equal "
+                             f"to out_channels, but got in_channels={in_channels} and out_channels={out_channels}")
         if fno_block_precision != "full":
             raise NotImplementedError("fno_block_precision must be 'full' (half/mixed spectral precision not built yet)")
         if implementation not in ("reconstructed", "factorized"):
@@ -631,7 +679,8 @@ class SpectralConv(BaseSpectralConv):
         # optional neuraloperator_b200.GradientAllReducer: backward then overlaps the dweight/dbias all-reduce with dx
         self.gradient_reducer = None
 
-        weight_shape = (in_channels, out_channels, *self.max_n_modes)
+        # separable: one channel axis only (:346-356)
+        weight_shape = (in_channels, *self.max_n_modes) if separable else (in_channels, out_channels, *self.max_n_modes)
         tensor_kwargs = decomposition_kwargs if decomposition_kwargs is not None else {}
         self.weight = FactorizedWeight.new(weight_shape, rank=self.rank, factorization=factorization or "Dense",
                                            fixed_rank_modes=fixed_rank_modes, dtype=torch.cfloat, device=device,
@@ -684,6 +733,17 @@ class SpectralConv(BaseSpectralConv):
                 get_plan(plan.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
         return plan.plan_kept
 
+    def _forward_separable(self, x, plan: Plan):
+        """Depthwise spectral conv (`separable=True`, `_contract_dense_separable` :49-52): the weight (C, *max_n_modes) --
+        reconstructed first if it is stored factorized -- is cut to the kept block (`weight[slices_w]`, :471-489) and
+        multiplied mode by mode on the device."""
+        w = self.weight.to_tensor()
+        for j in range(self.order):
+            lo, hi = plan.weight_row_range(j)
+            if lo != 0 or hi != w.shape[1 + j]:
+                w = w.narrow(1 + j, lo, hi - lo)
+        return _SpectralConvSeparable.apply(x, w.contiguous(), self.bias, plan)
+
     def _forward_tucker(self, x, plan: Plan):
         """Factor-by-factor contraction (reference implementation="factorized", `_contract_tucker` :76-103)."""
         w = self.weight
@@ -720,6 +780,8 @@ class SpectralConv(BaseSpectralConv):
         out_grid = self._output_grid(grid, output_shape)
         plan = get_plan(x.device, grid, out_grid, self.n_modes, self.max_n_modes, self.fft_norm)
         x = x.contiguous()
+        if self.separable:
+            return self._forward_separable(x, plan)
         if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "tucker" and \
                 self.in_channels <= 64 and self.out_channels <= 64:
             return self._forward_tucker(x, plan)

@@ -55,6 +55,12 @@ CASES = [
      {"factorization": "cp", "implementation": "factorized", "rank": 7}, {}),
     ("d2_tt", 2, 6, 5, (16, 12), (8, 6),
      {"factorization": "tt", "implementation": "factorized", "rank": [1, 3, 4, 3, 1]}, {}),
+    ("d2_separable", 2, 5, 5, (16, 12), (8, 6), {"separable": True}, {}),
+    ("d2_separable_max_modes", 2, 4, 4, (16, 12), (5, 4), {"separable": True, "max_n_modes": (8, 6)}, {}),
+    ("d1_separable", 3, 6, 6, (32,), (12,), {"separable": True, "implementation": "factorized"}, {}),
+    ("d3_separable", 1, 3, 3, (8, 8, 8), (4, 4, 4), {"separable": True}, {}),
+    ("d2_separable_tucker", 2, 5, 5, (16, 12), (8, 6),
+     {"separable": True, "factorization": "tucker", "implementation": "factorized", "rank": [3, 5, 3]}, {}),
 ]
 
 

@@ -165,6 +165,7 @@ class Weight:
     core: Optional[torch.Tensor] = None           # tucker (r_i, r_o, r_1..r_d)
     weights: Optional[torch.Tensor] = None        # cp (R,)
     factors: Optional[List[torch.Tensor]] = None  # tucker/cp (dim_k, r_k) ; tt (r_k, dim_k, r_k+1)
+    separable: bool = False                       # one channel axis only: logical shape (C, *max_n_modes) (:346-356)
 
     def params(self):
         if self.kind == "dense":
@@ -177,20 +178,25 @@ class Weight:
 
     def sliced(self, plans: Sequence[DimPlan]) -> "Weight":
         """`self.weight[slices_w]` (:489): a view for dense, sliced factors for Tucker/CP/TT."""
+        c0 = 1 if self.separable else 2               # channel axes before the mode axes (:471-474, :494-499)
         if self.kind == "dense":
             t = self.tensor
             for j, p in enumerate(plans):
-                t = t.narrow(2 + j, p.w_index[0], p.kept)
-            return Weight("dense", tensor=t)
+                t = t.narrow(c0 + j, p.w_index[0], p.kept)
+            return Weight("dense", tensor=t, separable=self.separable)
         fs = list(self.factors)
         for j, p in enumerate(plans):
             if self.kind == "tt":
-                fs[2 + j] = fs[2 + j][:, p.w_index[0]: p.w_index[0] + p.kept, :]
+                fs[c0 + j] = fs[c0 + j][:, p.w_index[0]: p.w_index[0] + p.kept, :]
             else:
-                fs[2 + j] = fs[2 + j][p.w_index[0]: p.w_index[0] + p.kept, :]
-        return Weight(self.kind, core=self.core, weights=self.weights, factors=fs)
+                fs[c0 + j] = fs[c0 + j][p.w_index[0]: p.w_index[0] + p.kept, :]
+        return Weight(self.kind, core=self.core, weights=self.weights, factors=fs, separable=self.separable)
 
     def contract(self, xm):
+        if self.separable:
+            # `_contract_dense_separable` (:49-52) and the separable einsums of the factorized forms (:27-31, :61-69, :84-96,
+            # :113-126): out[b,c,m] = x[b,c,m] * W[c,m] with W the (reconstructed) weight
+            return xm * self.to_dense()
         if self.kind == "dense":
             return contract_dense(xm, self.tensor)
         if self.kind == "tucker":
@@ -272,14 +278,15 @@ def spectral_conv_fwd_bwd(x, weight: Weight, bias, grad_y, n_modes, **kw):
     """Forward + the backward torch.autograd records for it. Returns y, dx, [dparams...], dbias."""
     x = x.detach().clone().requires_grad_(True)
     params = [p.detach().clone().requires_grad_(True) for p in weight.params()]
+    sep = weight.separable
     if weight.kind == "dense":
-        w = Weight("dense", tensor=params[0])
+        w = Weight("dense", tensor=params[0], separable=sep)
     elif weight.kind == "tucker":
-        w = Weight("tucker", core=params[0], factors=params[1:])
+        w = Weight("tucker", core=params[0], factors=params[1:], separable=sep)
     elif weight.kind == "cp":
-        w = Weight("cp", weights=params[0], factors=params[1:])
+        w = Weight("cp", weights=params[0], factors=params[1:], separable=sep)
     else:
-        w = Weight("tt", factors=params)
+        w = Weight("tt", factors=params, separable=sep)
     b = bias.detach().clone().requires_grad_(True) if bias is not None else None
     y = spectral_conv_forward(x, w, b, n_modes, **kw)
     y.backward(grad_y)

@@ -35,14 +35,15 @@ def golden_weight(meta, arrays):
     p = {k[3:].replace("__", "."): v for k, v in arrays.items() if k.startswith("p__")}
     nf = len([k for k in p if k.startswith("weight.factors.")])
     factors = [p[f"weight.factors.{i}"] for i in range(nf)]
+    sep = bool(meta["ctor"].get("separable", False))
     if kind == "dense":
-        return Weight("dense", tensor=p["weight.tensor"])
+        return Weight("dense", tensor=p["weight.tensor"], separable=sep)
     if kind == "tucker":
-        return Weight("tucker", core=p["weight.core"], factors=factors)
+        return Weight("tucker", core=p["weight.core"], factors=factors, separable=sep)
     if kind == "cp":
-        return Weight("cp", weights=p["weight.weights"], factors=factors)
+        return Weight("cp", weights=p["weight.weights"], factors=factors, separable=sep)
     if kind == "tt":
-        return Weight("tt", factors=factors)
+        return Weight("tt", factors=factors, separable=sep)
     raise ValueError(kind)
 
 

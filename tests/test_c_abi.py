@@ -85,6 +85,16 @@ def test_module_contract_factorized():
     assert torch.is_complex(conv.weight) and torch.is_complex(cp.weight)
 
 
+def test_module_contract_separable():
+    """separable=True: one channel axis (reference :346-356), equal channel counts enforced with the reference's ValueError."""
+    conv = nb.SpectralConv(5, 5, (8, 6), separable=True)
+    assert tuple(conv.weight.shape) == (5, 8, 4) and sorted(conv.state_dict().keys()) == ["bias", "weight.tensor"]
+    tk = nb.SpectralConv(5, 5, (8, 6), separable=True, factorization="tucker", rank=[3, 5, 3])
+    assert tuple(tk.weight.to_tensor().shape) == (5, 8, 4)
+    with pytest.raises(ValueError, match="in_channels must be equal"):
+        nb.SpectralConv(4, 6, (8, 6), separable=True)
+
+
 def test_tucker_rank_rule():
     # SURVEY.md App. B: (64,64,32,17) @ 0.1 -> (36,36,18,10)
     assert tucker_ranks((64, 64, 32, 17), 0.1) == [36, 36, 18, 10]

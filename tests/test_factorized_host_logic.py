@@ -53,11 +53,12 @@ class _Lib:
         return 0
 
     def sc_cp_apply(self, a, scale, out, conj, B, per, st):
-        out.copy_((a.reshape(B, per) * (scale.conj() if conj else scale)[None]).reshape(out.shape))
+        sc_ = scale.reshape(-1)
+        out.copy_((a.reshape(B, per) * (sc_.conj() if conj else sc_)[None]).reshape(out.shape))
         return 0
 
     def sc_cp_dscale(self, t, g, ds, B, per, st):
-        ds.copy_((t.reshape(B, per).conj() * g.reshape(B, per)).sum(0))
+        ds.copy_((t.reshape(B, per).conj() * g.reshape(B, per)).sum(0).reshape(ds.shape))
         return 0
 
     def sc_cp_factor_grad(self, us, ks, d, lam, ds, out, which, R, st):
@@ -150,3 +151,13 @@ def test_tucker_chain(emulated, kept):
     _compare(lambda x, b, core, ui, uo, *um: sc._SpectralConvTucker.apply(x, b, _Plan(kept), None, core, ui, uo, *um),
              lambda x, b, core, ui, uo, *um: O.contract_tucker(x.to(torch.complex64), core, [ui, uo, *um]).real + b,
              params, torch.randn(B, Co, *kept))
+
+
+@pytest.mark.parametrize("kept", KEPT)
+def test_separable_chain(emulated, kept):
+    d, B, C = len(kept), 2, 3
+    torch.manual_seed(3)
+    params = [torch.randn(B, C, *kept), _c(C, *kept), torch.randn(C, *[1] * d)]
+    _compare(lambda x, w, b: sc._SpectralConvSeparable.apply(x, w, b, _Plan(kept)),
+             lambda x, w, b: (x.to(torch.complex64) * w).real + b,
+             params, torch.randn(B, C, *kept))

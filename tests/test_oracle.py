@@ -37,7 +37,8 @@ def test_oracle_matches_golden(name):
         _close(db, gb, "dbias")
 
 
-@pytest.mark.parametrize("name", [c for c in CASES if golden_index()[c]["weight_kind"] == "dense"])
+@pytest.mark.parametrize("name", [c for c in CASES if golden_index()[c]["weight_kind"] == "dense"
+                                  and not golden_index()[c]["ctor"].get("separable")])
 def test_closed_form_f64_matches_golden(name):
     meta, arr = load_golden(name)
     kw = forward_kwargs(meta)
