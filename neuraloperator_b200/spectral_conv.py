@@ -779,6 +779,12 @@ class SpectralConv(BaseSpectralConv):
         grid = list(x.shape[2:])
         out_grid = self._output_grid(grid, output_shape)
         plan = get_plan(x.device, grid, out_grid, self.n_modes, self.max_n_modes, self.fft_norm)
+        if x.shape[0] == 0:
+            # empty batch (torch.fft accepts it in the reference): nothing to launch; stay connected to the autograd graph
+            z = x.sum() * 0
+            for prm in self.parameters():
+                z = z + (prm.real.sum() if prm.is_complex() else prm.sum()) * 0
+            return x.new_zeros((0, self.out_channels, *out_grid)) + z
         x = x.contiguous()
         if self.separable:
             return self._forward_separable(x, plan)

@@ -319,3 +319,14 @@ def test_separable_matches_oracle(cuda_device, B, C, grid, modes):
     y.backward(gy.to(cuda_device))
     assert rel_err(y, y_ref) < REL_TOL and rel_err(xd.grad, dx_ref) < REL_TOL
     assert rel_err(conv.weight.tensor.grad, dws_ref[0]) < REL_TOL and rel_err(conv.bias.grad, db_ref) < REL_TOL
+
+
+def test_empty_batch(cuda_device):
+    """B = 0 is accepted (the reference's torch.fft calls accept it): empty output of the right shape, zero gradients."""
+    conv = nb.SpectralConv(4, 6, (8, 8)).to(cuda_device)
+    x = torch.empty(0, 4, 16, 16, device=cuda_device, requires_grad=True)
+    y = conv(x)
+    assert tuple(y.shape) == (0, 6, 16, 16) and y.dtype == torch.float32
+    y.sum().backward()
+    assert conv.weight.tensor.grad is not None and float(conv.weight.tensor.grad.abs().max()) == 0.0
+    assert tuple(x.grad.shape) == (0, 4, 16, 16)
