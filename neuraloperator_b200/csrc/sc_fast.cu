@@ -190,6 +190,9 @@ struct AnaParams {
   const uint8_t* a2_img;   // [128 x 256] bf16, plain row-major: real-embedded leading-dim table (T1 rows 0-63, T2 rows 64-127);
                            // copied once into TENSOR MEMORY and used as the TMEM A operand of every stage-2 MMA
   int n_tiles, W, slabs, N1, KX, QROWS, n_stages, tmem_cols;
+#ifdef SC_L2_STREAM_HINT_BUILD
+  int l2_stream_hint;      // 1: the x slabs are loaded with an L2 evict-first policy (read once)
+#endif
   uint32_t off_f32, off_ring, off_b1, off_a2, off_b2, off_scratch, stage_off;   // stage_off: output staging, relative to off_scratch
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
@@ -261,6 +264,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // ------------------------------------------------------------------ TMA producer: one tensor load per 32 KB slab
     const int total = n_local * P.slabs;
     uint8_t* f32_stage = smem + P.off_f32;
+#ifdef SC_L2_STREAM_HINT_BUILD
+    const uint64_t pol = l2_policy_evict_first();
+#endif
     pdl_wait();                                  // x is produced by the previous kernel of the stream
     for (int idx = 0; idx < total; ++idx) {
       const int sb = idx % FA_F32_STAGES;
@@ -268,7 +274,11 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
       if (elect_one()) {
         const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
         mbar_arrive_expect_tx(&bar_f32_full[sb], 32768u);
-        tma_load_2d(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128);
+#ifdef SC_L2_STREAM_HINT_BUILD
+        if (P.l2_stream_hint) tma_load_2d_hint(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128, pol);
+        else
+#endif
+          tma_load_2d(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128);
       }
       __syncwarp();
     }
@@ -500,6 +510,9 @@ struct SynParams {
   const uint8_t* aa_img;   // [128 x 128] bf16 image: leading-dim table, columns (2q+s | 64+2q+s)
   const uint8_t* bb_img;   // two [W x 64] bf16 images: T1 then T2 of the last-dim table (rows = w, K = j)
   int n_tiles, W, KX, QROWS, H, n_channels, tmem_cols;
+#ifdef SC_L2_STREAM_HINT_BUILD
+  int l2_stream_hint;      // 1: the image rows are stored with an L2 evict-first policy (written once, not re-read by this step)
+#endif
   int slices_per_image;    // 3-D: the fused kernel sees (image, z) slices; bias channel = (slice / slices_per_image) % n_channels
   uint32_t off_aa, off_ba, off_u, off_bb, off_stage;
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
@@ -713,6 +726,9 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     uint8_t* my_stage = smem + P.off_stage + warp * 8192;   // two [32 x 128 B] boxes per warp
     uint32_t chunk_ctr = 0;
+#ifdef SC_L2_STREAM_HINT_BUILD
+    const uint64_t pol = l2_policy_evict_first();
+#endif
     pdl_wait();                                             // the output image may still be read by the previous kernel
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
@@ -750,7 +766,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&out_map, box, c, tile * 128 + warp * 32);
+#ifdef SC_L2_STREAM_HINT_BUILD
+          if (P.l2_stream_hint) tma_store_2d_hint(&out_map, box, c, tile * 128 + warp * 32, pol);
+          else
+#endif
+            tma_store_2d(&out_map, box, c, tile * 128 + warp * 32);
           bulk_commit();
         }
         ++chunk_ctr;
@@ -1562,6 +1582,20 @@ static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t sm
   return cudaLaunchKernelExC(&cfg, func, args);
 }
 
+// Experiment prepared for the next round, NOT yet measured or validated on hardware, therefore compiled out by default
+// (build with SC_EXTRA_NVCC_FLAGS=-DSC_L2_STREAM_HINT_BUILD): L2 evict-first policy on the image streams so that the weights
+// and mode tensors a step re-reads stay L2-resident.  SC_L2_STREAM_HINT=0|1 then switches it at run time for A/B runs.
+#ifdef SC_L2_STREAM_HINT_BUILD
+constexpr int SC_L2_STREAM_HINT_DEFAULT = 0;
+static int l2_stream_hint_enabled() {
+  static const int v = [] {
+    const char* e = getenv("SC_L2_STREAM_HINT");
+    return e != nullptr ? (atoi(e) != 0 ? 1 : 0) : SC_L2_STREAM_HINT_DEFAULT;
+  }();
+  return v;
+}
+#endif
+
 // SC_TRACE_FILE=<path>: record the per-role timeline of CTA 0 of every fused transform launch (debug only; synchronises)
 static long long* trace_begin() {
   if (getenv("SC_TRACE_FILE") == nullptr) return nullptr;
@@ -1592,6 +1626,9 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   P.x = images; P.out = modes_out; P.b1_img = t.d_b1; P.a2_img = t.d_a2;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.slabs = t.slabs; P.N1 = t.N1; P.KX = t.KX; P.QROWS = t.G * t.KY;
   P.n_stages = t.n_stages; P.tmem_cols = t.tmem_cols;
+#ifdef SC_L2_STREAM_HINT_BUILD
+  P.l2_stream_hint = l2_stream_hint_enabled();
+#endif
   P.off_f32 = t.off_f32; P.off_ring = t.off_ring;
   P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch; P.stage_off = t.stage_off;
   P.trace = trace_begin();
@@ -1626,6 +1663,9 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.KX = t.KX; P.QROWS = t.G * t.KY; P.H = t.H;
   P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
   P.slices_per_image = slices_per_image > 0 ? slices_per_image : 1;
+#ifdef SC_L2_STREAM_HINT_BUILD
+  P.l2_stream_hint = l2_stream_hint_enabled();
+#endif
   P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb; P.off_stage = t.off_stage;
   P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;

@@ -181,6 +181,26 @@ __device__ __forceinline__ void tma_load_2d(void* sdst, const void* tmap, uint64
                : "memory");
 }
 
+// L2 eviction-priority hint for data that is touched exactly once (image rows streaming through the transforms): their
+// lines are the first to go, so the small tensors a step re-reads (weights, kept modes) stay resident in the 126 MB L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* sdst, const void* tmap, uint64_t* bar, int x, int y, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(sdst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, const void* ssrc, int x, int y, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(tmap),
+               "r"(smem_u32(ssrc)), "r"(x), "r"(y), "l"(pol)
+               : "memory");
+}
+
 // 2-D tiled TMA store shared -> global through a tensor map (box laid out in the map's swizzle mode)
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* ssrc, int x, int y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(smem_u32(ssrc)),
