@@ -57,6 +57,10 @@ int  sc_plan_kept_modes(const sc_plan* plan, int32_t* kept_out);
 /* unshifted spectrum bin read by kept slot t of dim `dim`, and the weight row it is multiplied with
  * (the content of slices_x after undoing fftshift, and of slices_w; :476-519).  Each array has kept[dim] entries. */
 int  sc_plan_mode_bins(const sc_plan* plan, int dim, int32_t* in_bins_out, int32_t* weight_rows_out);
+/* The same index set straight from a problem description: pure host arithmetic, needs no device (what the CPU tests compare
+ * bit-exactly with the reference's slices).  kept_out: k'_dim; the two arrays must hold min(F_dim, n_modes_dim) entries. */
+int  sc_problem_mode_bins(const sc_problem* problem, int dim, int32_t* kept_out, int32_t* in_bins_out,
+                          int32_t* weight_rows_out);
 /* scratch the transform entry points need for `batch_times_channels` images (max over Ci, Co) */
 size_t sc_workspace_bytes(const sc_plan* plan, int64_t batch_times_channels);
 /* 0 = generic SIMT kernels only, 1 = tcgen05/TMA fused path where the shape qualifies (default) */

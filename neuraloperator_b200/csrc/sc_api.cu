@@ -42,6 +42,36 @@ static inline void unit(long long a, long long b, long long n, int sign, double*
   *im = sign * std::sin(ang);
 }
 
+// Kept-mode index set of one dim -- host only, no device state: what `SpectralConv.forward` derives at :465-519.
+//   t->k        kept modes  min(F, n_modes)                                   (:466)
+//   t->w0       first weight row used (`slices_w`)                            (:476-486)
+//   t->in_bins  unshifted spectrum bin read by kept slot s (`slices_x` after undoing the fftshift of :449)   (:500-519)
+static bool index_dim(const sc_problem& pr, int j, DimTables* tp) {
+  DimTables& t = *tp;
+  const bool last = (j == pr.ndim - 1);
+  t.N = pr.grid[j];
+  t.M = pr.out_grid[j];
+  if (t.N < 1 || t.M < 1) { set_error("grid sizes must be >= 1"); return false; }
+  if (pr.n_modes[j] < 1) { set_error("n_modes must be >= 1 along every dim"); return false; }
+  t.F = last ? t.N / 2 + 1 : t.N;
+  t.k = pr.n_modes[j] < t.F ? pr.n_modes[j] : t.F;                      // min(size, n_mode)   (:466)
+  const int start = pr.max_n_modes[j] - t.k;                            // (:465-468)
+  if (start < 0) { set_error("n_modes exceeds max_n_modes (weight too small for the requested modes)"); return false; }
+  t.in_bins.resize(t.k);
+  if (last) {
+    t.w0 = 0;                                                           // slice(None, -start)  (:486)
+    for (int s = 0; s < t.k; ++s) t.in_bins[s] = s;                      // slice(None, k)       (:514-517)
+  } else {
+    t.w0 = start ? start / 2 : 0;                                       // slice(start//2, -start//2) (:476-485)
+    const int centre = t.F / 2, neg = t.k / 2;                          // (:507-512)
+    for (int s = 0; s < t.k; ++s) {
+      const int shifted = centre - neg + s;
+      t.in_bins[s] = ((shifted - t.F / 2) % t.F + t.F) % t.F;           // undo fftshift = roll by F//2 (:449)
+    }
+  }
+  return true;
+}
+
 static bool build_plan(const sc_problem& pr, Plan* p) {
   p->prob = pr;
   p->d = pr.ndim;
@@ -54,27 +84,8 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
   p->weight_block_is_whole = true;
   for (int j = 0; j < d; ++j) {
     DimTables& t = p->dim[j];
-    const bool last = (j == d - 1);
-    t.N = pr.grid[j];
-    t.M = pr.out_grid[j];
-    if (t.N < 1 || t.M < 1) { set_error("grid sizes must be >= 1"); return false; }
-    if (pr.n_modes[j] < 1) { set_error("n_modes must be >= 1 along every dim"); return false; }
-    t.F = last ? t.N / 2 + 1 : t.N;
-    t.k = pr.n_modes[j] < t.F ? pr.n_modes[j] : t.F;                      // min(size, n_mode)   (:466)
-    const int start = pr.max_n_modes[j] - t.k;                            // (:465-468)
-    if (start < 0) { set_error("n_modes exceeds max_n_modes (weight too small for the requested modes)"); return false; }
-    t.in_bins.resize(t.k);
-    if (last) {
-      t.w0 = 0;                                                           // slice(None, -start)  (:486)
-      for (int s = 0; s < t.k; ++s) t.in_bins[s] = s;                      // slice(None, k)       (:514-517)
-    } else {
-      t.w0 = start ? start / 2 : 0;                                       // slice(start//2, -start//2) (:476-485)
-      const int centre = t.F / 2, neg = t.k / 2;                          // (:507-512)
-      for (int s = 0; s < t.k; ++s) {
-        const int shifted = centre - neg + s;
-        t.in_bins[s] = ((shifted - t.F / 2) % t.F + t.F) % t.F;           // undo fftshift = roll by F//2 (:449)
-      }
-    }
+    if (!index_dim(pr, j, &t)) return false;
+    const int start = pr.max_n_modes[j] - t.k;
     if (start != 0) p->weight_block_is_whole = false;
     p->n_modes_total *= t.k;
     p->grid_points *= t.N;
@@ -380,6 +391,20 @@ int sc_plan_kept_modes(const sc_plan* plan, int32_t* kept_out) {
   if (p == nullptr || kept_out == nullptr) return 0;
   for (int j = 0; j < p->d; ++j) kept_out[j] = p->dim[j].k;
   return p->d;
+}
+
+int sc_problem_mode_bins(const sc_problem* problem, int dim, int32_t* kept_out, int32_t* in_bins_out,
+                         int32_t* weight_rows_out) {
+  SC_REQUIRE(problem != nullptr && problem->ndim >= 1 && problem->ndim <= SC_MAX_DIMS && dim >= 0 && dim < problem->ndim,
+             "sc_problem_mode_bins: bad argument");
+  DimTables t;
+  SC_TRY(index_dim(*problem, dim, &t));
+  if (kept_out) *kept_out = t.k;
+  for (int s = 0; s < t.k; ++s) {
+    if (in_bins_out) in_bins_out[s] = t.in_bins[s];
+    if (weight_rows_out) weight_rows_out[s] = t.w0 + s;
+  }
+  return 0;
 }
 
 int sc_plan_mode_bins(const sc_plan* plan, int dim, int32_t* in_bins_out, int32_t* weight_rows_out) {

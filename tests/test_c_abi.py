@@ -110,3 +110,67 @@ def test_factorized_reconstruction_matches_oracle_layout():
     assert torch.allclose(w.to_dense(), conv.weight.to_tensor().detach(), atol=1e-6)
     xm = torch.randn(2, 6, 8, 4, dtype=torch.cfloat)
     assert torch.allclose(w.contract(xm), O.contract_dense(xm, w.to_dense()), atol=1e-5)
+
+
+def _c_mode_bins(lib, grid, stored, max_modes, dim):
+    prob = _lib.ScProblem()
+    prob.ndim = len(grid)
+    for j in range(len(grid)):
+        prob.grid[j] = grid[j]
+        prob.out_grid[j] = grid[j]
+        prob.n_modes[j] = stored[j]
+        prob.max_n_modes[j] = max_modes[j]
+    prob.fft_norm = 0
+    cap = max(grid) + 1
+    kept = ctypes.c_int32(0)
+    bins = (ctypes.c_int32 * cap)()
+    rows = (ctypes.c_int32 * cap)()
+    rc = lib.sc_problem_mode_bins(ctypes.byref(prob), dim, ctypes.byref(kept), bins, rows)
+    assert rc == 0, lib.sc_last_error()
+    return list(bins[:kept.value]), list(rows[:kept.value])
+
+
+def _torch_slicing_bins(N, n_mode_stored, max_mode, last):
+    """The reference's own slice objects (spectral_convolution.py:465-519) applied to index vectors with torch's fftshift."""
+    F = N // 2 + 1 if last else N
+    start = max_mode - min(F, n_mode_stored)                                    # :465-468
+    if last:
+        sw = slice(None, -start) if start else slice(None)                      # :486
+    else:
+        sw = slice(start // 2, -start // 2) if start else slice(start, None)    # :483-485
+    w_rows = torch.arange(max_mode)[sw]
+    kept = len(w_rows)
+    spec = torch.arange(F)
+    if last:
+        bins = spec[slice(None, kept) if kept < F else slice(None)]             # :514-517
+    else:
+        spec = torch.fft.fftshift(spec)                                         # :449
+        centre, neg, pos = F // 2, kept // 2, kept // 2 + kept % 2              # :507-512
+        bins = spec[slice(centre - neg, centre + pos)]
+    return bins.tolist(), w_rows.tolist()
+
+
+def test_kept_mode_index_set_is_bit_exact(lib):
+    """The library's host index math (sc_problem_mode_bins, no device needed) against the reference's slice objects and the
+    oracle, swept over even/odd grids, modes below / at / above the spectrum length and max_n_modes with even / odd starts."""
+    from oracle import spectral_conv_oracle as O
+    checked = 0
+    for N in list(range(1, 14)) + [16, 17, 31, 32, 33, 64]:
+        for last in (False, True):
+            F = N // 2 + 1 if last else N
+            for nm in sorted({1, 2, 3, F - 1, F, F + 1, F + 3, 5, 8} - {0, -1}):
+                for extra in (0, 1, 2, 3):
+                    if nm < 1:
+                        continue
+                    mx = nm + extra
+                    grid = (5, N) if last else (N, 6)          # put the dim under test in the leading or the last slot
+                    dim = 1 if last else 0
+                    stored = [3, nm] if last else [nm, 3]
+                    maxm = [3, mx] if last else [mx, 3]
+                    got = _c_mode_bins(lib, grid, stored, maxm, dim)
+                    want = _torch_slicing_bins(N, nm, mx, last)
+                    assert got == want, (N, last, nm, mx, got, want)
+                    p = O.kept_mode_plan(grid, stored, maxm)[dim]
+                    assert got == (p.in_bins, p.w_index)
+                    checked += 1
+    assert checked > 500
