@@ -61,6 +61,20 @@ int  sc_plan_mode_bins(const sc_plan* plan, int dim, int32_t* in_bins_out, int32
  * bit-exactly with the reference's slices).  kept_out: k'_dim; the two arrays must hold min(F_dim, n_modes_dim) entries. */
 int  sc_problem_mode_bins(const sc_problem* problem, int dim, int32_t* kept_out, int32_t* in_bins_out,
                           int32_t* weight_rows_out);
+/* The twiddle tables a plan for `problem` would upload, computed on the host (no device needed): the truncated transforms ARE
+ * products with these tables, so applying them in numpy reproduces the library's arithmetic up to summation order -- this is how
+ * the CPU tests check norms, the Hermitian rules of the C2R step (:552-559), resampling and odd sizes against the reference.
+ * Row-major float32; complex tables are interleaved (re, im) and `cols_out` counts floats.  `out` may be NULL to query the shape.
+ *   LAST_ANALYSIS          [N_d x 2k_d]   x-row -> (re, im) of the kept bins of the last dim, forward scale folded in
+ *   LAST_SYNTHESIS         [2k_d x M_d]   (re, im) of the kept bins -> output row, C2R rules + inverse scale folded in
+ *   LEAD_ANALYSIS (dim)    [k_j x N_j]    complex,  exp(-2 pi i b n / N_j) for the kept bins b in kept-slot order
+ *   LEAD_SYNTHESIS (dim)   [M_j x k_j]    complex,  exp(+2 pi i b n / M_j) * [b < M_j]
+ *   *_ADJOINT                             the conjugate transposes the backward pass multiplies with */
+enum { SC_TABLE_LAST_ANALYSIS = 0, SC_TABLE_LAST_ANALYSIS_ADJOINT = 1, SC_TABLE_LAST_SYNTHESIS = 2,
+       SC_TABLE_LAST_SYNTHESIS_ADJOINT = 3, SC_TABLE_LEAD_ANALYSIS = 4, SC_TABLE_LEAD_ANALYSIS_ADJOINT = 5,
+       SC_TABLE_LEAD_SYNTHESIS = 6, SC_TABLE_LEAD_SYNTHESIS_ADJOINT = 7 };
+int  sc_problem_table(const sc_problem* problem, int which, int dim, float* out, size_t out_capacity_floats,
+                      int64_t* rows_out, int64_t* cols_out);
 /* scratch the transform entry points need for `batch_times_channels` images (max over Ci, Co) */
 size_t sc_workspace_bytes(const sc_plan* plan, int64_t batch_times_channels);
 /* 0 = generic SIMT kernels only, 1 = tcgen05/TMA fused path where the shape qualifies (default) */

@@ -52,6 +52,7 @@ SIGNATURES = {
                                   c_i32, c_void_p, c_size_t, c_void_p]),
     "sc_table_contract": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p]),
     "sc_pair_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_void_p]),
+    "sc_problem_table": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p, c_void_p]),
     "sc_problem_mode_bins": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "sc_cp_scale": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_i32, c_void_p]),
     "sc_cp_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i32, c_i64, c_void_p]),

@@ -23,6 +23,7 @@ bool cuda_ok(cudaError_t e, const char* what) {
 
 template <typename T>
 static bool upload(Plan* p, const std::vector<T>& host, T** dev) {
+  if (p->host_only) { *dev = nullptr; return true; }   // table inspection without a device (sc_problem_table)
   void* d = nullptr;
   const size_t bytes = host.size() * sizeof(T);
   if (!cuda_ok(cudaMalloc(&d, bytes ? bytes : sizeof(T)), "cudaMalloc(table)")) return false;
@@ -78,7 +79,7 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
   const int d = p->d;
   if (d < 1 || d > SC_MAX_DIMS) { set_error("ndim must be in 1..4"); return false; }
   if (pr.fft_norm < 0 || pr.fft_norm > 2) { set_error("unknown fft_norm"); return false; }
-  if (!cuda_ok(cudaGetDevice(&p->device), "cudaGetDevice")) return false;
+  if (!p->host_only && !cuda_ok(cudaGetDevice(&p->device), "cudaGetDevice")) return false;
 
   p->n_modes_total = p->grid_points = p->out_points = p->weight_elems_per_io = 1;
   p->weight_block_is_whole = true;
@@ -174,7 +175,7 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
     for (int j = 0; j < d; ++j) dc = dc * p->dim[j].k + (j == d - 1 ? 0 : p->dim[j].k / 2);
     p->dc_slot = (int)dc;
   }
-  return fast_plan_init(p);
+  return p->host_only ? true : fast_plan_init(p);
 }
 
 static inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -391,6 +392,42 @@ int sc_plan_kept_modes(const sc_plan* plan, int32_t* kept_out) {
   if (p == nullptr || kept_out == nullptr) return 0;
   for (int j = 0; j < p->d; ++j) kept_out[j] = p->dim[j].k;
   return p->d;
+}
+
+int sc_problem_table(const sc_problem* problem, int which, int dim, float* out, size_t out_capacity_floats,
+                     int64_t* rows_out, int64_t* cols_out) {
+  SC_REQUIRE(problem != nullptr && rows_out != nullptr && cols_out != nullptr, "sc_problem_table: null argument");
+  Plan plan;
+  plan.host_only = true;
+  SC_TRY(build_plan(*problem, &plan));
+  const int d = plan.d;
+  const float* src = nullptr;
+  int64_t rows = 0, cols = 0;       // cols counts floats (complex tables: 2 per entry)
+  const DimTables& last = plan.dim[d - 1];
+  switch (which) {
+    case SC_TABLE_LAST_ANALYSIS:          src = plan.h_TA.data();  rows = last.N;     cols = 2 * last.k; break;
+    case SC_TABLE_LAST_ANALYSIS_ADJOINT:  src = plan.h_TAT.data(); rows = 2 * last.k; cols = last.N;     break;
+    case SC_TABLE_LAST_SYNTHESIS:         src = plan.h_TS.data();  rows = 2 * last.k; cols = last.M;     break;
+    case SC_TABLE_LAST_SYNTHESIS_ADJOINT: src = plan.h_TST.data(); rows = last.M;     cols = 2 * last.k; break;
+    default: {
+      SC_REQUIRE(dim >= 0 && dim < d - 1, "sc_problem_table: leading-dim tables need 0 <= dim < ndim - 1");
+      const DimTables& t = plan.dim[dim];
+      switch (which) {
+        case SC_TABLE_LEAD_ANALYSIS:          src = &t.h_A[0].x;  rows = t.k; cols = 2 * (int64_t)t.N; break;
+        case SC_TABLE_LEAD_ANALYSIS_ADJOINT:  src = &t.h_AH[0].x; rows = t.N; cols = 2 * (int64_t)t.k; break;
+        case SC_TABLE_LEAD_SYNTHESIS:         src = &t.h_S[0].x;  rows = t.M; cols = 2 * (int64_t)t.k; break;
+        case SC_TABLE_LEAD_SYNTHESIS_ADJOINT: src = &t.h_SH[0].x; rows = t.k; cols = 2 * (int64_t)t.M; break;
+        default: SC_REQUIRE(false, "sc_problem_table: unknown table id");
+      }
+    }
+  }
+  *rows_out = rows;
+  *cols_out = cols;
+  if (out != nullptr) {
+    SC_REQUIRE((size_t)(rows * cols) <= out_capacity_floats, "sc_problem_table: output buffer too small");
+    memcpy(out, src, (size_t)(rows * cols) * sizeof(float));
+  }
+  return 0;
 }
 
 int sc_problem_mode_bins(const sc_problem* problem, int dim, int32_t* kept_out, int32_t* in_bins_out,

@@ -49,6 +49,7 @@ struct Plan {
   int64_t weight_elems_per_io = 1;         // prod max_n_modes
   bool weight_block_is_whole = true;       // kept block == whole weight tensor
   bool fast_enabled = true;
+  bool host_only = false;                  // tables computed on the host only, nothing uploaded (sc_problem_table)
   std::vector<float> h_TA, h_TAT, h_TS, h_TST;   // host copies of the last-dim tables
   FastTables* fast = nullptr;              // tcgen05 path state (nullptr when the shape does not qualify)
   std::vector<void*> owned;                // every cudaMalloc made for this plan

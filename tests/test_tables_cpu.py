@@ -1,0 +1,116 @@
+"""The library's twiddle tables, fetched on the host (sc_problem_table: no GPU), applied in numpy and compared with the
+outputs of the unmodified reference stored in tests/golden/.
+
+The truncated transforms the kernels run ARE products with these tables (tcgen05 / SIMT kernels only differ in how they
+tile the products), so this pins norms, the Hermitian rules of the C2R step (spectral_convolution.py:552-559), resampling
+(`output_shape` / `resolution_scaling_factor`, :524-528), odd grids, modes above the spectrum length and `max_n_modes`
+on CPU, forward (y) and backward (dx), for every golden case.  The mode-wise contraction in the middle is taken from the
+oracle's einsum restatement (differentiated by torch for the backward direction)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_index, golden_weight, load_golden
+from neuraloperator_b200 import _lib
+from oracle import spectral_conv_oracle as O
+
+CASES = sorted(golden_index().keys())
+T_LAST_A, T_LAST_AT, T_LAST_S, T_LAST_ST, T_LEAD_A, T_LEAD_AH, T_LEAD_S, T_LEAD_SH = range(8)
+
+
+def _problem(meta):
+    prob = _lib.ScProblem()
+    d = len(meta["grid"])
+    prob.ndim = d
+    for j in range(d):
+        prob.grid[j] = meta["grid"][j]
+        prob.out_grid[j] = meta["out_grid"][j]
+        prob.n_modes[j] = meta["stored_n_modes"][j]
+        prob.max_n_modes[j] = meta["max_n_modes"][j]
+    prob.fft_norm = _lib.NORMS[meta["ctor"].get("fft_norm", "forward")]
+    return prob
+
+
+def _table(lib, prob, which, dim=0):
+    rows, cols = ctypes.c_int64(0), ctypes.c_int64(0)
+    assert lib.sc_problem_table(ctypes.byref(prob), which, dim, None, 0, ctypes.byref(rows), ctypes.byref(cols)) == 0, \
+        lib.sc_last_error()
+    buf = np.empty(rows.value * cols.value, dtype=np.float32)
+    rc = lib.sc_problem_table(ctypes.byref(prob), which, dim, buf.ctypes.data_as(ctypes.c_void_p), buf.size,
+                              ctypes.byref(rows), ctypes.byref(cols))
+    assert rc == 0, lib.sc_last_error()
+    t = buf.reshape(rows.value, cols.value).astype(np.float64)
+    if which >= T_LEAD_A:
+        t = t[:, 0::2] + 1j * t[:, 1::2]
+    return t
+
+
+def _apply(t, x, axis):
+    """out[..., p, ...] = sum_q t[p, q] x[..., q, ...] along `axis`."""
+    return np.moveaxis(np.tensordot(t, x, axes=([1], [axis])), 0, axis)
+
+
+def _interleave(z):
+    out = np.empty(z.shape[:-1] + (2 * z.shape[-1],), dtype=np.float64)
+    out[..., 0::2], out[..., 1::2] = z.real, z.imag
+    return out
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.load()
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tables_reproduce_reference_outputs(lib, name):
+    meta, arr = load_golden(name)
+    prob = _problem(meta)
+    d = prob.ndim
+    x = arr["x"].numpy().astype(np.float64)
+    gy = arr["gy"].numpy().astype(np.float64)
+
+    # ---- forward analysis: last dim (real table), then the leading dims (complex tables)
+    r = x @ _table(lib, prob, T_LAST_A)
+    xm = r[..., 0::2] + 1j * r[..., 1::2]
+    for j in range(d - 1):
+        xm = _apply(_table(lib, prob, T_LEAD_A, j), xm, 2 + j)
+
+    # ---- contraction (oracle einsum; torch records its backward)
+    plans = O.kept_mode_plan(meta["grid"], meta["stored_n_modes"], meta["max_n_modes"])
+    assert list(xm.shape[2:]) == [p.kept for p in plans]
+    w = golden_weight(meta, arr).sliced(plans)
+    xm_t = torch.from_numpy(xm).to(torch.complex128).requires_grad_(True)
+    w64 = O.Weight(w.kind, tensor=None if w.tensor is None else w.tensor.to(torch.complex128),
+                   core=None if w.core is None else w.core.to(torch.complex128),
+                   weights=None if w.weights is None else w.weights.to(torch.complex128),
+                   factors=None if w.factors is None else [f.to(torch.complex128) for f in w.factors],
+                   separable=w.separable)
+    ym_t = w64.contract(xm_t)
+    ym = ym_t.detach().numpy()
+
+    # ---- forward synthesis
+    u = ym
+    for j in range(d - 1):
+        u = _apply(_table(lib, prob, T_LEAD_S, j), u, 2 + j)
+    y = _interleave(u) @ _table(lib, prob, T_LAST_S)
+    if "p__bias" in arr:
+        y = y + arr["p__bias"].numpy().astype(np.float64)
+    y_ref = arr["y"].numpy().astype(np.float64)
+    assert list(y.shape) == list(y_ref.shape)
+    assert np.abs(y - y_ref).max() <= 2e-5 * np.abs(y_ref).max(), "y"
+
+    # ---- backward: adjoint of the synthesis, conjugate contraction, adjoint of the analysis
+    g = gy @ _table(lib, prob, T_LAST_ST)
+    gm = g[..., 0::2] + 1j * g[..., 1::2]
+    for j in range(d - 1):
+        gm = _apply(_table(lib, prob, T_LEAD_SH, j), gm, 2 + j)
+    ym_t.backward(torch.from_numpy(gm).to(torch.complex128))
+    dxm = xm_t.grad.numpy()
+    v = dxm
+    for j in range(d - 1):
+        v = _apply(_table(lib, prob, T_LEAD_AH, j), v, 2 + j)
+    dx = _interleave(v) @ _table(lib, prob, T_LAST_AT)
+    dx_ref = arr["dx"].numpy().astype(np.float64)
+    assert np.abs(dx - dx_ref).max() <= 2e-5 * np.abs(dx_ref).max(), "dx"
