@@ -114,3 +114,35 @@ def test_tables_reproduce_reference_outputs(lib, name):
     dx = _interleave(v) @ _table(lib, prob, T_LAST_AT)
     dx_ref = arr["dx"].numpy().astype(np.float64)
     assert np.abs(dx - dx_ref).max() <= 2e-5 * np.abs(dx_ref).max(), "dx"
+
+
+def _bf16_round(a):
+    """float32 -> nearest-even bfloat16, returned as float32 (the rounding `cvt.rn.bf16x2.f32` applies in the kernels)."""
+    u = np.asarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_bf16x3_operand_split_meets_the_tolerance(lib):
+    """Arithmetic model of the tensor-core path on CPU: x = x_hi + x_lo and T = T1 + T2 in bf16, products x_hi*T1 + x_lo*T1 +
+    x_hi*T2 accumulated in fp32.  With the library's own cfg-2 analysis table the result stays within 1e-5 of
+    the float64 product -- two orders below the 1e-3 contract; a plain bf16 product would miss it."""
+    prob = _lib.ScProblem()
+    prob.ndim = 2
+    for j, (n, k) in enumerate(((128, 32), (128, 17))):
+        prob.grid[j] = prob.out_grid[j] = n
+        prob.n_modes[j] = prob.max_n_modes[j] = k
+    prob.fft_norm = 0
+    t64 = _table(lib, prob, T_LAST_A)                       # [128 x 34], forward scale folded in
+    t = t64.astype(np.float32)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((512, 128)).astype(np.float32)
+    exact = x.astype(np.float64) @ t64
+    x_hi = _bf16_round(x)
+    x_lo = _bf16_round(x - x_hi)
+    t1 = _bf16_round(t)
+    t2 = _bf16_round(t - t1)
+    acc = (x_hi @ t1).astype(np.float32) + (x_lo @ t1).astype(np.float32) + (x_hi @ t2).astype(np.float32)
+    scale = np.abs(exact).max()
+    assert np.abs(acc - exact).max() / scale < 1e-5
+    assert np.abs((x_hi @ t1) - exact).max() / scale > 1e-3    # single bf16 product: not good enough, hence the split
