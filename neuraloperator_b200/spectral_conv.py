@@ -13,6 +13,7 @@ from collections import OrderedDict
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
+from torch.autograd.function import once_differentiable
 from torch import nn
 
 from . import _lib
@@ -222,6 +223,7 @@ class _SpectralConvDense(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         lib = _lib.load()
         xm, weight = ctx.saved_tensors
@@ -333,6 +335,7 @@ class _SpectralConvTucker(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         lib = _lib.load()
         plan, plan_kept, d = ctx.plan, ctx.plan_kept, ctx.d
@@ -422,6 +425,7 @@ class _SpectralConvCP(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         lib = _lib.load()
         plan = ctx.plan
@@ -496,6 +500,7 @@ class _SpectralConvTT(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         lib = _lib.load()
         plan, plan_kept, d = ctx.plan, ctx.plan_kept, ctx.d
@@ -559,6 +564,7 @@ class _SpectralConvSeparable(torch.autograd.Function):
         return y
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, gy):
         lib = _lib.load()
         plan = ctx.plan

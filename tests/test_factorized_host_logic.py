@@ -161,3 +161,14 @@ def test_separable_chain(emulated, kept):
     _compare(lambda x, w, b: sc._SpectralConvSeparable.apply(x, w, b, _Plan(kept)),
              lambda x, w, b: (x.to(torch.complex64) * w).real + b,
              params, torch.randn(B, C, *kept))
+
+
+def test_double_backward_is_refused_loudly(emulated):
+    """The kernels implement first-order gradients only; differentiating the backward pass must not silently return zeros."""
+    kept = (4, 3)
+    x = torch.randn(2, 3, *kept, requires_grad=True)
+    w = _c(3, *kept).requires_grad_(True)
+    y = sc._SpectralConvSeparable.apply(x, w, None, _Plan(kept))
+    (gx,) = torch.autograd.grad(y.square().sum(), x, create_graph=True)
+    with pytest.raises(RuntimeError, match="once_differentiable|differentiate twice"):
+        gx.sum().backward()
