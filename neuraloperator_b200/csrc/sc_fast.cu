@@ -1309,11 +1309,31 @@ struct FusedSynthesisTables {
 // allocator) to the same plan step after step, so encoded maps are kept in a small per-plan cache.
 struct TensorMapCacheEntry { const void* base; uint64_t rows, W; int kind; CUtensorMap map; };
 
+#ifdef SC_ROWS_KERNELS
+// last-dim ("rows") tensor-core kernels for grids the fused 2-D kernels do not cover -- see the section at the end of the file
+struct RowsAnaTables {
+  bool ok = false;
+  int W = 0, N1 = 0, out_cols = 0, slabs = 0, f32_stages = 0, ring_stages = 0, tmem_cols = 0;
+  uint32_t tab_bytes = 0, slot_bytes = 0, off_f32 = 0, off_ring = 0, smem_bytes = 0;
+  uint8_t* d_tab = nullptr;
+};
+struct RowsSynTables {
+  bool ok = false;
+  int W = 0, N1 = 0, in_cols = 0, n_chunks = 0, tmem_cols = 0;
+  uint32_t u_bytes = 0, chunk_bytes = 0, off_a = 0, off_ustage = 0, off_tab = 0, off_stage = 0, smem_bytes = 0;
+  uint8_t* d_tab = nullptr;
+};
+#endif
+
 struct FastTables {
   std::vector<TensorMapCacheEntry> map_cache;
   std::mutex map_mutex;
   FusedAnalysisTables ana[2];   // [0] forward analysis on `grid`, [1] adjoint-of-synthesis analysis on `out_grid`
   FusedSynthesisTables syn[2];  // [0] forward synthesis onto `out_grid`, [1] adjoint-of-analysis synthesis onto `grid`
+#ifdef SC_ROWS_KERNELS
+  RowsAnaTables rows_ana[2];    // same indexing as `ana`
+  RowsSynTables rows_syn[2];    // same indexing as `syn`
+#endif
   int sm_count = 0;
 };
 
@@ -1483,6 +1503,11 @@ static bool build_fused_synthesis(Plan* p, FusedSynthesisTables* t, int H, int W
   return true;
 }
 
+#ifdef SC_ROWS_KERNELS
+static bool build_rows_analysis(Plan* p, RowsAnaTables* t, int W, int out_cols, const std::vector<float>& tab);
+static bool build_rows_synthesis(Plan* p, RowsSynTables* t, int W, int in_cols, const std::vector<float>& tab);
+#endif
+
 bool fast_plan_init(Plan* p) {
   p->fast = nullptr;
   cudaDeviceProp prop{};
@@ -1490,6 +1515,18 @@ bool fast_plan_init(Plan* p) {
   if (prop.major != 10) return true;   // tcgen05 path is sm_100-only
   FastTables* f = new FastTables();
   f->sm_count = prop.multiProcessorCount;
+#ifdef SC_ROWS_KERNELS
+  {
+    const DimTables& Ld = p->dim[p->d - 1];
+    if (!build_rows_analysis(p, &f->rows_ana[0], Ld.N, 2 * Ld.k, p->h_TA) ||
+        !build_rows_analysis(p, &f->rows_ana[1], Ld.M, 2 * Ld.k, p->h_TST) ||
+        !build_rows_synthesis(p, &f->rows_syn[0], Ld.M, 2 * Ld.k, p->h_TS) ||
+        !build_rows_synthesis(p, &f->rows_syn[1], Ld.N, 2 * Ld.k, p->h_TAT)) {
+      delete f;
+      return false;
+    }
+  }
+#endif
   if (p->d < 2) { p->fast = f; return true; }   // only the tensor-core contraction applies to 1-D problems
   const DimTables& L = p->dim[p->d - 1];
   const DimTables& Y = p->dim[p->d - 2];
@@ -1689,5 +1726,497 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   trace_end(P.trace, "synthesis");
   return cuda_ok(cudaGetLastError(), "k_fused_synthesis launch");
 }
+
+#ifdef SC_ROWS_KERNELS
+// =====================================================================================================
+// "rows" kernels: the last-dim transform alone on tensor cores, for ANY number of rows
+//
+//   NOT YET VALIDATED ON HARDWARE -- written at the end of round 1 after the GPU budget was spent; compiled only with
+//   SC_EXTRA_NVCC_FLAGS=-DSC_ROWS_KERNELS and exercised by tests/test_gpu_rows.py (skipped unless the library was built that way).
+//
+//   The fused 2-D kernels above need a whole image inside one 128-row tile (H <= 128, W <= 128/256).  Larger grids (cfg-5:
+//   256^2 .. 1024^2), 1-D problems and 3-D problems with big planes run the generic chain: a real table GEMM over the last dim,
+//   which touches > 90 % of the bytes, then complex table products on the already-truncated leading dims.  These two kernels
+//   replace only that last-dim step; rows are whatever the leading dims multiply out to (a multiple of 128).
+//
+//   rows-analysis   C[r, 0:2k] = sum_w X[r, w] * T[w, 0:2k]           M = 128 rows, N = 2*N1 (T1 | T2), K = W in 64-column slabs
+//     warp 13     TMA producer: x slab [128 x 64] fp32 -> staging ring; table slab [2*N1 x 64] bf16 image (pre-swizzled, L2
+//                 resident, <= 32 KB) -> the operand ring slot, by a 1-D bulk copy
+//     warps 5-12  converters: staging -> bf16 hi/lo -> swizzled operand slab           (same code as the fused kernel)
+//     warp 4      MMA issuer (+ TMEM allocation): D[buf] += x_hi*[T1;T2] + x_lo*T1
+//     warps 0-3   epilogue: D -> (hi + lo sums) -> the row's 2k floats in global memory
+//   rows-synthesis  Y[r, w] = sum_j U[r, j] * T[j, w] (+ bias)          M = 128 rows, N = 64-column chunks, K = N1 <= 128
+//     warp 9      producer: the tile's contiguous [128 x 2k] fp32 block -> staging (one bulk copy); table chunk images
+//                 [T1 | T2] x [64 columns x K] -> two-deep ring
+//     warps 5-8   prep: staging row -> bf16 hi/lo A operand (single buffer)
+//     warp 4      MMA issuer: D[buf] = U_hi*T1 + U_lo*T1 + U_hi*T2 per chunk
+//     warps 0-3   epilogue: D -> + bias -> swizzled [32 x 32] boxes -> TMA tensor stores      (same code as the fused kernel)
+// =====================================================================================================
+constexpr int RA_CONV_WARPS = 8;
+constexpr int RA_CONV_WARP0 = 5;
+constexpr int RA_TMA_WARP = RA_CONV_WARP0 + RA_CONV_WARPS;   // 13
+constexpr int RA_THREADS = (RA_TMA_WARP + 1) * 32;           // 448
+constexpr int RA_CONV_ITERS = 128 / (RA_CONV_WARPS * 2);
+constexpr int RA_MAX_F32 = 3, RA_MAX_RING = 4;
+
+struct RowsAnaParams {
+  float* out;               // [rows x out_cols] fp32
+  const uint8_t* tab_img;   // per 64-column slab of the input: [2*N1 rows x 64] bf16 SW128 image (T1 rows, then T2 rows)
+  int n_tiles, slabs, out_cols, f32_stages, ring_stages, tmem_cols;
+  uint32_t off_f32, off_ring, slot_bytes, tab_bytes;
+};
+
+template <int N1>
+__global__ void __launch_bounds__(RA_THREADS, 1) k_rows_analysis(const RowsAnaParams P, const __grid_constant__ CUtensorMap x_map) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_f32_full[RA_MAX_F32], bar_f32_empty[RA_MAX_F32], bar_full[RA_MAX_RING], bar_tab_full[RA_MAX_RING],
+      bar_empty[RA_MAX_RING], bar_d_full[2], bar_d_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = P.ring_stages, FS = P.f32_stages;
+  pdl_launch_dependents();
+  if (tid == 0) {
+    for (int i = 0; i < FS; ++i) { mbar_init(&bar_f32_full[i], 1); mbar_init(&bar_f32_empty[i], RA_CONV_WARPS); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], RA_CONV_WARPS); mbar_init(&bar_tab_full[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_d_full[i], 1); mbar_init(&bar_d_empty[i], 128); }
+    mbar_init_fence();
+  }
+  if (warp == 4) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tm_d[2] = {tmem, tmem + (uint32_t)(2 * N1)};
+  const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = n_local * P.slabs;
+
+  if (warp == RA_TMA_WARP) {
+    // ------------------------------------------------------------------ producer
+    uint8_t* f32_stage = smem + P.off_f32;
+    pdl_wait();                                  // x is produced by the previous kernel of the stream
+    for (int idx = 0; idx < total; ++idx) {
+      const int sb = idx % FS;
+      const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
+      mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx / FS) & 1) ^ 1));
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bar_f32_full[sb], 32768u);
+        tma_load_2d(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128);
+      }
+      __syncwarp();
+      const int slot = idx % NS;
+      mbar_wait(&bar_empty[slot], (uint32_t)(((idx / NS) & 1) ^ 1));   // the MMAs that read this slot two rounds ago are done
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bar_tab_full[slot], P.tab_bytes);
+        bulk_load_1d(smem + P.off_ring + (size_t)slot * P.slot_bytes + 32768u, P.tab_img + (size_t)slab * P.tab_bytes, P.tab_bytes,
+                     &bar_tab_full[slot]);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= RA_CONV_WARP0) {
+    // ------------------------------------------------------------------ converters (fp32 staging -> bf16 hi/lo operand slabs)
+    const int lt = tid - RA_CONV_WARP0 * 32;
+    constexpr int RP = RA_CONV_WARPS * 2;        // rows covered per pass
+    const int rbase = lt >> 4, c4 = lt & 15;     // 16 float4 per 64-float row segment
+    uint8_t* f32_stage = smem + P.off_f32;
+    const uint32_t my_f32 = (uint32_t)(rbase * 256 + c4 * 16);
+    for (int idx = 0; idx < total; ++idx) {
+      const int slot = idx % NS;
+      const uint32_t ph = (uint32_t)((idx / NS) & 1);
+      const int sb = idx % FS;
+      mbar_wait(&bar_f32_full[sb], (uint32_t)((idx / FS) & 1));
+      uint2 hi[RA_CONV_ITERS], lo[RA_CONV_ITERS];
+      const uint8_t* fsrc = f32_stage + sb * 32768 + my_f32;
+#pragma unroll
+      for (int it = 0; it < RA_CONV_ITERS; ++it) {
+        const float4 v = *reinterpret_cast<const float4*>(fsrc + it * RP * 256);
+        split2_bf16(v.x, v.y, hi[it].x, lo[it].x);
+        split2_bf16(v.z, v.w, hi[it].y, lo[it].y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_f32_empty[sb]);
+      mbar_wait(&bar_empty[slot], ph ^ 1u);
+      uint8_t* shi = smem + P.off_ring + (size_t)slot * P.slot_bytes;
+      uint8_t* slo = shi + FA_SLAB_BYTES;
+#pragma unroll
+      for (int it = 0; it < RA_CONV_ITERS; ++it) {
+        const uint32_t off = sw128_offset(rbase + it * RP, c4 * 4, 128);
+        *reinterpret_cast<uint2*>(shi + off) = hi[it];
+        *reinterpret_cast<uint2*>(slo + off) = lo[it];
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[slot]);
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc_p1 = idesc_bf16(128, 2 * N1), idesc_p2 = idesc_bf16(128, N1);
+    const uint32_t ring_lo = desc_lo(smem_u32(smem + P.off_ring));
+    int g = 0;
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      mbar_wait(&bar_d_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+      tc_fence_after_sync();
+      for (int s = 0; s < P.slabs; ++s, ++g) {
+        const int slot = g % NS;
+        const uint32_t ph = (uint32_t)((g / NS) & 1);
+        mbar_wait(&bar_full[slot], ph);
+        mbar_wait(&bar_tab_full[slot], ph);
+        tc_fence_after_sync();
+        const uint32_t d_hi = ring_lo + (uint32_t)slot * (P.slot_bytes >> 4), d_lo = d_hi + (FA_SLAB_BYTES >> 4);
+        const uint32_t d_b = d_hi + (32768u >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            mma_bf16_ss(tm_d[buf], desc_from_lo(d_hi + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p1, (s | kk) != 0);
+            mma_bf16_ss(tm_d[buf], desc_from_lo(d_lo + 2 * kk), desc_from_lo(d_b + 2 * kk), idesc_p2, true);
+          }
+          mma_commit(&bar_empty[slot]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) mma_commit(&bar_d_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: D -> the row's out_cols floats
+    const int row = warp * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int oc = P.out_cols;
+    pdl_wait();                                  // the output buffer may still be read by the previous kernel
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      float* dst = P.out + ((size_t)tile * 128 + row) * oc;
+      mbar_wait(&bar_d_full[buf], (uint32_t)((i >> 1) & 1));
+      tc_fence_after_sync();
+#pragma unroll
+      for (int c = 0; c < N1; c += 16) {
+        float t1[16], t2[16];
+        tmem_ld16(tm_d[buf] + lane_sel + c, t1);        // x_hi*T1 + x_lo*T1
+        tmem_ld16(tm_d[buf] + lane_sel + N1 + c, t2);   // x_hi*T2
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2)
+          if (c + e < oc) *reinterpret_cast<float2*>(dst + c + e) = make_float2(t1[e] + t2[e], t1[e + 1] + t2[e + 1]);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bar_d_empty[buf]);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
+}
+
+constexpr int RS_PREP_WARP0 = 5, RS_PREP_WARPS = 4, RS_TMA_WARP = RS_PREP_WARP0 + RS_PREP_WARPS;   // 9
+constexpr int RS_THREADS = (RS_TMA_WARP + 1) * 32;                                                  // 320
+
+struct RowsSynParams {
+  const float* u;           // [rows x in_cols] fp32 (re, im interleaved)
+  const float* bias;        // may be null
+  const uint8_t* tab_img;   // per 64-column chunk of the output: T1 image then T2 image, each [64 rows x KS*64] bf16 SW128
+  int n_tiles, in_cols, n_chunks, n_channels, tmem_cols;
+  long long rows_per_image;
+  uint32_t off_a, off_ustage, off_tab, off_stage, u_bytes, chunk_bytes;
+};
+
+template <int N1>
+__global__ void __launch_bounds__(RS_THREADS, 1) k_rows_synthesis(const RowsSynParams P, const __grid_constant__ CUtensorMap out_map) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_u_full, bar_u_empty, bar_a_full, bar_a_empty, bar_tab_full[2], bar_tab_empty[2], bar_d_full[2], bar_d_empty[2];
+  __shared__ uint32_t tmem_base_slot;
+  constexpr int KS = (N1 + 63) / 64;                    // K slabs of the A operand / of a table image
+  constexpr uint32_t A_HALF = (uint32_t)KS * FA_SLAB_BYTES;   // hi slabs, then lo slabs
+  constexpr uint32_t T_IMG = (uint32_t)KS * 8192u;      // one [64 x KS*64] table image
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  if (tid == 0) {
+    mbar_init(&bar_u_full, 1);  mbar_init(&bar_u_empty, RS_PREP_WARPS);
+    mbar_init(&bar_a_full, RS_PREP_WARPS);  mbar_init(&bar_a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_tab_full[i], 1); mbar_init(&bar_tab_empty[i], 1);
+      mbar_init(&bar_d_full[i], 1);   mbar_init(&bar_d_empty[i], 128);
+    }
+    mbar_init_fence();
+  }
+  if (warp == 4) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tm_d[2] = {tmem, tmem + 64u};
+  const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int NCH = P.n_chunks;
+
+  if (warp == RS_TMA_WARP) {
+    // ------------------------------------------------------------------ producer
+    pdl_wait();                                  // U is produced by the previous kernel of the stream
+    int gc = 0;
+    for (int i = 0; i < n_local; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      mbar_wait(&bar_u_empty, (uint32_t)((i & 1) ^ 1));
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bar_u_full, P.u_bytes);
+        bulk_load_1d(smem + P.off_ustage, P.u + (size_t)tile * 128 * P.in_cols, P.u_bytes, &bar_u_full);
+      }
+      __syncwarp();
+      for (int c = 0; c < NCH; ++c, ++gc) {
+        const int slot = gc & 1;
+        mbar_wait(&bar_tab_empty[slot], (uint32_t)(((gc >> 1) & 1) ^ 1));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bar_tab_full[slot], P.chunk_bytes);
+          bulk_load_1d(smem + P.off_tab + (size_t)slot * P.chunk_bytes, P.tab_img + (size_t)c * P.chunk_bytes, P.chunk_bytes,
+                       &bar_tab_full[slot]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= RS_PREP_WARP0) {
+    // ------------------------------------------------------------------ prep: staging row -> bf16 hi/lo A operand
+    const int r = tid - RS_PREP_WARP0 * 32;      // tile row
+    const float* urow = reinterpret_cast<const float*>(smem + P.off_ustage) + (size_t)r * P.in_cols;
+    uint8_t* arow = smem + P.off_a + r * 128;
+    const int ic = P.in_cols;
+    for (int i = 0; i < n_local; ++i) {
+      mbar_wait(&bar_u_full, (uint32_t)(i & 1));
+      mbar_wait(&bar_a_empty, (uint32_t)((i & 1) ^ 1));   // the MMAs of the previous tile have read the operand
+#pragma unroll
+      for (int c0 = 0; c0 < N1 / 8; ++c0) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const int j = 8 * c0 + e;                        // in_cols is even: a pair is inside or outside together
+          const float2 pr = j < ic ? *reinterpret_cast<const float2*>(urow + j) : make_float2(0.f, 0.f);
+          v[e] = pr.x; v[e + 1] = pr.y;
+        }
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) split2_bf16(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+        uint8_t* dst = arow + (c0 >> 3) * FA_SLAB_BYTES + ((((c0 & 7) ^ r) & 7) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(dst + A_HALF) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bar_a_full); mbar_arrive(&bar_u_empty); }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = idesc_bf16(128, 64);
+    const uint32_t a_lo0 = desc_lo(smem_u32(smem + P.off_a)), tab_lo0 = desc_lo(smem_u32(smem + P.off_tab));
+    int gc = 0;
+    for (int i = 0; i < n_local; ++i) {
+      mbar_wait(&bar_a_full, (uint32_t)(i & 1));
+      tc_fence_after_sync();
+      for (int c = 0; c < NCH; ++c, ++gc) {
+        const int slot = gc & 1;
+        const uint32_t ph = (uint32_t)((gc >> 1) & 1);
+        mbar_wait(&bar_tab_full[slot], ph);
+        mbar_wait(&bar_d_empty[slot], ph ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t t1 = tab_lo0 + (uint32_t)slot * (P.chunk_bytes >> 4), t2 = t1 + (T_IMG >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < N1 / 16; ++ks) {
+            const uint32_t a_hi = a_lo0 + (uint32_t)(ks >> 2) * (FA_SLAB_BYTES >> 4) + 2 * (ks & 3), a_lo = a_hi + (A_HALF >> 4);
+            const uint32_t b_off = (uint32_t)(ks >> 2) * (8192u >> 4) + 2 * (ks & 3);
+            mma_bf16_ss(tm_d[slot], desc_from_lo(a_hi), desc_from_lo(t1 + b_off), idesc, ks > 0);
+            mma_bf16_ss(tm_d[slot], desc_from_lo(a_lo), desc_from_lo(t1 + b_off), idesc, true);
+            mma_bf16_ss(tm_d[slot], desc_from_lo(a_hi), desc_from_lo(t2 + b_off), idesc, true);
+          }
+          mma_commit(&bar_tab_empty[slot]);
+          mma_commit(&bar_d_full[slot]);
+          if (c == NCH - 1) mma_commit(&bar_a_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: D -> + bias -> TMA tensor stores
+    const int row = warp * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    uint8_t* my_stage = smem + P.off_stage + warp * 8192;   // two [32 x 128 B] boxes per warp
+    uint32_t box_ctr = 0;
+    int gc = 0;
+    pdl_wait();                                             // the output image may still be read by the previous kernel
+    for (int i = 0; i < n_local; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      float b = 0.f;
+      if (P.bias != nullptr) b = __ldg(P.bias + (int)((((long long)tile * 128 + row) / P.rows_per_image) % P.n_channels));
+      for (int c = 0; c < NCH; ++c, ++gc) {
+        const int buf = gc & 1;
+        mbar_wait(&bar_d_full[buf], (uint32_t)((gc >> 1) & 1));
+        tc_fence_after_sync();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float t[2][16];
+          tmem_ld16(tm_d[buf] + lane_sel + 32 * hf, t[0]);
+          tmem_ld16(tm_d[buf] + lane_sel + 32 * hf + 16, t[1]);
+          uint8_t* box = my_stage + (box_ctr & 1) * 4096;
+          if (lane == 0) bulk_wait_read_1();        // the store issued two boxes ago has finished reading this buffer
+          __syncwarp();
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+              const int ch = (16 * u + e) >> 2;      // 16-byte chunk index within the 128-byte row
+              *reinterpret_cast<float4*>(box + lane * 128 + (((ch ^ lane) & 7) << 4)) =
+                  make_float4(t[u][e] + b, t[u][e + 1] + b, t[u][e + 2] + b, t[u][e + 3] + b);
+            }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&out_map, box, c * 64 + 32 * hf, tile * 128 + warp * 32);
+            bulk_commit();
+          }
+          ++box_ctr;
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&bar_d_empty[buf]);
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+static bool rows_kernels_enabled() {
+  static const bool on = [] { const char* e = getenv("SC_ROWS"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
+
+// `tab` is [W x out_cols] row-major (p->h_TA / p->h_TST)
+static bool build_rows_analysis(Plan* p, RowsAnaTables* t, int W, int out_cols, const std::vector<float>& tab) {
+  t->ok = false;
+  if (W % 64 != 0 || out_cols < 2 || out_cols > 128) return true;
+  const int N1 = ((out_cols + 15) / 16) * 16;
+  t->W = W; t->N1 = N1; t->out_cols = out_cols; t->slabs = W / 64;
+  t->tab_bytes = (uint32_t)(2 * N1 * 128);
+  t->slot_bytes = 32768u + t->tab_bytes;
+  t->tmem_cols = 4 * N1 <= 64 ? 64 : 4 * N1 <= 128 ? 128 : 4 * N1 <= 256 ? 256 : 512;
+  const uint32_t budget = 227u * 1024u - 4096u;
+  t->ring_stages = 2;
+  t->f32_stages = 3;
+  if ((uint32_t)t->f32_stages * 32768u + 2u * t->slot_bytes + 1024u > budget) t->f32_stages = 2;
+  if ((uint32_t)t->f32_stages * 32768u + 2u * t->slot_bytes + 1024u > budget) return true;
+  t->off_f32 = 0;
+  t->off_ring = (uint32_t)t->f32_stages * 32768u;
+  t->smem_bytes = t->off_ring + 2u * t->slot_bytes + 1024u;
+  // every slab is its own [2*N1 x 64] image: host_sw128_offset puts slab s at s * rows * 128 bytes
+  std::vector<uint8_t> img((size_t)t->slabs * t->tab_bytes, 0);
+  for (int j = 0; j < out_cols; ++j)
+    for (int w = 0; w < W; ++w) put_split(img, 2 * N1, j, N1 + j, w, tab[(size_t)w * out_cols + j]);
+  if (!upload_bytes(p, img, &t->d_tab)) return false;
+  t->ok = true;
+  return true;
+}
+
+// `tab` is [in_cols x W] row-major (p->h_TS / p->h_TAT)
+static bool build_rows_synthesis(Plan* p, RowsSynTables* t, int W, int in_cols, const std::vector<float>& tab) {
+  t->ok = false;
+  if (W % 64 != 0 || in_cols < 2 || in_cols > 128) return true;
+  const int N1 = ((in_cols + 15) / 16) * 16;
+  const int KS = (N1 + 63) / 64;
+  t->W = W; t->N1 = N1; t->in_cols = in_cols; t->n_chunks = W / 64;
+  t->tmem_cols = 128;
+  t->u_bytes = (uint32_t)(128 * in_cols * 4);
+  t->chunk_bytes = (uint32_t)(2 * KS * 8192);
+  t->off_a = 0;
+  t->off_ustage = (uint32_t)(2 * KS) * (uint32_t)FA_SLAB_BYTES;
+  t->off_tab = t->off_ustage + ((t->u_bytes + 1023u) & ~1023u);
+  t->off_stage = t->off_tab + 2u * t->chunk_bytes;
+  t->smem_bytes = t->off_stage + 4u * 8192u + 1024u;
+  if (t->smem_bytes > 227u * 1024u - 4096u) return true;
+  std::vector<uint8_t> img((size_t)t->n_chunks * t->chunk_bytes, 0);
+  for (int c = 0; c < t->n_chunks; ++c)
+    for (int n = 0; n < 64; ++n)
+      for (int j = 0; j < in_cols; ++j) {
+        const float v = tab[(size_t)j * W + c * 64 + n];
+        const uint16_t t1 = bf16_bits(v);
+        const uint16_t t2 = bf16_bits(v - bf16_to_float(t1));
+        const size_t base = (size_t)c * t->chunk_bytes + host_sw128_offset(n, j, 64);
+        memcpy(&img[base], &t1, 2);
+        memcpy(&img[base + (size_t)KS * 8192], &t2, 2);
+      }
+  if (!upload_bytes(p, img, &t->d_tab)) return false;
+  t->ok = true;
+  return true;
+}
+
+bool rows_can_analyze(const Plan* p, bool adjoint, int64_t rows) {
+  return rows_kernels_enabled() && p->fast != nullptr && p->fast->rows_ana[adjoint ? 1 : 0].ok && rows > 0 && rows % 128 == 0;
+}
+bool rows_can_synthesize(const Plan* p, bool adjoint, int64_t rows) {
+  return rows_kernels_enabled() && p->fast != nullptr && p->fast->rows_syn[adjoint ? 1 : 0].ok && rows > 0 && rows % 128 == 0;
+}
+
+bool rows_analyze(const Plan* p, const float* x, int64_t rows, float* out, bool adjoint, cudaStream_t st) {
+  const RowsAnaTables& t = p->fast->rows_ana[adjoint ? 1 : 0];
+  RowsAnaParams P{};
+  P.out = out; P.tab_img = t.d_tab;
+  P.n_tiles = (int)(rows / 128); P.slabs = t.slabs; P.out_cols = t.out_cols;
+  P.f32_stages = t.f32_stages; P.ring_stages = t.ring_stages; P.tmem_cols = t.tmem_cols;
+  P.off_f32 = t.off_f32; P.off_ring = t.off_ring; P.slot_bytes = t.slot_bytes; P.tab_bytes = t.tab_bytes;
+  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  CUtensorMap x_map;
+  if (!cached_map(p, 0, x, (uint64_t)rows, (uint64_t)t.W, &x_map)) return false;
+  switch (t.N1) {
+#define SC_RA_CASE(N)                                                                                            \
+  case N: {                                                                                                      \
+    static SmemOptIn opt_in;                                                                                     \
+    if (!ensure_dynamic_smem((const void*)k_rows_analysis<N>, opt_in, p->device, t.smem_bytes,                   \
+                             "cudaFuncSetAttribute(k_rows_analysis)")) return false;                            \
+    { void* args[] = {(void*)&P, (void*)&x_map};                                                               \
+      if (!cuda_ok(launch_pdl((const void*)k_rows_analysis<N>, dim3(grid), dim3(RA_THREADS), t.smem_bytes, st, args), \
+                   "k_rows_analysis launch")) return false; }                                               \
+  } break;
+    SC_RA_CASE(16) SC_RA_CASE(32) SC_RA_CASE(48) SC_RA_CASE(64) SC_RA_CASE(80) SC_RA_CASE(96) SC_RA_CASE(112) SC_RA_CASE(128)
+#undef SC_RA_CASE
+    default: set_error("rows_analyze: unsupported N1"); return false;
+  }
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_rows_analysis launch");
+}
+
+bool rows_synthesize(const Plan* p, const float* u, int64_t rows, float* out, const float* bias, int64_t rows_per_image,
+                     int n_channels, bool adjoint, cudaStream_t st) {
+  const RowsSynTables& t = p->fast->rows_syn[adjoint ? 1 : 0];
+  RowsSynParams P{};
+  P.u = u; P.bias = bias; P.tab_img = t.d_tab;
+  P.n_tiles = (int)(rows / 128); P.in_cols = t.in_cols; P.n_chunks = t.n_chunks;
+  P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
+  P.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
+  P.off_a = t.off_a; P.off_ustage = t.off_ustage; P.off_tab = t.off_tab; P.off_stage = t.off_stage;
+  P.u_bytes = t.u_bytes; P.chunk_bytes = t.chunk_bytes;
+  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  CUtensorMap out_map;
+  if (!cached_map(p, 1, out, (uint64_t)rows, (uint64_t)t.W, &out_map)) return false;
+  switch (t.N1) {
+#define SC_RS_CASE(N)                                                                                            \
+  case N: {                                                                                                      \
+    static SmemOptIn opt_in;                                                                                     \
+    if (!ensure_dynamic_smem((const void*)k_rows_synthesis<N>, opt_in, p->device, t.smem_bytes,                  \
+                             "cudaFuncSetAttribute(k_rows_synthesis)")) return false;                           \
+    { void* args[] = {(void*)&P, (void*)&out_map};                                                             \
+      if (!cuda_ok(launch_pdl((const void*)k_rows_synthesis<N>, dim3(grid), dim3(RS_THREADS), t.smem_bytes, st, args), \
+                   "k_rows_synthesis launch")) return false; }                                              \
+  } break;
+    SC_RS_CASE(16) SC_RS_CASE(32) SC_RS_CASE(48) SC_RS_CASE(64) SC_RS_CASE(80) SC_RS_CASE(96) SC_RS_CASE(112) SC_RS_CASE(128)
+#undef SC_RS_CASE
+    default: set_error("rows_synthesize: unsupported N1"); return false;
+  }
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_rows_synthesis launch");
+}
+#endif   // SC_ROWS_KERNELS
 
 }  // namespace sc
