@@ -1341,6 +1341,20 @@ static int fast_sm_count(const Plan* p) { return p->fast->sm_count; }
 
 static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t W);
 static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint64_t W);
+typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+static bool thread_has_context() {
+  static const CtxGetCurrentFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<CtxGetCurrentFn>(ptr);
+    return static_cast<CtxGetCurrentFn>(nullptr);
+  }();
+  if (fn == nullptr) return true;   // cannot tell: leave the runtime alone
+  CUcontext ctx = nullptr;
+  return fn(&ctx) != CUDA_SUCCESS || ctx != nullptr;
+}
+
 // kind 0: x slab loads, kind 1: image row-tile stores
 static bool cached_map(const Plan* p, int kind, const void* base, uint64_t rows, uint64_t W, CUtensorMap* out) {
   FastTables* f = p->fast;
@@ -1349,8 +1363,10 @@ static bool cached_map(const Plan* p, int kind, const void* base, uint64_t rows,
     if (e.base == base && e.rows == rows && e.W == W && e.kind == kind) { *out = e.map; return true; }
   // cuTensorMapEncodeTiled is a driver entry point: it needs the primary context bound to THIS thread.  PyTorch's autograd
   // worker threads only get one lazily (first runtime call that needs it), and a backward whose allocations are all served
-  // from the caching allocator reaches this point before any such call -- cudaFree(0) binds it (cache misses only).
-  cudaFree(nullptr);
+  // from the caching allocator reaches this point before any such call -- cudaFree(0) binds it.  Only when the thread really
+  // has no context: cudaFree is not allowed while a stream capture is in progress (graph capture reaches this point with
+  // buffers from the graph's private pool, i.e. cache misses), and a capturing thread always has its context.
+  if (!thread_has_context()) cudaFree(nullptr);
   TensorMapCacheEntry e{base, rows, W, kind, {}};
   const bool ok = kind == 0 ? make_slab_load_map(&e.map, static_cast<const float*>(base), rows, W)
                             : make_row_tile_map(&e.map, static_cast<float*>(const_cast<void*>(base)), rows, W);
