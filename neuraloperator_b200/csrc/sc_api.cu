@@ -224,11 +224,9 @@ static bool analyze_generic(const Plan* p, const float* images, int64_t n_images
   const int64_t rows = n_images * lead;
   float2* cur = (d == 1) ? modes_out : b0;
   float2* nxt = b1;
-#ifdef SC_ROWS_KERNELS
   if (p->fast_enabled && rows_can_analyze(p, adjoint, rows)) {
     if (!rows_analyze(p, images, rows, reinterpret_cast<float*>(cur), adjoint, st)) return false;
   } else
-#endif
   if (!launch_real_table_gemm(images, adjoint ? p->d_TST : p->d_TA, adjoint ? p->ldTST : p->ldTA,
                               reinterpret_cast<float*>(cur), nullptr, rows, adjoint ? L.M : L.N, 2 * L.k, 1, 1, st))
     return false;
@@ -265,11 +263,9 @@ static bool synthesize_generic(const Plan* p, const float2* modes_in, int64_t n_
     cur = dst; which ^= 1;
   }
   const int64_t rows = n_images * lead;
-#ifdef SC_ROWS_KERNELS
   if (p->fast_enabled && rows_can_synthesize(p, adjoint, rows))
     return rows_synthesize(p, reinterpret_cast<const float*>(cur), rows, images_out, bias, lead, n_channels > 0 ? n_channels : 1,
                            adjoint, st);
-#endif
   return launch_real_table_gemm(reinterpret_cast<const float*>(cur), adjoint ? p->d_TAT : p->d_TS,
                                 adjoint ? p->ldTAT : p->ldTS, images_out, bias, rows, 2 * L.k, adjoint ? L.N : L.M,
                                 lead, n_channels > 0 ? n_channels : 1, st);
@@ -482,11 +478,9 @@ int sc_plan_uses_fast_path(const sc_plan* plan) {
   if (p == nullptr || !p->fast_enabled) return 0;
   int mask = (fast_can_analyze(p, false) ? 1 : 0) | (fast_can_synthesize(p, false) ? 2 : 0) |
              (fast_can_analyze(p, true) ? 4 : 0) | (fast_can_synthesize(p, true) ? 8 : 0);
-#ifdef SC_ROWS_KERNELS
   // bits 4-7: the last-dim ("rows") tensor-core kernels are available for the generic chain (row count permitting)
   mask |= (rows_can_analyze(p, false, 128) ? 16 : 0) | (rows_can_synthesize(p, false, 128) ? 32 : 0) |
           (rows_can_analyze(p, true, 128) ? 64 : 0) | (rows_can_synthesize(p, true, 128) ? 128 : 0);
-#endif
   return mask;
 }
 
@@ -662,9 +656,7 @@ const char* sc_last_error(void) { return t_error.c_str(); }
 uint64_t sc_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* sc_build_info(void) {
   return "libspectral_conv_b200 sm_100a nvcc " SC_STR(__CUDACC_VER_MAJOR__) "." SC_STR(__CUDACC_VER_MINOR__)
-#ifdef SC_ROWS_KERNELS
-         " +rows-kernels(unvalidated)"
-#endif
+         " +rows-kernels"
       ;
 }
 

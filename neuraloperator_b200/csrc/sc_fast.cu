@@ -190,9 +190,7 @@ struct AnaParams {
   const uint8_t* a2_img;   // [128 x 256] bf16, plain row-major: real-embedded leading-dim table (T1 rows 0-63, T2 rows 64-127);
                            // copied once into TENSOR MEMORY and used as the TMEM A operand of every stage-2 MMA
   int n_tiles, W, slabs, N1, KX, QROWS, n_stages, tmem_cols;
-#ifdef SC_L2_STREAM_HINT_BUILD
   int l2_stream_hint;      // 1: the x slabs are loaded with an L2 evict-first policy (read once)
-#endif
   uint32_t off_f32, off_ring, off_b1, off_a2, off_b2, off_scratch, stage_off;   // stage_off: output staging, relative to off_scratch
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
@@ -264,9 +262,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // ------------------------------------------------------------------ TMA producer: one tensor load per 32 KB slab
     const int total = n_local * P.slabs;
     uint8_t* f32_stage = smem + P.off_f32;
-#ifdef SC_L2_STREAM_HINT_BUILD
     const uint64_t pol = l2_policy_evict_first();
-#endif
     pdl_wait();                                  // x is produced by the previous kernel of the stream
     for (int idx = 0; idx < total; ++idx) {
       const int sb = idx % FA_F32_STAGES;
@@ -274,10 +270,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
       if (elect_one()) {
         const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
         mbar_arrive_expect_tx(&bar_f32_full[sb], 32768u);
-#ifdef SC_L2_STREAM_HINT_BUILD
         if (P.l2_stream_hint) tma_load_2d_hint(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128, pol);
         else
-#endif
           tma_load_2d(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128);
       }
       __syncwarp();
@@ -510,9 +504,7 @@ struct SynParams {
   const uint8_t* aa_img;   // [128 x 128] bf16 image: leading-dim table, columns (2q+s | 64+2q+s)
   const uint8_t* bb_img;   // two [W x 64] bf16 images: T1 then T2 of the last-dim table (rows = w, K = j)
   int n_tiles, W, KX, QROWS, H, n_channels, tmem_cols;
-#ifdef SC_L2_STREAM_HINT_BUILD
   int l2_stream_hint;      // 1: the image rows are stored with an L2 evict-first policy (written once, not re-read by this step)
-#endif
   int slices_per_image;    // 3-D: the fused kernel sees (image, z) slices; bias channel = (slice / slices_per_image) % n_channels
   uint32_t off_aa, off_ba, off_u, off_bb, off_stage;
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
@@ -726,9 +718,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
     uint8_t* my_stage = smem + P.off_stage + warp * 8192;   // two [32 x 128 B] boxes per warp
     uint32_t chunk_ctr = 0;
-#ifdef SC_L2_STREAM_HINT_BUILD
     const uint64_t pol = l2_policy_evict_first();
-#endif
     pdl_wait();                                             // the output image may still be read by the previous kernel
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
@@ -766,10 +756,8 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-#ifdef SC_L2_STREAM_HINT_BUILD
           if (P.l2_stream_hint) tma_store_2d_hint(&out_map, box, c, tile * 128 + warp * 32, pol);
           else
-#endif
             tma_store_2d(&out_map, box, c, tile * 128 + warp * 32);
           bulk_commit();
         }
@@ -1309,7 +1297,6 @@ struct FusedSynthesisTables {
 // allocator) to the same plan step after step, so encoded maps are kept in a small per-plan cache.
 struct TensorMapCacheEntry { const void* base; uint64_t rows, W; int kind; CUtensorMap map; };
 
-#ifdef SC_ROWS_KERNELS
 // last-dim ("rows") tensor-core kernels for grids the fused 2-D kernels do not cover -- see the section at the end of the file
 struct RowsAnaTables {
   bool ok = false;
@@ -1323,17 +1310,14 @@ struct RowsSynTables {
   uint32_t u_bytes = 0, chunk_bytes = 0, off_a = 0, off_ustage = 0, off_tab = 0, off_stage = 0, smem_bytes = 0;
   uint8_t* d_tab = nullptr;
 };
-#endif
 
 struct FastTables {
   std::vector<TensorMapCacheEntry> map_cache;
   std::mutex map_mutex;
   FusedAnalysisTables ana[2];   // [0] forward analysis on `grid`, [1] adjoint-of-synthesis analysis on `out_grid`
   FusedSynthesisTables syn[2];  // [0] forward synthesis onto `out_grid`, [1] adjoint-of-analysis synthesis onto `grid`
-#ifdef SC_ROWS_KERNELS
   RowsAnaTables rows_ana[2];    // same indexing as `ana`
   RowsSynTables rows_syn[2];    // same indexing as `syn`
-#endif
   int sm_count = 0;
 };
 
@@ -1519,10 +1503,8 @@ static bool build_fused_synthesis(Plan* p, FusedSynthesisTables* t, int H, int W
   return true;
 }
 
-#ifdef SC_ROWS_KERNELS
 static bool build_rows_analysis(Plan* p, RowsAnaTables* t, int W, int out_cols, const std::vector<float>& tab);
 static bool build_rows_synthesis(Plan* p, RowsSynTables* t, int W, int in_cols, const std::vector<float>& tab);
-#endif
 
 bool fast_plan_init(Plan* p) {
   p->fast = nullptr;
@@ -1531,7 +1513,6 @@ bool fast_plan_init(Plan* p) {
   if (prop.major != 10) return true;   // tcgen05 path is sm_100-only
   FastTables* f = new FastTables();
   f->sm_count = prop.multiProcessorCount;
-#ifdef SC_ROWS_KERNELS
   {
     const DimTables& Ld = p->dim[p->d - 1];
     if (!build_rows_analysis(p, &f->rows_ana[0], Ld.N, 2 * Ld.k, p->h_TA) ||
@@ -1542,7 +1523,6 @@ bool fast_plan_init(Plan* p) {
       return false;
     }
   }
-#endif
   if (p->d < 2) { p->fast = f; return true; }   // only the tensor-core contraction applies to 1-D problems
   const DimTables& L = p->dim[p->d - 1];
   const DimTables& Y = p->dim[p->d - 2];
@@ -1635,11 +1615,10 @@ static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t sm
   return cudaLaunchKernelExC(&cfg, func, args);
 }
 
-// Experiment prepared for the next round, NOT yet measured or validated on hardware, therefore compiled out by default
-// (build with SC_EXTRA_NVCC_FLAGS=-DSC_L2_STREAM_HINT_BUILD): L2 evict-first policy on the image streams so that the weights
-// and mode tensors a step re-reads stay L2-resident.  SC_L2_STREAM_HINT=0|1 then switches it at run time for A/B runs.
-#ifdef SC_L2_STREAM_HINT_BUILD
-constexpr int SC_L2_STREAM_HINT_DEFAULT = 0;
+// L2 evict-first policy on the image streams (x / gy loads, y / dx stores) so that the weights and mode tensors a step re-reads
+// stay L2-resident.  Measured on B200 (round 2, cfg-2 graph step, two A/B pairs): 167.5k -> 169.4k samples/s.
+// SC_L2_STREAM_HINT=0 switches it off at run time for A/B runs.
+constexpr int SC_L2_STREAM_HINT_DEFAULT = 1;
 static int l2_stream_hint_enabled() {
   static const int v = [] {
     const char* e = getenv("SC_L2_STREAM_HINT");
@@ -1647,7 +1626,6 @@ static int l2_stream_hint_enabled() {
   }();
   return v;
 }
-#endif
 
 // SC_TRACE_FILE=<path>: record the per-role timeline of CTA 0 of every fused transform launch (debug only; synchronises)
 static long long* trace_begin() {
@@ -1679,9 +1657,7 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   P.x = images; P.out = modes_out; P.b1_img = t.d_b1; P.a2_img = t.d_a2;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.slabs = t.slabs; P.N1 = t.N1; P.KX = t.KX; P.QROWS = t.G * t.KY;
   P.n_stages = t.n_stages; P.tmem_cols = t.tmem_cols;
-#ifdef SC_L2_STREAM_HINT_BUILD
   P.l2_stream_hint = l2_stream_hint_enabled();
-#endif
   P.off_f32 = t.off_f32; P.off_ring = t.off_ring;
   P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch; P.stage_off = t.stage_off;
   P.trace = trace_begin();
@@ -1716,9 +1692,7 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.KX = t.KX; P.QROWS = t.G * t.KY; P.H = t.H;
   P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
   P.slices_per_image = slices_per_image > 0 ? slices_per_image : 1;
-#ifdef SC_L2_STREAM_HINT_BUILD
   P.l2_stream_hint = l2_stream_hint_enabled();
-#endif
   P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb; P.off_stage = t.off_stage;
   P.trace = trace_begin();
   const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
@@ -1743,12 +1717,10 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   return cuda_ok(cudaGetLastError(), "k_fused_synthesis launch");
 }
 
-#ifdef SC_ROWS_KERNELS
 // =====================================================================================================
 // "rows" kernels: the last-dim transform alone on tensor cores, for ANY number of rows
 //
-//   NOT YET VALIDATED ON HARDWARE -- written at the end of round 1 after the GPU budget was spent; compiled only with
-//   SC_EXTRA_NVCC_FLAGS=-DSC_ROWS_KERNELS and exercised by tests/test_gpu_rows.py (skipped unless the library was built that way).
+//   Validated on B200 in round 2 (tests/test_gpu_rows.py); SC_ROWS=0 switches them off at run time for A/B runs.
 //
 //   The fused 2-D kernels above need a whole image inside one 128-row tile (H <= 128, W <= 128/256).  Larger grids (cfg-5:
 //   256^2 .. 1024^2), 1-D problems and 3-D problems with big planes run the generic chain: a real table GEMM over the last dim,
@@ -2233,6 +2205,5 @@ bool rows_synthesize(const Plan* p, const float* u, int64_t rows, float* out, co
   count_launch();
   return cuda_ok(cudaGetLastError(), "k_rows_synthesis launch");
 }
-#endif   // SC_ROWS_KERNELS
 
 }  // namespace sc

@@ -23,14 +23,12 @@ bool fast_can_contract(const Plan* p, int B, int Ci, int Co);
 bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long long sAK, const int* offA, bool conjA,
                          const float2* b, long long sBN, long long sBK, const int* offB, float2* out, long long sOR,
                          long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st);
-#ifdef SC_ROWS_KERNELS
 // last-dim transform alone on tensor cores for any number of rows (multiple of 128); see the end of sc_fast.cu
 bool rows_can_analyze(const Plan* p, bool adjoint, int64_t rows);
 bool rows_can_synthesize(const Plan* p, bool adjoint, int64_t rows);
 bool rows_analyze(const Plan* p, const float* x, int64_t rows, float* out, bool adjoint, cudaStream_t st);
 bool rows_synthesize(const Plan* p, const float* u, int64_t rows, float* out, const float* bias, int64_t rows_per_image,
                      int n_channels, bool adjoint, cudaStream_t st);
-#endif
 bool umma_selftest_ts(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
 bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaStream_t st);
 

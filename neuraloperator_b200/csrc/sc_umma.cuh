@@ -169,14 +169,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-#ifdef SC_ROWS_KERNELS
 // 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16); completion (bytes) on an mbarrier like the tensor loads
 __device__ __forceinline__ void bulk_load_1d(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-#endif
 
 // 2-D tiled TMA load global -> shared; completion (bytes) is signalled on an mbarrier armed with arrive.expect_tx
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {

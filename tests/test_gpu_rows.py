@@ -1,8 +1,4 @@
-"""Last-dim ("rows") tensor-core kernels for grids the fused 2-D kernels do not cover (cfg-5 sizes, 1-D, big 3-D planes).
-
-EXPERIMENTAL: the kernels were written after the round-1 GPU budget was spent and have not run on hardware yet.  They are
-compiled only with `SC_EXTRA_NVCC_FLAGS=-DSC_ROWS_KERNELS python -m neuraloperator_b200.build --force`; with the default
-library every test here is skipped."""
+"""Last-dim ("rows") tensor-core kernels for grids the fused 2-D kernels do not cover (cfg-5 sizes, 1-D, big 3-D planes)."""
 import pytest
 import torch
 
@@ -12,15 +8,6 @@ from neuraloperator_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 
-def _built_with_rows():
-    try:
-        return b"+rows-kernels" in _lib.load().sc_build_info()
-    except Exception:   # noqa: BLE001
-        return False
-
-
-needs_rows = pytest.mark.skipif(not _built_with_rows(), reason="library built without -DSC_ROWS_KERNELS")
-
 REL_TOL = 1e-4
 
 
@@ -29,7 +16,6 @@ def rel_err(a, ref):
     return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item()
 
 
-@needs_rows
 @pytest.mark.parametrize("grid,modes,n0,n1", [
     ((256, 256), (64, 64), 1, 2),        # cfg-5a shape: 2k = 66 -> N1 = 80, two K slabs in the synthesis
     ((1024,), (16,), 16, 32),            # cfg-1: 1-D, 16 slabs
@@ -64,7 +50,6 @@ def test_rows_kernels_match_the_generic_chain(cuda_device, grid, modes, n0, n1, 
     assert rel_err(yf, ys) < REL_TOL
 
 
-@needs_rows
 def test_cfg5a_forward_backward_against_the_oracle(cuda_device):
     from oracle import spectral_conv_oracle as O
     B, C, grid, modes = 1, 4, (256, 256), (64, 64)
