@@ -312,12 +312,18 @@ static bool synthesize(const Plan* p, const float2* modes_in, int64_t n_images, 
   return synthesize_generic(p, modes_in, n_images, n_channels, bias, images_out, adjoint, b0, b1, st);
 }
 
+// `chained`: the call is part of sc_forward_dense / sc_backward_dense, i.e. the kernel launched just before on the stream is
+// this library's transform kernel, which does not write the weights / saved modes: the contraction may fetch those operands
+// ahead of its grid-dependency wait.  Standalone calls (chained = false) make no assumption about their predecessor.
 static bool contract_fwd(const Plan* p, const float2* xm, const float2* w, float2* ym, int B, int Ci, int Co,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool chained) {
   const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
-  if (p->fast_enabled && fast_can_contract(p, B, Ci, Co))   // ym^T[o, b] = sum_i w[i, o] * xm[b, i]
+  if (p->fast_enabled && fast_can_contract(p, B, Ci, Co, mode_gemm_quad_eligible(p, Mt, w, xm, ym))) {   // ym^T[o, b] = sum_i w[i, o] * xm[b, i]
+    ModeGemmExtras ex;
+    ex.a_early = chained;
     return launch_mode_gemm_tc(p, w, Wp, (long long)Co * Wp, p->d_woff, false, xm, (long long)Ci * Mt, Mt, nullptr, ym, Mt,
-                               (long long)Co * Mt, nullptr, Co, B, Ci, Mt, st);
+                               (long long)Co * Mt, nullptr, Co, B, Ci, Mt, st, &ex);
+  }
   ModeGemmOperand a{xm, (int64_t)Ci * Mt, Mt, nullptr};
   ModeGemmOperand b{w, (int64_t)Co * Wp, Wp, p->d_woff};
   ModeGemmOperand o{ym, (int64_t)Co * Mt, Mt, nullptr};
@@ -325,24 +331,39 @@ static bool contract_fwd(const Plan* p, const float2* xm, const float2* w, float
 }
 
 static bool contract_bwd(const Plan* p, const float2* xm, const float2* gm, const float2* w, float2* dxm,
-                         float2* dw, float* dbias, int B, int Ci, int Co, cudaStream_t st) {
+                         float2* dw, float* dbias, int B, int Ci, int Co, cudaStream_t st, bool chained) {
   const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
-  const bool tc = p->fast_enabled && fast_can_contract(p, B, Ci, Co);
+  const bool quad_ok = (dw == nullptr || mode_gemm_quad_eligible(p, Mt, xm, gm, dw)) &&
+                       (dxm == nullptr || mode_gemm_quad_eligible(p, Mt, w, gm, dxm));
+  const bool tc = p->fast_enabled && fast_can_contract(p, B, Ci, Co, quad_ok);
   if (dw != nullptr && !p->weight_block_is_whole &&
       !cuda_ok(cudaMemsetAsync(dw, 0, (size_t)Ci * Co * Wp * sizeof(float2), st), "cudaMemsetAsync(dweight)"))
     return false;
   if (tc) {
-    // dweight[i, o] = sum_b conj(xm[b, i]) * gm[b, o]
-    if (dw != nullptr &&
-        !launch_mode_gemm_tc(p, xm, Mt, (long long)Ci * Mt, nullptr, true, gm, Mt, (long long)Co * Mt, nullptr, dw,
-                             (long long)Co * Wp, Wp, p->d_woff, Ci, Co, B, Mt, st))
-      return false;
-    if (dbias != nullptr && !launch_bias_grad(gm, dbias, B, Co, Mt, p->dc_slot, (float)(1.0 / p->s_inv), st)) return false;
+    bool bias_done = false, have_dw_launch = false;
+    // dweight[i, o] = sum_b conj(xm[b, i]) * gm[b, o]   (+ dbias from the DC slot of gm, fused into the same launch)
+    if (dw != nullptr) {
+      ModeGemmExtras ex;
+      ex.a_early = chained;                          // the saved modes come from the forward pass
+      if (dbias != nullptr) { ex.bias_gm = gm; ex.dbias = dbias; ex.bias_B = B; ex.bias_Co = Co; ex.bias_scale = (float)(1.0 / p->s_inv); }
+      if (!launch_mode_gemm_tc(p, xm, Mt, (long long)Ci * Mt, nullptr, true, gm, Mt, (long long)Co * Mt, nullptr, dw,
+                               (long long)Co * Wp, Wp, p->d_woff, Ci, Co, B, Mt, st, &ex))
+        return false;
+      bias_done = ex.bias_done;
+      have_dw_launch = true;
+    }
+    if (dbias != nullptr && !bias_done && !launch_bias_grad(gm, dbias, B, Co, Mt, p->dc_slot, (float)(1.0 / p->s_inv), st)) return false;
     // dxm^T[i, b] = sum_o conj(w[i, o]) * gm[b, o]
-    if (dxm != nullptr &&
-        !launch_mode_gemm_tc(p, w, (long long)Co * Wp, Wp, p->d_woff, true, gm, (long long)Co * Mt, Mt, nullptr, dxm, Mt,
-                             (long long)Ci * Mt, nullptr, Ci, B, Co, Mt, st))
-      return false;
+    if (dxm != nullptr) {
+      ModeGemmExtras ex;
+      // the kernel just before this one is the dweight / bias-gradient launch above (when there was one), which writes
+      // neither the weights nor gm
+      ex.a_early = chained || have_dw_launch;
+      ex.b_early = have_dw_launch;
+      if (!launch_mode_gemm_tc(p, w, (long long)Co * Wp, Wp, p->d_woff, true, gm, (long long)Co * Mt, Mt, nullptr, dxm, Mt,
+                               (long long)Ci * Mt, nullptr, Ci, B, Co, Mt, st, &ex))
+        return false;
+    }
     return true;
   }
   if (dw != nullptr) {
@@ -514,7 +535,7 @@ int sc_contract_dense(const sc_plan* plan, const sc_complex* xm, const sc_comple
   const Plan* p = reinterpret_cast<const Plan*>(plan);
   SC_REQUIRE(p != nullptr && xm != nullptr && weight != nullptr && ym != nullptr, "sc_contract_dense: null argument");
   SC_TRY(contract_fwd(p, reinterpret_cast<const float2*>(xm), reinterpret_cast<const float2*>(weight),
-                      reinterpret_cast<float2*>(ym), batch, in_channels, out_channels, static_cast<cudaStream_t>(stream)));
+                      reinterpret_cast<float2*>(ym), batch, in_channels, out_channels, static_cast<cudaStream_t>(stream), false));
   return 0;
 }
 
@@ -528,7 +549,7 @@ int sc_contract_dense_backward(const sc_plan* plan, const sc_complex* xm, const 
   SC_TRY(contract_bwd(p, reinterpret_cast<const float2*>(xm), reinterpret_cast<const float2*>(gm),
                       reinterpret_cast<const float2*>(weight), reinterpret_cast<float2*>(dxm),
                       reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels,
-                      static_cast<cudaStream_t>(stream)));
+                      static_cast<cudaStream_t>(stream), false));
   return 0;
 }
 
@@ -554,7 +575,7 @@ int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weig
   float2* xm = reinterpret_cast<float2*>(xm_saved);
   float2* ym = w.modes[0];
   SC_TRY(analyze(p, x, (int64_t)batch * in_channels, xm, false, w.buf[0], w.buf[1], st));
-  SC_TRY(contract_fwd(p, xm, reinterpret_cast<const float2*>(weight), ym, batch, in_channels, out_channels, st));
+  SC_TRY(contract_fwd(p, xm, reinterpret_cast<const float2*>(weight), ym, batch, in_channels, out_channels, st, true));
   SC_TRY(synthesize(p, ym, (int64_t)batch * out_channels, out_channels, bias, y, false, w.buf[0], w.buf[1], st));
   return 0;
 }
@@ -573,7 +594,7 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
   float2* dxm = dx != nullptr ? w.modes[1] : nullptr;
   SC_TRY(analyze(p, gy, (int64_t)batch * out_channels, gm, true, w.buf[0], w.buf[1], st));
   SC_TRY(contract_bwd(p, reinterpret_cast<const float2*>(xm_saved), gm, reinterpret_cast<const float2*>(weight), dxm,
-                      reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels, st));
+                      reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels, st, true));
   if (dx != nullptr)
     SC_TRY(synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
   return 0;

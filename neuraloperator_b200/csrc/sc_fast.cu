@@ -206,7 +206,6 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = P.n_stages;
-  pdl_launch_dependents();   // the next kernel may take over each SM as soon as this CTA leaves it
   uint8_t* s_b1 = smem + P.off_b1;
   uint8_t* s_b2 = smem + P.off_b2;
   float* s_scr = reinterpret_cast<float*>(smem + P.off_scratch);
@@ -264,6 +263,10 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     uint8_t* f32_stage = smem + P.off_f32;
     const uint64_t pol = l2_policy_evict_first();
     pdl_wait();                                  // x is produced by the previous kernel of the stream
+    // Hand-over to the next kernel of the stream only AFTER this CTA has seen its own predecessor complete: a kernel of this
+    // library may then read, ahead of its own wait, anything its immediate predecessor does not write (the contraction
+    // fetches the weights that way).  The dependents still start as soon as this CTA leaves its SM.
+    pdl_launch_dependents();
     for (int idx = 0; idx < total; ++idx) {
       const int sb = idx % FA_F32_STAGES;
       mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx / FA_F32_STAGES) & 1) ^ 1));
@@ -528,7 +531,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W = P.W, KX = P.KX;
-  pdl_launch_dependents();
   uint8_t* s_aa = smem + P.off_aa;
   uint8_t* s_ba = smem + P.off_ba;
   uint8_t* s_u = smem + P.off_u;
@@ -572,6 +574,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
     constexpr uint32_t T2 = 2 * N1 * 128;    // second K-slab (columns 64 + k): hi * T2
     constexpr uint32_t LO = N1 * 128;        // rows N1 + n: lo * T1
     pdl_wait();                              // the modes are produced by the previous kernel of the stream
+    pdl_launch_dependents();                 // (after the wait: see k_fused_analysis)
     for (int i = 0; i < n_local; ++i) {
       const int buf = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
@@ -1011,6 +1014,7 @@ __device__ __forceinline__ void mgq_load_operand(const ModeGemmQuadParams& P, ui
   const uint32_t sstep = (uint32_t)step * (IS_B ? 128u : 256u);
   const float2* base = (IS_B ? P.b : P.a) + m0 + (long long)r0 * s_row;
   pdl_wait();                                          // operands come from buffers of the previous kernel
+  pdl_launch_dependents();                             // (after the wait: see k_fused_analysis)
   if (!IS_B && lt < 32) SC_QTRACE(P, 0, 0, 2);
   for (int rd = 0; rd < P.rounds; ++rd) {
     const int k = rd * 32 + kq;
@@ -1079,7 +1083,6 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   __shared__ uint32_t tmem_base_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rowsB = 2 * P.NBp;
-  pdl_launch_dependents();
   if (tid == 128) SC_QTRACE(P, 0, 0, 0);
 
   if (tid == 0) {
@@ -1176,6 +1179,283 @@ __global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGem
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// =====================================================================================================
+// mode-wise complex GEMM, four consecutive modes per CTA, second generation ("quad2")
+//
+//   Same sector-exact global traffic as the quad kernel above (one 256-bit load / store per 4 modes of an element), but
+//   no K-rounds through a full shared memory:
+//     * the A operand (2x2-embedded, bf16 hi / lo) lives in TENSOR MEMORY: the loader thread that owns real row r converts
+//       its row's values in registers and writes them with tcgen05.st into a 4-slot ring of 8-k chunks (one MMA K-step);
+//     * the B operand (as stored, bf16 hi rows / lo rows) is the only shared-memory operand: K-slabs of 32 complex k,
+//       3-slot ring (never recycled for K <= 96);
+//     * ONE accumulator per mode: D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi as three N = NBp MMAs per K-step (the quad
+//       kernel keeps the hi / lo products in separate columns: twice the tensor memory);
+//     * loads are software-pipelined two batches deep per thread with L2 prefetches ahead of them, and operands that the
+//       previous kernel of the stream does not write (weights, saved modes) are fetched BEFORE the grid-dependency wait.
+//   Any MR / NB / KC: 64-row and 64-column tiles over gridDim.y, K streamed through the rings.
+//   warp 0 MMA issue (+TMEM), warp 1 dependency hand-over (+ fused bias gradient), warps 4-11 A loaders, 12-19 B loaders,
+//   all 20 warps epilogue.
+// =====================================================================================================
+constexpr int MQ2_A_WARPS = 8, MQ2_B_WARPS = 8;
+constexpr int MQ2_THREADS = (4 + MQ2_A_WARPS + MQ2_B_WARPS) * 32;   // 640
+constexpr int MQ2_A_SLOTS = 4;                  // TMEM ring: per slot 4 modes x (8 hi + 8 lo) columns
+constexpr int MQ2_B_SLOTS = 3;                  // shared-memory ring of K-slabs
+constexpr uint32_t MQ2_SLAB_BYTES = 65536;      // one K-slab of B for 4 modes
+constexpr uint32_t MQ2_MODE_BYTES = 16384;      // [<= 128 rows (hi, lo) x 128 B]
+constexpr uint32_t MQ2_TM_A = 256;              // D of mode j at column 64 j; A slot s at 256 + 64 s (+16 j, lo +8)
+
+struct ModeGemmQuad2Params {
+  const float2* a; const float2* b; float2* out;
+  long long sAR, sAK, sBN, sBK, sOR, sON;       // complex-element strides
+  int MR, NB, KC;                               // full extents (rows of A, rows of B, contraction length)
+  int n_tiles;                                  // 64-column tiles (gridDim.y = m_tiles * n_tiles)
+  int KCp, kshift;                              // B loader mapping: min(KC, 32) rounded up to a power of two (>= 8)
+  int conjA, a_early, b_early;                  // *_early: the operand is not written by the previous kernel of the stream
+  // fused bias gradient (dweight launch): dbias[o] = bias_scale * sum_b Re gm[b, o, dc]
+  const float2* bias_gm; float* dbias; int bias_B, bias_Co, dc_slot; long long bias_Mt; float bias_scale;
+};
+
+__global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGemmQuad2Params P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_a_full[MQ2_A_SLOTS], bar_a_empty[MQ2_A_SLOTS], bar_b_full[MQ2_B_SLOTS], bar_b_empty[MQ2_B_SLOTS], bar_d_full;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = (int)blockIdx.y / P.n_tiles, nt = (int)blockIdx.y % P.n_tiles;
+  const int MR = min(64, P.MR - 64 * mt), NB = min(64, P.NB - 64 * nt);
+  const int NBp = (NB + 15) & ~15;
+  const int KC = P.KC;
+  const int n_chunks = (KC + 7) >> 3, n_slabs = (KC + 31) >> 5;
+  const long long m0 = (long long)blockIdx.x * 4;      // first mode of this CTA's quad
+
+  if (tid == 0) {
+    for (int i = 0; i < MQ2_A_SLOTS; ++i) { mbar_init(&bar_a_full[i], MQ2_A_WARPS); mbar_init(&bar_a_empty[i], 1); }
+    for (int i = 0; i < MQ2_B_SLOTS; ++i) { mbar_init(&bar_b_full[i], MQ2_B_WARPS); mbar_init(&bar_b_empty[i], 1); }
+    mbar_init(&bar_d_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
+  if (NB < NBp || (KC & 7)) {   // padding rows / the K tail of B must hold finite values (zeros)
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (int)((n_slabs < MQ2_B_SLOTS ? n_slabs : MQ2_B_SLOTS) * (MQ2_SLAB_BYTES / 16));
+    for (int i = tid; i < n16; i += MQ2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp >= 4 + MQ2_A_WARPS) {
+    // ------------------------------------------------------------------ B loaders: global -> registers -> bf16 hi / lo -> swizzled smem
+    const int lt = tid - (4 + MQ2_A_WARPS) * 32;
+    const int kq = lt & (P.KCp - 1);                   // k within the 32-complex slab
+    const int r0 = lt >> P.kshift;
+    const int step = (MQ2_B_WARPS * 32) >> P.kshift;    // 8, 16 or 32 rows between a thread's elements
+    const uint32_t off_hi = (uint32_t)(r0 * 128 + ((((2 * kq) >> 3) ^ r0) & 7) * 16 + ((2 * kq) & 7) * 2);
+    const uint32_t off_lo = off_hi + (uint32_t)NBp * 128u;
+    const uint32_t sstep = (uint32_t)step * 128u;
+    const float2* base = P.b + m0 + (long long)(64 * nt + r0) * P.sBN;
+    if (!P.b_early) pdl_wait();
+    for (int rd = 0; rd < n_slabs; ++rd) {
+      const int slot = rd % MQ2_B_SLOTS;
+      const int k = rd * 32 + kq;
+      const bool k_in = kq < 32 && k < ((KC + 7) & ~7);    // inside the K range the MMAs read
+      const bool k_ok = k_in && k < KC;                    // real data (else: explicit zeros)
+      const float2* pk = base + (long long)k * P.sBK;
+      uint8_t* tile = smem + (size_t)slot * MQ2_SLAB_BYTES;
+#pragma unroll
+      for (int bt = 0; bt < 2; ++bt) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k_ok && r0 + (4 * bt + u) * step < NB) ld_global_v8(pk + (long long)(4 * bt + u) * step * P.sBN, v[u]);
+          else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+          }
+        }
+        if (bt == 0) {
+#pragma unroll
+          for (int u = 4; u < 8; ++u)
+            if (k_ok && r0 + u * step < NB) prefetch_l2(pk + (long long)u * step * P.sBN);
+          if (rd + 1 < n_slabs && kq < 32 && k + 32 < KC) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (r0 + u * step < NB) prefetch_l2(pk + 32 * P.sBK + (long long)u * step * P.sBN);
+          }
+          if (rd >= MQ2_B_SLOTS) mbar_wait(&bar_b_empty[slot], (uint32_t)(((rd / MQ2_B_SLOTS) - 1) & 1));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (k_in && r0 + (4 * bt + u) * step < NB) {
+            uint8_t* t0 = tile + off_hi + (4 * bt + u) * sstep;
+            uint8_t* t1 = tile + off_lo + (4 * bt + u) * sstep;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hi, lo;
+              split2_bf16(v[u][2 * j], v[u][2 * j + 1], hi, lo);
+              *reinterpret_cast<uint32_t*>(t0 + j * MQ2_MODE_BYTES) = hi;
+              *reinterpret_cast<uint32_t*>(t1 + j * MQ2_MODE_BYTES) = lo;
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_b_full[slot]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ A loaders: global -> registers -> bf16 hi / lo -> tensor memory
+    // thread <-> real row (lane of the TMEM quarter) and 4 of the 8 k of every chunk; the two lanes of a complex row read the
+    // same sectors (one request after coalescing) and keep different arrangements of them
+    const int aw = warp - 4, q = aw & 3, g = aw >> 2;
+    const int row = 32 * q + lane, R = row >> 1, part = row & 1;
+    const bool r_ok = R < MR;
+    const float2* pa = P.a + m0 + (long long)(64 * mt + R) * P.sAR + (long long)(4 * g) * P.sAK;
+    const uint32_t tm_mine = tmem + MQ2_TM_A + ((uint32_t)(32 * q) << 16) + (uint32_t)(4 * g);
+    // sign / order of the packed (first K element | second K element << 16) pair for this row
+    //   part 0: (re, -im)   conj: (re, im)        part 1: (im, re)   conj: (-im, re)
+    const uint32_t flip = part == 0 ? (P.conjA ? 0u : 0x80000000u) : (P.conjA ? 0x00008000u : 0u);
+    const uint32_t perm = part == 0 ? 0x3210u : 0x1032u;
+    if (!P.a_early) pdl_wait();
+    float v0[4][8], v1[4][8];
+    auto issue = [&](float (&buf)[4][8], int c) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r_ok && 8 * c + 4 * g + u < KC) ld_global_v8(pa + (long long)(8 * c + u) * P.sAK, buf[u]);
+        else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) buf[u][e] = 0.f;
+        }
+      }
+    };
+    auto consume = [&](float (&buf)[4][8], int c) {
+      const int s = c % MQ2_A_SLOTS;
+      if (c >= MQ2_A_SLOTS) {
+        mbar_wait(&bar_a_empty[s], (uint32_t)(((c / MQ2_A_SLOTS) - 1) & 1));
+        tc_fence_after_sync();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t hi, lo;
+          split2_bf16(buf[u][2 * j], buf[u][2 * j + 1], hi, lo);      // (re | im << 16)
+          hw[u] = __byte_perm(hi, 0, perm) ^ flip;
+          lw[u] = __byte_perm(lo, 0, perm) ^ flip;
+        }
+        tmem_st4(tm_mine + (uint32_t)(64 * s + 16 * j), hw[0], hw[1], hw[2], hw[3]);
+        tmem_st4(tm_mine + (uint32_t)(64 * s + 16 * j + 8), lw[0], lw[1], lw[2], lw[3]);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a_full[s]);
+    };
+    issue(v0, 0);
+    if (n_chunks > 1) issue(v1, 1);
+    if (r_ok) {
+      for (int c = 2; c < n_chunks && c < 10; ++c)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (8 * c + 4 * g + u < KC) prefetch_l2(pa + (long long)(8 * c + u) * P.sAK);
+    }
+    for (int c = 0; c < n_chunks; c += 2) {
+      consume(v0, c);
+      if (c + 2 < n_chunks) issue(v0, c + 2);
+      if (c + 1 < n_chunks) {
+        consume(v1, c + 1);
+        if (c + 3 < n_chunks) issue(v1, c + 3);
+      }
+      if (r_ok && c + 10 < n_chunks) {
+#pragma unroll
+        for (int cc = c + 10; cc < c + 12; ++cc)
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (cc < n_chunks && 8 * cc + 4 * g + u < KC) prefetch_l2(pa + (long long)(8 * cc + u) * P.sAK);
+      }
+    }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issue (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, NBp);
+      const uint32_t base_lo = desc_lo(smem_u32(smem));
+      const uint32_t lo_rows = ((uint32_t)NBp * 128u) >> 4;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % MQ2_A_SLOTS, slab = c >> 2, bslot = slab % MQ2_B_SLOTS;
+        if ((c & 3) == 0) mbar_wait(&bar_b_full[bslot], (uint32_t)((slab / MQ2_B_SLOTS) & 1));
+        mbar_wait(&bar_a_full[s], (uint32_t)((c / MQ2_A_SLOTS) & 1));
+        tc_fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a_hi = tmem + MQ2_TM_A + (uint32_t)(64 * s + 16 * j), a_lo = a_hi + 8;
+          const uint32_t b_hi = base_lo + (uint32_t)bslot * (MQ2_SLAB_BYTES >> 4) + (uint32_t)j * (MQ2_MODE_BYTES >> 4) + 2 * (uint32_t)(c & 3);
+          const uint32_t d = tmem + (uint32_t)(64 * j);
+          mma_bf16_ts(d, a_hi, desc_from_lo(b_hi), idesc, c > 0);
+          mma_bf16_ts(d, a_hi, desc_from_lo(b_hi + lo_rows), idesc, true);
+          mma_bf16_ts(d, a_lo, desc_from_lo(b_hi), idesc, true);
+        }
+        mma_commit(&bar_a_empty[s]);
+        if ((c & 3) == 3 || c == n_chunks - 1) mma_commit(&bar_b_empty[bslot]);
+      }
+      mma_commit(&bar_d_full);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ dependency hand-over: the next kernel of the stream may
+    // start once every CTA of this grid has seen its predecessor complete, so a kernel may read, ahead of its own wait, whatever
+    // its immediate predecessor does not write
+    pdl_wait();
+    pdl_launch_dependents();
+  }
+  if (warp >= 1 && warp < 4 && P.dbias != nullptr && blockIdx.y == 0 && (long long)P.dc_slot >= m0 && (long long)P.dc_slot < m0 + 4) {
+    // fused bias gradient: dbias[o] = sum_b Re gm[b, o, DC] / synthesis scale (the DC slot of gm is the plain sum of gy)
+    pdl_wait();
+    for (int o = warp - 1; o < P.bias_Co; o += 3) {
+      float sum = 0.f;
+      for (int bb = lane; bb < P.bias_B; bb += 32) sum += __ldg(&P.bias_gm[((long long)bb * P.bias_Co + o) * P.bias_Mt + P.dc_slot].x);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      if (lane == 0) P.dbias[o] = sum * P.bias_scale;
+    }
+  }
+  __syncwarp();
+  {
+    // ------------------------------------------------------------------ epilogue, ALL warps: four modes -> one 32-byte store
+    const int q = warp & 3, grp = warp >> 2;
+    const int row = q * 32 + lane;
+    const int R = row >> 1, part = row & 1;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    pdl_wait();                                        // the output buffer may still be read by the previous kernel
+    mbar_wait(&bar_d_full, 0);
+    tc_fence_after_sync();
+    float2* dst = P.out + m0 + (long long)(64 * mt + R) * P.sOR + (long long)(64 * nt) * P.sON;
+    for (int c = 8 * grp; c < NBp; c += 8 * (MQ2_THREADS / 128)) {
+      float acc[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmem_ld8(tmem + lane_sel + (uint32_t)(j * 64 + c), acc[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mine = acc[j][e];
+          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          o[2 * j] = mine; o[2 * j + 1] = other;      // (re, im) on even lanes
+        }
+        const int n = c + e;
+        if (part == 0 && R < MR && n < NB) st_global_v8(reinterpret_cast<float*>(dst + (long long)n * P.sON), o);
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // The opt-in dynamic shared memory limit is a per-device property of a kernel: remember what was set per device ordinal.
 constexpr int SC_MAX_DEVICES = 64;
 struct SmemOptIn { std::atomic<uint32_t> bytes[SC_MAX_DEVICES]; };
@@ -1226,18 +1506,66 @@ static bool launch_mode_gemm_quad(const Plan* p, const float2* a, long long sAR,
 
 static inline bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31u) == 0; }
 
+// SC_QUAD=1 selects the first-generation quad kernel (A/B runs); default: quad2
+static int quad_generation() {
+  static const int v = [] { const char* e = getenv("SC_QUAD"); return e != nullptr && atoi(e) == 1 ? 1 : 2; }();
+  return v;
+}
+
+static bool launch_mode_gemm_quad2(const Plan* p, const float2* a, long long sAR, long long sAK, bool conjA, const float2* b,
+                                   long long sBN, long long sBK, float2* out, long long sOR, long long sON, int MR, int NB,
+                                   int KC, int64_t n_modes, const ModeGemmExtras* ex, cudaStream_t st) {
+  ModeGemmQuad2Params P{};
+  P.a = a; P.b = b; P.out = out;
+  P.sAR = sAR; P.sAK = sAK; P.sBN = sBN; P.sBK = sBK; P.sOR = sOR; P.sON = sON;
+  P.MR = MR; P.NB = NB; P.KC = KC;
+  const int m_tiles = (MR + 63) / 64;
+  P.n_tiles = (NB + 63) / 64;
+  P.KCp = 8; P.kshift = 3;
+  const int kc_round = KC < 32 ? KC : 32;
+  while (P.KCp < kc_round) { P.KCp *= 2; ++P.kshift; }
+  P.conjA = conjA ? 1 : 0;
+  if (ex != nullptr) {
+    P.a_early = ex->a_early ? 1 : 0; P.b_early = ex->b_early ? 1 : 0;
+    if (ex->dbias != nullptr) {
+      P.bias_gm = ex->bias_gm; P.dbias = ex->dbias; P.bias_B = ex->bias_B; P.bias_Co = ex->bias_Co;
+      P.bias_Mt = n_modes; P.dc_slot = p->dc_slot; P.bias_scale = ex->bias_scale;
+    }
+  }
+  const uint32_t smem_bytes = MQ2_B_SLOTS * MQ2_SLAB_BYTES + 1024u;
+  static SmemOptIn opt_in;
+  if (!ensure_dynamic_smem((const void*)k_mode_gemm_quad2, opt_in, p->device, smem_bytes, "cudaFuncSetAttribute(k_mode_gemm_quad2)"))
+    return false;
+  count_launch();
+  void* args[] = {(void*)&P};
+  return cuda_ok(launch_pdl((const void*)k_mode_gemm_quad2, dim3((unsigned)(n_modes / 4), (unsigned)(m_tiles * P.n_tiles)),
+                            dim3(MQ2_THREADS), smem_bytes, st, args),
+                 "k_mode_gemm_quad2 launch");
+}
+
+bool mode_gemm_quad_eligible(const Plan* p, int64_t n_modes, const void* a, const void* b, const void* out) {
+  return p->fast != nullptr && p->weight_block_is_whole && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out);
+}
+
 bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long long sAK, const int* offA, bool conjA,
                          const float2* b, long long sBN, long long sBK, const int* offB, float2* out, long long sOR,
-                         long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st) {
-  // Quad variant: modes contiguous in every operand (no sliced weight block), every stride a multiple of 4 complex
+                         long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st,
+                         ModeGemmExtras* ex) {
+  // Quad variants: modes contiguous in every operand (no sliced weight block), every stride a multiple of 4 complex
   // elements and 32-byte aligned bases, so that 4 consecutive modes are exactly one sector.
   const bool contiguous = (offA == nullptr || p->weight_block_is_whole) && (offB == nullptr || p->weight_block_is_whole) &&
                           (offO == nullptr || p->weight_block_is_whole);
   const bool strides4 = ((sAR | sAK | sBN | sBK | sOR | sON) & 3) == 0;
-  if (contiguous && strides4 && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out) && MR <= 64 && NB <= 64 &&
-      KC <= 64) {
-    return launch_mode_gemm_quad(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, st);
+  if (contiguous && strides4 && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out)) {
+    if (quad_generation() == 2) {
+      if (!launch_mode_gemm_quad2(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st)) return false;
+      if (ex != nullptr && ex->dbias != nullptr) ex->bias_done = true;
+      return true;
+    }
+    if (MR <= 64 && NB <= 64 && KC <= 64)
+      return launch_mode_gemm_quad(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, st);
   }
+  if (!mode_gemm_tc_supported(MR, NB, KC)) { set_error("launch_mode_gemm_tc: extents above 64 need the quad layout"); return false; }
   ModeGemmTcParams P{};
   P.a = a; P.b = b; P.out = out;
   P.sAR = sAR; P.sAK = sAK; P.sBN = sBN; P.sBK = sBK; P.sOR = sOR; P.sON = sON;
@@ -1269,9 +1597,12 @@ bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long lon
   return cuda_ok(cudaGetLastError(), "k_mode_gemm_tc launch");
 }
 
-bool fast_can_contract(const Plan* p, int B, int Ci, int Co) {
-  return p->fast != nullptr && mode_gemm_tc_supported(Co, B, Ci) && mode_gemm_tc_supported(Ci, B, Co) &&
-         mode_gemm_tc_supported(Ci, Co, B);
+// quad_ok: the operands qualify for the quad kernels (mode_gemm_quad_eligible), which take any extents; the single-mode
+// tensor-core kernel (sliced weight blocks, unaligned bases) is limited to 64 x 64 x 64
+bool fast_can_contract(const Plan* p, int B, int Ci, int Co, bool quad_ok) {
+  if (p->fast == nullptr) return false;
+  if (quad_ok && quad_generation() == 2) return true;
+  return mode_gemm_tc_supported(Co, B, Ci) && mode_gemm_tc_supported(Ci, B, Co) && mode_gemm_tc_supported(Ci, Co, B);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1763,7 +2094,6 @@ __global__ void __launch_bounds__(RA_THREADS, 1) k_rows_analysis(const RowsAnaPa
   __shared__ uint32_t tmem_base_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NS = P.ring_stages, FS = P.f32_stages;
-  pdl_launch_dependents();
   if (tid == 0) {
     for (int i = 0; i < FS; ++i) { mbar_init(&bar_f32_full[i], 1); mbar_init(&bar_f32_empty[i], RA_CONV_WARPS); }
     for (int i = 0; i < NS; ++i) { mbar_init(&bar_full[i], RA_CONV_WARPS); mbar_init(&bar_tab_full[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -1783,6 +2113,7 @@ __global__ void __launch_bounds__(RA_THREADS, 1) k_rows_analysis(const RowsAnaPa
     // ------------------------------------------------------------------ producer
     uint8_t* f32_stage = smem + P.off_f32;
     pdl_wait();                                  // x is produced by the previous kernel of the stream
+    pdl_launch_dependents();                     // (after the wait: see k_fused_analysis)
     for (int idx = 0; idx < total; ++idx) {
       const int sb = idx % FS;
       const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
@@ -1920,7 +2251,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_rows_synthesis(const RowsSynP
   constexpr uint32_t A_HALF = (uint32_t)KS * FA_SLAB_BYTES;   // hi slabs, then lo slabs
   constexpr uint32_t T_IMG = (uint32_t)KS * 8192u;      // one [64 x KS*64] table image
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  pdl_launch_dependents();
   if (tid == 0) {
     mbar_init(&bar_u_full, 1);  mbar_init(&bar_u_empty, RS_PREP_WARPS);
     mbar_init(&bar_a_full, RS_PREP_WARPS);  mbar_init(&bar_a_empty, 1);
@@ -1942,6 +2272,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) k_rows_synthesis(const RowsSynP
   if (warp == RS_TMA_WARP) {
     // ------------------------------------------------------------------ producer
     pdl_wait();                                  // U is produced by the previous kernel of the stream
+    pdl_launch_dependents();                     // (after the wait: see k_fused_analysis)
     int gc = 0;
     for (int i = 0; i < n_local; ++i) {
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;

@@ -18,11 +18,20 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
                      float* images_out, bool adjoint, int slices_per_image, cudaStream_t st);
 int fast_tile_group(const Plan* p, bool synthesis, bool adjoint);   // slices per 128-row tile
 
-bool fast_can_contract(const Plan* p, int B, int Ci, int Co);
+bool mode_gemm_quad_eligible(const Plan* p, int64_t n_modes, const void* a, const void* b, const void* out);
+bool fast_can_contract(const Plan* p, int B, int Ci, int Co, bool quad_ok);
+// optional extras of a tensor-core contraction launch
+struct ModeGemmExtras {
+  bool a_early = false, b_early = false;   // the operand is NOT written by the kernel launched just before on the stream:
+                                           // its loads may start ahead of the grid-dependency wait
+  const float2* bias_gm = nullptr; float* dbias = nullptr; int bias_B = 0, bias_Co = 0; float bias_scale = 1.f;   // fuse k_bias_grad
+  bool bias_done = false;                  // out: the launch computed dbias
+};
 // out[R, n] (+ per-mode offset) = sum_k a(R, k) * b(n, k), complex, one product per kept mode, on tcgen05 (bf16x3)
 bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long long sAK, const int* offA, bool conjA,
                          const float2* b, long long sBN, long long sBK, const int* offB, float2* out, long long sOR,
-                         long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st);
+                         long long sON, const int* offO, int MR, int NB, int KC, int64_t n_modes, cudaStream_t st,
+                         ModeGemmExtras* extras = nullptr);
 // last-dim transform alone on tensor cores for any number of rows (multiple of 128); see the end of sc_fast.cu
 bool rows_can_analyze(const Plan* p, bool adjoint, int64_t rows);
 bool rows_can_synthesize(const Plan* p, bool adjoint, int64_t rows);

@@ -794,8 +794,7 @@ class SpectralConv(BaseSpectralConv):
         x = x.contiguous()
         if self.separable:
             return self._forward_separable(x, plan)
-        if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "tucker" and \
-                self.in_channels <= 64 and self.out_channels <= 64:
+        if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "tucker":
             return self._forward_tucker(x, plan)
         if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "cp":
             return self._forward_cp(x, plan)

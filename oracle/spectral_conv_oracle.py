@@ -120,7 +120,33 @@ def contract_tucker(xm: torch.Tensor, core: torch.Tensor, factors: Sequence[torc
     cs = EINSUM_SYMBOLS[order + 1: 2 * order + 1]
     fs = [xs[1] + cs[0], o + cs[1]] + [a + r for a, r in zip(xs[2:], cs[2:])]
     out = xs[0] + o + xs[2:]
-    return torch.einsum(f"{xs},{cs},{','.join(fs)}->{out}", xm, core, *factors)
+    # torch.einsum without opt_einsum contracts its operands left to right: `x, core` share no index, so the first
+    # intermediate is their outer product (2 TB at BASELINE config 3).  The reference runs this einsum through tensorly with
+    # the opt_einsum plugin (:16-17), i.e. along a cheap pairwise path; for large problems the same contraction is therefore
+    # evaluated pairwise here (channel mixing first, the core expanded along the mode axes, the dense mode product, output
+    # mixing).  tests/test_oracle.py checks the two evaluations against each other on small cases.
+    if xm.numel() * core.numel() <= (1 << 24):
+        return torch.einsum(f"{xs},{cs},{','.join(fs)}->{out}", xm, core, *factors)
+    return contract_tucker_pairwise(xm, core, factors)
+
+
+def contract_tucker_pairwise(xm: torch.Tensor, core: torch.Tensor, factors: Sequence[torch.Tensor]) -> torch.Tensor:
+    order = xm.ndim
+    d = order - 2
+    xs = EINSUM_SYMBOLS[:order]                       # b i m1..md
+    ms = xs[2:]
+    o = EINSUM_SYMBOLS[order]
+    cs = EINSUM_SYMBOLS[order + 1: 2 * order + 1]     # f g r1..rd
+    t = torch.einsum(f"{xs},{xs[1]}{cs[0]}->{xs[0]}{cs[0]}{ms}", xm, factors[0])               # b f m..
+    w = core
+    cur = list(cs)
+    for j in range(d):                                                                      # f g m1..mj r(j+1)..rd
+        nxt = list(cur)
+        nxt[2 + j] = ms[j]
+        w = torch.einsum(f"{''.join(cur)},{ms[j]}{cs[2 + j]}->{''.join(nxt)}", w, factors[2 + j])
+        cur = nxt
+    t = torch.einsum(f"{xs[0]}{cs[0]}{ms},{''.join(cur)}->{xs[0]}{cs[1]}{ms}", t, w)          # b g m..
+    return torch.einsum(f"{xs[0]}{cs[1]}{ms},{o}{cs[1]}->{xs[0]}{o}{ms}", t, factors[1])
 
 
 def contract_cp(xm: torch.Tensor, weights: torch.Tensor, factors: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -184,6 +184,43 @@ def test_highres_config_256(cuda_device):
     _fwd_bwd_vs_oracle(cuda_device, 16, 64, 64, (256, 256), (64, 64))
 
 
+@pytest.mark.parametrize("B,R", [(2, 512), (1, 1024)])
+def test_highres_config_512_1024(cuda_device, B, R):
+    """BASELINE config 5 at R = 512 and 1024: grid and modes as named, channels 64; the batch is cut (16 -> 2 / 1) so that the
+    CPU oracle finishes in seconds.  The last-dim tensor-core kernels + the leading-dim table kernels run here."""
+    _fwd_bwd_vs_oracle(cuda_device, B, 64, 64, (R, R), (64, 64))
+
+
+def test_hidden_channels_128_and_batch_96(cuda_device):
+    """Extents above the 64 x 64 tile of the tensor-core contraction: they run the tiled quad kernel, not a fallback."""
+    _fwd_bwd_vs_oracle(cuda_device, 4, 128, 128, (64, 64), (16, 16))
+    _fwd_bwd_vs_oracle(cuda_device, 96, 16, 24, (64, 64), (16, 16))
+
+
+def test_tfno_config_full_size(cuda_device):
+    """BASELINE config 3: TFNO2d, (B,C,H,W) = (32,64,128,128), modes (32,32), Tucker ranks (36,36,18,10) (= rank 0.1),
+    implementation="factorized": y, dx, the core gradient, every factor gradient and dbias against the CPU oracle."""
+    dev = cuda_device
+    B, C, grid, modes, ranks = 32, 64, (128, 128), (32, 32), [36, 36, 18, 10]
+    x, w, bias, gy = O.make_inputs(B, C, C, grid, modes, seed=3, kind="tucker", ranks=ranks)
+    y_ref, dx_ref, dws_ref, db_ref = O.spectral_conv_fwd_bwd(x, w, bias, gy, modes)
+    conv = nb.SpectralConv(C, C, modes, factorization="tucker", rank=ranks, implementation="factorized").to(dev)
+    with torch.no_grad():
+        for dst, src in zip(conv.weight.decomposition(), w.params()):
+            assert dst.shape == src.shape, (dst.shape, src.shape)
+            dst.copy_(src.to(dev))
+        conv.bias.copy_(bias.to(dev))
+    xd = x.to(dev).requires_grad_(True)
+    y = conv(xd)
+    y.backward(gy.to(dev))
+    assert rel_err(y, y_ref) < REL_TOL, "y"
+    assert rel_err(xd.grad, dx_ref) < REL_TOL, "dx"
+    assert rel_err(conv.bias.grad, db_ref) < REL_TOL, "dbias"
+    for i, (p, g) in enumerate(zip(conv.weight.decomposition(), dws_ref)):
+        assert p.grad is not None, f"param {i} received no grad"
+        assert rel_err(p.grad, g) < REL_TOL, f"dparam{i}"
+
+
 def test_properties_at_full_size(cuda_device):
     """Size-independent properties at the headline size: linearity in x, zero response to modes outside
     the kept set, dweight support, bias gradient == sum of the upstream gradient."""

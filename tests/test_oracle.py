@@ -110,3 +110,19 @@ def test_weight_rows_match_python_slices(maxm, n_mode, N):
         maxes = [2, maxm] if last else [maxm, 3]
         plan = O.kept_mode_plan(grid, stored, maxes)[1 if last else 0]
         assert plan.w_index == expect
+
+
+@pytest.mark.parametrize("shape,ranks", [((3, 5, 6, 4), (4, 3, 5, 2)), ((2, 6, 5, 4, 3), (3, 4, 2, 3, 2)), ((2, 4, 9), (3, 2, 4))])
+def test_tucker_pairwise_evaluation_equals_the_single_einsum(shape, ranks):
+    """Large Tucker problems (BASELINE config 3) are contracted pairwise in the oracle -- the path opt_einsum picks for the
+    reference's einsum (:76-103) -- because torch.einsum alone would first form the outer product of x and the core."""
+    from oracle import spectral_conv_oracle as O
+    torch.manual_seed(0)
+    B, Ci, *kept = shape
+    Co = 7
+    xm = torch.randn(B, Ci, *kept, dtype=torch.cfloat)
+    core = torch.randn(*ranks, dtype=torch.cfloat)
+    factors = [torch.randn(n, r, dtype=torch.cfloat) for n, r in zip([Ci, Co, *kept], ranks)]
+    a = O.contract_tucker(xm, core, factors)
+    b = O.contract_tucker_pairwise(xm, core, factors)
+    assert (a - b).abs().max().item() < 1e-5 * a.abs().max().item()
