@@ -36,6 +36,7 @@ extern "C" {
 typedef struct { float re, im; } sc_complex;   /* bit-compatible with torch.complex64 / cuFloatComplex */
 typedef struct sc_plan sc_plan;                /* opaque; owns the device-resident twiddle tables */
 typedef void* sc_stream;                       /* cudaStream_t */
+typedef void* sc_event;                        /* cudaEvent_t */
 
 enum { SC_NORM_FORWARD = 0, SC_NORM_BACKWARD = 1, SC_NORM_ORTHO = 2 };   /* fft_norm, :303,:342 */
 
@@ -137,14 +138,28 @@ int sc_cp_factor_grad(const sc_complex* const* mode_factors, const int32_t* kept
                       const sc_complex* dscale, sc_complex* out, int32_t which, int32_t rank, sc_stream stream);
 
 /* ---- whole forward / backward for a dense weight (one call per autograd.Function.forward/backward) ------ */
-/* y = SpectralConv.forward(x); xm_saved (B,Ci,k..) is the only activation kept for backward. */
+/* y = SpectralConv.forward(x); xm_saved (B*Ci*prod(k) sc_complex, 32-byte aligned) is the only activation kept for backward.
+ * It is OPAQUE: *saved_layout_out tells sc_backward_dense how its elements are ordered -- SC_MODES_STANDARD (B, Ci, k_1..k_d),
+ * or SC_MODES_QUAD_MAJOR [prod(k)/4][B][Ci][4], which the fused tcgen05 chain uses so that the operand sectors of the
+ * contraction kernels are contiguous.  Pass NULL to force the standard layout. */
+enum { SC_MODES_STANDARD = 0, SC_MODES_QUAD_MAJOR = 1 };
 int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weight, const float* bias,
-                     float* y, sc_complex* xm_saved, int32_t batch, int32_t in_channels, int32_t out_channels,
+                     float* y, sc_complex* xm_saved, int32_t* saved_layout_out,
+                     int32_t batch, int32_t in_channels, int32_t out_channels,
                      void* workspace, size_t workspace_bytes, sc_stream stream);
+/* saved_layout: what sc_forward_dense reported for xm_saved.  dx / dweight / dbias may each be NULL.
+ * grads_ready (may be NULL): recorded on `stream` as soon as dweight and dbias are complete, i.e. BEFORE the dxm product and the
+ * dx synthesis are launched: a data-parallel caller makes its collective stream wait on it and all-reduces the gradients
+ * underneath the rest of the backward pass (DDP overlap, neuralop/training/trainer.py:203-205). */
 int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* weight, const sc_complex* xm_saved,
-                      float* dx, sc_complex* dweight, float* dbias,
+                      int32_t saved_layout, float* dx, sc_complex* dweight, float* dbias,
                       int32_t batch, int32_t in_channels, int32_t out_channels,
-                      void* workspace, size_t workspace_bytes, sc_stream stream);
+                      void* workspace, size_t workspace_bytes, sc_stream stream, sc_event grads_ready);
+
+/* events for the grads_ready hand-over above (timing disabled); sc_stream_wait_event makes `stream` wait for the last record */
+int  sc_event_create(sc_event* event_out);
+void sc_event_destroy(sc_event event);
+int  sc_stream_wait_event(sc_stream stream, sc_event event);
 
 /* ---- diagnostics --------------------------------------------------------------------------------------- */
 const char* sc_last_error(void);          /* thread-local description of the last failure */
@@ -155,6 +170,11 @@ const char* sc_build_info(void);          /* "sm_100a nvcc <ver> ..." */
 int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream);
 /* the same product with the A operand resident in tensor memory (tcgen05.st + TMEM-A tcgen05.mma) */
 int sc_selftest_umma_ts(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream);
+
+/* measurement probe: one CTA per quad of modes gathers its (Ci x 64 x 32 B) block of a (Ci, 64, n_modes) complex64 tensor with 4-D
+ * tensor loads; cycles_out[2q] = cycles to issue, cycles_out[2q+1] = cycles until every box has landed (device int64[2 * n_modes / 4]) */
+int sc_probe_tma_gather(const sc_complex* w, int32_t in_channels, int32_t out_channels, int64_t n_modes, int64_t* cycles_out,
+                        sc_stream stream);
 
 #ifdef __cplusplus
 }

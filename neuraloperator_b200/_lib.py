@@ -46,10 +46,13 @@ SIGNATURES = {
     "sc_contract_dense_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_i32, c_i32, c_i32, c_void_p]),
     "sc_bias_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
-    "sc_forward_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32,
-                                 c_void_p, c_size_t, c_void_p]),
-    "sc_backward_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
-                                  c_i32, c_void_p, c_size_t, c_void_p]),
+    "sc_forward_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.POINTER(c_i32), c_i32, c_i32,
+                                 c_i32, c_void_p, c_size_t, c_void_p]),
+    "sc_backward_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
+                                  c_i32, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "sc_event_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "sc_event_destroy": (None, [c_void_p]),
+    "sc_stream_wait_event": (c_int, [c_void_p, c_void_p]),
     "sc_table_contract": (c_int, [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i32, c_void_p]),
     "sc_pair_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_void_p]),
     "sc_problem_table": (c_int, [c_void_p, c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p, c_void_p]),
@@ -58,6 +61,7 @@ SIGNATURES = {
     "sc_cp_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i32, c_i64, c_void_p]),
     "sc_cp_dscale": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_void_p]),
     "sc_cp_factor_grad": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
+    "sc_probe_tma_gather": (c_int, [c_void_p, c_i32, c_i32, c_i64, c_void_p, c_void_p]),
     "sc_last_error": (ctypes.c_char_p, []),
     "sc_kernel_launch_count": (ctypes.c_uint64, []),
     "sc_build_info": (ctypes.c_char_p, []),

@@ -2,6 +2,7 @@
 // orchestration of the transform / contraction kernels.  See include/spectral_conv_b200.h for the contract
 // and the reference lines each entry point replaces.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -272,12 +273,13 @@ static bool synthesize_generic(const Plan* p, const float2* modes_in, int64_t n_
 }
 
 static bool analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint,
-                    float2* b0, float2* b1, cudaStream_t st) {
+                    float2* b0, float2* b1, cudaStream_t st, bool quad_major = false, const L2Prefetch* pf = nullptr) {
   if (n_images <= 0) return true;
+  if (quad_major) return fast_analyze(p, images, n_images, modes_out, adjoint, st, true, pf);   // (dense_chain_quad_major checked the shape)
   if (p->fast_enabled && fast_can_analyze(p, adjoint)) {
     if (p->d == 2) {
       if (n_images % fast_tile_group(p, false, adjoint) == 0)
-        return fast_analyze(p, images, n_images, modes_out, adjoint, st);
+        return fast_analyze(p, images, n_images, modes_out, adjoint, st, false, pf);
     } else {   // d == 3: fused last two dims per (image, z) slice, then dim 0 on the truncated data
       const DimTables& Z = p->dim[0];
       const int64_t slices = n_images * (adjoint ? Z.M : Z.N);
@@ -292,8 +294,9 @@ static bool analyze(const Plan* p, const float* images, int64_t n_images, float2
 }
 
 static bool synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
-                       float* images_out, bool adjoint, float2* b0, float2* b1, cudaStream_t st) {
+                       float* images_out, bool adjoint, float2* b0, float2* b1, cudaStream_t st, bool quad_major = false) {
   if (n_images <= 0) return true;
+  if (quad_major) return fast_synthesize(p, modes_in, n_images, n_channels, bias, images_out, adjoint, 1, st, true);
   if (p->fast_enabled && fast_can_synthesize(p, adjoint)) {
     if (p->d == 2) {
       if (n_images % fast_tile_group(p, true, adjoint) == 0)
@@ -315,14 +318,30 @@ static bool synthesize(const Plan* p, const float2* modes_in, int64_t n_images, 
 // `chained`: the call is part of sc_forward_dense / sc_backward_dense, i.e. the kernel launched just before on the stream is
 // this library's transform kernel, which does not write the weights / saved modes: the contraction may fetch those operands
 // ahead of its grid-dependency wait.  Standalone calls (chained = false) make no assumption about their predecessor.
+//
+// Quad-major mode tensors (x_qm / y_qm / g_qm): inside the dense chains the kept-mode tensors are internal, so they are
+// laid out [quad of 4 modes][batch][channel][4] instead of [batch][channel][modes]: the 32-byte sectors one contraction CTA
+// touches are then contiguous along the channel index and its loads / stores coalesce (the standard layout costs one L1
+// wavefront per sector: measured LSU-bound).  Only the strides of the launch change.
+static bool l2_resident_env() {   // SC_CONTRACT_PREFETCH=1: keep the contraction's own L2 prefetches inside the chains too (A/B runs)
+  static const bool v = [] { const char* e = getenv("SC_CONTRACT_PREFETCH"); return e == nullptr || atoi(e) == 0; }();
+  return v;
+}
+
 static bool contract_fwd(const Plan* p, const float2* xm, const float2* w, float2* ym, int B, int Ci, int Co,
-                         cudaStream_t st, bool chained) {
+                         cudaStream_t st, bool chained, bool x_qm = false, bool y_qm = false) {
   const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
-  if (p->fast_enabled && fast_can_contract(p, B, Ci, Co, mode_gemm_quad_eligible(p, Mt, w, xm, ym))) {   // ym^T[o, b] = sum_i w[i, o] * xm[b, i]
+  const bool quad_ok = mode_gemm_quad_eligible(p, Mt, w, xm, ym);
+  if ((x_qm || y_qm) && !(quad_ok && quad2_enabled())) { set_error("quad-major mode tensors need the quad contraction kernel"); return false; }
+  if ((p->fast_enabled || x_qm || y_qm) && fast_can_contract(p, B, Ci, Co, quad_ok)) {   // ym^T[o, b] = sum_i w[i, o] * xm[b, i]
     ModeGemmExtras ex;
     ex.a_early = chained;
-    return launch_mode_gemm_tc(p, w, Wp, (long long)Co * Wp, p->d_woff, false, xm, (long long)Ci * Mt, Mt, nullptr, ym, Mt,
-                               (long long)Co * Mt, nullptr, Co, B, Ci, Mt, st, &ex);
+    ex.l2_resident = chained && l2_resident_env();
+    long long sBN = (long long)Ci * Mt, sBK = Mt, sOR = Mt, sON = (long long)Co * Mt;
+    if (x_qm) { ex.sBQ = (long long)B * Ci * 4; sBN = (long long)Ci * 4; sBK = 4; }
+    if (y_qm) { ex.sOQ = (long long)B * Co * 4; sOR = 4; sON = (long long)Co * 4; }
+    return launch_mode_gemm_tc(p, w, Wp, (long long)Co * Wp, p->d_woff, false, xm, sBN, sBK, nullptr, ym, sOR, sON, nullptr, Co, B,
+                               Ci, Mt, st, &ex);
   }
   ModeGemmOperand a{xm, (int64_t)Ci * Mt, Mt, nullptr};
   ModeGemmOperand b{w, (int64_t)Co * Wp, Wp, p->d_woff};
@@ -331,28 +350,43 @@ static bool contract_fwd(const Plan* p, const float2* xm, const float2* w, float
 }
 
 static bool contract_bwd(const Plan* p, const float2* xm, const float2* gm, const float2* w, float2* dxm,
-                         float2* dw, float* dbias, int B, int Ci, int Co, cudaStream_t st, bool chained) {
+                         float2* dw, float* dbias, int B, int Ci, int Co, cudaStream_t st, bool chained,
+                         bool x_qm = false, bool g_qm = false, cudaEvent_t grads_ready = nullptr) {
   const int64_t Mt = p->n_modes_total, Wp = p->weight_elems_per_io;
   const bool quad_ok = (dw == nullptr || mode_gemm_quad_eligible(p, Mt, xm, gm, dw)) &&
                        (dxm == nullptr || mode_gemm_quad_eligible(p, Mt, w, gm, dxm));
-  const bool tc = p->fast_enabled && fast_can_contract(p, B, Ci, Co, quad_ok);
+  const bool any_qm = (x_qm && dw != nullptr) || g_qm;
+  if (any_qm && !(quad_ok && quad2_enabled())) { set_error("quad-major mode tensors need the quad contraction kernel (32-byte aligned operands)"); return false; }
+  const bool tc = (p->fast_enabled || any_qm) && fast_can_contract(p, B, Ci, Co, quad_ok);
   if (dw != nullptr && !p->weight_block_is_whole &&
       !cuda_ok(cudaMemsetAsync(dw, 0, (size_t)Ci * Co * Wp * sizeof(float2), st), "cudaMemsetAsync(dweight)"))
     return false;
   if (tc) {
     bool bias_done = false, have_dw_launch = false;
+    // gm as an operand: rows o / k = b (dweight) or rows b / k = o (dxm)
+    const long long g_sB = g_qm ? (long long)Co * 4 : (long long)Co * Mt, g_sO = g_qm ? 4 : Mt, g_sQ = g_qm ? (long long)B * Co * 4 : 0;
     // dweight[i, o] = sum_b conj(xm[b, i]) * gm[b, o]   (+ dbias from the DC slot of gm, fused into the same launch)
     if (dw != nullptr) {
       ModeGemmExtras ex;
       ex.a_early = chained;                          // the saved modes come from the forward pass
-      if (dbias != nullptr) { ex.bias_gm = gm; ex.dbias = dbias; ex.bias_B = B; ex.bias_Co = Co; ex.bias_scale = (float)(1.0 / p->s_inv); }
-      if (!launch_mode_gemm_tc(p, xm, Mt, (long long)Ci * Mt, nullptr, true, gm, Mt, (long long)Co * Mt, nullptr, dw,
+      ex.l2_resident = chained && l2_resident_env();
+      if (dbias != nullptr) { ex.dbias = dbias; ex.bias_scale = (float)(1.0 / p->s_inv); }
+      long long sAR = Mt, sAK = (long long)Ci * Mt;
+      if (x_qm) { ex.sAQ = (long long)B * Ci * 4; sAR = 4; sAK = (long long)Ci * 4; }
+      ex.sBQ = g_sQ;
+      if (!launch_mode_gemm_tc(p, xm, sAR, sAK, nullptr, true, gm, g_sO, g_sB, nullptr, dw,
                                (long long)Co * Wp, Wp, p->d_woff, Ci, Co, B, Mt, st, &ex))
         return false;
       bias_done = ex.bias_done;
       have_dw_launch = true;
     }
-    if (dbias != nullptr && !bias_done && !launch_bias_grad(gm, dbias, B, Co, Mt, p->dc_slot, (float)(1.0 / p->s_inv), st)) return false;
+    if (dbias != nullptr && !bias_done) {
+      if (g_qm) { set_error("bias gradient from a quad-major gm needs the dweight launch"); return false; }
+      if (!launch_bias_grad(gm, dbias, B, Co, Mt, p->dc_slot, (float)(1.0 / p->s_inv), st)) return false;
+    }
+    // dweight and dbias are complete once the launches above retire: a data-parallel caller starts its gradient all-reduce
+    // on this event, underneath the dxm product and the dx synthesis
+    if (grads_ready != nullptr && !cuda_ok(cudaEventRecord(grads_ready, st), "cudaEventRecord(grads_ready)")) return false;
     // dxm^T[i, b] = sum_o conj(w[i, o]) * gm[b, o]
     if (dxm != nullptr) {
       ModeGemmExtras ex;
@@ -360,8 +394,12 @@ static bool contract_bwd(const Plan* p, const float2* xm, const float2* gm, cons
       // neither the weights nor gm
       ex.a_early = chained || have_dw_launch;
       ex.b_early = have_dw_launch;
-      if (!launch_mode_gemm_tc(p, w, (long long)Co * Wp, Wp, p->d_woff, true, gm, (long long)Co * Mt, Mt, nullptr, dxm, Mt,
-                               (long long)Ci * Mt, nullptr, Ci, B, Co, Mt, st, &ex))
+      ex.l2_resident = chained && l2_resident_env();
+      ex.sBQ = g_sQ;
+      long long sOR = Mt, sON = (long long)Ci * Mt;
+      if (g_qm) { ex.sOQ = (long long)B * Ci * 4; sOR = 4; sON = (long long)Ci * 4; }
+      if (!launch_mode_gemm_tc(p, w, (long long)Co * Wp, Wp, p->d_woff, true, gm, g_sB, g_sO, nullptr, dxm, sOR, sON, nullptr,
+                               Ci, B, Co, Mt, st, &ex))
         return false;
     }
     return true;
@@ -375,6 +413,7 @@ static bool contract_bwd(const Plan* p, const float2* xm, const float2* gm, cons
   if (dbias != nullptr &&
       !launch_bias_grad(gm, dbias, B, Co, Mt, p->dc_slot, (float)(1.0 / p->s_inv), st))
     return false;
+  if (grads_ready != nullptr && !cuda_ok(cudaEventRecord(grads_ready, st), "cudaEventRecord(grads_ready)")) return false;
   if (dxm != nullptr) {
     ModeGemmOperand a{gm, (int64_t)Co * Mt, Mt, nullptr};          // r = b, k = o
     ModeGemmOperand b{w, Wp, (int64_t)Co * Wp, p->d_woff};         // k = o, c = i  (conjugated)
@@ -382,6 +421,19 @@ static bool contract_bwd(const Plan* p, const float2* xm, const float2* gm, cons
     if (!launch_mode_gemm(a, false, b, true, o, B, Ci, Co, Mt, st)) return false;
   }
   return true;
+}
+
+// The dense chains keep their mode tensors quad-major when every stage is a kernel that speaks that layout: 2-D problem on
+// the fused tcgen05 transforms (whole tiles), quad contraction (whole weight block, mode count a multiple of 4, aligned weight).
+static bool dense_chain_quad_major(const Plan* p, int B, int Ci, int Co, const void* weight) {
+  static const bool env_on = [] { const char* e = getenv("SC_QUAD_MAJOR"); return e == nullptr || atoi(e) != 0; }();   // =0: A/B runs
+  if (!env_on || !p->fast_enabled || p->fast == nullptr || p->d != 2 || !quad2_enabled()) return false;
+  if (!fast_can_analyze(p, false) || !fast_can_analyze(p, true) || !fast_can_synthesize(p, false) || !fast_can_synthesize(p, true)) return false;
+  const int64_t ni = (int64_t)B * Ci, no = (int64_t)B * Co;
+  if (ni % fast_tile_group(p, false, false) || no % fast_tile_group(p, true, false) || no % fast_tile_group(p, false, true) ||
+      ni % fast_tile_group(p, true, true))
+    return false;
+  return p->weight_block_is_whole && p->n_modes_total % 4 == 0 && (reinterpret_cast<uintptr_t>(weight) & 31u) == 0;
 }
 
 }  // namespace sc
@@ -563,7 +615,7 @@ int sc_bias_grad(const sc_plan* plan, const sc_complex* gm, float* dbias, int32_
 }
 
 int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weight, const float* bias, float* y,
-                     sc_complex* xm_saved, int32_t batch, int32_t in_channels, int32_t out_channels,
+                     sc_complex* xm_saved, int32_t* saved_layout_out, int32_t batch, int32_t in_channels, int32_t out_channels,
                      void* workspace, size_t workspace_bytes, sc_stream stream) {
   const Plan* p = reinterpret_cast<const Plan*>(plan);
   SC_REQUIRE(p != nullptr && x != nullptr && weight != nullptr && y != nullptr && xm_saved != nullptr,
@@ -574,29 +626,66 @@ int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weig
   SC_TRY(carve(p, n_max, workspace, workspace_bytes, &w));
   float2* xm = reinterpret_cast<float2*>(xm_saved);
   float2* ym = w.modes[0];
-  SC_TRY(analyze(p, x, (int64_t)batch * in_channels, xm, false, w.buf[0], w.buf[1], st));
-  SC_TRY(contract_fwd(p, xm, reinterpret_cast<const float2*>(weight), ym, batch, in_channels, out_channels, st, true));
-  SC_TRY(synthesize(p, ym, (int64_t)batch * out_channels, out_channels, bias, y, false, w.buf[0], w.buf[1], st));
+  // without a place to report it the saved modes stay in the standard layout
+  const bool qm = saved_layout_out != nullptr && dense_chain_quad_major(p, batch, in_channels, out_channels, weight) &&
+                  (reinterpret_cast<uintptr_t>(xm_saved) & 31u) == 0;
+  if (saved_layout_out != nullptr) *saved_layout_out = qm ? SC_MODES_QUAD_MAJOR : SC_MODES_STANDARD;
+  // the forward contraction reads the whole weight right after the analysis: let the analysis launch pull it into L2
+  L2Prefetch pf;
+  pf.ptr[0] = weight; pf.bytes[0] = (unsigned long long)in_channels * out_channels * p->weight_elems_per_io * sizeof(float2);
+  SC_TRY(analyze(p, x, (int64_t)batch * in_channels, xm, false, w.buf[0], w.buf[1], st, qm, &pf));
+  SC_TRY(contract_fwd(p, xm, reinterpret_cast<const float2*>(weight), ym, batch, in_channels, out_channels, st, true, qm, qm));
+  SC_TRY(synthesize(p, ym, (int64_t)batch * out_channels, out_channels, bias, y, false, w.buf[0], w.buf[1], st, qm));
   return 0;
 }
 
 int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* weight, const sc_complex* xm_saved,
-                      float* dx, sc_complex* dweight, float* dbias, int32_t batch, int32_t in_channels,
-                      int32_t out_channels, void* workspace, size_t workspace_bytes, sc_stream stream) {
+                      int32_t saved_layout, float* dx, sc_complex* dweight, float* dbias, int32_t batch, int32_t in_channels,
+                      int32_t out_channels, void* workspace, size_t workspace_bytes, sc_stream stream, sc_event grads_ready) {
   const Plan* p = reinterpret_cast<const Plan*>(plan);
   SC_REQUIRE(p != nullptr && gy != nullptr && weight != nullptr, "sc_backward_dense: null argument");
   SC_REQUIRE(dweight == nullptr || xm_saved != nullptr, "sc_backward_dense: dweight needs the saved modes");
+  SC_REQUIRE(saved_layout == SC_MODES_STANDARD || saved_layout == SC_MODES_QUAD_MAJOR, "sc_backward_dense: unknown saved_layout");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t n_max = (int64_t)batch * (in_channels > out_channels ? in_channels : out_channels);
   Workspace w{};
   SC_TRY(carve(p, n_max, workspace, workspace_bytes, &w));
   float2* gm = w.modes[0];
   float2* dxm = dx != nullptr ? w.modes[1] : nullptr;
-  SC_TRY(analyze(p, gy, (int64_t)batch * out_channels, gm, true, w.buf[0], w.buf[1], st));
+  const bool x_qm = saved_layout == SC_MODES_QUAD_MAJOR;
+  // gm / dxm are internal to this call: quad-major whenever the chain allows it (a dbias without a dweight launch reads gm
+  // with the standalone kernel, which wants the standard layout)
+  const bool g_qm = dense_chain_quad_major(p, batch, in_channels, out_channels, weight) && (dbias == nullptr || dweight != nullptr) &&
+                    (dweight == nullptr || (reinterpret_cast<uintptr_t>(dweight) & 31u) == 0);
+  SC_REQUIRE(!x_qm || p->fast != nullptr, "sc_backward_dense: quad-major saved modes without the tensor-core path");
+  // the two backward contractions read the saved modes and the weight: the gy analysis pulls both into L2
+  L2Prefetch pf;
+  if (dweight != nullptr) { pf.ptr[0] = xm_saved; pf.bytes[0] = (unsigned long long)batch * in_channels * p->n_modes_total * sizeof(float2); }
+  if (dx != nullptr) { pf.ptr[1] = weight; pf.bytes[1] = (unsigned long long)in_channels * out_channels * p->weight_elems_per_io * sizeof(float2); }
+  SC_TRY(analyze(p, gy, (int64_t)batch * out_channels, gm, true, w.buf[0], w.buf[1], st, g_qm, &pf));
   SC_TRY(contract_bwd(p, reinterpret_cast<const float2*>(xm_saved), gm, reinterpret_cast<const float2*>(weight), dxm,
-                      reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels, st, true));
+                      reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels, st, true, x_qm, g_qm,
+                      static_cast<cudaEvent_t>(grads_ready)));
   if (dx != nullptr)
-    SC_TRY(synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+    SC_TRY(synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st, g_qm));
+  return 0;
+}
+
+int sc_event_create(sc_event* event_out) {
+  SC_REQUIRE(event_out != nullptr, "sc_event_create: null argument");
+  cudaEvent_t ev = nullptr;
+  SC_TRY(cuda_ok(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
+  *event_out = ev;
+  return 0;
+}
+
+void sc_event_destroy(sc_event event) {
+  if (event != nullptr) cudaEventDestroy(static_cast<cudaEvent_t>(event));
+}
+
+int sc_stream_wait_event(sc_stream stream, sc_event event) {
+  SC_REQUIRE(event != nullptr, "sc_stream_wait_event: null event");
+  SC_TRY(cuda_ok(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(event), 0), "cudaStreamWaitEvent"));
   return 0;
 }
 
@@ -670,6 +759,14 @@ int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_
 int sc_selftest_umma_ts(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream) {
   SC_REQUIRE(a != nullptr && b != nullptr && d != nullptr, "sc_selftest_umma_ts: null argument");
   SC_TRY(umma_selftest_ts(a, b, d, n, k, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_probe_tma_gather(const sc_complex* w, int32_t in_channels, int32_t out_channels, int64_t n_modes, int64_t* cycles_out,
+                        sc_stream stream) {
+  SC_REQUIRE(w != nullptr && cycles_out != nullptr, "sc_probe_tma_gather: null argument");
+  SC_TRY(tma_gather_probe(reinterpret_cast<const float2*>(w), in_channels, out_channels, n_modes,
+                          reinterpret_cast<long long*>(cycles_out), static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -174,6 +174,12 @@ bool umma_selftest(const float* A, const float* B, float* D, int N, int K, cudaS
       (P).trace[(((role) * 16 + (i)) * 4 + (ph))] = clock64();                                          \
   } while (0)
 
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 constexpr int FA_F32_STAGES = 3;   // depth of the fp32 TMA staging ring (32 KB slabs): covers the HBM latency under load
 constexpr int FA_LOADER_WARPS = 8;
 constexpr int FA_LOADER_ITERS = 128 / (FA_LOADER_WARPS * 2);   // row passes per slab: a loader warp covers 2 rows x 64 floats
@@ -191,6 +197,15 @@ struct AnaParams {
                            // copied once into TENSOR MEMORY and used as the TMEM A operand of every stage-2 MMA
   int n_tiles, W, slabs, N1, KX, QROWS, n_stages, tmem_cols;
   int l2_stream_hint;      // 1: the x slabs are loaded with an L2 evict-first policy (read once)
+  int quad_major;          // 1: modes are written in the quad-major layout out[quad][image][4 modes] (contraction operands become
+                           //    contiguous 32-byte sectors along the image index), 0: out[image][modes]
+  int G, Mt;               // images per tile, kept modes per image
+  long long n_images;      // all images of the launch (the quad stride of the quad-major layout, in sectors)
+  // Operands of the NEXT kernels of the chain (weights, saved modes) that this launch pulls into L2 while it streams the images:
+  // the transform is bound by shared memory, not by DRAM, so the extra reads are free here, whereas the contraction kernels
+  // would otherwise wait for them at DRAM latency with 32-byte requests (measured: ~9000 of their ~24000 cycles).
+  const uint8_t* pf_ptr[2];
+  unsigned long long pf_bytes[2];
   uint32_t off_f32, off_ring, off_b1, off_a2, off_b2, off_scratch, stage_off;   // stage_off: output staging, relative to off_scratch
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
@@ -267,10 +282,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
     // library may then read, ahead of its own wait, anything its immediate predecessor does not write (the contraction
     // fetches the weights that way).  The dependents still start as soon as this CTA leaves its SM.
     pdl_launch_dependents();
+    constexpr unsigned long long PF_PIECE = 8192;
     for (int idx = 0; idx < total; ++idx) {
       const int sb = idx % FA_F32_STAGES;
       mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx / FA_F32_STAGES) & 1) ^ 1));
       if (elect_one()) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {        // this CTA's idx-th 8 KB piece of each prefetch range
+          const unsigned long long off = ((unsigned long long)idx * gridDim.x + blockIdx.x) * PF_PIECE;
+          if (off < P.pf_bytes[r]) {
+            const unsigned long long left = P.pf_bytes[r] - off;
+            bulk_prefetch_l2(P.pf_ptr[r] + off, (uint32_t)(left < PF_PIECE ? left : PF_PIECE));
+          }
+        }
         const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
         mbar_arrive_expect_tx(&bar_f32_full[sb], 32768u);
         if (P.l2_stream_hint) tma_load_2d_hint(f32_stage + sb * 32768, &x_map, &bar_f32_full[sb], slab * 64, tile * 128, pol);
@@ -470,7 +494,18 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 0) SC_TRACE(P, 6, i, 2);
-      if (tid == 0) {
+      if (P.quad_major) {
+        // one 32-byte sector per (image of the tile, quad of modes): element (image, m) lives at ((m >> 2) * n_images + image) * 4 + (m & 3)
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int nq = P.Mt >> 2;
+        for (int idx = tid; idx < P.G * nq; idx += 128) {
+          const int g = idx / nq, q = idx - g * nq;
+          const float4* sp = reinterpret_cast<const float4*>(stage + g * P.Mt + 4 * q);
+          const float4 lo4 = sp[0], hi4 = sp[1];
+          const float o8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+          st_global_v8(reinterpret_cast<float*>(P.out + ((long long)q * P.n_images + (long long)tile * P.G + g) * 4), o8);
+        }
+      } else if (tid == 0) {
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         bulk_store(P.out + (size_t)tile * P.QROWS * KX, stage, (uint32_t)(P.QROWS * KX * 8));
         bulk_commit();
@@ -509,15 +544,11 @@ struct SynParams {
   int n_tiles, W, KX, QROWS, H, n_channels, tmem_cols;
   int l2_stream_hint;      // 1: the image rows are stored with an L2 evict-first policy (written once, not re-read by this step)
   int slices_per_image;    // 3-D: the fused kernel sees (image, z) slices; bias channel = (slice / slices_per_image) % n_channels
+  int quad_major, KY;      // 1: the modes arrive in the quad-major layout modes[quad][image][4 modes] (see AnaParams)
+  long long n_images;
   uint32_t off_aa, off_ba, off_u, off_bb, off_stage;
   long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
 };
-
-__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-               : "memory");
-}
 
 template <int N1>
 __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynParams P, const __grid_constant__ CUtensorMap out_map) {
@@ -579,11 +610,17 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       const int buf = i & 1;
       const int tile = (int)blockIdx.x + i * (int)gridDim.x;
       const float2* src = P.modes + ((size_t)tile * P.QROWS + q) * KX + kx0;
+      long long ustep = 4;
+      if (P.quad_major) {
+        const int g = q / P.KY, mbase = (q - g * P.KY) * KX + kx0;      // image of the tile, first mode of this thread's column set
+        src = P.modes + ((long long)(mbase >> 2) * P.n_images + (long long)tile * (P.QROWS / P.KY) + g) * 4 + (mbase & 3);
+        ustep = P.n_images * 4;
+      }
       float2 y[8];
       if (warp == 10) SC_TRACE(P, 0, i, 0);
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        if (q_ok && kx0 + 4 * u < KX) y[u] = __ldg(src + 4 * u);
+        if (q_ok && kx0 + 4 * u < KX) y[u] = __ldg(src + u * ustep);
       mbar_wait(&bar_ba_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
       if (warp == 10) SC_TRACE(P, 0, i, 1);
       uint8_t* ba = s_ba + buf * BA_BYTES;
@@ -1207,12 +1244,19 @@ constexpr uint32_t MQ2_TM_A = 256;              // D of mode j at column 64 j; A
 struct ModeGemmQuad2Params {
   const float2* a; const float2* b; float2* out;
   long long sAR, sAK, sBN, sBK, sOR, sON;       // complex-element strides
+  long long sAQ, sBQ, sOQ;                      // stride between quads: 4 in the standard (.., modes) layout; the quad-major layout
+                                                // [quad][..][4 modes] of the internal mode tensors has its own (see sc_api.cu)
+  int b_map;                                    // B loader lanes: 0 along k (k contiguous or nothing is), 1 along 8 rows x 4 k (rows contiguous)
   int MR, NB, KC;                               // full extents (rows of A, rows of B, contraction length)
   int n_tiles;                                  // 64-column tiles (gridDim.y = m_tiles * n_tiles)
   int KCp, kshift;                              // B loader mapping: min(KC, 32) rounded up to a power of two (>= 8)
   int conjA, a_early, b_early;                  // *_early: the operand is not written by the previous kernel of the stream
+  int l2_prefetch;                              // 1: issue L2 prefetches ahead of the loads (operands expected in DRAM).  Off inside the
+                                                // dense chains: their operands are L2-resident (fresh, or pulled in by the analysis
+                                                // launch), and every prefetch costs an L1 wavefront per 32-byte sector like a load
   // fused bias gradient (dweight launch): dbias[o] = bias_scale * sum_b Re gm[b, o, dc]
-  const float2* bias_gm; float* dbias; int bias_B, bias_Co, dc_slot; long long bias_Mt; float bias_scale;
+  const float2* bias_gm; float* dbias; int bias_B, bias_Co, dc_quad; long long bias_sB, bias_sO; float bias_scale;   // bias_gm points at (b=0, o=0, DC)
+  long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE, -DSC_TRACE_QUAD builds only), else nullptr
 };
 
 __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGemmQuad2Params P) {
@@ -1226,7 +1270,8 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
   const int NBp = (NB + 15) & ~15;
   const int KC = P.KC;
   const int n_chunks = (KC + 7) >> 3, n_slabs = (KC + 31) >> 5;
-  const long long m0 = (long long)blockIdx.x * 4;      // first mode of this CTA's quad
+  const long long qd = (long long)blockIdx.x;          // this CTA's quad of modes
+  if (tid == 128) SC_QTRACE(P, 0, 0, 0);
 
   if (tid == 0) {
     for (int i = 0; i < MQ2_A_SLOTS; ++i) { mbar_init(&bar_a_full[i], MQ2_A_WARPS); mbar_init(&bar_a_empty[i], 1); }
@@ -1245,20 +1290,24 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_slot;
+  if (tid == 128) SC_QTRACE(P, 0, 0, 1);
 
   if (warp >= 4 + MQ2_A_WARPS) {
     // ------------------------------------------------------------------ B loaders: global -> registers -> bf16 hi / lo -> swizzled smem
     const int lt = tid - (4 + MQ2_A_WARPS) * 32;
-    const int kq = lt & (P.KCp - 1);                   // k within the 32-complex slab
-    const int r0 = lt >> P.kshift;
-    const int step = (MQ2_B_WARPS * 32) >> P.kshift;    // 8, 16 or 32 rows between a thread's elements
+    // lanes along k (32 consecutive k of one row: coalesced when k is the contiguous index) or 8 rows x 4 k per warp
+    // (coalesced when the row is); either way a warp's swizzled stores touch 32 distinct banks
+    const int kq = P.b_map ? (((lt >> 5) << 2) | ((lt >> 3) & 3)) : (lt & (P.KCp - 1));   // k within the 32-complex slab
+    const int r0 = P.b_map ? (lt & 7) : (lt >> P.kshift);
+    const int step = P.b_map ? 8 : ((MQ2_B_WARPS * 32) >> P.kshift);    // 8, 16 or 32 rows between a thread's elements
     const uint32_t off_hi = (uint32_t)(r0 * 128 + ((((2 * kq) >> 3) ^ r0) & 7) * 16 + ((2 * kq) & 7) * 2);
     const uint32_t off_lo = off_hi + (uint32_t)NBp * 128u;
     const uint32_t sstep = (uint32_t)step * 128u;
-    const float2* base = P.b + m0 + (long long)(64 * nt + r0) * P.sBN;
+    const float2* base = P.b + qd * P.sBQ + (long long)(64 * nt + r0) * P.sBN;
     if (!P.b_early) pdl_wait();
     for (int rd = 0; rd < n_slabs; ++rd) {
       const int slot = rd % MQ2_B_SLOTS;
+      if (lt < 32) SC_QTRACE(P, 1, rd, 0);
       const int k = rd * 32 + kq;
       const bool k_in = kq < 32 && k < ((KC + 7) & ~7);    // inside the K range the MMAs read
       const bool k_ok = k_in && k < KC;                    // real data (else: explicit zeros)
@@ -1276,13 +1325,15 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
           }
         }
         if (bt == 0) {
+          if (P.l2_prefetch) {
 #pragma unroll
-          for (int u = 4; u < 8; ++u)
-            if (k_ok && r0 + u * step < NB) prefetch_l2(pk + (long long)u * step * P.sBN);
-          if (rd + 1 < n_slabs && kq < 32 && k + 32 < KC) {
+            for (int u = 4; u < 8; ++u)
+              if (k_ok && r0 + u * step < NB) prefetch_l2(pk + (long long)u * step * P.sBN);
+            if (rd + 1 < n_slabs && kq < 32 && k + 32 < KC) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (r0 + u * step < NB) prefetch_l2(pk + 32 * P.sBK + (long long)u * step * P.sBN);
+              for (int u = 0; u < 8; ++u)
+                if (r0 + u * step < NB) prefetch_l2(pk + 32 * P.sBK + (long long)u * step * P.sBN);
+            }
           }
           if (rd >= MQ2_B_SLOTS) mbar_wait(&bar_b_empty[slot], (uint32_t)(((rd / MQ2_B_SLOTS) - 1) & 1));
         }
@@ -1300,6 +1351,7 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
             }
           }
         }
+        if (lt < 32) SC_QTRACE(P, 1, rd, 1 + bt);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -1312,13 +1364,14 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
     const int aw = warp - 4, q = aw & 3, g = aw >> 2;
     const int row = 32 * q + lane, R = row >> 1, part = row & 1;
     const bool r_ok = R < MR;
-    const float2* pa = P.a + m0 + (long long)(64 * mt + R) * P.sAR + (long long)(4 * g) * P.sAK;
+    const float2* pa = P.a + qd * P.sAQ + (long long)(64 * mt + R) * P.sAR + (long long)(4 * g) * P.sAK;
     const uint32_t tm_mine = tmem + MQ2_TM_A + ((uint32_t)(32 * q) << 16) + (uint32_t)(4 * g);
     // sign / order of the packed (first K element | second K element << 16) pair for this row
     //   part 0: (re, -im)   conj: (re, im)        part 1: (im, re)   conj: (-im, re)
     const uint32_t flip = part == 0 ? (P.conjA ? 0u : 0x80000000u) : (P.conjA ? 0x00008000u : 0u);
     const uint32_t perm = part == 0 ? 0x3210u : 0x1032u;
     if (!P.a_early) pdl_wait();
+    if (aw == 0) SC_QTRACE(P, 0, 0, 2);
     float v0[4][8], v1[4][8];
     auto issue = [&](float (&buf)[4][8], int c) {
 #pragma unroll
@@ -1332,6 +1385,7 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
     };
     auto consume = [&](float (&buf)[4][8], int c) {
       const int s = c % MQ2_A_SLOTS;
+      if (aw == 0) SC_QTRACE(P, 0, 1 + c, 0);
       if (c >= MQ2_A_SLOTS) {
         mbar_wait(&bar_a_empty[s], (uint32_t)(((c / MQ2_A_SLOTS) - 1) & 1));
         tc_fence_after_sync();
@@ -1348,15 +1402,17 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
         }
         tmem_st4(tm_mine + (uint32_t)(64 * s + 16 * j), hw[0], hw[1], hw[2], hw[3]);
         tmem_st4(tm_mine + (uint32_t)(64 * s + 16 * j + 8), lw[0], lw[1], lw[2], lw[3]);
+        if (j == 0 && aw == 0) SC_QTRACE(P, 0, 1 + c, 1);
       }
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_a_full[s]);
+      if (aw == 0) SC_QTRACE(P, 0, 1 + c, 2);
     };
     issue(v0, 0);
     if (n_chunks > 1) issue(v1, 1);
-    if (r_ok) {
+    if (r_ok && P.l2_prefetch) {
       for (int c = 2; c < n_chunks && c < 10; ++c)
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -1369,7 +1425,7 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
         consume(v1, c + 1);
         if (c + 3 < n_chunks) issue(v1, c + 3);
       }
-      if (r_ok && c + 10 < n_chunks) {
+      if (r_ok && P.l2_prefetch && c + 10 < n_chunks) {
 #pragma unroll
         for (int cc = c + 10; cc < c + 12; ++cc)
 #pragma unroll
@@ -1388,6 +1444,7 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
         if ((c & 3) == 0) mbar_wait(&bar_b_full[bslot], (uint32_t)((slab / MQ2_B_SLOTS) & 1));
         mbar_wait(&bar_a_full[s], (uint32_t)((c / MQ2_A_SLOTS) & 1));
         tc_fence_after_sync();
+        SC_QTRACE(P, 2, c, 0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const uint32_t a_hi = tmem + MQ2_TM_A + (uint32_t)(64 * s + 16 * j), a_lo = a_hi + 8;
@@ -1399,6 +1456,7 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
         }
         mma_commit(&bar_a_empty[s]);
         if ((c & 3) == 3 || c == n_chunks - 1) mma_commit(&bar_b_empty[bslot]);
+        SC_QTRACE(P, 2, c, 1);
       }
       mma_commit(&bar_d_full);
     }
@@ -1410,12 +1468,12 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
     pdl_wait();
     pdl_launch_dependents();
   }
-  if (warp >= 1 && warp < 4 && P.dbias != nullptr && blockIdx.y == 0 && (long long)P.dc_slot >= m0 && (long long)P.dc_slot < m0 + 4) {
+  if (warp >= 1 && warp < 4 && P.dbias != nullptr && blockIdx.y == 0 && (int)blockIdx.x == P.dc_quad) {
     // fused bias gradient: dbias[o] = sum_b Re gm[b, o, DC] / synthesis scale (the DC slot of gm is the plain sum of gy)
     pdl_wait();
     for (int o = warp - 1; o < P.bias_Co; o += 3) {
       float sum = 0.f;
-      for (int bb = lane; bb < P.bias_B; bb += 32) sum += __ldg(&P.bias_gm[((long long)bb * P.bias_Co + o) * P.bias_Mt + P.dc_slot].x);
+      for (int bb = lane; bb < P.bias_B; bb += 32) sum += __ldg(&P.bias_gm[(long long)bb * P.bias_sB + (long long)o * P.bias_sO].x);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
       if (lane == 0) P.dbias[o] = sum * P.bias_scale;
@@ -1429,9 +1487,11 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
     const int R = row >> 1, part = row & 1;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     pdl_wait();                                        // the output buffer may still be read by the previous kernel
+    if (warp == 2) SC_QTRACE(P, 3, 0, 0);
     mbar_wait(&bar_d_full, 0);
     tc_fence_after_sync();
-    float2* dst = P.out + m0 + (long long)(64 * mt + R) * P.sOR + (long long)(64 * nt) * P.sON;
+    if (warp == 2) SC_QTRACE(P, 3, 0, 1);
+    float2* dst = P.out + qd * P.sOQ + (long long)(64 * mt + R) * P.sOR + (long long)(64 * nt) * P.sON;
     for (int c = 8 * grp; c < NBp; c += 8 * (MQ2_THREADS / 128)) {
       float acc[4][8];
 #pragma unroll
@@ -1451,8 +1511,301 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
       }
     }
     tc_fence_before_sync();
+    if (warp == 2) SC_QTRACE(P, 3, 0, 2);
   }
   __syncthreads();
+  if (warp == 2) SC_QTRACE(P, 3, 1, 0);
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =====================================================================================================
+// mode-wise complex GEMM, four consecutive modes per CTA, third generation ("quad3"): quad2 fed by the TMA engine
+//
+//   Measured on quad2 (B200, round 2): its 256-bit loads of scattered 32-byte sectors complete at ~13-20 B/clk per SM -- the
+//   LSU tracks each sector as its own request and the kernel spends ~15 000 of its ~21 000 cycles waiting for them --, whereas
+//   4-D tensor loads with a {8 floats, 1 quad, 64 rows, 8 k} box gather the same sectors at 28 B/clk per SM with every box in
+//   flight at once, no registers and no issue slots (sc_probe_tma_gather).  So here one producer lane streams both operands
+//   into raw fp32 rings in shared memory and the converter warps only move shared memory -> registers -> tensor memory (A) /
+//   swizzled bf16 tiles (B).  Tensor-memory ring, MMA issue and epilogue are quad2's.  K <= 64 (B tiles resident).
+//   warp 0 MMA issue (+TMEM), warp 1 TMA producer + dependency hand-over, warps 2-3 fused bias gradient,
+//   warps 4-11 A converters, 12-19 B converters, all 20 warps epilogue.
+// =====================================================================================================
+constexpr int MQ3_MAX_A_RAW = 8, MQ3_MAX_B_RAW = 2;
+constexpr int MQ3_CONV_WARPS = 16;                      // warps 4-19 convert both operands (B slab first, then its A chunks)
+constexpr uint32_t MQ3_A_RAW_BYTES = 8 * 64 * 32;      // one chunk: [8 k][64 rows][4 modes x (re, im)]
+
+struct ModeGemmQuad3Params {
+  float2* out;
+  long long sOR, sON, sOQ;                      // complex-element strides of the output (row, column, quad)
+  int MR, NB, KC;                               // full extents
+  int n_tiles;                                  // 64-column tiles (gridDim.y = m_tiles * n_tiles)
+  int conjA, a_early, b_early;
+  int n_a_raw, n_b_raw, b_box_rows;             // ring depths; rows of one B box (<= 64)
+  // How the operands reach shared memory (chosen on the host from the strides):
+  //   0  sectors scattered in memory: 4-D box {8 floats, 1 quad, rows, k}, one 32-byte request per sector; raw block [k][rows][32 B]
+  //   1  (B only) k is the contiguous index (quad-major xm / gm as the B operand of the forward / dxm products): 3-D box
+  //      {256 floats = 32 k, rows, 1 quad}, one 1 KB request per row; raw block [row][k][32 B]
+  //   2  the row is the contiguous index (quad-major operands of the dweight product): 3-D boxes {256 floats = 32 rows, k, 1 quad},
+  //      one 1 KB request per k and row half; raw block [row half][k][32 rows][32 B]
+  int a_variant, b_variant;
+  uint32_t tile_b_bytes, off_a_raw, off_b_raw, b_raw_bytes;
+  const float2* bias_gm; float* dbias; int bias_B, bias_Co, dc_quad; long long bias_sB, bias_sO; float bias_scale;
+  long long* trace;
+};
+
+__global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad3(const ModeGemmQuad3Params P, const __grid_constant__ CUtensorMap a_map,
+                                                                      const __grid_constant__ CUtensorMap b_map) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar_a_full[MQ2_A_SLOTS], bar_a_empty[MQ2_A_SLOTS], bar_b_full[2], bar_d_full;
+  __shared__ uint64_t bar_ar_full[MQ3_MAX_A_RAW], bar_ar_empty[MQ3_MAX_A_RAW], bar_br_full[MQ3_MAX_B_RAW], bar_br_empty[MQ3_MAX_B_RAW];
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mt = (int)blockIdx.y / P.n_tiles, nt = (int)blockIdx.y % P.n_tiles;
+  const int MR = min(64, P.MR - 64 * mt), NB = min(64, P.NB - 64 * nt);
+  const int NBp = (NB + 15) & ~15;
+  const int KC = P.KC;
+  const int n_chunks = (KC + 7) >> 3, n_slabs = (KC + 31) >> 5;
+  const int qd = (int)blockIdx.x;
+  const int NA = P.n_a_raw, NBR = P.n_b_raw;
+  if (tid == 128) SC_QTRACE(P, 0, 0, 0);
+
+  if (tid == 0) {
+    for (int i = 0; i < MQ2_A_SLOTS; ++i) { mbar_init(&bar_a_full[i], MQ3_CONV_WARPS); mbar_init(&bar_a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_b_full[i], MQ3_CONV_WARPS);
+    for (int i = 0; i < NA; ++i) { mbar_init(&bar_ar_full[i], 1); mbar_init(&bar_ar_empty[i], MQ3_CONV_WARPS); }
+    for (int i = 0; i < NBR; ++i) { mbar_init(&bar_br_full[i], 1); mbar_init(&bar_br_empty[i], MQ3_CONV_WARPS); }
+    mbar_init(&bar_d_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
+  if (NB < NBp) {   // padding rows of the B tiles must hold finite values (zeros)
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = (int)((uint32_t)(n_slabs * 4) * P.tile_b_bytes / 16);
+    for (int i = tid; i < n16; i += MQ2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  if (tid == 128) SC_QTRACE(P, 0, 0, 1);
+
+  if (warp == 1) {
+    // ------------------------------------------------------------------ TMA producer (one lane) + dependency hand-over
+    if (lane == 0) {
+      uint8_t* a_raw = smem + P.off_a_raw;
+      uint8_t* b_raw = smem + P.off_b_raw;
+      int ia = 0, ib = 0;
+      auto issue_a = [&](int c) {
+        const int slot = c % NA;
+        if (c >= NA) mbar_wait(&bar_ar_empty[slot], (uint32_t)(((c / NA) - 1) & 1));
+        mbar_arrive_expect_tx(&bar_ar_full[slot], MQ3_A_RAW_BYTES);
+        uint8_t* dst = a_raw + (size_t)slot * MQ3_A_RAW_BYTES;
+        if (P.a_variant == 2) {
+          tma_load_3d(dst, &a_map, &bar_ar_full[slot], 8 * 64 * mt, 8 * c, qd);
+          tma_load_3d(dst + MQ3_A_RAW_BYTES / 2, &a_map, &bar_ar_full[slot], 8 * (64 * mt + 32), 8 * c, qd);
+        } else {
+          tma_load_4d(dst, &a_map, &bar_ar_full[slot], 0, qd, 64 * mt, 8 * c);
+        }
+      };
+      auto issue_b = [&](int s) {
+        const int slot = s % NBR;
+        if (s >= NBR) mbar_wait(&bar_br_empty[slot], (uint32_t)(((s / NBR) - 1) & 1));
+        mbar_arrive_expect_tx(&bar_br_full[slot], P.b_raw_bytes);
+        uint8_t* dst = b_raw + (size_t)slot * P.b_raw_bytes;
+        if (P.b_variant == 1) {
+          tma_load_3d(dst, &b_map, &bar_br_full[slot], 8 * 32 * s, 64 * nt, qd);
+        } else if (P.b_variant == 2) {
+          tma_load_3d(dst, &b_map, &bar_br_full[slot], 8 * 64 * nt, 32 * s, qd);
+          if (P.b_box_rows > 32) tma_load_3d(dst + 32768, &b_map, &bar_br_full[slot], 8 * (64 * nt + 32), 32 * s, qd);
+        } else {
+          tma_load_4d(dst, &b_map, &bar_br_full[slot], 0, qd, 64 * nt, 32 * s);
+        }
+      };
+      // Consumption order: B slab s, then its A chunks 4s .. 4s+3.  Operands the previous kernel of the stream does not write
+      // may be fetched ahead of the dependency wait -- at most two A chunks, so that they do not sit in the TMA queue in front of
+      // the B slab the first MMA waits for.
+      if (P.b_early) issue_b(ib++);
+      if (P.a_early) while (ia < n_chunks && ia < 2) issue_a(ia++);
+      pdl_wait();
+      pdl_launch_dependents();   // (after the wait: see k_fused_analysis)
+      SC_QTRACE(P, 0, 0, 2);
+      while (ia < n_chunks || ib < n_slabs) {
+        if (ib < n_slabs && 4 * ib <= ia) issue_b(ib++);
+        else if (ia < n_chunks) issue_a(ia++);
+        else issue_b(ib++);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ converters (16 warps): per K-slab, B raw -> bf16 hi / lo ->
+    // swizzled tiles, then the slab's four A chunks raw -> bf16 hi / lo -> tensor memory
+    const int cw = warp - 4;
+    // B: a warp covers 8 rows x 4 k (256 contiguous raw bytes per quarter-warp, 32 distinct banks on the swizzled side);
+    //    warps 0-7 take rows 0-31, warps 8-15 rows 32-63
+    //    (k-contiguous raw blocks, variant 1: a warp covers the 32 k of one row instead -- 1 KB contiguous, one swizzled tile row)
+    const bool bk = P.b_variant == 1;
+    const int nlo = bk ? (cw & 7) : (lane & 7), kqb = bk ? lane : (((cw & 7) << 2) | (lane >> 3)), rhalf = cw >> 3;
+    const uint32_t off_hi = (uint32_t)(nlo * 128 + ((((2 * kqb) >> 3) ^ nlo) & 7) * 16 + ((2 * kqb) & 7) * 2);
+    const uint32_t off_lo = off_hi + (uint32_t)NBp * 128u;
+    const int rows = P.b_box_rows;
+    // raw address of element (row nlo + 8 u + 32 rhalf, k kqb) = b_src0 + u * b_ustep
+    const uint32_t b_src0 = bk ? (uint32_t)((nlo + 32 * rhalf) * 1024 + kqb * 32)
+                               : (P.b_variant == 2 ? (uint32_t)(rhalf * 32768 + kqb * (rows < 32 ? rows : 32) * 32 + nlo * 32)
+                                                   : (uint32_t)((kqb * rows + nlo + 32 * rhalf) * 32));
+    const uint32_t b_ustep = bk ? 8192u : 256u;
+    // A: thread <-> real row (lane of TMEM quarter q) and 2 of the 8 k of every chunk
+    const int q = cw & 3, g = cw >> 2;
+    const int row = 32 * q + lane, R = row >> 1, part = row & 1;
+    const uint32_t tm_mine = tmem + MQ2_TM_A + ((uint32_t)(32 * q) << 16) + (uint32_t)(2 * g);
+    //   part 0: (re, -im)   conj: (re, im)        part 1: (im, re)   conj: (-im, re)
+    const uint32_t flip = part == 0 ? (P.conjA ? 0u : 0x80000000u) : (P.conjA ? 0x00008000u : 0u);
+    const uint32_t perm = part == 0 ? 0x3210u : 0x1032u;
+    // raw address of (row R, k 2 g + u) = my_raw + u * a_ustep
+    const uint32_t my_raw = P.a_variant == 2 ? (uint32_t)((R >> 5) * (MQ3_A_RAW_BYTES / 2) + 2 * g * 1024 + (R & 31) * 32)
+                                             : (uint32_t)((2 * g * 64 + R) * 32);
+    const uint32_t a_ustep = P.a_variant == 2 ? 1024u : 2048u;
+    for (int s = 0; s < n_slabs; ++s) {
+      {
+        const int slot = s % NBR;
+        if (cw == 0) SC_QTRACE(P, 1, s, 0);
+        mbar_wait(&bar_br_full[slot], (uint32_t)((s / NBR) & 1));
+        if (cw == 0) SC_QTRACE(P, 1, s, 1);
+        const uint8_t* src = smem + P.off_b_raw + (size_t)slot * P.b_raw_bytes + b_src0;
+        uint8_t* tile = smem + (size_t)(s * 4) * P.tile_b_bytes + rhalf * 4096;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = nlo + 8 * u + 32 * rhalf;
+          if (n < NB) {
+            const float4 lo4 = *reinterpret_cast<const float4*>(src + u * b_ustep), hi4 = *reinterpret_cast<const float4*>(src + u * b_ustep + 16);
+            const float v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hi, lo;
+              split2_bf16(v[2 * j], v[2 * j + 1], hi, lo);
+              *reinterpret_cast<uint32_t*>(tile + j * P.tile_b_bytes + off_hi + u * 1024) = hi;
+              *reinterpret_cast<uint32_t*>(tile + j * P.tile_b_bytes + off_lo + u * 1024) = lo;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&bar_br_empty[slot]); mbar_arrive(&bar_b_full[s]); }
+        if (cw == 0) SC_QTRACE(P, 1, s, 2);
+      }
+      const int c_end = min(n_chunks, 4 * s + 4);
+      for (int c = 4 * s; c < c_end; ++c) {
+        const int rs = c % NA, ts = c % MQ2_A_SLOTS;
+        if (cw == 0) SC_QTRACE(P, 0, 1 + c, 0);
+        mbar_wait(&bar_ar_full[rs], (uint32_t)((c / NA) & 1));
+        if (cw == 0) SC_QTRACE(P, 0, 1 + c, 1);
+        const uint8_t* src = smem + P.off_a_raw + (size_t)rs * MQ3_A_RAW_BYTES + my_raw;
+        uint32_t hw[4][2], lw[4][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float4 lo4 = *reinterpret_cast<const float4*>(src + u * a_ustep), hi4 = *reinterpret_cast<const float4*>(src + u * a_ustep + 16);
+          const float v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t hi, lo;
+            split2_bf16(v[2 * j], v[2 * j + 1], hi, lo);      // (re | im << 16)
+            hw[j][u] = __byte_perm(hi, 0, perm) ^ flip;
+            lw[j][u] = __byte_perm(lo, 0, perm) ^ flip;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_ar_empty[rs]);       // the raw chunk has been consumed into registers
+        if (c >= MQ2_A_SLOTS) {
+          mbar_wait(&bar_a_empty[ts], (uint32_t)(((c / MQ2_A_SLOTS) - 1) & 1));
+          tc_fence_after_sync();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          tmem_st2(tm_mine + (uint32_t)(64 * ts + 16 * j), hw[j][0], hw[j][1]);
+          tmem_st2(tm_mine + (uint32_t)(64 * ts + 16 * j + 8), lw[j][0], lw[j][1]);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_a_full[ts]);
+        if (cw == 0) SC_QTRACE(P, 0, 1 + c, 2);
+      }
+    }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issue (one lane)
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16(128, NBp);
+      const uint32_t base_lo = desc_lo(smem_u32(smem));
+      const uint32_t lo_rows = ((uint32_t)NBp * 128u) >> 4;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c % MQ2_A_SLOTS, slab = c >> 2;
+        if ((c & 3) == 0) mbar_wait(&bar_b_full[slab], 0);
+        mbar_wait(&bar_a_full[s], (uint32_t)((c / MQ2_A_SLOTS) & 1));
+        tc_fence_after_sync();
+        SC_QTRACE(P, 2, c, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a_hi = tmem + MQ2_TM_A + (uint32_t)(64 * s + 16 * j), a_lo = a_hi + 8;
+          const uint32_t b_hi = base_lo + (uint32_t)(slab * 4 + j) * (P.tile_b_bytes >> 4) + 2 * (uint32_t)(c & 3);
+          const uint32_t d = tmem + (uint32_t)(64 * j);
+          mma_bf16_ts(d, a_hi, desc_from_lo(b_hi), idesc, c > 0);
+          mma_bf16_ts(d, a_hi, desc_from_lo(b_hi + lo_rows), idesc, true);
+          mma_bf16_ts(d, a_lo, desc_from_lo(b_hi), idesc, true);
+        }
+        mma_commit(&bar_a_empty[s]);
+        SC_QTRACE(P, 2, c, 1);
+      }
+      mma_commit(&bar_d_full);
+    }
+    __syncwarp();
+  } else if (P.dbias != nullptr && blockIdx.y == 0 && (int)blockIdx.x == P.dc_quad) {
+    // ------------------------------------------------------------------ warps 2-3: fused bias gradient
+    pdl_wait();
+    for (int o = warp - 2; o < P.bias_Co; o += 2) {
+      float sum = 0.f;
+      for (int bb = lane; bb < P.bias_B; bb += 32) sum += __ldg(&P.bias_gm[(long long)bb * P.bias_sB + (long long)o * P.bias_sO].x);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+      if (lane == 0) P.dbias[o] = sum * P.bias_scale;
+    }
+  }
+  __syncwarp();
+  {
+    // ------------------------------------------------------------------ epilogue, ALL warps: four modes -> one 32-byte store
+    const int q = warp & 3, grp = warp >> 2;
+    const int row = q * 32 + lane;
+    const int R = row >> 1, part = row & 1;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    pdl_wait();                                        // the output buffer may still be read by the previous kernel
+    if (warp == 2) SC_QTRACE(P, 3, 0, 0);
+    mbar_wait(&bar_d_full, 0);
+    tc_fence_after_sync();
+    if (warp == 2) SC_QTRACE(P, 3, 0, 1);
+    float2* dst = P.out + (long long)qd * P.sOQ + (long long)(64 * mt + R) * P.sOR + (long long)(64 * nt) * P.sON;
+    for (int c = 8 * grp; c < NBp; c += 8 * (MQ2_THREADS / 128)) {
+      float acc[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tmem_ld8(tmem + lane_sel + (uint32_t)(j * 64 + c), acc[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mine = acc[j][e];
+          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          o[2 * j] = mine; o[2 * j + 1] = other;      // (re, im) on even lanes
+        }
+        const int n = c + e;
+        if (part == 0 && R < MR && n < NB) st_global_v8(reinterpret_cast<float*>(dst + (long long)n * P.sON), o);
+      }
+    }
+    tc_fence_before_sync();
+    if (warp == 2) SC_QTRACE(P, 3, 0, 2);
+  }
+  __syncthreads();
+  if (warp == 2) SC_QTRACE(P, 3, 1, 0);
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -1525,23 +1878,142 @@ static bool launch_mode_gemm_quad2(const Plan* p, const float2* a, long long sAR
   const int kc_round = KC < 32 ? KC : 32;
   while (P.KCp < kc_round) { P.KCp *= 2; ++P.kshift; }
   P.conjA = conjA ? 1 : 0;
+  P.sAQ = P.sBQ = P.sOQ = 4;
+  P.l2_prefetch = 1;
   if (ex != nullptr) {
     P.a_early = ex->a_early ? 1 : 0; P.b_early = ex->b_early ? 1 : 0;
+    P.l2_prefetch = ex->l2_resident ? 0 : 1;
+    if (ex->sAQ) P.sAQ = ex->sAQ;
+    if (ex->sBQ) P.sBQ = ex->sBQ;
+    if (ex->sOQ) P.sOQ = ex->sOQ;
     if (ex->dbias != nullptr) {
-      P.bias_gm = ex->bias_gm; P.dbias = ex->dbias; P.bias_B = ex->bias_B; P.bias_Co = ex->bias_Co;
-      P.bias_Mt = n_modes; P.dc_slot = p->dc_slot; P.bias_scale = ex->bias_scale;
+      // gm is the B operand of the dweight product: rows n = o, k = b
+      P.bias_gm = b + (long long)(p->dc_slot >> 2) * P.sBQ + (p->dc_slot & 3);
+      P.bias_sB = sBK; P.bias_sO = sBN;
+      P.dbias = ex->dbias; P.bias_B = KC; P.bias_Co = NB; P.dc_quad = p->dc_slot >> 2; P.bias_scale = ex->bias_scale;
     }
   }
+  P.b_map = (sBN < sBK) ? 1 : 0;
   const uint32_t smem_bytes = MQ2_B_SLOTS * MQ2_SLAB_BYTES + 1024u;
   static SmemOptIn opt_in;
   if (!ensure_dynamic_smem((const void*)k_mode_gemm_quad2, opt_in, p->device, smem_bytes, "cudaFuncSetAttribute(k_mode_gemm_quad2)"))
     return false;
   count_launch();
+#ifdef SC_TRACE_QUAD
+  P.trace = trace_begin();
+#endif
   void* args[] = {(void*)&P};
-  return cuda_ok(launch_pdl((const void*)k_mode_gemm_quad2, dim3((unsigned)(n_modes / 4), (unsigned)(m_tiles * P.n_tiles)),
-                            dim3(MQ2_THREADS), smem_bytes, st, args),
-                 "k_mode_gemm_quad2 launch");
+  const bool ok = cuda_ok(launch_pdl((const void*)k_mode_gemm_quad2, dim3((unsigned)(n_modes / 4), (unsigned)(m_tiles * P.n_tiles)),
+                                     dim3(MQ2_THREADS), smem_bytes, st, args),
+                          "k_mode_gemm_quad2 launch");
+#ifdef SC_TRACE_QUAD
+  trace_end(P.trace, conjA ? (sBN < sBK ? "quad2 dweight" : "quad2 dxm") : "quad2 fwd");
+#endif
+  return ok;
 }
+
+static bool make_sector_gather_map(CUtensorMap* map, const float2* base, uint64_t n_quads, uint64_t n_rows, uint64_t n_k,
+                                   uint64_t stride_quad_bytes, uint64_t stride_row_bytes, uint64_t stride_k_bytes, uint32_t box_rows,
+                                   uint32_t box_k);
+
+static bool cached_gather_map(const Plan* p, const float2* base, uint64_t nq, uint64_t rows, uint64_t k, uint64_t sq, uint64_t sr,
+                              uint64_t sk, uint32_t box_rows, uint32_t box_k, CUtensorMap* out);
+
+static bool cached_wide_map(const Plan* p, const float2* base, uint64_t inner_floats, uint64_t n_second, uint64_t nq, uint64_t stride_second_bytes,
+                            uint64_t stride_quad_bytes, uint32_t box_inner, uint32_t box_second, CUtensorMap* out);
+// SC_WIDE_BOXES=0: every operand through the 32-byte-sector gather boxes (A/B runs)
+static bool wide_boxes_enabled() {
+  static const bool v = [] { const char* e = getenv("SC_WIDE_BOXES"); return e == nullptr || atoi(e) != 0; }();
+  return v;
+}
+// SC_QUAD3=0 keeps the LSU-fed quad2 kernel (A/B runs)
+static bool quad3_enabled() {
+  static const bool v = [] { const char* e = getenv("SC_QUAD3"); return e == nullptr || atoi(e) != 0; }();
+  return v;
+}
+
+// returns false with *handled = false when the shape does not fit the TMA-fed kernel (the caller then runs quad2)
+static bool launch_mode_gemm_quad3(const Plan* p, const float2* a, long long sAR, long long sAK, bool conjA, const float2* b,
+                                   long long sBN, long long sBK, float2* out, long long sOR, long long sON, int MR, int NB,
+                                   int KC, int64_t n_modes, const ModeGemmExtras* ex, cudaStream_t st, bool* handled) {
+  *handled = false;
+  if (!quad3_enabled() || KC > 64) return true;
+  const long long sAQ = ex != nullptr && ex->sAQ ? ex->sAQ : 4, sBQ = ex != nullptr && ex->sBQ ? ex->sBQ : 4, sOQ = ex != nullptr && ex->sOQ ? ex->sOQ : 4;
+  // tensor-map strides are byte counts that must be multiples of 16 and below 2^40
+  const long long strides[6] = {sAQ, sAR, sAK, sBQ, sBN, sBK};
+  for (long long v : strides) if (v <= 0 || (v & 1) != 0 || v * 8 >= (1ll << 40)) return true;
+  ModeGemmQuad3Params P{};
+  P.out = out; P.sOR = sOR; P.sON = sON; P.sOQ = sOQ;
+  P.MR = MR; P.NB = NB; P.KC = KC;
+  const int m_tiles = (MR + 63) / 64;
+  P.n_tiles = (NB + 63) / 64;
+  P.conjA = conjA ? 1 : 0;
+  const int n_chunks = (KC + 7) / 8, n_slabs = (KC + 31) / 32;
+  const int nb_max = NB < 64 ? NB : 64;
+  P.b_box_rows = nb_max;
+  const uint32_t nbp_max = (uint32_t)((nb_max + 15) / 16 * 16);
+  P.tile_b_bytes = 2u * nbp_max * 128u;
+  P.a_variant = (sAR == 4 && wide_boxes_enabled()) ? 2 : 0;
+  P.b_variant = !wide_boxes_enabled() ? 0 : (sBK == 4 ? 1 : (sBN == 4 ? 2 : 0));
+  P.b_raw_bytes = 32u * (uint32_t)nb_max * 32u;      // one raw K-slab: [32 k][nb_max rows][32 B] = nb_max KB
+  if (P.b_variant == 2 && nb_max > 32) P.b_raw_bytes = 65536u;   // two full 32-row boxes (rows past NB are zero-filled)
+  const uint32_t budget = 227u * 1024u - 2048u;
+  const uint32_t b_tiles = (uint32_t)(n_slabs * 4) * P.tile_b_bytes;
+  P.n_b_raw = n_slabs < 2 ? n_slabs : 2;
+  if (b_tiles + (uint32_t)P.n_b_raw * P.b_raw_bytes + 2u * MQ3_A_RAW_BYTES > budget) P.n_b_raw = 1;
+  if (b_tiles + (uint32_t)P.n_b_raw * P.b_raw_bytes + 2u * MQ3_A_RAW_BYTES > budget) return true;
+  P.off_b_raw = (b_tiles + 1023u) & ~1023u;
+  P.off_a_raw = P.off_b_raw + (uint32_t)P.n_b_raw * P.b_raw_bytes;
+  int na = (int)((budget - P.off_a_raw) / MQ3_A_RAW_BYTES);
+  if (na > n_chunks) na = n_chunks;
+  if (na > MQ3_MAX_A_RAW) na = MQ3_MAX_A_RAW;
+  if (na < 2 && n_chunks > 1) return true;
+  P.n_a_raw = na;
+  const uint32_t smem_bytes = P.off_a_raw + (uint32_t)na * MQ3_A_RAW_BYTES + 1024u;
+  if (ex != nullptr) {
+    P.a_early = ex->a_early ? 1 : 0; P.b_early = ex->b_early ? 1 : 0;
+    if (ex->dbias != nullptr) {
+      P.bias_gm = b + (long long)(p->dc_slot >> 2) * sBQ + (p->dc_slot & 3);
+      P.bias_sB = sBK; P.bias_sO = sBN;
+      P.dbias = ex->dbias; P.bias_B = KC; P.bias_Co = NB; P.dc_quad = p->dc_slot >> 2; P.bias_scale = ex->bias_scale;
+    }
+  }
+  CUtensorMap a_map, b_map;
+  const uint64_t nq = (uint64_t)(n_modes / 4);
+  if (P.a_variant == 2) {   // rows contiguous: {8 * MR floats, KC, quads}, box {256 floats = 32 rows, 8 k, 1}
+    if (!cached_wide_map(p, a, (uint64_t)MR * 8, (uint64_t)KC, nq, (uint64_t)sAK * 8, (uint64_t)sAQ * 8, 256, 8, &a_map)) return false;
+  } else if (!cached_gather_map(p, a, nq, (uint64_t)MR, (uint64_t)KC, (uint64_t)sAQ * 8, (uint64_t)sAR * 8, (uint64_t)sAK * 8, 64, 8, &a_map)) {
+    return false;
+  }
+  if (P.b_variant == 1) {          // k contiguous: {8 * KC floats, NB rows, quads}, box {256 floats = 32 k, rows, 1}
+    if (!cached_wide_map(p, b, (uint64_t)KC * 8, (uint64_t)NB, nq, (uint64_t)sBN * 8, (uint64_t)sBQ * 8, 256, (uint32_t)nb_max, &b_map)) return false;
+  } else if (P.b_variant == 2) {   // rows contiguous: {8 * NB floats, KC, quads}, box {256 floats = 32 rows, 32 k, 1}
+    if (!cached_wide_map(p, b, (uint64_t)NB * 8, (uint64_t)KC, nq, (uint64_t)sBK * 8, (uint64_t)sBQ * 8, (uint32_t)(nb_max < 32 ? nb_max * 8 : 256), 32,
+                         &b_map))
+      return false;
+  } else if (!cached_gather_map(p, b, nq, (uint64_t)NB, (uint64_t)KC, (uint64_t)sBQ * 8, (uint64_t)sBN * 8, (uint64_t)sBK * 8, (uint32_t)nb_max, 32,
+                                &b_map)) {
+    return false;
+  }
+  static SmemOptIn opt_in;
+  if (!ensure_dynamic_smem((const void*)k_mode_gemm_quad3, opt_in, p->device, smem_bytes, "cudaFuncSetAttribute(k_mode_gemm_quad3)"))
+    return false;
+  count_launch();
+#ifdef SC_TRACE_QUAD
+  P.trace = trace_begin();
+#endif
+  void* args[] = {(void*)&P, (void*)&a_map, (void*)&b_map};
+  const bool ok = cuda_ok(launch_pdl((const void*)k_mode_gemm_quad3, dim3((unsigned)(n_modes / 4), (unsigned)(m_tiles * P.n_tiles)),
+                                     dim3(MQ2_THREADS), smem_bytes, st, args),
+                          "k_mode_gemm_quad3 launch");
+#ifdef SC_TRACE_QUAD
+  trace_end(P.trace, conjA ? (sBN < sBK ? "quad3 dweight" : "quad3 dxm") : "quad3 fwd");
+#endif
+  *handled = ok;
+  return ok;
+}
+
+bool quad2_enabled() { return quad_generation() == 2; }
 
 bool mode_gemm_quad_eligible(const Plan* p, int64_t n_modes, const void* a, const void* b, const void* out) {
   return p->fast != nullptr && p->weight_block_is_whole && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out);
@@ -1558,7 +2030,9 @@ bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long lon
   const bool strides4 = ((sAR | sAK | sBN | sBK | sOR | sON) & 3) == 0;
   if (contiguous && strides4 && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out)) {
     if (quad_generation() == 2) {
-      if (!launch_mode_gemm_quad2(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st)) return false;
+      bool handled = false;
+      if (!launch_mode_gemm_quad3(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st, &handled)) return false;
+      if (!handled && !launch_mode_gemm_quad2(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st)) return false;
       if (ex != nullptr && ex->dbias != nullptr) ex->bias_done = true;
       return true;
     }
@@ -1642,7 +2116,10 @@ struct RowsSynTables {
   uint8_t* d_tab = nullptr;
 };
 
+struct GatherMapCacheEntry { const void* base; uint64_t nq, rows, k, sq, sr, sk; uint32_t box_rows, box_k; CUtensorMap map; };
+
 struct FastTables {
+  std::vector<GatherMapCacheEntry> gather_cache;
   std::vector<TensorMapCacheEntry> map_cache;
   std::mutex map_mutex;
   FusedAnalysisTables ana[2];   // [0] forward analysis on `grid`, [1] adjoint-of-synthesis analysis on `out_grid`
@@ -1688,6 +2165,22 @@ static bool cached_map(const Plan* p, int kind, const void* base, uint64_t rows,
   if (!ok) return false;
   if (f->map_cache.size() >= 32) f->map_cache.erase(f->map_cache.begin());
   f->map_cache.push_back(e);
+  *out = e.map;
+  return true;
+}
+
+static bool cached_gather_map(const Plan* p, const float2* base, uint64_t nq, uint64_t rows, uint64_t k, uint64_t sq, uint64_t sr,
+                              uint64_t sk, uint32_t box_rows, uint32_t box_k, CUtensorMap* out) {
+  FastTables* f = p->fast;
+  std::lock_guard<std::mutex> lock(f->map_mutex);
+  for (const GatherMapCacheEntry& e : f->gather_cache)
+    if (e.base == base && e.nq == nq && e.rows == rows && e.k == k && e.sq == sq && e.sr == sr && e.sk == sk && e.box_rows == box_rows &&
+        e.box_k == box_k) { *out = e.map; return true; }
+  if (!thread_has_context()) cudaFree(nullptr);   // (see cached_map)
+  GatherMapCacheEntry e{base, nq, rows, k, sq, sr, sk, box_rows, box_k, {}};
+  if (!make_sector_gather_map(&e.map, base, nq, rows, k, sq, sr, sk, box_rows, box_k)) return false;
+  if (f->gather_cache.size() >= 48) f->gather_cache.erase(f->gather_cache.begin());
+  f->gather_cache.push_back(e);
   *out = e.map;
   return true;
 }
@@ -1934,6 +2427,101 @@ static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t row
   return true;
 }
 
+// 3-D view {contiguous floats, second index, quads} of a quad-major tensor: one request per 1 KB row of the box
+static bool cached_wide_map(const Plan* p, const float2* base, uint64_t inner_floats, uint64_t n_second, uint64_t nq, uint64_t stride_second_bytes,
+                            uint64_t stride_quad_bytes, uint32_t box_inner, uint32_t box_second, CUtensorMap* out) {
+  FastTables* f = p->fast;
+  std::lock_guard<std::mutex> lock(f->map_mutex);
+  // shares the gather cache: rows = inner_floats, k = n_second, sr = 0 marks the 3-D kind
+  for (const GatherMapCacheEntry& e : f->gather_cache)
+    if (e.base == base && e.nq == nq && e.rows == inner_floats && e.k == n_second && e.sq == stride_quad_bytes && e.sr == 0 &&
+        e.sk == stride_second_bytes && e.box_rows == box_inner && e.box_k == box_second) { *out = e.map; return true; }
+  if (!thread_has_context()) cudaFree(nullptr);   // (see cached_map)
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  GatherMapCacheEntry e{base, nq, inner_floats, n_second, stride_quad_bytes, 0, stride_second_bytes, box_inner, box_second, {}};
+  const cuuint64_t dims[3] = {inner_floats, n_second, nq};
+  const cuuint64_t strides[2] = {stride_second_bytes, stride_quad_bytes};
+  const cuuint32_t box[3] = {box_inner, box_second, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (wide rows) failed: CUresult " + std::to_string((int)r)); return false; }
+  if (f->gather_cache.size() >= 48) f->gather_cache.erase(f->gather_cache.begin());
+  f->gather_cache.push_back(e);
+  *out = e.map;
+  return true;
+}
+
+// ---- probe: how fast does the TMA engine gather 32-byte sectors?  One CTA per quad of modes pulls its [Ci x Co x 32 B] block of a
+// (Ci, Co, modes) complex64 tensor into shared memory with 4-D tensor loads (box {8 floats, 1 quad, 64 o, 8 i} = 16 KB), all eight
+// boxes in flight at once; per-CTA cycles (start -> every box landed) go to `cycles_out`.
+__global__ void __launch_bounds__(64) k_tma_gather_probe(const __grid_constant__ CUtensorMap w_map, long long* cycles_out, int n_boxes,
+                                                         int k_per_box) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar[16];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_boxes; ++i) mbar_init(&bar[i], 1);
+    mbar_init_fence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int c = 0; c < n_boxes; ++c) {
+      mbar_arrive_expect_tx(&bar[c], (uint32_t)(k_per_box * 64 * 32));
+      tma_load_4d(smem + (size_t)c * k_per_box * 64 * 32, &w_map, &bar[c], 0, (int)blockIdx.x, 0, c * k_per_box);
+    }
+    const long long t1 = clock64();
+    for (int c = 0; c < n_boxes; ++c) mbar_wait(&bar[c], 0);
+    const long long t2 = clock64();
+    cycles_out[2 * blockIdx.x] = t1 - t0;
+    cycles_out[2 * blockIdx.x + 1] = t2 - t0;
+  }
+}
+
+static bool make_sector_gather_map(CUtensorMap* map, const float2* base, uint64_t n_quads, uint64_t n_rows, uint64_t n_k,
+                                   uint64_t stride_quad_bytes, uint64_t stride_row_bytes, uint64_t stride_k_bytes, uint32_t box_rows,
+                                   uint32_t box_k);
+
+bool tma_gather_probe(const float2* w, int Ci, int Co, int64_t Mt, long long* cycles_out, cudaStream_t st) {
+  if (Mt % 4 != 0 || Ci % 8 != 0 || Ci > 128 || Co != 64) { set_error("tma probe: need Mt % 4 == 0, Co == 64, Ci % 8 == 0, Ci <= 128"); return false; }
+  if (!thread_has_context()) cudaFree(nullptr);
+  CUtensorMap map;
+  if (!make_sector_gather_map(&map, w, (uint64_t)(Mt / 4), (uint64_t)Co, (uint64_t)Ci, 32, (uint64_t)Mt * 8, (uint64_t)Co * Mt * 8, 64, 8))
+    return false;
+  const int n_boxes = Ci / 8;
+  const size_t smem = (size_t)n_boxes * 8 * 64 * 32 + 1024;
+  if (!cuda_ok(cudaFuncSetAttribute(k_tma_gather_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "cudaFuncSetAttribute(k_tma_gather_probe)"))
+    return false;
+  k_tma_gather_probe<<<(unsigned)(Mt / 4), 64, smem, st>>>(map, cycles_out, n_boxes, 8);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_tma_gather_probe launch");
+}
+
+// (quad, row, k) view of a complex64 tensor whose 4 consecutive modes are one 32-byte sector: dims {8 floats, quads, rows, k},
+// box {8, 1, box_rows, box_k}: one tensor load gathers box_rows x box_k sectors into a dense [k][row][8 floats] block
+static bool make_sector_gather_map(CUtensorMap* map, const float2* base, uint64_t n_quads, uint64_t n_rows, uint64_t n_k,
+                                   uint64_t stride_quad_bytes, uint64_t stride_row_bytes, uint64_t stride_k_bytes, uint32_t box_rows,
+                                   uint32_t box_k) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  const cuuint64_t dims[4] = {8, n_quads, n_rows, n_k};
+  const cuuint64_t strides[3] = {stride_quad_bytes, stride_row_bytes, stride_k_bytes};
+  const cuuint32_t box[4] = {8, 1, box_rows, box_k};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (sector gather) failed: CUresult " + std::to_string((int)r));
+    return false;
+  }
+  return true;
+}
+
 // launch with programmatic stream serialization: the kernel may begin (prologue only; see pdl_wait) before the previous
 // kernel of the stream has drained
 static cudaError_t launch_pdl(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
@@ -1981,14 +2569,28 @@ static void trace_end(long long* d, const char* what) {
   fclose(f);
 }
 
-bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint, cudaStream_t st) {
+bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint, cudaStream_t st,
+                  bool quad_major, const L2Prefetch* pf) {
   const FusedAnalysisTables& t = p->fast->ana[adjoint ? 1 : 0];
+  if (quad_major && ((t.KY * t.KX) % 4 != 0 || (reinterpret_cast<uintptr_t>(modes_out) & 31u) != 0)) {
+    set_error("fast_analyze: the quad-major layout needs a mode count that is a multiple of 4 and a 32-byte aligned buffer");
+    return false;
+  }
   if (n_images % t.G != 0) { set_error("fast_analyze: image count not a multiple of the tile group"); return false; }
   AnaParams P{};
   P.x = images; P.out = modes_out; P.b1_img = t.d_b1; P.a2_img = t.d_a2;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.slabs = t.slabs; P.N1 = t.N1; P.KX = t.KX; P.QROWS = t.G * t.KY;
   P.n_stages = t.n_stages; P.tmem_cols = t.tmem_cols;
   P.l2_stream_hint = l2_stream_hint_enabled();
+  P.quad_major = quad_major ? 1 : 0; P.G = t.G; P.Mt = t.KY * t.KX; P.n_images = n_images;
+  if (pf != nullptr) {
+    static const bool pf_on = [] { const char* e = getenv("SC_L2_PREFETCH"); return e == nullptr || atoi(e) != 0; }();   // =0: A/B runs
+    for (int r = 0; r < 2 && pf_on; ++r) {
+      if (pf->ptr[r] == nullptr || (reinterpret_cast<uintptr_t>(pf->ptr[r]) & 15u) != 0) continue;
+      P.pf_ptr[r] = static_cast<const uint8_t*>(pf->ptr[r]);
+      P.pf_bytes[r] = pf->bytes[r] & ~(unsigned long long)15;
+    }
+  }
   P.off_f32 = t.off_f32; P.off_ring = t.off_ring;
   P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch; P.stage_off = t.stage_off;
   P.trace = trace_begin();
@@ -2015,14 +2617,16 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
 }
 
 bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias,
-                     float* images_out, bool adjoint, int slices_per_image, cudaStream_t st) {
+                     float* images_out, bool adjoint, int slices_per_image, cudaStream_t st, bool quad_major) {
   const FusedSynthesisTables& t = p->fast->syn[adjoint ? 1 : 0];
+  if (quad_major && (t.KY * t.KX) % 4 != 0) { set_error("fast_synthesize: the quad-major layout needs a mode count that is a multiple of 4"); return false; }
   if (n_images % t.G != 0) { set_error("fast_synthesize: image count not a multiple of the tile group"); return false; }
   SynParams P{};
   P.modes = modes_in; P.out = images_out; P.bias = bias; P.aa_img = t.d_aa; P.bb_img = t.d_bb;
   P.n_tiles = (int)(n_images / t.G); P.W = t.W; P.KX = t.KX; P.QROWS = t.G * t.KY; P.H = t.H;
   P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
   P.slices_per_image = slices_per_image > 0 ? slices_per_image : 1;
+  P.quad_major = quad_major ? 1 : 0; P.KY = t.KY; P.n_images = n_images;
   P.l2_stream_hint = l2_stream_hint_enabled();
   P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb; P.off_stage = t.off_stage;
   P.trace = trace_begin();

@@ -2,11 +2,18 @@
 
 The reference wraps the model in DDP (neuralop/training/trainer.py:203-205): samples are independent in the forward pass and
 in dx; only dweight / dbias sum over the batch.  `GradientAllReducer` averages gradient tensors across ranks on a side
-stream (complex64 grads travel as (re, im) float pairs, in place, no packing copy), so that the collective overlaps whatever
-the caller launches next.  Attached to a `SpectralConv` (`conv.gradient_reducer = reducer`) the backward pass itself starts
-the all-reduce of dweight / dbias as soon as the contraction backward has produced them, i.e. underneath the dx synthesis
-kernel -- the DDP overlap, for a single layer.  Backend: NCCL over NVLink/NVSwitch on the B200 box, gloo in the CPU tests.
+stream (complex64 grads travel as (re, im) float pairs, in place, no packing copy).
+
+Attached to a `SpectralConv` (`conv.gradient_reducer = reducer`) the backward pass itself all-reduces dweight / dbias: the
+library records an event as soon as the dweight kernel has been launched (`sc_backward_dense(..., grads_ready)`), the
+collective stream waits on it, and the collective runs underneath the dxm contraction and the dx synthesis kernel -- the DDP
+overlap, for a single layer.  Before `backward` returns, the compute stream is made to wait for the collective, so whatever
+autograd does next with the returned tensors (steal them as `.grad`, or accumulate them into an existing `.grad`) is ordered
+after the in-place reduction.  Gradients reduced that way are remembered (by storage address) and skipped by `start()`, which
+reduces the `.grad` of every OTHER registered parameter.  Backend: NCCL over NVLink/NVSwitch on the B200 box, gloo in the CPU
+tests.
 """
+import ctypes
 from typing import Iterable, List, Optional
 
 import torch
@@ -19,8 +26,9 @@ class GradientAllReducer:
         self.group = process_group
         self.average = average
         self._stream: Optional[torch.cuda.Stream] = None
-        self._pending = []          # (work, tensor) pairs of the collectives in flight
-        self._early = False         # True once a backward pass has already started this step's collectives
+        self._pending = []            # (work, tensor, op) of the collectives in flight
+        self._reduced_in_backward = set()   # data_ptr of gradient buffers a backward pass already reduced this step
+        self._event = None            # sc_event handle (created on first use)
 
     @staticmethod
     def _as_real(t: torch.Tensor) -> torch.Tensor:
@@ -56,43 +64,63 @@ class GradientAllReducer:
     def _backend_has_avg(self) -> bool:
         return dist.get_backend(self.group) == "nccl"
 
-    def start_tensors(self, tensors: Iterable[torch.Tensor]):
-        """Launch the all-reduce of `tensors` (in place). On CUDA it runs on a side stream that first waits for the work
-        already queued on the current stream (the kernels that produced the tensors)."""
+    def _side_stream(self, device) -> torch.cuda.Stream:
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=device)
+        return self._stream
+
+    def grads_ready_event(self) -> ctypes.c_void_p:
+        """The `grads_ready` event handed to sc_backward_dense (created once per reducer)."""
+        if self._event is None:
+            from . import _lib
+            ev = ctypes.c_void_p()
+            _lib.check(_lib.load().sc_event_create(ctypes.byref(ev)), "sc_event_create")
+            self._event = ev
+        return self._event
+
+    def start_tensors(self, tensors: Iterable[torch.Tensor], after_event: Optional[ctypes.c_void_p] = None):
+        """Launch the all-reduce of `tensors` (in place). On CUDA it runs on a side stream that first waits for `after_event`
+        (an sc_event recorded on the compute stream) or, without one, for everything already queued on the current stream."""
         tensors = self._coalesce([self._as_real(t) for t in tensors if t is not None])
         if self.world_size() == 1 or not tensors:
             return
         device = tensors[0].device
         op = dist.ReduceOp.AVG if (self.average and self._backend_has_avg()) else dist.ReduceOp.SUM
         if device.type == "cuda":
-            if self._stream is None:
-                self._stream = torch.cuda.Stream(device=device)
-            self._stream.wait_stream(torch.cuda.current_stream(device))
-            with torch.cuda.stream(self._stream):
+            side = self._side_stream(device)
+            if after_event is not None:
+                from . import _lib
+                _lib.check(_lib.load().sc_stream_wait_event(ctypes.c_void_p(side.cuda_stream), after_event), "sc_stream_wait_event")
+            else:
+                side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
                 for t in tensors:
                     r = self._as_real(t)
-                    r.record_stream(self._stream)
+                    r.record_stream(side)
                     self._pending.append((dist.all_reduce(r, op=op, group=self.group, async_op=True), r, op))
         else:
             for t in tensors:
                 r = self._as_real(t)
                 self._pending.append((dist.all_reduce(r, op=op, group=self.group, async_op=True), r, op))
 
-    def start_early(self, tensors):
-        """Called from inside a backward pass (SpectralConv with a reducer attached)."""
-        self._early = True
-        self.start_tensors(tensors)
+    def reduce_in_backward(self, tensors, after_event: Optional[ctypes.c_void_p] = None):
+        """Called from inside a backward pass with the gradients it is about to return: all-reduce them (after `after_event`,
+        i.e. underneath the kernels already queued behind it) and order the compute stream after the result."""
+        tensors = [t for t in tensors if t is not None]
+        if self.world_size() == 1 or not tensors:
+            return
+        self.start_tensors(tensors, after_event=after_event)
+        self._wait_pending()
+        for t in tensors:
+            self._reduced_in_backward.add(t.data_ptr())
 
     def start(self):
-        """All-reduce the `.grad` of the registered parameters, unless a backward pass already did it for this step."""
-        if self._early:
-            return
-        self.start_tensors([p.grad for p in self.params if p.grad is not None])
+        """All-reduce the `.grad` of every registered parameter that a backward pass has not reduced already."""
+        grads = [p.grad for p in self.params if p.grad is not None and p.grad.data_ptr() not in self._reduced_in_backward]
+        self.start_tensors(grads)
 
-    def finish(self):
-        """Wait for the collectives; the current stream then sees the averaged gradients."""
+    def _wait_pending(self):
         if not self._pending:
-            self._early = False
             return
         device = self._pending[0][1].device
         scale = 1.0 / self.world_size()
@@ -109,8 +137,21 @@ class GradientAllReducer:
                 if self.average and op == dist.ReduceOp.SUM:
                     r.mul_(scale)
         self._pending = []
-        self._early = False
+
+    def finish(self):
+        """Wait for the collectives; the current stream then sees the averaged gradients.  Ends the step."""
+        self._wait_pending()
+        self._reduced_in_backward.clear()
 
     def all_reduce(self):
         self.start()
         self.finish()
+
+    def __del__(self):
+        try:
+            if self._event is not None:
+                from . import _lib
+                _lib.load().sc_event_destroy(self._event)
+                self._event = None
+        except Exception:   # noqa: BLE001
+            pass

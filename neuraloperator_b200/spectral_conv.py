@@ -212,9 +212,11 @@ class _SpectralConvDense(torch.autograd.Function):
         n_max = B * max(Ci, Co)
         ws = _workspace(plan, n_max, dev)
         b = bias.reshape(-1) if bias is not None else None
+        layout = ctypes.c_int32(0)
         with torch.cuda.device(dev):
-            _lib.check(lib.sc_forward_dense(plan.handle, _ptr(x), _ptr(weight), _ptr(b), _ptr(y), _ptr(xm), B, Ci, Co,
-                                            _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_forward_dense")
+            _lib.check(lib.sc_forward_dense(plan.handle, _ptr(x), _ptr(weight), _ptr(b), _ptr(y), _ptr(xm), ctypes.byref(layout),
+                                            B, Ci, Co, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_forward_dense")
+        ctx.saved_layout = int(layout.value)      # xm is opaque: the library says how it ordered the saved modes
         ctx.plan = plan
         ctx.reducer = reducer
         ctx.has_bias = bias is not None
@@ -247,23 +249,15 @@ class _SpectralConvDense(torch.autograd.Function):
             db = torch.empty(Co, dtype=torch.float32, device=dev) if need_db else None
         ws = _workspace(plan, B * max(Ci, Co), dev)
         reducer = ctx.reducer
+        data_parallel = reducer is not None and reducer.world_size() > 1 and (dw is not None or db is not None)
+        # data parallel: the library records `grads_ready` right after the dweight (+dbias) launch; the reducer's collective
+        # stream waits on it, so the all-reduce runs underneath the dxm contraction and the dx synthesis kernel
+        ev = reducer.grads_ready_event() if data_parallel else ctypes.c_void_p(0)
         with torch.cuda.device(dev):
-            if reducer is None or reducer.world_size() == 1:
-                _lib.check(lib.sc_backward_dense(plan.handle, _ptr(gy), _ptr(weight), _ptr(xm), _ptr(dx), _ptr(dw), _ptr(db),
-                                                 B, Ci, Co, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_backward_dense")
-            else:
-                # data parallel: same kernels, but the gradient all-reduce of dweight / dbias is launched on the reducer's
-                # side stream right after the contraction backward, underneath the dx synthesis kernel
-                st = _stream_ptr(dev)
-                gm = torch.empty((B, Co, *plan.kept), dtype=torch.complex64, device=dev)
-                dxm = torch.empty((B, Ci, *plan.kept), dtype=torch.complex64, device=dev) if need_dx else None
-                _lib.check(lib.sc_analyze(plan.handle, _ptr(gy), B * Co, _ptr(gm), 1, _ptr(ws), ws.numel(), st), "sc_analyze")
-                _lib.check(lib.sc_contract_dense_backward(plan.handle, _ptr(xm), _ptr(gm), _ptr(weight), _ptr(dxm), _ptr(dw),
-                                                          _ptr(db), B, Ci, Co, st), "sc_contract_dense_backward")
-                reducer.start_early([dw, db])
-                if need_dx:
-                    _lib.check(lib.sc_synthesize(plan.handle, _ptr(dxm), B * Ci, 0, _ptr(None), _ptr(dx), 1, _ptr(ws),
-                                                 ws.numel(), st), "sc_synthesize")
+            _lib.check(lib.sc_backward_dense(plan.handle, _ptr(gy), _ptr(weight), _ptr(xm), ctx.saved_layout, _ptr(dx), _ptr(dw),
+                                             _ptr(db), B, Ci, Co, _ptr(ws), ws.numel(), _stream_ptr(dev), ev), "sc_backward_dense")
+            if data_parallel:
+                reducer.reduce_in_backward([dw, db], after_event=ev)
         if db is not None:
             db = db.reshape(ctx.bias_shape)
         return dx, dw, db, None, None

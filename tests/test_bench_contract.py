@@ -33,3 +33,17 @@ def test_reference_arm_is_rank0_only_under_torchrun():
                         "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_torch_cufft_denominator_is_the_reference_op_sequence():
+    """bench.py's PyTorch+cuFFT denominator restates the reference forward (it must not import oracle/ on the timed path);
+    on CPU it has to agree bit-exactly with the oracle, which is pinned to the unmodified reference."""
+    import torch
+    import bench
+    from oracle import spectral_conv_oracle as O
+    for (B, Ci, Co, grid, modes) in [(2, 3, 4, (16, 12), (8, 6)), (2, 3, 3, (32,), (8,)), (1, 2, 3, (8, 6, 10), (4, 4, 6)),
+                                     (2, 3, 4, (9, 11), (4, 5))]:
+        x, w, bias, gy = O.make_inputs(B, Ci, Co, grid, modes, seed=1)
+        y_ref = O.spectral_conv_forward(x, w, bias, modes)
+        y = bench.torch_cufft_forward(x, w.tensor, bias, O.stored_n_modes(modes))
+        assert torch.equal(y, y_ref)
