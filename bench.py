@@ -308,8 +308,14 @@ def run_ours(args):
     x = torch.randn(B, C, H, W, device=dev, requires_grad=True)
     g = torch.randn(B, C, H, W, device=dev)
     reducer = nb.GradientAllReducer(conv.parameters()) if world > 1 else None
-    if args.no_graph:
-        conv.gradient_reducer = reducer  # eager path: backward starts the all-reduce of dW/db underneath the dx synthesis kernel
+    reserved_sms = 0
+    if reducer is not None:
+        # backward all-reduces dweight / dbias itself: the collective starts on the library's grads_ready event (right after the
+        # dweight kernel) on the reducer's stream and runs underneath the dxm contraction and the dx synthesis kernel; the
+        # persistent transform launches leave a few SMs free so that NCCL's CTAs find room next to them
+        conv.gradient_reducer = reducer
+        reserved_sms = int(os.environ.get("SC_RESERVED_SMS", "12"))
+        nb.get_plan(dev, (H, W), (H, W), conv.n_modes, conv.max_n_modes).set_reserved_sms(reserved_sms)
 
     def step_body():
         conv.weight.tensor.grad = None
@@ -317,10 +323,13 @@ def run_ours(args):
         x.grad = None
         y = conv(x)
         y.backward(g)
+        if reducer is not None:
+            reducer.finish()               # nothing pending (backward already ordered the stream after the collective): ends the step's bookkeeping
 
-    # The step is 8 kernel launches of 20-40 us each: capture it once in a CUDA graph so that the timed loop is not bound
-    # by Python / autograd dispatch (the eager path is what `e2e` measures).
+    # The step is 6 kernel launches of 10-40 us each (+ one NCCL all-reduce on N > 1): capture it once in a CUDA graph so that the
+    # timed loop is not bound by Python / autograd / NCCL enqueue (the eager path is what `e2e` measures).
     graph = None
+    graph_error = None
     c0 = _lib.launch_count()
     step_body()
     launches_per_step = _lib.launch_count() - c0       # kernels this library launches for one fwd+bwd
@@ -334,22 +343,22 @@ def run_ours(args):
                     step_body()
             torch.cuda.current_stream(dev).wait_stream(side)
             torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread_local: NCCL's watchdog thread queries events while this thread captures
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                 step_body()
         except Exception as exc:  # pragma: no cover - reported in the JSON line
             graph = None
-            graph_error = repr(exc)
+            graph_error = repr(exc)[:300]
             torch.cuda.synchronize(dev)
 
     def step():
         if graph is not None:
-            graph.replay()
+            graph.replay()                 # N > 1: the all-reduce is a node of the graph, forked after the dweight kernel
         else:
             step_body()
-        if reducer is not None:            # one in-place NCCL all-reduce (AVG) of dW and db per step, outside the captured graph
-            reducer.start()                # (capturing the collective inside the graph dead-locked on this stack; no-op if the
-            reducer.finish()               #  eager backward already started it)
 
     def barrier():
         if world > 1:
@@ -444,7 +453,6 @@ def run_ours(args):
             y = conv(xd2)
             y.backward(gd_buf[sb])
             if reducer is not None:
-                reducer.start()
                 reducer.finish()
             ev_free[sb].record(main)
             outs = (y.detach(), xd2.grad, conv.weight.tensor.grad, conv.bias.grad)
@@ -531,7 +539,11 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "no flush: x, g, y, dx are 134 MB each (537 MB touched per step) > 126 MB L2",
-                       "fast_path_mask": plan.uses_fast_path(), "cuda_graph": graph is not None},
+                       "fast_path_mask": plan.uses_fast_path(), "cuda_graph": graph is not None, "cuda_graph_error": graph_error,
+                       "allreduce": None if world == 1 else ("one NCCL all-reduce (AVG) of dweight+dbias per step, started on the "
+                                    "grads_ready event after the dweight kernel, overlapping dxm + dx synthesis"
+                                    + (", captured in the CUDA graph" if graph is not None else ", eager")),
+                       "reserved_sms": reserved_sms},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,

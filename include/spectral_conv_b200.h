@@ -81,6 +81,9 @@ size_t sc_workspace_bytes(const sc_plan* plan, int64_t batch_times_channels);
 /* 0 = generic SIMT kernels only, 1 = tcgen05/TMA fused path where the shape qualifies (default) */
 int  sc_plan_set_fast_path(sc_plan* plan, int enable);
 int  sc_plan_uses_fast_path(const sc_plan* plan);
+/* The persistent transform kernels launch one CTA per SM; n_sms of them are left free (default 0) so that a collective running
+ * on another stream (the data-parallel gradient all-reduce, see sc_backward_dense) finds room for its own CTAs. */
+int  sc_plan_set_reserved_sms(sc_plan* plan, int n_sms);
 
 /* ---- the two transforms ------------------------------------------------------------------------------- */
 /* Truncated analysis:  images (n_images, grid..) real  ->  modes (n_images, k_1..k_d).
@@ -155,6 +158,25 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
                       int32_t saved_layout, float* dx, sc_complex* dweight, float* dbias,
                       int32_t batch, int32_t in_channels, int32_t out_channels,
                       void* workspace, size_t workspace_bytes, sc_stream stream, sc_event grads_ready);
+
+/* ---- whole forward / backward for a Tucker weight, contracted factor by factor (_contract_tucker, :76-103) ----------------
+ * ranks = {r_in, r_out, r_1..r_d} (the core's extents); core (r_in, r_out, r_1..r_d); u_in (Ci, r_in); u_out (Co, r_out);
+ * u_modes[j] = the KEPT rows of mode factor j, contiguous (k_j, r_j) (`weight[slices_w]` slices the factors, :489).
+ * plan_kept: the same problem with max_n_modes == kept modes (may be `plan` itself when nothing is cut).
+ * `saved` (sc_tucker_saved_elems() elements, opaque) carries the activations backward needs: the kept input modes, the two
+ * rank-channel intermediates, the expanded core and the expansion chain.  One workspace size serves both calls. */
+size_t sc_tucker_saved_elems(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks);
+size_t sc_tucker_workspace_bytes(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks);
+int sc_forward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const float* x, const sc_complex* core, const sc_complex* u_in,
+                      const sc_complex* u_out, const sc_complex* const* u_modes, const float* bias, float* y, sc_complex* saved,
+                      int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks,
+                      void* workspace, size_t workspace_bytes, sc_stream stream);
+/* every gradient in the layout of its parameter (PyTorch conjugate convention); dbias may be NULL */
+int sc_backward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const float* gy, const sc_complex* core, const sc_complex* u_in,
+                       const sc_complex* u_out, const sc_complex* const* u_modes, const sc_complex* saved, float* dx,
+                       sc_complex* d_core, sc_complex* d_u_in, sc_complex* d_u_out, sc_complex* const* d_u_modes, float* dbias,
+                       int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks,
+                       void* workspace, size_t workspace_bytes, sc_stream stream);
 
 /* events for the grads_ready hand-over above (timing disabled); sc_stream_wait_event makes `stream` wait for the last record */
 int  sc_event_create(sc_event* event_out);

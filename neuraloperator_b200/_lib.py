@@ -39,6 +39,7 @@ SIGNATURES = {
     "sc_workspace_bytes": (c_size_t, [c_void_p, c_i64]),
     "sc_plan_set_fast_path": (c_int, [c_void_p, c_int]),
     "sc_plan_uses_fast_path": (c_int, [c_void_p]),
+    "sc_plan_set_reserved_sms": (c_int, [c_void_p, c_int]),
     "sc_analyze": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "sc_synthesize": (c_int, [c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                               c_void_p]),
@@ -50,6 +51,12 @@ SIGNATURES = {
                                  c_i32, c_void_p, c_size_t, c_void_p]),
     "sc_backward_dense": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32,
                                   c_i32, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "sc_tucker_saved_elems": (c_size_t, [c_void_p, c_i32, c_i32, c_i32, c_void_p]),
+    "sc_tucker_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32, c_i32, c_void_p]),
+    "sc_forward_tucker": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sc_backward_tucker": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sc_event_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "sc_event_destroy": (None, [c_void_p]),
     "sc_stream_wait_event": (c_int, [c_void_p, c_void_p]),

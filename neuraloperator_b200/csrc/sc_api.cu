@@ -1,6 +1,7 @@
 // C ABI of libspectral_conv_b200.so: plan construction (kept-mode index set + twiddle tables) and the
 // orchestration of the transform / contraction kernels.  See include/spectral_conv_b200.h for the contract
 // and the reference lines each entry point replaces.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -546,6 +547,12 @@ int sc_plan_set_fast_path(sc_plan* plan, int enable) {
   return 0;
 }
 
+int sc_plan_set_reserved_sms(sc_plan* plan, int n_sms) {
+  SC_REQUIRE(plan != nullptr && n_sms >= 0, "sc_plan_set_reserved_sms: bad argument");
+  reinterpret_cast<Plan*>(plan)->reserved_sms = n_sms;
+  return 0;
+}
+
 int sc_plan_uses_fast_path(const sc_plan* plan) {
   const Plan* p = reinterpret_cast<const Plan*>(plan);
   if (p == nullptr || !p->fast_enabled) return 0;
@@ -668,6 +675,169 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
                       static_cast<cudaEvent_t>(grads_ready)));
   if (dx != nullptr)
     SC_TRY(synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st, g_qm));
+  return 0;
+}
+
+// ---- Tucker-factorized forward / backward as ONE call each (reference _contract_tucker, :76-103) --------------------------
+namespace {
+struct TuckerDims {
+  int d = 0, B = 0, Ci = 0, Co = 0, rf = 0, rg = 0;
+  int r[SC_MAX_DIMS] = {0}, k[SC_MAX_DIMS] = {0};
+  int64_t M = 1;
+  // A_j: the core with axes j .. d-1 expanded to kept modes: [rf*rg][r_0..r_{j-1}][k_j..k_{d-1}]; A_d = core, A_0 = expanded weight
+  int64_t chain_elems(int j) const {
+    int64_t e = (int64_t)rf * rg;
+    for (int l = 0; l < j; ++l) e *= r[l];
+    for (int l = j; l < d; ++l) e *= k[l];
+    return e;
+  }
+  int64_t outer(int j) const { int64_t e = (int64_t)rf * rg; for (int l = 0; l < j; ++l) e *= r[l]; return e; }
+  int64_t inner(int j) const { int64_t e = 1; for (int l = j + 1; l < d; ++l) e *= k[l]; return e; }
+  // saved-buffer offsets (complex elements)
+  int64_t off_xm() const { return 0; }
+  int64_t off_t1() const { return (int64_t)B * Ci * M; }
+  int64_t off_t2() const { return off_t1() + (int64_t)B * rf * M; }
+  int64_t off_wc() const { return off_t2() + (int64_t)B * rg * M; }
+  int64_t off_chain(int j) const {   // A_j for 1 <= j <= d-1
+    int64_t o = off_wc() + (int64_t)rf * rg * M;
+    for (int l = 1; l < j; ++l) o += chain_elems(l);
+    return o;
+  }
+  int64_t saved_elems() const { return off_chain(d); }
+};
+
+bool tucker_dims(const Plan* p, int B, int Ci, int Co, const int32_t* ranks, TuckerDims* t) {
+  if (p == nullptr || ranks == nullptr || B < 1 || Ci < 1 || Co < 1) { set_error("tucker: bad arguments"); return false; }
+  t->d = p->d; t->B = B; t->Ci = Ci; t->Co = Co; t->rf = ranks[0]; t->rg = ranks[1];
+  t->M = p->n_modes_total;
+  if (t->rf < 1 || t->rg < 1) { set_error("tucker: ranks must be >= 1"); return false; }
+  for (int j = 0; j < p->d; ++j) {
+    t->r[j] = ranks[2 + j]; t->k[j] = p->dim[j].k;
+    if (t->r[j] < 1) { set_error("tucker: ranks must be >= 1"); return false; }
+  }
+  return true;
+}
+
+inline size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct TuckerBwdArena { float2 *g2, *g1, *dwc, *da[2], *pr_scratch; unsigned int* counter; size_t bytes; };
+
+TuckerBwdArena tucker_bwd_arena(const TuckerDims& t, char* base) {
+  TuckerBwdArena a{};
+  size_t off = 0;
+  auto take = [&](size_t elems) { float2* ptr = reinterpret_cast<float2*>(base + off); off += a256(elems * sizeof(float2)); return ptr; };
+  a.g2 = take((size_t)t.B * t.rg * t.M);
+  a.g1 = take((size_t)t.B * t.rf * t.M);
+  a.dwc = take((size_t)t.rf * t.rg * t.M);
+  int64_t mx = 0;
+  for (int j = 0; j <= t.d; ++j) mx = std::max(mx, t.chain_elems(j));
+  a.da[0] = take((size_t)mx);
+  a.da[1] = take((size_t)mx);
+  size_t sc = std::max(pair_reduce_split_scratch_bytes(t.B, t.rg, t.Co, (int)t.M), pair_reduce_split_scratch_bytes(t.B, t.Ci, t.rf, (int)t.M));
+  for (int j = 0; j < t.d; ++j) sc = std::max(sc, pair_reduce_split_scratch_bytes(t.outer(j), t.r[j], t.k[j], (int)t.inner(j)));
+  a.pr_scratch = reinterpret_cast<float2*>(base + off); off += a256(sc);
+  a.counter = reinterpret_cast<unsigned int*>(base + off); off += 256;
+  a.bytes = off;
+  return a;
+}
+}  // namespace
+
+size_t sc_tucker_saved_elems(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks) {
+  TuckerDims t;
+  if (!tucker_dims(reinterpret_cast<const Plan*>(plan), batch, in_channels, out_channels, ranks, &t)) return 0;
+  return (size_t)t.saved_elems();
+}
+
+size_t sc_tucker_workspace_bytes(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  TuckerDims t;
+  if (!tucker_dims(p, batch, in_channels, out_channels, ranks, &t)) return 0;
+  const int64_t n_max = (int64_t)batch * std::max(in_channels, out_channels);
+  return a256(sc_workspace_bytes(plan, n_max)) + tucker_bwd_arena(t, nullptr).bytes;
+}
+
+int sc_forward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const float* x, const sc_complex* core, const sc_complex* u_in,
+                      const sc_complex* u_out, const sc_complex* const* u_modes, const float* bias, float* y, sc_complex* saved,
+                      int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks, void* workspace,
+                      size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  const Plan* pk = reinterpret_cast<const Plan*>(plan_kept);
+  SC_REQUIRE(p != nullptr && pk != nullptr && x != nullptr && core != nullptr && u_in != nullptr && u_out != nullptr && u_modes != nullptr &&
+             y != nullptr && saved != nullptr, "sc_forward_tucker: null argument");
+  SC_REQUIRE(pk->n_modes_total == p->n_modes_total && pk->weight_elems_per_io == p->n_modes_total,
+             "sc_forward_tucker: plan_kept must be the same problem with weight extents == kept modes");
+  TuckerDims t;
+  SC_TRY(tucker_dims(p, batch, in_channels, out_channels, ranks, &t));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)t.B * std::max(t.Ci, t.Co);
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, workspace_bytes, &w));
+  float2* sv = reinterpret_cast<float2*>(saved);
+  float2 *xm = sv + t.off_xm(), *t1 = sv + t.off_t1(), *t2 = sv + t.off_t2(), *wc = sv + t.off_wc();
+  float2* ym = w.modes[0];
+  SC_TRY(analyze(p, x, (int64_t)t.B * t.Ci, xm, false, w.buf[0], w.buf[1], st));
+  // expand the core along the mode axes, last axis first: A_d = core, A_j = U_j x_j A_{j+1}   (A_0 = wc)
+  const float2* cur = reinterpret_cast<const float2*>(core);
+  for (int j = t.d - 1; j >= 0; --j) {
+    float2* dst = j == 0 ? wc : sv + t.off_chain(j);
+    SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_modes[j]), t.r[j], 1, false, cur, dst, t.outer(j), t.k[j], t.r[j],
+                                             (int)t.inner(j), st));
+    cur = dst;
+  }
+  // channel mixing with U_in, the dense mode product on rank channels, channel mixing with U_out
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_in), 1, t.rf, false, xm, t1, t.B, t.rf, t.Ci, (int)t.M, st));
+  SC_TRY(contract_fwd(pk, t1, wc, t2, t.B, t.rf, t.rg, st, false));
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_out), t.rg, 1, false, t2, ym, t.B, t.Co, t.rg, (int)t.M, st));
+  SC_TRY(synthesize(p, ym, (int64_t)t.B * t.Co, t.Co, bias, y, false, w.buf[0], w.buf[1], st));
+  return 0;
+}
+
+int sc_backward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const float* gy, const sc_complex* core, const sc_complex* u_in,
+                       const sc_complex* u_out, const sc_complex* const* u_modes, const sc_complex* saved, float* dx, sc_complex* d_core,
+                       sc_complex* d_u_in, sc_complex* d_u_out, sc_complex* const* d_u_modes, float* dbias, int32_t batch,
+                       int32_t in_channels, int32_t out_channels, const int32_t* ranks, void* workspace, size_t workspace_bytes,
+                       sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  const Plan* pk = reinterpret_cast<const Plan*>(plan_kept);
+  SC_REQUIRE(p != nullptr && pk != nullptr && gy != nullptr && core != nullptr && u_in != nullptr && u_out != nullptr && u_modes != nullptr &&
+             saved != nullptr && dx != nullptr && d_core != nullptr && d_u_in != nullptr && d_u_out != nullptr && d_u_modes != nullptr,
+             "sc_backward_tucker: null argument");
+  TuckerDims t;
+  SC_TRY(tucker_dims(p, batch, in_channels, out_channels, ranks, &t));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)t.B * std::max(t.Ci, t.Co);
+  const size_t tw = a256(sc_workspace_bytes(plan, n_max));
+  SC_REQUIRE(workspace != nullptr && workspace_bytes >= tw + tucker_bwd_arena(t, nullptr).bytes, "sc_backward_tucker: workspace too small (see sc_tucker_workspace_bytes)");
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, tw, &w));
+  TuckerBwdArena a = tucker_bwd_arena(t, static_cast<char*>(workspace) + tw);
+  SC_TRY(cuda_ok(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st), "cudaMemsetAsync(counter)"));
+  const float2* sv = reinterpret_cast<const float2*>(saved);
+  const float2 *xm = sv + t.off_xm(), *t1 = sv + t.off_t1(), *t2 = sv + t.off_t2(), *wc = sv + t.off_wc();
+  float2* gm = w.modes[0];
+  float2* dxm = w.modes[1];
+  SC_TRY(analyze(p, gy, (int64_t)t.B * t.Co, gm, true, w.buf[0], w.buf[1], st));
+  if (dbias != nullptr) SC_TRY(launch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
+  // out side: g2 = U_out^H gm,  dU_out[o, g] = sum conj(t2[b, g, m]) gm[b, o, m]
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_out), 1, t.rg, true, gm, a.g2, t.B, t.rg, t.Co, (int)t.M, st));
+  SC_TRY(launch_pair_reduce_split(t2, gm, reinterpret_cast<float2*>(d_u_out), 1, t.rg, t.B, t.rg, t.Co, (int)t.M, a.pr_scratch, a.counter, st));
+  // core side: the two mode GEMMs of the dense backward, on rank channels
+  SC_TRY(contract_bwd(pk, t1, a.g2, wc, a.g1, a.dwc, nullptr, t.B, t.rf, t.rg, st, false));
+  // in side
+  SC_TRY(launch_pair_reduce_split(xm, a.g1, reinterpret_cast<float2*>(d_u_in), t.rf, 1, t.B, t.Ci, t.rf, (int)t.M, a.pr_scratch, a.counter, st));
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_in), t.rf, 1, true, a.g1, dxm, t.B, t.Ci, t.rf, (int)t.M, st));
+  SC_TRY(synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+  // mode factors and core: undo the expansion chain, first axis first
+  const float2* d_a = a.dwc;
+  for (int j = 0; j < t.d; ++j) {
+    const float2* a_next = (j + 1 == t.d) ? reinterpret_cast<const float2*>(core) : sv + t.off_chain(j + 1);     // A_{j+1}
+    SC_TRY(launch_pair_reduce_split(a_next, d_a, reinterpret_cast<float2*>(d_u_modes[j]), 1, t.r[j], t.outer(j), t.r[j], t.k[j], (int)t.inner(j),
+                                    a.pr_scratch, a.counter, st));
+    float2* dst = (j + 1 == t.d) ? reinterpret_cast<float2*>(d_core) : a.da[j & 1];
+    SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_modes[j]), 1, t.r[j], true, d_a, dst, t.outer(j), t.r[j], t.k[j],
+                                             (int)t.inner(j), st));
+    d_a = dst;
+  }
   return 0;
 }
 

@@ -521,6 +521,328 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 }
 
 // =====================================================================================================
+// fused analysis, second generation: the image rows (A operand of stage 1) live in TENSOR MEMORY
+//
+//   k_fused_analysis is bound by shared-memory bandwidth (per 128-row tile: 64 KB TMA write, 64 KB converter reads, 64 KB of
+//   swizzled bf16 hi / lo stores, ~100 KB of stage-1 operand fetches, ...).  Here the converters own image rows (thread <-> TMEM
+//   lane), read them from 128-byte-swizzled TMA boxes and write the bf16 hi / lo pairs with tcgen05.st into a two-stage ring of
+//   [128 lanes x (32 + 32) columns]; the stage-1 MMAs take A from tensor memory.  That removes the bf16 stores and the A half of
+//   the operand fetches (~128 KB of the ~360 KB per tile) and frees the shared memory of the operand ring for a deeper fp32 TMA
+//   ring.  Tensor memory: D1[2] 4*N1 | D2 N1 (single-buffered) | leading-dim table 128 | x ring 128  ->  N1 <= 48.
+//   Everything downstream of stage 1 is k_fused_analysis unchanged.
+// =====================================================================================================
+constexpr int FA2_X_STAGES = 2, FA2_MAX_F32 = 6;
+
+template <int N1>
+__global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis2(const AnaParams P, const __grid_constant__ CUtensorMap x_map) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
+  __shared__ uint64_t bar_full[FA2_X_STAGES], bar_empty[FA2_X_STAGES], bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_b2_empty,
+      bar_d2_full[1], bar_d2_empty[1], bar_f32_full[FA2_MAX_F32], bar_f32_empty[FA2_MAX_F32];
+  __shared__ uint32_t tmem_base_slot;
+  constexpr int half = N1 / 2;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int FS = P.n_stages;        // depth of the fp32 TMA staging ring (the bf16 operand ring of k_fused_analysis is gone)
+  uint8_t* s_b1 = smem + P.off_b1;
+  uint8_t* s_b2 = smem + P.off_b2;
+  float* s_scr = reinterpret_cast<float*>(smem + P.off_scratch);
+
+  if (tid == 0) {
+    for (int i = 0; i < FA2_X_STAGES; ++i) { mbar_init(&bar_full[i], FA_LOADER_WARPS); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_d1_full[i], 1); mbar_init(&bar_d1_empty[i], 128); }
+    mbar_init(&bar_d2_full[0], 1); mbar_init(&bar_d2_empty[0], 128);
+    for (int i = 0; i < FS; ++i) { mbar_init(&bar_f32_full[i], 1); mbar_init(&bar_f32_empty[i], FA_LOADER_WARPS); }
+    mbar_init(&bar_b2_full, 128);
+    mbar_init(&bar_b2_empty, 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(&tmem_base_slot, (uint32_t)P.tmem_cols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  if (warp < FA_LOADER_WARP0) {
+    // constant operand images are staged by the consumer-side warps only; the loaders start streaming x at once
+    constexpr int NT = FA_LOADER_WARP0 * 32;
+    copy_image(s_b1, P.b1_img, (2 * N1 * P.W * 2) / 16, tid, NT);
+    if (warp < 4) {   // leading-dim table -> tensor memory: lane = table row, two bf16 K-elements per 32-bit column
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(P.a2_img) + (size_t)(warp * 32 + lane) * 128;
+      const uint32_t tm_a2_w = tmem_base_slot + (uint32_t)(5 * N1) + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 2
+      for (int c = 0; c < 128; c += 16) {
+        uint32_t w[16];
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + c + e));
+          w[e] = v.x; w[e + 1] = v.y; w[e + 2] = v.z; w[e + 3] = v.w;
+        }
+        tmem_st16(tm_a2_w + c, w);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+    }
+    uint4* z = reinterpret_cast<uint4*>(s_b2);   // padding rows of B2 (kx >= KX) stay zero for the whole kernel
+    for (int i = tid; i < (N1 * 512) / 16; i += NT) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory");
+  }
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tm_d1[2] = {tmem, tmem + (uint32_t)(2 * N1)};
+  // columns: D1[2] 4*N1 | D2 N1 (single) | leading-dim table 128 | x operand ring FA2_X_STAGES x (32 hi + 32 lo)
+  const uint32_t tm_d2[1] = {tmem + (uint32_t)(4 * N1)};
+  const uint32_t tm_a2 = tmem + (uint32_t)(5 * N1);
+  const uint32_t tm_x = tmem + (uint32_t)(5 * N1 + 128);
+
+  const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == FA_TMA_WARP) {
+    // ------------------------------------------------------------------ TMA producer: one tensor load per 32 KB slab
+    const int total = n_local * P.slabs;
+    uint8_t* f32_stage = smem + P.off_f32;
+    const uint64_t pol = l2_policy_evict_first();
+    pdl_wait();                                  // x is produced by the previous kernel of the stream
+    // Hand-over to the next kernel of the stream only AFTER this CTA has seen its own predecessor complete: a kernel of this
+    // library may then read, ahead of its own wait, anything its immediate predecessor does not write (the contraction
+    // fetches the weights that way).  The dependents still start as soon as this CTA leaves its SM.
+    pdl_launch_dependents();
+    constexpr unsigned long long PF_PIECE = 8192;
+    for (int idx = 0; idx < total; ++idx) {
+      const int sb = idx % FS;
+      mbar_wait(&bar_f32_empty[sb], (uint32_t)(((idx / FS) & 1) ^ 1));
+      if (elect_one()) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {        // this CTA's idx-th 8 KB piece of each prefetch range
+          const unsigned long long off = ((unsigned long long)idx * gridDim.x + blockIdx.x) * PF_PIECE;
+          if (off < P.pf_bytes[r]) {
+            const unsigned long long left = P.pf_bytes[r] - off;
+            bulk_prefetch_l2(P.pf_ptr[r] + off, (uint32_t)(left < PF_PIECE ? left : PF_PIECE));
+          }
+        }
+        const int tile = (int)blockIdx.x + (idx / P.slabs) * (int)gridDim.x, slab = idx % P.slabs;
+        // a slab = two [128 rows x 32 floats] boxes in the 128-byte swizzle: a thread can then read ITS ROW conflict-free
+        mbar_arrive_expect_tx(&bar_f32_full[sb], 32768u);
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {
+          if (P.l2_stream_hint) tma_load_2d_hint(f32_stage + sb * 32768 + hb * 16384, &x_map, &bar_f32_full[sb], slab * 64 + hb * 32, tile * 128, pol);
+          else tma_load_2d(f32_stage + sb * 32768 + hb * 16384, &x_map, &bar_f32_full[sb], slab * 64 + hb * 32, tile * 128);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp >= FA_LOADER_WARP0) {
+    // ------------------------------------------------------------------ converters: fp32 staging -> bf16 hi / lo -> TENSOR MEMORY
+    // The A operand of stage 1 (the image rows) lives in tensor memory: thread <-> image row (its TMEM lane) and one of the two
+    // 32-float boxes of the slab.  Versus the shared-memory operand ring of k_fused_analysis this removes, per 128-row tile, the
+    // 64 KB of swizzled bf16 stores and the 64 KB the MMAs re-read from them (the kernel is bound by shared-memory bandwidth).
+    const int cw = warp - FA_LOADER_WARP0, q = cw & 3, hb = cw >> 2;
+    const int row = 32 * q + lane;
+    uint8_t* f32_stage = smem + P.off_f32;
+    const uint32_t my_row = (uint32_t)(hb * 16384 + row * 128);
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t tm_mine = tm_x + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * hb);
+    const int total = n_local * P.slabs;
+    for (int idx = 0; idx < total; ++idx) {
+      const int xs = idx % FA2_X_STAGES;
+      const int sb = idx % FS;
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 0);
+      mbar_wait(&bar_f32_full[sb], (uint32_t)((idx / FS) & 1));
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 7, idx, 0);
+      uint32_t hi[16], lo[16];
+      const uint8_t* fsrc = f32_stage + sb * 32768 + my_row;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {            // 16-byte chunk c of the row sits at chunk position c ^ (row & 7)
+        const float4 v = *reinterpret_cast<const float4*>(fsrc + ((c ^ sw) << 4));
+        split2_bf16(v.x, v.y, hi[2 * c], lo[2 * c]);
+        split2_bf16(v.z, v.w, hi[2 * c + 1], lo[2 * c + 1]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_f32_empty[sb]);   // this warp has consumed its pieces of the staging buffer
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 1);
+      mbar_wait(&bar_empty[xs], (uint32_t)(((idx / FA2_X_STAGES) & 1) ^ 1));
+      tc_fence_after_sync();
+      if (warp == FA_LOADER_WARP0) SC_TRACE(P, 0, idx, 2);
+      tmem_st16(tm_mine + (uint32_t)(64 * xs), hi);
+      tmem_st16(tm_mine + (uint32_t)(64 * xs + 32), lo);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[xs]);
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ stage-1 MMA issuer (warp-uniform, one elected lane issues)
+    {
+      const uint32_t idesc_p1 = idesc_bf16(128, 2 * N1), idesc_p2 = idesc_bf16(128, N1);
+      const uint32_t b1_lo = desc_lo(smem_u32(s_b1));
+      uint32_t g = 0;
+      for (int i = 0; i < n_local; ++i) {
+        const int buf = i & 1;
+        SC_TRACE(P, 1, i, 0);
+        mbar_wait(&bar_d1_empty[buf], (uint32_t)(((i >> 1) & 1) ^ 1));
+        tc_fence_after_sync();
+        SC_TRACE(P, 1, i, 1);
+        for (int s = 0; s < P.slabs; ++s, ++g) {
+          const int xs = (int)(g % (uint32_t)FA2_X_STAGES);
+          mbar_wait(&bar_full[xs], (g / (uint32_t)FA2_X_STAGES) & 1u);
+          tc_fence_after_sync();
+          const uint32_t x_hi = tm_x + (uint32_t)(64 * xs), x_lo = x_hi + 32;
+          const uint32_t d_b = b1_lo + (uint32_t)s * ((2 * N1 * 128) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              mma_bf16_ts(tm_d1[buf], x_hi + 8 * kk, desc_from_lo(d_b + 2 * kk), idesc_p1, (s | kk) != 0);
+              mma_bf16_ts(tm_d1[buf], x_lo + 8 * kk, desc_from_lo(d_b + 2 * kk), idesc_p2, true);
+            }
+            mma_commit(&bar_empty[xs]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) mma_commit(&bar_d1_full[buf]);
+        __syncwarp();
+        SC_TRACE(P, 1, i, 2);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ stage-2 MMA issuer
+    {
+      const uint32_t idesc_p2 = idesc_bf16(128, N1);
+      const uint32_t b2_lo = desc_lo(smem_u32(s_b2));
+      for (int i = 0; i < n_local; ++i) {
+        const int buf = 0;
+        SC_TRACE(P, 3, i, 0);
+        mbar_wait(&bar_b2_full, (uint32_t)(i & 1));
+        mbar_wait(&bar_d2_empty[buf], (uint32_t)((i & 1) ^ 1));
+        tc_fence_after_sync();
+        SC_TRACE(P, 3, i, 1);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+            const int slab = ks >> 2, kk = ks & 3;
+            mma_bf16_ts(tm_d2[buf], tm_a2 + ks * 8, desc_from_lo(b2_lo + slab * ((N1 * 128) >> 4) + 2 * kk), idesc_p2, ks > 0);
+          }
+          mma_commit(&bar_b2_empty);
+          mma_commit(&bar_d2_full[buf]);
+        }
+        __syncwarp();
+        SC_TRACE(P, 3, i, 2);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue 1: D1 -> B operand of stage 2
+    const int q4 = warp - 4;                                  // TMEM lane quarter; tile row h = q4*32 + lane
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const int KX = P.KX;
+    // B2[n][k2], k2 = 2*h + part: row h owns 4 bytes of every row n, inside K-slab q4 (64 columns = 32 rows h)
+    uint8_t* b2_mine = s_b2 + q4 * (N1 * 128) + (lane & 3) * 4;
+    const int chunk = lane >> 2;
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = i & 1;
+      if (warp == 4) SC_TRACE(P, 2, i, 0);
+      mbar_wait(&bar_d1_full[buf], (uint32_t)((i >> 1) & 1));
+      mbar_wait(&bar_b2_empty, (uint32_t)((i & 1) ^ 1));
+      tc_fence_after_sync();
+      if (warp == 4) SC_TRACE(P, 2, i, 1);
+#pragma unroll
+      for (int c = 0; c < N1; c += 16) {
+        float t1[16], t2[16];
+        tmem_ld16(tm_d1[buf] + lane_sel + c, t1);        // x_hi*T1 + x_lo*T1
+        tmem_ld16(tm_d1[buf] + lane_sel + N1 + c, t2);   // x_hi*T2
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int kx = c / 2 + e;                       // compile-time; slots kx >= KX hold exact zeros (zero table rows)
+          uint32_t hi, lo;
+          split2_bf16(t1[2 * e] + t2[2 * e], t1[2 * e + 1] + t2[2 * e + 1], hi, lo);
+          *reinterpret_cast<uint32_t*>(b2_mine + kx * 128 + ((chunk ^ (kx & 7)) << 4)) = hi;
+          *reinterpret_cast<uint32_t*>(b2_mine + (half + kx) * 128 + ((chunk ^ ((half + kx) & 7)) << 4)) = lo;
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&bar_d1_empty[buf]);
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_b2_full);
+      if (warp == 4) SC_TRACE(P, 2, i, 2);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue 2: D2 -> kept modes
+    const int row = warp * 32 + lane;                        // output row i' (0-63: T1 rows, 64-127: T2 rows)
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    const int KX = P.KX;
+    pdl_wait();                                              // the mode buffer may still be read by the previous kernel
+    for (int i = 0; i < n_local; ++i) {
+      const int buf = 0;
+      if (warp == 0) SC_TRACE(P, 4, i, 0);
+      mbar_wait(&bar_d2_full[buf], (uint32_t)(i & 1));
+      tc_fence_after_sync();
+      if (warp == 0) SC_TRACE(P, 4, i, 1);
+      float d[N1];
+#pragma unroll
+      for (int c = 0; c < N1; c += 16) tmem_ld16(tm_d2[buf] + lane_sel + c, *reinterpret_cast<float(*)[16]>(&d[c]));
+      tmem_ld_wait();
+      if (warp == 0) SC_TRACE(P, 5, i, 0);
+      tc_fence_before_sync();
+      mbar_arrive(&bar_d2_empty[buf]);
+      if (warp == 0) SC_TRACE(P, 5, i, 1);
+      // T2 rows (warps 2,3) hand hi+lo sums to the matching T1 rows (warps 0,1).  Straight-line code over all N1/2 column
+      // slots (padding slots carry exact zeros): runtime bounds checks here turn into a serial LDS->FADD->SHFL->STS chain.
+      constexpr int SP = half + 1;                 // scratch row pitch in floats
+      if (warp >= 2) {
+        float* dst = s_scr + (row - 64) * SP;
+#pragma unroll
+        for (int kx = 0; kx < half; ++kx) dst[kx] = d[kx] + d[half + kx];
+      }
+      if (tid == 0) bulk_wait_read_1();            // the block stored two tiles ago has left its staging buffer
+      if (warp == 0) SC_TRACE(P, 5, i, 2);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0) SC_TRACE(P, 6, i, 0);
+      // the tile's modes are ONE contiguous block of QROWS*KX complex numbers: stage it, then a single bulk async store
+      float2* stage = reinterpret_cast<float2*>(smem + P.off_scratch + P.stage_off) + (i & 1) * (P.QROWS * KX);
+      if (warp < 2) {
+        const float* src = s_scr + row * SP;
+        const int q = row >> 1, part = row & 1;
+        const bool live = q < P.QROWS && part == 0;
+        float mine[half], other[half];
+#pragma unroll
+        for (int kx = 0; kx < half; ++kx) mine[kx] = d[kx] + d[half + kx] + src[kx];
+#pragma unroll
+        for (int kx = 0; kx < half; ++kx) other[kx] = __shfl_xor_sync(0xffffffffu, mine[kx], 1);
+        float2* my = stage + q * KX;
+#pragma unroll
+        for (int kx = 0; kx < half; ++kx)
+          if (live && kx < KX) my[kx] = make_float2(mine[kx], other[kx]);
+      }
+      if (warp == 0) SC_TRACE(P, 6, i, 1);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 0) SC_TRACE(P, 6, i, 2);
+      if (P.quad_major) {
+        // one 32-byte sector per (image of the tile, quad of modes): element (image, m) lives at ((m >> 2) * n_images + image) * 4 + (m & 3)
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        const int nq = P.Mt >> 2;
+        for (int idx = tid; idx < P.G * nq; idx += 128) {
+          const int g = idx / nq, q = idx - g * nq;
+          const float4* sp = reinterpret_cast<const float4*>(stage + g * P.Mt + 4 * q);
+          const float4 lo4 = sp[0], hi4 = sp[1];
+          const float o8[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+          st_global_v8(reinterpret_cast<float*>(P.out + ((long long)q * P.n_images + (long long)tile * P.G + g) * 4), o8);
+        }
+      } else if (tid == 0) {
+        const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+        bulk_store(P.out + (size_t)tile * P.QROWS * KX, stage, (uint32_t)(P.QROWS * KX * 8));
+        bulk_commit();
+      }
+      if (warp == 0) SC_TRACE(P, 4, i, 2);
+    }
+    if (tid == 0) bulk_wait_all();
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, (uint32_t)P.tmem_cols);
+}
+
+// =====================================================================================================
 // fused synthesis:  kept modes of the G images of a tile  ->  128 image rows (+ bias)
 //
 //   stage A (leading dim) DA[hl, n] = sum_k AA[hl, k] * BA[n, k]      M=128 (rows)  N=2*N1  K=128 (T1 | T2 halves)
@@ -2084,6 +2406,9 @@ bool fast_can_contract(const Plan* p, int B, int Ci, int Co, bool quad_ok) {
 // ---------------------------------------------------------------------------------------------------------
 struct FusedAnalysisTables {
   bool ok = false;
+  bool v2_ok = false;       // k_fused_analysis2 (x operand in tensor memory) applies
+  int v2_stages = 0;
+  uint32_t v2_off_b1 = 0, v2_off_b2 = 0, v2_off_scratch = 0, v2_smem_bytes = 0;
   int W = 0, H = 0, G = 0, N1 = 0, KX = 0, KY = 0, slabs = 0, n_stages = 0, tmem_cols = 0;
   uint8_t* d_b1 = nullptr;
   uint8_t* d_a2 = nullptr;
@@ -2130,6 +2455,12 @@ struct FastTables {
 };
 
 static int fast_sm_count(const Plan* p) { return p->fast->sm_count; }
+// CTAs of a persistent transform launch: one per SM, minus the SMs reserved for a concurrent collective (sc_plan_set_reserved_sms)
+static int persistent_grid(const Plan* p, int n_tiles) {
+  int sms = p->fast->sm_count - p->reserved_sms;
+  if (sms < 1) sms = 1;
+  return n_tiles < sms ? n_tiles : sms;
+}
 
 static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t W);
 static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint64_t W);
@@ -2147,7 +2478,8 @@ static bool thread_has_context() {
   return fn(&ctx) != CUDA_SUCCESS || ctx != nullptr;
 }
 
-// kind 0: x slab loads, kind 1: image row-tile stores
+static bool make_swizzled_box_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t W);
+// kind 0: x slab loads, kind 1: image row-tile stores, kind 2: x loads as 128-byte-swizzled [128 x 32] boxes (k_fused_analysis2)
 static bool cached_map(const Plan* p, int kind, const void* base, uint64_t rows, uint64_t W, CUtensorMap* out) {
   FastTables* f = p->fast;
   std::lock_guard<std::mutex> lock(f->map_mutex);
@@ -2161,7 +2493,8 @@ static bool cached_map(const Plan* p, int kind, const void* base, uint64_t rows,
   if (!thread_has_context()) cudaFree(nullptr);
   TensorMapCacheEntry e{base, rows, W, kind, {}};
   const bool ok = kind == 0 ? make_slab_load_map(&e.map, static_cast<const float*>(base), rows, W)
-                            : make_row_tile_map(&e.map, static_cast<float*>(const_cast<void*>(base)), rows, W);
+                  : kind == 2 ? make_swizzled_box_map(&e.map, static_cast<const float*>(base), rows, W)
+                              : make_row_tile_map(&e.map, static_cast<float*>(const_cast<void*>(base)), rows, W);
   if (!ok) return false;
   if (f->map_cache.size() >= 32) f->map_cache.erase(f->map_cache.begin());
   f->map_cache.push_back(e);
@@ -2273,6 +2606,19 @@ static bool build_fused_analysis(Plan* p, FusedAnalysisTables* t, int H, int W, 
   t->off_scratch = t->off_b2 + (uint32_t)N1 * 512u;
   t->smem_bytes = t->off_scratch + scratch_total + 1024u;
   t->ok = true;
+  // second generation: no bf16 operand ring; fp32 staging as deep as shared memory allows
+  if (5 * N1 + 128 + 64 * FA2_X_STAGES <= 512) {
+    int st2 = (int)((227u * 1024u - 4096u - fixed) / 32768u);
+    if (st2 > FA2_MAX_F32) st2 = FA2_MAX_F32;
+    if (st2 >= 2) {
+      t->v2_ok = true;
+      t->v2_stages = st2;
+      t->v2_off_b1 = (uint32_t)st2 * 32768u;
+      t->v2_off_b2 = t->v2_off_b1 + (uint32_t)b1.size();
+      t->v2_off_scratch = t->v2_off_b2 + (uint32_t)N1 * 512u;
+      t->v2_smem_bytes = t->v2_off_scratch + scratch_total + 1024u;
+    }
+  }
   return true;
 }
 
@@ -2405,6 +2751,22 @@ static bool make_row_tile_map(CUtensorMap* map, float* base, uint64_t rows, uint
               std::to_string((unsigned long long)(uintptr_t)base) + ", rows " + std::to_string(rows) + ", W " + std::to_string(W));
     return false;
   }
+  return true;
+}
+
+// fp32 matrix [rows x W] (row-major), boxes of [128 rows x 32 floats] in the 128-byte swizzle: a thread that owns a row reads
+// its eight 16-byte chunks from eight different bank groups than its neighbours
+static bool make_swizzled_box_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t W) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  const cuuint64_t dims[2] = {W, rows};
+  const cuuint64_t strides[1] = {W * sizeof(float)};
+  const cuuint32_t box[2] = {32, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (swizzled x boxes) failed: CUresult " + std::to_string((int)r)); return false; }
   return true;
 }
 
@@ -2594,8 +2956,31 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
   P.off_f32 = t.off_f32; P.off_ring = t.off_ring;
   P.off_b1 = t.off_b1; P.off_a2 = t.off_a2; P.off_b2 = t.off_b2; P.off_scratch = t.off_scratch; P.stage_off = t.stage_off;
   P.trace = trace_begin();
-  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  const int grid = persistent_grid(p, P.n_tiles);
   CUtensorMap x_map;
+  static const bool ana2_on = [] { const char* e = getenv("SC_ANA2"); return e == nullptr || atoi(e) != 0; }();   // =0: first generation (A/B runs)
+  if (t.v2_ok && ana2_on) {
+    P.n_stages = t.v2_stages; P.tmem_cols = 512;
+    P.off_f32 = 0; P.off_ring = 0; P.off_b1 = t.v2_off_b1; P.off_a2 = t.v2_off_b2; P.off_b2 = t.v2_off_b2; P.off_scratch = t.v2_off_scratch;
+    if (!cached_map(p, 2, images, (uint64_t)P.n_tiles * 128, (uint64_t)t.W, &x_map)) return false;
+    switch (t.N1) {
+#define SC_FA2_CASE(N)                                                                                           \
+  case N: {                                                                                                      \
+    static SmemOptIn opt_in;                                                                                     \
+    if (!ensure_dynamic_smem((const void*)k_fused_analysis2<N>, opt_in, p->device, t.v2_smem_bytes,              \
+                             "cudaFuncSetAttribute(k_fused_analysis2)")) return false;                          \
+    { void* args[] = {(void*)&P, (void*)&x_map};                                                               \
+      if (!cuda_ok(launch_pdl((const void*)k_fused_analysis2<N>, dim3(grid), dim3(FA_THREADS), t.v2_smem_bytes, st, args), \
+                   "k_fused_analysis2 launch")) return false; }                                             \
+  } break;
+      SC_FA2_CASE(16) SC_FA2_CASE(32) SC_FA2_CASE(48)
+#undef SC_FA2_CASE
+      default: set_error("fast_analyze: unsupported N1"); return false;
+    }
+    count_launch();
+    trace_end(P.trace, "analysis2");
+    return cuda_ok(cudaGetLastError(), "k_fused_analysis2 launch");
+  }
   if (!cached_map(p, 0, images, (uint64_t)P.n_tiles * 128, (uint64_t)t.W, &x_map)) return false;
   switch (t.N1) {
 #define SC_FA_CASE(N)                                                                                            \
@@ -2630,7 +3015,7 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   P.l2_stream_hint = l2_stream_hint_enabled();
   P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb; P.off_stage = t.off_stage;
   P.trace = trace_begin();
-  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  const int grid = persistent_grid(p, P.n_tiles);
   CUtensorMap out_map;
   if (!cached_map(p, 1, images_out, (uint64_t)P.n_tiles * 128, (uint64_t)t.W, &out_map)) return false;
   switch (t.N1) {
@@ -3089,7 +3474,7 @@ bool rows_analyze(const Plan* p, const float* x, int64_t rows, float* out, bool 
   P.n_tiles = (int)(rows / 128); P.slabs = t.slabs; P.out_cols = t.out_cols;
   P.f32_stages = t.f32_stages; P.ring_stages = t.ring_stages; P.tmem_cols = t.tmem_cols;
   P.off_f32 = t.off_f32; P.off_ring = t.off_ring; P.slot_bytes = t.slot_bytes; P.tab_bytes = t.tab_bytes;
-  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  const int grid = persistent_grid(p, P.n_tiles);
   CUtensorMap x_map;
   if (!cached_map(p, 0, x, (uint64_t)rows, (uint64_t)t.W, &x_map)) return false;
   switch (t.N1) {
@@ -3120,7 +3505,7 @@ bool rows_synthesize(const Plan* p, const float* u, int64_t rows, float* out, co
   P.rows_per_image = rows_per_image > 0 ? rows_per_image : 1;
   P.off_a = t.off_a; P.off_ustage = t.off_ustage; P.off_tab = t.off_tab; P.off_stage = t.off_stage;
   P.u_bytes = t.u_bytes; P.chunk_bytes = t.chunk_bytes;
-  const int grid = P.n_tiles < p->fast->sm_count ? P.n_tiles : p->fast->sm_count;
+  const int grid = persistent_grid(p, P.n_tiles);
   CUtensorMap out_map;
   if (!cached_map(p, 1, out, (uint64_t)rows, (uint64_t)t.W, &out_map)) return false;
   switch (t.N1) {

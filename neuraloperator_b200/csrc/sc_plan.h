@@ -49,6 +49,7 @@ struct Plan {
   int64_t weight_elems_per_io = 1;         // prod max_n_modes
   bool weight_block_is_whole = true;       // kept block == whole weight tensor
   bool fast_enabled = true;
+  int reserved_sms = 0;                    // SMs the persistent transform kernels leave free (for a concurrent collective)
   bool host_only = false;                  // tables computed on the host only, nothing uploaded (sc_problem_table)
   std::vector<float> h_TA, h_TAT, h_TS, h_TST;   // host copies of the last-dim tables
   FastTables* fast = nullptr;              // tcgen05 path state (nullptr when the shape does not qualify)
@@ -72,6 +73,10 @@ bool launch_complex_table_gemm_strided(const float2* T, int64_t sTp, int64_t sTq
 // out[p, q] (strided) = sum_{o,i} conj(A[o,p,i]) * B[o,q,i]
 bool launch_pair_reduce(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I,
                         cudaStream_t st);
+// the same reduction split over (o, i), one pass over the inputs, deterministic; scratch + a zeroed counter from the caller
+size_t pair_reduce_split_scratch_bytes(int64_t O, int P, int Q, int I);
+bool launch_pair_reduce_split(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I,
+                              float2* scratch, unsigned int* counter, cudaStream_t st);
 // CP pieces (sc_generic.cu, section 2c)
 bool launch_cp_scale(const float2* const* u, const int* k, int d, const float2* lambda, float2* scale, int R, int64_t M, cudaStream_t st);
 bool launch_cp_apply(const float2* in, const float2* scale, float2* out, bool conj_scale, int batch, int64_t per_batch, cudaStream_t st);

@@ -89,6 +89,10 @@ class Plan:
     def set_fast_path(self, enable: bool):
         _lib.check(self._lib.sc_plan_set_fast_path(self.handle, int(bool(enable))), "sc_plan_set_fast_path")
 
+    def set_reserved_sms(self, n_sms: int):
+        """Leave `n_sms` SMs free in the persistent transform launches (room for a concurrent NCCL collective)."""
+        _lib.check(self._lib.sc_plan_set_reserved_sms(self.handle, int(n_sms)), "sc_plan_set_reserved_sms")
+
     def uses_fast_path(self) -> int:
         return int(self._lib.sc_plan_uses_fast_path(self.handle))
 
@@ -135,6 +139,15 @@ def _stream_ptr(device) -> ctypes.c_void_p:
 
 def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _rank_array(core) -> ctypes.Array:
+    return (ctypes.c_int32 * core.ndim)(*[int(r) for r in core.shape])
+
+
+def _ptr_array(tensors) -> ctypes.Array:
+    """Host array of device pointers (`const sc_complex* const*` arguments)."""
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
 
 def _workspace(plan: Plan, n_images: int, device) -> torch.Tensor:
@@ -291,41 +304,40 @@ class _SpectralConvTucker(torch.autograd.Function):
     """y = SpectralConv.forward(x) with a Tucker weight, contracted factor by factor (einsum `abcd,fghi,bf,eg,ch,di->aecd`,
     reference :86-98):  xm -> U_in -> (core expanded along the mode axes with the kept rows of the mode factors) -> U_out.
     Inputs: x, core (r_in, r_out, r_1..r_d), U_in (Ci, r_in), U_out (Co, r_out), mode factors ALREADY sliced to the kept rows
-    (k_j, r_j) -- autograd handles the slicing --, bias.  `plan_kept` is a plan whose weight extents equal the kept modes."""
+    (k_j, r_j) -- autograd handles the slicing --, bias.  `plan_kept` is a plan whose weight extents equal the kept modes.
+    One C call per direction (`sc_forward_tucker` / `sc_backward_tucker`): the chain of ~20 launches is issued by the library
+    from one workspace, the only Python-side allocations are the outputs and the opaque saved-activation buffer."""
+
+    @staticmethod
+    def _args(plan, B, Ci, Co, core):
+        lib = _lib.load()
+        ranks = _rank_array(core)
+        ws_bytes = int(lib.sc_tucker_workspace_bytes(plan.handle, B, Ci, Co, ranks))
+        saved_elems = int(lib.sc_tucker_saved_elems(plan.handle, B, Ci, Co, ranks))
+        return ranks, ws_bytes, saved_elems
 
     @staticmethod
     def forward(ctx, x, bias, plan, plan_kept, core, u_in, u_out, *u_modes):
         lib = _lib.load()
         dev = x.device
         B, Ci = x.shape[:2]
-        Co, rg = u_out.shape
-        rf = u_in.shape[1]
+        Co = u_out.shape[0]
         d = plan.ndim
-        kept = plan.kept
-        M = plan.n_modes_total
-        ranks = list(core.shape[2:])
+        core = core.contiguous()
+        ranks, ws_bytes, saved_elems = _SpectralConvTucker._args(plan, B, Ci, Co, core)
+        y = torch.empty((B, Co, *plan.out_grid), dtype=torch.float32, device=dev)
+        saved = torch.empty(saved_elems, dtype=torch.complex64, device=dev)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        modes_ptrs = _ptr_array(u_modes)
+        b = bias.reshape(-1) if bias is not None else None
         with torch.cuda.device(dev):
-            xm = analyze(plan, x)                                                   # (B, Ci, *kept)
-            # expand the core along the mode axes, last axis first: A_d = core, A_{j-1} = U_j x_j A_j
-            chain = [core.contiguous()]
-            for j in range(d - 1, -1, -1):
-                outer = rf * rg
-                for l in range(j):
-                    outer *= ranks[l]
-                inner = 1
-                for l in range(j + 1, d):
-                    inner *= kept[l]
-                uj = u_modes[j]
-                chain.append(_table_contract(uj, uj.shape[1], 1, False, chain[-1], outer, kept[j], ranks[j], inner))
-            wc = chain[-1]                                                          # (rf, rg, *kept)
-            t1 = _table_contract(u_in, 1, rf, False, xm, B, rf, Ci, M)              # T[p=f, q=i] = U_in[i, f]
-            t2 = contract_dense(plan_kept, t1.view(B, rf, *kept), wc.view(rf, rg, *kept))
-            ym = _table_contract(u_out, rg, 1, False, t2, B, Co, rg, M)             # T[p=o, q=g] = U_out[o, g]
-            y = synthesize(plan, ym.view(B, Co, *kept), bias)
+            _lib.check(lib.sc_forward_tucker(plan.handle, plan_kept.handle, _ptr(x), _ptr(core), _ptr(u_in), _ptr(u_out), modes_ptrs, _ptr(b),
+                                             _ptr(y), _ptr(saved), B, Ci, Co, ranks, _ptr(ws), ws.numel(), _stream_ptr(dev)),
+                       "sc_forward_tucker")
         ctx.plan, ctx.plan_kept, ctx.d = plan, plan_kept, d
         ctx.bias_shape = bias.shape if bias is not None else None
-        ctx.dims = (B, Ci, Co, rf, rg, M, ranks)
-        ctx.save_for_backward(xm, t1, t2, wc, u_in, u_out, *u_modes, *chain[:-1])
+        ctx.dims = (B, Ci, Co)
+        ctx.save_for_backward(saved, core, u_in, u_out, *u_modes)
         return y
 
     @staticmethod
@@ -333,48 +345,29 @@ class _SpectralConvTucker(torch.autograd.Function):
     def backward(ctx, gy):
         lib = _lib.load()
         plan, plan_kept, d = ctx.plan, ctx.plan_kept, ctx.d
-        B, Ci, Co, rf, rg, M, ranks = ctx.dims
-        kept = plan.kept
-        saved = ctx.saved_tensors
-        xm, t1, t2, wc, u_in, u_out = saved[:6]
-        u_modes = saved[6:6 + d]
-        chain = saved[6 + d:]                    # A_d (= core), A_{d-1}, ..., A_1
+        B, Ci, Co = ctx.dims
+        saved, core, u_in, u_out = ctx.saved_tensors[:4]
+        u_modes = ctx.saved_tensors[4:4 + d]
         dev = gy.device
         gy = gy.contiguous()
-        cplx = dict(dtype=torch.complex64, device=dev)
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        ranks, ws_bytes, _ = _SpectralConvTucker._args(plan, B, Ci, Co, core)
+        dx = torch.empty((B, Ci, *plan.grid), dtype=torch.float32, device=dev)
+        d_core = torch.empty_like(core)
+        d_u_in = torch.empty_like(u_in)
+        d_u_out = torch.empty_like(u_out)
+        d_modes = [torch.empty_like(u) for u in u_modes]
+        db = torch.empty(Co, dtype=torch.float32, device=dev) if ctx.bias_shape is not None else None
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        modes_ptrs = _ptr_array(u_modes)
+        dmodes_ptrs = _ptr_array(d_modes)
         with torch.cuda.device(dev):
-            gm = analyze(plan, gy, adjoint=True)                                    # (B, Co, *kept)
-            db = None
-            if ctx.bias_shape is not None:
-                db = torch.empty(Co, dtype=torch.float32, device=dev)
-                _lib.check(lib.sc_bias_grad(plan.handle, _ptr(gm), _ptr(db), B, Co, _stream_ptr(dev)), "sc_bias_grad")
-                db = db.reshape(ctx.bias_shape)
-            # out side
-            g2 = _table_contract(u_out, 1, rg, True, gm, B, rg, Co, M)              # T[p=g, q=o] = conj(U_out[o, g])
-            d_u_out = _pair_reduce(t2, gm, torch.empty(Co, rg, **cplx), 1, rg, B, rg, Co, M)      # out[(g,o)] -> dU_out[o, g]
-            # core side: the same two mode GEMMs as the dense backward, on rank channels
-            g1, d_wc, _ = contract_dense_backward(plan_kept, t1.view(B, rf, *kept), g2.view(B, rg, *kept),
-                                                  wc.view(rf, rg, *kept), need_dbias=False)
-            # in side
-            d_u_in = _pair_reduce(xm, g1, torch.empty(Ci, rf, **cplx), rf, 1, B, Ci, rf, M)       # out[(i,f)] -> dU_in[i, f]
-            dxm = _table_contract(u_in, rf, 1, True, g1, B, Ci, rf, M)              # T[p=i, q=f] = conj(U_in[i, f])
-            dx = synthesize(plan, dxm.view(B, Ci, *kept), adjoint=True)
-            # mode factors and core: undo the expansion chain, first axis first
-            d_modes = [None] * d
-            d_a = d_wc.reshape(-1)
-            for j in range(d):
-                a_j = chain[d - 1 - j]                                               # A_{j+1} in 1-based terms: before axis j was expanded
-                outer = rf * rg
-                for l in range(j):
-                    outer *= ranks[l]
-                inner = 1
-                for l in range(j + 1, d):
-                    inner *= kept[l]
-                uj = u_modes[j]
-                d_modes[j] = _pair_reduce(a_j, d_a, torch.empty(kept[j], ranks[j], **cplx), 1, ranks[j], outer, ranks[j],
-                                          kept[j], inner)                           # out[(h,m)] -> dU_j[m, h]
-                d_a = _table_contract(uj, 1, ranks[j], True, d_a, outer, ranks[j], kept[j], inner)   # T[p=h, q=m] = conj(U_j[m, h])
-            d_core = d_a.view(rf, rg, *ranks)
+            _lib.check(lib.sc_backward_tucker(plan.handle, plan_kept.handle, _ptr(gy), _ptr(core), _ptr(u_in), _ptr(u_out), modes_ptrs,
+                                              _ptr(saved), _ptr(dx), _ptr(d_core), _ptr(d_u_in), _ptr(d_u_out), dmodes_ptrs, _ptr(db),
+                                              B, Ci, Co, ranks, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_backward_tucker")
+        if db is not None:
+            db = db.reshape(ctx.bias_shape)
         return (dx, db, None, None, d_core, d_u_in, d_u_out, *d_modes)
 
 

@@ -70,15 +70,47 @@ class _Lib:
         return 0
 
 
+    # the Tucker chain is one C call per direction: emulate the documented contract of the two entry points (the chain itself is
+    # checked on the GPU); what is checked here is the Python plumbing -- argument order, the saved buffer, which gradient goes where
+    def sc_tucker_workspace_bytes(self, plan, B, Ci, Co, ranks):
+        return 16
+
+    def sc_tucker_saved_elems(self, plan, B, Ci, Co, ranks):
+        return 0
+
+    def sc_forward_tucker(self, plan, plan_kept, x, core, u_in, u_out, u_modes, bias, y, saved, B, Ci, Co, ranks, ws, n, st):
+        self._tucker_x = x.detach().clone()
+        out = O.contract_tucker(x.to(torch.complex64), core, [u_in, u_out, *u_modes]).real
+        y.copy_(out + (bias.reshape(1, -1, *[1] * (out.ndim - 2)) if bias is not None else 0))
+        return 0
+
+    def sc_backward_tucker(self, plan, plan_kept, gy, core, u_in, u_out, u_modes, saved, dx, d_core, d_u_in, d_u_out, d_u_modes, dbias,
+                           B, Ci, Co, ranks, ws, n, st):
+        with torch.enable_grad():
+            ps = [t.detach().clone().requires_grad_(True) for t in (self._tucker_x, core, u_in, u_out, *u_modes)]
+            O.contract_tucker(ps[0].to(torch.complex64), ps[1], ps[2:]).real.backward(gy)
+        for dst, src in zip([dx, d_core, d_u_in, d_u_out, *d_u_modes], ps):
+            dst.copy_(src.grad)
+        if dbias is not None:
+            dbias.copy_(gy.sum(dim=[0] + list(range(2, gy.ndim))))
+        return 0
+
+
+_LIB = _Lib()
+
+
 class _Plan:
     def __init__(self, kept):
         self.kept, self.ndim, self.n_modes_total, self.handle = list(kept), len(kept), math.prod(kept), None
+        self.grid = self.out_grid = list(kept)
 
 
 @pytest.fixture
 def emulated(monkeypatch):
     """analysis = real -> complex embedding, synthesis = real part (+ bias): a valid adjoint pair, so the transforms drop out."""
-    monkeypatch.setattr(sc._lib, "load", lambda: _Lib())
+    monkeypatch.setattr(sc._lib, "load", lambda: _LIB)
+    monkeypatch.setattr(sc, "_ptr_array", lambda ts: list(ts))
+    monkeypatch.setattr(sc, "_rank_array", lambda core: [int(r) for r in core.shape])
     monkeypatch.setattr(sc._lib, "check", lambda rc, what: None)
     monkeypatch.setattr(sc, "_ptr", lambda t: t)
     monkeypatch.setattr(sc, "_stream_ptr", lambda dev: None)
@@ -148,7 +180,7 @@ def test_tucker_chain(emulated, kept):
     ranks = [2, 3] + [2 + (j % 2) for j in range(d)]
     params = [torch.randn(B, Ci, *kept), torch.randn(Co, *[1] * d), _c(*ranks), _c(Ci, ranks[0]), _c(Co, ranks[1]),
               *[_c(k, r) for k, r in zip(kept, ranks[2:])]]
-    _compare(lambda x, b, core, ui, uo, *um: sc._SpectralConvTucker.apply(x, b, _Plan(kept), None, core, ui, uo, *um),
+    _compare(lambda x, b, core, ui, uo, *um: sc._SpectralConvTucker.apply(x, b, _Plan(kept), _Plan(kept), core, ui, uo, *um),
              lambda x, b, core, ui, uo, *um: O.contract_tucker(x.to(torch.complex64), core, [ui, uo, *um]).real + b,
              params, torch.randn(B, Co, *kept))
 
