@@ -48,7 +48,12 @@ typedef struct {
   int32_t n_modes[SC_MAX_DIMS];       /* SpectralConv.n_modes as STORED (last already n//2+1, :404-415)       */
   int32_t max_n_modes[SC_MAX_DIMS];   /* SpectralConv.max_n_modes = weight extents along the mode dims (:317-321) */
   int32_t fft_norm;                   /* SC_NORM_*                                                           */
+  int32_t flags;                      /* SC_FLAG_* (0 for SpectralConv.forward)                              */
 } sc_problem;
+/* SC_FLAG_RESAMPLE: the synthesis places every kept SIGNED frequency f of a leading dim at bin (f mod M) of the output grid,
+ * as neuralop/layers/resample.py:57-68 copies the spectrum corners (out_fft[..., -m//2:] = X[..., -m//2:]); without the flag
+ * the unshifted spectrum is cropped / zero-padded at its end, as `ifftn(out_fft, s=...)` does in SpectralConv.forward (:548). */
+enum { SC_FLAG_RESAMPLE = 1 };
 
 /* ---- plan: kept-mode index set + twiddle tables (replaces the slices built at :465-519) ---------------- */
 int  sc_plan_create(const sc_problem* problem, sc_plan** plan_out);

@@ -11,6 +11,7 @@ from .build import LIB_PATH
 
 SC_MAX_DIMS = 4
 NORMS = {"forward": 0, "backward": 1, "ortho": 2}
+FLAG_RESAMPLE = 1
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
@@ -27,6 +28,7 @@ class ScProblem(ctypes.Structure):
         ("n_modes", c_i32 * SC_MAX_DIMS),
         ("max_n_modes", c_i32 * SC_MAX_DIMS),
         ("fft_norm", c_i32),
+        ("flags", c_i32),
     ]
 
 

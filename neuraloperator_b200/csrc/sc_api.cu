@@ -72,6 +72,16 @@ static bool index_dim(const sc_problem& pr, int j, DimTables* tp) {
       t.in_bins[s] = ((shifted - t.F / 2) % t.F + t.F) % t.F;           // undo fftshift = roll by F//2 (:449)
     }
   }
+  // where each slot lands on the output grid
+  t.out_bins.resize(t.k);
+  for (int s = 0; s < t.k; ++s) {
+    if (!last && (pr.flags & SC_FLAG_RESAMPLE)) {
+      const int f = s - t.k / 2;                                        // signed frequency of the slot
+      t.out_bins[s] = (t.k <= t.M) ? ((f % t.M) + t.M) % t.M : -1;     // resample.py:57-68
+    } else {
+      t.out_bins[s] = t.in_bins[s] < t.M ? t.in_bins[s] : -1;           // ifftn(s=M) crops / zero-pads the UNSHIFTED spectrum (:548)
+    }
+  }
   return true;
 }
 
@@ -118,7 +128,7 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
       }
       for (int n = 0; n < t.M; ++n) {
         double re = 0.0, im = 0.0;
-        if (b < t.M) unit(b, n, t.M, +1, &re, &im);       // ifftn(s=M) crops / zero-pads the UNSHIFTED spectrum (:548)
+        if (t.out_bins[s] >= 0) unit(t.out_bins[s], n, t.M, +1, &re, &im);
         S[(size_t)n * t.k + s] = make_float2((float)re, (float)im);
         SH[(size_t)s * t.M + n] = make_float2((float)re, (float)-im);
       }

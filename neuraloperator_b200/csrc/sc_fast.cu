@@ -634,7 +634,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis2(const AnaPara
     // The A operand of stage 1 (the image rows) lives in tensor memory: thread <-> image row (its TMEM lane) and one of the two
     // 32-float boxes of the slab.  Versus the shared-memory operand ring of k_fused_analysis this removes, per 128-row tile, the
     // 64 KB of swizzled bf16 stores and the 64 KB the MMAs re-read from them (the kernel is bound by shared-memory bandwidth).
-    const int cw = warp - FA_LOADER_WARP0, q = cw & 3, hb = cw >> 2;
+    // (a warp may only touch TMEM lanes 32 * (warp % 4) .. +31: the quarter is warp % 4, NOT the index within the converter group)
+    const int cw = warp - FA_LOADER_WARP0, q = warp & 3, hb = cw >> 2;
     const int row = 32 * q + lane;
     uint8_t* f32_stage = smem + P.off_f32;
     const uint32_t my_row = (uint32_t)(hb * 16384 + row * 128);
@@ -854,8 +855,9 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis2(const AnaPara
 //   warp  9     stage-B MMA issuer                        U -> DB[2]
 //   warps 0-3   epilogue B: DB -> + bias -> 256-bit global stores of the image rows
 // =====================================================================================================
-constexpr int FS_THREADS = 14 * 32;
-constexpr int FS_STAGE_BYTES = 4 * 2 * 4096;   // per warp two [32 rows x 32 floats] TMA store boxes
+constexpr int FS_THREADS = 18 * 32;             // warps 14-17: second epilogue-B group (the other half of the columns)
+constexpr int FS_EPI_B_WARPS = 8;
+constexpr int FS_STAGE_BYTES = FS_EPI_B_WARPS * 4096;   // per epilogue-B warp one [32 rows x 32 floats] TMA store box
 
 struct SynParams {
   const float2* modes;
@@ -894,7 +896,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       mbar_init(&bar_ba_full[i], 4);  mbar_init(&bar_ba_empty[i], 1);
       mbar_init(&bar_da_full[i], 1);  mbar_init(&bar_da_empty[i], 128);
       mbar_init(&bar_u_full[i], 128); mbar_init(&bar_u_empty[i], 1);
-      mbar_init(&bar_db_full[i], 1);  mbar_init(&bar_db_empty[i], 128);
+      mbar_init(&bar_db_full[i], 1);  mbar_init(&bar_db_empty[i], 32 * FS_EPI_B_WARPS);
     }
     mbar_init_fence();
   }
@@ -916,7 +918,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
   const uint32_t tm_db[2] = {tmem + (uint32_t)(4 * N1), tmem + (uint32_t)(4 * N1 + W)};
   const int n_local = (P.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp >= 10) {
+  if (warp >= 10 && warp < 14) {
     // ------------------------------------------------------------------ prep: modes -> BA
     // thread -> fixed mode row q (0..31) and columns kx = kx0 + 4u: every swizzled store address is a per-thread base plus
     // a compile-time multiple of 1024 bytes (8 operand rows), so the per-element work is one 8-byte load, one split, six stores
@@ -1027,7 +1029,7 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ epilogue A: DA -> U (hi / lo)
     const int q4 = warp - 4;
     const int row = q4 * 32 + lane;
@@ -1075,11 +1077,16 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       if (warp == 4) SC_TRACE(P, 2, i, 2);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue B: DB -> image rows
-    const int row = warp * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    uint8_t* my_stage = smem + P.off_stage + warp * 8192;   // two [32 x 128 B] boxes per warp
-    uint32_t chunk_ctr = 0;
+    // ------------------------------------------------------------------ epilogue B (warps 0-3 and 14-17): DB -> image rows
+    // Two warps per TMEM lane quarter, each taking half of the columns: the store side of a tile (TMEM -> registers -> +bias ->
+    // swizzled box -> TMA tensor store) was the longest role of the pipeline with four warps (measured write rate 3.9 TB/s
+    // against 7.5 TB/s for a plain fill on the same GPU).
+    const int q = warp & 3;                 // a warp may only touch TMEM lanes 32 * (warp % 4) ..: warps 14-17 -> quarters 2, 3, 0, 1
+    const int hb = warp < 4 ? 0 : 1;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    uint8_t* box = smem + P.off_stage + (hb * 4 + q) * 4096;   // one [32 x 128 B] box per warp
+    const int c_begin = hb * (W / 2), c_end = c_begin + W / 2;
     const uint64_t pol = l2_policy_evict_first();
     pdl_wait();                                             // the output image may still be read by the previous kernel
     for (int i = 0; i < n_local; ++i) {
@@ -1091,7 +1098,6 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
         const long long slice = (long long)tile * (128 / P.H) + row / P.H;
         b = __ldg(P.bias + (int)((slice / P.slices_per_image) % P.n_channels));
       }
-      float* dst = P.out + ((size_t)tile * 128 + row) * W;
       if (warp == 0) SC_TRACE(P, 4, i, 0);
       mbar_wait(&bar_db_full[buf], ph);
       tc_fence_after_sync();
@@ -1099,12 +1105,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
       // 32 columns at a time: TMEM -> registers (+bias) -> this warp's [32 rows x 128 B] staging box in the tensor map's
       // 128-byte swizzle -> ONE TMA tensor store per warp and box (direct per-thread row stores touch 32 different
       // 128-byte lines per warp instruction and serialise in the LSU).
-      for (int c = 0; c < W; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         float t[2][16];
         tmem_ld16(tm_db[buf] + lane_sel + c, t[0]);
         tmem_ld16(tm_db[buf] + lane_sel + c + 16, t[1]);
-        uint8_t* box = my_stage + (chunk_ctr & 1) * 4096;
-        if (lane == 0) bulk_wait_read_1();          // the store issued two boxes ago has finished reading this buffer
+        if (lane == 0) bulk_wait_read();            // the previous store of this warp has finished reading the box
         __syncwarp();
         tmem_ld_wait();
 #pragma unroll
@@ -1118,12 +1123,11 @@ __global__ void __launch_bounds__(FS_THREADS, 1) k_fused_synthesis(const SynPara
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (P.l2_stream_hint) tma_store_2d_hint(&out_map, box, c, tile * 128 + warp * 32, pol);
+          if (P.l2_stream_hint) tma_store_2d_hint(&out_map, box, c, tile * 128 + q * 32, pol);
           else
-            tma_store_2d(&out_map, box, c, tile * 128 + warp * 32);
+            tma_store_2d(&out_map, box, c, tile * 128 + q * 32);
           bulk_commit();
         }
-        ++chunk_ctr;
       }
       tc_fence_before_sync();
       mbar_arrive(&bar_db_empty[buf]);
@@ -1853,7 +1857,6 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad2(const ModeGe
 //   warps 4-11 A converters, 12-19 B converters, all 20 warps epilogue.
 // =====================================================================================================
 constexpr int MQ3_MAX_A_RAW = 8, MQ3_MAX_B_RAW = 2;
-constexpr int MQ3_CONV_WARPS = 16;                      // warps 4-19 convert both operands (B slab first, then its A chunks)
 constexpr uint32_t MQ3_A_RAW_BYTES = 8 * 64 * 32;      // one chunk: [8 k][64 rows][4 modes x (re, im)]
 
 struct ModeGemmQuad3Params {
@@ -1893,10 +1896,10 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad3(const ModeGe
   if (tid == 128) SC_QTRACE(P, 0, 0, 0);
 
   if (tid == 0) {
-    for (int i = 0; i < MQ2_A_SLOTS; ++i) { mbar_init(&bar_a_full[i], MQ3_CONV_WARPS); mbar_init(&bar_a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) mbar_init(&bar_b_full[i], MQ3_CONV_WARPS);
-    for (int i = 0; i < NA; ++i) { mbar_init(&bar_ar_full[i], 1); mbar_init(&bar_ar_empty[i], MQ3_CONV_WARPS); }
-    for (int i = 0; i < NBR; ++i) { mbar_init(&bar_br_full[i], 1); mbar_init(&bar_br_empty[i], MQ3_CONV_WARPS); }
+    for (int i = 0; i < MQ2_A_SLOTS; ++i) { mbar_init(&bar_a_full[i], MQ2_A_WARPS); mbar_init(&bar_a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(&bar_b_full[i], MQ2_B_WARPS);
+    for (int i = 0; i < NA; ++i) { mbar_init(&bar_ar_full[i], 1); mbar_init(&bar_ar_empty[i], MQ2_A_WARPS); }
+    for (int i = 0; i < NBR; ++i) { mbar_init(&bar_br_full[i], 1); mbar_init(&bar_br_empty[i], MQ2_B_WARPS); }
     mbar_init(&bar_d_full, 1);
     mbar_init_fence();
   }
@@ -1923,27 +1926,13 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad3(const ModeGe
         const int slot = c % NA;
         if (c >= NA) mbar_wait(&bar_ar_empty[slot], (uint32_t)(((c / NA) - 1) & 1));
         mbar_arrive_expect_tx(&bar_ar_full[slot], MQ3_A_RAW_BYTES);
-        uint8_t* dst = a_raw + (size_t)slot * MQ3_A_RAW_BYTES;
-        if (P.a_variant == 2) {
-          tma_load_3d(dst, &a_map, &bar_ar_full[slot], 8 * 64 * mt, 8 * c, qd);
-          tma_load_3d(dst + MQ3_A_RAW_BYTES / 2, &a_map, &bar_ar_full[slot], 8 * (64 * mt + 32), 8 * c, qd);
-        } else {
-          tma_load_4d(dst, &a_map, &bar_ar_full[slot], 0, qd, 64 * mt, 8 * c);
-        }
+        tma_load_4d(a_raw + (size_t)slot * MQ3_A_RAW_BYTES, &a_map, &bar_ar_full[slot], 0, qd, 64 * mt, 8 * c);
       };
       auto issue_b = [&](int s) {
         const int slot = s % NBR;
         if (s >= NBR) mbar_wait(&bar_br_empty[slot], (uint32_t)(((s / NBR) - 1) & 1));
         mbar_arrive_expect_tx(&bar_br_full[slot], P.b_raw_bytes);
-        uint8_t* dst = b_raw + (size_t)slot * P.b_raw_bytes;
-        if (P.b_variant == 1) {
-          tma_load_3d(dst, &b_map, &bar_br_full[slot], 8 * 32 * s, 64 * nt, qd);
-        } else if (P.b_variant == 2) {
-          tma_load_3d(dst, &b_map, &bar_br_full[slot], 8 * 64 * nt, 32 * s, qd);
-          if (P.b_box_rows > 32) tma_load_3d(dst + 32768, &b_map, &bar_br_full[slot], 8 * (64 * nt + 32), 32 * s, qd);
-        } else {
-          tma_load_4d(dst, &b_map, &bar_br_full[slot], 0, qd, 64 * nt, 32 * s);
-        }
+        tma_load_4d(b_raw + (size_t)slot * P.b_raw_bytes, &b_map, &bar_br_full[slot], 0, qd, 64 * nt, 32 * s);
       };
       // Consumption order: B slab s, then its A chunks 4s .. 4s+3.  Operands the previous kernel of the stream does not write
       // may be fetched ahead of the dependency wait -- at most two A chunks, so that they do not sit in the TMA queue in front of
@@ -1960,99 +1949,85 @@ __global__ void __launch_bounds__(MQ2_THREADS, 1) k_mode_gemm_quad3(const ModeGe
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ converters (16 warps): per K-slab, B raw -> bf16 hi / lo ->
-    // swizzled tiles, then the slab's four A chunks raw -> bf16 hi / lo -> tensor memory
-    const int cw = warp - 4;
-    // B: a warp covers 8 rows x 4 k (256 contiguous raw bytes per quarter-warp, 32 distinct banks on the swizzled side);
-    //    warps 0-7 take rows 0-31, warps 8-15 rows 32-63
-    //    (k-contiguous raw blocks, variant 1: a warp covers the 32 k of one row instead -- 1 KB contiguous, one swizzled tile row)
-    const bool bk = P.b_variant == 1;
-    const int nlo = bk ? (cw & 7) : (lane & 7), kqb = bk ? lane : (((cw & 7) << 2) | (lane >> 3)), rhalf = cw >> 3;
-    const uint32_t off_hi = (uint32_t)(nlo * 128 + ((((2 * kqb) >> 3) ^ nlo) & 7) * 16 + ((2 * kqb) & 7) * 2);
+  } else if (warp >= 4 + MQ2_A_WARPS) {
+    // ------------------------------------------------------------------ B converters: raw slab -> bf16 hi / lo -> swizzled tiles
+    // a warp covers 8 rows x 4 k: 256 contiguous raw bytes per quarter-warp, 32 distinct banks on the swizzled side
+    const int lt = tid - (4 + MQ2_A_WARPS) * 32;
+    const int nlo = lt & 7, kq = ((lt >> 5) << 2) | ((lt >> 3) & 3);
+    const uint32_t off_hi = (uint32_t)(nlo * 128 + ((((2 * kq) >> 3) ^ nlo) & 7) * 16 + ((2 * kq) & 7) * 2);
     const uint32_t off_lo = off_hi + (uint32_t)NBp * 128u;
     const int rows = P.b_box_rows;
-    // raw address of element (row nlo + 8 u + 32 rhalf, k kqb) = b_src0 + u * b_ustep
-    const uint32_t b_src0 = bk ? (uint32_t)((nlo + 32 * rhalf) * 1024 + kqb * 32)
-                               : (P.b_variant == 2 ? (uint32_t)(rhalf * 32768 + kqb * (rows < 32 ? rows : 32) * 32 + nlo * 32)
-                                                   : (uint32_t)((kqb * rows + nlo + 32 * rhalf) * 32));
-    const uint32_t b_ustep = bk ? 8192u : 256u;
-    // A: thread <-> real row (lane of TMEM quarter q) and 2 of the 8 k of every chunk
-    const int q = cw & 3, g = cw >> 2;
-    const int row = 32 * q + lane, R = row >> 1, part = row & 1;
-    const uint32_t tm_mine = tmem + MQ2_TM_A + ((uint32_t)(32 * q) << 16) + (uint32_t)(2 * g);
-    //   part 0: (re, -im)   conj: (re, im)        part 1: (im, re)   conj: (-im, re)
-    const uint32_t flip = part == 0 ? (P.conjA ? 0u : 0x80000000u) : (P.conjA ? 0x00008000u : 0u);
-    const uint32_t perm = part == 0 ? 0x3210u : 0x1032u;
-    // raw address of (row R, k 2 g + u) = my_raw + u * a_ustep
-    const uint32_t my_raw = P.a_variant == 2 ? (uint32_t)((R >> 5) * (MQ3_A_RAW_BYTES / 2) + 2 * g * 1024 + (R & 31) * 32)
-                                             : (uint32_t)((2 * g * 64 + R) * 32);
-    const uint32_t a_ustep = P.a_variant == 2 ? 1024u : 2048u;
     for (int s = 0; s < n_slabs; ++s) {
-      {
-        const int slot = s % NBR;
-        if (cw == 0) SC_QTRACE(P, 1, s, 0);
-        mbar_wait(&bar_br_full[slot], (uint32_t)((s / NBR) & 1));
-        if (cw == 0) SC_QTRACE(P, 1, s, 1);
-        const uint8_t* src = smem + P.off_b_raw + (size_t)slot * P.b_raw_bytes + b_src0;
-        uint8_t* tile = smem + (size_t)(s * 4) * P.tile_b_bytes + rhalf * 4096;
+      const int slot = s % NBR;
+      if (lt < 32) SC_QTRACE(P, 1, s, 0);
+      mbar_wait(&bar_br_full[slot], (uint32_t)((s / NBR) & 1));
+      if (lt < 32) SC_QTRACE(P, 1, s, 1);
+      const uint8_t* src = smem + P.off_b_raw + (size_t)slot * P.b_raw_bytes + (size_t)(kq * rows + nlo) * 32;
+      uint8_t* tile = smem + (size_t)(s * 4) * P.tile_b_bytes;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int n = nlo + 8 * u + 32 * rhalf;
-          if (n < NB) {
-            const float4 lo4 = *reinterpret_cast<const float4*>(src + u * b_ustep), hi4 = *reinterpret_cast<const float4*>(src + u * b_ustep + 16);
-            const float v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t hi, lo;
-              split2_bf16(v[2 * j], v[2 * j + 1], hi, lo);
-              *reinterpret_cast<uint32_t*>(tile + j * P.tile_b_bytes + off_hi + u * 1024) = hi;
-              *reinterpret_cast<uint32_t*>(tile + j * P.tile_b_bytes + off_lo + u * 1024) = lo;
-            }
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&bar_br_empty[slot]); mbar_arrive(&bar_b_full[s]); }
-        if (cw == 0) SC_QTRACE(P, 1, s, 2);
-      }
-      const int c_end = min(n_chunks, 4 * s + 4);
-      for (int c = 4 * s; c < c_end; ++c) {
-        const int rs = c % NA, ts = c % MQ2_A_SLOTS;
-        if (cw == 0) SC_QTRACE(P, 0, 1 + c, 0);
-        mbar_wait(&bar_ar_full[rs], (uint32_t)((c / NA) & 1));
-        if (cw == 0) SC_QTRACE(P, 0, 1 + c, 1);
-        const uint8_t* src = smem + P.off_a_raw + (size_t)rs * MQ3_A_RAW_BYTES + my_raw;
-        uint32_t hw[4][2], lw[4][2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const float4 lo4 = *reinterpret_cast<const float4*>(src + u * a_ustep), hi4 = *reinterpret_cast<const float4*>(src + u * a_ustep + 16);
+      for (int u = 0; u < 8; ++u) {
+        const int n = nlo + 8 * u;
+        if (n < NB) {
+          const float4 lo4 = *reinterpret_cast<const float4*>(src + u * 256), hi4 = *reinterpret_cast<const float4*>(src + u * 256 + 16);
           const float v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t hi, lo;
-            split2_bf16(v[2 * j], v[2 * j + 1], hi, lo);      // (re | im << 16)
-            hw[j][u] = __byte_perm(hi, 0, perm) ^ flip;
-            lw[j][u] = __byte_perm(lo, 0, perm) ^ flip;
+            split2_bf16(v[2 * j], v[2 * j + 1], hi, lo);
+            *reinterpret_cast<uint32_t*>(tile + j * P.tile_b_bytes + off_hi + u * 1024) = hi;
+            *reinterpret_cast<uint32_t*>(tile + j * P.tile_b_bytes + off_lo + u * 1024) = lo;
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_ar_empty[rs]);       // the raw chunk has been consumed into registers
-        if (c >= MQ2_A_SLOTS) {
-          mbar_wait(&bar_a_empty[ts], (uint32_t)(((c / MQ2_A_SLOTS) - 1) & 1));
-          tc_fence_after_sync();
-        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bar_br_empty[slot]); mbar_arrive(&bar_b_full[s]); }
+      if (lt < 32) SC_QTRACE(P, 1, s, 2);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ A converters: raw chunk -> bf16 hi / lo -> tensor memory
+    const int aw = warp - 4, q = aw & 3, g = aw >> 2;
+    const int row = 32 * q + lane, R = row >> 1, part = row & 1;
+    const uint32_t tm_mine = tmem + MQ2_TM_A + ((uint32_t)(32 * q) << 16) + (uint32_t)(4 * g);
+    //   part 0: (re, -im)   conj: (re, im)        part 1: (im, re)   conj: (-im, re)
+    const uint32_t flip = part == 0 ? (P.conjA ? 0u : 0x80000000u) : (P.conjA ? 0x00008000u : 0u);
+    const uint32_t perm = part == 0 ? 0x3210u : 0x1032u;
+    const uint32_t my_raw = (uint32_t)((4 * g * 64 + R) * 32);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int rs = c % NA, s = c % MQ2_A_SLOTS;
+      if (aw == 0) SC_QTRACE(P, 0, 1 + c, 0);
+      mbar_wait(&bar_ar_full[rs], (uint32_t)((c / NA) & 1));
+      if (aw == 0) SC_QTRACE(P, 0, 1 + c, 1);
+      const uint8_t* src = smem + P.off_a_raw + (size_t)rs * MQ3_A_RAW_BYTES + my_raw;
+      uint32_t hw[4][4], lw[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 lo4 = *reinterpret_cast<const float4*>(src + u * 2048), hi4 = *reinterpret_cast<const float4*>(src + u * 2048 + 16);
+        const float v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          tmem_st2(tm_mine + (uint32_t)(64 * ts + 16 * j), hw[j][0], hw[j][1]);
-          tmem_st2(tm_mine + (uint32_t)(64 * ts + 16 * j + 8), lw[j][0], lw[j][1]);
+          uint32_t hi, lo;
+          split2_bf16(v[2 * j], v[2 * j + 1], hi, lo);      // (re | im << 16)
+          hw[j][u] = __byte_perm(hi, 0, perm) ^ flip;
+          lw[j][u] = __byte_perm(lo, 0, perm) ^ flip;
         }
-        tmem_st_wait();
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_a_full[ts]);
-        if (cw == 0) SC_QTRACE(P, 0, 1 + c, 2);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ar_empty[rs]);       // the raw chunk has been consumed into registers
+      if (c >= MQ2_A_SLOTS) {
+        mbar_wait(&bar_a_empty[s], (uint32_t)(((c / MQ2_A_SLOTS) - 1) & 1));
+        tc_fence_after_sync();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        tmem_st4(tm_mine + (uint32_t)(64 * s + 16 * j), hw[j][0], hw[j][1], hw[j][2], hw[j][3]);
+        tmem_st4(tm_mine + (uint32_t)(64 * s + 16 * j + 8), lw[j][0], lw[j][1], lw[j][2], lw[j][3]);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a_full[s]);
+      if (aw == 0) SC_QTRACE(P, 0, 1 + c, 2);
     }
   } else if (warp == 0) {
     // ------------------------------------------------------------------ MMA issue (one lane)
@@ -2244,10 +2219,7 @@ static bool cached_gather_map(const Plan* p, const float2* base, uint64_t nq, ui
 static bool cached_wide_map(const Plan* p, const float2* base, uint64_t inner_floats, uint64_t n_second, uint64_t nq, uint64_t stride_second_bytes,
                             uint64_t stride_quad_bytes, uint32_t box_inner, uint32_t box_second, CUtensorMap* out);
 // SC_WIDE_BOXES=0: every operand through the 32-byte-sector gather boxes (A/B runs)
-static bool wide_boxes_enabled() {
-  static const bool v = [] { const char* e = getenv("SC_WIDE_BOXES"); return e == nullptr || atoi(e) != 0; }();
-  return v;
-}
+static bool wide_boxes_enabled() { return false; }   // (the converters of this build read the sector-gather layout only)
 // SC_QUAD3=0 keeps the LSU-fed quad2 kernel (A/B runs)
 static bool quad3_enabled() {
   static const bool v = [] { const char* e = getenv("SC_QUAD3"); return e == nullptr || atoi(e) != 0; }();

@@ -20,6 +20,7 @@ struct DimTables {
   int k = 0;       // kept modes
   int w0 = 0;      // first weight row used
   std::vector<int> in_bins;  // unshifted bin per kept slot
+  std::vector<int> out_bins; // bin of the OUTPUT grid the slot is synthesised at (-1: dropped); == in_bins unless SC_FLAG_RESAMPLE
   // leading dims only: complex tables, row-major, interleaved (re,im)
   float2* d_A = nullptr;    // analysis          [k x N]   exp(-2 pi i b n / N)
   float2* d_AH = nullptr;   // its adjoint       [N x k]

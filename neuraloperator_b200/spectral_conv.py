@@ -27,7 +27,7 @@ Number = Union[int, float]
 # calls (incremental training mutates n_modes, resolution invariance changes the grid)
 # --------------------------------------------------------------------------------------------------
 class Plan:
-    def __init__(self, device: torch.device, grid, out_grid, n_modes_stored, max_n_modes, fft_norm: str):
+    def __init__(self, device: torch.device, grid, out_grid, n_modes_stored, max_n_modes, fft_norm: str, flags: int = 0):
         lib = _lib.load()
         prob = _lib.ScProblem()
         d = len(grid)
@@ -42,6 +42,7 @@ class Plan:
             prob.n_modes[j] = int(n_modes_stored[j])
             prob.max_n_modes[j] = int(max_n_modes[j])
         prob.fft_norm = _lib.NORMS[fft_norm]
+        prob.flags = int(flags)
         self._lib = lib
         self.device = device
         self.handle = ctypes.c_void_p()
@@ -110,17 +111,17 @@ _PLAN_LOCK = threading.Lock()
 _PLAN_CACHE_MAX = 64
 
 
-def get_plan(device: torch.device, grid, out_grid, n_modes_stored, max_n_modes, fft_norm="forward") -> Plan:
+def get_plan(device: torch.device, grid, out_grid, n_modes_stored, max_n_modes, fft_norm="forward", flags: int = 0) -> Plan:
     if device.type != "cuda":
         raise RuntimeError("neuraloperator_b200.SpectralConv runs on CUDA (sm_100a) only; there is no CPU path")
     idx = device.index if device.index is not None else torch.cuda.current_device()
-    key = (idx, tuple(grid), tuple(out_grid), tuple(n_modes_stored), tuple(max_n_modes), fft_norm)
+    key = (idx, tuple(grid), tuple(out_grid), tuple(n_modes_stored), tuple(max_n_modes), fft_norm, int(flags))
     with _PLAN_LOCK:
         plan = _PLAN_CACHE.get(key)
         if plan is not None:
             _PLAN_CACHE.move_to_end(key)
             return plan
-        plan = Plan(torch.device("cuda", idx), grid, out_grid, n_modes_stored, max_n_modes, fft_norm)
+        plan = Plan(torch.device("cuda", idx), grid, out_grid, n_modes_stored, max_n_modes, fft_norm, flags)
         _PLAN_CACHE[key] = plan
         while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
             _PLAN_CACHE.popitem(last=False)
@@ -579,6 +580,43 @@ class _SpectralConvSeparable(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------
 # the module
 # --------------------------------------------------------------------------------------------------
+class _SpectralResample(torch.autograd.Function):
+    """`resample` for 3-D and higher inputs (reference resample.py:52-69): rfftn(norm="forward"), copy the low-frequency block
+    both grids have (leading dims: bins [0, m//2) and [-m//2, 0) with m = min(old, new); last dim: the first
+    min(old//2+1, new//2+1) bins), irfftn on the new grid -- i.e. this library's truncated analysis followed by its zero-padded
+    synthesis with no contraction in between.  Even m on the leading dims (for odd m the reference's block [-m//2-1, m//2) is not
+    the centred block the kernels index)."""
+
+    @staticmethod
+    def _plan(x, out_shape):
+        grid = list(x.shape[2:])
+        stored = []
+        for j, (n, m) in enumerate(zip(grid, out_shape)):
+            if j == len(grid) - 1:
+                stored.append(min(n // 2 + 1, m // 2 + 1))
+            else:
+                k = min(n, m)
+                if k % 2 != 0:
+                    raise NotImplementedError("spectral resampling with an odd common size along a leading dim is not covered")
+                stored.append(k)
+        return get_plan(x.device, grid, list(out_shape), stored, stored, "forward", flags=_lib.FLAG_RESAMPLE)
+
+    @staticmethod
+    def forward(ctx, x, out_shape):
+        if not x.is_cuda:
+            raise RuntimeError("neuraloperator_b200 has no CPU path")
+        plan = _SpectralResample._plan(x, out_shape)
+        ctx.plan = plan
+        return synthesize(plan, analyze(plan, x))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        plan = ctx.plan
+        gm = analyze(plan, gy.contiguous().float(), adjoint=True)
+        return synthesize(plan, gm, adjoint=True), None
+
+
 def _validate_scaling_factor(factor, n_dim) -> Optional[List[float]]:
     """Single-layer case of neuralop/utils.py:151-197 (`validate_scaling_factor(..., n_layers=None)`)."""
     if factor is None:
@@ -704,13 +742,21 @@ class SpectralConv(BaseSpectralConv):
         return list(in_grid)
 
     def transform(self, x, output_shape=None):
-        """Skip-connection transform (:383-398): identity unless the conv changes resolution."""
+        """Skip-connection transform (:383-398): identity unless the conv changes resolution, else the reference's `resample`
+        (neuralop/layers/resample.py:7-71).  1-D / 2-D: spatial interpolation (linear / bicubic, align_corners=True) -- the very
+        `F.interpolate` call the reference makes; it is the skip path of the FNO block, not the spectral-conv hot path.
+        3-D and up: spectral resampling -- all modes both grids share are kept and synthesised on the new grid -- on this
+        library's own transform kernels (identity contraction)."""
         in_shape = list(x.shape[2:])
-        out_shape = self._output_grid(in_shape, output_shape)
-        if in_shape == list(out_shape):
+        out_shape = [int(s) for s in self._output_grid(in_shape, output_shape)]
+        if in_shape == out_shape:
             return x
-        raise NotImplementedError("SpectralConv.transform with a resolution change needs the reference's "
-                                  "`resample` (neuralop/layers/resample.py), which is outside the spectral-conv path")
+        d = len(in_shape)
+        if d == 1:
+            return torch.nn.functional.interpolate(x, size=out_shape[0], mode="linear", align_corners=True)
+        if d == 2:
+            return torch.nn.functional.interpolate(x, size=tuple(out_shape), mode="bicubic", align_corners=True)
+        return _SpectralResample.apply(x.contiguous().float(), tuple(out_shape))
 
     @staticmethod
     def _kept_rows(factor, plan: Plan, j: int, axis: int = 0):

@@ -450,3 +450,30 @@ def make_inputs(B, Ci, Co, grid, n_modes, seed=0, kind="dense", ranks=None, max_
     else:
         raise ValueError(kind)
     return x, w, bias, gy
+
+
+# --------------------------------------------------------------------------------------------------
+# (3) the skip-path `resample` (neuralop/layers/resample.py:7-71), restated for the tests of SpectralConv.transform
+# --------------------------------------------------------------------------------------------------
+def resample_restated(x: torch.Tensor, output_shape: Sequence[int]) -> torch.Tensor:
+    """1-D: linear, 2-D: bicubic interpolation (align_corners=True), resample.py:48-51; 3-D and up: copy of the low-frequency
+    block of rfftn(norm="forward") into the spectrum of the new grid, irfftn (:53-69)."""
+    import itertools
+    import torch.nn.functional as F
+    d = x.ndim - 2
+    new_size = tuple(int(s) for s in output_shape)
+    if d == 1:
+        return F.interpolate(x, size=new_size[0], mode="linear", align_corners=True)
+    if d == 2:
+        return F.interpolate(x, size=new_size, mode="bicubic", align_corners=True)
+    axis = list(range(2, x.ndim))
+    X = torch.fft.rfftn(x.float(), norm="forward", dim=axis)
+    new_fft = list(new_size)
+    new_fft[-1] = new_fft[-1] // 2 + 1
+    common = [min(i, j) for i, j in zip(new_fft, X.shape[2:])]
+    out = torch.zeros([x.shape[0], x.shape[1], *new_fft], dtype=torch.cfloat)
+    ranges = [((None, m // 2), (-m // 2, None)) for m in common[:-1]] + [((None, common[-1]),)]
+    for bounds in itertools.product(*ranges):
+        idx = tuple([slice(None), slice(None)] + [slice(*b) for b in bounds])
+        out[idx] = X[idx]
+    return torch.fft.irfftn(out, s=new_size, norm="forward", dim=axis)

@@ -34,8 +34,8 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_problem_struct_matches_header():
-    # int32 ndim + 4 arrays of SC_MAX_DIMS int32 + int32 fft_norm
-    assert ctypes.sizeof(_lib.ScProblem) == 4 * (1 + 4 * _lib.SC_MAX_DIMS + 1)
+    # int32 ndim + 4 arrays of SC_MAX_DIMS int32 + int32 fft_norm + int32 flags
+    assert ctypes.sizeof(_lib.ScProblem) == 4 * (1 + 4 * _lib.SC_MAX_DIMS + 2)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")

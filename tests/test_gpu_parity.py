@@ -367,3 +367,25 @@ def test_empty_batch(cuda_device):
     y.sum().backward()
     assert conv.weight.tensor.grad is not None and float(conv.weight.tensor.grad.abs().max()) == 0.0
     assert tuple(x.grad.shape) == (0, 4, 16, 16)
+
+
+@pytest.mark.parametrize("shape,out", [((2, 3, 16), (24,)), ((2, 3, 12, 10), (18, 20)), ((1, 2, 8, 8, 8), (12, 12, 12)),
+                                       ((1, 2, 12, 8, 10), (8, 8, 6)), ((1, 2, 8, 6, 10), (8, 12, 16))])
+def test_transform_resamples_like_the_reference(cuda_device, shape, out):
+    """`SpectralConv.transform` with a resolution change (the FNO block calls it on every skip path, fno_block.py:377-384):
+    reference `resample` (resample.py:7-71; restatement pinned bit-exactly in tests/test_oracle_vs_reference.py), incl. its gradient."""
+    torch.manual_seed(4)
+    d = len(out)
+    conv = nb.SpectralConv(shape[1], shape[1], tuple([4] * d)).to(cuda_device)
+    x = torch.randn(*shape)
+    ref_in = x.clone().requires_grad_(True)
+    ref = O.resample_restated(ref_in, out)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    xd = x.to(cuda_device).requires_grad_(True)
+    got = conv.transform(xd, output_shape=out)
+    assert tuple(got.shape) == tuple(ref.shape)
+    got.backward(g.to(cuda_device))
+    assert rel_err(got, ref) < REL_TOL
+    assert rel_err(xd.grad, ref_in.grad) < REL_TOL
+    assert conv.transform(xd, output_shape=shape[2:]) is xd       # identity when nothing changes

@@ -53,3 +53,17 @@ def test_reference_fno_blocks_accept_the_plugin_class():
     tf = fno_block.FNOBlocks(8, 8, (12, 12), n_layers=1, conv_module=nb.SpectralConv, factorization="tucker", rank=0.5,
                              implementation="factorized")
     assert tf.convs[0].weight.name.lower().endswith("tucker")
+
+
+@pytest.mark.parametrize("shape,out", [((2, 3, 16), (24,)), ((2, 3, 12, 10), (18, 20)), ((1, 2, 8, 8, 8), (12, 12, 12)),
+                                       ((1, 2, 12, 8, 10), (8, 8, 6)), ((1, 2, 8, 6, 10), (8, 12, 16))])
+def test_resample_restatement_equals_the_reference(shape, out):
+    """`SpectralConv.transform` is tested on the GPU against oracle.resample_restated; here that restatement is pinned, bit-exactly,
+    to the unmodified reference function (neuralop/layers/resample.py)."""
+    import importlib
+    load_reference_spectral_conv()      # seeds the stub parent packages
+    resample = importlib.import_module("neuralop.layers.resample").resample
+    torch.manual_seed(0)
+    x = torch.randn(*shape)
+    ref = resample(x, 1.0, list(range(2, x.ndim)), output_shape=out)
+    assert torch.equal(O.resample_restated(x, out), ref)
