@@ -110,6 +110,20 @@ def time_cuda(fn, warm, reps):
     return e0.elapsed_time(e1) / reps
 
 
+def time_cuda_rot(fn, warm, reps):
+    import torch
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 # BASELINE.json configs other than the headline one: (name, batch, channels, grid, n_modes, kind)
 OTHER_CONFIGS = [
     ("1 FNO1d Burgers", 16, 32, (1024,), (16,), "dense"),
@@ -409,6 +423,25 @@ def run_ours(args):
     del xs
     kept = plan.kept
     m_tot = kept[0] * kept[1]
+    # the other two kernels of the step, timed the same way (CUDA events, back to back, rotating buffers > L2 for the images)
+    kernels = None
+    if rank == 0:
+        ys = [torch.empty(B, C, H, W, device=dev) for _ in range(3)]
+        ym = torch.randn(B, C, *kept, dtype=torch.complex64, device=dev)
+        bias_v = conv.bias.detach().reshape(-1)
+        syn_ms = time_cuda_rot(lambda i: nb.synthesize(plan, ym, bias_v), 3, 21)
+        xm = torch.randn(B, C, *kept, dtype=torch.complex64, device=dev)
+        gm = torch.randn(B, C, *kept, dtype=torch.complex64, device=dev)
+        wt = conv.weight.tensor.detach()
+        cf_ms = time_cuda_rot(lambda i: nb.contract_dense(plan, xm, wt), 3, 21)
+        cb_ms = time_cuda_rot(lambda i: nb.contract_dense_backward(plan, xm, gm, wt), 3, 21)
+        syn_bytes = 4 * B * C * H * W + 8 * B * C * m_tot
+        con_bytes = 8 * (2 * B * C * m_tot + C * C * m_tot)
+        kernels = {"note": "standalone launches through the C ABI, standard mode layout, operands of the contractions L2-resident",
+                   "synthesis": {"ms": syn_ms, "bytes": syn_bytes, "gbs": syn_bytes / syn_ms / 1e6},
+                   "contract_fwd": {"ms": cf_ms, "bytes": con_bytes, "gbs": con_bytes / cf_ms / 1e6},
+                   "contract_bwd_dw_plus_dxm": {"ms": cb_ms, "bytes": 2 * con_bytes, "gbs": 2 * con_bytes / cb_ms / 1e6}}
+        del ys, ym, xm, gm
     analyze_bytes = 4 * B * C * H * W + 8 * B * C * m_tot
     peak, peak_src = measured_peaks()
     achieved = analyze_bytes / (analyze_ms * 1e-3) / 1e9
@@ -552,13 +585,19 @@ def run_ours(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_launch": analyze_bytes, "ms_per_launch": analyze_ms, "traffic": ncu_traffic(plan),
                          "step": {"bytes": step_bytes, "achieved": step_gbs, "frac": step_gbs / peak}},
+            "kernels": kernels,
             "cpu_baseline": cpu_base,
             "torch_gpu_baseline": torch_gpu,
             "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # The captured graph holds NCCL work: tearing the process group down under it has been seen to hang (2-GPU run, round 2).
+        # The line is out; leave without the collective teardown.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        torch.cuda.synchronize(dev)
+        os._exit(0)
     return 0
 
 

@@ -156,7 +156,8 @@ static bool build_plan(const sc_problem& pr, Plan* p) {
       // the reference also zeroes Im of the LAST bin of the input-sized spectrum when M is even (:552-559)
       const bool used = q < t.M / 2 + 1;
       const bool edge = (q == 0) || (t.M % 2 == 0 && q == t.M / 2);
-      const bool im_dead = edge || (t.M % 2 == 0 && q == t.F - 1);
+      // (that zeroing of the last input bin is SpectralConv.forward's; `resample` hands the spectrum to irfftn untouched)
+      const bool im_dead = edge || (!(pr.flags & SC_FLAG_RESAMPLE) && t.M % 2 == 0 && q == t.F - 1);
       const double cq = edge ? 1.0 : 2.0;
       for (int n = 0; n < t.M; ++n) {
         double re = 0.0, im = 0.0;

@@ -200,6 +200,7 @@ struct AnaParams {
   int quad_major;          // 1: modes are written in the quad-major layout out[quad][image][4 modes] (contraction operands become
                            //    contiguous 32-byte sectors along the image index), 0: out[image][modes]
   int G, Mt;               // images per tile, kept modes per image
+  int qm_tma;              // 1: quad-major output through one tensor store per tile (k_fused_analysis2, one image per tile)
   long long n_images;      // all images of the launch (the quad stride of the quad-major layout, in sectors)
   // Operands of the NEXT kernels of the chain (weights, saved modes) that this launch pulls into L2 while it streams the images:
   // the transform is bound by shared memory, not by DRAM, so the extra reads are free here, whereas the contraction kernels
@@ -534,7 +535,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis(const AnaParam
 constexpr int FA2_X_STAGES = 2, FA2_MAX_F32 = 6;
 
 template <int N1>
-__global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis2(const AnaParams P, const __grid_constant__ CUtensorMap x_map) {
+__global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis2(const AnaParams P, const __grid_constant__ CUtensorMap x_map,
+                                                                     const __grid_constant__ CUtensorMap qm_map) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms need 1024-byte alignment
   __shared__ uint64_t bar_full[FA2_X_STAGES], bar_empty[FA2_X_STAGES], bar_d1_full[2], bar_d1_empty[2], bar_b2_full, bar_b2_empty,
@@ -817,7 +819,15 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis2(const AnaPara
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 0) SC_TRACE(P, 6, i, 2);
-      if (P.quad_major) {
+      if (P.quad_major && P.qm_tma) {
+        // the tile's modes [quad][8 floats] go out as ONE tensor store (box {8 floats, 1 image, Mt/4 quads}): the TMA engine scatters
+        // the 32-byte sectors asynchronously (the per-thread store loop below cost ~1500 of this role's ~2700 cycles per tile)
+        if (tid == 0) {
+          const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+          tma_store_3d(&qm_map, stage, 0, tile, 0);
+          bulk_commit();
+        }
+      } else if (P.quad_major) {
         // one 32-byte sector per (image of the tile, quad of modes): element (image, m) lives at ((m >> 2) * n_images + image) * 4 + (m & 3)
         const int tile = (int)blockIdx.x + i * (int)gridDim.x;
         const int nq = P.Mt >> 2;
@@ -2217,7 +2227,7 @@ static bool cached_gather_map(const Plan* p, const float2* base, uint64_t nq, ui
                               uint64_t sk, uint32_t box_rows, uint32_t box_k, CUtensorMap* out);
 
 static bool cached_wide_map(const Plan* p, const float2* base, uint64_t inner_floats, uint64_t n_second, uint64_t nq, uint64_t stride_second_bytes,
-                            uint64_t stride_quad_bytes, uint32_t box_inner, uint32_t box_second, CUtensorMap* out);
+                            uint64_t stride_quad_bytes, uint32_t box_inner, uint32_t box_second, CUtensorMap* out, uint32_t box_quads = 1);
 // SC_WIDE_BOXES=0: every operand through the 32-byte-sector gather boxes (A/B runs)
 static bool wide_boxes_enabled() { return false; }   // (the converters of this build read the sector-gather layout only)
 // SC_QUAD3=0 keeps the LSU-fed quad2 kernel (A/B runs)
@@ -2763,20 +2773,20 @@ static bool make_slab_load_map(CUtensorMap* map, const float* base, uint64_t row
 
 // 3-D view {contiguous floats, second index, quads} of a quad-major tensor: one request per 1 KB row of the box
 static bool cached_wide_map(const Plan* p, const float2* base, uint64_t inner_floats, uint64_t n_second, uint64_t nq, uint64_t stride_second_bytes,
-                            uint64_t stride_quad_bytes, uint32_t box_inner, uint32_t box_second, CUtensorMap* out) {
+                            uint64_t stride_quad_bytes, uint32_t box_inner, uint32_t box_second, CUtensorMap* out, uint32_t box_quads) {
   FastTables* f = p->fast;
   std::lock_guard<std::mutex> lock(f->map_mutex);
   // shares the gather cache: rows = inner_floats, k = n_second, sr = 0 marks the 3-D kind
   for (const GatherMapCacheEntry& e : f->gather_cache)
     if (e.base == base && e.nq == nq && e.rows == inner_floats && e.k == n_second && e.sq == stride_quad_bytes && e.sr == 0 &&
-        e.sk == stride_second_bytes && e.box_rows == box_inner && e.box_k == box_second) { *out = e.map; return true; }
+        e.sk == stride_second_bytes && e.box_rows == box_inner && e.box_k == box_second + (box_quads << 16)) { *out = e.map; return true; }
   if (!thread_has_context()) cudaFree(nullptr);   // (see cached_map)
   EncodeTiledFn enc = tensor_map_encoder();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
-  GatherMapCacheEntry e{base, nq, inner_floats, n_second, stride_quad_bytes, 0, stride_second_bytes, box_inner, box_second, {}};
+  GatherMapCacheEntry e{base, nq, inner_floats, n_second, stride_quad_bytes, 0, stride_second_bytes, box_inner, box_second + (box_quads << 16), {}};
   const cuuint64_t dims[3] = {inner_floats, n_second, nq};
   const cuuint64_t strides[2] = {stride_second_bytes, stride_quad_bytes};
-  const cuuint32_t box[3] = {box_inner, box_second, 1};
+  const cuuint32_t box[3] = {box_inner, box_second, box_quads};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(base), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -2935,13 +2945,21 @@ bool fast_analyze(const Plan* p, const float* images, int64_t n_images, float2* 
     P.n_stages = t.v2_stages; P.tmem_cols = 512;
     P.off_f32 = 0; P.off_ring = 0; P.off_b1 = t.v2_off_b1; P.off_a2 = t.v2_off_b2; P.off_b2 = t.v2_off_b2; P.off_scratch = t.v2_off_scratch;
     if (!cached_map(p, 2, images, (uint64_t)P.n_tiles * 128, (uint64_t)t.W, &x_map)) return false;
+    CUtensorMap qm_map = x_map;   // (placeholder when unused)
+    static const bool qm_tma_on = [] { const char* e = getenv("SC_QM_TMA"); return e == nullptr || atoi(e) != 0; }();   // =0: store loop (A/B runs)
+    if (quad_major && qm_tma_on && t.G == 1 && P.Mt / 4 <= 256 && ((P.off_scratch + P.stage_off) % 128u) == 0 && (P.Mt * 8) % 128 == 0) {
+      // {8 floats, images, quads}: image stride 32 B, quad stride n_images * 32 B
+      if (!cached_wide_map(p, modes_out, 8, (uint64_t)n_images, (uint64_t)(P.Mt / 4), 32, (uint64_t)n_images * 32, 8, 1, &qm_map, (uint32_t)(P.Mt / 4)))
+        return false;
+      P.qm_tma = 1;
+    }
     switch (t.N1) {
 #define SC_FA2_CASE(N)                                                                                           \
   case N: {                                                                                                      \
     static SmemOptIn opt_in;                                                                                     \
     if (!ensure_dynamic_smem((const void*)k_fused_analysis2<N>, opt_in, p->device, t.v2_smem_bytes,              \
                              "cudaFuncSetAttribute(k_fused_analysis2)")) return false;                          \
-    { void* args[] = {(void*)&P, (void*)&x_map};                                                               \
+    { void* args[] = {(void*)&P, (void*)&x_map, (void*)&qm_map};                                              \
       if (!cuda_ok(launch_pdl((const void*)k_fused_analysis2<N>, dim3(grid), dim3(FA_THREADS), t.v2_smem_bytes, st, args), \
                    "k_fused_analysis2 launch")) return false; }                                             \
   } break;
@@ -2984,7 +3002,8 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
   P.n_channels = n_channels > 0 ? n_channels : 1; P.tmem_cols = t.tmem_cols;
   P.slices_per_image = slices_per_image > 0 ? slices_per_image : 1;
   P.quad_major = quad_major ? 1 : 0; P.KY = t.KY; P.n_images = n_images;
-  P.l2_stream_hint = l2_stream_hint_enabled();
+  static const int syn_hint = [] { const char* e = getenv("SC_SYN_STORE_HINT"); return e == nullptr ? -1 : atoi(e); }();   // A/B runs
+  P.l2_stream_hint = syn_hint >= 0 ? syn_hint : l2_stream_hint_enabled();
   P.off_aa = t.off_aa; P.off_ba = t.off_ba; P.off_u = t.off_u; P.off_bb = t.off_bb; P.off_stage = t.off_stage;
   P.trace = trace_begin();
   const int grid = persistent_grid(p, P.n_tiles);

@@ -243,6 +243,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* ssrc,
                "r"(x), "r"(y)
                : "memory");
 }
+// 3-D tiled TMA store shared -> global (dense box in shared memory)
+__device__ __forceinline__ void tma_store_3d(const void* tmap, const void* ssrc, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap), "r"(smem_u32(ssrc)),
+               "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
