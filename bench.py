@@ -321,7 +321,12 @@ def run_ours(args):
     conv = nb.SpectralConv(C, C, MODES).to(dev)
     x = torch.randn(B, C, H, W, device=dev, requires_grad=True)
     g = torch.randn(B, C, H, W, device=dev)
-    reducer = nb.GradientAllReducer(conv.parameters()) if world > 1 else None
+    # SC_ALLREDUCE=nccl: NCCL all-reduce; default: the library's own two-shot kernel over NVLink peer memory (sc_allreduce_p2p)
+    collective = os.environ.get("SC_ALLREDUCE", "p2p")
+    reducer = None
+    if world > 1:
+        reducer = (nb.PeerGradientAllReducer(conv.parameters(), n_ctas=int(os.environ.get("SC_ALLREDUCE_CTAS", "12")))
+                   if collective == "p2p" else nb.GradientAllReducer(conv.parameters()))
     reserved_sms = 0
     if reducer is not None:
         # backward all-reduces dweight / dbias itself: the collective starts on the library's grads_ready event (right after the
@@ -345,7 +350,17 @@ def run_ours(args):
     graph = None
     graph_error = None
     c0 = _lib.launch_count()
-    step_body()
+    try:
+        step_body()
+    except Exception as exc:   # noqa: BLE001 -- e.g. no CUDA symmetric memory on this box: fall back to the NCCL collective
+        if reducer is None or collective != "p2p":
+            raise
+        print(f"bench.py: peer-memory all-reduce unavailable ({exc!r}); using NCCL", file=sys.stderr, flush=True)
+        collective = "nccl"
+        reducer = nb.GradientAllReducer(conv.parameters())
+        conv.gradient_reducer = reducer
+        c0 = _lib.launch_count()
+        step_body()
     launches_per_step = _lib.launch_count() - c0       # kernels this library launches for one fwd+bwd
     torch.cuda.synchronize(dev)
     if not args.no_graph:
@@ -573,7 +588,9 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": "no flush: x, g, y, dx are 134 MB each (537 MB touched per step) > 126 MB L2",
                        "fast_path_mask": plan.uses_fast_path(), "cuda_graph": graph is not None, "cuda_graph_error": graph_error,
-                       "allreduce": None if world == 1 else ("one NCCL all-reduce (AVG) of dweight+dbias per step, started on the "
+                       "allreduce": None if world == 1 else (("one two-shot all-reduce kernel of this library over NVLink peer memory "
+                                    "(sc_allreduce_p2p, symmetric memory) " if collective == "p2p" else "one NCCL all-reduce (AVG) ")
+                                    + "of dweight+dbias per step, started on the "
                                     "grads_ready event after the dweight kernel, overlapping dxm + dx synthesis"
                                     + (", captured in the CUDA graph" if graph is not None else ", eager")),
                        "reserved_sms": reserved_sms},

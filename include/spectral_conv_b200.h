@@ -86,8 +86,9 @@ size_t sc_workspace_bytes(const sc_plan* plan, int64_t batch_times_channels);
 /* 0 = generic SIMT kernels only, 1 = tcgen05/TMA fused path where the shape qualifies (default) */
 int  sc_plan_set_fast_path(sc_plan* plan, int enable);
 int  sc_plan_uses_fast_path(const sc_plan* plan);
-/* The persistent transform kernels launch one CTA per SM; n_sms of them are left free (default 0) so that a collective running
- * on another stream (the data-parallel gradient all-reduce, see sc_backward_dense) finds room for its own CTAs. */
+/* The persistent transform kernels launch one CTA per SM; the dx synthesis of sc_backward_dense, when called with a grads_ready
+ * event, leaves n_sms of them free (default 0) so that the collective the caller runs on another stream (the data-parallel
+ * gradient all-reduce) finds room for its own CTAs. */
 int  sc_plan_set_reserved_sms(sc_plan* plan, int n_sms);
 
 /* ---- the two transforms ------------------------------------------------------------------------------- */
@@ -182,6 +183,16 @@ int sc_backward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const floa
                        sc_complex* d_core, sc_complex* d_u_in, sc_complex* d_u_out, sc_complex* const* d_u_modes, float* dbias,
                        int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks,
                        void* workspace, size_t workspace_bytes, sc_stream stream);
+
+/* ---- the one collective of the data-parallel step, over NVLink peer memory -------------------------------------------------
+ * In-place all-reduce of `n_floats` (multiple of 4) floats: result = scale * sum over ranks (scale = 1 / world_size averages, as
+ * DDP does, trainer.py:203-205).  peer_buffers[r] / peer_signal_pads[r] (HOST arrays of world_size DEVICE pointers) are rank r's
+ * buffer and zero-initialised flag pad as mapped into THIS process -- CUDA symmetric memory (torch.distributed._symmetric_memory:
+ * `rendezvous(...).buffer_ptrs / .signal_pad_ptrs`); the pad needs n_ctas * world_size 32-bit flags.  Every rank must call it with
+ * the same n_floats / n_ctas; all n_ctas CTAs of a rank have to become resident together (they hand-shake with their peers), so keep
+ * n_ctas at or below the SMs the concurrent kernels leave free (sc_plan_set_reserved_sms). */
+int sc_allreduce_p2p(float* const* peer_buffers, uint32_t* const* peer_signal_pads, int32_t rank, int32_t world_size, int64_t n_floats,
+                     float scale, int32_t n_ctas, sc_stream stream);
 
 /* events for the grads_ready hand-over above (timing disabled); sc_stream_wait_event makes `stream` wait for the last record */
 int  sc_event_create(sc_event* event_out);

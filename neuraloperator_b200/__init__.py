@@ -6,6 +6,6 @@ Only the spectral-convolution hot path of neuraloperator lives here; use `Spectr
 from .spectral_conv import (BaseSpectralConv, Plan, SpectralConv, analyze, contract_dense,  # noqa: F401
                             contract_dense_backward, get_plan, spectral_conv_dense, synthesize)
 from .factorized import FactorizedWeight  # noqa: F401
-from .data_parallel import GradientAllReducer  # noqa: F401
+from .data_parallel import GradientAllReducer, PeerGradientAllReducer  # noqa: F401
 
 __version__ = "0.1.0"

@@ -59,6 +59,7 @@ SIGNATURES = {
                                   c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sc_backward_tucker": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sc_allreduce_p2p": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, ctypes.c_float, c_i32, c_void_p]),
     "sc_event_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "sc_event_destroy": (None, [c_void_p]),
     "sc_stream_wait_event": (c_int, [c_void_p, c_void_p]),

@@ -684,8 +684,13 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
   SC_TRY(contract_bwd(p, reinterpret_cast<const float2*>(xm_saved), gm, reinterpret_cast<const float2*>(weight), dxm,
                       reinterpret_cast<float2*>(dweight), dbias, batch, in_channels, out_channels, st, true, x_qm, g_qm,
                       static_cast<cudaEvent_t>(grads_ready)));
-  if (dx != nullptr)
-    SC_TRY(synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st, g_qm));
+  if (dx != nullptr) {
+    // with a collective running on the caller's side stream (grads_ready given), the dx synthesis leaves SMs free for it
+    fast_set_reserve(grads_ready != nullptr);
+    const bool ok = synthesize(p, dxm, (int64_t)batch * in_channels, 0, nullptr, dx, true, w.buf[0], w.buf[1], st, g_qm);
+    fast_set_reserve(false);
+    SC_TRY(ok);
+  }
   return 0;
 }
 
@@ -731,7 +736,7 @@ bool tucker_dims(const Plan* p, int B, int Ci, int Co, const int32_t* ranks, Tuc
 
 inline size_t a256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-struct TuckerBwdArena { float2 *g2, *g1, *dwc, *da[2], *pr_scratch; unsigned int* counter; size_t bytes; };
+struct TuckerBwdArena { float2 *g2, *g1, *dwc, *da[2]; size_t bytes; };
 
 TuckerBwdArena tucker_bwd_arena(const TuckerDims& t, char* base) {
   TuckerBwdArena a{};
@@ -744,10 +749,6 @@ TuckerBwdArena tucker_bwd_arena(const TuckerDims& t, char* base) {
   for (int j = 0; j <= t.d; ++j) mx = std::max(mx, t.chain_elems(j));
   a.da[0] = take((size_t)mx);
   a.da[1] = take((size_t)mx);
-  size_t sc = std::max(pair_reduce_split_scratch_bytes(t.B, t.rg, t.Co, (int)t.M), pair_reduce_split_scratch_bytes(t.B, t.Ci, t.rf, (int)t.M));
-  for (int j = 0; j < t.d; ++j) sc = std::max(sc, pair_reduce_split_scratch_bytes(t.outer(j), t.r[j], t.k[j], (int)t.inner(j)));
-  a.pr_scratch = reinterpret_cast<float2*>(base + off); off += a256(sc);
-  a.counter = reinterpret_cast<unsigned int*>(base + off); off += 256;
   a.bytes = off;
   return a;
 }
@@ -822,7 +823,6 @@ int sc_backward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const floa
   Workspace w{};
   SC_TRY(carve(p, n_max, workspace, tw, &w));
   TuckerBwdArena a = tucker_bwd_arena(t, static_cast<char*>(workspace) + tw);
-  SC_TRY(cuda_ok(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st), "cudaMemsetAsync(counter)"));
   const float2* sv = reinterpret_cast<const float2*>(saved);
   const float2 *xm = sv + t.off_xm(), *t1 = sv + t.off_t1(), *t2 = sv + t.off_t2(), *wc = sv + t.off_wc();
   float2* gm = w.modes[0];
@@ -831,24 +831,30 @@ int sc_backward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const floa
   if (dbias != nullptr) SC_TRY(launch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
   // out side: g2 = U_out^H gm,  dU_out[o, g] = sum conj(t2[b, g, m]) gm[b, o, m]
   SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_out), 1, t.rg, true, gm, a.g2, t.B, t.rg, t.Co, (int)t.M, st));
-  SC_TRY(launch_pair_reduce_split(t2, gm, reinterpret_cast<float2*>(d_u_out), 1, t.rg, t.B, t.rg, t.Co, (int)t.M, a.pr_scratch, a.counter, st));
+  SC_TRY(launch_pair_reduce(t2, gm, reinterpret_cast<float2*>(d_u_out), 1, t.rg, t.B, t.rg, t.Co, (int)t.M, st));
   // core side: the two mode GEMMs of the dense backward, on rank channels
   SC_TRY(contract_bwd(pk, t1, a.g2, wc, a.g1, a.dwc, nullptr, t.B, t.rf, t.rg, st, false));
   // in side
-  SC_TRY(launch_pair_reduce_split(xm, a.g1, reinterpret_cast<float2*>(d_u_in), t.rf, 1, t.B, t.Ci, t.rf, (int)t.M, a.pr_scratch, a.counter, st));
+  SC_TRY(launch_pair_reduce(xm, a.g1, reinterpret_cast<float2*>(d_u_in), t.rf, 1, t.B, t.Ci, t.rf, (int)t.M, st));
   SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_in), t.rf, 1, true, a.g1, dxm, t.B, t.Ci, t.rf, (int)t.M, st));
   SC_TRY(synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
   // mode factors and core: undo the expansion chain, first axis first
   const float2* d_a = a.dwc;
   for (int j = 0; j < t.d; ++j) {
     const float2* a_next = (j + 1 == t.d) ? reinterpret_cast<const float2*>(core) : sv + t.off_chain(j + 1);     // A_{j+1}
-    SC_TRY(launch_pair_reduce_split(a_next, d_a, reinterpret_cast<float2*>(d_u_modes[j]), 1, t.r[j], t.outer(j), t.r[j], t.k[j], (int)t.inner(j),
-                                    a.pr_scratch, a.counter, st));
+    SC_TRY(launch_pair_reduce(a_next, d_a, reinterpret_cast<float2*>(d_u_modes[j]), 1, t.r[j], t.outer(j), t.r[j], t.k[j], (int)t.inner(j), st));
     float2* dst = (j + 1 == t.d) ? reinterpret_cast<float2*>(d_core) : a.da[j & 1];
     SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_modes[j]), 1, t.r[j], true, d_a, dst, t.outer(j), t.r[j], t.k[j],
                                              (int)t.inner(j), st));
     d_a = dst;
   }
+  return 0;
+}
+
+int sc_allreduce_p2p(float* const* peer_buffers, uint32_t* const* peer_signal_pads, int32_t rank, int32_t world_size, int64_t n_floats,
+                     float scale, int32_t n_ctas, sc_stream stream) {
+  SC_REQUIRE(peer_buffers != nullptr && peer_signal_pads != nullptr, "sc_allreduce_p2p: null argument");
+  SC_TRY(launch_allreduce_p2p(peer_buffers, peer_signal_pads, rank, world_size, n_floats, scale, n_ctas, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 

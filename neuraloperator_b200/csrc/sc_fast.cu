@@ -2438,8 +2438,10 @@ struct FastTables {
 
 static int fast_sm_count(const Plan* p) { return p->fast->sm_count; }
 // CTAs of a persistent transform launch: one per SM, minus the SMs reserved for a concurrent collective (sc_plan_set_reserved_sms)
+static thread_local bool t_reserve_sms = false;   // set by sc_backward_dense around the launches a collective runs next to
+void fast_set_reserve(bool on) { t_reserve_sms = on; }
 static int persistent_grid(const Plan* p, int n_tiles) {
-  int sms = p->fast->sm_count - p->reserved_sms;
+  int sms = p->fast->sm_count - (t_reserve_sms ? p->reserved_sms : 0);
   if (sms < 1) sms = 1;
   return n_tiles < sms ? n_tiles : sms;
 }

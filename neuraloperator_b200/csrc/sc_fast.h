@@ -22,6 +22,7 @@ bool fast_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, in
                      float* images_out, bool adjoint, int slices_per_image, cudaStream_t st, bool quad_major = false);
 int fast_tile_group(const Plan* p, bool synthesis, bool adjoint);   // slices per 128-row tile
 
+void fast_set_reserve(bool on);   // the next persistent transform launches of this thread leave plan->reserved_sms SMs free
 bool quad2_enabled();   // second-generation quad contraction kernel selected (default; SC_QUAD=1 selects the first)
 bool mode_gemm_quad_eligible(const Plan* p, int64_t n_modes, const void* a, const void* b, const void* out);
 bool fast_can_contract(const Plan* p, int B, int Ci, int Co, bool quad_ok);

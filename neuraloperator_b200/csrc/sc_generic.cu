@@ -301,111 +301,6 @@ bool launch_pair_reduce(const float2* A, const float2* B, float2* out, int64_t s
 }
 
 // =====================================================================================================
-// 2b'. pair reduction, split over the reduction axis (used by the factorized C entry points, which own a workspace):
-//     every input element is read ONCE (k_pair_reduce re-reads each input row once per 4 x 4 output tile: 160 MB of L2 traffic
-//     for the 14 MB of the cfg-3 factor gradients).  A CTA walks chunks of 32 consecutive i of one o, stages the [P x 32] and
-//     [Q x 32] slices in shared memory (transposed, padded) and accumulates a 64 x 64 block of outputs in registers
-//     (thread (tp, tq) owns p = tp + 16 a, q = tq + 16 b); partial blocks go to a scratch buffer and the LAST CTA to finish
-//     adds them in CTA order (deterministic), so the whole reduction is one launch.
-// =====================================================================================================
-constexpr int PR2_THREADS = 256, PR2_TILE = 64, PR2_CHUNK = 32, PR2_PAD = PR2_TILE + 1;
-
-__global__ void __launch_bounds__(PR2_THREADS)
-k_pair_reduce_split(const float2* __restrict__ A, const float2* __restrict__ B, float2* __restrict__ out, long long sOp, long long sOq,
-                    long long O, int P, int Q, int I, float2* __restrict__ scratch, unsigned int* __restrict__ counter) {
-  __shared__ float2 sA[PR2_CHUNK][PR2_PAD], sB[PR2_CHUNK][PR2_PAD];
-  __shared__ bool s_last;
-  const int tid = threadIdx.x, tp = tid >> 4, tq = tid & 15;
-  const int p_tiles = (P + PR2_TILE - 1) / PR2_TILE, q_tiles = (Q + PR2_TILE - 1) / PR2_TILE;
-  const int ichunks = (I + PR2_CHUNK - 1) / PR2_CHUNK;
-  const long long n_chunks = O * (long long)ichunks;
-  const long long PQ = (long long)P * Q;
-  float2* my_part = scratch + (long long)blockIdx.x * PQ;
-  for (int pt = 0; pt < p_tiles; ++pt)
-    for (int qt = 0; qt < q_tiles; ++qt) {
-      const int p0 = pt * PR2_TILE, q0 = qt * PR2_TILE;
-      float2 acc[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = make_float2(0.f, 0.f);
-      for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const long long o = c / ichunks;
-        const int i0 = (int)(c - o * ichunks) * PR2_CHUNK;
-        // stage: consecutive threads -> consecutive i (coalesced), rows p / q strided over the 8 warps
-        const int ii = tid & 31;
-        const bool i_ok = i0 + ii < I;
-        for (int r = tid >> 5; r < PR2_TILE; r += PR2_THREADS / 32) {
-          float2 va = make_float2(0.f, 0.f), vb = make_float2(0.f, 0.f);
-          if (i_ok && p0 + r < P) va = __ldg(A + (o * P + p0 + r) * (long long)I + i0 + ii);
-          if (i_ok && q0 + r < Q) vb = __ldg(B + (o * Q + q0 + r) * (long long)I + i0 + ii);
-          sA[ii][r] = va;
-          sB[ii][r] = vb;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < PR2_CHUNK; ++k) {
-          float2 av[4], bv[4];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) { av[a] = sA[k][tp + 16 * a]; bv[a] = sB[k][tq + 16 * a]; }
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {   // conj(a) * b
-              acc[a][b].x = fmaf(av[a].x, bv[b].x, acc[a][b].x);
-              acc[a][b].x = fmaf(av[a].y, bv[b].y, acc[a][b].x);
-              acc[a][b].y = fmaf(av[a].x, bv[b].y, acc[a][b].y);
-              acc[a][b].y = fmaf(-av[a].y, bv[b].x, acc[a][b].y);
-            }
-        }
-        __syncthreads();
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int p = p0 + tp + 16 * a, q = q0 + tq + 16 * b;
-          if (p < P && q < Q) my_part[(long long)p * Q + q] = acc[a][b];
-        }
-    }
-  // last CTA to arrive sums the partial blocks in CTA order
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (long long e = tid; e < PQ; e += PR2_THREADS) {
-    float2 v = make_float2(0.f, 0.f);
-    for (unsigned int blk = 0; blk < gridDim.x; ++blk) {
-      const float2 w = scratch[(long long)blk * PQ + e];
-      v.x += w.x; v.y += w.y;
-    }
-    const long long p = e / Q, q = e - p * Q;
-    out[p * sOp + q * sOq] = v;
-  }
-  if (tid == 0) *counter = 0;   // ready for the next launch on this stream
-}
-
-size_t pair_reduce_split_scratch_bytes(int64_t O, int P, int Q, int I) {
-  const int64_t n_chunks = O * ((I + PR2_CHUNK - 1) / PR2_CHUNK);
-  const int64_t grid = n_chunks < 296 ? n_chunks : 296;
-  return (size_t)(grid > 0 ? grid : 1) * P * Q * sizeof(float2);
-}
-
-// `counter` must be zero on entry (the kernel re-zeroes it); `scratch` holds pair_reduce_split_scratch_bytes()
-bool launch_pair_reduce_split(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I,
-                              float2* scratch, unsigned int* counter, cudaStream_t st) {
-  if (P <= 0 || Q <= 0) return true;
-  const int64_t n_chunks = O * ((I + PR2_CHUNK - 1) / PR2_CHUNK);
-  if (n_chunks <= 0) return cuda_ok(cudaMemsetAsync(out, 0, 0, st), "noop");
-  const int grid = (int)(n_chunks < 296 ? n_chunks : 296);
-  k_pair_reduce_split<<<grid, PR2_THREADS, 0, st>>>(A, B, out, (long long)sOp, (long long)sOq, (long long)O, P, Q, I, scratch, counter);
-  count_launch();
-  return cuda_ok(cudaGetLastError(), "k_pair_reduce_split launch");
-}
-
-// =====================================================================================================
 // 2c. CP (canonical polyadic) pieces, reference `_contract_cp` :55-73.
 //     scale[e, m] = lambda_e * prod_j U_j[m_j, e]   (Khatri-Rao rows of the kept mode-factor rows)
 //     apply:  out[a, e, m] = in[a, e, m] * op(scale[e, m])

@@ -74,10 +74,6 @@ bool launch_complex_table_gemm_strided(const float2* T, int64_t sTp, int64_t sTq
 // out[p, q] (strided) = sum_{o,i} conj(A[o,p,i]) * B[o,q,i]
 bool launch_pair_reduce(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I,
                         cudaStream_t st);
-// the same reduction split over (o, i), one pass over the inputs, deterministic; scratch + a zeroed counter from the caller
-size_t pair_reduce_split_scratch_bytes(int64_t O, int P, int Q, int I);
-bool launch_pair_reduce_split(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I,
-                              float2* scratch, unsigned int* counter, cudaStream_t st);
 // CP pieces (sc_generic.cu, section 2c)
 bool launch_cp_scale(const float2* const* u, const int* k, int d, const float2* lambda, float2* scale, int R, int64_t M, cudaStream_t st);
 bool launch_cp_apply(const float2* in, const float2* scale, float2* out, bool conj_scale, int batch, int64_t per_batch, cudaStream_t st);
@@ -92,5 +88,9 @@ bool launch_mode_gemm(ModeGemmOperand A, bool conjA, ModeGemmOperand B, bool con
                       int nR, int nC, int nK, int64_t nModes, cudaStream_t st);
 bool launch_bias_grad(const float2* gm, float* dbias, int batch, int out_channels, int64_t n_modes, int dc_slot,
                       float inv_scale, cudaStream_t st);
+
+// two-shot all-reduce (average) over NVLink peer memory, sc_collective.cu
+bool launch_allreduce_p2p(float* const* bufs, uint32_t* const* signals, int rank, int world, int64_t n_floats, float scale, int n_ctas,
+                          cudaStream_t st);
 
 }  // namespace sc

@@ -155,3 +155,70 @@ class GradientAllReducer:
                 self._event = None
         except Exception:   # noqa: BLE001
             pass
+
+
+class PeerGradientAllReducer(GradientAllReducer):
+    """`GradientAllReducer` whose collective is this library's own kernel over NVLink peer memory (`sc_allreduce_p2p`).
+
+    The gradients of the attached `SpectralConv` (dweight and dbias, back to back) are written by the backward kernels straight
+    into a CUDA symmetric-memory buffer (`torch.distributed._symmetric_memory`: every rank maps every other rank's buffer), and
+    the two-shot all-reduce kernel averages them in place on the collective stream, behind the library's `grads_ready` event --
+    no NCCL call, no copy, ~12 CTAs.  The buffer is persistent: the `.grad` tensors autograd hands out are views of it and are
+    overwritten by the next backward pass (the usual `zero_grad(set_to_none=True)` training loop).
+    Everything that does not live in that buffer (other parameters) still goes through the base class (NCCL / gloo)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter] = (), process_group=None, average: bool = True, n_ctas: int = 12):
+        super().__init__(params, process_group, average)
+        self.n_ctas = int(n_ctas)
+        self._sym = {}            # (n_floats, device index) -> (tensor, padded length, peer buffer array, signal pad array)
+
+    def grad_buffer(self, n_floats: int, device) -> torch.Tensor:
+        """A persistent symmetric-memory float32 buffer of `n_floats` elements (collective on first use: every rank calls it)."""
+        key = (int(n_floats), device.index)
+        ent = self._sym.get(key)
+        if ent is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            padded = (int(n_floats) + 3) // 4 * 4
+            t = symm_mem.empty(padded, dtype=torch.float32, device=device)
+            group = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(t, group)
+            world = hdl.world_size
+            off = int(getattr(hdl, "offset", 0) or 0)
+            bufs = (ctypes.c_void_p * world)(*[int(p) + off for p in hdl.buffer_ptrs])
+            sigs = (ctypes.c_void_p * world)(*[int(p) for p in hdl.signal_pad_ptrs])
+            if int(hdl.signal_pad_size) < 4 * self.n_ctas * world:
+                raise RuntimeError("symmetric-memory signal pad too small for the requested number of CTAs")
+            ent = self._sym[key] = (t, padded, bufs, sigs, hdl)
+        return ent[0][:n_floats]
+
+    def _entry_of(self, tensors):
+        for t in tensors:
+            for ent in self._sym.values():
+                if t.untyped_storage().data_ptr() == ent[0].untyped_storage().data_ptr():
+                    return ent
+        return None
+
+    def reduce_in_backward(self, tensors, after_event: Optional[ctypes.c_void_p] = None):
+        tensors = [t for t in tensors if t is not None]
+        world = self.world_size()
+        if world == 1 or not tensors:
+            return
+        ent = self._entry_of(tensors)
+        if ent is None:                      # not in the symmetric buffer: NCCL / gloo path of the base class
+            return super().reduce_in_backward(tensors, after_event)
+        from . import _lib
+        lib = _lib.load()
+        buf, padded, bufs, sigs, hdl = ent
+        device = buf.device
+        side = self._side_stream(device)
+        if after_event is not None:
+            _lib.check(lib.sc_stream_wait_event(ctypes.c_void_p(side.cuda_stream), after_event), "sc_stream_wait_event")
+        else:
+            side.wait_stream(torch.cuda.current_stream(device))
+        scale = 1.0 / world if self.average else 1.0
+        with torch.cuda.device(device):
+            _lib.check(lib.sc_allreduce_p2p(bufs, sigs, dist.get_rank(self.group), world, padded, scale, self.n_ctas,
+                                            ctypes.c_void_p(side.cuda_stream)), "sc_allreduce_p2p")
+        torch.cuda.current_stream(device).wait_stream(side)
+        for t in tensors:
+            self._reduced_in_backward.add(t.data_ptr())

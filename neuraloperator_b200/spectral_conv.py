@@ -253,9 +253,11 @@ class _SpectralConvDense(torch.autograd.Function):
         dev = gy.device
         dx = torch.empty((B, Ci, *plan.grid), dtype=torch.float32, device=dev) if need_dx else None
         if need_dw and need_db:
-            # dweight and dbias share one allocation so that a data-parallel reducer moves them with ONE collective
+            # dweight and dbias share one allocation so that a data-parallel reducer moves them with ONE collective; a peer-memory
+            # reducer hands out its symmetric buffer, so that the kernels write the gradients where the collective reads them
             n_w = weight.numel() * 2
-            flat = torch.empty(n_w + Co, dtype=torch.float32, device=dev)
+            owner = getattr(ctx.reducer, "grad_buffer", None) if ctx.reducer is not None and ctx.reducer.world_size() > 1 else None
+            flat = owner(n_w + Co, dev) if owner is not None else torch.empty(n_w + Co, dtype=torch.float32, device=dev)
             dw = torch.view_as_complex(flat[:n_w].view(*weight.shape, 2))
             db = flat[n_w:]
         else:
