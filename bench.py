@@ -50,14 +50,15 @@ def measured_peaks():
 
 def ncu_traffic(plan):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused analysis kernel, from the committed ncu launch
-    list of this round's build (profiles/r02_launches.csv, `--cache-control none`); None when that file or kernel is absent."""
+    list of this round's build (profiles/r02_launches.csv, `--cache-control none`, summarised in r02_launches_summary.json);
+    None when that file or kernel is absent.  A citation of a committed capture, not a measurement of this run."""
     if not plan.uses_fast_path() & 1:
         return None
     path = os.path.join(ROOT, "profiles", "r02_launches_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        k = d["k_fused_analysis"]
+        k = d.get("k_fused_analysis2") or d["k_fused_analysis"]
         return (k["dram_read_mb"] + k["dram_write_mb"]) * 1e6
     except Exception:
         return None
