@@ -237,7 +237,8 @@ static bool analyze_generic(const Plan* p, const float* images, int64_t n_images
   const int64_t rows = n_images * lead;
   float2* cur = (d == 1) ? modes_out : b0;
   float2* nxt = b1;
-  if (p->fast_enabled && rows_can_analyze(p, adjoint, rows)) {
+  if (p->fast_enabled && rows_can_analyze(p, adjoint, rows) &&
+      ((reinterpret_cast<uintptr_t>(images) | reinterpret_cast<uintptr_t>(cur)) & 15u) == 0) {
     if (!rows_analyze(p, images, rows, reinterpret_cast<float*>(cur), adjoint, st)) return false;
   } else
   if (!launch_real_table_gemm(images, adjoint ? p->d_TST : p->d_TA, adjoint ? p->ldTST : p->ldTA,
@@ -276,7 +277,8 @@ static bool synthesize_generic(const Plan* p, const float2* modes_in, int64_t n_
     cur = dst; which ^= 1;
   }
   const int64_t rows = n_images * lead;
-  if (p->fast_enabled && rows_can_synthesize(p, adjoint, rows))
+  if (p->fast_enabled && rows_can_synthesize(p, adjoint, rows) &&
+      ((reinterpret_cast<uintptr_t>(images_out) | reinterpret_cast<uintptr_t>(cur)) & 15u) == 0)
     return rows_synthesize(p, reinterpret_cast<const float*>(cur), rows, images_out, bias, lead, n_channels > 0 ? n_channels : 1,
                            adjoint, st);
   return launch_real_table_gemm(reinterpret_cast<const float*>(cur), adjoint ? p->d_TAT : p->d_TS,
@@ -288,7 +290,9 @@ static bool analyze(const Plan* p, const float* images, int64_t n_images, float2
                     float2* b0, float2* b1, cudaStream_t st, bool quad_major = false, const L2Prefetch* pf = nullptr) {
   if (n_images <= 0) return true;
   if (quad_major) return fast_analyze(p, images, n_images, modes_out, adjoint, st, true, pf);   // (dense_chain_quad_major checked the shape)
-  if (p->fast_enabled && fast_can_analyze(p, adjoint)) {
+  // tensor maps and bulk copies need 16-byte aligned bases: an offset view (e.g. buf[1:].view(...)) takes the generic chain
+  const bool aligned = ((reinterpret_cast<uintptr_t>(images) | reinterpret_cast<uintptr_t>(modes_out)) & 15u) == 0;
+  if (p->fast_enabled && aligned && fast_can_analyze(p, adjoint)) {
     if (p->d == 2) {
       if (n_images % fast_tile_group(p, false, adjoint) == 0)
         return fast_analyze(p, images, n_images, modes_out, adjoint, st, false, pf);
@@ -309,7 +313,8 @@ static bool synthesize(const Plan* p, const float2* modes_in, int64_t n_images, 
                        float* images_out, bool adjoint, float2* b0, float2* b1, cudaStream_t st, bool quad_major = false) {
   if (n_images <= 0) return true;
   if (quad_major) return fast_synthesize(p, modes_in, n_images, n_channels, bias, images_out, adjoint, 1, st, true);
-  if (p->fast_enabled && fast_can_synthesize(p, adjoint)) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(images_out) | reinterpret_cast<uintptr_t>(modes_in)) & 15u) == 0;
+  if (p->fast_enabled && aligned && fast_can_synthesize(p, adjoint)) {
     if (p->d == 2) {
       if (n_images % fast_tile_group(p, true, adjoint) == 0)
         return fast_synthesize(p, modes_in, n_images, n_channels, bias, images_out, adjoint, 1, st);
@@ -646,7 +651,8 @@ int sc_forward_dense(const sc_plan* plan, const float* x, const sc_complex* weig
   float2* ym = w.modes[0];
   // without a place to report it the saved modes stay in the standard layout
   const bool qm = saved_layout_out != nullptr && dense_chain_quad_major(p, batch, in_channels, out_channels, weight) &&
-                  (reinterpret_cast<uintptr_t>(xm_saved) & 31u) == 0;
+                  (reinterpret_cast<uintptr_t>(xm_saved) & 31u) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0;
   if (saved_layout_out != nullptr) *saved_layout_out = qm ? SC_MODES_QUAD_MAJOR : SC_MODES_STANDARD;
   // the forward contraction reads the whole weight right after the analysis: let the analysis launch pull it into L2
   L2Prefetch pf;
@@ -674,7 +680,8 @@ int sc_backward_dense(const sc_plan* plan, const float* gy, const sc_complex* we
   // gm / dxm are internal to this call: quad-major whenever the chain allows it (a dbias without a dweight launch reads gm
   // with the standalone kernel, which wants the standard layout)
   const bool g_qm = dense_chain_quad_major(p, batch, in_channels, out_channels, weight) && (dbias == nullptr || dweight != nullptr) &&
-                    (dweight == nullptr || (reinterpret_cast<uintptr_t>(dweight) & 31u) == 0);
+                    (dweight == nullptr || (reinterpret_cast<uintptr_t>(dweight) & 31u) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(dx)) & 15u) == 0;
   SC_REQUIRE(!x_qm || p->fast != nullptr, "sc_backward_dense: quad-major saved modes without the tensor-core path");
   // the two backward contractions read the saved modes and the weight: the gy analysis pulls both into L2
   L2Prefetch pf;

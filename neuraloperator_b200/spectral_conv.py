@@ -817,6 +817,14 @@ class SpectralConv(BaseSpectralConv):
             raise RuntimeError("neuraloperator_b200.SpectralConv has no CPU path: move the module and input to a B200")
         if x.dtype != torch.float32:
             raise TypeError(f"SpectralConv (full precision, real data) expects float32 input, got {x.dtype}")
+        # the kernels read the parameters through raw pointers: complex64 / float32 on x's device, nothing else
+        for name, prm in self.named_parameters():
+            want = torch.float32 if name == "bias" else torch.complex64
+            if prm.dtype != want:
+                raise TypeError(f"SpectralConv parameter {name} is {prm.dtype}; the kernels need {want} "
+                                "(module.double() / .half() are not supported: full precision, spectral_convolution.py:459-462)")
+            if prm.device != x.device:
+                raise RuntimeError(f"SpectralConv parameter {name} lives on {prm.device} but the input on {x.device}")
         grid = list(x.shape[2:])
         out_grid = self._output_grid(grid, output_shape)
         plan = get_plan(x.device, grid, out_grid, self.n_modes, self.max_n_modes, self.fft_norm)
