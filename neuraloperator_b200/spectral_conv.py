@@ -619,6 +619,127 @@ class _SpectralResample(torch.autograd.Function):
         return synthesize(plan, gm, adjoint=True), None
 
 
+# --------------------------------------------------------------------------------------------------
+# complex_data=True (reference :439-441, :470-479, :500-519, :531-538): C2C transforms along every dim
+# --------------------------------------------------------------------------------------------------
+class ComplexPlan:
+    """Kept-mode index set and twiddle tables of the complex-data path.  Every dim is a complex table product (there is no
+    half spectrum), so the whole chain runs on the library's complex table kernel (`sc_table_contract`) and the dense
+    mode-wise contraction; nothing here is specific to a grid size.  Index rules (restated from the reference, pinned by the
+    oracle's `kept_mode_plan_complex` against the live module): every dim is FFT-shifted unless the conv is 1-D; the weight is
+    cut centrally along every dim; the last dim nevertheless takes the FIRST k entries of its (shifted) spectrum; on the way
+    back only the leading dims are un-shifted, so the last dim's slots are synthesised at their own index."""
+
+    def __init__(self, device, grid, out_grid, n_modes, max_n_modes, fft_norm):
+        import math
+        d = len(grid)
+        self.ndim, self.grid, self.out_grid = d, tuple(grid), tuple(out_grid)
+        self.kept, self.w_start, self.analysis, self.synthesis = [], [], [], []
+        if fft_norm == "forward":
+            s_fwd, s_inv = 1.0 / math.prod(grid), 1.0
+        elif fft_norm == "backward":
+            s_fwd, s_inv = 1.0, 1.0 / math.prod(out_grid)
+        else:
+            s_fwd, s_inv = 1.0 / math.sqrt(math.prod(grid)), 1.0 / math.sqrt(math.prod(out_grid))
+        for j in range(d):
+            last = j == d - 1
+            N, M = int(grid[j]), int(out_grid[j])
+            k = min(N, int(n_modes[j]))
+            start = int(max_n_modes[j]) - k
+            if start < 0:
+                raise ValueError("n_modes exceeds max_n_modes (weight too small for the requested modes)")
+            shift = N // 2 if d > 1 else 0
+            pos = list(range(k)) if last else list(range(N // 2 - k // 2, N // 2 + k // 2 + k % 2))
+            in_bins = torch.tensor([(q - shift) % N for q in pos], dtype=torch.float64)
+            out_pos = torch.tensor(pos if last else [(q - shift) % N for q in pos], dtype=torch.float64)
+            n_in = torch.arange(N, dtype=torch.float64)
+            n_out = torch.arange(M, dtype=torch.float64)
+            ang_a = -2.0 * math.pi * torch.remainder(in_bins[:, None] * n_in[None, :], N) / N               # [k x N]
+            ang_s = 2.0 * math.pi * torch.remainder(n_out[:, None] * out_pos[None, :], M) / M              # [M x k]
+            a = torch.polar(torch.full_like(ang_a, s_fwd if last else 1.0), ang_a)
+            sy = torch.polar(torch.full_like(ang_s, s_inv if last else 1.0), ang_s) * (out_pos[None, :] < M)   # ifftn(s=M) crops the end
+            self.kept.append(k)
+            self.w_start.append(start // 2 if start else 0)
+            self.analysis.append(a.to(torch.complex64).contiguous().to(device))
+            self.synthesis.append(sy.to(torch.complex64).contiguous().to(device))
+        self.kept = tuple(self.kept)
+        # the dense mode GEMM only needs a plan whose kept block is (k_1..k_d) with weight extents == kept
+        self.contract_plan = get_plan(device, [*self.kept[:-1], 2 * self.kept[-1]], [*self.kept[:-1], 2 * self.kept[-1]],
+                                      list(self.kept), list(self.kept), "forward")
+
+
+_COMPLEX_PLANS: "OrderedDict[tuple, ComplexPlan]" = OrderedDict()
+
+
+def get_complex_plan(device, grid, out_grid, n_modes, max_n_modes, fft_norm) -> ComplexPlan:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, tuple(grid), tuple(out_grid), tuple(n_modes), tuple(max_n_modes), fft_norm)
+    with _PLAN_LOCK:
+        plan = _COMPLEX_PLANS.get(key)
+        if plan is None:
+            plan = _COMPLEX_PLANS[key] = ComplexPlan(torch.device("cuda", idx), grid, out_grid, n_modes, max_n_modes, fft_norm)
+            while len(_COMPLEX_PLANS) > _PLAN_CACHE_MAX:
+                _COMPLEX_PLANS.popitem(last=False)
+        return plan
+
+
+def _apply_tables(tables, src, lead, sizes_in, sizes_out, order, adjoint):
+    """Applies one table per dim to `src` (lead, *sizes_in) -> (lead, *sizes_out): `order` lists the dims in the order they are
+    transformed.  adjoint: the conjugate transpose of every table."""
+    cur = src.reshape(-1)
+    sizes = list(sizes_in)
+    for j in order:
+        P, Q = sizes_out[j], sizes_in[j]
+        outer = lead
+        for l in range(j):
+            outer *= sizes[l]
+        inner = 1
+        for l in range(j + 1, len(sizes)):
+            inner *= sizes[l]
+        t = tables[j]
+        if adjoint:      # T'[p, q] = conj(T[q, p]),  T is (Q x P) row-major
+            cur = _table_contract(t, 1, P, True, cur, outer, P, Q, inner)
+        else:            # T is (P x Q) row-major
+            cur = _table_contract(t, Q, 1, False, cur, outer, P, Q, inner)
+        sizes[j] = P
+    return cur.view(lead, *sizes) if isinstance(lead, int) else cur
+
+
+class _SpectralConvComplex(torch.autograd.Function):
+    """y = SpectralConv.forward(x) for complex data and a dense kept-block weight (B,Ci,*grid) -> (B,Co,*out_grid), without the
+    bias: C2C analysis (one complex table product per dim, last dim first), dense mode-wise contraction, C2C synthesis."""
+
+    @staticmethod
+    def forward(ctx, x, w_kept, plan: ComplexPlan):
+        B, Ci = x.shape[:2]
+        Co = w_kept.shape[1]
+        d = plan.ndim
+        with torch.cuda.device(x.device):
+            xm = _apply_tables(plan.analysis, x, B * Ci, plan.grid, plan.kept, range(d - 1, -1, -1), False).view(B, Ci, *plan.kept)
+            ym = contract_dense(plan.contract_plan, xm, w_kept)
+            y = _apply_tables(plan.synthesis, ym, B * Co, plan.kept, plan.out_grid, range(d), False).view(B, Co, *plan.out_grid)
+        ctx.plan = plan
+        ctx.save_for_backward(xm, w_kept)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        plan = ctx.plan
+        xm, w_kept = ctx.saved_tensors
+        B, Ci = xm.shape[:2]
+        Co = w_kept.shape[1]
+        d = plan.ndim
+        gy = gy.contiguous()
+        if gy.dtype != torch.complex64:
+            gy = gy.to(torch.complex64)
+        with torch.cuda.device(gy.device):
+            gm = _apply_tables(plan.synthesis, gy, B * Co, plan.out_grid, plan.kept, range(d - 1, -1, -1), True).view(B, Co, *plan.kept)
+            dxm, dw, _ = contract_dense_backward(plan.contract_plan, xm, gm, w_kept, need_dbias=False)
+            dx = _apply_tables(plan.analysis, dxm, B * Ci, plan.kept, plan.grid, range(d), True).view(B, Ci, *plan.grid)
+        return dx, dw, None
+
+
 def _validate_scaling_factor(factor, n_dim) -> Optional[List[float]]:
     """Single-layer case of neuralop/utils.py:151-197 (`validate_scaling_factor(..., n_layers=None)`)."""
     if factor is None:
@@ -647,8 +768,9 @@ class BaseSpectralConv(nn.Module):
 class SpectralConv(BaseSpectralConv):
     """Fourier-layer spectral convolution (real data, full precision) on hand-written sm_100a kernels.
 
-    Parameters: identical to the reference class (spectral_convolution.py:183-305). Variants the kernels do
-    not cover raise `NotImplementedError` at construction: `complex_data=True`, `fno_block_precision != "full"`.
+    Parameters: identical to the reference class (spectral_convolution.py:183-305). `complex_data=True` runs C2C transforms on the
+    complex table kernels (any grid; dense or reconstructed weights). Variants the kernels do not cover raise
+    `NotImplementedError` at construction: `fno_block_precision != "full"`, `complex_data` together with `separable`.
     """
 
     def __init__(
@@ -673,8 +795,8 @@ class SpectralConv(BaseSpectralConv):
         device=None,
     ):
         super().__init__(device=device)
-        if complex_data:
-            raise NotImplementedError("complex_data=True (C2C transforms) is not covered by the B200 kernels yet")
+        if complex_data and separable:
+            raise NotImplementedError("complex_data=True with separable=True is not covered by the B200 kernels")
         if separable and in_channels != out_channels:
             raise ValueError("To use separable Fourier Conv, in_channels must be equal "
                              f"to out_channels, but got in_channels={in_channels} and out_channels={out_channels}")
@@ -754,6 +876,9 @@ class SpectralConv(BaseSpectralConv):
         if in_shape == out_shape:
             return x
         d = len(in_shape)
+        if x.is_complex():
+            raise NotImplementedError("SpectralConv.transform with a resolution change is not available for complex data "
+                                      "(the reference's `resample` interpolates real tensors)")
         if d == 1:
             return torch.nn.functional.interpolate(x, size=out_shape[0], mode="linear", align_corners=True)
         if d == 2:
@@ -773,6 +898,29 @@ class SpectralConv(BaseSpectralConv):
             plan.plan_kept = plan if plan.max_n_modes == plan.kept else \
                 get_plan(plan.device, plan.grid, plan.out_grid, list(plan.kept), list(plan.kept), self.fft_norm)
         return plan.plan_kept
+
+    def _forward_complex(self, x, output_shape):
+        """complex_data=True (:439-441, :470-479, :531-538): C2C transforms, every weight form contracted as a reconstructed
+        dense kept block (`weight[slices_w]`, differentiable: autograd scatters dweight back and reconstructs factor gradients)."""
+        if x.dtype != torch.complex64:
+            raise TypeError(f"SpectralConv(complex_data=True, full precision) expects complex64 input, got {x.dtype}")
+        for name, prm in self.named_parameters():
+            if prm.device != x.device:
+                raise RuntimeError(f"SpectralConv parameter {name} lives on {prm.device} but the input on {x.device}")
+        grid = list(x.shape[2:])
+        out_grid = self._output_grid(grid, output_shape)
+        plan = get_complex_plan(x.device, grid, out_grid, self.n_modes, self.max_n_modes, self.fft_norm)
+        if x.shape[0] == 0:
+            z = (x.sum() * 0).real
+            for prm in self.parameters():
+                z = z + (prm.real.sum() if prm.is_complex() else prm.sum()) * 0
+            return x.new_zeros((0, self.out_channels, *out_grid)) + z
+        w = self.weight.to_tensor()
+        for j in range(self.order):
+            if plan.w_start[j] != 0 or plan.kept[j] != w.shape[2 + j]:
+                w = w.narrow(2 + j, plan.w_start[j], plan.kept[j])
+        y = _SpectralConvComplex.apply(x.contiguous(), w.contiguous(), plan)
+        return y + self.bias if self.bias is not None else y                  # (:567-568; real bias on complex data)
 
     def _forward_separable(self, x, plan: Plan):
         """Depthwise spectral conv (`separable=True`, `_contract_dense_separable` :49-52): the weight (C, *max_n_modes) --
@@ -815,6 +963,8 @@ class SpectralConv(BaseSpectralConv):
             raise ValueError(f"expected {self.in_channels} input channels, got {x.shape[1]}")
         if not x.is_cuda:
             raise RuntimeError("neuraloperator_b200.SpectralConv has no CPU path: move the module and input to a B200")
+        if self.complex_data:
+            return self._forward_complex(x, output_shape)
         if x.dtype != torch.float32:
             raise TypeError(f"SpectralConv (full precision, real data) expects float32 input, got {x.dtype}")
         # the kernels read the parameters through raw pointers: complex64 / float32 on x's device, nothing else

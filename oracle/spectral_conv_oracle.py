@@ -477,3 +477,77 @@ def resample_restated(x: torch.Tensor, output_shape: Sequence[int]) -> torch.Ten
         idx = tuple([slice(None), slice(None)] + [slice(*b) for b in bounds])
         out[idx] = X[idx]
     return torch.fft.irfftn(out, s=new_size, norm="forward", dim=axis)
+
+
+# --------------------------------------------------------------------------------------------------
+# (4) complex_data=True (spectral_convolution.py:439-441, :470-479, :500-519, :531-538), dense weight
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class ComplexDimPlan:
+    grid: int             # N_j
+    kept: int             # k_j = min(N_j, n_modes_j)      (n_modes is NOT halved for complex data, :408-414)
+    in_bins: List[int]    # unshifted spectrum bin read by kept slot t
+    out_pos: List[int]    # index of the (input-sized) output spectrum the slot is written to BEFORE `ifftn(s=...)` crops / pads it
+    w_index: List[int]    # weight row used by slot t
+
+
+def kept_mode_plan_complex(grid: Sequence[int], n_modes: Sequence[int], max_n_modes: Optional[Sequence[int]] = None):
+    """The index math of the complex-data path, which differs from the real one in three places:
+    every dim is FFT-shifted (:439-441) -- unless the conv is 1-D, where nothing is (:448-449); the weight is cut centrally along
+    every dim (:475-479); and the generic "last dim takes the first k entries" override (:514-517) still applies, now to the
+    SHIFTED last dim.  On the way back only the leading dims are un-shifted (:531-532), so the last dim's slots stay where they are."""
+    d = len(grid)
+    if max_n_modes is None:
+        max_n_modes = list(n_modes)
+    plans = []
+    for j in range(d):
+        last = j == d - 1
+        N = int(grid[j])
+        k = min(N, int(n_modes[j]))
+        start = int(max_n_modes[j]) - k
+        if start < 0:
+            raise ValueError("n_modes exceeds max_n_modes")
+        w0 = start // 2 if start else 0                                   # slice(start//2, -start//2)   (:475-479)
+        w_idx = list(range(w0, w0 + k))
+        shift = (N // 2) if d > 1 else 0                                  # fftshift rolls by N//2 (:448-449)
+        if last:
+            pos = list(range(k))                                          # slice(None, k) / slice(None)  (:514-517)
+        else:
+            centre = N // 2
+            pos = list(range(centre - k // 2, centre + k // 2 + k % 2))   # (:507-512)
+        in_bins = [(s - shift) % N for s in pos]
+        out_pos = [(s - shift) % N for s in pos] if not last else list(pos)   # ifftshift on the leading dims only (:531-532)
+        plans.append(ComplexDimPlan(N, k, in_bins, out_pos, w_idx))
+    return plans
+
+
+def spectral_conv_forward_complex(x: torch.Tensor, w_dense: torch.Tensor, bias: Optional[torch.Tensor], n_modes: Sequence[int],
+                                  max_n_modes: Optional[Sequence[int]] = None, output_shape: Optional[Sequence[int]] = None,
+                                  resolution_scaling_factor: Optional[Sequence[float]] = None, fft_norm: str = "forward"):
+    """`SpectralConv.forward` with complex_data=True and a dense weight, in gather / scatter form."""
+    B, Ci, *grid = x.shape
+    d = len(grid)
+    if max_n_modes is None:
+        max_n_modes = list(n_modes)
+    plans = kept_mode_plan_complex(grid, n_modes, max_n_modes)
+    dims = list(range(-d, 0))
+    xm = torch.fft.fftn(x, norm=fft_norm, dim=dims)                                     # :439
+    for j, p in enumerate(plans):
+        xm = _gather(xm, 2 + j, p.in_bins)
+    w = w_dense
+    for j, p in enumerate(plans):
+        w = w.narrow(2 + j, p.w_index[0], p.kept)                                       # :489
+    ym = contract_dense(xm.to(torch.cfloat), w)                                         # :520-522
+    out_grid = resolve_output_grid(grid, resolution_scaling_factor, output_shape)       # :524-528
+    Co = ym.shape[1]
+    out_spec = torch.zeros([B, Co] + list(grid), dtype=torch.cfloat, device=x.device)   # :460-462
+    index = [torch.arange(B).view(-1, *[1] * (d + 1)), torch.arange(Co).view(1, -1, *[1] * d)]
+    for j, p in enumerate(plans):
+        shape = [1] * (d + 2)
+        shape[2 + j] = -1
+        index.append(torch.as_tensor(p.out_pos, dtype=torch.long).view(shape))
+    out_spec[tuple(index)] = ym
+    y = torch.fft.ifftn(out_spec, s=out_grid, dim=dims, norm=fft_norm)                   # :538
+    if bias is not None:
+        y = y + bias                                                                    # :567-568
+    return y

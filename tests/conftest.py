@@ -82,3 +82,22 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+def complex_golden_index():
+    with open(os.path.join(GOLDEN_DIR, "complex_index.json")) as f:
+        return json.load(f)["cases"]
+
+
+def load_complex_golden(name):
+    """complex_data=True cases (oracle/make_golden_complex.py): complex tensors are stored as (..., 2) arrays under `<key>__c`."""
+    meta = complex_golden_index()[name]
+    data = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = {}
+    for k in data.files:
+        t = torch.from_numpy(data[k])
+        if k.endswith("__c"):
+            out[k[:-3]] = torch.view_as_complex(t.contiguous())
+        else:
+            out[k] = t
+    return meta, out

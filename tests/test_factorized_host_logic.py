@@ -204,3 +204,66 @@ def test_double_backward_is_refused_loudly(emulated):
     (gx,) = torch.autograd.grad(y.square().sum(), x, create_graph=True)
     with pytest.raises(RuntimeError, match="once_differentiable|differentiate twice"):
         gx.sum().backward()
+
+
+@pytest.mark.parametrize("grid,modes,kw", [
+    ((16, 12), (8, 6), {}), ((16,), (6,), {}), ((8, 6, 10), (4, 4, 6), {}), ((9, 11), (4, 5), {}), ((12, 12), (16, 16), {}),
+    ((16, 12), (6, 4), {"max_n_modes": (8, 6)}), ((16, 12), (5, 3), {"max_n_modes": (8, 6)}),
+    ((12, 12), (10, 8), {"out": (24, 24)}), ((12, 12), (10, 8), {"out": (6, 6)}), ((12, 13), (6, 6), {"out": (9, 16)}),
+    ((12, 12), (10, 8), {"fft_norm": "ortho"}), ((12, 12), (10, 8), {"fft_norm": "backward"}), ((6, 6, 6, 6), (4, 4, 4, 4), {}),
+])
+def test_complex_data_chain(emulated, monkeypatch, grid, modes, kw):
+    """complex_data=True is composed on the host from the complex table kernel and the dense mode GEMM: with those two emulated,
+    the tables, the index rules (shift on every dim, central weight cut, first-k rule on the shifted last dim, no un-shift of
+    the last dim) and the adjoint chain of the backward pass are checked against the oracle's restatement of the reference
+    (pinned bit-exactly to the live module in tests/test_oracle_vs_reference.py), differentiated by torch."""
+    monkeypatch.setattr(sc, "get_plan", lambda *a, **k: _Plan(a[3]))
+    torch.manual_seed(5)
+    B, Ci, Co = 2, 3, 4
+    maxm = list(kw.get("max_n_modes", modes))
+    out = list(kw.get("out", grid))
+    norm = kw.get("fft_norm", "forward")
+    plan = sc.ComplexPlan(torch.device("cpu"), list(grid), out, list(modes), maxm, norm)
+    x = torch.randn(B, Ci, *grid, dtype=torch.complex64)
+    w = _c(Ci, Co, *maxm)
+    bias = torch.randn(Co, *[1] * len(grid))
+    gy = torch.randn(B, Co, *out, dtype=torch.complex64)
+
+    def ours(x_, w_, b_):
+        wk = w_
+        for j in range(len(grid)):
+            wk = wk.narrow(2 + j, plan.w_start[j], plan.kept[j])
+        return sc._SpectralConvComplex.apply(x_, wk.contiguous(), plan) + b_
+
+    def ref(x_, w_, b_):
+        return O.spectral_conv_forward_complex(x_, w_, b_, list(modes), max_n_modes=maxm, output_shape=out, fft_norm=norm)
+
+    _compare(ours, ref, [x, w, bias], gy)
+
+
+from conftest import complex_golden_index, load_complex_golden  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(complex_golden_index().keys()))
+def test_complex_module_forward_against_reference_goldens(emulated, monkeypatch, name):
+    """The whole complex_data module path (weight slicing, reconstructed Tucker weights, resampling, bias) with the two device
+    primitives emulated, against what the unmodified reference returned: y, dx and every parameter gradient."""
+    import neuraloperator_b200 as nb
+    monkeypatch.setattr(sc, "get_plan", lambda *a, **k: _Plan(a[3]))
+    monkeypatch.setattr(sc, "get_complex_plan", lambda dev, grid, out, nm, mx, norm: sc.ComplexPlan(torch.device("cpu"), grid, out, nm, mx, norm))
+    meta, arr = load_complex_golden(name)
+    conv = nb.SpectralConv(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), complex_data=True, **dict(meta["ctor"]))
+    assert conv.n_modes == meta["stored_n_modes"] and list(conv.max_n_modes) == meta["max_n_modes"]
+    params = dict(conv.named_parameters())
+    with torch.no_grad():
+        for pname in meta["params"]:
+            ours = pname.replace("weight.factors.", "weight.factors.factor_")
+            params[ours].copy_(arr["p__" + pname.replace(".", "__")])
+    x = arr["x"].clone().requires_grad_(True)
+    y = conv._forward_complex(x, meta["forward"].get("output_shape"))
+    assert list(y.shape[2:]) == meta["out_grid"]
+    y.backward(arr["gy"])
+    assert _rel(y.detach(), arr["y"]) < 2e-5 and _rel(x.grad, arr["dx"]) < 2e-5
+    for pname in meta["params"]:
+        ours = pname.replace("weight.factors.", "weight.factors.factor_")
+        assert _rel(params[ours].grad, arr["g__" + pname.replace(".", "__")]) < 5e-5, pname

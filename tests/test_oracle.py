@@ -126,3 +126,37 @@ def test_tucker_pairwise_evaluation_equals_the_single_einsum(shape, ranks):
     a = O.contract_tucker(xm, core, factors)
     b = O.contract_tucker_pairwise(xm, core, factors)
     assert (a - b).abs().max().item() < 1e-5 * a.abs().max().item()
+
+
+from conftest import complex_golden_index, load_complex_golden  # noqa: E402
+
+COMPLEX_CASES = sorted(complex_golden_index().keys())
+
+
+def _complex_kwargs(meta):
+    kw = {"max_n_modes": meta["max_n_modes"], "fft_norm": meta["ctor"].get("fft_norm", "forward")}
+    if "output_shape" in meta["forward"]:
+        kw["output_shape"] = meta["forward"]["output_shape"]
+    elif "resolution_scaling_factor" in meta["ctor"]:
+        kw["output_shape"] = meta["out_grid"]
+    return kw
+
+
+def _complex_dense_weight(meta, arr):
+    if meta["weight_kind"].endswith("dense"):
+        return arr["p__weight__tensor"]
+    factors = [arr[f"p__weight__factors__{i}"] for i in range(len(meta["grid"]) + 2)]
+    return O.tucker_to_dense(arr["p__weight__core"], factors)
+
+
+@pytest.mark.parametrize("name", COMPLEX_CASES)
+def test_complex_oracle_matches_reference_golden(name):
+    """complex_data=True: the oracle's gather / scatter restatement against what the unmodified reference returned (y, dx)."""
+    meta, arr = load_complex_golden(name)
+    x = arr["x"].clone().requires_grad_(True)
+    w = _complex_dense_weight(meta, arr)
+    y = O.spectral_conv_forward_complex(x, w, arr.get("p__bias"), meta["n_modes"], **_complex_kwargs(meta))
+    assert list(y.shape[2:]) == meta["out_grid"]
+    assert (y - arr["y"]).abs().max() <= 2e-5 * arr["y"].abs().max()
+    y.backward(arr["gy"])
+    assert (x.grad - arr["dx"]).abs().max() <= 2e-5 * arr["dx"].abs().max()

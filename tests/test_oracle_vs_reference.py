@@ -67,3 +67,32 @@ def test_resample_restatement_equals_the_reference(shape, out):
     x = torch.randn(*shape)
     ref = resample(x, 1.0, list(range(2, x.ndim)), output_shape=out)
     assert torch.equal(O.resample_restated(x, out), ref)
+
+
+@pytest.mark.parametrize("grid,modes,kw", [
+    ((16,), (6,), {}), ((16, 12), (8, 6), {}), ((9, 11), (4, 5), {}), ((8, 6, 10), (4, 4, 6), {}), ((12, 12), (16, 16), {}),
+    ((16, 12), (6, 4), {"max_n_modes": (8, 6)}), ((16, 12), (5, 3), {"max_n_modes": (8, 6)}),
+    ((12, 12), (10, 8), {"resolution_scaling_factor": 2}), ((12, 12), (10, 8), {"resolution_scaling_factor": 0.5}),
+    ((12, 12), (10, 8), {"fft_norm": "ortho"}),
+])
+def test_live_reference_bit_exact_complex_data(grid, modes, kw):
+    """complex_data=True: forward and every gradient of the oracle restatement equal the live reference bit for bit."""
+    ref = load_reference_spectral_conv()
+    torch.manual_seed(11)
+    conv = ref.SpectralConv(3, 4, modes, complex_data=True, **kw)
+    x = torch.randn(2, 3, *grid, dtype=torch.cfloat, requires_grad=True)
+    y = conv(x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    okw = {"max_n_modes": conv.max_n_modes, "fft_norm": kw.get("fft_norm", "forward")}
+    if "resolution_scaling_factor" in kw:
+        okw["resolution_scaling_factor"] = [float(kw["resolution_scaling_factor"])] * len(grid)
+    x2 = x.detach().clone().requires_grad_(True)
+    w2 = conv.weight.tensor.detach().clone().requires_grad_(True)
+    b2 = conv.bias.detach().clone().requires_grad_(True)
+    y2 = O.spectral_conv_forward_complex(x2, w2, b2, modes, **okw)
+    y2.backward(g)
+    assert torch.equal(y.detach(), y2.detach())
+    assert torch.equal(x.grad, x2.grad)
+    assert torch.equal(conv.weight.tensor.grad, w2.grad)
+    assert torch.equal(conv.bias.grad, b2.grad)

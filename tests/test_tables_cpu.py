@@ -146,3 +146,47 @@ def test_bf16x3_operand_split_meets_the_tolerance(lib):
     scale = np.abs(exact).max()
     assert np.abs(acc - exact).max() / scale < 1e-5
     assert np.abs((x_hi @ t1) - exact).max() / scale > 1e-3    # single bf16 product: not good enough, hence the split
+
+
+@pytest.mark.parametrize("grid,out", [((8, 8, 8), (12, 12, 12)), ((12, 8, 10), (8, 8, 6)), ((8, 6, 10), (8, 12, 16)), ((8, 8, 8, 8), (4, 8, 12, 6))])
+def test_resample_tables_reproduce_the_reference_resample(lib, grid, out):
+    """SpectralConv.transform for 3-D+ = analysis and synthesis of a SC_FLAG_RESAMPLE plan with nothing in between.  Applied in
+    numpy, the plan's host tables must reproduce the reference's spectral `resample` (resample.py:52-69, restated in the oracle
+    and pinned bit-exactly to the live function), forward and adjoint (the backward of transform)."""
+    d = len(grid)
+    stored = [min(n, m) for n, m in zip(grid[:-1], out[:-1])] + [min(grid[-1] // 2 + 1, out[-1] // 2 + 1)]
+    assert all(k % 2 == 0 for k in stored[:-1])
+    prob = _lib.ScProblem()
+    prob.ndim = d
+    for j in range(d):
+        prob.grid[j], prob.out_grid[j] = grid[j], out[j]
+        prob.n_modes[j] = prob.max_n_modes[j] = stored[j]
+    prob.fft_norm = 0
+    prob.flags = _lib.FLAG_RESAMPLE
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 3, *grid))
+    r = x @ _table(lib, prob, T_LAST_A)
+    xm = r[..., 0::2] + 1j * r[..., 1::2]
+    for j in range(d - 1):
+        xm = _apply(_table(lib, prob, T_LEAD_A, j), xm, 2 + j)
+    u = xm
+    for j in range(d - 1):
+        u = _apply(_table(lib, prob, T_LEAD_S, j), u, 2 + j)
+    y = _interleave(u) @ _table(lib, prob, T_LAST_S)
+    xt = torch.from_numpy(x).float().requires_grad_(True)
+    ref = O.resample_restated(xt, out)
+    assert list(y.shape) == list(ref.shape)
+    assert np.abs(y - ref.detach().numpy()).max() <= 2e-5 * np.abs(ref.detach().numpy()).max()
+    # adjoint: what transform's backward applies to the upstream gradient
+    gy = rng.standard_normal(y.shape)
+    ref.backward(torch.from_numpy(gy).float())
+    g = gy @ _table(lib, prob, T_LAST_ST)
+    gm = g[..., 0::2] + 1j * g[..., 1::2]
+    for j in range(d - 1):
+        gm = _apply(_table(lib, prob, T_LEAD_SH, j), gm, 2 + j)
+    v = gm
+    for j in range(d - 1):
+        v = _apply(_table(lib, prob, T_LEAD_AH, j), v, 2 + j)
+    dx = _interleave(v) @ _table(lib, prob, T_LAST_AT)
+    dx_ref = xt.grad.numpy()
+    assert np.abs(dx - dx_ref).max() <= 2e-5 * np.abs(dx_ref).max()
