@@ -859,11 +859,12 @@ __global__ void __launch_bounds__(FA_THREADS, 1) k_fused_analysis2(const AnaPara
 //   stage A (leading dim) DA[hl, n] = sum_k AA[hl, k] * BA[n, k]      M=128 (rows)  N=2*N1  K=128 (T1 | T2 halves)
 //   stage B (last dim)    DB[hl, w] = sum_j U[hl, j] * TS[j, w]       M=128         N=W     K=N1 x 3 bf16 products
 //
-//   warps 10-13 prep       modes -> bf16 hi/lo real-embedded B operand of stage A (BA[2])
+//   warps 10-13 prep       modes (standard or quad-major layout) -> bf16 hi/lo real-embedded B operand of stage A (BA[2])
 //   warp  8     stage-A MMA issuer (+ TMEM allocation)   BA -> DA[2]
 //   warps 4-7   epilogue A: DA -> U -> bf16 hi/lo A operand of stage B (U[2])
 //   warp  9     stage-B MMA issuer                        U -> DB[2]
-//   warps 0-3   epilogue B: DB -> + bias -> 256-bit global stores of the image rows
+//   warps 0-3, 14-17  epilogue B (two warps per TMEM lane quarter, half of the columns each): DB -> + bias -> swizzled
+//               [32 rows x 128 B] box -> one TMA tensor store per box
 // =====================================================================================================
 constexpr int FS_THREADS = 18 * 32;             // warps 14-17: second epilogue-B group (the other half of the columns)
 constexpr int FS_EPI_B_WARPS = 8;
