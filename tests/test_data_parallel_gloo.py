@@ -56,7 +56,9 @@ def _worker_mixed(rank, world, port, out):
     w = torch.nn.Parameter(torch.zeros(3, 4, 5, dtype=torch.cfloat))
     b = torch.nn.Parameter(torch.zeros(4, 1, 1))
     extra = torch.nn.Parameter(torch.zeros(7))
-    red = GradientAllReducer([w, b, extra])
+    # the peer-memory reducer must behave like the base class for tensors that do not live in its symmetric buffer (CPU here)
+    from neuraloperator_b200.data_parallel import PeerGradientAllReducer
+    red = PeerGradientAllReducer([w, b, extra])
     ok = True
     for step in range(2):                       # two steps: the per-step bookkeeping is reset by finish()
         gw, gb = torch.randn(3, 4, 5, dtype=torch.cfloat), torch.randn(4, 1, 1)
