@@ -1336,27 +1336,7 @@ __global__ void __launch_bounds__(MG2_THREADS, 1) k_mode_gemm_tc(const ModeGemmT
   if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
-// =====================================================================================================
-// mode-wise complex GEMM, four consecutive modes per CTA  ("quad" variant)
-//
-//   Every operand stores the mode index innermost, so the values of 4 consecutive modes of one (row, k) element
-//   are one aligned 32-byte sector: the loaders fetch them with ONE 256-bit load and scatter them into the four
-//   per-mode operand tiles; the epilogue gathers the four per-mode results and writes ONE 32-byte sector.
-//   Global traffic is therefore sector-exact (the single-mode kernel above touches every sector four times).
-//   K (<= 128 real) is consumed in rounds of one 64-wide slab; the four accumulators live side by side in TMEM.
-// =====================================================================================================
-constexpr int MGQ_THREADS = (4 + MG2_LOADER_WARPS) * 32;   // warps 0-3: MMA issue (warp 0) + epilogue, warps 4-19: loaders
-
-struct ModeGemmQuadParams {
-  const float2* a; const float2* b; float2* out;
-  long long sAR, sAK, sBN, sBK, sOR, sON;
-  int MR, NB, KC, NBp, KCp, kshift, conjA, n_groups, rounds, zero_fill;
-  long long* trace;        // debug timeline of CTA 0 (SC_TRACE_FILE), else nullptr
-};
-// fixed per-mode tile layout (compile-time offsets keep the scatter stores on immediate addressing):
-//   [A_hi 16 KB | A_lo 16 KB | B (hi rows, lo rows) up to 16 KB]
-constexpr uint32_t MGQ_MODE_BYTES = 49152, MGQ_OFF_ALO = 16384, MGQ_OFF_B = 32768;
-
+// helpers of the quad kernels below (four consecutive modes of one element = one aligned 32-byte sector)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void ld_global_v8(const float2* p, float (&v)[8]) {
@@ -1365,205 +1345,24 @@ __device__ __forceinline__ void ld_global_v8(const float2* p, float (&v)[8]) {
                : "l"(p));
 }
 
-// timeline of the quad kernel only in -DSC_TRACE_QUAD builds (the extra live pointer costs spills in the loaders)
+// per-role clock64 timeline of CTA 0 of the quad kernels, only in -DSC_TRACE_QUAD builds (scripts/trace_run.py)
 #ifdef SC_TRACE_QUAD
 #define SC_QTRACE(P, role, i, ph) SC_TRACE(P, role, i, ph)
 #else
 #define SC_QTRACE(P, role, i, ph) do { } while (0)
 #endif
 
-// one loader group (256 threads) of the quad kernel: streams operand A (IS_B = false) or B into the four per-mode tiles
-template <bool IS_B>
-__device__ __forceinline__ void mgq_load_operand(const ModeGemmQuadParams& P, uint8_t* smem, int lt, long long m0,
-                                                 uint64_t* bar_full, uint64_t* bar_empty) {
-  const int lane = threadIdx.x & 31;
-  const int kq = lt & (P.KCp - 1);                     // k within the 32-complex slab handled per round (KCp <= 32 here)
-  const int r0 = lt >> P.kshift;
-  const int step = (MG2_LOADERS / 2) >> P.kshift;      // 8, 16 or 32 rows between a thread's elements
-  const int n_rows = IS_B ? P.NB : P.MR;
-  const long long s_row = IS_B ? P.sBN : P.sAR, s_k = IS_B ? P.sBK : P.sAK;
-  // byte offset of this thread's first element inside a per-mode tile, and the distance between its rows
-  const uint32_t off0 = IS_B ? MGQ_OFF_B + sw128_offset(r0, 2 * kq, 2 * P.NBp) : sw128_offset(2 * r0, 2 * kq, 128);
-  const uint32_t off1 = IS_B ? off0 + (uint32_t)P.NBp * 128u : sw128_offset(2 * r0 + 1, 2 * kq, 128);
-  const uint32_t sstep = (uint32_t)step * (IS_B ? 128u : 256u);
-  const float2* base = (IS_B ? P.b : P.a) + m0 + (long long)r0 * s_row;
-  pdl_wait();                                          // operands come from buffers of the previous kernel
-  pdl_launch_dependents();                             // (after the wait: see k_fused_analysis)
-  if (!IS_B && lt < 32) SC_QTRACE(P, 0, 0, 2);
-  for (int rd = 0; rd < P.rounds; ++rd) {
-    const int k = rd * 32 + kq;
-    const bool k_ok = kq < 32 && k < P.KC;
-    const float2* pk = base + (long long)k * s_k;
-    if (!IS_B && lt < 32) SC_QTRACE(P, 0, 1 + rd, 0);
-#pragma unroll
-    for (int bt = 0; bt < 2; ++bt) {
-      float v[4][8];                                   // 4 rows x 4 modes
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (k_ok && r0 + (4 * bt + u) * step < n_rows) ld_global_v8(pk + (long long)(4 * bt + u) * step * s_row, v[u]);
-      if (bt == 0) {
-        // pull what this thread needs next into L2 while the batch is in flight
-#pragma unroll
-        for (int u = 4; u < 8; ++u)
-          if (k_ok && r0 + u * step < n_rows) prefetch_l2(pk + (long long)u * step * s_row);
-        if (rd + 1 < P.rounds && kq < 32 && k + 32 < P.KC) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u)
-            if (r0 + u * step < n_rows) prefetch_l2(pk + 32 * s_k + (long long)u * step * s_row);
-        }
-        if (rd > 0) mbar_wait(bar_empty, (uint32_t)((rd - 1) & 1));   // MMAs of the previous round have read the tiles
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (k_ok && r0 + (4 * bt + u) * step < n_rows) {
-          uint8_t* t0 = smem + off0 + (4 * bt + u) * sstep;
-          uint8_t* t1 = smem + off1 + (4 * bt + u) * sstep;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t hi, lo;
-            split2_bf16(v[u][2 * j], v[u][2 * j + 1], hi, lo);
-            if (IS_B) {                                // rows (n, hi) at off0, (n, lo) NBp rows further
-              *reinterpret_cast<uint32_t*>(t0 + j * MGQ_MODE_BYTES) = hi;
-              *reinterpret_cast<uint32_t*>(t1 + j * MGQ_MODE_BYTES) = lo;
-            } else {                                   // complex row r -> real rows 2r (re, -im | conj: re, im) and 2r+1 (im, re | conj: -im... )
-              uint32_t r0h, r1h, r0l, r1l;
-              if (P.conjA) {
-                r0h = hi; r1h = __byte_perm(hi, 0, 0x1032) ^ 0x00008000u;
-                r0l = lo; r1l = __byte_perm(lo, 0, 0x1032) ^ 0x00008000u;
-              } else {
-                r0h = hi ^ 0x80000000u; r1h = __byte_perm(hi, 0, 0x1032);
-                r0l = lo ^ 0x80000000u; r1l = __byte_perm(lo, 0, 0x1032);
-              }
-              *reinterpret_cast<uint32_t*>(t0 + j * MGQ_MODE_BYTES) = r0h;
-              *reinterpret_cast<uint32_t*>(t1 + j * MGQ_MODE_BYTES) = r1h;
-              *reinterpret_cast<uint32_t*>(t0 + j * MGQ_MODE_BYTES + MGQ_OFF_ALO) = r0l;
-              *reinterpret_cast<uint32_t*>(t1 + j * MGQ_MODE_BYTES + MGQ_OFF_ALO) = r1l;
-            }
-          }
-        }
-      }
-      if (!IS_B && lt < 32) SC_QTRACE(P, 0, 1 + rd, 1 + bt);
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_full);
-  }
-}
-
-__global__ void __launch_bounds__(MGQ_THREADS, 1) k_mode_gemm_quad(const ModeGemmQuadParams P) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ uint64_t bar_full, bar_empty, bar_d_full;
-  __shared__ uint32_t tmem_base_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rowsB = 2 * P.NBp;
-  if (tid == 128) SC_QTRACE(P, 0, 0, 0);
-
-  if (tid == 0) {
-    mbar_init(&bar_full, MG2_LOADER_WARPS);
-    mbar_init(&bar_empty, 1);
-    mbar_init(&bar_d_full, 1);
-    mbar_init_fence();
-  }
-  if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
-  if (P.zero_fill) {
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < (int)(4 * MGQ_MODE_BYTES / 16); i += MGQ_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-  }
-  fence_proxy_async_smem();
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = tmem_base_slot;
-  const long long m0 = (long long)blockIdx.x * 4;      // first mode of this CTA's quad
-  if (tid == 128) SC_QTRACE(P, 0, 0, 1);
-
-  if (warp >= 4) {
-    // ------------------------------------------------------------------ loaders: warps 4-11 own operand A, warps 12-19 operand B,
-    // so that both operands of a round are in flight at once (4 x 256-bit loads per thread and batch, <= 2 batches per round)
-    if (tid - 4 * 32 < MG2_LOADERS / 2) mgq_load_operand<false>(P, smem, tid - 4 * 32, m0, &bar_full, &bar_empty);
-    else mgq_load_operand<true>(P, smem, tid - 4 * 32 - MG2_LOADERS / 2, m0, &bar_full, &bar_empty);
-  } else if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issue (one thread)
-    const uint32_t idesc1 = idesc_bf16(128, rowsB), idesc2 = idesc_bf16(128, P.NBp);
-    const uint32_t base_lo = desc_lo(smem_u32(smem));
-    for (int rd = 0; rd < P.rounds; ++rd) {
-      mbar_wait(&bar_full, (uint32_t)(rd & 1));
-      tc_fence_after_sync();
-      SC_QTRACE(P, 1, 1 + rd, 0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t a_hi = base_lo + (uint32_t)j * (MGQ_MODE_BYTES >> 4), a_lo = a_hi + (MGQ_OFF_ALO >> 4), b_op = a_hi + (MGQ_OFF_B >> 4);
-        const uint32_t d = tmem + (uint32_t)(j * 128);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          mma_bf16_ss(d, desc_from_lo(a_hi + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc1, (rd | kk) != 0);
-          mma_bf16_ss(d, desc_from_lo(a_lo + 2 * kk), desc_from_lo(b_op + 2 * kk), idesc2, true);
-        }
-      }
-      mma_commit(&bar_empty);
-      SC_QTRACE(P, 1, 1 + rd, 1);
-    }
-    mma_commit(&bar_d_full);
-  }
-  __syncwarp();
-  {
-    // ------------------------------------------------------------------ epilogue, ALL warps: four modes -> one 32-byte store.
-    // A warp may read the TMEM lane quarter (warp & 3); the five warps of a quarter split the 8-column chunks.
-    const int q = warp & 3, grp = warp >> 2;
-    const int row = q * 32 + lane;
-    const int R = row >> 1, part = row & 1;
-    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    if (warp < 4) pdl_wait();                          // (loaders already waited) the output buffer may still be read by the previous kernel
-    mbar_wait(&bar_d_full, 0);
-    tc_fence_after_sync();
-    if (warp == 0) SC_QTRACE(P, 1, 5, 0);
-    float2* dst = P.out + m0 + (long long)R * P.sOR;
-    for (int c = 8 * grp; c < P.NBp; c += 8 * (MGQ_THREADS / 128)) {
-      float acc[4][8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float t1[8], t2[8];
-        tmem_ld8(tmem + lane_sel + (uint32_t)(j * 128 + c), t1);
-        tmem_ld8(tmem + lane_sel + (uint32_t)(j * 128 + P.NBp + c), t2);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[j][e] = t1[e] + t2[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float mine = acc[j][e];
-          const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
-          o[2 * j] = mine; o[2 * j + 1] = other;      // (re, im) on even lanes
-        }
-        const int n = c + e;
-        if (part == 0 && R < P.MR && n < P.NB) st_global_v8(reinterpret_cast<float*>(dst + (long long)n * P.sON), o);
-      }
-    }
-    tc_fence_before_sync();
-    if (warp == 0) SC_QTRACE(P, 1, 5, 1);
-  }
-
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 0) SC_QTRACE(P, 1, 5, 2);
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
 // =====================================================================================================
 // mode-wise complex GEMM, four consecutive modes per CTA, second generation ("quad2")
 //
-//   Same sector-exact global traffic as the quad kernel above (one 256-bit load / store per 4 modes of an element), but
-//   no K-rounds through a full shared memory:
+//   Sector-exact global traffic (one 256-bit load / store per 4 modes of an element) like the round-1 quad kernel it replaced
+//   (that one kept both operands as bf16 tiles in shared memory, 192 KB, and consumed K in two serial rounds); here:
 //     * the A operand (2x2-embedded, bf16 hi / lo) lives in TENSOR MEMORY: the loader thread that owns real row r converts
 //       its row's values in registers and writes them with tcgen05.st into a 4-slot ring of 8-k chunks (one MMA K-step);
 //     * the B operand (as stored, bf16 hi rows / lo rows) is the only shared-memory operand: K-slabs of 32 complex k,
 //       3-slot ring (never recycled for K <= 96);
-//     * ONE accumulator per mode: D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi as three N = NBp MMAs per K-step (the quad
-//       kernel keeps the hi / lo products in separate columns: twice the tensor memory);
+//     * ONE accumulator per mode: D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi as three N = NBp MMAs per K-step (hi / lo products
+//       in separate columns would take twice the tensor memory);
 //     * loads are software-pipelined two batches deep per thread with L2 prefetches ahead of them, and operands that the
 //       previous kernel of the stream does not write (weights, saved modes) are fetched BEFORE the grid-dependency wait.
 //   Any MR / NB / KC: 64-row and 64-column tiles over gridDim.y, K streamed through the rings.
@@ -2137,41 +1936,7 @@ static bool mode_gemm_tc_supported(int MR, int NB, int KC) {
   return MR >= 1 && MR <= 64 && NB >= 1 && NB <= 64 && KC >= 1 && KC <= 64;
 }
 
-static bool launch_mode_gemm_quad(const Plan* p, const float2* a, long long sAR, long long sAK, bool conjA, const float2* b,
-                                  long long sBN, long long sBK, float2* out, long long sOR, long long sON, int MR, int NB,
-                                  int KC, int64_t n_modes, cudaStream_t st) {
-  ModeGemmQuadParams P{};
-  P.a = a; P.b = b; P.out = out;
-  P.sAR = sAR; P.sAK = sAK; P.sBN = sBN; P.sBK = sBK; P.sOR = sOR; P.sON = sON;
-  P.MR = MR; P.NB = NB; P.KC = KC;
-  P.NBp = (NB + 15) / 16 * 16;
-  P.rounds = (KC + 31) / 32;
-  P.KCp = 8; P.kshift = 3;
-  const int kc_round = KC < 32 ? KC : 32;
-  while (P.KCp < kc_round) { P.KCp *= 2; ++P.kshift; }
-  P.conjA = conjA ? 1 : 0;
-  P.n_groups = (int)(n_modes / 4);
-  P.zero_fill = (MR < 64 || NB < P.NBp || (KC % 32) != 0) ? 1 : 0;
-  const uint32_t smem_bytes = 4 * MGQ_MODE_BYTES + 1024u;
-  static SmemOptIn opt_in;
-  if (!ensure_dynamic_smem((const void*)k_mode_gemm_quad, opt_in, p->device, smem_bytes, "cudaFuncSetAttribute(k_mode_gemm_quad)"))
-    return false;
-  count_launch();
-  P.trace = trace_begin();
-  void* args[] = {(void*)&P};
-  const bool ok = cuda_ok(launch_pdl((const void*)k_mode_gemm_quad, dim3(P.n_groups), dim3(MGQ_THREADS), smem_bytes, st, args),
-                          "k_mode_gemm_quad launch");
-  trace_end(P.trace, conjA ? "quad conjA" : "quad");
-  return ok;
-}
-
 static inline bool aligned32(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 31u) == 0; }
-
-// SC_QUAD=1 selects the first-generation quad kernel (A/B runs); default: quad2
-static int quad_generation() {
-  static const int v = [] { const char* e = getenv("SC_QUAD"); return e != nullptr && atoi(e) == 1 ? 1 : 2; }();
-  return v;
-}
 
 static bool launch_mode_gemm_quad2(const Plan* p, const float2* a, long long sAR, long long sAK, bool conjA, const float2* b,
                                    long long sBN, long long sBK, float2* out, long long sOR, long long sON, int MR, int NB,
@@ -2318,7 +2083,7 @@ static bool launch_mode_gemm_quad3(const Plan* p, const float2* a, long long sAR
   return ok;
 }
 
-bool quad2_enabled() { return quad_generation() == 2; }
+bool quad2_enabled() { return true; }
 
 bool mode_gemm_quad_eligible(const Plan* p, int64_t n_modes, const void* a, const void* b, const void* out) {
   return p->fast != nullptr && p->weight_block_is_whole && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out);
@@ -2334,15 +2099,11 @@ bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long lon
                           (offO == nullptr || p->weight_block_is_whole);
   const bool strides4 = ((sAR | sAK | sBN | sBK | sOR | sON) & 3) == 0;
   if (contiguous && strides4 && n_modes % 4 == 0 && aligned32(a) && aligned32(b) && aligned32(out)) {
-    if (quad_generation() == 2) {
-      bool handled = false;
-      if (!launch_mode_gemm_quad3(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st, &handled)) return false;
-      if (!handled && !launch_mode_gemm_quad2(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st)) return false;
-      if (ex != nullptr && ex->dbias != nullptr) ex->bias_done = true;
-      return true;
-    }
-    if (MR <= 64 && NB <= 64 && KC <= 64)
-      return launch_mode_gemm_quad(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, st);
+    bool handled = false;
+    if (!launch_mode_gemm_quad3(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st, &handled)) return false;
+    if (!handled && !launch_mode_gemm_quad2(p, a, sAR, sAK, conjA, b, sBN, sBK, out, sOR, sON, MR, NB, KC, n_modes, ex, st)) return false;
+    if (ex != nullptr && ex->dbias != nullptr) ex->bias_done = true;
+    return true;
   }
   if (!mode_gemm_tc_supported(MR, NB, KC)) { set_error("launch_mode_gemm_tc: extents above 64 need the quad layout"); return false; }
   ModeGemmTcParams P{};
@@ -2380,7 +2141,7 @@ bool launch_mode_gemm_tc(const Plan* p, const float2* a, long long sAR, long lon
 // tensor-core kernel (sliced weight blocks, unaligned bases) is limited to 64 x 64 x 64
 bool fast_can_contract(const Plan* p, int B, int Ci, int Co, bool quad_ok) {
   if (p->fast == nullptr) return false;
-  if (quad_ok && quad_generation() == 2) return true;
+  if (quad_ok) return true;
   return mode_gemm_tc_supported(Co, B, Ci) && mode_gemm_tc_supported(Ci, B, Co) && mode_gemm_tc_supported(Ci, Co, B);
 }
 
