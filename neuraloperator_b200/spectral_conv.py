@@ -707,37 +707,54 @@ def _apply_tables(tables, src, lead, sizes_in, sizes_out, order, adjoint):
 
 class _SpectralConvComplex(torch.autograd.Function):
     """y = SpectralConv.forward(x) for complex data and a dense kept-block weight (B,Ci,*grid) -> (B,Co,*out_grid), without the
-    bias: C2C analysis (one complex table product per dim, last dim first), dense mode-wise contraction, C2C synthesis."""
+    bias: C2C analysis (one complex table product per dim, last dim first), mode-wise contraction, C2C synthesis.  The
+    contraction is the dense mode GEMM (w_kept: (Ci, Co, *kept)) or, for `separable` (w_kept: (C, *kept),
+    `_contract_dense_separable` :49-52), the mode-wise product."""
 
     @staticmethod
-    def forward(ctx, x, w_kept, plan: ComplexPlan):
+    def forward(ctx, x, w_kept, plan: ComplexPlan, separable=False):
+        lib = _lib.load()
         B, Ci = x.shape[:2]
-        Co = w_kept.shape[1]
+        Co = Ci if separable else w_kept.shape[1]
         d = plan.ndim
         with torch.cuda.device(x.device):
             xm = _apply_tables(plan.analysis, x, B * Ci, plan.grid, plan.kept, range(d - 1, -1, -1), False).view(B, Ci, *plan.kept)
-            ym = contract_dense(plan.contract_plan, xm, w_kept)
+            if separable:
+                ym = torch.empty_like(xm)
+                _lib.check(lib.sc_cp_apply(_ptr(xm), _ptr(w_kept), _ptr(ym), 0, B, xm[0].numel(), _stream_ptr(x.device)), "sc_cp_apply")
+            else:
+                ym = contract_dense(plan.contract_plan, xm, w_kept)
             y = _apply_tables(plan.synthesis, ym, B * Co, plan.kept, plan.out_grid, range(d), False).view(B, Co, *plan.out_grid)
         ctx.plan = plan
+        ctx.separable = separable
         ctx.save_for_backward(xm, w_kept)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
+        lib = _lib.load()
         plan = ctx.plan
         xm, w_kept = ctx.saved_tensors
         B, Ci = xm.shape[:2]
-        Co = w_kept.shape[1]
+        Co = Ci if ctx.separable else w_kept.shape[1]
         d = plan.ndim
         gy = gy.contiguous()
         if gy.dtype != torch.complex64:
             gy = gy.to(torch.complex64)
+        st = _stream_ptr(gy.device)
         with torch.cuda.device(gy.device):
             gm = _apply_tables(plan.synthesis, gy, B * Co, plan.out_grid, plan.kept, range(d - 1, -1, -1), True).view(B, Co, *plan.kept)
-            dxm, dw, _ = contract_dense_backward(plan.contract_plan, xm, gm, w_kept, need_dbias=False)
+            if ctx.separable:
+                per = xm[0].numel()
+                dw = torch.empty_like(w_kept)
+                _lib.check(lib.sc_cp_dscale(_ptr(xm), _ptr(gm), _ptr(dw), B, per, st), "sc_cp_dscale")
+                dxm = torch.empty_like(gm)
+                _lib.check(lib.sc_cp_apply(_ptr(gm), _ptr(w_kept), _ptr(dxm), 1, B, per, st), "sc_cp_apply")
+            else:
+                dxm, dw, _ = contract_dense_backward(plan.contract_plan, xm, gm, w_kept, need_dbias=False)
             dx = _apply_tables(plan.analysis, dxm, B * Ci, plan.kept, plan.grid, range(d), True).view(B, Ci, *plan.grid)
-        return dx, dw, None
+        return dx, dw, None, None
 
 
 def _validate_scaling_factor(factor, n_dim) -> Optional[List[float]]:
@@ -770,7 +787,7 @@ class SpectralConv(BaseSpectralConv):
 
     Parameters: identical to the reference class (spectral_convolution.py:183-305). `complex_data=True` runs C2C transforms on the
     complex table kernels (any grid; dense or reconstructed weights). Variants the kernels do not cover raise
-    `NotImplementedError` at construction: `fno_block_precision != "full"`, `complex_data` together with `separable`.
+    `NotImplementedError` at construction: `fno_block_precision != "full"`.
     """
 
     def __init__(
@@ -795,8 +812,6 @@ class SpectralConv(BaseSpectralConv):
         device=None,
     ):
         super().__init__(device=device)
-        if complex_data and separable:
-            raise NotImplementedError("complex_data=True with separable=True is not covered by the B200 kernels")
         if separable and in_channels != out_channels:
             raise ValueError("To use separable Fourier Conv, in_channels must be equal "
                              f"to out_channels, but got in_channels={in_channels} and out_channels={out_channels}")
@@ -916,10 +931,11 @@ class SpectralConv(BaseSpectralConv):
                 z = z + (prm.real.sum() if prm.is_complex() else prm.sum()) * 0
             return x.new_zeros((0, self.out_channels, *out_grid)) + z
         w = self.weight.to_tensor()
+        lead = 1 if self.separable else 2                                     # separable: one channel axis (:346-356)
         for j in range(self.order):
-            if plan.w_start[j] != 0 or plan.kept[j] != w.shape[2 + j]:
-                w = w.narrow(2 + j, plan.w_start[j], plan.kept[j])
-        y = _SpectralConvComplex.apply(x.contiguous(), w.contiguous(), plan)
+            if plan.w_start[j] != 0 or plan.kept[j] != w.shape[lead + j]:
+                w = w.narrow(lead + j, plan.w_start[j], plan.kept[j])
+        y = _SpectralConvComplex.apply(x.contiguous(), w.contiguous(), plan, self.separable)
         return y + self.bias if self.bias is not None else y                  # (:567-568; real bias on complex data)
 
     def _forward_separable(self, x, plan: Plan):

@@ -31,6 +31,11 @@ CASES = [
     ("cplx_d3", 1, 3, 4, (8, 6, 10), (4, 4, 6), {}, {}),
     ("cplx_d4", 1, 2, 2, (6, 6, 6, 6), (4, 4, 4, 4), {}, {}),
     ("cplx_d2_tucker_reconstructed", 2, 6, 5, (16, 12), (8, 6), {"factorization": "tucker", "rank": [4, 3, 5, 3]}, {}),
+    # separable=True (one channel axis, mode-wise product); appended so that the seeds of the cases above do not move
+    ("cplx_d2_separable", 2, 5, 5, (16, 12), (8, 6), {"separable": True}, {}),
+    ("cplx_d1_separable_upsample", 2, 4, 4, (16,), (6,), {"separable": True, "resolution_scaling_factor": 2}, {}),
+    ("cplx_d3_separable_max_modes", 1, 3, 3, (8, 6, 10), (3, 4, 5), {"separable": True, "max_n_modes": (4, 4, 6)}, {}),
+    ("cplx_d2_separable_tucker", 2, 5, 5, (16, 12), (8, 6), {"separable": True, "factorization": "tucker", "rank": [3, 5, 3]}, {}),
 ]
 
 

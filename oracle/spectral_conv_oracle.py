@@ -523,8 +523,10 @@ def kept_mode_plan_complex(grid: Sequence[int], n_modes: Sequence[int], max_n_mo
 
 def spectral_conv_forward_complex(x: torch.Tensor, w_dense: torch.Tensor, bias: Optional[torch.Tensor], n_modes: Sequence[int],
                                   max_n_modes: Optional[Sequence[int]] = None, output_shape: Optional[Sequence[int]] = None,
-                                  resolution_scaling_factor: Optional[Sequence[float]] = None, fft_norm: str = "forward"):
-    """`SpectralConv.forward` with complex_data=True and a dense weight, in gather / scatter form."""
+                                  resolution_scaling_factor: Optional[Sequence[float]] = None, fft_norm: str = "forward",
+                                  separable: bool = False):
+    """`SpectralConv.forward` with complex_data=True and a dense weight, in gather / scatter form.  separable: the weight is
+    (C, *max_n_modes) and the contraction is the mode-wise product (`_contract_dense_separable` :49-52)."""
     B, Ci, *grid = x.shape
     d = len(grid)
     if max_n_modes is None:
@@ -535,9 +537,10 @@ def spectral_conv_forward_complex(x: torch.Tensor, w_dense: torch.Tensor, bias: 
     for j, p in enumerate(plans):
         xm = _gather(xm, 2 + j, p.in_bins)
     w = w_dense
+    lead = 1 if separable else 2                                                        # :346-356: one channel axis
     for j, p in enumerate(plans):
-        w = w.narrow(2 + j, p.w_index[0], p.kept)                                       # :489
-    ym = contract_dense(xm.to(torch.cfloat), w)                                         # :520-522
+        w = w.narrow(lead + j, p.w_index[0], p.kept)                                    # :489
+    ym = xm.to(torch.cfloat) * w if separable else contract_dense(xm.to(torch.cfloat), w)   # :520-522
     out_grid = resolve_output_grid(grid, resolution_scaling_factor, output_shape)       # :524-528
     Co = ym.shape[1]
     out_spec = torch.zeros([B, Co] + list(grid), dtype=torch.cfloat, device=x.device)   # :460-462

@@ -63,8 +63,8 @@ def test_module_contract_dense():
         conv(x)
     cplx = nb.SpectralConv(4, 4, (8, 8), complex_data=True)     # C2C: n_modes not halved (reference :408-414)
     assert cplx.n_modes == [8, 8] and tuple(cplx.weight.shape) == (4, 4, 8, 8)
-    with pytest.raises(NotImplementedError):
-        nb.SpectralConv(4, 4, (8, 8), complex_data=True, separable=True)
+    csep = nb.SpectralConv(4, 4, (8, 8), complex_data=True, separable=True)
+    assert tuple(csep.weight.shape) == (4, 8, 8)
     with pytest.raises(NotImplementedError):
         nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half")
     with pytest.raises(ValueError):

@@ -229,16 +229,21 @@ def test_complex_data_chain(emulated, monkeypatch, grid, modes, kw):
     bias = torch.randn(Co, *[1] * len(grid))
     gy = torch.randn(B, Co, *out, dtype=torch.complex64)
 
-    def ours(x_, w_, b_):
+    def ours(x_, w_, b_, lead=2):
         wk = w_
         for j in range(len(grid)):
-            wk = wk.narrow(2 + j, plan.w_start[j], plan.kept[j])
-        return sc._SpectralConvComplex.apply(x_, wk.contiguous(), plan) + b_
+            wk = wk.narrow(lead + j, plan.w_start[j], plan.kept[j])
+        return sc._SpectralConvComplex.apply(x_, wk.contiguous(), plan, lead == 1) + b_
 
-    def ref(x_, w_, b_):
-        return O.spectral_conv_forward_complex(x_, w_, b_, list(modes), max_n_modes=maxm, output_shape=out, fft_norm=norm)
+    def ref(x_, w_, b_, separable=False):
+        return O.spectral_conv_forward_complex(x_, w_, b_, list(modes), max_n_modes=maxm, output_shape=out, fft_norm=norm,
+                                               separable=separable)
 
     _compare(ours, ref, [x, w, bias], gy)
+    # separable=True: one channel axis, mode-wise product (sc_cp_apply / sc_cp_dscale in place of the mode GEMM)
+    ws = _c(Ci, *maxm)
+    _compare(lambda x_, w_, b_: ours(x_, w_, b_, 1), lambda x_, w_, b_: ref(x_, w_, b_, True),
+             [x, ws, torch.randn(Ci, *[1] * len(grid))], torch.randn(B, Ci, *out, dtype=torch.complex64))
 
 
 from conftest import complex_golden_index, load_complex_golden  # noqa: E402

@@ -74,17 +74,19 @@ def test_resample_restatement_equals_the_reference(shape, out):
     ((16, 12), (6, 4), {"max_n_modes": (8, 6)}), ((16, 12), (5, 3), {"max_n_modes": (8, 6)}),
     ((12, 12), (10, 8), {"resolution_scaling_factor": 2}), ((12, 12), (10, 8), {"resolution_scaling_factor": 0.5}),
     ((12, 12), (10, 8), {"fft_norm": "ortho"}),
+    ((16, 12), (8, 6), {"separable": True}), ((16,), (6,), {"separable": True}), ((8, 6, 10), (4, 4, 6), {"separable": True}),
+    ((16, 12), (5, 3), {"separable": True, "max_n_modes": (8, 6)}),
 ])
 def test_live_reference_bit_exact_complex_data(grid, modes, kw):
     """complex_data=True: forward and every gradient of the oracle restatement equal the live reference bit for bit."""
     ref = load_reference_spectral_conv()
     torch.manual_seed(11)
-    conv = ref.SpectralConv(3, 4, modes, complex_data=True, **kw)
+    conv = ref.SpectralConv(3, 3 if kw.get("separable") else 4, modes, complex_data=True, **kw)
     x = torch.randn(2, 3, *grid, dtype=torch.cfloat, requires_grad=True)
     y = conv(x)
     g = torch.randn_like(y)
     y.backward(g)
-    okw = {"max_n_modes": conv.max_n_modes, "fft_norm": kw.get("fft_norm", "forward")}
+    okw = {"max_n_modes": conv.max_n_modes, "fft_norm": kw.get("fft_norm", "forward"), "separable": bool(kw.get("separable"))}
     if "resolution_scaling_factor" in kw:
         okw["resolution_scaling_factor"] = [float(kw["resolution_scaling_factor"])] * len(grid)
     x2 = x.detach().clone().requires_grad_(True)
@@ -92,7 +94,14 @@ def test_live_reference_bit_exact_complex_data(grid, modes, kw):
     b2 = conv.bias.detach().clone().requires_grad_(True)
     y2 = O.spectral_conv_forward_complex(x2, w2, b2, modes, **okw)
     y2.backward(g)
-    assert torch.equal(y.detach(), y2.detach())
-    assert torch.equal(x.grad, x2.grad)
-    assert torch.equal(conv.weight.tensor.grad, w2.grad)
-    assert torch.equal(conv.bias.grad, b2.grad)
+    if kw.get("separable"):
+        # the mode-wise product runs on a strided view in the reference and on the gathered block here: ATen's vectorised and
+        # scalar complex multiplies round differently in the last bit, so this one is pinned to 1 ulp-level instead of bit-exactly
+        def same(a, b):
+            return (a - b).abs().max().item() <= 4e-7 * max(b.abs().max().item(), 1e-30)
+    else:
+        same = torch.equal
+    assert same(y.detach(), y2.detach())
+    assert same(x.grad, x2.grad)
+    assert same(conv.weight.tensor.grad, w2.grad)
+    assert same(conv.bias.grad, b2.grad)
