@@ -134,7 +134,8 @@ COMPLEX_CASES = sorted(complex_golden_index().keys())
 
 
 def _complex_kwargs(meta):
-    kw = {"max_n_modes": meta["max_n_modes"], "fft_norm": meta["ctor"].get("fft_norm", "forward")}
+    kw = {"max_n_modes": meta["max_n_modes"], "fft_norm": meta["ctor"].get("fft_norm", "forward"),
+          "separable": bool(meta["ctor"].get("separable", False))}
     if "output_shape" in meta["forward"]:
         kw["output_shape"] = meta["forward"]["output_shape"]
     elif "resolution_scaling_factor" in meta["ctor"]:
@@ -145,7 +146,8 @@ def _complex_kwargs(meta):
 def _complex_dense_weight(meta, arr):
     if meta["weight_kind"].endswith("dense"):
         return arr["p__weight__tensor"]
-    factors = [arr[f"p__weight__factors__{i}"] for i in range(len(meta["grid"]) + 2)]
+    n_axes = len(meta["grid"]) + (1 if meta["ctor"].get("separable") else 2)      # separable: one channel axis
+    factors = [arr[f"p__weight__factors__{i}"] for i in range(n_axes)]
     return O.tucker_to_dense(arr["p__weight__core"], factors)
 
 
