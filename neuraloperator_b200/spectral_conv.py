@@ -107,7 +107,7 @@ class Plan:
 
 
 _PLAN_CACHE: "OrderedDict[tuple, Plan]" = OrderedDict()
-_PLAN_LOCK = threading.Lock()
+_PLAN_LOCK = threading.RLock()      # re-entrant: building a ComplexPlan (under the lock) asks get_plan for its contraction plan
 _PLAN_CACHE_MAX = 64
 
 
@@ -630,9 +630,10 @@ class ComplexPlan:
     cut centrally along every dim; the last dim nevertheless takes the FIRST k entries of its (shifted) spectrum; on the way
     back only the leading dims are un-shifted, so the last dim's slots are synthesised at their own index."""
 
-    def __init__(self, device, grid, out_grid, n_modes, max_n_modes, fft_norm):
+    def __init__(self, device, grid, out_grid, n_modes, max_n_modes, fft_norm, table_device=None):
         import math
         d = len(grid)
+        table_device = device if table_device is None else table_device      # (tests build the tables without a GPU)
         self.ndim, self.grid, self.out_grid = d, tuple(grid), tuple(out_grid)
         self.kept, self.w_start, self.analysis, self.synthesis = [], [], [], []
         if fft_norm == "forward":
@@ -660,8 +661,8 @@ class ComplexPlan:
             sy = torch.polar(torch.full_like(ang_s, s_inv if last else 1.0), ang_s) * (out_pos[None, :] < M)   # ifftn(s=M) crops the end
             self.kept.append(k)
             self.w_start.append(start // 2 if start else 0)
-            self.analysis.append(a.to(torch.complex64).contiguous().to(device))
-            self.synthesis.append(sy.to(torch.complex64).contiguous().to(device))
+            self.analysis.append(a.to(torch.complex64).contiguous().to(table_device))
+            self.synthesis.append(sy.to(torch.complex64).contiguous().to(table_device))
         self.kept = tuple(self.kept)
         # the dense mode GEMM only needs a plan whose kept block is (k_1..k_d) with weight extents == kept
         self.contract_plan = get_plan(device, [*self.kept[:-1], 2 * self.kept[-1]], [*self.kept[:-1], 2 * self.kept[-1]],

@@ -176,3 +176,28 @@ def test_kept_mode_index_set_is_bit_exact(lib):
                     assert got == (p.in_bins, p.w_index)
                     checked += 1
     assert checked > 500
+
+
+def test_complex_contraction_plans_are_valid_problems(lib):
+    """complex_data=True borrows the dense mode GEMM through a real-data plan whose kept block is (k_1..k_d): grid
+    (k_1, .., k_{d-1}, 2 k_d), stored modes == max modes == k.  The library's host-side plan builder (no device needed) must
+    accept every such problem the complex goldens produce and keep exactly k_j modes with weight rows 0..k_j-1 (whole block)."""
+    from conftest import complex_golden_index
+    for name, meta in complex_golden_index().items():
+        grid = meta["grid"]
+        kept = [min(n, k) for n, k in zip(grid, meta["stored_n_modes"])]
+        cgrid = [*kept[:-1], 2 * kept[-1]]
+        for dim in range(len(kept)):
+            bins, rows = _c_mode_bins(lib, cgrid, kept, kept, dim)
+            assert len(bins) == kept[dim] and rows == list(range(kept[dim])), (name, dim, bins, rows)
+        # the table builder runs the full host-side plan construction
+        prob = _lib.ScProblem()
+        prob.ndim = len(kept)
+        for j in range(len(kept)):
+            prob.grid[j] = prob.out_grid[j] = cgrid[j]
+            prob.n_modes[j] = prob.max_n_modes[j] = kept[j]
+        r, c = ctypes.c_int64(0), ctypes.c_int64(0)
+        rc = lib.sc_problem_table(ctypes.byref(prob), 0, 0,   # SC_TABLE_LAST_ANALYSIS
+                                  None, 0, ctypes.byref(r), ctypes.byref(c))
+        assert rc == 0, (name, lib.sc_last_error())
+        assert (r.value, c.value) == (cgrid[-1], 2 * kept[-1]), (name, r.value, c.value)

@@ -272,3 +272,34 @@ def test_complex_module_forward_against_reference_goldens(emulated, monkeypatch,
     for pname in meta["params"]:
         ours = pname.replace("weight.factors.", "weight.factors.factor_")
         assert _rel(params[ours].grad, arr["g__" + pname.replace(".", "__")]) < 5e-5, pname
+
+
+def test_complex_plan_cache_does_not_deadlock(monkeypatch):
+    """get_complex_plan builds a ComplexPlan under the plan-cache lock, and the ComplexPlan asks get_plan (same lock) for its
+    contraction plan: with only the C plan object faked, the real cache code must return (run on a watchdog thread, so that
+    a regression fails instead of hanging the suite) and must hand back the cached object the second time."""
+    import threading
+
+    class _FakeCPlan:
+        def __init__(self, device, grid, out_grid, n_modes, max_n_modes, fft_norm, flags=0):
+            self.args = (tuple(grid), tuple(out_grid), tuple(n_modes), tuple(max_n_modes), fft_norm, flags)
+
+    real = sc.ComplexPlan
+    monkeypatch.setattr(sc, "Plan", _FakeCPlan)
+    monkeypatch.setattr(sc, "ComplexPlan", lambda dev, *a: real(dev, *a, table_device=torch.device("cpu")))
+    monkeypatch.setattr(sc, "_PLAN_CACHE", type(sc._PLAN_CACHE)())
+    monkeypatch.setattr(sc, "_COMPLEX_PLANS", type(sc._COMPLEX_PLANS)())
+    out = {}
+
+    def work():
+        dev = torch.device("cuda", 0)
+        out["a"] = sc.get_complex_plan(dev, [16, 12], [16, 12], [8, 6], [8, 6], "forward")
+        out["b"] = sc.get_complex_plan(dev, [16, 12], [16, 12], [8, 6], [8, 6], "forward")
+
+    t = threading.Thread(target=work, daemon=True)
+    t.start()
+    t.join(20)
+    assert not t.is_alive(), "get_complex_plan deadlocked on the plan-cache lock"
+    assert out["a"] is out["b"] and out["a"].kept == (8, 6)
+    # the contraction plan: kept block (8, 6) of a real-data problem whose last dim is twice as long
+    assert out["a"].contract_plan.args == ((8, 12), (8, 12), (8, 6), (8, 6), "forward", 0)
