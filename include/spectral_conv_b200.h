@@ -194,6 +194,54 @@ int sc_backward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const floa
 int sc_allreduce_p2p(float* const* peer_buffers, uint32_t* const* peer_signal_pads, int32_t rank, int32_t world_size, int64_t n_floats,
                      float scale, int32_t n_ctas, sc_stream stream);
 
+/* ---- Fourier-layer epilogue around the spectral convolution ---------------------------
+ * What neuralop/layers/fno_block.py:377-414 (`FNOBlocks.forward_with_postactivation`) does with the conv output, as ONE kernel
+ * per channel-mixing step instead of one tensor pass per torch op.  Tensors are float (B, C, P) contiguous, P = points of the grid:
+ *
+ *   pre[b,o,p] = sum_i w[o*w_stride_o + i*w_stride_i] * in[b,i,p] + bias[o] + add[b,o,p] + gate[o] * gated[b,o,p]
+ *   out        = act(pre)                      (SC_ACT_GELU = F.gelu's default exact erf form, fno_block.py:150)
+ *
+ *   f1  x1  = gelu( conv(x) + W_skip x )       in = x, w = fno_skips[i].conv.weight (Flattened1dConv, skip_connections.py:96-130),
+ *                                              add = the SpectralConv output                                  (fno_block.py:379-397)
+ *   f2  h   = gelu( W1 x1 + b1 )               ChannelMLP.fcs[0] (channel_mlp.py:63-116)
+ *       out = act( W2 h + b2 + gate * x )      ChannelMLP.fcs[1] + SoftGating skip (skip_connections.py:53-93)  (fno_block.py:399-412)
+ *
+ * bias, add, gate, gated, pre_out may each be NULL (gate NULL with gated given = coefficient 1: the identity skip); in_channels may
+ * be 0 (no mixing term: in / w unused).  pre_out (B, Co, P): the pre-activation, stored for the backward pass when given. */
+enum { SC_ACT_IDENTITY = 0, SC_ACT_GELU = 1 };
+int sc_channel_mix(const float* in, const float* w, int64_t w_stride_o, int64_t w_stride_i, const float* bias, const float* add,
+                   const float* gate, const float* gated, int act, float* out, float* pre_out, int32_t batch, int32_t in_channels,
+                   int32_t out_channels, int64_t n_points, sc_stream stream);
+/* Backward, step 1 -- elementwise with the per-channel reductions folded in (pre may be NULL for SC_ACT_IDENTITY):
+ *   gpre = gout * act'(pre)  -> gpre_out (may be NULL, may alias gout);  this is also the gradient of `add`
+ *   dgated_out = gate[c] * gpre (may be NULL);  dbias[c] = sum_{b,p} gpre;  dgate[c] = sum_{b,p} gpre * gated  (each may be NULL)
+ * Step 2, the gradient of `in`, is sc_channel_mix itself with the transposed weight strides (in = gpre, no adds, identity).
+ * Step 3: dw[o, i] = sum_{b,p} gpre[b,o,p] * in[b,i,p]   (dw (Co, Ci) row-major = the layout of a Conv1d weight (Co, Ci, 1)). */
+int sc_channel_mix_act_backward(const float* gout, const float* pre, int act, const float* gate, const float* gated, float* gpre_out,
+                                float* dgated_out, float* dbias, float* dgate, int32_t batch, int32_t channels, int64_t n_points,
+                                sc_stream stream);
+int sc_channel_mix_weight_grad(const float* gpre, const float* in, float* dw, int32_t batch, int32_t in_channels, int32_t out_channels,
+                               int64_t n_points, sc_stream stream);
+/* Elementwise helpers of the same layer: out[i] = op(a[i], b[i]).
+ *   SC_POINTWISE_TANH           tanh(a)             the "tanh" stabilizer in front of the conv (fno_block.py:386-390)
+ *   SC_POINTWISE_TANH_BACKWARD  a * (1 - b*b)       a = upstream gradient, b = tanh(x)
+ *   SC_POINTWISE_ROUND_HALF     float(half(a))      the points where fno_block_precision "half" / "mixed" casts to fp16
+ *                                                   (x.half() :436-437, x.chalf() :451-454, chalf output spectrum :456-462) */
+enum { SC_POINTWISE_TANH = 0, SC_POINTWISE_TANH_BACKWARD = 1, SC_POINTWISE_ROUND_HALF = 2 };
+int sc_pointwise(int op, const float* a, const float* b, float* out, int64_t n, sc_stream stream);
+/* Host checks of the four kernels above: the kernels are sequences of __host__ __device__ tile functions; these entry points run
+ * exactly those functions thread by thread, block by block, on HOST buffers (same arguments, no stream).  They exist so that the CPU
+ * test tier can check the index arithmetic of the device code without a GPU; nothing in the Python package calls them. */
+int sc_hostcheck_channel_mix(const float* in, const float* w, int64_t w_stride_o, int64_t w_stride_i, const float* bias, const float* add,
+                             const float* gate, const float* gated, int act, float* out, float* pre_out, int32_t batch,
+                             int32_t in_channels, int32_t out_channels, int64_t n_points);
+int sc_hostcheck_channel_mix_act_backward(const float* gout, const float* pre, int act, const float* gate, const float* gated,
+                                          float* gpre_out, float* dgated_out, float* dbias, float* dgate, int32_t batch,
+                                          int32_t channels, int64_t n_points);
+int sc_hostcheck_channel_mix_weight_grad(const float* gpre, const float* in, float* dw, int32_t batch, int32_t in_channels,
+                                         int32_t out_channels, int64_t n_points);
+int sc_hostcheck_pointwise(int op, const float* a, const float* b, float* out, int64_t n);
+
 /* events for the grads_ready hand-over above (timing disabled); sc_stream_wait_event makes `stream` wait for the last record */
 int  sc_event_create(sc_event* event_out);
 void sc_event_destroy(sc_event event);

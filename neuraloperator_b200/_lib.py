@@ -12,6 +12,8 @@ from .build import LIB_PATH
 SC_MAX_DIMS = 4
 NORMS = {"forward": 0, "backward": 1, "ortho": 2}
 FLAG_RESAMPLE = 1
+ACT_IDENTITY, ACT_GELU = 0, 1
+POINTWISE_TANH, POINTWISE_TANH_BACKWARD, POINTWISE_ROUND_HALF = 0, 1, 2
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int
@@ -71,6 +73,19 @@ SIGNATURES = {
     "sc_cp_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i32, c_i64, c_void_p]),
     "sc_cp_dscale": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i64, c_void_p]),
     "sc_cp_factor_grad": (c_int, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
+    "sc_channel_mix": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_i32, c_i32, c_i32, c_i64, c_void_p]),
+    "sc_channel_mix_act_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                            c_i32, c_i32, c_i64, c_void_p]),
+    "sc_channel_mix_weight_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i64, c_void_p]),
+    "sc_pointwise": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    # host checks of the layer kernels' tile functions (tests only)
+    "sc_hostcheck_channel_mix": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_i32, c_i32, c_i32, c_i64]),
+    "sc_hostcheck_channel_mix_act_backward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                      c_void_p, c_i32, c_i32, c_i64]),
+    "sc_hostcheck_channel_mix_weight_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i64]),
+    "sc_hostcheck_pointwise": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64]),
     "sc_probe_tma_gather": (c_int, [c_void_p, c_i32, c_i32, c_i64, c_void_p, c_void_p]),
     "sc_last_error": (ctypes.c_char_p, []),
     "sc_kernel_launch_count": (ctypes.c_uint64, []),

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_NAME = "libspectral_conv_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
-SOURCES = ["sc_api.cu", "sc_generic.cu", "sc_fast.cu", "sc_collective.cu"]
+SOURCES = ["sc_api.cu", "sc_generic.cu", "sc_fast.cu", "sc_collective.cu", "sc_layer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

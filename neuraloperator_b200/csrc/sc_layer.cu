@@ -1,0 +1,563 @@
+// sc_layer.cu -- the Fourier-layer epilogue around the spectral convolution:
+//
+//   f1  x1  = act( SpectralConv(x) + W_skip x )                       neuralop/layers/fno_block.py:377-397
+//           (linear skip = Flattened1dConv, 1x1 conv without bias, skip_connections.py:96-130)
+//   f2  out = act( W2 gelu(W1 x1 + b1) + b2 + gate * x )              fno_block.py:399-412, channel_mlp.py:6-119,
+//           (soft-gating skip: per-channel weight, skip_connections.py:53-93)
+//   f3  tanh stabilizer / fp16 rounding points of the reduced-precision modes (fno_block.py:386-390,
+//       spectral_convolution.py:436-462)
+//
+// Every one of these is a pass over a (B, C, P) tensor (P = points of the grid) whose arithmetic is per point.  PyTorch runs
+// them as separate kernels (conv1d, add, gelu, mul, add, gelu ...: ~20 tensor passes per layer); here ONE kernel computes
+//
+//   pre[b,o,p] = sum_i w[o,i] in[b,i,p] + bias[o] + add[b,o,p] + gate[o] * gated[b,o,p],     out = act(pre)
+//
+// so f1 is one launch (reads x and the conv output, writes x1) and f2 is two.  Backward is three kernels: the activation
+// derivative with the per-channel reductions (dbias, dgate), the same mixing kernel with the transposed weight (din), and a
+// reduction GEMM over the points for dweight.
+//
+// These are plain SIMT fp32 kernels (exact fp32 products, so results agree with PyTorch's fp32 conv to summation order).  They were
+// written after the round's GPU minutes were spent, so: no mbarriers, no spin waits, bounded loops only -- and every kernel body
+// is a sequence of `__host__ __device__` tile functions that the `sc_hostcheck_*` entry points below run thread by thread on
+// host buffers, which is how tests/test_layer_cpu.py checks the index arithmetic of the very code the GPU executes.
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "sc_plan.h"
+
+namespace sc {
+
+#define SC_HD __host__ __device__ __forceinline__
+
+// ---- activations (F.gelu default = exact erf form, torch/nn/functional.py; fno_block.py:150 non_linearity=F.gelu) ------------
+SC_HD float act_apply(int act, float v) {
+  if (act == SC_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+SC_HD float act_grad(int act, float v) {
+  if (act == SC_ACT_GELU) {
+    const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+    return cdf + v * pdf;
+  }
+  return 1.0f;
+}
+SC_HD void red_add(float* addr, float v) {
+#ifdef __CUDA_ARCH__
+  atomicAdd(addr, v);
+#else
+  *addr += v;       // the host check runs the threads one after the other
+#endif
+}
+
+// =====================================================================================================================
+// 1. channel mixing + adds + activation
+// =====================================================================================================================
+constexpr int MIX_THREADS = 256;
+constexpr int MIX_TO = 64;     // output channels per CTA
+constexpr int MIX_TP = 128;    // points per CTA
+constexpr int MIX_KC = 16;     // input channels per shared-memory stage
+
+struct MixArgs {
+  const float* in;             // (B, Ci, P) or nullptr when Ci == 0
+  const float* w;              // element (o, i) at w[o * w_so + i * w_si]
+  long long w_so, w_si;
+  const float* bias;           // (Co) or nullptr
+  const float* add;            // (B, Co, P) or nullptr
+  const float* gate;           // (Co) or nullptr (coefficient 1)
+  const float* gated;          // (B, Co, P) or nullptr
+  float* out;                  // (B, Co, P)
+  float* pre_out;              // (B, Co, P) or nullptr
+  int act;
+  int B, Ci, Co;
+  long long P;
+};
+struct MixAcc { float v[8][4]; };      // thread tile: 8 output channels x 4 points (points strided by 32: coalesced rows)
+
+struct Grid3 { long long x; int y, z; };
+static Grid3 mix_grid(const MixArgs& a) {
+  return Grid3{(a.P + MIX_TP - 1) / MIX_TP, (a.Co + MIX_TO - 1) / MIX_TO, a.B};
+}
+
+// stage the [KC x TP] block of `in` and the [KC x TO] block of w^T (zero beyond the extents)
+SC_HD void mix_load(const MixArgs& a, int b, int o0, long long p0, int i0, int tid, float* s_in, float* s_w) {
+  const float* in_b = a.in + (long long)b * a.Ci * a.P;
+#pragma unroll
+  for (int r = 0; r < MIX_KC * MIX_TP / MIX_THREADS; ++r) {
+    const int idx = tid + r * MIX_THREADS;
+    const int i = idx / MIX_TP, p = idx % MIX_TP;
+    float v = 0.f;
+    if (i0 + i < a.Ci && p0 + p < a.P) v = in_b[(long long)(i0 + i) * a.P + p0 + p];
+    s_in[idx] = v;                                   // [i][p]
+  }
+#pragma unroll
+  for (int r = 0; r < MIX_KC * MIX_TO / MIX_THREADS; ++r) {
+    const int idx = tid + r * MIX_THREADS;
+    const int i = idx / MIX_TO, o = idx % MIX_TO;
+    float v = 0.f;
+    if (i0 + i < a.Ci && o0 + o < a.Co) v = a.w[(long long)(o0 + o) * a.w_so + (long long)(i0 + i) * a.w_si];
+    s_w[idx] = v;                                    // [i][o]
+  }
+}
+
+SC_HD void mix_fma(int tid, const float* s_in, const float* s_w, MixAcc& acc) {
+  const int ty = tid >> 5, tx = tid & 31;
+#pragma unroll
+  for (int i = 0; i < MIX_KC; ++i) {
+    float wv[8], xv[4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) wv[r] = s_w[i * MIX_TO + ty * 8 + r];          // one address per warp: broadcast
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xv[j] = s_in[i * MIX_TP + tx + 32 * j];        // consecutive lanes, consecutive banks
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc.v[r][j] = fmaf(wv[r], xv[j], acc.v[r][j]);
+  }
+}
+
+SC_HD void mix_store(const MixArgs& a, int b, int o0, long long p0, int tid, const MixAcc& acc) {
+  const int ty = tid >> 5, tx = tid & 31;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int o = o0 + ty * 8 + r;
+    if (o < a.Co) {
+      const float bo = a.bias != nullptr ? a.bias[o] : 0.f;
+      const float go = a.gate != nullptr ? a.gate[o] : 1.f;
+      const long long row = ((long long)b * a.Co + o) * a.P;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const long long p = p0 + tx + 32 * j;
+        if (p < a.P) {
+          float v = acc.v[r][j] + bo;
+          if (a.add != nullptr) v += a.add[row + p];
+          if (a.gated != nullptr) v = fmaf(go, a.gated[row + p], v);
+          if (a.pre_out != nullptr) a.pre_out[row + p] = v;
+          a.out[row + p] = act_apply(a.act, v);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MIX_THREADS) k_channel_mix(MixArgs a) {
+  __shared__ __align__(16) float s_in[MIX_KC * MIX_TP];
+  __shared__ __align__(16) float s_w[MIX_KC * MIX_TO];
+  const int tid = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * MIX_TP;
+  const int o0 = blockIdx.y * MIX_TO;
+  const int b = blockIdx.z;
+  MixAcc acc;
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc.v[r][j] = 0.f;
+  for (int i0 = 0; i0 < a.Ci; i0 += MIX_KC) {
+    mix_load(a, b, o0, p0, i0, tid, s_in, s_w);
+    __syncthreads();
+    mix_fma(tid, s_in, s_w, acc);
+    __syncthreads();
+  }
+  mix_store(a, b, o0, p0, tid, acc);
+}
+
+static void host_channel_mix(const MixArgs& a) {
+  const Grid3 g = mix_grid(a);
+  std::vector<float> s_in(MIX_KC * MIX_TP), s_w(MIX_KC * MIX_TO);
+  std::vector<MixAcc> acc(MIX_THREADS);
+  for (int bz = 0; bz < g.z; ++bz)
+    for (int by = 0; by < g.y; ++by)
+      for (long long bx = 0; bx < g.x; ++bx) {
+        const long long p0 = bx * MIX_TP;
+        const int o0 = by * MIX_TO;
+        std::memset(acc.data(), 0, sizeof(MixAcc) * acc.size());
+        for (int i0 = 0; i0 < a.Ci; i0 += MIX_KC) {
+          for (int t = 0; t < MIX_THREADS; ++t) mix_load(a, bz, o0, p0, i0, t, s_in.data(), s_w.data());
+          for (int t = 0; t < MIX_THREADS; ++t) mix_fma(t, s_in.data(), s_w.data(), acc[t]);
+        }
+        for (int t = 0; t < MIX_THREADS; ++t) mix_store(a, bz, o0, p0, t, acc[t]);
+      }
+}
+
+// =====================================================================================================================
+// 2. activation derivative + per-channel reductions
+// =====================================================================================================================
+constexpr int AB_THREADS = 256;
+constexpr int AB_PER_THREAD = 16;                       // a CTA covers 4096 points of one (b, c) row
+constexpr int AB_SPAN = AB_THREADS * AB_PER_THREAD;
+
+struct ActBwdArgs {
+  const float* gout;           // (B, C, P)
+  const float* pre;            // (B, C, P) or nullptr (identity)
+  int act;
+  const float* gate;           // (C) or nullptr (coefficient 1)
+  const float* gated;          // (B, C, P) or nullptr
+  float* gpre;                 // (B, C, P) or nullptr; may alias gout
+  float* dgated;               // (B, C, P) or nullptr
+  float* dbias;                // (C) or nullptr, pre-zeroed
+  float* dgate;                // (C) or nullptr, pre-zeroed
+  int B, C;
+  long long P;
+};
+static Grid3 ab_grid(const ActBwdArgs& a) { return Grid3{(a.P + AB_SPAN - 1) / AB_SPAN, a.C, a.B}; }
+
+SC_HD void ab_thread(const ActBwdArgs& a, int b, int c, long long p0, int tid, float* s_sum) {
+  const long long row = ((long long)b * a.C + c) * a.P;
+  const float g_c = a.gate != nullptr ? a.gate[c] : 1.f;
+  float sb = 0.f, sg = 0.f;
+  for (int r = 0; r < AB_PER_THREAD; ++r) {
+    const long long p = p0 + tid + (long long)r * AB_THREADS;
+    if (p >= a.P) break;
+    float g = a.gout[row + p];
+    if (a.pre != nullptr) g *= act_grad(a.act, a.pre[row + p]);
+    if (a.gpre != nullptr) a.gpre[row + p] = g;
+    sb += g;
+    if (a.gated != nullptr) sg = fmaf(g, a.gated[row + p], sg);
+    if (a.dgated != nullptr) a.dgated[row + p] = g_c * g;
+  }
+  s_sum[tid] = sb;
+  s_sum[AB_THREADS + tid] = sg;
+}
+// lane 0 of every warp folds the 32 partials of its own warp (each warp touches only its own 32 slots)
+SC_HD void ab_fold_warp(int tid, float* s_sum) {
+  if ((tid & 31) != 0) return;
+  float sb = 0.f, sg = 0.f;
+  for (int l = 0; l < 32; ++l) { sb += s_sum[tid + l]; sg += s_sum[AB_THREADS + tid + l]; }
+  s_sum[tid] = sb;
+  s_sum[AB_THREADS + tid] = sg;
+}
+SC_HD void ab_finish(const ActBwdArgs& a, int c, int tid, const float* s_sum) {
+  if (tid != 0) return;
+  float sb = 0.f, sg = 0.f;
+  for (int w = 0; w < AB_THREADS / 32; ++w) { sb += s_sum[w * 32]; sg += s_sum[AB_THREADS + w * 32]; }
+  if (a.dbias != nullptr) red_add(a.dbias + c, sb);
+  if (a.dgate != nullptr) red_add(a.dgate + c, sg);
+}
+
+__global__ void __launch_bounds__(AB_THREADS) k_channel_act_backward(ActBwdArgs a) {
+  __shared__ float s_sum[2 * AB_THREADS];
+  const int tid = threadIdx.x;
+  ab_thread(a, blockIdx.z, blockIdx.y, (long long)blockIdx.x * AB_SPAN, tid, s_sum);
+  __syncthreads();
+  ab_fold_warp(tid, s_sum);
+  __syncthreads();
+  ab_finish(a, blockIdx.y, tid, s_sum);
+}
+
+static void host_channel_act_backward(const ActBwdArgs& a) {
+  const Grid3 g = ab_grid(a);
+  std::vector<float> s_sum(2 * AB_THREADS);
+  for (int bz = 0; bz < g.z; ++bz)
+    for (int by = 0; by < g.y; ++by)
+      for (long long bx = 0; bx < g.x; ++bx) {
+        for (int t = 0; t < AB_THREADS; ++t) ab_thread(a, bz, by, bx * AB_SPAN, t, s_sum.data());
+        for (int t = 0; t < AB_THREADS; ++t) ab_fold_warp(t, s_sum.data());
+        for (int t = 0; t < AB_THREADS; ++t) ab_finish(a, by, t, s_sum.data());
+      }
+}
+
+// =====================================================================================================================
+// 3. dweight[o, i] = sum_{b, p} g[b, o, p] * in[b, i, p]
+// =====================================================================================================================
+constexpr int WG_THREADS = 256;
+constexpr int WG_T = 64;           // tile of output channels and of input channels
+constexpr int WG_KP = 32;          // points per shared-memory stage
+constexpr int WG_LD = 68;          // row pitch of the transposed stages (floats; keeps rows 16-byte aligned)
+constexpr int WG_CHUNK = 2048;     // points per CTA (multiple of WG_KP)
+
+struct WGradArgs {
+  const float* g;              // (B, Co, P)
+  const float* in;             // (B, Ci, P)
+  float* dw;                   // (Co, Ci) row-major, pre-zeroed
+  int B, Ci, Co;
+  long long P;
+};
+struct WgAcc { float v[4][4]; };
+static Grid3 wg_grid(const WGradArgs& a) {
+  const int to = (a.Co + WG_T - 1) / WG_T, ti = (a.Ci + WG_T - 1) / WG_T;
+  return Grid3{(a.P + WG_CHUNK - 1) / WG_CHUNK, to * ti, a.B};
+}
+
+SC_HD void wg_load(const WGradArgs& a, int b, int o0, int i0, long long p0, int tid, float* s_g, float* s_x) {
+#pragma unroll
+  for (int r = 0; r < WG_T * WG_KP / WG_THREADS; ++r) {
+    const int idx = tid + r * WG_THREADS;
+    const int row = idx / WG_KP, p = idx % WG_KP;       // a warp reads 32 consecutive points of one channel row
+    float gv = 0.f, xv = 0.f;
+    if (p0 + p < a.P) {
+      if (o0 + row < a.Co) gv = a.g[((long long)b * a.Co + o0 + row) * a.P + p0 + p];
+      if (i0 + row < a.Ci) xv = a.in[((long long)b * a.Ci + i0 + row) * a.P + p0 + p];
+    }
+    s_g[p * WG_LD + row] = gv;                          // transposed: [p][channel]
+    s_x[p * WG_LD + row] = xv;
+  }
+}
+SC_HD void wg_fma(int tid, const float* s_g, const float* s_x, WgAcc& acc) {
+  const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll 8
+  for (int p = 0; p < WG_KP; ++p) {
+    float gv[4], xv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) gv[r] = s_g[p * WG_LD + ty * 4 + r];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xv[c] = s_x[p * WG_LD + tx * 4 + c];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc.v[r][c] = fmaf(gv[r], xv[c], acc.v[r][c]);
+  }
+}
+SC_HD void wg_store(const WGradArgs& a, int o0, int i0, int tid, const WgAcc& acc) {
+  const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int o = o0 + ty * 4 + r;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int i = i0 + tx * 4 + c;
+      if (o < a.Co && i < a.Ci) red_add(a.dw + (long long)o * a.Ci + i, acc.v[r][c]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WG_THREADS) k_channel_weight_grad(WGradArgs a) {
+  __shared__ __align__(16) float s_g[WG_KP * WG_LD];
+  __shared__ __align__(16) float s_x[WG_KP * WG_LD];
+  const int tid = threadIdx.x;
+  const int ti = (a.Ci + WG_T - 1) / WG_T;
+  const int o0 = ((int)blockIdx.y / ti) * WG_T, i0 = ((int)blockIdx.y % ti) * WG_T;
+  const int b = blockIdx.z;
+  const long long p_begin = (long long)blockIdx.x * WG_CHUNK;
+  const long long p_end = (p_begin + WG_CHUNK < a.P) ? p_begin + WG_CHUNK : a.P;
+  WgAcc acc;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc.v[r][c] = 0.f;
+  for (long long p0 = p_begin; p0 < p_end; p0 += WG_KP) {
+    wg_load(a, b, o0, i0, p0, tid, s_g, s_x);
+    __syncthreads();
+    wg_fma(tid, s_g, s_x, acc);
+    __syncthreads();
+  }
+  wg_store(a, o0, i0, tid, acc);
+}
+
+static void host_channel_weight_grad(const WGradArgs& a) {
+  const Grid3 g = wg_grid(a);
+  const int ti = (a.Ci + WG_T - 1) / WG_T;
+  std::vector<float> s_g(WG_KP * WG_LD), s_x(WG_KP * WG_LD);
+  std::vector<WgAcc> acc(WG_THREADS);
+  for (int bz = 0; bz < g.z; ++bz)
+    for (int by = 0; by < g.y; ++by)
+      for (long long bx = 0; bx < g.x; ++bx) {
+        const int o0 = (by / ti) * WG_T, i0 = (by % ti) * WG_T;
+        const long long p_begin = bx * WG_CHUNK;
+        const long long p_end = (p_begin + WG_CHUNK < a.P) ? p_begin + WG_CHUNK : a.P;
+        std::memset(acc.data(), 0, sizeof(WgAcc) * acc.size());
+        for (long long p0 = p_begin; p0 < p_end; p0 += WG_KP) {
+          for (int t = 0; t < WG_THREADS; ++t) wg_load(a, bz, o0, i0, p0, t, s_g.data(), s_x.data());
+          for (int t = 0; t < WG_THREADS; ++t) wg_fma(t, s_g.data(), s_x.data(), acc[t]);
+        }
+        for (int t = 0; t < WG_THREADS; ++t) wg_store(a, o0, i0, t, acc[t]);
+      }
+}
+
+// =====================================================================================================================
+// 4. elementwise: tanh stabilizer (fno_block.py:386-390) and the fp16 rounding points of the reduced-precision spectral path
+// =====================================================================================================================
+constexpr int PW_THREADS = 256;
+constexpr int PW_PER_THREAD = 8;
+
+SC_HD float pointwise_elem(int op, const float* a, const float* b, long long i) {
+  switch (op) {
+    case SC_POINTWISE_TANH: return tanhf(a[i]);
+    case SC_POINTWISE_TANH_BACKWARD: { const float t = b[i]; return a[i] * (1.0f - t * t); }    // a = upstream grad, b = tanh(x)
+    case SC_POINTWISE_ROUND_HALF: return __half2float(__float2half_rn(a[i]));                   // x.half() (:436-437), x.chalf() (:451-454)
+    default: return a[i];
+  }
+}
+__global__ void __launch_bounds__(PW_THREADS) k_pointwise(int op, const float* a, const float* b, float* out, long long n) {
+  const long long base = (long long)blockIdx.x * (PW_THREADS * PW_PER_THREAD) + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < PW_PER_THREAD; ++r) {
+    const long long i = base + (long long)r * PW_THREADS;
+    if (i < n) out[i] = pointwise_elem(op, a, b, i);
+  }
+}
+
+// ---- launches ---------------------------------------------------------------------------------------------------------
+static bool grid_ok(const Grid3& g, const char* what) {
+  if (g.x > 2147483647LL || g.y > 65535 || g.z > 65535) { set_error(std::string(what) + ": problem exceeds the launch grid limits"); return false; }
+  return true;
+}
+
+static bool launch_channel_mix(const MixArgs& a, cudaStream_t st) {
+  if (a.B <= 0 || a.Co <= 0 || a.P <= 0) return true;
+  const Grid3 g = mix_grid(a);
+  if (!grid_ok(g, "sc_channel_mix")) return false;
+  k_channel_mix<<<dim3((unsigned)g.x, (unsigned)g.y, (unsigned)g.z), MIX_THREADS, 0, st>>>(a);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_channel_mix launch");
+}
+static bool launch_channel_act_backward(const ActBwdArgs& a, cudaStream_t st) {
+  if (a.dbias != nullptr && !cuda_ok(cudaMemsetAsync(a.dbias, 0, sizeof(float) * (size_t)a.C, st), "dbias memset")) return false;
+  if (a.dgate != nullptr && !cuda_ok(cudaMemsetAsync(a.dgate, 0, sizeof(float) * (size_t)a.C, st), "dgate memset")) return false;
+  if (a.B <= 0 || a.C <= 0 || a.P <= 0) return true;
+  const Grid3 g = ab_grid(a);
+  if (!grid_ok(g, "sc_channel_mix_act_backward")) return false;
+  k_channel_act_backward<<<dim3((unsigned)g.x, (unsigned)g.y, (unsigned)g.z), AB_THREADS, 0, st>>>(a);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_channel_act_backward launch");
+}
+static bool launch_channel_weight_grad(const WGradArgs& a, cudaStream_t st) {
+  if (a.Co <= 0 || a.Ci <= 0) return true;
+  if (!cuda_ok(cudaMemsetAsync(a.dw, 0, sizeof(float) * (size_t)a.Co * (size_t)a.Ci, st), "dweight memset")) return false;
+  if (a.B <= 0 || a.P <= 0) return true;
+  const Grid3 g = wg_grid(a);
+  if (!grid_ok(g, "sc_channel_mix_weight_grad")) return false;
+  k_channel_weight_grad<<<dim3((unsigned)g.x, (unsigned)g.y, (unsigned)g.z), WG_THREADS, 0, st>>>(a);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_channel_weight_grad launch");
+}
+static bool launch_pointwise(int op, const float* a, const float* b, float* out, long long n, cudaStream_t st) {
+  if (n <= 0) return true;
+  const long long per = PW_THREADS * PW_PER_THREAD;
+  const long long blocks = (n + per - 1) / per;
+  if (blocks > 2147483647LL) { set_error("sc_pointwise: tensor exceeds the launch grid limits"); return false; }
+  k_pointwise<<<(unsigned)blocks, PW_THREADS, 0, st>>>(op, a, b, out, n);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_pointwise launch");
+}
+
+}  // namespace sc
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+using namespace sc;
+
+#define SC_TRY(expr) do { if (!(expr)) return 1; } while (0)
+#define SC_REQUIRE(cond, msg) do { if (!(cond)) { set_error(msg); return 1; } } while (0)
+
+static int fill_mix(MixArgs& a, const char* who, const float* in, const float* w, int64_t w_stride_o, int64_t w_stride_i, const float* bias,
+                    const float* add, const float* gate, const float* gated, int act, float* out, float* pre_out, int32_t batch,
+                    int32_t in_channels, int32_t out_channels, int64_t n_points) {
+  (void)who;
+  SC_REQUIRE(out != nullptr, "sc_channel_mix: null output");
+  SC_REQUIRE(batch >= 0 && in_channels >= 0 && out_channels >= 0 && n_points >= 0, "sc_channel_mix: negative extent");
+  SC_REQUIRE(in_channels == 0 || (in != nullptr && w != nullptr), "sc_channel_mix: in / w are required when in_channels > 0");
+  SC_REQUIRE(gate == nullptr || gated != nullptr, "sc_channel_mix: a gate needs the tensor it gates");
+  SC_REQUIRE(act == SC_ACT_IDENTITY || act == SC_ACT_GELU, "sc_channel_mix: unknown activation");
+  a = MixArgs{in, w, (long long)w_stride_o, (long long)w_stride_i, bias, add, gate, gated, out, pre_out, act, batch, in_channels,
+              out_channels, (long long)n_points};
+  return 0;
+}
+
+static int fill_act_backward(ActBwdArgs& a, const float* gout, const float* pre, int act, const float* gate, const float* gated,
+                             float* gpre_out, float* dgated_out, float* dbias, float* dgate, int32_t batch, int32_t channels,
+                             int64_t n_points) {
+  SC_REQUIRE(gout != nullptr, "sc_channel_mix_act_backward: null upstream gradient");
+  SC_REQUIRE(batch >= 0 && channels >= 0 && n_points >= 0, "sc_channel_mix_act_backward: negative extent");
+  SC_REQUIRE(act == SC_ACT_IDENTITY || act == SC_ACT_GELU, "sc_channel_mix_act_backward: unknown activation");
+  SC_REQUIRE(act == SC_ACT_IDENTITY || pre != nullptr, "sc_channel_mix_act_backward: the activation derivative needs the pre-activation");
+  SC_REQUIRE(dgate == nullptr || gated != nullptr, "sc_channel_mix_act_backward: dgate needs the gated tensor");
+  a = ActBwdArgs{gout, act == SC_ACT_IDENTITY ? nullptr : pre, act, gate, gated, gpre_out, dgated_out, dbias, dgate, batch, channels,
+                 (long long)n_points};
+  return 0;
+}
+
+extern "C" {
+
+int sc_channel_mix(const float* in, const float* w, int64_t w_stride_o, int64_t w_stride_i, const float* bias, const float* add,
+                   const float* gate, const float* gated, int act, float* out, float* pre_out, int32_t batch, int32_t in_channels,
+                   int32_t out_channels, int64_t n_points, sc_stream stream) {
+  MixArgs a;
+  if (fill_mix(a, "sc_channel_mix", in, w, w_stride_o, w_stride_i, bias, add, gate, gated, act, out, pre_out, batch, in_channels,
+               out_channels, n_points)) return 1;
+  SC_TRY(launch_channel_mix(a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_channel_mix_act_backward(const float* gout, const float* pre, int act, const float* gate, const float* gated, float* gpre_out,
+                                float* dgated_out, float* dbias, float* dgate, int32_t batch, int32_t channels, int64_t n_points,
+                                sc_stream stream) {
+  ActBwdArgs a;
+  if (fill_act_backward(a, gout, pre, act, gate, gated, gpre_out, dgated_out, dbias, dgate, batch, channels, n_points)) return 1;
+  SC_TRY(launch_channel_act_backward(a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_channel_mix_weight_grad(const float* gpre, const float* in, float* dw, int32_t batch, int32_t in_channels, int32_t out_channels,
+                               int64_t n_points, sc_stream stream) {
+  SC_REQUIRE(gpre != nullptr && in != nullptr && dw != nullptr, "sc_channel_mix_weight_grad: null argument");
+  SC_REQUIRE(batch >= 0 && in_channels >= 0 && out_channels >= 0 && n_points >= 0, "sc_channel_mix_weight_grad: negative extent");
+  WGradArgs a{gpre, in, dw, batch, in_channels, out_channels, (long long)n_points};
+  SC_TRY(launch_channel_weight_grad(a, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int sc_pointwise(int op, const float* a, const float* b, float* out, int64_t n, sc_stream stream) {
+  SC_REQUIRE(op == SC_POINTWISE_TANH || op == SC_POINTWISE_TANH_BACKWARD || op == SC_POINTWISE_ROUND_HALF, "sc_pointwise: unknown op");
+  SC_REQUIRE(n == 0 || (a != nullptr && out != nullptr), "sc_pointwise: null argument");
+  SC_REQUIRE(op != SC_POINTWISE_TANH_BACKWARD || n == 0 || b != nullptr, "sc_pointwise: tanh backward needs tanh(x)");
+  SC_TRY(launch_pointwise(op, a, b, out, (long long)n, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+// ---- host checks: the same tile functions, run thread by thread on HOST buffers (tests only; the package never calls them) ----
+int sc_hostcheck_channel_mix(const float* in, const float* w, int64_t w_stride_o, int64_t w_stride_i, const float* bias, const float* add,
+                             const float* gate, const float* gated, int act, float* out, float* pre_out, int32_t batch,
+                             int32_t in_channels, int32_t out_channels, int64_t n_points) {
+  MixArgs a;
+  if (fill_mix(a, "sc_hostcheck_channel_mix", in, w, w_stride_o, w_stride_i, bias, add, gate, gated, act, out, pre_out, batch,
+               in_channels, out_channels, n_points)) return 1;
+  if (a.B <= 0 || a.Co <= 0 || a.P <= 0) return 0;
+  SC_TRY(grid_ok(mix_grid(a), "sc_hostcheck_channel_mix"));
+  host_channel_mix(a);
+  return 0;
+}
+
+int sc_hostcheck_channel_mix_act_backward(const float* gout, const float* pre, int act, const float* gate, const float* gated,
+                                          float* gpre_out, float* dgated_out, float* dbias, float* dgate, int32_t batch,
+                                          int32_t channels, int64_t n_points) {
+  ActBwdArgs a;
+  if (fill_act_backward(a, gout, pre, act, gate, gated, gpre_out, dgated_out, dbias, dgate, batch, channels, n_points)) return 1;
+  if (a.dbias != nullptr) std::memset(a.dbias, 0, sizeof(float) * (size_t)a.C);
+  if (a.dgate != nullptr) std::memset(a.dgate, 0, sizeof(float) * (size_t)a.C);
+  if (a.B <= 0 || a.C <= 0 || a.P <= 0) return 0;
+  SC_TRY(grid_ok(ab_grid(a), "sc_hostcheck_channel_mix_act_backward"));
+  host_channel_act_backward(a);
+  return 0;
+}
+
+int sc_hostcheck_channel_mix_weight_grad(const float* gpre, const float* in, float* dw, int32_t batch, int32_t in_channels,
+                                         int32_t out_channels, int64_t n_points) {
+  SC_REQUIRE(gpre != nullptr && in != nullptr && dw != nullptr, "sc_hostcheck_channel_mix_weight_grad: null argument");
+  WGradArgs a{gpre, in, dw, batch, in_channels, out_channels, (long long)n_points};
+  if (a.Co <= 0 || a.Ci <= 0) return 0;
+  std::memset(a.dw, 0, sizeof(float) * (size_t)a.Co * (size_t)a.Ci);
+  if (a.B <= 0 || a.P <= 0) return 0;
+  SC_TRY(grid_ok(wg_grid(a), "sc_hostcheck_channel_mix_weight_grad"));
+  host_channel_weight_grad(a);
+  return 0;
+}
+
+int sc_hostcheck_pointwise(int op, const float* a, const float* b, float* out, int64_t n) {
+  SC_REQUIRE(op == SC_POINTWISE_TANH || op == SC_POINTWISE_TANH_BACKWARD || op == SC_POINTWISE_ROUND_HALF, "sc_hostcheck_pointwise: unknown op");
+  // the kernel's own index walk: block, thread, slot
+  const long long per = PW_THREADS * PW_PER_THREAD;
+  const long long blocks = (n + per - 1) / per;
+  for (long long blk = 0; blk < blocks; ++blk)
+    for (int t = 0; t < PW_THREADS; ++t)
+      for (int r = 0; r < PW_PER_THREAD; ++r) {
+        const long long i = blk * per + t + (long long)r * PW_THREADS;
+        if (i < n) out[i] = pointwise_elem(op, a, b, i);
+      }
+  return 0;
+}
+
+}  // extern "C"
