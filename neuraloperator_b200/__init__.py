@@ -9,3 +9,5 @@ from .factorized import FactorizedWeight  # noqa: F401
 from .data_parallel import GradientAllReducer, PeerGradientAllReducer  # noqa: F401
 
 __version__ = "0.1.0"
+from .fno_block import (ChannelMLP, Flattened1dConv, FNOBlocks, SoftGating, channel_mix,  # noqa: F401
+                        skip_connection)

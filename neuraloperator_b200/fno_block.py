@@ -1,0 +1,451 @@
+"""The Fourier layer around the spectral convolution (tanh stabilizer of f3): B200-native drop-ins
+for `neuralop.layers.fno_block.FNOBlocks`, `neuralop.layers.channel_mlp.ChannelMLP` and the skip connections of
+`neuralop.layers.skip_connections` -- same constructor arguments, same parameter names (state dicts load both ways), same forward
+semantics (fno_block.py:371-453), with everything after the spectral convolution running in the fused kernels of
+`csrc/sc_layer.cu`:
+
+    f1   x1  = act( SpectralConv(x) + W_skip x )                 ONE launch: reads x and the conv output, writes x1
+    f2   h   = gelu( W1 x1 + b1 );  out = act( W2 h + b2 + gate * x )     two launches
+
+instead of one tensor pass per torch op (conv1d, add, gelu, mul, add, gelu ...).  No CPU / PyTorch fallback: the modules raise on
+CPU tensors, and configurations the kernels do not cover (norm layers, complex data, dropout, activations other than GELU,
+conv_bias_kernel > 1) raise `NotImplementedError` at construction.
+"""
+import ctypes
+import math
+from typing import List, Optional, Union
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from .spectral_conv import SpectralConv, _ptr, _stream_ptr
+
+Number = Union[int, float]
+ACT_IDENTITY, ACT_GELU = _lib.ACT_IDENTITY, _lib.ACT_GELU
+
+
+def _require_device_tensor(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"neuraloperator_b200 has no CPU path: {what} must live on a B200 (got {t.device})")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32 (full precision, real data), got {t.dtype}")
+
+
+def _launch_channel_mix(x, weight, w_stride_o, w_stride_i, bias, add, gate, gated, act, out, pre, B, Ci, Co, P):
+    lib = _lib.load()
+    dev = out.device
+    with torch.cuda.device(dev):
+        _lib.check(lib.sc_channel_mix(_ptr(x), _ptr(weight), w_stride_o, w_stride_i, _ptr(bias), _ptr(add), _ptr(gate), _ptr(gated), act,
+                                      _ptr(out), _ptr(pre), B, Ci, Co, P, _stream_ptr(dev)), "sc_channel_mix")
+
+
+class _ChannelMix(torch.autograd.Function):
+    """out = act( W x + bias + add + gate * gated )  on (B, C, *S) tensors; any of x/W, bias, add, gate, gated may be None
+    (gate None with gated given: coefficient 1).  W: (Co, Ci) or a Conv1d weight (Co, Ci, 1); gate: any shape with Co elements."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, add, gate, gated, act):
+        ref = add if add is not None else (gated if gated is not None else x)
+        if x is None and ref is None:
+            raise ValueError("channel_mix needs at least one tensor operand")
+        B, spatial = ref.shape[0], tuple(ref.shape[2:])
+        P = math.prod(spatial)
+        Ci = x.shape[1] if x is not None else 0
+        Co = weight.shape[0] if weight is not None else ref.shape[1]
+        for name, t in (("x", x), ("add", add), ("gated", gated), ("weight", weight), ("bias", bias), ("gate", gate)):
+            if t is not None:
+                _require_device_tensor(t, f"channel_mix {name}")
+        if x is not None:
+            if weight is None or weight.numel() != Co * Ci:
+                raise ValueError(f"channel_mix: weight must hold (Co, Ci) = ({Co}, {Ci}) elements")
+            if tuple(x.shape[2:]) != spatial or x.shape[0] != B:
+                raise ValueError(f"channel_mix: x {tuple(x.shape)} does not match the other operands (B={B}, grid={spatial})")
+            x = x.contiguous()
+            weight = weight.contiguous()
+        for name, t in (("add", add), ("gated", gated)):
+            if t is not None and tuple(t.shape) != (B, Co, *spatial):
+                raise ValueError(f"channel_mix: {name} must be {(B, Co, *spatial)}, got {tuple(t.shape)}")
+        if bias is not None and bias.numel() != Co:
+            raise ValueError(f"channel_mix: bias must hold {Co} elements")
+        if gate is not None and (gated is None or gate.numel() != Co):
+            raise ValueError(f"channel_mix: gate must hold {Co} elements and needs the tensor it gates")
+        add = add.contiguous() if add is not None else None
+        gated = gated.contiguous() if gated is not None else None
+        bias_c = bias.contiguous() if bias is not None else None
+        gate_c = gate.contiguous() if gate is not None else None
+        out = torch.empty((B, Co, *spatial), dtype=torch.float32, device=ref.device)
+        # the GELU derivative needs the pre-activation: stored only when some input asks for a gradient
+        pre = torch.empty_like(out) if act != ACT_IDENTITY and any(ctx.needs_input_grad) else None
+        if out.numel():
+            _launch_channel_mix(x, weight, Ci, 1, bias_c, add, gate_c, gated, act, out, pre, B, Ci, Co, P)
+        ctx.act, ctx.dims = act, (B, Ci, Co, P)
+        ctx.shapes = (weight.shape if weight is not None else None, bias.shape if bias is not None else None,
+                      gate.shape if gate is not None else None)
+        ctx.save_for_backward(x, weight, pre, gate_c, gated)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        x, weight, pre, gate_c, gated = ctx.saved_tensors
+        act = ctx.act
+        B, Ci, Co, P = ctx.dims
+        w_shape, b_shape, g_shape = ctx.shapes
+        need_x, need_w, need_b, need_add, need_gate, need_gated = ctx.needs_input_grad[:6]
+        need_x = need_x and x is not None
+        need_w = need_w and weight is not None
+        dev = gout.device
+        gout = gout.contiguous()
+        if gout.dtype != torch.float32:
+            gout = gout.float()
+        if gout.numel() == 0:
+            z = lambda t, need: torch.zeros_like(t) if need and t is not None else None      # noqa: E731
+            return (z(x, need_x), z(weight, need_w), torch.zeros(b_shape, device=dev) if need_b and b_shape is not None else None,
+                    gout if need_add else None, torch.zeros(g_shape, device=dev) if need_gate and g_shape is not None else None,
+                    z(gated, need_gated), None)
+        f32 = dict(dtype=torch.float32, device=dev)
+        gpre = gout if act == ACT_IDENTITY else torch.empty_like(gout)
+        dbias = torch.empty(Co, **f32) if need_b and b_shape is not None else None
+        dgate = torch.empty(Co, **f32) if need_gate and g_shape is not None else None
+        dgated = torch.empty_like(gout) if need_gated and gated is not None else None
+        st = _stream_ptr(dev)
+        with torch.cuda.device(dev):
+            if act != ACT_IDENTITY or dbias is not None or dgate is not None or dgated is not None:
+                _lib.check(lib.sc_channel_mix_act_backward(_ptr(gout), _ptr(pre), act, _ptr(gate_c), _ptr(gated if dgate is not None else None),
+                                                           _ptr(gpre if act != ACT_IDENTITY else None), _ptr(dgated), _ptr(dbias), _ptr(dgate),
+                                                           B, Co, P, st), "sc_channel_mix_act_backward")
+            dx = None
+            if need_x:
+                # din[b, i, p] = sum_o W[o, i] gpre[b, o, p]: the mixing kernel with the weight read through transposed strides
+                dx = torch.empty_like(x)
+                _lib.check(lib.sc_channel_mix(_ptr(gpre), _ptr(weight), 1, Ci, None, None, None, None, ACT_IDENTITY, _ptr(dx), None,
+                                              B, Co, Ci, P, st), "sc_channel_mix (input gradient)")
+            dw = None
+            if need_w:
+                dw = torch.empty(Co, Ci, **f32)
+                _lib.check(lib.sc_channel_mix_weight_grad(_ptr(gpre), _ptr(x), _ptr(dw), B, Ci, Co, P, st), "sc_channel_mix_weight_grad")
+                dw = dw.view(w_shape)
+        return (dx, dw, dbias.view(b_shape) if dbias is not None else None, gpre if need_add else None,
+                dgate.view(g_shape) if dgate is not None else None, dgated, None)
+
+
+def channel_mix(x=None, weight=None, bias=None, add=None, gate=None, gated=None, act: int = ACT_IDENTITY):
+    """Functional form of the fused pointwise op (differentiable in every tensor argument)."""
+    return _ChannelMix.apply(x, weight, bias, add, gate, gated, int(act))
+
+
+class _Tanh(torch.autograd.Function):
+    """The "tanh" stabilizer in front of the spectral conv (fno_block.py:386-390)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        _require_device_tensor(x, "tanh stabilizer input")
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        if x.numel():
+            with torch.cuda.device(x.device):
+                _lib.check(lib.sc_pointwise(_lib.POINTWISE_TANH, _ptr(x), None, _ptr(out), x.numel(), _stream_ptr(x.device)), "sc_pointwise")
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        (out,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        dx = torch.empty_like(out)
+        if out.numel():
+            with torch.cuda.device(g.device):
+                _lib.check(lib.sc_pointwise(_lib.POINTWISE_TANH_BACKWARD, _ptr(g), _ptr(out), _ptr(dx), out.numel(), _stream_ptr(g.device)),
+                           "sc_pointwise")
+        return dx
+
+
+# --------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names (state-dict compatible) and fused forwards
+# --------------------------------------------------------------------------------------------------
+class SoftGating(nn.Module):
+    """`x * w` with w of shape (1, C, 1, ..) (skip_connections.py:53-93)."""
+
+    def __init__(self, in_features, out_features=None, n_dim=2, bias=False):
+        super().__init__()
+        if out_features is not None and in_features != out_features:
+            raise ValueError(f"Got in_features={in_features} and out_features={out_features}, "
+                             "but these two must be the same for soft-gating")
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.ones(1, self.in_features, *(1,) * n_dim))
+        self.bias = nn.Parameter(torch.ones(1, self.in_features, *(1,) * n_dim)) if bias else None
+
+    def forward(self, x):
+        return channel_mix(bias=self.bias, gate=self.weight, gated=x)
+
+
+class Flattened1dConv(nn.Module):
+    """The "linear" skip: a Conv1d with kernel size 1 over the flattened grid (skip_connections.py:96-130)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size=1, bias=False):
+        super().__init__()
+        if kernel_size != 1:
+            raise NotImplementedError("Flattened1dConv: only kernel_size=1 (a pointwise channel mixing) is built")
+        self.conv = nn.Conv1d(in_channels=in_channels, out_channels=out_channels, kernel_size=1, bias=bias)     # parameter container
+
+    def forward(self, x):
+        return channel_mix(x, self.conv.weight, self.conv.bias)
+
+
+def skip_connection(in_features, out_features, n_dim=2, bias=False, skip_type="soft-gating"):
+    """Same wrapper as skip_connections.py:5-50."""
+    kind = skip_type.lower()
+    if kind == "soft-gating":
+        return SoftGating(in_features=in_features, out_features=out_features, bias=bias, n_dim=n_dim)
+    if kind == "linear":
+        return Flattened1dConv(in_channels=in_features, out_channels=out_features, kernel_size=1, bias=bias)
+    if kind == "identity":
+        return nn.Identity()
+    raise ValueError(f"Got skip-connection type={skip_type}, expected one of {'soft-gating', 'linear', 'id'}.")
+
+
+class ChannelMLP(nn.Module):
+    """Pointwise MLP over the channels (channel_mlp.py:6-119): every layer is one fused launch (mixing + bias + GELU); the last one
+    can also take the block's skip term and final activation (`_forward_fused`)."""
+
+    def __init__(self, in_channels, out_channels=None, hidden_channels=None, n_layers=2, n_dim=2, non_linearity=F.gelu, dropout=0.0):
+        super().__init__()
+        if non_linearity is not F.gelu:
+            raise NotImplementedError("ChannelMLP: the fused kernels implement F.gelu (exact erf form) only")
+        if dropout > 0.0:
+            raise NotImplementedError("ChannelMLP: dropout is not built")
+        self.n_layers = n_layers
+        self.in_channels = in_channels
+        self.out_channels = in_channels if out_channels is None else out_channels
+        self.hidden_channels = in_channels if hidden_channels is None else hidden_channels
+        self.non_linearity = non_linearity
+        self.dropout = None
+        self.fcs = nn.ModuleList()                                                       # Conv1d modules as parameter containers
+        for i in range(n_layers):
+            cin = self.in_channels if i == 0 else self.hidden_channels
+            cout = self.out_channels if i == n_layers - 1 else self.hidden_channels
+            self.fcs.append(nn.Conv1d(cin, cout, 1))
+
+    def _forward_fused(self, x, gate=None, gated=None, final_act=ACT_IDENTITY):
+        for i, fc in enumerate(self.fcs):
+            if i < self.n_layers - 1:
+                x = channel_mix(x, fc.weight, fc.bias, act=ACT_GELU)
+            else:
+                x = channel_mix(x, fc.weight, fc.bias, gate=gate, gated=gated, act=final_act)
+        return x
+
+    def forward(self, x):
+        return self._forward_fused(x)
+
+
+# --------------------------------------------------------------------------------------------------
+# FNOBlocks
+# --------------------------------------------------------------------------------------------------
+def _validate_scaling_factor(factor, n_dim, n_layers):
+    """neuralop/utils.py:151-197 with n_layers given: a list (per layer) of lists (per dim) of floats, or None."""
+    if factor is None:
+        return None
+    if isinstance(factor, (float, int)):
+        return [[float(factor)] * n_dim] * n_layers
+    if isinstance(factor, list) and len(factor) > 0 and all(isinstance(s, (float, int)) for s in factor):
+        return [[float(s)] * n_dim for s in factor]
+    if isinstance(factor, list) and len(factor) > 0 and all(isinstance(s, list) for s in factor):
+        return [[float(v) for v in s] for s in factor]
+    return None
+
+
+class FNOBlocks(nn.Module):
+    """Drop-in for `neuralop.layers.fno_block.FNOBlocks` (fno_block.py:46-470) on the B200 kernels: n_layers Fourier layers, each
+    SpectralConv + skip + (ChannelMLP + skip), applied one at a time with `forward(x, index)`.  Same arguments; unsupported choices
+    raise NotImplementedError here instead of silently running something else."""
+
+    def __init__(
+        self,
+        in_channels,
+        out_channels,
+        n_modes,
+        resolution_scaling_factor=None,
+        n_layers=1,
+        max_n_modes=None,
+        fno_block_precision="full",
+        use_channel_mlp=True,
+        channel_mlp_dropout=0,
+        channel_mlp_expansion=0.5,
+        non_linearity=F.gelu,
+        stabilizer=None,
+        norm=None,
+        norm_groups=1,
+        ada_in_features=None,
+        preactivation=False,
+        fno_skip="linear",
+        conv_bias_kernel=1,
+        channel_mlp_skip="soft-gating",
+        complex_data=False,
+        separable=False,
+        factorization=None,
+        rank=1.0,
+        conv_module=SpectralConv,
+        fixed_rank_modes=False,
+        implementation="factorized",
+        decomposition_kwargs=dict(),
+        enforce_hermitian_symmetry=True,
+    ):
+        super().__init__()
+        if isinstance(n_modes, int):
+            n_modes = [n_modes]
+        self._n_modes = n_modes
+        self.n_dim = len(n_modes)
+        if norm is not None:
+            raise NotImplementedError(f"FNOBlocks(norm={norm!r}): normalisation layers are not built")
+        if complex_data:
+            raise NotImplementedError("FNOBlocks(complex_data=True): the layer epilogue kernels are real-valued "
+                                      "(SpectralConv itself supports complex data)")
+        if non_linearity is not F.gelu:
+            raise NotImplementedError("FNOBlocks: the fused epilogue implements F.gelu (exact erf form) only")
+        if channel_mlp_dropout:
+            raise NotImplementedError("FNOBlocks: channel_mlp_dropout is not built")
+        if conv_bias_kernel != 1:
+            raise NotImplementedError("FNOBlocks: conv_bias_kernel > 1 (a local convolution as the skip) is not built")
+        if stabilizer not in (None, "tanh"):
+            raise ValueError(f"unknown stabilizer {stabilizer!r}")
+        for name, kind in (("fno_skip", fno_skip), ("channel_mlp_skip", channel_mlp_skip)):
+            if kind is not None and kind.lower() not in ("linear", "soft-gating", "identity"):
+                raise ValueError(f"Got {name}={kind}, expected one of 'soft-gating', 'linear', 'identity' or None")
+        self.resolution_scaling_factor = _validate_scaling_factor(resolution_scaling_factor, self.n_dim, n_layers)
+        self.max_n_modes = max_n_modes
+        self.fno_block_precision = fno_block_precision
+        self.in_channels, self.out_channels, self.n_layers = in_channels, out_channels, n_layers
+        self.stabilizer, self.rank, self.factorization = stabilizer, rank, factorization
+        self.fixed_rank_modes, self.decomposition_kwargs = fixed_rank_modes, decomposition_kwargs
+        self.fno_skip = fno_skip.lower() if fno_skip is not None else None
+        self.conv_bias_kernel = conv_bias_kernel
+        self.channel_mlp_skip = channel_mlp_skip.lower() if channel_mlp_skip is not None else None
+        self.complex_data = complex_data
+        self.use_channel_mlp = use_channel_mlp
+        self.channel_mlp_expansion, self.channel_mlp_dropout = channel_mlp_expansion, channel_mlp_dropout
+        self.implementation, self.separable, self.preactivation = implementation, separable, preactivation
+        self.ada_in_features, self.enforce_hermitian_symmetry = ada_in_features, enforce_hermitian_symmetry
+        self.non_linearity = non_linearity
+        self.norm = None
+        self.n_norms = 2
+
+        self.convs = nn.ModuleList([
+            conv_module(
+                self.in_channels, self.out_channels, self.n_modes,
+                resolution_scaling_factor=(self.resolution_scaling_factor[i] if resolution_scaling_factor is not None else None),
+                max_n_modes=max_n_modes, rank=rank, fixed_rank_modes=fixed_rank_modes, implementation=implementation,
+                separable=separable, factorization=factorization, fno_block_precision=fno_block_precision,
+                decomposition_kwargs=decomposition_kwargs, complex_data=complex_data,
+                **({"enforce_hermitian_symmetry": enforce_hermitian_symmetry} if issubclass(conv_module, SpectralConv) else {}),
+            )
+            for i in range(n_layers)
+        ])
+        if self.fno_skip is not None:
+            self.fno_skips = nn.ModuleList([skip_connection(self.in_channels, self.out_channels, skip_type=self.fno_skip, n_dim=self.n_dim)
+                                            for _ in range(n_layers)])
+        else:
+            self.fno_skips = None
+        if self.use_channel_mlp:
+            self.channel_mlp = nn.ModuleList([
+                ChannelMLP(in_channels=self.out_channels, hidden_channels=round(self.out_channels * channel_mlp_expansion),
+                           dropout=channel_mlp_dropout, n_dim=self.n_dim)
+                for _ in range(n_layers)])
+            if self.channel_mlp_skip is not None:
+                self.channel_mlp_skips = nn.ModuleList([
+                    skip_connection(self.in_channels, self.out_channels, skip_type=self.channel_mlp_skip, n_dim=self.n_dim)
+                    for _ in range(n_layers)])
+            else:
+                self.channel_mlp_skips = None
+
+    # -- helpers ------------------------------------------------------------------------------------
+    @staticmethod
+    def _skip_terms(kind, module, x):
+        """The skip as (x_mix, weight, gate, gated) operands of the fused op, without materialising it."""
+        if kind == "linear":
+            if module.conv.bias is not None:
+                return None          # (never built by skip_connection's default bias=False: materialise)
+            return x, module.conv.weight, None, None
+        if kind == "soft-gating":
+            if module.bias is not None:
+                return None
+            return None, None, module.weight, x
+        return None, None, None, x   # identity
+
+    def _resamples(self, conv, x, output_shape):
+        grid = list(x.shape[2:])
+        if hasattr(conv, "_output_grid"):
+            return [int(s) for s in conv._output_grid(grid, output_shape)] != grid
+        return output_shape is not None and list(output_shape) != grid
+
+    def _fourier_step(self, x, index, output_shape, act):
+        """f1: act( conv(stabilizer(x)) + fno_skip(x) )."""
+        conv = self.convs[index]
+        x_conv = _Tanh.apply(x) if self.stabilizer == "tanh" else x
+        x_fno = conv(x_conv, output_shape=output_shape)
+        if self.fno_skips is None:
+            return x_fno if act == ACT_IDENTITY else channel_mix(add=x_fno, act=act)
+        terms = None if self._resamples(conv, x, output_shape) else self._skip_terms(self.fno_skip, self.fno_skips[index], x)
+        if terms is None:
+            # the skip lives on the input grid and the conv changed the resolution (or the skip carries a bias): materialise it,
+            # resample it as the reference does (`convs[i].transform`, fno_block.py:380), then ONE launch for add + activation
+            x_skip = conv.transform(self.fno_skips[index](x), output_shape=output_shape)
+            return channel_mix(add=x_fno, gated=x_skip, act=act)
+        xm, w, gate, gated = terms
+        return channel_mix(xm, w, add=x_fno, gate=gate, gated=gated, act=act)
+
+    def _mlp_step(self, x1, x, index, output_shape, act):
+        """f2: act( channel_mlp(x1) + channel_mlp_skip(x) )."""
+        mlp = self.channel_mlp[index]
+        if self.channel_mlp_skips is None:
+            return mlp._forward_fused(x1, final_act=act)
+        conv = self.convs[index]
+        kind, module = self.channel_mlp_skip, self.channel_mlp_skips[index]
+        if kind == "linear" or self._resamples(conv, x, output_shape) or (kind == "soft-gating" and module.bias is not None):
+            x_skip = conv.transform(module(x), output_shape=output_shape)
+            return mlp._forward_fused(x1, gated=x_skip, final_act=act)
+        gate = module.weight if kind == "soft-gating" else None
+        return mlp._forward_fused(x1, gate=gate, gated=x, final_act=act)
+
+    # -- forward ------------------------------------------------------------------------------------
+    def forward(self, x, index=0, output_shape=None):
+        if self.preactivation:
+            return self.forward_with_preactivation(x, index, output_shape)
+        return self.forward_with_postactivation(x, index, output_shape)
+
+    def forward_with_postactivation(self, x, index=0, output_shape=None):
+        """fno_block.py:377-414."""
+        _require_device_tensor(x, "FNOBlocks input")
+        x = x.contiguous()
+        act = ACT_GELU if index < (self.n_layers - 1) else ACT_IDENTITY
+        x1 = self._fourier_step(x, index, output_shape, act)
+        if self.use_channel_mlp:
+            return self._mlp_step(x1, x, index, output_shape, act)
+        # no channel MLP: the reference applies the non-linearity a second time (fno_block.py:411-412)
+        return x1 if act == ACT_IDENTITY else channel_mix(add=x1, act=act)
+
+    def forward_with_preactivation(self, x, index=0, output_shape=None):
+        """fno_block.py:416-453: activation first, then conv + skip (+ activation unless last), then the channel MLP + skip."""
+        _require_device_tensor(x, "FNOBlocks input")
+        x = channel_mix(add=x.contiguous(), act=ACT_GELU)
+        act = ACT_GELU if index < (self.n_layers - 1) else ACT_IDENTITY
+        x1 = self._fourier_step(x, index, output_shape, act)
+        if self.use_channel_mlp:
+            return self._mlp_step(x1, x, index, output_shape, ACT_IDENTITY)
+        return x1
+
+    @property
+    def n_modes(self):
+        return self._n_modes
+
+    @n_modes.setter
+    def n_modes(self, n_modes):
+        for i in range(self.n_layers):
+            self.convs[i].n_modes = n_modes
+        self._n_modes = n_modes

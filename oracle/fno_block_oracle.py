@@ -1,0 +1,113 @@
+"""CPU oracle for the Fourier layer around the spectral convolution.  TEST INFRASTRUCTURE --
+NOT PRODUCT CODE: only `tests/`, `bench.py`'s baseline legs and `oracle/make_golden_block.py` import it.
+
+What it restates (reference = neuraloperator @ 93d3f06, paths relative to /root/reference):
+
+  * `fno_block_forward`   <- neuralop/layers/fno_block.py:377-414 (`forward_with_postactivation`) and :416-453
+                             (`forward_with_preactivation`), for norm=None, real data, non_linearity=F.gelu
+  * `_skip`               <- neuralop/layers/skip_connections.py:85-93 (SoftGating.forward), :118-130 (Flattened1dConv.forward),
+                             nn.Identity
+  * `_channel_mlp`        <- neuralop/layers/channel_mlp.py:92-116 (ChannelMLP.forward, dropout = 0)
+  * the conv              <- `oracle.spectral_conv_oracle.spectral_conv_forward` (pinned on its own)
+  * the skip resampling   <- `SpectralConv.transform` (spectral_convolution.py:383-398) -> `resample_restated`
+
+The backward is whatever torch.autograd records for these CPU ops -- as in the reference, which has no hand-written backward.
+Pinning: `tests/test_block_oracle.py` compares this restatement with golden vectors minted by `oracle/make_golden_block.py` from the
+UNMODIFIED `FNOBlocks` (imported through `oracle/load_reference.py`) and, where /root/reference exists, with the live class.
+Parameters are passed as a dict keyed by the reference's state-dict names (`fno_skips.0.conv.weight`, `channel_mlp.0.fcs.1.bias`, ...).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from . import spectral_conv_oracle as O
+
+
+def _skip(kind: Optional[str], params: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor) -> torch.Tensor:
+    if kind == "linear":
+        w = params[prefix + ".conv.weight"]                                   # (Co, Ci, 1), no bias (skip_connection default)
+        size = list(x.shape)
+        return F.conv1d(x.reshape(size[0], size[1], -1), w).view(size[0], w.shape[0], *size[2:])
+    if kind == "soft-gating":
+        return params[prefix + ".weight"] * x
+    if kind == "identity":
+        return x
+    raise ValueError(kind)
+
+
+def _channel_mlp(params: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, n_layers: int = 2) -> torch.Tensor:
+    size = list(x.shape)
+    h = x.reshape(size[0], size[1], -1)
+    for i in range(n_layers):
+        h = F.conv1d(h, params[f"{prefix}.fcs.{i}.weight"], params[f"{prefix}.fcs.{i}.bias"])
+        if i < n_layers - 1:
+            h = F.gelu(h)
+    return h.reshape(size[0], h.shape[1], *size[2:])
+
+
+def _transform(x, in_grid, out_grid):
+    return x if list(in_grid) == list(out_grid) else O.resample_restated(x, out_grid)
+
+
+def conv_weight_from_params(params: Dict[str, torch.Tensor], index: int, kind: str = "dense") -> O.Weight:
+    """The oracle's Weight for layer `index` from reference-named parameters (`convs.<i>.weight.tensor` / `.core` / `.factors.<j>`)."""
+    pre = f"convs.{index}.weight."
+    fs = sorted((k for k in params if k.startswith(pre + "factors.")), key=lambda k: int(k.rsplit(".", 1)[1].replace("factor_", "")))
+    factors = [params[k] for k in fs]
+    if kind == "dense":
+        return O.Weight("dense", tensor=params[pre + "tensor"])
+    if kind == "tucker":
+        return O.Weight("tucker", core=params[pre + "core"], factors=factors)
+    if kind == "cp":
+        return O.Weight("cp", weights=params[pre + "weights"], factors=factors)
+    if kind == "tt":
+        return O.Weight("tt", factors=factors)
+    raise ValueError(kind)
+
+
+def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: int, *, n_modes: Sequence[int], n_layers: int,
+                      weight_kind: str = "dense", fno_skip: Optional[str] = "linear", channel_mlp_skip: Optional[str] = "soft-gating",
+                      use_channel_mlp: bool = True, stabilizer: Optional[str] = None, preactivation: bool = False,
+                      output_shape: Optional[Sequence[int]] = None, resolution_scaling_factor=None,
+                      max_n_modes: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """One Fourier layer: `FNOBlocks.forward(x, index, output_shape)` for norm=None, real data, GELU."""
+    grid = list(x.shape[2:])
+    rsf = resolution_scaling_factor
+    if rsf is not None and not isinstance(rsf, (list, tuple)):
+        rsf = [float(rsf)] * len(grid)
+    out_grid = O.resolve_output_grid(grid, rsf, output_shape)
+    nonlin = index < n_layers - 1
+    if preactivation:
+        x = F.gelu(x)                                                           # :419
+    x_skip_fno = None
+    if fno_skip is not None:                                                    # :378-380 / :424-426
+        x_skip_fno = _transform(_skip(fno_skip, params, f"fno_skips.{index}", x), grid, out_grid)
+    x_skip_mlp = None
+    if use_channel_mlp and channel_mlp_skip is not None:                        # :382-384 / :428-430
+        x_skip_mlp = _transform(_skip(channel_mlp_skip, params, f"channel_mlp_skips.{index}", x), grid, out_grid)
+    xc = torch.tanh(x) if stabilizer == "tanh" else x                           # :386-390
+    w = conv_weight_from_params(params, index, weight_kind)
+    x_fno = O.spectral_conv_forward(xc, w, params.get(f"convs.{index}.bias"), n_modes, max_n_modes=max_n_modes,
+                                    output_shape=output_shape, resolution_scaling_factor=rsf)      # :392
+    y = x_fno + x_skip_fno if x_skip_fno is not None else x_fno                 # :397
+    if nonlin:
+        y = F.gelu(y)                                                           # :399-400
+    if use_channel_mlp:                                                         # :402-406
+        y = _channel_mlp(params, f"channel_mlp.{index}", y)
+        if x_skip_mlp is not None:
+            y = y + x_skip_mlp
+    if nonlin and not preactivation:                                            # :411-412 (the pre-activation form ends without it)
+        y = F.gelu(y)
+    return y
+
+
+def fno_block_fwd_bwd(x, params, index, grad_y, **kw):
+    """Forward + autograd backward. Returns y, dx, {name: grad} for every parameter the layer touched."""
+    x = x.detach().clone().requires_grad_(True)
+    ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    y = fno_block_forward(x, ps, index, **kw)
+    y.backward(grad_y)
+    return y.detach(), x.grad, {k: v.grad for k, v in ps.items() if v.grad is not None}

@@ -101,3 +101,42 @@ def load_complex_golden(name):
         else:
             out[k] = t
     return meta, out
+
+
+def block_golden_index():
+    with open(os.path.join(GOLDEN_DIR, "block_index.json")) as f:
+        return json.load(f)["cases"]
+
+
+def load_block_golden(name):
+    """Fourier-layer cases (oracle/make_golden_block.py): returns meta, {x, gy, y, dx}, params {ref name: tensor}, grads {ref name: tensor}."""
+    meta = block_golden_index()[name]
+    data = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    io, params, grads = {}, {}, {}
+    for k in data.files:
+        t = torch.from_numpy(data[k])
+        key = k
+        if k.endswith("__c"):
+            t, key = torch.view_as_complex(t.contiguous()), k[:-3]
+        if key.startswith("p__"):
+            params[key[3:].replace("__", ".")] = t
+        elif key.startswith("g__"):
+            grads[key[3:].replace("__", ".")] = t
+        else:
+            io[key] = t
+    return meta, io, params, grads
+
+
+def block_oracle_kwargs(meta):
+    """Keyword arguments of oracle.fno_block_oracle.fno_block_forward for a golden case."""
+    ctor = meta["ctor"]
+    kw = dict(n_modes=meta["n_modes"], n_layers=meta["n_layers"], weight_kind=meta["weight_kind"],
+              fno_skip=ctor.get("fno_skip", "linear"), channel_mlp_skip=ctor.get("channel_mlp_skip", "soft-gating"),
+              use_channel_mlp=ctor.get("use_channel_mlp", True), stabilizer=ctor.get("stabilizer"),
+              preactivation=ctor.get("preactivation", False), resolution_scaling_factor=ctor.get("resolution_scaling_factor"))
+    if "max_n_modes" in ctor:
+        from oracle.spectral_conv_oracle import stored_n_modes
+        kw["max_n_modes"] = stored_n_modes(ctor["max_n_modes"])
+    if "output_shape" in meta["forward"]:
+        kw["output_shape"] = meta["forward"]["output_shape"]
+    return kw

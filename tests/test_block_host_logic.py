@@ -1,0 +1,192 @@
+"""`neuraloperator_b200.FNOBlocks` end to end WITHOUT a GPU, against golden vectors minted from the unmodified reference FNOBlocks.
+
+Two things are replaced: (1) the four layer-epilogue kernels run through their host checks (`sc_hostcheck_*`: the kernels' own tile
+functions executed thread by thread on CPU buffers), (2) the spectral convolution inside the block is the CPU oracle (the CUDA conv
+has its own GPU tiers).  Everything else is the product code: which skip becomes which operand of the fused op, the activation per
+layer index, pre / post-activation order, the resampling of the skips, the autograd wiring of every gradient, state-dict names."""
+import contextlib
+import importlib
+
+import pytest
+import torch
+
+import neuraloperator_b200 as nb
+from neuraloperator_b200 import _lib, fno_block as fb
+from conftest import block_golden_index, load_block_golden
+from oracle import fno_block_oracle as BO
+from oracle import spectral_conv_oracle as O
+from oracle.load_reference import load_reference_spectral_conv, reference_available
+
+CASES = sorted(block_golden_index().keys())
+
+
+class _HostLib:
+    """The layer entry points of the C ABI, served by the library's own host checks (same arguments minus the stream)."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self.calls = []
+
+    def sc_channel_mix(self, *a):
+        self.calls.append("sc_channel_mix")
+        return self._lib.sc_hostcheck_channel_mix(*a[:-1])
+
+    def sc_channel_mix_act_backward(self, *a):
+        self.calls.append("sc_channel_mix_act_backward")
+        return self._lib.sc_hostcheck_channel_mix_act_backward(*a[:-1])
+
+    def sc_channel_mix_weight_grad(self, *a):
+        self.calls.append("sc_channel_mix_weight_grad")
+        return self._lib.sc_hostcheck_channel_mix_weight_grad(*a[:-1])
+
+    def sc_pointwise(self, *a):
+        self.calls.append("sc_pointwise")
+        return self._lib.sc_hostcheck_pointwise(*a[:-1])
+
+    def sc_last_error(self):
+        return self._lib.sc_last_error()
+
+
+def _oracle_conv_forward(self, x, output_shape=None):
+    """SpectralConv.forward served by the CPU oracle (differentiable through torch.fft), from the module's own parameters."""
+    kind = getattr(self.weight, "kind", "dense")
+    if kind == "dense":
+        w = O.Weight("dense", tensor=self.weight.tensor)
+    elif kind == "tucker":
+        w = O.Weight("tucker", core=self.weight.core, factors=list(self.weight.factors))
+    elif kind == "cp":
+        w = O.Weight("cp", weights=self.weight.weights, factors=list(self.weight.factors))
+    else:
+        w = O.Weight("tt", factors=list(self.weight.factors))
+    user_modes = list(self.n_modes)
+    user_modes[-1] = (user_modes[-1] - 1) * 2            # the oracle takes USER modes and halves the last one itself
+    return O.spectral_conv_forward(x, w, self.bias, user_modes, max_n_modes=list(self.max_n_modes), output_shape=output_shape,
+                                   resolution_scaling_factor=self.resolution_scaling_factor, fft_norm=self.fft_norm)
+
+
+def _oracle_transform(self, x, output_shape=None):
+    in_shape = list(x.shape[2:])
+    out_shape = [int(s) for s in self._output_grid(in_shape, output_shape)]
+    return x if in_shape == out_shape else O.resample_restated(x, out_shape)
+
+
+@pytest.fixture
+def host(monkeypatch):
+    real = _lib.load()
+    h = _HostLib(real)
+    monkeypatch.setattr(fb._lib, "load", lambda: h)
+    monkeypatch.setattr(fb._lib, "check", lambda rc, what: (_ for _ in ()).throw(RuntimeError(f"{what}: {real.sc_last_error()}")) if rc else None)
+    monkeypatch.setattr(fb, "_require_device_tensor", lambda t, what: None)
+    monkeypatch.setattr(fb, "_stream_ptr", lambda dev: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
+    monkeypatch.setattr(nb.SpectralConv, "forward", _oracle_conv_forward)
+    monkeypatch.setattr(nb.SpectralConv, "transform", _oracle_transform)
+    return h
+
+
+def rel_err(a, ref):
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    return (a.detach() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-20)
+
+
+def _our_name(pname):
+    return pname.replace("weight.factors.", "weight.factors.factor_")
+
+
+def _build(meta):
+    ctor = dict(meta["ctor"])
+    if "max_n_modes" in ctor:
+        ctor["max_n_modes"] = tuple(ctor["max_n_modes"])
+    return nb.FNOBlocks(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), n_layers=meta["n_layers"], **ctor)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_block_module_matches_reference_golden(host, name):
+    meta, io, params, grads = load_block_golden(name)
+    blk = _build(meta)
+    ours = dict(blk.named_parameters())
+    assert sorted(_our_name(p) for p in meta["params"]) == sorted(ours.keys())          # same parameter set and names as the reference block
+    with torch.no_grad():
+        for pname, val in params.items():
+            assert ours[_our_name(pname)].shape == val.shape, pname
+            ours[_our_name(pname)].copy_(val)
+    x = io["x"].clone().requires_grad_(True)
+    kw = {k: tuple(v) for k, v in meta["forward"].items()}
+    y = blk(x, meta["index"], **kw)
+    assert y.dtype == torch.float32 and list(y.shape[2:]) == meta["out_grid"]
+    y.backward(io["gy"])
+    assert rel_err(y, io["y"]) < 2e-5, "y"
+    assert rel_err(x.grad, io["dx"]) < 2e-5, "dx"
+    for pname in meta["params"]:
+        p = ours[_our_name(pname)]
+        if pname in meta["touched"]:
+            assert p.grad is not None, pname
+            assert rel_err(p.grad, grads[pname]) < 3e-5, pname
+        else:
+            assert p.grad is None, pname
+    assert "sc_channel_mix" in host.calls                                                    # the fused kernels' code did the work
+
+
+def test_launch_counts_of_the_default_layer(host):
+    """Default layer (linear skip, ChannelMLP + soft gating), no resolution change: f1 is ONE mixing launch, f2 two; backward is
+    3 activation-backward + 3 input-gradient + 3 weight-gradient launches."""
+    meta, io, params, _ = load_block_golden("block_d2_default_mid")
+    blk = _build(meta)
+    x = io["x"].clone().requires_grad_(True)
+    y = blk(x, 0)
+    assert host.calls == ["sc_channel_mix"] * 3
+    host.calls.clear()
+    y.backward(io["gy"])
+    assert sorted(host.calls) == sorted(["sc_channel_mix_act_backward"] * 3 + ["sc_channel_mix"] * 3 + ["sc_channel_mix_weight_grad"] * 3)
+    host.calls.clear()
+    with torch.no_grad():
+        blk(io["x"], 1)                                 # last layer: identity activation, still three launches
+    assert host.calls == ["sc_channel_mix"] * 3
+
+
+def test_state_dict_round_trip_with_the_reference(host):
+    """A reference FNOBlocks state dict loads into ours (and back) by name: same keys, same shapes."""
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference_spectral_conv()
+    ref_fb = importlib.import_module("neuralop.layers.fno_block")
+    torch.manual_seed(4)
+    ref = ref_fb.FNOBlocks(6, 6, (8, 8), n_layers=3, implementation="reconstructed")
+    ours = nb.FNOBlocks(6, 6, (8, 8), n_layers=3, implementation="reconstructed")
+    sd = ref.state_dict()
+    assert sorted(sd.keys()) == sorted(ours.state_dict().keys())
+    ours.load_state_dict(sd)
+    ref.load_state_dict(ours.state_dict())
+    x = torch.randn(2, 6, 16, 16)
+    for i in range(3):
+        assert rel_err(ours(x, i), ref(x, i).detach()) < 2e-5
+    # the whole stack, layer after layer, as FNO.forward applies it (fno.py:376-379)
+    a, b = x, x
+    for i in range(3):
+        a, b = ours(a, i), ref(b, i)
+    assert rel_err(a, b.detach()) < 5e-5
+
+
+def test_unsupported_configurations_raise():
+    for kw in (dict(norm="group_norm"), dict(complex_data=True), dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
+               dict(non_linearity=torch.nn.functional.relu)):
+        with pytest.raises(NotImplementedError):
+            nb.FNOBlocks(4, 4, (4, 4), **kw)
+    with pytest.raises(ValueError):
+        nb.FNOBlocks(4, 4, (4, 4), fno_skip="bogus")
+    with pytest.raises(ValueError):
+        nb.FNOBlocks(4, 6, (4, 4))                       # soft gating needs in == out channels (skip_connections.py:74-79)
+
+
+def test_no_cpu_path():
+    blk = nb.FNOBlocks(4, 4, (4, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        blk(torch.randn(1, 4, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        nb.ChannelMLP(4)(torch.randn(1, 4, 8))
+
+
+def test_n_modes_setter_reaches_every_conv():
+    blk = nb.FNOBlocks(4, 4, (8, 8), n_layers=2)
+    blk.n_modes = (4, 6)
+    assert blk.n_modes == (4, 6) and all(c.n_modes == [4, 4] for c in blk.convs)

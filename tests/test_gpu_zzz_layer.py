@@ -1,0 +1,131 @@
+"""The Fourier-layer epilogue (tanh stabilizer) on the GPU: the fused kernels of csrc/sc_layer.cu against
+float64 CPU restatements of the reference ops, and `neuraloperator_b200.FNOBlocks` (CUDA spectral conv + fused epilogue) against
+golden vectors minted from the unmodified reference FNOBlocks (oracle/make_golden_block.py): y, dx, every parameter gradient.
+(Named zzz so that it runs after every tier that was validated on hardware: this file was written after the round's GPU minutes were
+spent; the kernels' tile code is checked on CPU by tests/test_layer_cpu.py, the module logic by tests/test_block_host_logic.py.)"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import neuraloperator_b200 as nb
+from neuraloperator_b200 import _lib
+from conftest import block_golden_index, load_block_golden
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]
+REL_TOL = 1e-4
+CASES = sorted(block_golden_index().keys())
+
+
+def rel_err(a, ref):
+    a, ref = a.detach().cpu().double(), ref.detach().cpu().double()
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    return (a - ref).abs().max().item() / max(ref.abs().max().item(), 1e-20)
+
+
+@pytest.mark.parametrize("B,Ci,Co,grid", [(2, 3, 5, (7,)), (2, 17, 65, (129,)), (3, 70, 130, (3, 11)), (4, 64, 64, (128, 128)),
+                                           (2, 32, 16, (16, 16, 16)), (1, 64, 32, (100, 100))])
+@pytest.mark.parametrize("opts", ["plain", "all"])
+def test_channel_mix_forward_backward_vs_float64(cuda_device, B, Ci, Co, grid, opts):
+    g = torch.Generator().manual_seed(Ci * 31 + Co)
+    dd = dict(dtype=torch.float64)
+    x = torch.randn(B, Ci, *grid, generator=g, **dd).requires_grad_(True)
+    w = (torch.randn(Co, Ci, 1, generator=g, **dd) / Ci ** 0.5).requires_grad_(True)
+    full = opts == "all"
+    bias = torch.randn(Co, generator=g, **dd).requires_grad_(True) if full else None
+    add = torch.randn(B, Co, *grid, generator=g, **dd).requires_grad_(True) if full else None
+    gate = torch.randn(1, Co, *[1] * len(grid), generator=g, **dd).requires_grad_(True) if full else None
+    gated = torch.randn(B, Co, *grid, generator=g, **dd).requires_grad_(True) if full else None
+    gout = torch.randn(B, Co, *grid, generator=g, **dd)
+    pre = F.conv1d(x.flatten(2), w, bias).view(B, Co, *grid)
+    if full:
+        pre = pre + add + gate * gated
+    ref = F.gelu(pre) if full else pre
+    ref.backward(gout)
+    leaves = [t for t in (x, w, bias, add, gate, gated) if t is not None]
+    dev = [t.detach().float().to(cuda_device).requires_grad_(True) if t is not None else None for t in (x, w, bias, add, gate, gated)]
+    before = _lib.launch_count()
+    out = nb.channel_mix(*dev, act=_lib.ACT_GELU if full else _lib.ACT_IDENTITY)
+    out.backward(gout.float().to(cuda_device))
+    torch.cuda.synchronize()
+    assert _lib.launch_count() > before
+    assert rel_err(out, ref) < REL_TOL, "out"
+    for name, t_dev, t_ref in zip(("x", "w", "bias", "add", "gate", "gated"), dev, (x, w, bias, add, gate, gated)):
+        if t_ref is not None:
+            assert t_dev.grad is not None, name
+            assert rel_err(t_dev.grad, t_ref.grad) < REL_TOL, name
+    assert len(leaves) >= 2
+
+
+def test_channel_mix_no_grad_and_empty(cuda_device):
+    x = torch.randn(2, 4, 9, device=cuda_device)
+    w = torch.randn(6, 4, 1, device=cuda_device)
+    with torch.no_grad():
+        y = nb.channel_mix(x, w, act=_lib.ACT_GELU)
+    assert rel_err(y, F.gelu(F.conv1d(x.cpu().double(), w.cpu().double()))) < REL_TOL
+    e = nb.channel_mix(torch.empty(0, 4, 9, device=cuda_device), w)
+    assert tuple(e.shape) == (0, 6, 9)
+
+
+def test_tanh_stabilizer_kernel(cuda_device):
+    x = (3 * torch.randn(3, 5, 33, device=cuda_device)).requires_grad_(True)
+    from neuraloperator_b200.fno_block import _Tanh
+    y = _Tanh.apply(x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr = x.detach().cpu().double().requires_grad_(True)
+    yr = torch.tanh(xr)
+    yr.backward(g.cpu().double())
+    assert rel_err(y, yr) < 1e-6 and rel_err(x.grad, xr.grad) < 1e-5
+
+
+def _our_name(pname):
+    return pname.replace("weight.factors.", "weight.factors.factor_")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_block_module_matches_reference_golden(cuda_device, name):
+    meta, io, params, grads = load_block_golden(name)
+    ctor = dict(meta["ctor"])
+    if "max_n_modes" in ctor:
+        ctor["max_n_modes"] = tuple(ctor["max_n_modes"])
+    blk = nb.FNOBlocks(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), n_layers=meta["n_layers"], **ctor).to(cuda_device)
+    ours = dict(blk.named_parameters())
+    with torch.no_grad():
+        for pname, val in params.items():
+            assert ours[_our_name(pname)].shape == val.shape, pname
+            ours[_our_name(pname)].copy_(val.to(cuda_device))
+    x = io["x"].to(cuda_device).requires_grad_(True)
+    kw = {k: tuple(v) for k, v in meta["forward"].items()}
+    y = blk(x, meta["index"], **kw)
+    assert y.dtype == torch.float32 and list(y.shape[2:]) == meta["out_grid"]
+    y.backward(io["gy"].to(cuda_device))
+    torch.cuda.synchronize()
+    assert rel_err(y, io["y"]) < REL_TOL, "y"
+    assert rel_err(x.grad, io["dx"]) < REL_TOL, "dx"
+    for pname in meta["touched"]:
+        p = ours[_our_name(pname)]
+        assert p.grad is not None, pname
+        assert rel_err(p.grad, grads[pname]) < REL_TOL, pname
+
+
+def test_headline_shape_layer_against_oracle(cuda_device):
+    """One full Fourier layer at the tile shapes of the headline config (channels 64, 128 x 128, modes 32 x 32; batch 4): the fused
+    tcgen05 conv kernels + the fused epilogue, against the CPU oracle of the reference block."""
+    from oracle import fno_block_oracle as BO
+    torch.manual_seed(12)
+    blk = nb.FNOBlocks(64, 64, (32, 32), n_layers=2, implementation="reconstructed").to(cuda_device)
+    with torch.no_grad():
+        for pname, p in blk.named_parameters():
+            if "skips" in pname:
+                p.add_(0.2 * torch.randn_like(p))
+    x = torch.randn(4, 64, 128, 128, device=cuda_device, requires_grad=True)
+    y = blk(x, 0)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    torch.cuda.synchronize()
+    params = {k: v.detach().cpu() for k, v in blk.named_parameters()}
+    y_ref, dx_ref, g_ref = BO.fno_block_fwd_bwd(x.detach().cpu(), params, 0, gy.cpu(), n_modes=(32, 32), n_layers=2)
+    assert rel_err(y, y_ref) < REL_TOL and rel_err(x.grad, dx_ref) < REL_TOL
+    for pname, p in blk.named_parameters():
+        if pname in g_ref:
+            assert rel_err(p.grad, g_ref[pname]) < REL_TOL, pname
