@@ -187,6 +187,136 @@ def measure_config(nb, dev, peak, batch, ch, grid, modes, kind, with_torch=True)
     return out
 
 
+def torch_layer_forward(x, prm, n_modes_stored, last=False):
+    """One Fourier layer of the reference (fno_block.py:377-414: linear skip, ChannelMLP + soft gating, GELU) as plain PyTorch ops on
+    the GPU -- the denominator for the fused layer epilogue.  prm: w, b (conv), w_skip, w1, b1, w2, b2, gate."""
+    import torch
+    import torch.nn.functional as F
+    size = list(x.shape)
+    flat = lambda t: t.reshape(size[0], t.shape[1], -1)                                   # noqa: E731
+    x_skip = F.conv1d(flat(x), prm["w_skip"]).view(size)
+    x_skip_mlp = prm["gate"] * x
+    y = torch_cufft_forward(x, prm["w"], prm["b"], n_modes_stored) + x_skip
+    if not last:
+        y = F.gelu(y)
+    h = F.gelu(F.conv1d(flat(y), prm["w1"], prm["b1"]))
+    y = F.conv1d(h, prm["w2"], prm["b2"]).view(size) + x_skip_mlp
+    return y if last else F.gelu(y)
+
+
+def run_layer(args):
+    """`--layer-only` (own process, called from the main run): the Fourier layer around the conv at the
+    headline shape -- nb.FNOBlocks (CUDA conv + fused epilogue kernels) next to the same layer on PyTorch eager + cuFFT/cuBLAS/cuDNN,
+    plus the epilogue alone and a parity figure of ours against PyTorch (TF32 off for that comparison)."""
+    import torch
+    import torch.nn.functional as F
+    import neuraloperator_b200 as nb
+    from neuraloperator_b200 import _lib
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    blk = nb.FNOBlocks(C, C, MODES, n_layers=2, implementation="reconstructed").to(dev)
+    with torch.no_grad():
+        blk.channel_mlp_skips[0].weight.add_(0.2 * torch.randn_like(blk.channel_mlp_skips[0].weight))
+    conv = blk.convs[0]
+    x = torch.randn(B, C, H, W, device=dev)
+    g = torch.randn(B, C, H, W, device=dev)
+    prm = {"w": conv.weight.tensor, "b": conv.bias, "w_skip": blk.fno_skips[0].conv.weight, "w1": blk.channel_mlp[0].fcs[0].weight,
+           "b1": blk.channel_mlp[0].fcs[0].bias, "w2": blk.channel_mlp[0].fcs[1].weight, "b2": blk.channel_mlp[0].fcs[1].bias,
+           "gate": blk.channel_mlp_skips[0].weight}
+    prm_t = {k: v.detach().clone().requires_grad_(True) for k, v in prm.items()}
+
+    def zero(ps):
+        for p_ in ps:
+            p_.grad = None
+
+    def ours_layer():
+        zero(blk.parameters())
+        xx = x.detach().requires_grad_(True)
+        blk(xx, 0).backward(g)
+        return xx
+
+    def torch_layer():
+        zero(prm_t.values())
+        xx = x.detach().requires_grad_(True)
+        torch_layer_forward(xx, prm_t, conv.n_modes).backward(g)
+        return xx
+
+    c0 = _lib.launch_count()
+    ours_layer()
+    torch.cuda.synchronize(dev)
+    launches = _lib.launch_count() - c0
+    # parity of the whole layer against PyTorch on the same GPU (fp32 everywhere: TF32 off for this comparison only)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xo, xt = ours_layer(), torch_layer()
+    with torch.no_grad():
+        yo, yt = blk(x, 0), torch_layer_forward(x, prm_t, conv.n_modes)
+    rel = lambda a, b_: float((a - b_).abs().max() / b_.abs().max())                         # noqa: E731
+    parity = {"y": rel(yo, yt), "dx": rel(xo.grad, xt.grad), "dw_skip": rel(prm["w_skip"].grad, prm_t["w_skip"].grad),
+              "dw1": rel(prm["w1"].grad, prm_t["w1"].grad), "dw2": rel(prm["w2"].grad, prm_t["w2"].grad),
+              "dgate": rel(prm["gate"].grad, prm_t["gate"].grad), "dW_conv": rel(prm["w"].grad, prm_t["w"].grad)}
+    del xo, xt, yo, yt
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    t_ours = time_cuda(ours_layer, 3, 20)
+    t_torch = time_cuda(torch_layer, 3, 20)
+
+    # the epilogue alone, forward + backward, the conv output given
+    x_fno = torch.randn(B, C, H, W, device=dev)
+
+    def ours_epilogue():
+        zero(blk.parameters())
+        xx, xf = x.detach().requires_grad_(True), x_fno.detach().requires_grad_(True)
+        x1 = nb.channel_mix(xx, prm["w_skip"], add=xf, act=_lib.ACT_GELU)
+        blk.channel_mlp[0]._forward_fused(x1, gate=prm["gate"], gated=xx, final_act=_lib.ACT_GELU).backward(g)
+
+    def torch_epilogue():
+        zero(prm_t.values())
+        xx, xf = x.detach().requires_grad_(True), x_fno.detach().requires_grad_(True)
+        size = list(xx.shape)
+        flat = lambda t: t.reshape(size[0], t.shape[1], -1)                                # noqa: E731
+        x1 = F.gelu(xf + F.conv1d(flat(xx), prm_t["w_skip"]).view(size))
+        h = F.gelu(F.conv1d(flat(x1), prm_t["w1"], prm_t["b1"]))
+        F.gelu(F.conv1d(h, prm_t["w2"], prm_t["b2"]).view(size) + prm_t["gate"] * xx).backward(g)
+
+    t_ours_ep = time_cuda(ours_epilogue, 3, 20)
+    t_torch_ep = time_cuda(torch_epilogue, 3, 20)
+    with torch.no_grad():
+        def ours_ep_fwd():
+            x1 = nb.channel_mix(x, prm["w_skip"], add=x_fno, act=_lib.ACT_GELU)
+            blk.channel_mlp[0]._forward_fused(x1, gate=prm["gate"], gated=x, final_act=_lib.ACT_GELU)
+        t_ours_ep_fwd = time_cuda(ours_ep_fwd, 3, 20)
+    n_bytes = 4 * B * C * H * W
+    fwd_bytes = 7 * n_bytes            # f1: x, conv output -> x1 (3); f2: x1 -> h (1.5), h, x -> out (2.5), in units of one (B,C,H,W) pass
+    peak, _ = measured_peaks()
+    out = {"what": "one Fourier layer (fno_block.py:377-414: SpectralConv + linear skip + GELU + ChannelMLP(0.5) + soft-gating skip + GELU) "
+                   "fwd+bwd, eager nn.Module, same shape as the headline step; PyTorch = the same ops on eager + cuFFT/cuBLAS/cuDNN",
+           "shape": [B, C, H, W], "ours_ms_per_step": t_ours, "torch_ms_per_step": t_torch, "speedup_vs_torch": t_torch / t_ours,
+           "ours_launches_per_step": launches,
+           "epilogue_only": {"ours_fwd_bwd_ms": t_ours_ep, "torch_fwd_bwd_ms": t_torch_ep, "speedup": t_torch_ep / t_ours_ep,
+                             "ours_fwd_ms": t_ours_ep_fwd, "fwd_algorithmic_bytes": fwd_bytes,
+                             "fwd_gbs": fwd_bytes / t_ours_ep_fwd / 1e6, "fwd_roofline_frac": fwd_bytes / t_ours_ep_fwd / 1e6 / peak,
+                             "kernels": "k_channel_mix (SIMT fp32), k_channel_act_backward, k_channel_weight_grad: first hardware run of "
+                                        "these kernels is this driver run (written after the round's GPU minutes were spent)"},
+           "max_rel_err_vs_torch_fp32": parity}
+    print("LAYER_JSON " + json.dumps(out), flush=True)
+    return 0
+
+
+def layer_block_subprocess(timeout_s=240):
+    """Runs `bench.py --layer-only` in its own process: a fault in the (new) layer kernels cannot touch the headline line."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--layer-only"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           text=True, timeout=timeout_s)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("LAYER_JSON "):
+                return json.loads(ln[len("LAYER_JSON "):])
+        return {"error": f"exit code {r.returncode}: {r.stderr.strip()[-400:]}"}
+    except Exception as exc:   # noqa: BLE001
+        return {"error": repr(exc)[:300]}
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons WHILE the timed region runs.  The timed region is only ~10 ms (50 steps of
     0.2 ms), far below nvidia-smi's sampling period, so NVML is polled directly from a thread (about every millisecond)."""
@@ -541,6 +671,7 @@ def run_ours(args):
 
     torch_gpu = None
     configs = None
+    fourier_layer = None
     if rank == 0 and world == 1 and not args.no_configs:
         # the reference op sequence on PyTorch + cuFFT/cuBLAS on this GPU, same shapes, eager -- the ">= 1.5x" denominator;
         # ours eager (nn.Module) next to it, and the graph-replayed headline step
@@ -573,6 +704,8 @@ def run_ours(args):
             except Exception as exc:   # noqa: BLE001 -- reported in the line, the headline number stands
                 configs[name] = {"error": repr(exc)[:300]}
                 torch.cuda.synchronize(dev)
+        torch.cuda.empty_cache()
+        fourier_layer = layer_block_subprocess()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times, cores, sample_b = cpu_oracle_step_time(steps=5, warmup=1, max_seconds=15.0)
@@ -607,6 +740,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base,
             "torch_gpu_baseline": torch_gpu,
             "configs": configs,
+            "fourier_layer": fourier_layer,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -627,8 +761,11 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the PyTorch+cuFFT denominator and the other BASELINE configs")
+    ap.add_argument("--layer-only", action="store_true", help="internal: measure the Fourier layer (f1 / f2) and print LAYER_JSON")
     ap.add_argument("--no-graph", action="store_true", help="time the eager autograd path instead of a captured CUDA graph")
     args = ap.parse_args()
+    if args.layer_only:
+        return run_layer(args)
     if args.impl == "reference":
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup

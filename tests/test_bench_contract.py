@@ -47,3 +47,24 @@ def test_torch_cufft_denominator_is_the_reference_op_sequence():
         y_ref = O.spectral_conv_forward(x, w, bias, modes)
         y = bench.torch_cufft_forward(x, w.tensor, bias, O.stored_n_modes(modes))
         assert torch.equal(y, y_ref)
+
+
+def test_torch_layer_denominator_is_the_reference_fourier_layer():
+    """bench.py's PyTorch denominator for the Fourier layer (f1 / f2) restates fno_block.py:377-414; on CPU it agrees with the block
+    oracle, which is pinned to the unmodified reference FNOBlocks (tests/test_block_oracle.py)."""
+    import torch
+    import bench
+    from conftest import block_oracle_kwargs, load_block_golden
+    from oracle import fno_block_oracle as BO
+    from oracle import spectral_conv_oracle as O
+    for name, last in (("block_d2_default_mid", False), ("block_d2_default_last", True)):
+        meta, io, params, _ = load_block_golden(name)
+        i = meta["index"]
+        prm = {"w": params[f"convs.{i}.weight.tensor"], "b": params[f"convs.{i}.bias"], "w_skip": params[f"fno_skips.{i}.conv.weight"],
+               "w1": params[f"channel_mlp.{i}.fcs.0.weight"], "b1": params[f"channel_mlp.{i}.fcs.0.bias"],
+               "w2": params[f"channel_mlp.{i}.fcs.1.weight"], "b2": params[f"channel_mlp.{i}.fcs.1.bias"],
+               "gate": params[f"channel_mlp_skips.{i}.weight"]}
+        y = bench.torch_layer_forward(io["x"], prm, O.stored_n_modes(meta["n_modes"]), last=last)
+        y_ref = BO.fno_block_forward(io["x"], params, i, **block_oracle_kwargs(meta))
+        assert (y - y_ref).abs().max() <= 1e-6 * y_ref.abs().max()
+        assert (y - io["y"]).abs().max() <= 2e-5 * io["y"].abs().max()
