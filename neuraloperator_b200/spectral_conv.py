@@ -758,6 +758,59 @@ class _SpectralConvComplex(torch.autograd.Function):
         return dx, dw, None, None
 
 
+# --------------------------------------------------------------------------------------------------
+# reduced spectral precision, fno_block_precision = "half" / "mixed" (reference :436-437, :451-462; einsum_utils.py:10-36)
+# --------------------------------------------------------------------------------------------------
+def _round_half_(t: torch.Tensor) -> torch.Tensor:
+    """Rounds a float32 / complex64 device tensor to the nearest fp16 values IN PLACE (what `.half()` / `.chalf()` keep)."""
+    lib = _lib.load()
+    flat = torch.view_as_real(t) if t.is_complex() else t
+    if flat.numel():
+        with torch.cuda.device(t.device):
+            _lib.check(lib.sc_pointwise(_lib.POINTWISE_ROUND_HALF, _ptr(flat), None, _ptr(flat), flat.numel(), _stream_ptr(t.device)),
+                       "sc_pointwise")
+    return t
+
+
+class _SpectralConvDenseReduced(torch.autograd.Function):
+    """SpectralConv.forward with fno_block_precision "mixed" (full-precision transform, fp16 modes and contraction, :451-462) or
+    "half" (the input is cast to fp16 first, :436-437), dense weight.  The kernels keep computing in fp32; the tensors are rounded
+    to fp16 at the points where the reference casts -- x (half only), the kept input modes (`x.chalf()`), the weight
+    (`einsum_complexhalf` casts it, einsum_utils.py:20-23) and the contracted modes (the chalf output spectrum) -- so the result
+    differs from the reference's by fp16 rounding noise only (its half FFTs and fp16 products round more often, not less).  The
+    casts are straight-through for gradients, as autograd treats `.half()`; backward is the full-precision backward on the
+    rounded tensors.  There is no bandwidth gain yet: the mode tensors are still stored as complex64."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, plan: Plan, round_input: bool):
+        if round_input:
+            x = _round_half_(x.clone())
+        xm = _round_half_(analyze(plan, x))
+        w_r = _round_half_(weight.detach().clone())
+        ym = _round_half_(contract_dense(plan, xm, w_r))
+        y = synthesize(plan, ym, bias)
+        ctx.plan = plan
+        ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.save_for_backward(xm, w_r)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        plan = ctx.plan
+        xm, w_r = ctx.saved_tensors
+        gy = gy.contiguous()
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.bias_shape is not None and ctx.needs_input_grad[2]
+        gm = analyze(plan, gy, adjoint=True)
+        dxm, dw, db = contract_dense_backward(plan, xm, gm, w_r, need_dxm=need_dx, need_dweight=need_dw, need_dbias=need_db)
+        dx = synthesize(plan, dxm, adjoint=True) if need_dx else None
+        if db is not None:
+            db = db.reshape(ctx.bias_shape)
+        return dx, dw, db, None, None
+
+
 def _validate_scaling_factor(factor, n_dim) -> Optional[List[float]]:
     """Single-layer case of neuralop/utils.py:151-197 (`validate_scaling_factor(..., n_layers=None)`)."""
     if factor is None:
@@ -787,8 +840,9 @@ class SpectralConv(BaseSpectralConv):
     """Fourier-layer spectral convolution (real data, full precision) on hand-written sm_100a kernels.
 
     Parameters: identical to the reference class (spectral_convolution.py:183-305). `complex_data=True` runs C2C transforms on the
-    complex table kernels (any grid; dense or reconstructed weights). Variants the kernels do not cover raise
-    `NotImplementedError` at construction: `fno_block_precision != "full"`.
+    complex table kernels (any grid; dense or reconstructed weights). `fno_block_precision` "half" / "mixed" round the tensors to
+    fp16 where the reference casts (dense or reconstructed weights, real data); combinations the kernels do not cover raise
+    `NotImplementedError` at construction.
     """
 
     def __init__(
@@ -816,8 +870,12 @@ class SpectralConv(BaseSpectralConv):
         if separable and in_channels != out_channels:
             raise ValueError("To use separable Fourier Conv, in_channels must be equal "
                              f"to out_channels, but got in_channels={in_channels} and out_channels={out_channels}")
-        if fno_block_precision != "full":
-            raise NotImplementedError("fno_block_precision must be 'full' (half/mixed spectral precision not built yet)")
+        if fno_block_precision not in ("full", "half", "mixed"):
+            raise ValueError(f"Got fno_block_precision={fno_block_precision}, expected 'full', 'half' or 'mixed'")
+        if fno_block_precision != "full" and (complex_data or separable or
+                                              (implementation == "factorized" and factorization not in (None, "dense", "Dense", "ComplexDense"))):
+            raise NotImplementedError("fno_block_precision 'half' / 'mixed' is built for real data and a dense or reconstructed weight "
+                                      "(not for complex_data, separable, or a factor-by-factor contraction)")
         if implementation not in ("reconstructed", "factorized"):
             raise ValueError(f'Got implementation={implementation}, expected "reconstructed" or "factorized"')
         if fft_norm not in _lib.NORMS:
@@ -1002,6 +1060,10 @@ class SpectralConv(BaseSpectralConv):
                 z = z + (prm.real.sum() if prm.is_complex() else prm.sum()) * 0
             return x.new_zeros((0, self.out_channels, *out_grid)) + z
         x = x.contiguous()
+        if self.fno_block_precision != "full":
+            w = self.weight.to_tensor()
+            return _SpectralConvDenseReduced.apply(x, w if w.is_contiguous() else w.contiguous(), self.bias, plan,
+                                                   self.fno_block_precision == "half")
         if self.separable:
             return self._forward_separable(x, plan)
         if self.implementation == "factorized" and getattr(self.weight, "kind", "") == "tucker":

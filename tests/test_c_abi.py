@@ -65,8 +65,14 @@ def test_module_contract_dense():
     assert cplx.n_modes == [8, 8] and tuple(cplx.weight.shape) == (4, 4, 8, 8)
     csep = nb.SpectralConv(4, 4, (8, 8), complex_data=True, separable=True)
     assert tuple(csep.weight.shape) == (4, 8, 8)
+    assert nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half").fno_block_precision == "half"
+    assert nb.SpectralConv(4, 4, (8, 8), fno_block_precision="mixed", factorization="tucker", rank=[2, 2, 3, 3]).implementation == "reconstructed"
+    with pytest.raises(NotImplementedError):     # factor-by-factor contraction in reduced precision is not built
+        nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half", factorization="tucker", implementation="factorized")
     with pytest.raises(NotImplementedError):
-        nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half")
+        nb.SpectralConv(4, 4, (8, 8), fno_block_precision="mixed", complex_data=True)
+    with pytest.raises(ValueError):
+        nb.SpectralConv(4, 4, (8, 8), fno_block_precision="quarter")
     with pytest.raises(ValueError):
         nb.SpectralConv(4, 4, (8, 8), implementation="nope")
 

@@ -129,3 +129,52 @@ def test_headline_shape_layer_against_oracle(cuda_device):
     for pname, p in blk.named_parameters():
         if pname in g_ref:
             assert rel_err(p.grad, g_ref[pname]) < REL_TOL, pname
+
+
+# ---- f3: fno_block_precision "half" / "mixed" ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["mixed", "half"])
+@pytest.mark.parametrize("B,Ci,Co,grid,modes", [(2, 4, 4, (16, 12), (8, 6)), (2, 3, 5, (64,), (16,)), (2, 8, 8, (128, 128), (32, 32)),
+                                                (1, 4, 4, (8, 8, 8), (4, 4, 4))])
+def test_reduced_precision_matches_rounding_point_oracle(cuda_device, precision, B, Ci, Co, grid, modes):
+    """The module with fp16 rounding points against the oracle's statement of the same pipeline (oracle.spectral_conv_forward_reduced;
+    its contraction stage is pinned to the reference's einsum_complexhalf on CPU).  Tolerance: fp16 rounding noise (a mode that lands
+    within 1e-6 of a rounding boundary may flip by one fp16 ulp between the two transforms)."""
+    from oracle import spectral_conv_oracle as O
+    x, w, bias, gy = O.make_inputs(B, Ci, Co, grid, modes, seed=4)
+    xr = x.clone().requires_grad_(True)
+    wt = w.tensor.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    y_ref = O.spectral_conv_forward_reduced(xr, O.Weight("dense", tensor=wt), br, modes, precision)
+    y_ref.backward(gy)
+    y_full = O.spectral_conv_forward(x, w, bias, modes)
+    conv = nb.SpectralConv(Ci, Co, modes, fno_block_precision=precision).to(cuda_device)
+    with torch.no_grad():
+        conv.weight.tensor.copy_(w.tensor.to(cuda_device))
+        conv.bias.copy_(bias.to(cuda_device))
+    xd = x.to(cuda_device).requires_grad_(True)
+    y = conv(xd)
+    assert y.dtype == torch.float32
+    y.backward(gy.to(cuda_device))
+    torch.cuda.synchronize()
+    tol = 2e-3
+    assert rel_err(y, y_ref) < tol, "y"
+    assert rel_err(xd.grad, xr.grad) < tol, "dx"
+    assert rel_err(conv.weight.tensor.grad, wt.grad) < tol, "dW"
+    assert rel_err(conv.bias.grad, br.grad) < tol, "db"
+    assert 1e-7 < rel_err(y, y_full) < 5e-3                      # reduced precision really happened, and stays fp16-close to full
+    assert torch.equal(xd.detach().cpu(), x)                     # "half" rounds a copy, never the caller's tensor
+
+
+def test_block_with_mixed_precision_and_tanh_runs(cuda_device):
+    """The configuration the reference recommends for reduced precision (stabilizer="tanh", fno_block.py:95-99) through FNOBlocks."""
+    torch.manual_seed(5)
+    blk = nb.FNOBlocks(8, 8, (8, 8), n_layers=2, fno_block_precision="mixed", stabilizer="tanh").to(cuda_device)
+    full = nb.FNOBlocks(8, 8, (8, 8), n_layers=2, stabilizer="tanh").to(cuda_device)
+    full.load_state_dict(blk.state_dict())
+    x = torch.randn(2, 8, 16, 16, device=cuda_device, requires_grad=True)
+    y = blk(x, 0)
+    y.sum().backward()
+    with torch.no_grad():
+        y_full = full(x, 0)
+    assert torch.isfinite(y).all() and torch.isfinite(x.grad).all()
+    assert rel_err(y, y_full) < 5e-3
