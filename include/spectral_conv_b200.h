@@ -184,6 +184,31 @@ int sc_backward_tucker(const sc_plan* plan, const sc_plan* plan_kept, const floa
                        int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks,
                        void* workspace, size_t workspace_bytes, sc_stream stream);
 
+/* ---- whole forward / backward for a CP weight (_contract_cp, :55-73) and a TT weight (_contract_tt, :106-127), one call each ------
+ * The launches of the per-factor building blocks above, in the same order and with the same operands as the Python-orchestrated
+ * chains, issued from one opaque `saved` buffer and one workspace (graph-capturable, no host allocations in between).
+ * CP: lambda (R), u_in (Ci, R), u_out (Co, R), u_modes[j] = the KEPT rows of mode factor j, contiguous (k_j, R).
+ * TT: ranks = {r1, r_0 .. r_{d-1}}: g0 (1, Ci, r1), g1 (r1, Co, r_0), cores[j] = the KEPT rows of mode core j, contiguous
+ *     (r_j, k_j, r_{j+1}) with r_d = 1; plan_kept as for the Tucker entry points.  Gradients in the layout of their parameter. */
+size_t sc_cp_saved_elems(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, int32_t rank);
+size_t sc_cp_workspace_bytes(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, int32_t rank);
+int sc_forward_cp(const sc_plan* plan, const float* x, const sc_complex* lambda, const sc_complex* u_in, const sc_complex* u_out,
+                  const sc_complex* const* u_modes, const float* bias, float* y, sc_complex* saved, int32_t batch, int32_t in_channels,
+                  int32_t out_channels, int32_t rank, void* workspace, size_t workspace_bytes, sc_stream stream);
+int sc_backward_cp(const sc_plan* plan, const float* gy, const sc_complex* lambda, const sc_complex* u_in, const sc_complex* u_out,
+                   const sc_complex* const* u_modes, const sc_complex* saved, float* dx, sc_complex* d_lambda, sc_complex* d_u_in,
+                   sc_complex* d_u_out, sc_complex* const* d_u_modes, float* dbias, int32_t batch, int32_t in_channels,
+                   int32_t out_channels, int32_t rank, void* workspace, size_t workspace_bytes, sc_stream stream);
+size_t sc_tt_saved_elems(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks);
+size_t sc_tt_workspace_bytes(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks);
+int sc_forward_tt(const sc_plan* plan, const sc_plan* plan_kept, const float* x, const sc_complex* g0, const sc_complex* g1,
+                  const sc_complex* const* cores, const float* bias, float* y, sc_complex* saved, int32_t batch, int32_t in_channels,
+                  int32_t out_channels, const int32_t* ranks, void* workspace, size_t workspace_bytes, sc_stream stream);
+int sc_backward_tt(const sc_plan* plan, const sc_plan* plan_kept, const float* gy, const sc_complex* g0, const sc_complex* g1,
+                   const sc_complex* const* cores, const sc_complex* saved, float* dx, sc_complex* d_g0, sc_complex* d_g1,
+                   sc_complex* const* d_cores, float* dbias, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks,
+                   void* workspace, size_t workspace_bytes, sc_stream stream);
+
 /* ---- the one collective of the data-parallel step, over NVLink peer memory -------------------------------------------------
  * In-place all-reduce of `n_floats` (multiple of 4) floats: result = scale * sum over ranks (scale = 1 / world_size averages, as
  * DDP does, trainer.py:203-205).  peer_buffers[r] / peer_signal_pads[r] (HOST arrays of world_size DEVICE pointers) are rank r's

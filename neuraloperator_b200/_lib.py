@@ -61,6 +61,18 @@ SIGNATURES = {
                                   c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sc_backward_tucker": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sc_cp_saved_elems": (c_size_t, [c_void_p, c_i32, c_i32, c_i32, c_i32]),
+    "sc_cp_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32, c_i32, c_i32]),
+    "sc_forward_cp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_i32, c_i32, c_i32, c_i32, c_void_p, c_size_t, c_void_p]),
+    "sc_backward_cp": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_void_p, c_size_t, c_void_p]),
+    "sc_tt_saved_elems": (c_size_t, [c_void_p, c_i32, c_i32, c_i32, c_void_p]),
+    "sc_tt_workspace_bytes": (c_size_t, [c_void_p, c_i32, c_i32, c_i32, c_void_p]),
+    "sc_forward_tt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sc_backward_tt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sc_allreduce_p2p": (c_int, [c_void_p, c_void_p, c_i32, c_i32, c_i64, ctypes.c_float, c_i32, c_void_p]),
     "sc_event_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "sc_event_destroy": (None, [c_void_p]),

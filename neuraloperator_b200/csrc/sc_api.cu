@@ -944,6 +944,275 @@ int sc_cp_factor_grad(const sc_complex* const* mode_factors, const int32_t* kept
   return 0;
 }
 
+// ---- CP-factorized forward / backward as ONE call each (reference _contract_cp, :55-73) -----------------------------------
+// The same launches, in the same order and with the same operands, as the Python-orchestrated chain (`_SpectralConvCP`,
+// neuraloperator_b200/spectral_conv.py), issued from one saved buffer and one workspace.
+namespace {
+struct CpDims {
+  int d = 0, B = 0, Ci = 0, Co = 0, R = 0;
+  int k[SC_MAX_DIMS] = {0};
+  int64_t M = 1;
+  // saved-buffer offsets (complex elements): kept input modes | x U_in | (x U_in) * scale | scale
+  int64_t off_t1() const { return (int64_t)B * Ci * M; }
+  int64_t off_t2() const { return off_t1() + (int64_t)B * R * M; }
+  int64_t off_scale() const { return off_t2() + (int64_t)B * R * M; }
+  int64_t saved_elems() const { return off_scale() + (int64_t)R * M; }
+};
+
+bool cp_dims(const Plan* p, int B, int Ci, int Co, int R, CpDims* t) {
+  if (p == nullptr || B < 1 || Ci < 1 || Co < 1 || R < 1) { set_error("cp: bad arguments"); return false; }
+  t->d = p->d; t->B = B; t->Ci = Ci; t->Co = Co; t->R = R; t->M = p->n_modes_total;
+  for (int j = 0; j < p->d; ++j) t->k[j] = p->dim[j].k;
+  return true;
+}
+
+struct CpBwdArena { float2 *g2, *g1, *dscale; size_t bytes; };
+
+CpBwdArena cp_bwd_arena(const CpDims& t, char* base) {
+  CpBwdArena a{};
+  size_t off = 0;
+  auto take = [&](size_t elems) { float2* ptr = reinterpret_cast<float2*>(base + off); off += a256(elems * sizeof(float2)); return ptr; };
+  a.g2 = take((size_t)t.B * t.R * t.M);
+  a.g1 = take((size_t)t.B * t.R * t.M);
+  a.dscale = take((size_t)t.R * t.M);
+  a.bytes = off;
+  return a;
+}
+}  // namespace
+
+size_t sc_cp_saved_elems(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, int32_t rank) {
+  CpDims t;
+  if (!cp_dims(reinterpret_cast<const Plan*>(plan), batch, in_channels, out_channels, rank, &t)) return 0;
+  return (size_t)t.saved_elems();
+}
+
+size_t sc_cp_workspace_bytes(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, int32_t rank) {
+  CpDims t;
+  if (!cp_dims(reinterpret_cast<const Plan*>(plan), batch, in_channels, out_channels, rank, &t)) return 0;
+  const int64_t n_max = (int64_t)batch * std::max(in_channels, out_channels);
+  return a256(sc_workspace_bytes(plan, n_max)) + cp_bwd_arena(t, nullptr).bytes;
+}
+
+int sc_forward_cp(const sc_plan* plan, const float* x, const sc_complex* lambda, const sc_complex* u_in, const sc_complex* u_out,
+                  const sc_complex* const* u_modes, const float* bias, float* y, sc_complex* saved, int32_t batch, int32_t in_channels,
+                  int32_t out_channels, int32_t rank, void* workspace, size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && x != nullptr && lambda != nullptr && u_in != nullptr && u_out != nullptr && u_modes != nullptr && y != nullptr &&
+             saved != nullptr, "sc_forward_cp: null argument");
+  CpDims t;
+  SC_TRY(cp_dims(p, batch, in_channels, out_channels, rank, &t));
+  const float2* u[SC_MAX_DIMS]; int k[SC_MAX_DIMS];
+  SC_TRY(cp_args(u_modes, t.k, t.d, u, k));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)t.B * std::max(t.Ci, t.Co);
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, workspace_bytes, &w));
+  float2* sv = reinterpret_cast<float2*>(saved);
+  float2 *xm = sv, *t1 = sv + t.off_t1(), *t2 = sv + t.off_t2(), *scale = sv + t.off_scale();
+  float2* ym = w.modes[0];
+  SC_TRY(analyze(p, x, (int64_t)t.B * t.Ci, xm, false, w.buf[0], w.buf[1], st));
+  SC_TRY(launch_cp_scale(u, k, t.d, reinterpret_cast<const float2*>(lambda), scale, t.R, t.M, st));
+  // T[p = e, q = i] = U_in[i, e];  pointwise scale;  T[p = o, q = e] = U_out[o, e]
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_in), 1, t.R, false, xm, t1, t.B, t.R, t.Ci, (int)t.M, st));
+  SC_TRY(launch_cp_apply(t1, scale, t2, false, t.B, (int64_t)t.R * t.M, st));
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_out), t.R, 1, false, t2, ym, t.B, t.Co, t.R, (int)t.M, st));
+  SC_TRY(synthesize(p, ym, (int64_t)t.B * t.Co, t.Co, bias, y, false, w.buf[0], w.buf[1], st));
+  return 0;
+}
+
+int sc_backward_cp(const sc_plan* plan, const float* gy, const sc_complex* lambda, const sc_complex* u_in, const sc_complex* u_out,
+                   const sc_complex* const* u_modes, const sc_complex* saved, float* dx, sc_complex* d_lambda, sc_complex* d_u_in,
+                   sc_complex* d_u_out, sc_complex* const* d_u_modes, float* dbias, int32_t batch, int32_t in_channels,
+                   int32_t out_channels, int32_t rank, void* workspace, size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  SC_REQUIRE(p != nullptr && gy != nullptr && lambda != nullptr && u_in != nullptr && u_out != nullptr && u_modes != nullptr &&
+             saved != nullptr && dx != nullptr && d_lambda != nullptr && d_u_in != nullptr && d_u_out != nullptr && d_u_modes != nullptr,
+             "sc_backward_cp: null argument");
+  CpDims t;
+  SC_TRY(cp_dims(p, batch, in_channels, out_channels, rank, &t));
+  const float2* u[SC_MAX_DIMS]; int k[SC_MAX_DIMS];
+  SC_TRY(cp_args(u_modes, t.k, t.d, u, k));
+  for (int j = 0; j < t.d; ++j) SC_REQUIRE(d_u_modes[j] != nullptr, "sc_backward_cp: null mode-factor gradient");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)t.B * std::max(t.Ci, t.Co);
+  const size_t tw = a256(sc_workspace_bytes(plan, n_max));
+  SC_REQUIRE(workspace != nullptr && workspace_bytes >= tw + cp_bwd_arena(t, nullptr).bytes, "sc_backward_cp: workspace too small (see sc_cp_workspace_bytes)");
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, tw, &w));
+  CpBwdArena a = cp_bwd_arena(t, static_cast<char*>(workspace) + tw);
+  const float2* sv = reinterpret_cast<const float2*>(saved);
+  const float2 *xm = sv, *t1 = sv + t.off_t1(), *t2 = sv + t.off_t2(), *scale = sv + t.off_scale();
+  const float2* lam = reinterpret_cast<const float2*>(lambda);
+  float2* gm = w.modes[0];
+  float2* dxm = w.modes[1];
+  const int64_t per = (int64_t)t.R * t.M;
+  SC_TRY(analyze(p, gy, (int64_t)t.B * t.Co, gm, true, w.buf[0], w.buf[1], st));
+  if (dbias != nullptr) SC_TRY(launch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
+  // out side: g2 = U_out^H gm,  dU_out[o, e] = sum conj(t2[b, e, m]) gm[b, o, m]
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_out), 1, t.R, true, gm, a.g2, t.B, t.R, t.Co, (int)t.M, st));
+  SC_TRY(launch_pair_reduce(t2, gm, reinterpret_cast<float2*>(d_u_out), 1, t.R, t.B, t.R, t.Co, (int)t.M, st));
+  // pointwise stage: dscale = sum_b conj(t1) g2,  g1 = g2 conj(scale)
+  SC_TRY(launch_cp_dscale(t1, a.g2, a.dscale, t.B, per, st));
+  SC_TRY(launch_cp_apply(a.g2, scale, a.g1, true, t.B, per, st));
+  // in side
+  SC_TRY(launch_pair_reduce(xm, a.g1, reinterpret_cast<float2*>(d_u_in), t.R, 1, t.B, t.Ci, t.R, (int)t.M, st));
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_in), t.R, 1, true, a.g1, dxm, t.B, t.Ci, t.R, (int)t.M, st));
+  SC_TRY(synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+  // lambda and the mode factors from dscale
+  SC_TRY(launch_cp_factor_grad(u, k, t.d, lam, a.dscale, reinterpret_cast<float2*>(d_lambda), -1, t.R, t.M, st));
+  for (int j = 0; j < t.d; ++j)
+    SC_TRY(launch_cp_factor_grad(u, k, t.d, lam, a.dscale, reinterpret_cast<float2*>(d_u_modes[j]), j, t.R, t.M, st));
+  return 0;
+}
+
+// ---- TT-factorized forward / backward as ONE call each (reference _contract_tt, :106-127) ---------------------------------
+// W[i,o,m] = G0[0,i,:] G1[:,o,:] C_0[:,m_0,:] .. C_{d-1}[:,m_{d-1},0].  ranks = {r1, r_0 .. r_{d-1}}: G0 (1, Ci, r1), G1 (r1, Co, r_0),
+// cores[j] = the KEPT rows of mode core j, contiguous (r_j, k_j, r_{j+1}) with r_d = 1.  Same launches, order and operands as the
+// Python-orchestrated chain (`_SpectralConvTT`): the mode cores are multiplied right to left into V[r_0, m]; G1 V is a rank-r1 weight
+// block that the dense mode GEMM applies to xm G0.
+namespace {
+struct TtDims {
+  int d = 0, B = 0, Ci = 0, Co = 0, r1 = 0;
+  int r[SC_MAX_DIMS + 1] = {0}, k[SC_MAX_DIMS] = {0};      // r[j]: left rank of mode core j, r[d] = 1
+  int64_t M = 1;
+  int64_t inner(int j) const { int64_t e = 1; for (int l = j + 1; l < d; ++l) e *= k[l]; return e; }      // prod_{l > j} k_l
+  int64_t chain_elems(int j) const { return (int64_t)r[j] * k[j] * inner(j); }                            // A_j: (r_j, k_j .. k_{d-1})
+  // saved-buffer offsets (complex elements): kept input modes | xm G0 | G1 V | A_{d-2}, .., A_0 (A_{d-1} is cores[d-1] itself)
+  int64_t off_t1() const { return (int64_t)B * Ci * M; }
+  int64_t off_wc() const { return off_t1() + (int64_t)B * r1 * M; }
+  int64_t off_chain(int j) const {       // 0 <= j <= d-2
+    int64_t o = off_wc() + (int64_t)r1 * Co * M;
+    for (int l = d - 2; l > j; --l) o += chain_elems(l);
+    return o;
+  }
+  int64_t saved_elems() const { return d >= 2 ? off_chain(0) + chain_elems(0) : off_wc() + (int64_t)r1 * Co * M; }
+};
+
+bool tt_dims(const Plan* p, int B, int Ci, int Co, const int32_t* ranks, TtDims* t) {
+  if (p == nullptr || ranks == nullptr || B < 1 || Ci < 1 || Co < 1) { set_error("tt: bad arguments"); return false; }
+  t->d = p->d; t->B = B; t->Ci = Ci; t->Co = Co; t->r1 = ranks[0]; t->M = p->n_modes_total;
+  if (t->r1 < 1) { set_error("tt: ranks must be >= 1"); return false; }
+  for (int j = 0; j < p->d; ++j) {
+    t->r[j] = ranks[1 + j]; t->k[j] = p->dim[j].k;
+    if (t->r[j] < 1) { set_error("tt: ranks must be >= 1"); return false; }
+  }
+  t->r[p->d] = 1;
+  return true;
+}
+
+struct TtBwdArena { float2 *g1, *dwc, *da[2]; size_t bytes; };
+
+TtBwdArena tt_bwd_arena(const TtDims& t, char* base) {
+  TtBwdArena a{};
+  size_t off = 0;
+  auto take = [&](size_t elems) { float2* ptr = reinterpret_cast<float2*>(base + off); off += a256(elems * sizeof(float2)); return ptr; };
+  a.g1 = take((size_t)t.B * t.r1 * t.M);
+  a.dwc = take((size_t)t.r1 * t.Co * t.M);
+  int64_t mx = 0;
+  for (int j = 0; j < t.d; ++j) mx = std::max(mx, t.chain_elems(j));
+  a.da[0] = take((size_t)mx);
+  a.da[1] = take((size_t)mx);
+  a.bytes = off;
+  return a;
+}
+}  // namespace
+
+size_t sc_tt_saved_elems(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks) {
+  TtDims t;
+  if (!tt_dims(reinterpret_cast<const Plan*>(plan), batch, in_channels, out_channels, ranks, &t)) return 0;
+  return (size_t)t.saved_elems();
+}
+
+size_t sc_tt_workspace_bytes(const sc_plan* plan, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks) {
+  TtDims t;
+  if (!tt_dims(reinterpret_cast<const Plan*>(plan), batch, in_channels, out_channels, ranks, &t)) return 0;
+  const int64_t n_max = (int64_t)batch * std::max(in_channels, out_channels);
+  return a256(sc_workspace_bytes(plan, n_max)) + tt_bwd_arena(t, nullptr).bytes;
+}
+
+int sc_forward_tt(const sc_plan* plan, const sc_plan* plan_kept, const float* x, const sc_complex* g0, const sc_complex* g1,
+                  const sc_complex* const* cores, const float* bias, float* y, sc_complex* saved, int32_t batch, int32_t in_channels,
+                  int32_t out_channels, const int32_t* ranks, void* workspace, size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  const Plan* pk = reinterpret_cast<const Plan*>(plan_kept);
+  SC_REQUIRE(p != nullptr && pk != nullptr && x != nullptr && g0 != nullptr && g1 != nullptr && cores != nullptr && y != nullptr &&
+             saved != nullptr, "sc_forward_tt: null argument");
+  SC_REQUIRE(pk->n_modes_total == p->n_modes_total && pk->weight_elems_per_io == p->n_modes_total,
+             "sc_forward_tt: plan_kept must be the same problem with weight extents == kept modes");
+  TtDims t;
+  SC_TRY(tt_dims(p, batch, in_channels, out_channels, ranks, &t));
+  for (int j = 0; j < t.d; ++j) SC_REQUIRE(cores[j] != nullptr, "sc_forward_tt: null mode core");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)t.B * std::max(t.Ci, t.Co);
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, workspace_bytes, &w));
+  float2* sv = reinterpret_cast<float2*>(saved);
+  float2 *xm = sv, *t1 = sv + t.off_t1(), *wc = sv + t.off_wc();
+  float2* ym = w.modes[0];
+  SC_TRY(analyze(p, x, (int64_t)t.B * t.Ci, xm, false, w.buf[0], w.buf[1], st));
+  // A_{d-1} = cores[d-1] (r_{d-1}, k_{d-1});  A_j[(a, m_j), rest] = sum_b C_j[a, m_j, b] A_{j+1}[b, rest];  V = A_0 (r_0, M)
+  const float2* cur = reinterpret_cast<const float2*>(cores[t.d - 1]);
+  for (int j = t.d - 2; j >= 0; --j) {
+    float2* dst = sv + t.off_chain(j);
+    SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(cores[j]), t.r[j + 1], 1, false, cur, dst, 1, t.r[j] * t.k[j],
+                                             t.r[j + 1], (int)t.inner(j), st));
+    cur = dst;
+  }
+  // wc[(r, o), m] = sum_s G1[r, o, s] V[s, m];  t1 = xm G0;  dense mode product on the r1 rank channels
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g1), t.r[0], 1, false, cur, wc, 1, t.r1 * t.Co, t.r[0], (int)t.M, st));
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g0), 1, t.r1, false, xm, t1, t.B, t.r1, t.Ci, (int)t.M, st));
+  SC_TRY(contract_fwd(pk, t1, wc, ym, t.B, t.r1, t.Co, st, false));
+  SC_TRY(synthesize(p, ym, (int64_t)t.B * t.Co, t.Co, bias, y, false, w.buf[0], w.buf[1], st));
+  return 0;
+}
+
+int sc_backward_tt(const sc_plan* plan, const sc_plan* plan_kept, const float* gy, const sc_complex* g0, const sc_complex* g1,
+                   const sc_complex* const* cores, const sc_complex* saved, float* dx, sc_complex* d_g0, sc_complex* d_g1,
+                   sc_complex* const* d_cores, float* dbias, int32_t batch, int32_t in_channels, int32_t out_channels, const int32_t* ranks,
+                   void* workspace, size_t workspace_bytes, sc_stream stream) {
+  const Plan* p = reinterpret_cast<const Plan*>(plan);
+  const Plan* pk = reinterpret_cast<const Plan*>(plan_kept);
+  SC_REQUIRE(p != nullptr && pk != nullptr && gy != nullptr && g0 != nullptr && g1 != nullptr && cores != nullptr && saved != nullptr &&
+             dx != nullptr && d_g0 != nullptr && d_g1 != nullptr && d_cores != nullptr, "sc_backward_tt: null argument");
+  TtDims t;
+  SC_TRY(tt_dims(p, batch, in_channels, out_channels, ranks, &t));
+  for (int j = 0; j < t.d; ++j) SC_REQUIRE(cores[j] != nullptr && d_cores[j] != nullptr, "sc_backward_tt: null mode core / gradient");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_max = (int64_t)t.B * std::max(t.Ci, t.Co);
+  const size_t tw = a256(sc_workspace_bytes(plan, n_max));
+  SC_REQUIRE(workspace != nullptr && workspace_bytes >= tw + tt_bwd_arena(t, nullptr).bytes, "sc_backward_tt: workspace too small (see sc_tt_workspace_bytes)");
+  Workspace w{};
+  SC_TRY(carve(p, n_max, workspace, tw, &w));
+  TtBwdArena a = tt_bwd_arena(t, static_cast<char*>(workspace) + tw);
+  const float2* sv = reinterpret_cast<const float2*>(saved);
+  const float2 *xm = sv, *t1 = sv + t.off_t1(), *wc = sv + t.off_wc();
+  float2* gm = w.modes[0];
+  float2* dxm = w.modes[1];
+  SC_TRY(analyze(p, gy, (int64_t)t.B * t.Co, gm, true, w.buf[0], w.buf[1], st));
+  if (dbias != nullptr) SC_TRY(launch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
+  // the two mode GEMMs of the dense backward on the rank channels: g1 = d(t1), dwc = d(wc)
+  SC_TRY(contract_bwd(pk, t1, gm, wc, a.g1, a.dwc, nullptr, t.B, t.r1, t.Co, st, false));
+  // in side: dG0[0, i, r] = sum conj(xm[b, i, m]) g1[b, r, m];  dxm = g1 G0^H
+  SC_TRY(launch_pair_reduce(xm, a.g1, reinterpret_cast<float2*>(d_g0), t.r1, 1, t.B, t.Ci, t.r1, (int)t.M, st));
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g0), t.r1, 1, true, a.g1, dxm, t.B, t.Ci, t.r1, (int)t.M, st));
+  SC_TRY(synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+  // weight side: dG1[(r, o), s] = sum_m conj(V[s, m]) dwc[(r, o), m];  dV = G1^H dwc;  then undo the chain, first axis first
+  const float2* v = t.d >= 2 ? sv + t.off_chain(0) : reinterpret_cast<const float2*>(cores[0]);
+  SC_TRY(launch_pair_reduce(v, a.dwc, reinterpret_cast<float2*>(d_g1), 1, t.r[0], 1, t.r[0], t.r1 * t.Co, (int)t.M, st));
+  float2* d_a = t.d == 1 ? reinterpret_cast<float2*>(d_cores[0]) : a.da[0];
+  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g1), 1, t.r[0], true, a.dwc, d_a, 1, t.r[0], t.r1 * t.Co, (int)t.M, st));
+  for (int j = 0; j + 1 < t.d; ++j) {
+    const float2* a_next = (j + 1 == t.d - 1) ? reinterpret_cast<const float2*>(cores[t.d - 1]) : sv + t.off_chain(j + 1);     // A_{j+1}: (r_{j+1}, inner)
+    const int64_t inner = t.inner(j);
+    SC_TRY(launch_pair_reduce(a_next, d_a, reinterpret_cast<float2*>(d_cores[j]), 1, t.r[j + 1], 1, t.r[j + 1], t.r[j] * t.k[j], (int)inner, st));
+    float2* dst = (j + 1 == t.d - 1) ? reinterpret_cast<float2*>(d_cores[t.d - 1]) : a.da[(j + 1) & 1];
+    SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(cores[j]), 1, t.r[j + 1], true, d_a, dst, 1, t.r[j + 1],
+                                             t.r[j] * t.k[j], (int)inner, st));
+    d_a = dst;
+  }
+  return 0;
+}
+
 int sc_selftest_umma(const float* a, const float* b, float* d, int32_t n, int32_t k, sc_stream stream) {
   SC_REQUIRE(a != nullptr && b != nullptr && d != nullptr, "sc_selftest_umma: null argument");
   SC_TRY(umma_selftest(a, b, d, n, k, static_cast<cudaStream_t>(stream)));

@@ -531,6 +531,120 @@ class _SpectralConvTT(torch.autograd.Function):
 
 
 # --------------------------------------------------------------------------------------------------
+# CP / TT chains as ONE C call per direction (sc_forward_cp / sc_backward_cp, sc_forward_tt / sc_backward_tt): the same launches as
+# `_SpectralConvCP` / `_SpectralConvTT` above, issued by the library from one saved buffer and one workspace.  They were written
+# after the round's GPU minutes were spent, so the Python-orchestrated chains (validated on hardware) stay the default; set
+# `FACTORIZED_CHAINS_IN_C = True` (or SC_FACTORIZED_C=1 in the environment) to route CP / TT through the C entry points.
+# --------------------------------------------------------------------------------------------------
+import os as _os
+
+FACTORIZED_CHAINS_IN_C = _os.environ.get("SC_FACTORIZED_C", "0") == "1"
+
+
+class _SpectralConvCPCall(torch.autograd.Function):
+    """`_SpectralConvCP` behind one C call per direction."""
+
+    @staticmethod
+    def forward(ctx, x, bias, plan, lam, u_in, u_out, *u_modes):
+        lib = _lib.load()
+        dev = x.device
+        B, Ci = x.shape[:2]
+        Co, R = u_out.shape
+        saved = torch.empty(int(lib.sc_cp_saved_elems(plan.handle, B, Ci, Co, R)), dtype=torch.complex64, device=dev)
+        ws = torch.empty(max(int(lib.sc_cp_workspace_bytes(plan.handle, B, Ci, Co, R)), 16), dtype=torch.uint8, device=dev)
+        y = torch.empty((B, Co, *plan.out_grid), dtype=torch.float32, device=dev)
+        b = bias.reshape(-1) if bias is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.sc_forward_cp(plan.handle, _ptr(x), _ptr(lam), _ptr(u_in), _ptr(u_out), _ptr_array(u_modes), _ptr(b), _ptr(y),
+                                         _ptr(saved), B, Ci, Co, R, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_forward_cp")
+        ctx.plan = plan
+        ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.dims = (B, Ci, Co, R)
+        ctx.save_for_backward(saved, lam, u_in, u_out, *u_modes)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        plan = ctx.plan
+        B, Ci, Co, R = ctx.dims
+        saved, lam, u_in, u_out = ctx.saved_tensors[:4]
+        u_modes = ctx.saved_tensors[4:]
+        dev = gy.device
+        gy = gy.contiguous()
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        dx = torch.empty((B, Ci, *plan.grid), dtype=torch.float32, device=dev)
+        d_lam, d_u_in, d_u_out = torch.empty_like(lam), torch.empty_like(u_in), torch.empty_like(u_out)
+        d_modes = [torch.empty_like(u) for u in u_modes]
+        db = torch.empty(Co, dtype=torch.float32, device=dev) if ctx.bias_shape is not None else None
+        ws = torch.empty(max(int(lib.sc_cp_workspace_bytes(plan.handle, B, Ci, Co, R)), 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sc_backward_cp(plan.handle, _ptr(gy), _ptr(lam), _ptr(u_in), _ptr(u_out), _ptr_array(u_modes), _ptr(saved),
+                                          _ptr(dx), _ptr(d_lam), _ptr(d_u_in), _ptr(d_u_out), _ptr_array(d_modes), _ptr(db),
+                                          B, Ci, Co, R, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_backward_cp")
+        if db is not None:
+            db = db.reshape(ctx.bias_shape)
+        return (dx, db, None, d_lam, d_u_in, d_u_out, *d_modes)
+
+
+class _SpectralConvTTCall(torch.autograd.Function):
+    """`_SpectralConvTT` behind one C call per direction."""
+
+    @staticmethod
+    def _ranks(g1c, cores):
+        return (ctypes.c_int32 * (1 + len(cores)))(int(g1c.shape[0]), *[int(c.shape[0]) for c in cores])
+
+    @staticmethod
+    def forward(ctx, x, bias, plan, plan_kept, g0, g1c, *cores):
+        lib = _lib.load()
+        dev = x.device
+        B, Ci = x.shape[:2]
+        Co = g1c.shape[1]
+        cores = tuple(c.contiguous() for c in cores)
+        ranks = _SpectralConvTTCall._ranks(g1c, cores)
+        saved = torch.empty(int(lib.sc_tt_saved_elems(plan.handle, B, Ci, Co, ranks)), dtype=torch.complex64, device=dev)
+        ws = torch.empty(max(int(lib.sc_tt_workspace_bytes(plan.handle, B, Ci, Co, ranks)), 16), dtype=torch.uint8, device=dev)
+        y = torch.empty((B, Co, *plan.out_grid), dtype=torch.float32, device=dev)
+        b = bias.reshape(-1) if bias is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.sc_forward_tt(plan.handle, plan_kept.handle, _ptr(x), _ptr(g0), _ptr(g1c), _ptr_array(cores), _ptr(b), _ptr(y),
+                                         _ptr(saved), B, Ci, Co, ranks, _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_forward_tt")
+        ctx.plan, ctx.plan_kept = plan, plan_kept
+        ctx.bias_shape = bias.shape if bias is not None else None
+        ctx.dims = (B, Ci, Co)
+        ctx.save_for_backward(saved, g0, g1c, *cores)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        plan, plan_kept = ctx.plan, ctx.plan_kept
+        B, Ci, Co = ctx.dims
+        saved, g0, g1c = ctx.saved_tensors[:3]
+        cores = ctx.saved_tensors[3:]
+        dev = gy.device
+        gy = gy.contiguous()
+        if gy.dtype != torch.float32:
+            gy = gy.float()
+        ranks = _SpectralConvTTCall._ranks(g1c, cores)
+        dx = torch.empty((B, Ci, *plan.grid), dtype=torch.float32, device=dev)
+        d_g0, d_g1 = torch.empty_like(g0), torch.empty_like(g1c)
+        d_cores = [torch.empty_like(c) for c in cores]
+        db = torch.empty(Co, dtype=torch.float32, device=dev) if ctx.bias_shape is not None else None
+        ws = torch.empty(max(int(lib.sc_tt_workspace_bytes(plan.handle, B, Ci, Co, ranks)), 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sc_backward_tt(plan.handle, plan_kept.handle, _ptr(gy), _ptr(g0), _ptr(g1c), _ptr_array(cores), _ptr(saved),
+                                          _ptr(dx), _ptr(d_g0), _ptr(d_g1), _ptr_array(d_cores), _ptr(db), B, Ci, Co, ranks,
+                                          _ptr(ws), ws.numel(), _stream_ptr(dev)), "sc_backward_tt")
+        if db is not None:
+            db = db.reshape(ctx.bias_shape)
+        return (dx, db, None, None, d_g0, d_g1, *d_cores)
+
+
+# --------------------------------------------------------------------------------------------------
 # separable (depthwise) contraction, reference `_contract_dense_separable` :49-52
 # --------------------------------------------------------------------------------------------------
 class _SpectralConvSeparable(torch.autograd.Function):
@@ -1021,15 +1135,15 @@ class SpectralConv(BaseSpectralConv):
         w = self.weight
         factors = list(w.factors)
         u_modes = [self._kept_rows(factors[2 + j], plan, j) for j in range(self.order)]
-        return _SpectralConvCP.apply(x, self.bias, plan, w.weights.contiguous(), factors[0].contiguous(),
-                                     factors[1].contiguous(), *u_modes)
+        fn = _SpectralConvCPCall if FACTORIZED_CHAINS_IN_C else _SpectralConvCP
+        return fn.apply(x, self.bias, plan, w.weights.contiguous(), factors[0].contiguous(), factors[1].contiguous(), *u_modes)
 
     def _forward_tt(self, x, plan: Plan):
         """Core-by-core contraction (reference implementation="factorized", `_contract_tt` :106-127)."""
         factors = list(self.weight.factors)
         cores = [self._kept_rows(factors[2 + j], plan, j, axis=1) for j in range(self.order)]
-        return _SpectralConvTT.apply(x, self.bias, plan, self._plan_kept(plan), factors[0].contiguous(),
-                                     factors[1].contiguous(), *cores)
+        fn = _SpectralConvTTCall if FACTORIZED_CHAINS_IN_C else _SpectralConvTT
+        return fn.apply(x, self.bias, plan, self._plan_kept(plan), factors[0].contiguous(), factors[1].contiguous(), *cores)
 
     def forward(self, x: torch.Tensor, output_shape: Optional[Tuple[int]] = None):
         if x.ndim != self.order + 2:

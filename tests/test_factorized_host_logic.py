@@ -96,6 +96,54 @@ class _Lib:
         return 0
 
 
+    # CP / TT behind one C call per direction (sc_forward_cp / sc_backward_cp, sc_forward_tt / sc_backward_tt): same treatment
+    def sc_cp_saved_elems(self, plan, B, Ci, Co, R):
+        return 0
+
+    def sc_cp_workspace_bytes(self, plan, B, Ci, Co, R):
+        return 16
+
+    def sc_forward_cp(self, plan, x, lam, u_in, u_out, u_modes, bias, y, saved, B, Ci, Co, R, ws, n, st):
+        assert (B, Ci, Co, R) == (x.shape[0], u_in.shape[0], u_out.shape[0], lam.shape[0])
+        self._cp_x = x.detach().clone()
+        out = O.contract_cp(x.to(torch.complex64), lam, [u_in, u_out, *u_modes]).real
+        y.copy_(out + (bias.reshape(1, -1, *[1] * (out.ndim - 2)) if bias is not None else 0))
+        return 0
+
+    def sc_backward_cp(self, plan, gy, lam, u_in, u_out, u_modes, saved, dx, d_lam, d_u_in, d_u_out, d_u_modes, dbias, B, Ci, Co, R, ws, n, st):
+        with torch.enable_grad():
+            ps = [t.detach().clone().requires_grad_(True) for t in (self._cp_x, lam, u_in, u_out, *u_modes)]
+            O.contract_cp(ps[0].to(torch.complex64), ps[1], ps[2:]).real.backward(gy)
+        for dst, src in zip([dx, d_lam, d_u_in, d_u_out, *d_u_modes], ps):
+            dst.copy_(src.grad)
+        if dbias is not None:
+            dbias.copy_(gy.sum(dim=[0] + list(range(2, gy.ndim))))
+        return 0
+
+    def sc_tt_saved_elems(self, plan, B, Ci, Co, ranks):
+        return 0
+
+    def sc_tt_workspace_bytes(self, plan, B, Ci, Co, ranks):
+        return 16
+
+    def sc_forward_tt(self, plan, plan_kept, x, g0, g1, cores, bias, y, saved, B, Ci, Co, ranks, ws, n, st):
+        assert list(ranks) == [g1.shape[0]] + [c.shape[0] for c in cores]          # {r1, r_0 .. r_{d-1}}
+        self._tt_x = x.detach().clone()
+        out = O.contract_tt(x.to(torch.complex64), [g0, g1, *cores]).real
+        y.copy_(out + (bias.reshape(1, -1, *[1] * (out.ndim - 2)) if bias is not None else 0))
+        return 0
+
+    def sc_backward_tt(self, plan, plan_kept, gy, g0, g1, cores, saved, dx, d_g0, d_g1, d_cores, dbias, B, Ci, Co, ranks, ws, n, st):
+        with torch.enable_grad():
+            ps = [t.detach().clone().requires_grad_(True) for t in (self._tt_x, g0, g1, *cores)]
+            O.contract_tt(ps[0].to(torch.complex64), ps[1:]).real.backward(gy)
+        for dst, src in zip([dx, d_g0, d_g1, *d_cores], ps):
+            dst.copy_(src.grad)
+        if dbias is not None:
+            dbias.copy_(gy.sum(dim=[0] + list(range(2, gy.ndim))))
+        return 0
+
+
 _LIB = _Lib()
 
 
@@ -303,3 +351,26 @@ def test_complex_plan_cache_does_not_deadlock(monkeypatch):
     assert out["a"] is out["b"] and out["a"].kept == (8, 6)
     # the contraction plan: kept block (8, 6) of a real-data problem whose last dim is twice as long
     assert out["a"].contract_plan.args == ((8, 12), (8, 12), (8, 6), (8, 6), "forward", 0)
+
+
+@pytest.mark.parametrize("kept", KEPT)
+def test_cp_chain_single_c_call_plumbing(emulated, kept):
+    """`_SpectralConvCPCall`: argument order, output / gradient buffers and which gradient goes where (the chain itself lives in C)."""
+    d, B, Ci, Co, R = len(kept), 2, 3, 4, 5
+    torch.manual_seed(0)
+    params = [torch.randn(B, Ci, *kept), torch.randn(Co, *[1] * d), _c(R), _c(Ci, R), _c(Co, R), *[_c(k, R) for k in kept]]
+    _compare(lambda x, b, lam, ui, uo, *um: sc._SpectralConvCPCall.apply(x, b, _Plan(kept), lam, ui, uo, *um),
+             lambda x, b, lam, ui, uo, *um: O.contract_cp(x.to(torch.complex64), lam, [ui, uo, *um]).real + b,
+             params, torch.randn(B, Co, *kept))
+
+
+@pytest.mark.parametrize("kept", KEPT)
+def test_tt_chain_single_c_call_plumbing(emulated, kept):
+    d, B, Ci, Co = len(kept), 2, 3, 4
+    torch.manual_seed(1)
+    r = [1, 3, 4] + [2 + j for j in range(d - 1)] + [1]
+    params = [torch.randn(B, Ci, *kept), torch.randn(Co, *[1] * d), _c(1, Ci, r[1]), _c(r[1], Co, r[2]),
+              *[_c(r[2 + j], kept[j], r[3 + j]) for j in range(d)]]
+    _compare(lambda x, b, *cores: sc._SpectralConvTTCall.apply(x, b, _Plan(kept), _Plan(kept), *cores),
+             lambda x, b, *cores: O.contract_tt(x.to(torch.complex64), list(cores)).real + b,
+             params, torch.randn(B, Co, *kept))
