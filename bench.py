@@ -293,7 +293,8 @@ def run_layer(args):
     out = {"what": "one Fourier layer (fno_block.py:377-414: SpectralConv + linear skip + GELU + ChannelMLP(0.5) + soft-gating skip + GELU) "
                    "fwd+bwd, eager nn.Module, same shape as the headline step; PyTorch = the same ops on eager + cuFFT/cuBLAS/cuDNN",
            "shape": [B, C, H, W], "ours_ms_per_step": t_ours, "torch_ms_per_step": t_torch, "speedup_vs_torch": t_torch / t_ours,
-           "ours_launches_per_step": launches,
+           "ours_launches_per_step": launches, "mixing_kernel": "k_channel_mix_tc (tcgen05 bf16x3, opt-in)" if nb.uses_tensor_core_mixing()
+           else "k_channel_mix (SIMT fp32, default)",
            "epilogue_only": {"ours_fwd_bwd_ms": t_ours_ep, "torch_fwd_bwd_ms": t_torch_ep, "speedup": t_torch_ep / t_ours_ep,
                              "ours_fwd_ms": t_ours_ep_fwd, "fwd_algorithmic_bytes": fwd_bytes,
                              "fwd_gbs": fwd_bytes / t_ours_ep_fwd / 1e6, "fwd_roofline_frac": fwd_bytes / t_ours_ep_fwd / 1e6 / peak,
@@ -304,11 +305,13 @@ def run_layer(args):
     return 0
 
 
-def layer_block_subprocess(timeout_s=240):
-    """Runs `bench.py --layer-only` in its own process: a fault in the (new) layer kernels cannot touch the headline line."""
+def layer_block_subprocess(timeout_s=240, tensor_cores=False):
+    """Runs `bench.py --layer-only` in its own process: a fault in the (new) layer kernels cannot touch the headline line.
+    tensor_cores: the opt-in tcgen05 variant of the mixing kernel (SC_MIX_TC=1) instead of the default exact-fp32 SIMT kernel."""
     try:
+        env = dict(os.environ, SC_MIX_TC="1" if tensor_cores else "0")
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--layer-only"], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                           text=True, timeout=timeout_s)
+                           text=True, timeout=timeout_s, env=env)
         for ln in r.stdout.splitlines():
             if ln.startswith("LAYER_JSON "):
                 return json.loads(ln[len("LAYER_JSON "):])
@@ -672,6 +675,7 @@ def run_ours(args):
     torch_gpu = None
     configs = None
     fourier_layer = None
+    fourier_layer_tc = None
     if rank == 0 and world == 1 and not args.no_configs:
         # the reference op sequence on PyTorch + cuFFT/cuBLAS on this GPU, same shapes, eager -- the ">= 1.5x" denominator;
         # ours eager (nn.Module) next to it, and the graph-replayed headline step
@@ -706,6 +710,8 @@ def run_ours(args):
                 torch.cuda.synchronize(dev)
         torch.cuda.empty_cache()
         fourier_layer = layer_block_subprocess()
+        # the same block with the mixing launches on the opt-in tcgen05 kernel (never run on hardware before this driver run)
+        fourier_layer_tc = layer_block_subprocess(tensor_cores=True)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times, cores, sample_b = cpu_oracle_step_time(steps=5, warmup=1, max_seconds=15.0)
@@ -741,6 +747,7 @@ def run_ours(args):
             "torch_gpu_baseline": torch_gpu,
             "configs": configs,
             "fourier_layer": fourier_layer,
+            "fourier_layer_tensor_cores": fourier_layer_tc,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -247,6 +247,10 @@ int sc_channel_mix_act_backward(const float* gout, const float* pre, int act, co
                                 sc_stream stream);
 int sc_channel_mix_weight_grad(const float* gpre, const float* in, float* dw, int32_t batch, int32_t in_channels, int32_t out_channels,
                                int64_t n_points, sc_stream stream);
+/* sc_channel_mix on the tensor cores (tcgen05 bf16x3, activations as a tensor-memory A operand; Ci <= 256, Co <= 128): OPT-IN --
+ * the kernel was written without hardware access, the exact-fp32 SIMT kernel stays the default.  Also enabled by SC_MIX_TC=1. */
+int sc_layer_set_tensor_cores(int enable);
+int sc_layer_uses_tensor_cores(void);
 /* Elementwise helpers of the same layer: out[i] = op(a[i], b[i]).
  *   SC_POINTWISE_TANH           tanh(a)             the "tanh" stabilizer in front of the conv (fno_block.py:386-390)
  *   SC_POINTWISE_TANH_BACKWARD  a * (1 - b*b)       a = upstream gradient, b = tanh(x)

@@ -10,4 +10,4 @@ from .data_parallel import GradientAllReducer, PeerGradientAllReducer  # noqa: F
 
 __version__ = "0.1.0"
 from .fno_block import (ChannelMLP, Flattened1dConv, FNOBlocks, SoftGating, channel_mix,  # noqa: F401
-                        skip_connection)
+                        set_tensor_core_mixing, skip_connection, uses_tensor_core_mixing)

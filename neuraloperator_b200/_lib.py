@@ -91,6 +91,8 @@ SIGNATURES = {
                                             c_i32, c_i32, c_i64, c_void_p]),
     "sc_channel_mix_weight_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i64, c_void_p]),
     "sc_pointwise": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "sc_layer_set_tensor_cores": (c_int, [c_int]),
+    "sc_layer_uses_tensor_cores": (c_int, []),
     # host checks of the layer kernels' tile functions (tests only)
     "sc_hostcheck_channel_mix": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                          c_void_p, c_i32, c_i32, c_i32, c_i64]),

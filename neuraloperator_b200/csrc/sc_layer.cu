@@ -22,11 +22,14 @@
 // host buffers, which is how tests/test_layer_cpu.py checks the index arithmetic of the very code the GPU executes.
 #include <cuda_fp16.h>
 
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "sc_plan.h"
+#include "sc_umma.cuh"
 
 namespace sc {
 
@@ -162,6 +165,165 @@ __global__ void __launch_bounds__(MIX_THREADS) k_channel_mix(MixArgs a) {
     __syncthreads();
   }
   mix_store(a, b, o0, p0, tid, acc);
+}
+
+// =====================================================================================================================
+// 1b. the same op on the tensor cores (tcgen05, bf16x3) -- OPT-IN (sc_layer_set_tensor_cores / SC_MIX_TC=1), never run on hardware
+// =====================================================================================================================
+// D[128 points x Np] = A[128 points x Kp] * W[Np x Kp]^T per tile, built on the library's validated bring-up kernel for a tensor-memory
+// A operand (`k_umma_selftest_ts`, sc_fast.cu): thread <-> point <-> TMEM lane, so every global access of the kernel is a coalesced
+// 128-byte row (consecutive lanes, consecutive points of one channel).  Per tile: each thread loads the Kp channel values of its
+// point, splits them into bf16 hi / lo pairs and writes them with tcgen05.st as the A operand (no shared-memory staging of the
+// activations at all); W is split once per CTA into two K-major SWIZZLE_128B images (hi, lo) in shared memory; one thread issues
+// D = A_hi W_hi + A_lo W_hi + A_hi W_lo (3 x Kp/16 MMAs, fp32 accumulation in TMEM); the epilogue reads D back with tcgen05.ld
+// (thread <-> point again) and applies bias / add / gate / activation on the way to global memory.  Tensor memory: D | A_hi | A_lo =
+// Np + Kp columns (128 at C = 64: four CTAs per SM).  All waits are the library's bounded mbarrier wait (trap after 2 s, no hang).
+using namespace umma;
+
+constexpr int TC_THREADS = 128;
+
+struct MixTcArgs {
+  MixArgs m;
+  int Np, Kp;                  // Co padded to 16, Ci padded to 64
+  long long tiles_per_batch, n_tiles;
+  uint32_t tmem_cols, col_ahi, col_alo;
+};
+
+__global__ void __launch_bounds__(TC_THREADS) k_channel_mix_tc(MixTcArgs a) {
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const MixArgs& m = a.m;
+  const int Np = a.Np, Kp = a.Kp;
+  uint8_t* sBhi = tc_smem;
+  uint8_t* sBlo = tc_smem + (size_t)Np * Kp * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_base, a.tmem_cols);
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+  for (int idx = tid; idx < Np * Kp; idx += TC_THREADS) {
+    const int o = idx / Kp, i = idx % Kp;
+    const float w = (o < m.Co && i < m.Ci) ? m.w[(long long)o * m.w_so + (long long)i * m.w_si] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+    const uint32_t off = sw128_offset(o, i, Np);
+    *reinterpret_cast<__nv_bfloat16*>(sBhi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(sBlo + off) = lo;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  const uint32_t idesc = idesc_bf16(128, Np);
+  uint32_t phase = 0;
+  for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int b = (int)(t / a.tiles_per_batch);
+    const long long p = (t % a.tiles_per_batch) * 128 + tid;
+    const bool p_ok = p < m.P;
+    const float* in_p = m.in + (long long)b * m.Ci * m.P + p;             // dereferenced only when p_ok
+    // ---- A operand: my point's channel values -> bf16 hi / lo pairs -> tensor memory ----
+    for (int c0 = 0; c0 < Kp; c0 += 32) {
+      float xv[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int i = c0 + e;
+        xv[e] = (p_ok && i < m.Ci) ? in_p[(long long)i * m.P] : 0.f;
+      }
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) split2_bf16(xv[2 * e], xv[2 * e + 1], hi[e], lo[e]);
+      tmem_st16(tmem + lane_base + a.col_ahi + (uint32_t)(c0 >> 1), hi);
+      tmem_st16(tmem + lane_base + a.col_alo + (uint32_t)(c0 >> 1), lo);
+    }
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    // ---- D = A_hi W_hi + A_lo W_hi + A_hi W_lo ----
+    if (tid == 0) {
+      for (int ks = 0; ks < Kp / 16; ++ks) {
+        const int slab = ks >> 2, kk = ks & 3;
+        const uint32_t boff = (uint32_t)(slab * Np * 128 + kk * 32);
+        const uint64_t dhi = smem_desc_sw128(smem_u32(sBhi) + boff);
+        const uint64_t dlo = smem_desc_sw128(smem_u32(sBlo) + boff);
+        mma_bf16_ts(tmem, tmem + a.col_ahi + (uint32_t)(ks * 8), dhi, idesc, ks > 0);
+        mma_bf16_ts(tmem, tmem + a.col_alo + (uint32_t)(ks * 8), dhi, idesc, true);
+        mma_bf16_ts(tmem, tmem + a.col_ahi + (uint32_t)(ks * 8), dlo, idesc, true);
+      }
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    tc_fence_after_sync();
+    // ---- epilogue: D[my point, :] -> + bias + add + gate * gated -> activation -> global ----
+    for (int c = 0; c < Np; c += 16) {
+      float v[16];
+      tmem_ld16(tmem + lane_base + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (p_ok) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int o = c + e;
+          if (o < m.Co) {
+            const long long at = ((long long)b * m.Co + o) * m.P + p;
+            float r = v[e];
+            if (m.bias != nullptr) r += m.bias[o];
+            if (m.add != nullptr) r += m.add[at];
+            if (m.gated != nullptr) r = fmaf(m.gate != nullptr ? m.gate[o] : 1.f, m.gated[at], r);
+            if (m.pre_out != nullptr) m.pre_out[at] = r;
+            m.out[at] = act_apply(m.act, r);
+          }
+        }
+      }
+    }
+    tc_fence_before_sync();
+    __syncthreads();                 // every warp has read D and the MMAs have consumed A: both regions are free for the next tile
+    tc_fence_after_sync();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, a.tmem_cols);
+}
+
+static std::atomic<int> g_mix_tc{-1};      // -1: read SC_MIX_TC on first use
+static bool mix_tc_enabled() {
+  int v = g_mix_tc.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = std::getenv("SC_MIX_TC");
+    v = (e != nullptr && std::atoi(e) == 1) ? 1 : 0;
+    g_mix_tc.store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
+}
+static bool mix_tc_can(const MixArgs& a) {
+  return a.Ci >= 1 && a.Ci <= 256 && a.Co >= 1 && a.Co <= 128 && a.B >= 1 && a.P >= 1;
+}
+static bool launch_channel_mix_tc(const MixArgs& m, cudaStream_t st) {
+  MixTcArgs a{};
+  a.m = m;
+  a.Np = (m.Co + 15) / 16 * 16;
+  a.Kp = (m.Ci + 63) / 64 * 64;
+  a.tiles_per_batch = (m.P + 127) / 128;
+  a.n_tiles = a.tiles_per_batch * m.B;
+  a.col_ahi = (uint32_t)a.Np;
+  a.col_alo = (uint32_t)(a.Np + a.Kp / 2);
+  const uint32_t need = (uint32_t)(a.Np + a.Kp);
+  a.tmem_cols = 32;
+  while (a.tmem_cols < need) a.tmem_cols *= 2;             // power of two, <= 512 (Np <= 128, Kp <= 256: 384 -> 512)
+  const size_t smem = (size_t)2 * a.Np * a.Kp * 2 + 1024;
+  if (smem > 48 * 1024 &&          // (per device and cheap: set whenever the default 48 KB limit is exceeded)
+      !cuda_ok(cudaFuncSetAttribute(k_channel_mix_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+               "cudaFuncSetAttribute(k_channel_mix_tc)"))
+    return false;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long ctas_per_sm = 512 / a.tmem_cols;         // what tensor memory lets be resident
+  long long grid = (long long)sms * (ctas_per_sm < 1 ? 1 : ctas_per_sm);
+  if (grid > a.n_tiles) grid = a.n_tiles;
+  k_channel_mix_tc<<<(unsigned)grid, TC_THREADS, smem, st>>>(a);
+  count_launch();
+  return cuda_ok(cudaGetLastError(), "k_channel_mix_tc launch");
 }
 
 static void host_channel_mix(const MixArgs& a) {
@@ -397,6 +559,7 @@ static bool grid_ok(const Grid3& g, const char* what) {
 
 static bool launch_channel_mix(const MixArgs& a, cudaStream_t st) {
   if (a.B <= 0 || a.Co <= 0 || a.P <= 0) return true;
+  if (mix_tc_enabled() && mix_tc_can(a)) return launch_channel_mix_tc(a, st);
   const Grid3 g = mix_grid(a);
   if (!grid_ok(g, "sc_channel_mix")) return false;
   k_channel_mix<<<dim3((unsigned)g.x, (unsigned)g.y, (unsigned)g.z), MIX_THREADS, 0, st>>>(a);
@@ -499,6 +662,13 @@ int sc_channel_mix_weight_grad(const float* gpre, const float* in, float* dw, in
   SC_TRY(launch_channel_weight_grad(a, static_cast<cudaStream_t>(stream)));
   return 0;
 }
+
+int sc_layer_set_tensor_cores(int enable) {
+  g_mix_tc.store(enable != 0 ? 1 : 0, std::memory_order_relaxed);
+  return 0;
+}
+
+int sc_layer_uses_tensor_cores(void) { return mix_tc_enabled() ? 1 : 0; }
 
 int sc_pointwise(int op, const float* a, const float* b, float* out, int64_t n, sc_stream stream) {
   SC_REQUIRE(op == SC_POINTWISE_TANH || op == SC_POINTWISE_TANH_BACKWARD || op == SC_POINTWISE_ROUND_HALF, "sc_pointwise: unknown op");

@@ -34,6 +34,16 @@ def _require_device_tensor(t: torch.Tensor, what: str):
         raise TypeError(f"{what} must be float32 (full precision, real data), got {t.dtype}")
 
 
+def set_tensor_core_mixing(enable: bool) -> None:
+    """Route `channel_mix` (forward and input gradient; Ci <= 256, Co <= 128) through the tcgen05 bf16x3 kernel instead of the exact
+    fp32 SIMT kernel.  OPT-IN: that kernel was written without hardware access (also: SC_MIX_TC=1 in the environment)."""
+    _lib.check(_lib.load().sc_layer_set_tensor_cores(int(bool(enable))), "sc_layer_set_tensor_cores")
+
+
+def uses_tensor_core_mixing() -> bool:
+    return bool(_lib.load().sc_layer_uses_tensor_cores())
+
+
 def _launch_channel_mix(x, weight, w_stride_o, w_stride_i, bias, add, gate, gated, act, out, pre, B, Ci, Co, P):
     lib = _lib.load()
     dev = out.device
