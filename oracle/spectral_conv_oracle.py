@@ -620,3 +620,36 @@ def spectral_conv_forward_reduced(x: torch.Tensor, weight: Weight, bias: Optiona
         out_spec[..., -1].imag.zero_()                                       # :555-556
     y = torch.fft.irfft(out_spec, n=out_grid[-1], dim=-1, norm=fft_norm)
     return y + bias if bias is not None else y
+
+
+# --------------------------------------------------------------------------------------------------
+# (6) the two transforms on their own (what sc_analyze / sc_synthesize compute), for CPU emulation of the device primitives in
+#     host-logic tests: the same torch.fft statements as `spectral_conv_forward` (1), split at the contraction
+# --------------------------------------------------------------------------------------------------
+def analyze_modes(x: torch.Tensor, plans: Sequence[DimPlan], fft_norm: str = "forward") -> torch.Tensor:
+    """rfftn + fftshift + x[slices_x] as a gather (:443-449, :500-519): (B, C, *grid) real -> (B, C, *kept) complex64."""
+    d = len(plans)
+    xm = torch.fft.rfftn(x, norm=fft_norm, dim=list(range(-d, 0)))
+    for j, p in enumerate(plans):
+        xm = _gather(xm, 2 + j, p.in_bins)
+    return xm.to(torch.cfloat)
+
+
+def synthesize_modes(ym: torch.Tensor, plans: Sequence[DimPlan], out_grid: Sequence[int], fft_norm: str = "forward") -> torch.Tensor:
+    """scatter + ifftshift + ifftn(leading) + zero Im(DC / Nyquist) + irfft (:460-462, :520-559): (B, C, *kept) -> (B, C, *out_grid)."""
+    B, Co = ym.shape[:2]
+    d = len(plans)
+    dims = list(range(-d, 0))
+    out_spec = torch.zeros([B, Co] + [p.spec for p in plans], dtype=torch.cfloat)
+    index = [torch.arange(B).view(-1, *[1] * (d + 1)), torch.arange(Co).view(1, -1, *[1] * d)]
+    for j, p in enumerate(plans):
+        shape = [1] * (d + 2)
+        shape[2 + j] = -1
+        index.append(torch.as_tensor(p.in_bins, dtype=torch.long).view(shape))
+    out_spec = out_spec.index_put(tuple(index), ym)
+    if d > 1:
+        out_spec = torch.fft.ifftn(out_spec, s=list(out_grid[:-1]), dim=dims[:-1], norm=fft_norm)
+    out_spec[..., 0].imag.zero_()
+    if out_grid[-1] % 2 == 0:
+        out_spec[..., -1].imag.zero_()
+    return torch.fft.irfft(out_spec, n=out_grid[-1], dim=-1, norm=fft_norm)
