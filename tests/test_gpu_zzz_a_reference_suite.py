@@ -4,7 +4,7 @@
 resolution scaling x modes), the same assertions.  Differences: tensors live on the device; the dense twin gets the factorized conv's
 reconstructed weight by `copy_` (the reference swaps in a tltorch tensor); `assert_close` uses the parity tolerance of this repo
 (1e-4 of max|ref|, contract 1e-3) instead of torch's fp32 defaults, because the transforms run as bf16x3 / fp32 table products.
-(Named zzzz: added after the round's GPU minutes were spent, so it runs after the tiers that were validated on hardware.)"""
+(Named zzz_a: added after the round's GPU minutes were spent, so it runs after the tiers that were validated on hardware.)"""
 import pytest
 import torch
 

@@ -4,7 +4,7 @@ separable x 1-4 dims x real / complex; Hermitian flag x dims x even / odd sizes 
 module's own host logic -- plan lookup, weight slicing, which chain runs, operand strides, mutable n_modes, output grids -- with the
 device primitives emulated by the oracle's torch.fft statements of the two transforms and by einsums for the contractions.  Where the
 live reference is importable, every result is ALSO compared with the unmodified reference class on the same weights.
-The GPU twin of this file is tests/test_gpu_zzzz_reference_suite.py."""
+The GPU twin of this file is tests/test_gpu_zzz_a_reference_suite.py."""
 import contextlib
 import math
 
