@@ -7,6 +7,7 @@ from .spectral_conv import (BaseSpectralConv, Plan, SpectralConv, analyze, contr
                             contract_dense_backward, get_plan, spectral_conv_dense, synthesize)
 from .factorized import FactorizedWeight  # noqa: F401
 from .data_parallel import GradientAllReducer, PeerGradientAllReducer  # noqa: F401
+from .integration import use_b200_layers  # noqa: F401
 
 __version__ = "0.1.0"
 from .fno_block import (ChannelMLP, Flattened1dConv, FNOBlocks, SoftGating, channel_mix,  # noqa: F401

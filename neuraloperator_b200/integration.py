@@ -1,0 +1,67 @@
+"""Switching an existing reference model over to the B200 kernels.
+
+`use_b200_layers(model)` takes an instance of the reference's `neuralop.models.FNO` / `TFNO` (or any module that holds a reference
+`FNOBlocks` / `ChannelMLP`) and replaces, in place, every sub-module this package has a drop-in for:
+
+    neuralop.layers.fno_block.FNOBlocks        -> neuraloperator_b200.FNOBlocks   (SpectralConv + fused layer epilogue)
+    neuralop.layers.channel_mlp.ChannelMLP     -> neuraloperator_b200.ChannelMLP  (lifting / projection: one fused launch per layer)
+
+Parameters are carried over by name (`load_state_dict`: the drop-ins use the reference's parameter names), so a trained checkpoint
+keeps working; the model's own `forward` (positional embedding, domain padding, the loop over layers, fno.py:346-406) stays the
+reference's Python.  Modules are recognised by class NAME and constructor attributes, so this file does not import the reference.
+"""
+import torch.nn.functional as F
+from torch import nn
+
+from .fno_block import ChannelMLP, FNOBlocks
+
+
+def _convert_channel_mlp(ref: nn.Module) -> ChannelMLP:
+    if getattr(ref, "dropout", None) is not None:
+        raise NotImplementedError("ChannelMLP with dropout has no B200 drop-in")
+    new = ChannelMLP(ref.in_channels, out_channels=ref.out_channels, hidden_channels=ref.hidden_channels, n_layers=ref.n_layers,
+                     non_linearity=ref.non_linearity)
+    new.load_state_dict(ref.state_dict())
+    return new
+
+
+def _convert_fno_blocks(ref: nn.Module) -> FNOBlocks:
+    if getattr(ref, "norm", None) is not None:
+        raise NotImplementedError("FNOBlocks with a normalisation layer has no B200 drop-in")
+    rsf = ref.resolution_scaling_factor
+    new = FNOBlocks(
+        ref.in_channels, ref.out_channels, ref.n_modes, resolution_scaling_factor=rsf, n_layers=ref.n_layers,
+        max_n_modes=ref.max_n_modes, fno_block_precision=ref.fno_block_precision, use_channel_mlp=ref.use_channel_mlp,
+        channel_mlp_dropout=ref.channel_mlp_dropout, channel_mlp_expansion=ref.channel_mlp_expansion,
+        non_linearity=ref.non_linearity, stabilizer=ref.stabilizer, norm=None, preactivation=ref.preactivation,
+        fno_skip=ref.fno_skip, conv_bias_kernel=ref.conv_bias_kernel, channel_mlp_skip=ref.channel_mlp_skip,
+        complex_data=ref.complex_data, separable=ref.separable, factorization=ref.factorization, rank=ref.rank,
+        fixed_rank_modes=ref.fixed_rank_modes, implementation=ref.implementation, decomposition_kwargs=ref.decomposition_kwargs,
+        enforce_hermitian_symmetry=getattr(ref, "enforce_hermitian_symmetry", True))
+    state = {}
+    for k, v in ref.state_dict().items():                       # tltorch names its factors `factors.factor_<j>`; accept `factors.<j>` too
+        parts = k.split(".")
+        if len(parts) >= 2 and parts[-2] == "factors" and parts[-1].isdigit():
+            parts[-1] = "factor_" + parts[-1]
+        state[".".join(parts)] = v
+    new.load_state_dict(state)
+    return new
+
+
+_CONVERTERS = {"FNOBlocks": _convert_fno_blocks, "ChannelMLP": _convert_channel_mlp}
+
+
+def use_b200_layers(model: nn.Module) -> nn.Module:
+    """Replaces, in place and recursively, every reference `FNOBlocks` / `ChannelMLP` inside `model` by its B200 drop-in with the same
+    parameters; returns `model`.  Move the model to the GPU afterwards (or before: device and dtype of the parameters are kept)."""
+    for name, child in list(model.named_children()):
+        conv = _CONVERTERS.get(type(child).__name__)
+        if conv is not None and not type(child).__module__.startswith("neuraloperator_b200"):
+            ref_param = next(child.parameters(), None)
+            new = conv(child)
+            if ref_param is not None:
+                new = new.to(ref_param.device)
+            setattr(model, name, new)
+        else:
+            use_b200_layers(child)
+    return model

@@ -140,3 +140,55 @@ def block_oracle_kwargs(meta):
     if "output_shape" in meta["forward"]:
         kw["output_shape"] = meta["forward"]["output_shape"]
     return kw
+
+
+def fno_golden_index():
+    with open(os.path.join(GOLDEN_DIR, "fno_index.json")) as f:
+        return json.load(f)["cases"]
+
+
+def load_fno_golden(name):
+    """Model-level cases (oracle/make_golden_fno.py): meta, {x, gy, y, dx}, params, grads keyed by the reference's parameter names."""
+    meta = fno_golden_index()[name]
+    data = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    io, params, grads = {}, {}, {}
+    for k in data.files:
+        t = torch.from_numpy(data[k])
+        key = k
+        if k.endswith("__c"):
+            t, key = torch.view_as_complex(t.contiguous()), k[:-3]
+        if key.startswith("p__"):
+            params[key[3:].replace("__", ".")] = t
+        elif key.startswith("g__"):
+            grads[key[3:].replace("__", ".")] = t
+        else:
+            io[key] = t
+    return meta, io, params, grads
+
+
+def build_fno_stack(meta, params, device=None):
+    """lifting -> FNOBlocks -> projection from this package's drop-ins, as `FNO.__init__` builds them (fno.py:289-345, defaults:
+    lifting / projection channel ratio 2), holding the golden's parameters.  Returns (modules dict, forward function)."""
+    import neuraloperator_b200 as nb
+    kw = dict(meta["ctor"])
+    hidden, n_layers = kw.pop("hidden_channels"), kw.pop("n_layers")
+    cin, cout, modes = kw.pop("in_channels"), kw.pop("out_channels"), tuple(kw.pop("n_modes"))
+    mods = torch.nn.ModuleDict({
+        "lifting": nb.ChannelMLP(cin, out_channels=hidden, hidden_channels=2 * hidden, n_layers=2),
+        "fno_blocks": nb.FNOBlocks(hidden, hidden, modes, n_layers=n_layers, **kw),
+        "projection": nb.ChannelMLP(hidden, out_channels=cout, hidden_channels=2 * hidden, n_layers=2),
+    })
+    ours = dict(mods.named_parameters())
+    assert sorted(ours) == sorted(k.replace("weight.factors.", "weight.factors.factor_") for k in params), "parameter names differ"
+    with torch.no_grad():
+        for k, v in params.items():
+            ours[k.replace("weight.factors.", "weight.factors.factor_")].copy_(v)
+    if device is not None:
+        mods = mods.to(device)
+
+    def forward(x):
+        x = mods["lifting"](x)
+        for i in range(n_layers):
+            x = mods["fno_blocks"](x, i)
+        return mods["projection"](x)
+    return mods, forward

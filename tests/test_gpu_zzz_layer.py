@@ -178,3 +178,22 @@ def test_block_with_mixed_precision_and_tanh_runs(cuda_device):
         y_full = full(x, 0)
     assert torch.isfinite(y).all() and torch.isfinite(x.grad).all()
     assert rel_err(y, y_full) < 5e-3
+
+
+# ---- model level: the drop-ins stacked as the reference FNO stacks them ----------------------------------------------------------
+@pytest.mark.parametrize("name", ["fno_d1_small", "fno_d2_small", "tfno_d2_small"])
+def test_stacked_drop_ins_match_reference_fno_golden(cuda_device, name):
+    """lifting (ChannelMLP) -> n_layers x FNOBlocks -> projection (ChannelMLP), every piece from this package, against y, dx and every
+    parameter gradient of the unmodified reference `neuralop.models.FNO` / TFNO (oracle/make_golden_fno.py)."""
+    from conftest import build_fno_stack, load_fno_golden
+    meta, io, params, grads = load_fno_golden(name)
+    mods, forward = build_fno_stack(meta, params, device=cuda_device)
+    x = io["x"].to(cuda_device).requires_grad_(True)
+    y = forward(x)
+    y.backward(io["gy"].to(cuda_device))
+    torch.cuda.synchronize()
+    assert rel_err(y, io["y"]) < REL_TOL, "y"
+    assert rel_err(x.grad, io["dx"]) < REL_TOL, "dx"
+    ours = dict(mods.named_parameters())
+    for k, g in grads.items():
+        assert rel_err(ours[k.replace("weight.factors.", "weight.factors.factor_")].grad, g) < 2 * REL_TOL, k

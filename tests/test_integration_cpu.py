@@ -1,0 +1,76 @@
+"""Model-level integration without a GPU (kernels through their host checks, conv through the CPU oracle, as in
+tests/test_block_host_logic.py):
+(1) the drop-ins stacked as the reference `FNO` stacks them (lifting -> n_layers x FNOBlocks -> projection) against goldens minted from
+    the unmodified reference model (oracle/make_golden_fno.py): y, dx, every parameter gradient;
+(2) `neuraloperator_b200.use_b200_layers(model)` on a live reference FNO / TFNO: same outputs and gradients before and after the swap."""
+import pytest
+import torch
+
+import neuraloperator_b200 as nb
+from conftest import build_fno_stack, fno_golden_index, load_fno_golden
+from oracle.load_reference import reference_available
+from test_block_host_logic import host, rel_err  # noqa: F401  (fixture)
+
+
+@pytest.mark.parametrize("name", sorted(fno_golden_index().keys()))
+def test_stacked_drop_ins_match_reference_fno_golden(host, name):  # noqa: F811
+    meta, io, params, grads = load_fno_golden(name)
+    mods, forward = build_fno_stack(meta, params)
+    x = io["x"].clone().requires_grad_(True)
+    y = forward(x)
+    y.backward(io["gy"])
+    assert rel_err(y, io["y"]) < 3e-5 and rel_err(x.grad, io["dx"]) < 3e-5
+    ours = dict(mods.named_parameters())
+    for k, g in grads.items():
+        assert rel_err(ours[k.replace("weight.factors.", "weight.factors.factor_")].grad, g) < 5e-5, k
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("kw", [dict(n_modes=(8, 8), in_channels=2, out_channels=3, hidden_channels=8, n_layers=2),
+                                dict(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, factorization="tucker",
+                                     implementation="factorized", rank=[3, 3, 4, 3]),
+                                dict(n_modes=(10,), in_channels=1, out_channels=1, hidden_channels=4, n_layers=3, stabilizer="tanh",
+                                     fno_skip="soft-gating", channel_mlp_skip="linear")])
+def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
+    import sys
+    sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
+    from make_golden_fno import load_reference_fno
+    fno = load_reference_fno()
+    torch.manual_seed(21)
+    model = fno.FNO(**kw)                                  # default positional embedding (grid) + no padding: stays reference code
+    grid = (16,) * len(kw["n_modes"])
+    x = torch.randn(2, kw["in_channels"], *grid)
+    gy = None
+    xr = x.clone().requires_grad_(True)
+    y_ref = model(xr)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    dx_ref = xr.grad.clone()
+    names = sorted(k for k, _ in model.named_parameters())
+    model.zero_grad(set_to_none=True)
+
+    out = nb.use_b200_layers(model)
+    assert out is model
+    assert type(model.fno_blocks) is nb.FNOBlocks and type(model.lifting) is nb.ChannelMLP and type(model.projection) is nb.ChannelMLP
+    assert sorted(k.replace("factors.factor_", "factors.") for k, _ in model.named_parameters()) == names
+    xo = x.clone().requires_grad_(True)
+    y = model(xo)
+    y.backward(gy)
+    assert rel_err(y, y_ref.detach()) < 3e-5 and rel_err(xo.grad, dx_ref) < 3e-5
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, ref_grads[k.replace("factors.factor_", "factors.")]) < 5e-5, k
+    nb.use_b200_layers(model)                              # idempotent: nothing left to convert
+    assert type(model.fno_blocks) is nb.FNOBlocks
+
+
+def test_unsupported_reference_modules_are_reported():
+    class ChannelMLP(torch.nn.Module):                     # a reference-like ChannelMLP with dropout
+        in_channels = out_channels = hidden_channels = 4
+        n_layers = 2
+        non_linearity = staticmethod(torch.nn.functional.gelu)
+        dropout = torch.nn.ModuleList([torch.nn.Dropout(0.1)])
+    holder = torch.nn.Module()
+    holder.mlp = ChannelMLP()
+    with pytest.raises(NotImplementedError):
+        nb.use_b200_layers(holder)
