@@ -48,6 +48,22 @@ SC_HD float act_grad(int act, float v) {
   }
   return 1.0f;
 }
+// (d0, d1) += a * (b0, b1) as ONE packed instruction: on sm_100 the scalar FFMA issues every other cycle per sub-partition and
+// the two-wide `fma.rn.f32x2` (SASS FFMA2, with `a` as a broadcast scalar operand) is what reaches the full fp32 FMA rate; same
+// round-to-nearest fused multiply-add per element, so the host check (two fmaf) computes bit-identical values.
+SC_HD void fma2(float& d0, float& d1, float a, float b0, float b1) {
+#ifdef __CUDA_ARCH__
+  uint64_t av, bv, cv, dv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a), "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(cv) : "f"(d0), "f"(d1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dv) : "l"(av), "l"(bv), "l"(cv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dv));
+#else
+  d0 = fmaf(a, b0, d0);
+  d1 = fmaf(a, b1, d1);
+#endif
+}
 SC_HD void red_add(float* addr, float v) {
 #ifdef __CUDA_ARCH__
   atomicAdd(addr, v);
@@ -116,9 +132,10 @@ SC_HD void mix_fma(int tid, const float* s_in, const float* s_w, MixAcc& acc) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) xv[j] = s_in[i * MIX_TP + tx + 32 * j];        // consecutive lanes, consecutive banks
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc.v[r][j] = fmaf(wv[r], xv[j], acc.v[r][j]);
+    for (int r = 0; r < 8; ++r) {
+      fma2(acc.v[r][0], acc.v[r][1], wv[r], xv[0], xv[1]);
+      fma2(acc.v[r][2], acc.v[r][3], wv[r], xv[2], xv[3]);
+    }
   }
 }
 
@@ -467,9 +484,10 @@ SC_HD void wg_fma(int tid, const float* s_g, const float* s_x, WgAcc& acc) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) xv[c] = s_x[p * WG_LD + tx * 4 + c];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc.v[r][c] = fmaf(gv[r], xv[c], acc.v[r][c]);
+    for (int r = 0; r < 4; ++r) {
+      fma2(acc.v[r][0], acc.v[r][1], gv[r], xv[0], xv[1]);
+      fma2(acc.v[r][2], acc.v[r][3], gv[r], xv[2], xv[3]);
+    }
   }
 }
 SC_HD void wg_store(const WGradArgs& a, int o0, int i0, int tid, const WgAcc& acc) {
