@@ -261,7 +261,6 @@ def run_layer(args):
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     t_ours = time_cuda(ours_layer, 3, 20)
     t_torch = time_cuda(torch_layer, 3, 20)
-
     # the epilogue alone, forward + backward, the conv output given
     x_fno = torch.randn(B, C, H, W, device=dev)
 
@@ -287,12 +286,34 @@ def run_layer(args):
             x1 = nb.channel_mix(x, prm["w_skip"], add=x_fno, act=_lib.ACT_GELU)
             blk.channel_mlp[0]._forward_fused(x1, gate=prm["gate"], gated=x, final_act=_lib.ACT_GELU)
         t_ours_ep_fwd = time_cuda(ours_ep_fwd, 3, 20)
+    # the same layer step replayed from a CUDA graph (as the headline step is): what is left when the Python / autograd issue time is gone
+    t_graph, graph_err = None, None
+    try:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                ours_layer()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        layer_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(layer_graph):
+            ours_layer()
+        t_graph = time_cuda(layer_graph.replay, 3, 20)
+    except Exception as exc:   # noqa: BLE001 -- reported, the eager numbers stand
+        graph_err = repr(exc)[:200]
+        try:
+            torch.cuda.synchronize(dev)
+        except Exception:   # noqa: BLE001
+            pass
+
     n_bytes = 4 * B * C * H * W
     fwd_bytes = 7 * n_bytes            # f1: x, conv output -> x1 (3); f2: x1 -> h (1.5), h, x -> out (2.5), in units of one (B,C,H,W) pass
     peak, _ = measured_peaks()
     out = {"what": "one Fourier layer (fno_block.py:377-414: SpectralConv + linear skip + GELU + ChannelMLP(0.5) + soft-gating skip + GELU) "
                    "fwd+bwd, eager nn.Module, same shape as the headline step; PyTorch = the same ops on eager + cuFFT/cuBLAS/cuDNN",
            "shape": [B, C, H, W], "ours_ms_per_step": t_ours, "torch_ms_per_step": t_torch, "speedup_vs_torch": t_torch / t_ours,
+           "ours_cuda_graph_ms_per_step": t_graph, "cuda_graph_error": graph_err,
            "ours_launches_per_step": launches, "mixing_kernel": "k_channel_mix_tc (tcgen05 bf16x3, opt-in)" if nb.uses_tensor_core_mixing()
            else "k_channel_mix (SIMT fp32, default)",
            "epilogue_only": {"ours_fwd_bwd_ms": t_ours_ep, "torch_fwd_bwd_ms": t_torch_ep, "speedup": t_torch_ep / t_ours_ep,
