@@ -20,7 +20,8 @@ def tensor_cores():
 
 
 def rel_err(a, ref):
-    a, ref = a.detach().cpu().double(), ref.detach().cpu().double()
+    wide = lambda t: t.detach().cpu().to(torch.complex128 if t.is_complex() else torch.float64)       # noqa: E731
+    a, ref = wide(a), wide(ref)
     return (a - ref).abs().max().item() / max(ref.abs().max().item(), 1e-20)
 
 
