@@ -270,6 +270,13 @@ int sc_hostcheck_channel_mix_act_backward(const float* gout, const float* pre, i
 int sc_hostcheck_channel_mix_weight_grad(const float* gpre, const float* in, float* dw, int32_t batch, int32_t in_channels,
                                          int32_t out_channels, int64_t n_points);
 int sc_hostcheck_pointwise(int op, const float* a, const float* b, float* out, int64_t n);
+/* Dry run of sc_forward_cp / sc_backward_cp (kind 0, ranks[0] = R) or sc_forward_tt / sc_backward_tt (kind 1) for `problem` on a
+ * host-only plan: every primitive launch of the chain is RECORDED instead of executed -- {opcode, n_args, args...} words, pointers as
+ * integers over synthetic buffer addresses (region << 40; regions listed at the definition in csrc/sc_api.cu) -- so that the CPU test
+ * tier can replay the orchestration (which buffer goes where with which strides, in which order) on host arrays against the oracle.
+ * log_out may be NULL to query the size; returns 0 and the word count in *n_words_out.  Test hook: the package never calls it. */
+int sc_hostcheck_chain_log(const sc_problem* problem, int kind, int direction, int32_t batch, int32_t in_channels, int32_t out_channels,
+                           const int32_t* ranks, int64_t* log_out, size_t capacity_words, int64_t* n_words_out);
 
 /* events for the grads_ready hand-over above (timing disabled); sc_stream_wait_event makes `stream` wait for the last record */
 int  sc_event_create(sc_event* event_out);

@@ -100,6 +100,7 @@ SIGNATURES = {
                                                       c_void_p, c_i32, c_i32, c_i64]),
     "sc_hostcheck_channel_mix_weight_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i64]),
     "sc_hostcheck_pointwise": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64]),
+    "sc_hostcheck_chain_log": (c_int, [c_void_p, c_int, c_int, c_i32, c_i32, c_i32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sc_probe_tma_gather": (c_int, [c_void_p, c_i32, c_i32, c_i64, c_void_p, c_void_p]),
     "sc_last_error": (ctypes.c_char_p, []),
     "sc_kernel_launch_count": (ctypes.c_uint64, []),

@@ -944,6 +944,91 @@ int sc_cp_factor_grad(const sc_complex* const* mode_factors, const int32_t* kept
   return 0;
 }
 
+// ---- dry run of the CP / TT chains (test hook) ------------------------------------------------------------------------------
+// The chain entry points below are sequences of primitive launches whose only own logic is WHICH buffer (offset into the saved
+// buffer / workspace / a parameter) goes WHERE with WHICH strides.  With a recorder installed (sc_hostcheck_chain_log) every
+// primitive call of a chain is appended to a log -- opcode, argument count, arguments (pointers as integers) -- instead of being
+// launched, so that the CPU test tier can replay the log on host arrays and compare the result with the oracle: the orchestration
+// is checked without a GPU, the primitives themselves are validated on hardware.
+extern "C++" {
+namespace {
+enum { CH_ANALYZE = 1, CH_SYNTHESIZE, CH_TABLE, CH_PAIR, CH_CP_SCALE, CH_CP_APPLY, CH_CP_DSCALE, CH_CP_FACTOR_GRAD, CH_BIAS_GRAD,
+       CH_CONTRACT_FWD, CH_CONTRACT_BWD };
+thread_local std::vector<int64_t>* t_chain_log = nullptr;
+
+inline int64_t ch_word(const void* ptr) { return (int64_t)reinterpret_cast<uintptr_t>(ptr); }
+inline int64_t ch_word(int64_t v) { return v; }
+inline int64_t ch_word(int v) { return v; }
+inline int64_t ch_word(bool v) { return v ? 1 : 0; }
+inline int64_t ch_word(float v) { int64_t w = 0; std::memcpy(&w, &v, sizeof(float)); return w; }
+template <class... A>
+void ch_log(int op, A... a) {
+  t_chain_log->push_back(op);
+  t_chain_log->push_back((int64_t)sizeof...(A));
+  (t_chain_log->push_back(ch_word(a)), ...);
+}
+
+bool ch_analyze(const Plan* p, const float* images, int64_t n_images, float2* modes_out, bool adjoint, float2* b0, float2* b1,
+                cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_ANALYZE, images, n_images, modes_out, adjoint); return true; }
+  return analyze(p, images, n_images, modes_out, adjoint, b0, b1, st);
+}
+bool ch_synthesize(const Plan* p, const float2* modes_in, int64_t n_images, int n_channels, const float* bias, float* images_out,
+                   bool adjoint, float2* b0, float2* b1, cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_SYNTHESIZE, modes_in, n_images, n_channels, bias, images_out, adjoint); return true; }
+  return synthesize(p, modes_in, n_images, n_channels, bias, images_out, adjoint, b0, b1, st);
+}
+bool ch_table(const float2* T, int64_t sTp, int64_t sTq, bool conjT, const float2* in, float2* out, int64_t O, int P, int Q, int I,
+              cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_TABLE, T, sTp, sTq, conjT, in, out, O, P, Q, I); return true; }
+  return launch_complex_table_gemm_strided(T, sTp, sTq, conjT, in, out, O, P, Q, I, st);
+}
+bool ch_pair(const float2* A, const float2* B, float2* out, int64_t sOp, int64_t sOq, int64_t O, int P, int Q, int I, cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_PAIR, A, B, out, sOp, sOq, O, P, Q, I); return true; }
+  return launch_pair_reduce(A, B, out, sOp, sOq, O, P, Q, I, st);
+}
+bool ch_cp_scale(const float2* const* u, const int* k, int d, const float2* lambda, float2* scale, int R, int64_t M, cudaStream_t st) {
+  if (t_chain_log != nullptr) {
+    ch_log(CH_CP_SCALE, d, u[0], d > 1 ? u[1] : nullptr, d > 2 ? u[2] : nullptr, d > 3 ? u[3] : nullptr, k[0], d > 1 ? k[1] : 0,
+           d > 2 ? k[2] : 0, d > 3 ? k[3] : 0, lambda, scale, R, M);
+    return true;
+  }
+  return launch_cp_scale(u, k, d, lambda, scale, R, M, st);
+}
+bool ch_cp_apply(const float2* in, const float2* scale, float2* out, bool conj_scale, int batch, int64_t per_batch, cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_CP_APPLY, in, scale, out, conj_scale, batch, per_batch); return true; }
+  return launch_cp_apply(in, scale, out, conj_scale, batch, per_batch, st);
+}
+bool ch_cp_dscale(const float2* t, const float2* g, float2* dscale, int batch, int64_t per_batch, cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_CP_DSCALE, t, g, dscale, batch, per_batch); return true; }
+  return launch_cp_dscale(t, g, dscale, batch, per_batch, st);
+}
+bool ch_cp_factor_grad(const float2* const* u, const int* k, int d, const float2* lambda, const float2* dscale, float2* out, int which,
+                       int R, int64_t M, cudaStream_t st) {
+  if (t_chain_log != nullptr) {
+    ch_log(CH_CP_FACTOR_GRAD, d, u[0], d > 1 ? u[1] : nullptr, d > 2 ? u[2] : nullptr, d > 3 ? u[3] : nullptr, k[0], d > 1 ? k[1] : 0,
+           d > 2 ? k[2] : 0, d > 3 ? k[3] : 0, lambda, dscale, out, which, R, M);
+    return true;
+  }
+  return launch_cp_factor_grad(u, k, d, lambda, dscale, out, which, R, M, st);
+}
+bool ch_bias_grad(const float2* gm, float* dbias, int batch, int out_channels, int64_t n_modes, int dc_slot, float inv_scale,
+                  cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_BIAS_GRAD, gm, dbias, batch, out_channels, n_modes, dc_slot, inv_scale); return true; }
+  return launch_bias_grad(gm, dbias, batch, out_channels, n_modes, dc_slot, inv_scale, st);
+}
+bool ch_contract_fwd(const Plan* p, const float2* xm, const float2* w, float2* ym, int B, int Ci, int Co, cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_CONTRACT_FWD, xm, w, ym, B, Ci, Co); return true; }
+  return contract_fwd(p, xm, w, ym, B, Ci, Co, st, false);
+}
+bool ch_contract_bwd(const Plan* p, const float2* xm, const float2* gm, const float2* w, float2* dxm, float2* dw, int B, int Ci, int Co,
+                     cudaStream_t st) {
+  if (t_chain_log != nullptr) { ch_log(CH_CONTRACT_BWD, xm, gm, w, dxm, dw, B, Ci, Co); return true; }
+  return contract_bwd(p, xm, gm, w, dxm, dw, nullptr, B, Ci, Co, st, false);
+}
+}  // namespace
+}  // extern "C++"
+
 // ---- CP-factorized forward / backward as ONE call each (reference _contract_cp, :55-73) -----------------------------------
 // The same launches, in the same order and with the same operands, as the Python-orchestrated chain (`_SpectralConvCP`,
 // neuraloperator_b200/spectral_conv.py), issued from one saved buffer and one workspace.
@@ -1010,13 +1095,13 @@ int sc_forward_cp(const sc_plan* plan, const float* x, const sc_complex* lambda,
   float2* sv = reinterpret_cast<float2*>(saved);
   float2 *xm = sv, *t1 = sv + t.off_t1(), *t2 = sv + t.off_t2(), *scale = sv + t.off_scale();
   float2* ym = w.modes[0];
-  SC_TRY(analyze(p, x, (int64_t)t.B * t.Ci, xm, false, w.buf[0], w.buf[1], st));
-  SC_TRY(launch_cp_scale(u, k, t.d, reinterpret_cast<const float2*>(lambda), scale, t.R, t.M, st));
+  SC_TRY(ch_analyze(p, x, (int64_t)t.B * t.Ci, xm, false, w.buf[0], w.buf[1], st));
+  SC_TRY(ch_cp_scale(u, k, t.d, reinterpret_cast<const float2*>(lambda), scale, t.R, t.M, st));
   // T[p = e, q = i] = U_in[i, e];  pointwise scale;  T[p = o, q = e] = U_out[o, e]
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_in), 1, t.R, false, xm, t1, t.B, t.R, t.Ci, (int)t.M, st));
-  SC_TRY(launch_cp_apply(t1, scale, t2, false, t.B, (int64_t)t.R * t.M, st));
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_out), t.R, 1, false, t2, ym, t.B, t.Co, t.R, (int)t.M, st));
-  SC_TRY(synthesize(p, ym, (int64_t)t.B * t.Co, t.Co, bias, y, false, w.buf[0], w.buf[1], st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(u_in), 1, t.R, false, xm, t1, t.B, t.R, t.Ci, (int)t.M, st));
+  SC_TRY(ch_cp_apply(t1, scale, t2, false, t.B, (int64_t)t.R * t.M, st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(u_out), t.R, 1, false, t2, ym, t.B, t.Co, t.R, (int)t.M, st));
+  SC_TRY(ch_synthesize(p, ym, (int64_t)t.B * t.Co, t.Co, bias, y, false, w.buf[0], w.buf[1], st));
   return 0;
 }
 
@@ -1046,22 +1131,22 @@ int sc_backward_cp(const sc_plan* plan, const float* gy, const sc_complex* lambd
   float2* gm = w.modes[0];
   float2* dxm = w.modes[1];
   const int64_t per = (int64_t)t.R * t.M;
-  SC_TRY(analyze(p, gy, (int64_t)t.B * t.Co, gm, true, w.buf[0], w.buf[1], st));
-  if (dbias != nullptr) SC_TRY(launch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
+  SC_TRY(ch_analyze(p, gy, (int64_t)t.B * t.Co, gm, true, w.buf[0], w.buf[1], st));
+  if (dbias != nullptr) SC_TRY(ch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
   // out side: g2 = U_out^H gm,  dU_out[o, e] = sum conj(t2[b, e, m]) gm[b, o, m]
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_out), 1, t.R, true, gm, a.g2, t.B, t.R, t.Co, (int)t.M, st));
-  SC_TRY(launch_pair_reduce(t2, gm, reinterpret_cast<float2*>(d_u_out), 1, t.R, t.B, t.R, t.Co, (int)t.M, st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(u_out), 1, t.R, true, gm, a.g2, t.B, t.R, t.Co, (int)t.M, st));
+  SC_TRY(ch_pair(t2, gm, reinterpret_cast<float2*>(d_u_out), 1, t.R, t.B, t.R, t.Co, (int)t.M, st));
   // pointwise stage: dscale = sum_b conj(t1) g2,  g1 = g2 conj(scale)
-  SC_TRY(launch_cp_dscale(t1, a.g2, a.dscale, t.B, per, st));
-  SC_TRY(launch_cp_apply(a.g2, scale, a.g1, true, t.B, per, st));
+  SC_TRY(ch_cp_dscale(t1, a.g2, a.dscale, t.B, per, st));
+  SC_TRY(ch_cp_apply(a.g2, scale, a.g1, true, t.B, per, st));
   // in side
-  SC_TRY(launch_pair_reduce(xm, a.g1, reinterpret_cast<float2*>(d_u_in), t.R, 1, t.B, t.Ci, t.R, (int)t.M, st));
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(u_in), t.R, 1, true, a.g1, dxm, t.B, t.Ci, t.R, (int)t.M, st));
-  SC_TRY(synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+  SC_TRY(ch_pair(xm, a.g1, reinterpret_cast<float2*>(d_u_in), t.R, 1, t.B, t.Ci, t.R, (int)t.M, st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(u_in), t.R, 1, true, a.g1, dxm, t.B, t.Ci, t.R, (int)t.M, st));
+  SC_TRY(ch_synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
   // lambda and the mode factors from dscale
-  SC_TRY(launch_cp_factor_grad(u, k, t.d, lam, a.dscale, reinterpret_cast<float2*>(d_lambda), -1, t.R, t.M, st));
+  SC_TRY(ch_cp_factor_grad(u, k, t.d, lam, a.dscale, reinterpret_cast<float2*>(d_lambda), -1, t.R, t.M, st));
   for (int j = 0; j < t.d; ++j)
-    SC_TRY(launch_cp_factor_grad(u, k, t.d, lam, a.dscale, reinterpret_cast<float2*>(d_u_modes[j]), j, t.R, t.M, st));
+    SC_TRY(ch_cp_factor_grad(u, k, t.d, lam, a.dscale, reinterpret_cast<float2*>(d_u_modes[j]), j, t.R, t.M, st));
   return 0;
 }
 
@@ -1149,20 +1234,20 @@ int sc_forward_tt(const sc_plan* plan, const sc_plan* plan_kept, const float* x,
   float2* sv = reinterpret_cast<float2*>(saved);
   float2 *xm = sv, *t1 = sv + t.off_t1(), *wc = sv + t.off_wc();
   float2* ym = w.modes[0];
-  SC_TRY(analyze(p, x, (int64_t)t.B * t.Ci, xm, false, w.buf[0], w.buf[1], st));
+  SC_TRY(ch_analyze(p, x, (int64_t)t.B * t.Ci, xm, false, w.buf[0], w.buf[1], st));
   // A_{d-1} = cores[d-1] (r_{d-1}, k_{d-1});  A_j[(a, m_j), rest] = sum_b C_j[a, m_j, b] A_{j+1}[b, rest];  V = A_0 (r_0, M)
   const float2* cur = reinterpret_cast<const float2*>(cores[t.d - 1]);
   for (int j = t.d - 2; j >= 0; --j) {
     float2* dst = sv + t.off_chain(j);
-    SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(cores[j]), t.r[j + 1], 1, false, cur, dst, 1, t.r[j] * t.k[j],
+    SC_TRY(ch_table(reinterpret_cast<const float2*>(cores[j]), t.r[j + 1], 1, false, cur, dst, 1, t.r[j] * t.k[j],
                                              t.r[j + 1], (int)t.inner(j), st));
     cur = dst;
   }
   // wc[(r, o), m] = sum_s G1[r, o, s] V[s, m];  t1 = xm G0;  dense mode product on the r1 rank channels
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g1), t.r[0], 1, false, cur, wc, 1, t.r1 * t.Co, t.r[0], (int)t.M, st));
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g0), 1, t.r1, false, xm, t1, t.B, t.r1, t.Ci, (int)t.M, st));
-  SC_TRY(contract_fwd(pk, t1, wc, ym, t.B, t.r1, t.Co, st, false));
-  SC_TRY(synthesize(p, ym, (int64_t)t.B * t.Co, t.Co, bias, y, false, w.buf[0], w.buf[1], st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(g1), t.r[0], 1, false, cur, wc, 1, t.r1 * t.Co, t.r[0], (int)t.M, st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(g0), 1, t.r1, false, xm, t1, t.B, t.r1, t.Ci, (int)t.M, st));
+  SC_TRY(ch_contract_fwd(pk, t1, wc, ym, t.B, t.r1, t.Co, st));
+  SC_TRY(ch_synthesize(p, ym, (int64_t)t.B * t.Co, t.Co, bias, y, false, w.buf[0], w.buf[1], st));
   return 0;
 }
 
@@ -1188,27 +1273,86 @@ int sc_backward_tt(const sc_plan* plan, const sc_plan* plan_kept, const float* g
   const float2 *xm = sv, *t1 = sv + t.off_t1(), *wc = sv + t.off_wc();
   float2* gm = w.modes[0];
   float2* dxm = w.modes[1];
-  SC_TRY(analyze(p, gy, (int64_t)t.B * t.Co, gm, true, w.buf[0], w.buf[1], st));
-  if (dbias != nullptr) SC_TRY(launch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
+  SC_TRY(ch_analyze(p, gy, (int64_t)t.B * t.Co, gm, true, w.buf[0], w.buf[1], st));
+  if (dbias != nullptr) SC_TRY(ch_bias_grad(gm, dbias, t.B, t.Co, t.M, p->dc_slot, (float)(1.0 / p->s_inv), st));
   // the two mode GEMMs of the dense backward on the rank channels: g1 = d(t1), dwc = d(wc)
-  SC_TRY(contract_bwd(pk, t1, gm, wc, a.g1, a.dwc, nullptr, t.B, t.r1, t.Co, st, false));
+  SC_TRY(ch_contract_bwd(pk, t1, gm, wc, a.g1, a.dwc, t.B, t.r1, t.Co, st));
   // in side: dG0[0, i, r] = sum conj(xm[b, i, m]) g1[b, r, m];  dxm = g1 G0^H
-  SC_TRY(launch_pair_reduce(xm, a.g1, reinterpret_cast<float2*>(d_g0), t.r1, 1, t.B, t.Ci, t.r1, (int)t.M, st));
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g0), t.r1, 1, true, a.g1, dxm, t.B, t.Ci, t.r1, (int)t.M, st));
-  SC_TRY(synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
+  SC_TRY(ch_pair(xm, a.g1, reinterpret_cast<float2*>(d_g0), t.r1, 1, t.B, t.Ci, t.r1, (int)t.M, st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(g0), t.r1, 1, true, a.g1, dxm, t.B, t.Ci, t.r1, (int)t.M, st));
+  SC_TRY(ch_synthesize(p, dxm, (int64_t)t.B * t.Ci, 0, nullptr, dx, true, w.buf[0], w.buf[1], st));
   // weight side: dG1[(r, o), s] = sum_m conj(V[s, m]) dwc[(r, o), m];  dV = G1^H dwc;  then undo the chain, first axis first
   const float2* v = t.d >= 2 ? sv + t.off_chain(0) : reinterpret_cast<const float2*>(cores[0]);
-  SC_TRY(launch_pair_reduce(v, a.dwc, reinterpret_cast<float2*>(d_g1), 1, t.r[0], 1, t.r[0], t.r1 * t.Co, (int)t.M, st));
+  SC_TRY(ch_pair(v, a.dwc, reinterpret_cast<float2*>(d_g1), 1, t.r[0], 1, t.r[0], t.r1 * t.Co, (int)t.M, st));
   float2* d_a = t.d == 1 ? reinterpret_cast<float2*>(d_cores[0]) : a.da[0];
-  SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(g1), 1, t.r[0], true, a.dwc, d_a, 1, t.r[0], t.r1 * t.Co, (int)t.M, st));
+  SC_TRY(ch_table(reinterpret_cast<const float2*>(g1), 1, t.r[0], true, a.dwc, d_a, 1, t.r[0], t.r1 * t.Co, (int)t.M, st));
   for (int j = 0; j + 1 < t.d; ++j) {
     const float2* a_next = (j + 1 == t.d - 1) ? reinterpret_cast<const float2*>(cores[t.d - 1]) : sv + t.off_chain(j + 1);     // A_{j+1}: (r_{j+1}, inner)
     const int64_t inner = t.inner(j);
-    SC_TRY(launch_pair_reduce(a_next, d_a, reinterpret_cast<float2*>(d_cores[j]), 1, t.r[j + 1], 1, t.r[j + 1], t.r[j] * t.k[j], (int)inner, st));
+    SC_TRY(ch_pair(a_next, d_a, reinterpret_cast<float2*>(d_cores[j]), 1, t.r[j + 1], 1, t.r[j + 1], t.r[j] * t.k[j], (int)inner, st));
     float2* dst = (j + 1 == t.d - 1) ? reinterpret_cast<float2*>(d_cores[t.d - 1]) : a.da[(j + 1) & 1];
-    SC_TRY(launch_complex_table_gemm_strided(reinterpret_cast<const float2*>(cores[j]), 1, t.r[j + 1], true, d_a, dst, 1, t.r[j + 1],
+    SC_TRY(ch_table(reinterpret_cast<const float2*>(cores[j]), 1, t.r[j + 1], true, d_a, dst, 1, t.r[j + 1],
                                              t.r[j] * t.k[j], (int)inner, st));
     d_a = dst;
+  }
+  return 0;
+}
+
+// ---- test hook: the launch sequence of a CP / TT chain for `problem`, recorded instead of executed (no device needed) ------------
+// kind 0 = CP (ranks[0] = R), 1 = TT (ranks = {r1, r_0 .. r_{d-1}}); direction 0 = forward, 1 = backward.  Buffers are given as
+// synthetic addresses (region << 40): 1 x / gy, 2 y / dx, 3 saved, 4 workspace, 5 lambda, 6 u_in / g0, 7 u_out / g1, 8+j mode factor /
+// core j, 12 bias / dbias, 15 d_lambda, 16 d_u_in / d_g0, 17 d_u_out / d_g1, 18+j gradient of mode factor / core j.
+// log_out receives {opcode, n_args, args...} records (see the CH_* enum and the ch_* wrappers); returns the number of words.
+int sc_hostcheck_chain_log(const sc_problem* problem, int kind, int direction, int32_t batch, int32_t in_channels, int32_t out_channels,
+                           const int32_t* ranks, int64_t* log_out, size_t capacity_words, int64_t* n_words_out) {
+  SC_REQUIRE(problem != nullptr && ranks != nullptr && n_words_out != nullptr, "sc_hostcheck_chain_log: null argument");
+  SC_REQUIRE((kind == 0 || kind == 1) && (direction == 0 || direction == 1), "sc_hostcheck_chain_log: bad kind / direction");
+  Plan plan, plan_kept;
+  plan.host_only = true;
+  plan_kept.host_only = true;
+  SC_TRY(build_plan(*problem, &plan));
+  sc_problem pk = *problem;
+  for (int j = 0; j < plan.d; ++j) { pk.n_modes[j] = plan.dim[j].k; pk.max_n_modes[j] = plan.dim[j].k; }
+  SC_TRY(build_plan(pk, &plan_kept));
+  auto at = [](int region) { return reinterpret_cast<void*>((uintptr_t)region << 40); };
+  const sc_complex* modes_in[SC_MAX_DIMS];
+  sc_complex* modes_out[SC_MAX_DIMS];
+  for (int j = 0; j < SC_MAX_DIMS; ++j) { modes_in[j] = static_cast<const sc_complex*>(at(8 + j)); modes_out[j] = static_cast<sc_complex*>(at(18 + j)); }
+  const sc_plan* P = reinterpret_cast<const sc_plan*>(&plan);
+  const sc_plan* PK = reinterpret_cast<const sc_plan*>(&plan_kept);
+  std::vector<int64_t> log;
+  // record 0: what the Python side allocates for this chain (the replay checks every access against these bounds)
+  const size_t saved_elems = kind == 0 ? sc_cp_saved_elems(P, batch, in_channels, out_channels, ranks[0])
+                                       : sc_tt_saved_elems(P, batch, in_channels, out_channels, ranks);
+  const size_t ws_bytes = kind == 0 ? sc_cp_workspace_bytes(P, batch, in_channels, out_channels, ranks[0])
+                                    : sc_tt_workspace_bytes(P, batch, in_channels, out_channels, ranks);
+  log.push_back(0); log.push_back(2); log.push_back((int64_t)saved_elems); log.push_back((int64_t)ws_bytes);
+  t_chain_log = &log;
+  int rc = 0;
+  if (kind == 0 && direction == 0)
+    rc = sc_forward_cp(P, static_cast<const float*>(at(1)), static_cast<const sc_complex*>(at(5)), static_cast<const sc_complex*>(at(6)),
+                       static_cast<const sc_complex*>(at(7)), modes_in, static_cast<const float*>(at(12)), static_cast<float*>(at(2)),
+                       static_cast<sc_complex*>(at(3)), batch, in_channels, out_channels, ranks[0], at(4), ws_bytes, nullptr);
+  else if (kind == 0)
+    rc = sc_backward_cp(P, static_cast<const float*>(at(1)), static_cast<const sc_complex*>(at(5)), static_cast<const sc_complex*>(at(6)),
+                        static_cast<const sc_complex*>(at(7)), modes_in, static_cast<const sc_complex*>(at(3)), static_cast<float*>(at(2)),
+                        static_cast<sc_complex*>(at(15)), static_cast<sc_complex*>(at(16)), static_cast<sc_complex*>(at(17)), modes_out,
+                        static_cast<float*>(at(12)), batch, in_channels, out_channels, ranks[0], at(4), ws_bytes, nullptr);
+  else if (direction == 0)
+    rc = sc_forward_tt(P, PK, static_cast<const float*>(at(1)), static_cast<const sc_complex*>(at(6)), static_cast<const sc_complex*>(at(7)),
+                       modes_in, static_cast<const float*>(at(12)), static_cast<float*>(at(2)), static_cast<sc_complex*>(at(3)), batch,
+                       in_channels, out_channels, ranks, at(4), ws_bytes, nullptr);
+  else
+    rc = sc_backward_tt(P, PK, static_cast<const float*>(at(1)), static_cast<const sc_complex*>(at(6)), static_cast<const sc_complex*>(at(7)),
+                        modes_in, static_cast<const sc_complex*>(at(3)), static_cast<float*>(at(2)), static_cast<sc_complex*>(at(16)),
+                        static_cast<sc_complex*>(at(17)), modes_out, static_cast<float*>(at(12)), batch, in_channels, out_channels, ranks,
+                        at(4), ws_bytes, nullptr);
+  t_chain_log = nullptr;
+  if (rc != 0) return rc;
+  *n_words_out = (int64_t)log.size();
+  if (log_out != nullptr) {
+    SC_REQUIRE(log.size() <= capacity_words, "sc_hostcheck_chain_log: log buffer too small");
+    std::memcpy(log_out, log.data(), log.size() * sizeof(int64_t));
   }
   return 0;
 }
