@@ -307,6 +307,41 @@ def run_layer(args):
         except Exception:   # noqa: BLE001
             pass
 
+    # ---- the layer kernels one by one (standalone launches through the C ABI / the functional op, same tensors) ----
+    kernels = {}
+    try:
+        import ctypes
+        lib = _lib.load()
+        ptr = lambda t_: ctypes.c_void_p(t_.data_ptr()) if t_ is not None else None                     # noqa: E731
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        n_pass = 4 * B * C * H * W                                                                       # bytes of one (B, C, H, W) pass
+        hid = prm["w1"].shape[0]
+        Pn = H * W
+        with torch.no_grad():
+            h_act = nb.channel_mix(x, prm["w1"], prm["b1"], act=_lib.ACT_GELU)
+            gpre = torch.randn(B, C, H, W, device=dev)
+            pre = torch.randn(B, C, H, W, device=dev)
+            gout, dgated = torch.empty_like(gpre), torch.empty_like(gpre)
+            dbias, dgate = torch.empty(C, device=dev), torch.empty(C, device=dev)
+            dx_buf = torch.empty_like(x)
+            dw_buf = torch.empty(C, C, device=dev)
+            gate_flat = prm["gate"].detach().reshape(-1).contiguous()
+            w_skip2 = prm["w_skip"].detach().reshape(C, C).contiguous()
+            cases = {
+                "mix_f1 (x, conv out -> x1: skip GEMM + add + GELU)": (lambda: nb.channel_mix(x, prm["w_skip"], add=x_fno, act=_lib.ACT_GELU), 3.0, 2 * C * C),
+                "mix_fc1 (x1 -> h: GEMM + bias + GELU)": (lambda: nb.channel_mix(x, prm["w1"], prm["b1"], act=_lib.ACT_GELU), 1.0 + hid / C, 2 * C * hid),
+                "mix_fc2 (h, x -> out: GEMM + bias + gate * x + GELU)": (lambda: nb.channel_mix(h_act, prm["w2"], prm["b2"], gate=prm["gate"], gated=x, act=_lib.ACT_GELU), hid / C + 2.0, 2 * C * hid),
+                "act_backward (GELU' + dbias + dgate + d gated)": (lambda: lib.sc_channel_mix_act_backward(ptr(gpre), ptr(pre), _lib.ACT_GELU, ptr(gate_flat), ptr(x), ptr(gout), ptr(dgated), ptr(dbias), ptr(dgate), B, C, Pn, st), 5.0, 0),
+                "input_gradient (W^T gpre)": (lambda: lib.sc_channel_mix(ptr(gpre), ptr(w_skip2), 1, C, None, None, None, None, _lib.ACT_IDENTITY, ptr(dx_buf), None, B, C, C, Pn, st), 2.0, 2 * C * C),
+                "weight_gradient (sum over points of gpre x^T)": (lambda: lib.sc_channel_mix_weight_grad(ptr(gpre), ptr(x), ptr(dw_buf), B, C, C, Pn, st), 2.0, 2 * C * C),
+            }
+            for name, (fn, passes, flops_per_point) in cases.items():
+                ms_k = time_cuda(fn, 3, 20)
+                kb = passes * n_pass
+                kernels[name] = {"ms": ms_k, "algorithmic_bytes": kb, "gbs": kb / ms_k / 1e6, "hbm_frac": kb / ms_k / 1e6 / measured_peaks()[0],
+                                 "tflops": flops_per_point * B * Pn / ms_k / 1e9}
+    except Exception as exc:   # noqa: BLE001
+        kernels["error"] = repr(exc)[:200]
     n_bytes = 4 * B * C * H * W
     fwd_bytes = 7 * n_bytes            # f1: x, conv output -> x1 (3); f2: x1 -> h (1.5), h, x -> out (2.5), in units of one (B,C,H,W) pass
     peak, _ = measured_peaks()
@@ -321,7 +356,7 @@ def run_layer(args):
                              "fwd_gbs": fwd_bytes / t_ours_ep_fwd / 1e6, "fwd_roofline_frac": fwd_bytes / t_ours_ep_fwd / 1e6 / peak,
                              "kernels": "k_channel_mix (SIMT fp32), k_channel_act_backward, k_channel_weight_grad: first hardware run of "
                                         "these kernels is this driver run (written after the round's GPU minutes were spent)"},
-           "max_rel_err_vs_torch_fp32": parity}
+           "kernels": kernels, "max_rel_err_vs_torch_fp32": parity}
     print("LAYER_JSON " + json.dumps(out), flush=True)
     return 0
 
