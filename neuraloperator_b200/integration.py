@@ -5,15 +5,19 @@
 
     neuralop.layers.fno_block.FNOBlocks        -> neuraloperator_b200.FNOBlocks   (SpectralConv + fused layer epilogue)
     neuralop.layers.channel_mlp.ChannelMLP     -> neuraloperator_b200.ChannelMLP  (lifting / projection: one fused launch per layer)
+    neuralop.layers.spectral_convolution.SpectralConv -> neuraloperator_b200.SpectralConv  (wherever the block around it has no
+                                                  drop-in -- norm layers, complex data, dropout: the block stays, its convs move over)
 
 Parameters are carried over by name (`load_state_dict`: the drop-ins use the reference's parameter names), so a trained checkpoint
 keeps working; the model's own `forward` (positional embedding, domain padding, the loop over layers, fno.py:346-406) stays the
 reference's Python.  Modules are recognised by class NAME and constructor attributes, so this file does not import the reference.
 """
-import torch.nn.functional as F
+import warnings
+
 from torch import nn
 
 from .fno_block import ChannelMLP, FNOBlocks
+from .spectral_conv import SpectralConv
 
 
 def _convert_channel_mlp(ref: nn.Module) -> ChannelMLP:
@@ -48,7 +52,28 @@ def _convert_fno_blocks(ref: nn.Module) -> FNOBlocks:
     return new
 
 
-_CONVERTERS = {"FNOBlocks": _convert_fno_blocks, "ChannelMLP": _convert_channel_mlp}
+def _convert_spectral_conv(ref: nn.Module) -> SpectralConv:
+    """A reference `SpectralConv` (spectral_convolution.py:183-570) -> the B200 class with the same configuration and parameters.
+    Used when the block around it cannot be replaced as a whole (norm layers, complex data ...): the hot path still moves over."""
+    stored = list(ref.n_modes)                                   # the reference stores the last dim already halved (:404-415)
+    user_modes = stored if ref.complex_data else stored[:-1] + [(stored[-1] - 1) * 2]
+    rsf = ref.resolution_scaling_factor
+    new = SpectralConv(ref.in_channels, ref.out_channels, tuple(user_modes), complex_data=ref.complex_data,
+                       max_n_modes=list(ref.max_n_modes), bias=ref.bias is not None, separable=ref.separable,
+                       resolution_scaling_factor=rsf, fno_block_precision=ref.fno_block_precision, rank=ref.rank,
+                       factorization=ref.factorization, implementation=ref.implementation,
+                       enforce_hermitian_symmetry=getattr(ref, "enforce_hermitian_symmetry", True), fft_norm=ref.fft_norm)
+    state = {}
+    for k, v in ref.state_dict().items():
+        parts = k.split(".")
+        if len(parts) >= 2 and parts[-2] == "factors" and parts[-1].isdigit():
+            parts[-1] = "factor_" + parts[-1]
+        state[".".join(parts)] = v
+    new.load_state_dict(state)
+    return new
+
+
+_CONVERTERS = {"FNOBlocks": _convert_fno_blocks, "ChannelMLP": _convert_channel_mlp, "SpectralConv": _convert_spectral_conv}
 
 
 def use_b200_layers(model: nn.Module) -> nn.Module:
@@ -58,10 +83,21 @@ def use_b200_layers(model: nn.Module) -> nn.Module:
         conv = _CONVERTERS.get(type(child).__name__)
         if conv is not None and not type(child).__module__.startswith("neuraloperator_b200"):
             ref_param = next(child.parameters(), None)
-            new = conv(child)
+            try:
+                new = conv(child)
+            except NotImplementedError as why:
+                if type(child).__name__ == "SpectralConv":
+                    raise
+                # e.g. a block with norm layers: keep the reference module, move what is inside it (its SpectralConvs) over
+                warnings.warn(f"use_b200_layers: {name} ({type(child).__name__}) stays the reference module: {why}", stacklevel=2)
+                use_b200_layers(child)
+                continue
             if ref_param is not None:
                 new = new.to(ref_param.device)
-            setattr(model, name, new)
+            if isinstance(model, (nn.ModuleList, nn.Sequential)):
+                model[int(name)] = new
+            else:
+                setattr(model, name, new)
         else:
             use_b200_layers(child)
     return model

@@ -64,6 +64,37 @@ def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
     assert type(model.fno_blocks) is nb.FNOBlocks
 
 
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+def test_blocks_without_a_drop_in_keep_the_reference_block_and_swap_its_convs(host):  # noqa: F811
+    """norm="group_norm": the reference FNOBlocks stays (its norm layers have no drop-in), the SpectralConvs inside it and the
+    lifting / projection MLPs move over; outputs and gradients are unchanged."""
+    import sys
+    sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
+    from make_golden_fno import load_reference_fno
+    fno = load_reference_fno()
+    torch.manual_seed(5)
+    model = fno.FNO(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=8, n_layers=2, norm="group_norm", max_n_modes=(10, 8))
+    x = torch.randn(2, 1, 16, 12)
+    xr = x.clone().requires_grad_(True)
+    y_ref = model(xr)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    dx_ref = xr.grad.clone()
+    model.zero_grad(set_to_none=True)
+    nb.use_b200_layers(model)
+    assert type(model.fno_blocks).__module__.startswith("neuralop.")                    # the block is still the reference's
+    assert all(type(c) is nb.SpectralConv for c in model.fno_blocks.convs)              # ... its convs are ours
+    assert type(model.lifting) is nb.ChannelMLP
+    assert model.fno_blocks.convs[0].n_modes == [8, 4] and list(model.fno_blocks.convs[0].max_n_modes) == [10, 8]
+    xo = x.clone().requires_grad_(True)
+    y = model(xo)
+    y.backward(gy)
+    assert rel_err(y, y_ref.detach()) < 3e-5 and rel_err(xo.grad, dx_ref) < 3e-5
+    for k, p in model.named_parameters():
+        assert rel_err(p.grad, ref_grads[k]) < 5e-5, k
+
+
 def test_unsupported_reference_modules_are_reported():
     class ChannelMLP(torch.nn.Module):                     # a reference-like ChannelMLP with dropout
         in_channels = out_channels = hidden_channels = 4
@@ -72,5 +103,6 @@ def test_unsupported_reference_modules_are_reported():
         dropout = torch.nn.ModuleList([torch.nn.Dropout(0.1)])
     holder = torch.nn.Module()
     holder.mlp = ChannelMLP()
-    with pytest.raises(NotImplementedError):
+    with pytest.warns(UserWarning, match="stays the reference module"):
         nb.use_b200_layers(holder)
+    assert type(holder.mlp) is ChannelMLP                  # left in place, and said so
