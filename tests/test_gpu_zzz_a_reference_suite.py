@@ -1,97 +1,26 @@
-"""The reference's OWN test file for this path, `neuralop/layers/tests/test_spectral_convolution.py` (:7-90 `test_SpectralConv`,
-:93-125 `test_SpectralConv2`), restated line by line against `neuraloperator_b200.SpectralConv` on the GPU: the same parameter grid
-(4 factorizations x 2 implementations x separable x 1-4 dims x real / complex data; Hermitian flag x dims x even / odd sizes x
-resolution scaling x modes), the same assertions.  Differences: tensors live on the device; the dense twin gets the factorized conv's
-reconstructed weight by `copy_` (the reference swaps in a tltorch tensor); `assert_close` uses the parity tolerance of this repo
-(1e-4 of max|ref|, contract 1e-3) instead of torch's fp32 defaults, because the transforms run as bf16x3 / fp32 table products.
-(Named zzz_a: added after the round's GPU minutes were spent, so it runs after the tiers that were validated on hardware.)"""
+"""The reference's OWN test file for this path (`neuralop/layers/tests/test_spectral_convolution.py`: `test_SpectralConv` :7-90,
+`test_SpectralConv2` :93-125) against `neuraloperator_b200.SpectralConv` on the GPU: its whole parameter grid (4 factorizations x 2
+implementations x separable x 1-4 dims x real / complex data; Hermitian flag x dims x even / odd sizes x resolution scaling x modes)
+and its assertions, as stated by `suite_factorized_vs_dense` / `suite_real_output_shapes` in tests/test_reference_suite_cpu.py (where
+the same suite runs on CPU with the device primitives emulated and every result is also compared with the live reference class).
+Closeness uses this repo's parity tolerance (1e-4 of max|ref|; contract 1e-3) instead of torch's fp32 defaults: the transforms run as
+bf16x3 / fp32 table products.  (Named zzz_a: added after the round's GPU minutes were spent, so it runs after the tiers that were
+validated on hardware.)"""
 import pytest
 import torch
 
-import neuraloperator_b200 as nb
+from test_reference_suite_cpu import GRID_1, GRID_2, suite_factorized_vs_dense, suite_real_output_shapes
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]
 
 
-def assert_close(a, b, tol=1e-4):
-    assert a.shape == b.shape
-    scale = max(b.abs().max().item(), 1e-20)
-    assert (a - b).abs().max().item() / scale < tol
-
-
-@pytest.mark.parametrize("factorization", ["Dense", "CP", "Tucker", "TT"])
-@pytest.mark.parametrize("implementation", ["factorized", "reconstructed"])
-@pytest.mark.parametrize("separable", [False, True])
-@pytest.mark.parametrize("dim", [1, 2, 3, 4])
-@pytest.mark.parametrize("complex_data", [False, True])
+@pytest.mark.parametrize("factorization,implementation,separable,dim,complex_data", GRID_1)
 def test_SpectralConv(cuda_device, factorization, implementation, separable, dim, complex_data):
-    """Compares factorized and dense convolution output, checks the output size, verifies that dynamically changing the number of
-    Fourier modes doesn't break the conv (reference :7-90)."""
-    torch.manual_seed(0)
-    modes = (10, 8, 6, 6)
-    incremental_modes = (6, 6, 4, 4)
-    dtype = torch.cfloat if complex_data else torch.float32
-
-    conv = nb.SpectralConv(3, 3, modes[:dim], bias=False, implementation=implementation, factorization=factorization,
-                           complex_data=complex_data, separable=separable).to(cuda_device)
-    conv_dense = nb.SpectralConv(3, 3, modes[:dim], bias=False, implementation="reconstructed", factorization=None,
-                                 complex_data=complex_data).to(cuda_device)
-    x = torch.randn(2, 3, *(12,) * dim, dtype=dtype, device=cuda_device)
-
-    assert torch.is_complex(conv.weight)
-    assert torch.is_complex(conv_dense.weight)
-
-    # this closeness test only works if the weights in full form have the same shape
-    if not separable:
-        with torch.no_grad():
-            conv_dense.weight.tensor.copy_(conv.weight.to_tensor())
-
-    res_dense = conv_dense(x)
-    res = conv(x)
-    res_shape = res.shape
-    if not separable:
-        assert_close(res, res_dense)
-
-    # Dynamically reduce the number of modes in Fourier space
-    conv.n_modes = incremental_modes[:dim]
-    res = conv(x)
-    assert res_shape == res.shape
-
-    # Downsample outputs
-    block = nb.SpectralConv(3, 4, modes[:dim], resolution_scaling_factor=0.5).to(cuda_device)
-    x = torch.randn(2, 3, *(12,) * dim, device=cuda_device)
-    res = block(x)
-    assert list(res.shape[2:]) == [12 // 2] * dim
-
-    # Upsample outputs
-    block = nb.SpectralConv(3, 4, modes[:dim], resolution_scaling_factor=2).to(cuda_device)
-    x = torch.randn(2, 3, *(12,) * dim, device=cuda_device)
-    res = block(x)
-    assert res.shape[1] == 4  # Check out channels
-    assert list(res.shape[2:]) == [12 * 2] * dim
+    suite_factorized_vs_dense(cuda_device, factorization, implementation, separable, dim, complex_data, 1e-4)
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("enforce_hermitian_symmetry", [True, False])
-@pytest.mark.parametrize("dim", [1, 2, 3])
-@pytest.mark.parametrize("spatial_size", [8, 9])  # Even and odd: Nyquist handling differs
-@pytest.mark.parametrize("resolution_scaling_factor", [None, 0.5, 2])
-@pytest.mark.parametrize("modes", [(4, 4, 4), (4, 5, 7)])
+@pytest.mark.parametrize("enforce_hermitian_symmetry,dim,spatial_size,resolution_scaling_factor,modes", GRID_2)
 def test_SpectralConv2(cuda_device, enforce_hermitian_symmetry, dim, spatial_size, modes, resolution_scaling_factor):
-    """Reference :93-125."""
-    modes = modes[:dim]
-    size = [spatial_size] * dim
-    if resolution_scaling_factor is None:
-        out_size = size
-    else:
-        out_size = [round(s * resolution_scaling_factor) for s in size]
-
-    conv = nb.SpectralConv(3, 4, modes, enforce_hermitian_symmetry=enforce_hermitian_symmetry, complex_data=False,
-                           resolution_scaling_factor=resolution_scaling_factor).to(cuda_device)
-    x = torch.randn(2, 3, *size, dtype=torch.float32, device=cuda_device)
-    res = conv(x)
+    suite_real_output_shapes(cuda_device, enforce_hermitian_symmetry, dim, spatial_size, resolution_scaling_factor, modes, 1e-4)
     torch.cuda.synchronize()
-
-    assert res.shape == (2, 4, *out_size)
-    assert res.dtype == torch.float32
-    assert not torch.is_complex(res)

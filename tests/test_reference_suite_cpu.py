@@ -84,7 +84,7 @@ def emulated(monkeypatch):
     return lib
 
 
-def assert_close(a, b, tol=2e-5):
+def assert_close(a, b, tol):
     assert a.shape == b.shape
     assert (a - b).abs().max().item() / max(b.abs().max().item(), 1e-20) < tol
 
@@ -104,72 +104,76 @@ def _reference_twin(conv, **ctor):
     return twin
 
 
-@pytest.mark.parametrize("factorization", ["Dense", "CP", "Tucker", "TT"])
-@pytest.mark.parametrize("implementation", ["factorized", "reconstructed"])
-@pytest.mark.parametrize("separable", [False, True])
-@pytest.mark.parametrize("dim", [1, 2, 3, 4])
-@pytest.mark.parametrize("complex_data", [False, True])
-def test_SpectralConv(emulated, factorization, implementation, separable, dim, complex_data):
+FACTORIZATIONS = ["Dense", "CP", "Tucker", "TT"]
+IMPLEMENTATIONS = ["factorized", "reconstructed"]
+GRID_1 = [(f, i, s, d, c) for c in (False, True) for d in (1, 2, 3, 4) for s in (False, True) for i in IMPLEMENTATIONS for f in FACTORIZATIONS]
+GRID_2 = [(h, d, n, r, m) for m in ((4, 4, 4), (4, 5, 7)) for r in (None, 0.5, 2) for n in (8, 9) for d in (1, 2, 3) for h in (True, False)]
+MODES, FEWER_MODES, SIDE = (10, 8, 6, 6), (6, 6, 4, 4), 12
+
+
+def suite_factorized_vs_dense(device, factorization, implementation, separable, dim, complex_data, tol, twin_of=None):
+    """What the reference's `test_SpectralConv` (:7-90) asserts, for one point of its parameter grid, on `device`:
+    a conv in any weight form equals its dense twin holding the reconstructed weight; shrinking `n_modes` at run time keeps the output
+    shape; a conv with resolution_scaling_factor 0.5 / 2 halves / doubles every spatial extent.  twin_of(conv, **ctor) may return the
+    unmodified reference module with the same weight: then every output is compared with it as well."""
     torch.manual_seed(0)
-    modes = (10, 8, 6, 6)
-    incremental_modes = (6, 6, 4, 4)
-    dtype = torch.cfloat if complex_data else torch.float32
-    conv = nb.SpectralConv(3, 3, modes[:dim], bias=False, implementation=implementation, factorization=factorization,
-                           complex_data=complex_data, separable=separable)
-    conv_dense = nb.SpectralConv(3, 3, modes[:dim], bias=False, implementation="reconstructed", factorization=None, complex_data=complex_data)
-    x = torch.randn(2, 3, *(12,) * dim, dtype=dtype)
-    assert torch.is_complex(conv.weight) and torch.is_complex(conv_dense.weight)
-    if not separable:
-        with torch.no_grad():
-            conv_dense.weight.tensor.copy_(conv.weight.to_tensor())
+    modes = MODES[:dim]
+    make = lambda *a, **k: nb.SpectralConv(*a, **k).to(device)                                            # noqa: E731
+    conv = make(3, 3, modes, bias=False, implementation=implementation, factorization=factorization, complex_data=complex_data,
+                separable=separable)
+    dense = make(3, 3, modes, bias=False, implementation="reconstructed", factorization=None, complex_data=complex_data)
+    x = torch.randn(2, 3, *(SIDE,) * dim, dtype=torch.cfloat if complex_data else torch.float32, device=device)
+    assert torch.is_complex(conv.weight) and torch.is_complex(dense.weight)
     with torch.no_grad():
-        res_dense = conv_dense(x)
-        res = conv(x)
-        res_shape = res.shape
+        if not separable:                                   # (the full weights have the same shape only then)
+            dense.weight.tensor.copy_(conv.weight.to_tensor())
+        out = conv(x)
         if not separable:
-            assert_close(res, res_dense)
-        twin = _reference_twin(conv, user_modes=modes[:dim])
+            assert_close(out, dense(x), tol)
+        twin = twin_of(conv, user_modes=modes) if twin_of is not None else None
         if twin is not None:
-            assert_close(res, twin(x))                                   # the unmodified reference, same weight
-        # Dynamically reduce the number of modes in Fourier space
-        conv.n_modes = incremental_modes[:dim]
-        res = conv(x)
-        assert res_shape == res.shape
+            assert_close(out, twin(x.cpu()).to(device), tol)
+        conv.n_modes = FEWER_MODES[:dim]                    # incremental training shrinks the modes at run time
+        fewer = conv(x)
+        assert fewer.shape == out.shape
         if twin is not None:
-            twin.n_modes = incremental_modes[:dim]
-            assert_close(res, twin(x))
-        for factor, want in ((0.5, 12 // 2), (2, 12 * 2)):               # down- / up-sample outputs
-            block = nb.SpectralConv(3, 4, modes[:dim], resolution_scaling_factor=factor)
-            xr = torch.randn(2, 3, *(12,) * dim)
-            res = block(xr)
-            assert res.shape[1] == 4 and list(res.shape[2:]) == [want] * dim
-            twin = _reference_twin(block, user_modes=modes[:dim], resolution_scaling_factor=factor)
+            twin.n_modes = FEWER_MODES[:dim]
+            assert_close(fewer, twin(x.cpu()).to(device), tol)
+        for factor, side in ((0.5, SIDE // 2), (2, SIDE * 2)):
+            scaler = make(3, 4, modes, resolution_scaling_factor=factor)
+            xr = torch.randn(2, 3, *(SIDE,) * dim, device=device)
+            res = scaler(xr)
+            assert res.shape[1] == 4 and list(res.shape[2:]) == [side] * dim
+            twin = twin_of(scaler, user_modes=modes, resolution_scaling_factor=factor) if twin_of is not None else None
             if twin is not None:
-                assert_close(res, twin(xr))
+                assert_close(res, twin(xr.cpu()).to(device), tol)
 
 
-@pytest.mark.parametrize("enforce_hermitian_symmetry", [True, False])
-@pytest.mark.parametrize("dim", [1, 2, 3])
-@pytest.mark.parametrize("spatial_size", [8, 9])
-@pytest.mark.parametrize("resolution_scaling_factor", [None, 0.5, 2])
-@pytest.mark.parametrize("modes", [(4, 4, 4), (4, 5, 7)])
-def test_SpectralConv2(emulated, enforce_hermitian_symmetry, dim, spatial_size, modes, resolution_scaling_factor):
+def suite_real_output_shapes(device, hermitian, dim, side, scaling, modes, tol, with_twin=False):
+    """The reference's `test_SpectralConv2` (:93-125): real float32 output of the right (rounded) size for even / odd grids, with and
+    without the Hermitian flag, at every resolution scaling."""
     modes = modes[:dim]
-    size = [spatial_size] * dim
-    out_size = size if resolution_scaling_factor is None else [round(s * resolution_scaling_factor) for s in size]
-    conv = nb.SpectralConv(3, 4, modes, enforce_hermitian_symmetry=enforce_hermitian_symmetry, complex_data=False,
-                           resolution_scaling_factor=resolution_scaling_factor)
-    x = torch.randn(2, 3, *size, dtype=torch.float32)
+    want = [side] * dim if scaling is None else [round(side * scaling)] * dim
+    conv = nb.SpectralConv(3, 4, modes, enforce_hermitian_symmetry=hermitian, complex_data=False, resolution_scaling_factor=scaling).to(device)
+    x = torch.randn(2, 3, *[side] * dim, dtype=torch.float32, device=device)
     with torch.no_grad():
         res = conv(x)
-    assert res.shape == (2, 4, *out_size)
-    assert res.dtype == torch.float32
-    assert not torch.is_complex(res)
-    if reference_available():
+    assert tuple(res.shape) == (2, 4, *want) and res.dtype == torch.float32 and not torch.is_complex(res)
+    if with_twin and reference_available():
         ref = load_reference_spectral_conv()
-        twin = ref.SpectralConv(3, 4, modes, enforce_hermitian_symmetry=enforce_hermitian_symmetry, complex_data=False,
-                                resolution_scaling_factor=resolution_scaling_factor)
+        twin = ref.SpectralConv(3, 4, modes, enforce_hermitian_symmetry=hermitian, complex_data=False, resolution_scaling_factor=scaling)
         with torch.no_grad():
             twin.weight.tensor.copy_(conv.weight.to_tensor())
             twin.bias.copy_(conv.bias)
-            assert_close(res, twin(x))
+            assert_close(res, twin(x.cpu()).to(device), tol)
+
+
+@pytest.mark.parametrize("factorization,implementation,separable,dim,complex_data", GRID_1)
+def test_SpectralConv(emulated, factorization, implementation, separable, dim, complex_data):
+    suite_factorized_vs_dense(torch.device("cpu"), factorization, implementation, separable, dim, complex_data, 2e-5, twin_of=_reference_twin)
+
+
+@pytest.mark.parametrize("enforce_hermitian_symmetry,dim,spatial_size,resolution_scaling_factor,modes", GRID_2)
+def test_SpectralConv2(emulated, enforce_hermitian_symmetry, dim, spatial_size, modes, resolution_scaling_factor):
+    suite_real_output_shapes(torch.device("cpu"), enforce_hermitian_symmetry, dim, spatial_size, resolution_scaling_factor, modes, 2e-5,
+                             with_twin=True)
