@@ -459,3 +459,24 @@ class FNOBlocks(nn.Module):
         for i in range(self.n_layers):
             self.convs[i].n_modes = n_modes
         self._n_modes = n_modes
+
+    def get_block(self, indices):
+        """One layer of the jointly parametrised block as a module of its own (fno_block.py:466-479): shares the parameters."""
+        if self.n_layers == 1:
+            raise ValueError("A single layer is parametrized, directly use the main class.")
+        return LayerView(self, indices)
+
+    def __getitem__(self, indices):
+        return self.get_block(indices)
+
+
+class LayerView(nn.Module):
+    """`FNOBlocks[i]`: forward(x) = blocks.forward(x, i) (the reference's SubModule, fno_block.py:482-500)."""
+
+    def __init__(self, blocks: FNOBlocks, index: int):
+        super().__init__()
+        self.main_module = blocks
+        self.indices = index
+
+    def forward(self, x, output_shape=None):
+        return self.main_module.forward(x, self.indices, output_shape=output_shape)

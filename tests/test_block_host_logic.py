@@ -186,6 +186,17 @@ def test_no_cpu_path():
         nb.ChannelMLP(4)(torch.randn(1, 4, 8))
 
 
+def test_layer_views_share_the_parameters(host):
+    """`blocks[i]` (fno_block.py:466-500): one layer as a module of its own, same parameters, same result."""
+    meta, io, params, _ = load_block_golden("block_d2_default_mid")
+    blk = _build(meta)
+    with torch.no_grad():
+        assert rel_err(blk[1](io["x"]), blk(io["x"], 1)) == 0.0
+    assert [id(p) for p in blk[0].parameters()] == [id(p) for p in blk.parameters()]
+    with pytest.raises(ValueError):
+        nb.FNOBlocks(4, 4, (4, 4), n_layers=1).get_block(0)
+
+
 def test_n_modes_setter_reaches_every_conv():
     blk = nb.FNOBlocks(4, 4, (8, 8), n_layers=2)
     blk.n_modes = (4, 6)
