@@ -51,13 +51,20 @@ def measured_peaks():
 def ncu_traffic(plan):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused analysis kernel, from the committed ncu launch
     list of this round's build (profiles/r02_launches.csv, `--cache-control none`, summarised in r02_launches_summary.json);
-    None when that file or kernel is absent.  A citation of a committed capture, not a measurement of this run."""
+    None when that file or kernel is absent, or when csrc/sc_fast.cu / sc_umma.cuh no longer hash to what the capture was taken
+    from (`_source_sha1` in the summary).  A citation of a committed capture, not a measurement of this run."""
     if not plan.uses_fast_path() & 1:
         return None
     path = os.path.join(ROOT, "profiles", "r02_launches_summary.json")
     try:
         with open(path) as f:
             d = json.load(f)
+        # staleness guard: the capture is only cited while the kernel sources it was taken from are unchanged
+        import hashlib
+        for fname, sha in d.get("_source_sha1", {}).items():
+            with open(os.path.join(ROOT, "neuraloperator_b200", "csrc", fname), "rb") as src:
+                if hashlib.sha1(src.read()).hexdigest() != sha:
+                    return None
         k = d.get("k_fused_analysis2") or d["k_fused_analysis"]
         return (k["dram_read_mb"] + k["dram_write_mb"]) * 1e6
     except Exception:
