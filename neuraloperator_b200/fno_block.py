@@ -8,8 +8,9 @@ semantics (fno_block.py:371-453), with everything after the spectral convolution
     f2   h   = gelu( W1 x1 + b1 );  out = act( W2 h + b2 + gate * x )     two launches
 
 instead of one tensor pass per torch op (conv1d, add, gelu, mul, add, gelu ...).  No CPU / PyTorch fallback: the modules raise on
-CPU tensors, and configurations the kernels do not cover (norm layers, complex data, dropout, activations other than GELU,
-conv_bias_kernel > 1) raise `NotImplementedError` at construction.
+CPU tensors, and configurations the kernels do not cover (batch / AdaIN norm, complex data, dropout, activations other than GELU,
+conv_bias_kernel > 1) raise `NotImplementedError` at construction.  `norm="instance_norm"` / `"group_norm"` are composed from the
+same kernels (one statistics pass + one fused affine / add / activation launch per normalisation).
 """
 import ctypes
 import math
@@ -177,6 +178,95 @@ class _Tanh(torch.autograd.Function):
         return dx
 
 
+class _RowSums(torch.autograd.Function):
+    """(sum_p x, sum_p x^2) of every (b, c) row of a (B, C, *S) tensor in ONE pass over x: the reduction half of
+    `k_channel_act_backward` on the tensor viewed as (1, B*C, P) -- with g = gated = x its dbias is sum g and its dgate sum g * gated.
+    Backward: dx = g1[b,c] + 2 g2[b,c] x, the mixing kernel without a mixing term (bias + gate * gated) on the same view."""
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        _require_device_tensor(x, "normalisation input")
+        x = x.contiguous()
+        B, C = x.shape[:2]
+        P = math.prod(x.shape[2:])
+        s1 = torch.empty(B * C, dtype=torch.float32, device=x.device)
+        s2 = torch.empty(B * C, dtype=torch.float32, device=x.device)
+        if x.numel():
+            with torch.cuda.device(x.device):
+                _lib.check(lib.sc_channel_mix_act_backward(_ptr(x), None, ACT_IDENTITY, None, _ptr(x), None, None, _ptr(s1), _ptr(s2),
+                                                           1, B * C, P, _stream_ptr(x.device)), "sc_channel_mix_act_backward (row sums)")
+        else:
+            s1.zero_()
+            s2.zero_()
+        ctx.save_for_backward(x)
+        return s1.view(B, C), s2.view(B, C)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g1, g2):
+        (x,) = ctx.saved_tensors
+        B, C = x.shape[:2]
+        P = math.prod(x.shape[2:])
+        dx = torch.empty_like(x)
+        if x.numel():
+            b = g1.reshape(-1).float().contiguous()
+            g = (2.0 * g2).reshape(-1).float().contiguous()
+            _launch_channel_mix(None, None, 0, 0, b, None, g, x, ACT_IDENTITY, dx, None, 1, 0, B * C, P)
+        return dx
+
+
+def _norm_scale_shift(norm: nn.Module, x: torch.Tensor):
+    """Normalisation of x (B, C, *S) as a per-row affine map  y = scale[b,c] * x + shift[b,c]:  the statistics come from one pass over
+    x (`_RowSums`); everything else is arithmetic on (B, C) tensors, differentiated by autograd (d weight / d bias of a GroupNorm
+    fall out of it).  instance_norm: F.instance_norm without affine / running statistics (normalization_layers.py:60-96);
+    group_norm: nn.GroupNorm(num_groups, C) (fno_block.py:318-326).  Biased variance, eps inside the square root, as both do."""
+    B, C = x.shape[:2]
+    P = math.prod(x.shape[2:])
+    s1, s2 = _RowSums.apply(x)
+    if isinstance(norm, nn.GroupNorm):
+        G = norm.num_groups
+        n = P * (C // G)
+        mean = s1.view(B, G, -1).sum(-1) / n
+        var = (s2.view(B, G, -1).sum(-1) / n - mean * mean).clamp_min(0.0)
+        rstd = torch.rsqrt(var + norm.eps)
+        mean_c, rstd_c = mean.repeat_interleave(C // G, dim=1), rstd.repeat_interleave(C // G, dim=1)
+        scale = rstd_c * norm.weight.view(1, C) if norm.weight is not None else rstd_c
+        shift = -mean_c * scale
+        if norm.bias is not None:
+            shift = shift + norm.bias.view(1, C)
+        return scale, shift
+    mean = s1 / P
+    var = (s2 / P - mean * mean).clamp_min(0.0)
+    rstd = torch.rsqrt(var + norm.eps)
+    return rstd, -mean * rstd
+
+
+def _apply_norm(x, scale, shift, add=None, act=ACT_IDENTITY):
+    """act( scale[b,c] * x + shift[b,c] + add ): ONE launch of the mixing kernel on the (1, B*C, *S) view (gate = scale, bias = shift)."""
+    B, C = x.shape[:2]
+    sp = tuple(x.shape[2:])
+    out = channel_mix(bias=shift.reshape(-1), add=add.reshape(1, B * C, *sp) if add is not None else None, gate=scale.reshape(-1),
+                      gated=x.reshape(1, B * C, *sp), act=act)
+    return out.view(B, C, *sp)
+
+
+class InstanceNorm(nn.Module):
+    """Parameter-free instance normalisation (normalization_layers.py:60-96) for the fused block: statistics per (sample, channel)."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        extra = set(kwargs) - {"eps"}
+        if extra:
+            raise NotImplementedError(f"InstanceNorm: only eps is supported, got {sorted(extra)}")
+        self.eps = float(kwargs.get("eps", 1e-5))
+        self.kwargs = kwargs
+
+    def forward(self, x):
+        scale, shift = _norm_scale_shift(self, x)
+        return _apply_norm(x, scale, shift)
+
+
 # --------------------------------------------------------------------------------------------------
 # parameter containers with the reference's names (state-dict compatible) and fused forwards
 # --------------------------------------------------------------------------------------------------
@@ -312,8 +402,10 @@ class FNOBlocks(nn.Module):
             n_modes = [n_modes]
         self._n_modes = n_modes
         self.n_dim = len(n_modes)
-        if norm is not None:
-            raise NotImplementedError(f"FNOBlocks(norm={norm!r}): normalisation layers are not built")
+        if norm not in (None, "instance_norm", "group_norm"):
+            if norm in ("batch_norm", "ada_in"):
+                raise NotImplementedError(f"FNOBlocks(norm={norm!r}): only instance_norm and group_norm are built")
+            raise ValueError(f"Got norm={norm} but expected None or one of [instance_norm, group_norm, batch_norm, ada_in]")
         if complex_data:
             raise NotImplementedError("FNOBlocks(complex_data=True): the layer epilogue kernels are real-valued "
                                       "(SpectralConv itself supports complex data)")
@@ -343,8 +435,14 @@ class FNOBlocks(nn.Module):
         self.implementation, self.separable, self.preactivation = implementation, separable, preactivation
         self.ada_in_features, self.enforce_hermitian_symmetry = ada_in_features, enforce_hermitian_symmetry
         self.non_linearity = non_linearity
-        self.norm = None
         self.n_norms = 2
+        if norm is None:
+            self.norm = None
+        elif norm == "instance_norm":
+            self.norm = nn.ModuleList([InstanceNorm() for _ in range(n_layers * self.n_norms)])
+        else:   # group_norm: nn.GroupNorm modules as parameter containers (their forward is never called)
+            self.norm = nn.ModuleList([nn.GroupNorm(num_groups=norm_groups, num_channels=self.out_channels)
+                                       for _ in range(n_layers * self.n_norms)])
 
         self.convs = nn.ModuleList([
             conv_module(
@@ -394,11 +492,19 @@ class FNOBlocks(nn.Module):
             return [int(s) for s in conv._output_grid(grid, output_shape)] != grid
         return output_shape is not None and list(output_shape) != grid
 
-    def _fourier_step(self, x, index, output_shape, act):
-        """f1: act( conv(stabilizer(x)) + fno_skip(x) )."""
+    def _fourier_step(self, x, index, output_shape, act, norm=None):
+        """f1: act( norm(conv(stabilizer(x))) + fno_skip(x) )."""
         conv = self.convs[index]
         x_conv = _Tanh.apply(x) if self.stabilizer == "tanh" else x
         x_fno = conv(x_conv, output_shape=output_shape)
+        if norm is not None:
+            # the normalisation is a per-(sample, channel) affine map of the conv output: one pass for its statistics, then ONE launch
+            # for  act( scale * x_fno + shift + skip )  -- the skip is materialised first (its mixing is per channel, the map per row)
+            scale, shift = _norm_scale_shift(norm, x_fno)
+            x_skip = None
+            if self.fno_skips is not None:
+                x_skip = conv.transform(self.fno_skips[index](x), output_shape=output_shape)
+            return _apply_norm(x_fno, scale, shift, add=x_skip, act=act)
         if self.fno_skips is None:
             return x_fno if act == ACT_IDENTITY else channel_mix(add=x_fno, act=act)
         terms = None if self._resamples(conv, x, output_shape) else self._skip_terms(self.fno_skip, self.fno_skips[index], x)
@@ -434,6 +540,11 @@ class FNOBlocks(nn.Module):
         _require_device_tensor(x, "FNOBlocks input")
         x = x.contiguous()
         act = ACT_GELU if index < (self.n_layers - 1) else ACT_IDENTITY
+        if self.norm is not None:
+            x1 = self._fourier_step(x, index, output_shape, act, norm=self.norm[self.n_norms * index])
+            pre = self._mlp_step(x1, x, index, output_shape, ACT_IDENTITY) if self.use_channel_mlp else x1
+            scale, shift = _norm_scale_shift(self.norm[self.n_norms * index + 1], pre)           # fno_block.py:408-412
+            return _apply_norm(pre, scale, shift, act=act)
         x1 = self._fourier_step(x, index, output_shape, act)
         if self.use_channel_mlp:
             return self._mlp_step(x1, x, index, output_shape, act)
@@ -444,8 +555,12 @@ class FNOBlocks(nn.Module):
         """fno_block.py:416-453: activation first, then conv + skip (+ activation unless last), then the channel MLP + skip."""
         _require_device_tensor(x, "FNOBlocks input")
         x = channel_mix(add=x.contiguous(), act=ACT_GELU)
+        if self.norm is not None:                                                                # fno_block.py:421-422
+            x = _apply_norm(x, *_norm_scale_shift(self.norm[self.n_norms * index], x))
         act = ACT_GELU if index < (self.n_layers - 1) else ACT_IDENTITY
         x1 = self._fourier_step(x, index, output_shape, act)
+        if self.norm is not None:                                                                # fno_block.py:444-445
+            x1 = _apply_norm(x1, *_norm_scale_shift(self.norm[self.n_norms * index + 1], x1))
         if self.use_channel_mlp:
             return self._mlp_step(x1, x, index, output_shape, ACT_IDENTITY)
         return x1

@@ -4,7 +4,7 @@ NOT PRODUCT CODE: only `tests/`, `bench.py`'s baseline legs and `oracle/make_gol
 What it restates (reference = neuraloperator @ 93d3f06, paths relative to /root/reference):
 
   * `fno_block_forward`   <- neuralop/layers/fno_block.py:377-414 (`forward_with_postactivation`) and :416-453
-                             (`forward_with_preactivation`), for norm=None, real data, non_linearity=F.gelu
+                             (`forward_with_preactivation`), for norm in {None, instance_norm, group_norm}, real data, non_linearity=F.gelu
   * `_skip`               <- neuralop/layers/skip_connections.py:85-93 (SoftGating.forward), :118-130 (Flattened1dConv.forward),
                              nn.Identity
   * `_channel_mlp`        <- neuralop/layers/channel_mlp.py:92-116 (ChannelMLP.forward, dropout = 0)
@@ -48,6 +48,15 @@ def _channel_mlp(params: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, 
     return h.reshape(size[0], h.shape[1], *size[2:])
 
 
+def _norm(kind: Optional[str], params: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, groups: int = 1) -> torch.Tensor:
+    """InstanceNorm.forward (normalization_layers.py:91-96) / nn.GroupNorm(norm_groups, C) (fno_block.py:318-326)."""
+    if kind == "instance_norm":
+        return F.instance_norm(x)
+    if kind == "group_norm":
+        return F.group_norm(x, groups, params[prefix + ".weight"], params[prefix + ".bias"])
+    raise ValueError(kind)
+
+
 def _transform(x, in_grid, out_grid):
     return x if list(in_grid) == list(out_grid) else O.resample_restated(x, out_grid)
 
@@ -72,8 +81,8 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
                       weight_kind: str = "dense", fno_skip: Optional[str] = "linear", channel_mlp_skip: Optional[str] = "soft-gating",
                       use_channel_mlp: bool = True, stabilizer: Optional[str] = None, preactivation: bool = False,
                       output_shape: Optional[Sequence[int]] = None, resolution_scaling_factor=None,
-                      max_n_modes: Optional[Sequence[int]] = None) -> torch.Tensor:
-    """One Fourier layer: `FNOBlocks.forward(x, index, output_shape)` for norm=None, real data, GELU."""
+                      max_n_modes: Optional[Sequence[int]] = None, norm: Optional[str] = None, norm_groups: int = 1) -> torch.Tensor:
+    """One Fourier layer: `FNOBlocks.forward(x, index, output_shape)` for real data, GELU, norm in {None, instance_norm, group_norm}."""
     grid = list(x.shape[2:])
     rsf = resolution_scaling_factor
     if rsf is not None and not isinstance(rsf, (list, tuple)):
@@ -82,6 +91,8 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
     nonlin = index < n_layers - 1
     if preactivation:
         x = F.gelu(x)                                                           # :419
+        if norm is not None:
+            x = _norm(norm, params, f"norm.{2 * index}", x, norm_groups)         # :421-422
     x_skip_fno = None
     if fno_skip is not None:                                                    # :378-380 / :424-426
         x_skip_fno = _transform(_skip(fno_skip, params, f"fno_skips.{index}", x), grid, out_grid)
@@ -92,13 +103,19 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
     w = conv_weight_from_params(params, index, weight_kind)
     x_fno = O.spectral_conv_forward(xc, w, params.get(f"convs.{index}.bias"), n_modes, max_n_modes=max_n_modes,
                                     output_shape=output_shape, resolution_scaling_factor=rsf)      # :392
+    if norm is not None and not preactivation:
+        x_fno = _norm(norm, params, f"norm.{2 * index}", x_fno, norm_groups)     # :394-395
     y = x_fno + x_skip_fno if x_skip_fno is not None else x_fno                 # :397
     if nonlin:
         y = F.gelu(y)                                                           # :399-400
+    if norm is not None and preactivation:
+        y = _norm(norm, params, f"norm.{2 * index + 1}", y, norm_groups)         # :444-445
     if use_channel_mlp:                                                         # :402-406
         y = _channel_mlp(params, f"channel_mlp.{index}", y)
         if x_skip_mlp is not None:
             y = y + x_skip_mlp
+    if norm is not None and not preactivation:
+        y = _norm(norm, params, f"norm.{2 * index + 1}", y, norm_groups)         # :408-409
     if nonlin and not preactivation:                                            # :411-412 (the pre-activation form ends without it)
         y = F.gelu(y)
     return y

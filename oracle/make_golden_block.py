@@ -51,6 +51,15 @@ CASES = [
     ("block_d2_cp_reconstructed", 2, 6, 6, (16, 12), (8, 6), 2, 0,
      {"factorization": "cp", "implementation": "reconstructed", "rank": 7}, {}),
     ("block_d2_darcy_small", 2, 16, 16, (32, 32), (16, 16), 4, 2, {}, {}),
+    # appended (seeds follow the position in this list: keep the order)
+    ("block_d2_instance_norm_mid", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"norm": "instance_norm"}, {}),
+    ("block_d2_instance_norm_last", 2, 6, 6, (12, 14), (6, 6), 2, 1, {"norm": "instance_norm"}, {}),
+    ("block_d2_group_norm_mid", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"norm": "group_norm"}, {}),
+    ("block_d2_group_norm_3_groups", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"norm": "group_norm", "norm_groups": 3}, {}),
+    ("block_d1_group_norm_preactivation", 2, 4, 4, (30,), (8,), 2, 0, {"norm": "group_norm", "norm_groups": 2, "preactivation": True}, {}),
+    ("block_d3_instance_norm_no_mlp", 1, 4, 4, (6, 8, 10), (4, 4, 4), 2, 0, {"norm": "instance_norm", "use_channel_mlp": False}, {}),
+    ("block_d2_group_norm_upsample_softgating", 2, 4, 4, (10, 12), (6, 6), 2, 0,
+     {"norm": "group_norm", "resolution_scaling_factor": 2, "fno_skip": "soft-gating"}, {}),
 ]
 
 
@@ -66,7 +75,7 @@ def main():
         blk = fb.FNOBlocks(Ci, Co, modes, n_layers=n_layers, **ctor)
         with torch.no_grad():                                   # soft-gating weights start at exactly 1: make them matter
             for pname, p in blk.named_parameters():
-                if "channel_mlp_skips" in pname or (pname.startswith("fno_skips") and p.ndim == len(grid) + 2):
+                if "channel_mlp_skips" in pname or (pname.startswith("fno_skips") and p.ndim == len(grid) + 2) or pname.startswith("norm."):
                     p.add_(0.3 * torch.randn_like(p))
         x = torch.randn(B, Ci, *grid, requires_grad=True)
         y = blk(x, idx, **fkw)

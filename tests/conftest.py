@@ -133,7 +133,8 @@ def block_oracle_kwargs(meta):
     kw = dict(n_modes=meta["n_modes"], n_layers=meta["n_layers"], weight_kind=meta["weight_kind"],
               fno_skip=ctor.get("fno_skip", "linear"), channel_mlp_skip=ctor.get("channel_mlp_skip", "soft-gating"),
               use_channel_mlp=ctor.get("use_channel_mlp", True), stabilizer=ctor.get("stabilizer"),
-              preactivation=ctor.get("preactivation", False), resolution_scaling_factor=ctor.get("resolution_scaling_factor"))
+              preactivation=ctor.get("preactivation", False), resolution_scaling_factor=ctor.get("resolution_scaling_factor"),
+              norm=ctor.get("norm"), norm_groups=ctor.get("norm_groups", 1))
     if "max_n_modes" in ctor:
         from oracle.spectral_conv_oracle import stored_n_modes
         kw["max_n_modes"] = stored_n_modes(ctor["max_n_modes"])

@@ -89,6 +89,17 @@ def rel_err(a, ref):
     return (a.detach() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-20)
 
 
+def grad_err(got, ref, all_refs):
+    """rel_err of one parameter gradient -- unless the reference gradient vanishes identically in exact arithmetic (the conv bias in
+    front of an instance / group norm: the normalisation removes per-channel constants): then both sides are rounding noise, and what
+    is checked is that ours is as negligible as the reference's, on the scale of the case's largest gradient."""
+    scale = max(float(g.abs().max()) for g in all_refs.values())
+    if float(ref.abs().max()) < 1e-5 * scale:
+        assert got.shape == ref.shape
+        return float(got.detach().abs().max()) / scale
+    return rel_err(got, ref)
+
+
 def _our_name(pname):
     return pname.replace("weight.factors.", "weight.factors.factor_")
 
@@ -121,7 +132,7 @@ def test_block_module_matches_reference_golden(host, name):
         p = ours[_our_name(pname)]
         if pname in meta["touched"]:
             assert p.grad is not None, pname
-            assert rel_err(p.grad, grads[pname]) < 3e-5, pname
+            assert grad_err(p.grad, grads[pname], grads) < 3e-5, pname
         else:
             assert p.grad is None, pname
     assert "sc_channel_mix" in host.calls                                                    # the fused kernels' code did the work
@@ -168,12 +179,14 @@ def test_state_dict_round_trip_with_the_reference(host):
 
 
 def test_unsupported_configurations_raise():
-    for kw in (dict(norm="group_norm"), dict(complex_data=True), dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
+    for kw in (dict(norm="batch_norm"), dict(norm="ada_in"), dict(complex_data=True), dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
                dict(non_linearity=torch.nn.functional.relu)):
         with pytest.raises(NotImplementedError):
             nb.FNOBlocks(4, 4, (4, 4), **kw)
     with pytest.raises(ValueError):
         nb.FNOBlocks(4, 4, (4, 4), fno_skip="bogus")
+    with pytest.raises(ValueError):
+        nb.FNOBlocks(4, 4, (4, 4), norm="bogus")
     with pytest.raises(ValueError):
         nb.FNOBlocks(4, 6, (4, 4))                       # soft gating needs in == out channels (skip_connections.py:74-79)
 

@@ -23,6 +23,16 @@ def rel_err(a, ref):
     return (a - ref).abs().max().item() / max(ref.abs().max().item(), 1e-20)
 
 
+def grad_err(got, ref, all_refs):
+    """rel_err of one parameter gradient; a reference gradient that vanishes identically (the conv bias in front of an instance /
+    group norm) is rounding noise on both sides: then ours has to be as negligible, on the scale of the case's largest gradient."""
+    scale = max(float(g.abs().max()) for g in all_refs.values())
+    if float(ref.abs().max()) < 1e-5 * scale:
+        assert got.shape == ref.shape
+        return float(got.detach().abs().max()) / scale
+    return rel_err(got, ref)
+
+
 @pytest.mark.parametrize("B,Ci,Co,grid", [(2, 3, 5, (7,)), (2, 17, 65, (129,)), (3, 70, 130, (3, 11)), (4, 64, 64, (128, 128)),
                                            (2, 32, 16, (16, 16, 16)), (1, 64, 32, (100, 100))])
 @pytest.mark.parametrize("opts", ["plain", "all"])
@@ -106,7 +116,7 @@ def test_block_module_matches_reference_golden(cuda_device, name):
     for pname in meta["touched"]:
         p = ours[_our_name(pname)]
         assert p.grad is not None, pname
-        assert rel_err(p.grad, grads[pname]) < REL_TOL, pname
+        assert grad_err(p.grad, grads[pname], grads) < REL_TOL, pname
 
 
 def test_headline_shape_layer_against_oracle(cuda_device):
