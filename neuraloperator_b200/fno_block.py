@@ -12,9 +12,8 @@ CPU tensors, and configurations the kernels do not cover (batch / AdaIN norm, co
 conv_bias_kernel > 1) raise `NotImplementedError` at construction.  `norm="instance_norm"` / `"group_norm"` are composed from the
 same kernels (one statistics pass + one fused affine / add / activation launch per normalisation).
 """
-import ctypes
 import math
-from typing import List, Optional, Union
+from typing import Union
 
 import torch
 import torch.nn.functional as F

@@ -13,7 +13,6 @@ import torch
 import neuraloperator_b200 as nb
 from neuraloperator_b200 import _lib, fno_block as fb
 from conftest import block_golden_index, load_block_golden
-from oracle import fno_block_oracle as BO
 from oracle import spectral_conv_oracle as O
 from oracle.load_reference import load_reference_spectral_conv, reference_available
 

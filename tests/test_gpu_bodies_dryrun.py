@@ -12,7 +12,6 @@ import ctypes
 import pytest
 import torch
 
-import neuraloperator_b200 as nb
 from neuraloperator_b200 import _lib, spectral_conv as sc
 from oracle import spectral_conv_oracle as O
 from test_block_host_logic import host  # noqa: F401  (fixture: layer kernels -> host checks, conv -> oracle)

@@ -7,7 +7,6 @@ executes -- against plain torch restatements of the reference ops (conv1d with a
 neuralop/layers/fno_block.py:377-414, channel_mlp.py:92-116, skip_connections.py:85-130).  What a CPU cannot check: launch
 configuration, shared-memory races, atomics -- the kernels keep those trivial (two __syncthreads per stage, atomicAdd epilogues)."""
 import ctypes
-import itertools
 
 import pytest
 import torch
