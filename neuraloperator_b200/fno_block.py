@@ -8,9 +8,9 @@ semantics (fno_block.py:371-453), with everything after the spectral convolution
     f2   h   = gelu( W1 x1 + b1 );  out = act( W2 h + b2 + gate * x )     two launches
 
 instead of one tensor pass per torch op (conv1d, add, gelu, mul, add, gelu ...).  No CPU / PyTorch fallback: the modules raise on
-CPU tensors, and configurations the kernels do not cover (batch / AdaIN norm, complex data, dropout, activations other than GELU,
-conv_bias_kernel > 1) raise `NotImplementedError` at construction.  `norm="instance_norm"` / `"group_norm"` are composed from the
-same kernels (one statistics pass + one fused affine / add / activation launch per normalisation).
+CPU tensors, and configurations the kernels do not cover (complex data, dropout, activations other than GELU, conv_bias_kernel > 1)
+raise `NotImplementedError` at construction.  The four `norm` options are composed from the same kernels (one statistics pass + one
+fused affine / add / activation launch per normalisation).
 """
 import math
 from typing import Union
@@ -219,7 +219,9 @@ def _norm_scale_shift(norm: nn.Module, x: torch.Tensor):
     """Normalisation of x (B, C, *S) as a per-row affine map  y = scale[b,c] * x + shift[b,c]:  the statistics come from one pass over
     x (`_RowSums`); everything else is arithmetic on (B, C) tensors, differentiated by autograd (d weight / d bias of a GroupNorm
     fall out of it).  instance_norm: F.instance_norm without affine / running statistics (normalization_layers.py:60-96);
-    group_norm: nn.GroupNorm(num_groups, C) (fno_block.py:318-326).  Biased variance, eps inside the square root, as both do."""
+    group_norm: nn.GroupNorm(num_groups, C) (fno_block.py:318-326); batch_norm: nn.BatchNorm{n}d in training / eval mode incl. the
+    running statistics (:99-158); ada_in: instance statistics with weight / bias from the embedding MLP (:5-57).  Biased variance, eps
+    inside the square root, as all of them do."""
     B, C = x.shape[:2]
     P = math.prod(x.shape[2:])
     s1, s2 = _RowSums.apply(x)
@@ -235,9 +237,37 @@ def _norm_scale_shift(norm: nn.Module, x: torch.Tensor):
         if norm.bias is not None:
             shift = shift + norm.bias.view(1, C)
         return scale, shift
+    if isinstance(norm, BatchNorm):
+        bn = norm.norm                                               # F.batch_norm semantics (torch/nn/modules/batchnorm.py)
+        use_batch = bn.training or not bn.track_running_stats
+        if use_batch:
+            n = B * P
+            mean = s1.sum(0) / n
+            var = (s2.sum(0) / n - mean * mean).clamp_min(0.0)       # biased: what normalises the batch
+            if bn.training and bn.track_running_stats:
+                with torch.no_grad():
+                    bn.num_batches_tracked += 1
+                    m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                    bn.running_mean.mul_(1 - m).add_(m * mean.detach())
+                    bn.running_var.mul_(1 - m).add_(m * var.detach() * (n / max(n - 1, 1)))      # unbiased in the running average
+        else:
+            mean, var = bn.running_mean, bn.running_var
+        scale = torch.rsqrt(var + bn.eps)
+        if bn.weight is not None:
+            scale = scale * bn.weight
+        shift = -mean * scale
+        if bn.bias is not None:
+            shift = shift + bn.bias
+        return scale.view(1, C).expand(B, C), shift.view(1, C).expand(B, C)
     mean = s1 / P
     var = (s2 / P - mean * mean).clamp_min(0.0)
     rstd = torch.rsqrt(var + norm.eps)
+    if isinstance(norm, AdaIN):
+        if norm.embedding is None:
+            raise RuntimeError("AdaIN: update embeddding before running forward")
+        weight, bias = torch.split(norm.mlp(norm.embedding), C, dim=0)
+        scale = rstd * weight.view(1, C)
+        return scale, bias.view(1, C) - mean * scale
     return rstd, -mean * rstd
 
 
@@ -248,6 +278,38 @@ def _apply_norm(x, scale, shift, add=None, act=ACT_IDENTITY):
     out = channel_mix(bias=shift.reshape(-1), add=add.reshape(1, B * C, *sp) if add is not None else None, gate=scale.reshape(-1),
                       gated=x.reshape(1, B * C, *sp), act=act)
     return out.view(B, C, *sp)
+
+
+class BatchNorm(nn.Module):
+    """Parameter container for batch normalisation (normalization_layers.py:99-158): `self.norm` holds weight, bias and the running
+    statistics under the reference's names (a BatchNorm1d: the parameters of BatchNorm{1,2,3}d are the same)."""
+
+    def __init__(self, n_dim: int, num_features: int, **kwargs):
+        super().__init__()
+        self.n_dim, self.num_features, self.kwargs = n_dim, num_features, kwargs
+        self.norm = nn.BatchNorm1d(num_features=num_features, **kwargs)
+
+    def forward(self, x):
+        scale, shift = _norm_scale_shift(self, x)
+        return _apply_norm(x, scale, shift)
+
+
+class AdaIN(nn.Module):
+    """Adaptive instance normalisation (normalization_layers.py:5-57): instance statistics, weight and bias from an embedding through
+    a small MLP (host-sized: embed_dim -> 512 -> 2 C)."""
+
+    def __init__(self, embed_dim, in_channels, mlp=None, eps=1e-5):
+        super().__init__()
+        self.in_channels, self.embed_dim, self.eps = in_channels, embed_dim, eps
+        self.mlp = mlp if mlp is not None else nn.Sequential(nn.Linear(embed_dim, 512), nn.GELU(), nn.Linear(512, 2 * in_channels))
+        self.embedding = None
+
+    def set_embedding(self, x):
+        self.embedding = x.reshape(self.embed_dim,)
+
+    def forward(self, x):
+        scale, shift = _norm_scale_shift(self, x)
+        return _apply_norm(x, scale, shift)
 
 
 class InstanceNorm(nn.Module):
@@ -401,9 +463,7 @@ class FNOBlocks(nn.Module):
             n_modes = [n_modes]
         self._n_modes = n_modes
         self.n_dim = len(n_modes)
-        if norm not in (None, "instance_norm", "group_norm"):
-            if norm in ("batch_norm", "ada_in"):
-                raise NotImplementedError(f"FNOBlocks(norm={norm!r}): only instance_norm and group_norm are built")
+        if norm not in (None, "instance_norm", "group_norm", "batch_norm", "ada_in"):
             raise ValueError(f"Got norm={norm} but expected None or one of [instance_norm, group_norm, batch_norm, ada_in]")
         if complex_data:
             raise NotImplementedError("FNOBlocks(complex_data=True): the layer epilogue kernels are real-valued "
@@ -439,9 +499,13 @@ class FNOBlocks(nn.Module):
             self.norm = None
         elif norm == "instance_norm":
             self.norm = nn.ModuleList([InstanceNorm() for _ in range(n_layers * self.n_norms)])
-        else:   # group_norm: nn.GroupNorm modules as parameter containers (their forward is never called)
+        elif norm == "group_norm":   # nn.GroupNorm modules as parameter containers (their forward is never called)
             self.norm = nn.ModuleList([nn.GroupNorm(num_groups=norm_groups, num_channels=self.out_channels)
                                        for _ in range(n_layers * self.n_norms)])
+        elif norm == "batch_norm":
+            self.norm = nn.ModuleList([BatchNorm(n_dim=self.n_dim, num_features=self.out_channels) for _ in range(n_layers * self.n_norms)])
+        else:
+            self.norm = nn.ModuleList([AdaIN(ada_in_features, out_channels) for _ in range(n_layers * self.n_norms)])
 
         self.convs = nn.ModuleList([
             conv_module(
@@ -470,6 +534,16 @@ class FNOBlocks(nn.Module):
                     for _ in range(n_layers)])
             else:
                 self.channel_mlp_skips = None
+
+    def set_ada_in_embeddings(self, *embeddings):
+        """Sets the embeddings of the AdaIN layers (fno_block.py:354-369): one for all, or one per norm layer."""
+        if self.norm is not None:
+            if len(embeddings) == 1:
+                for norm in self.norm:
+                    norm.set_embedding(embeddings[0])
+            else:
+                for norm, embedding in zip(self.norm, embeddings):
+                    norm.set_embedding(embedding)
 
     # -- helpers ------------------------------------------------------------------------------------
     @staticmethod

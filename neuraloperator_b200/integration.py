@@ -37,6 +37,10 @@ def _convert_fno_blocks(ref: nn.Module) -> FNOBlocks:
             norm = "instance_norm"
         elif kind == "GroupNorm":
             norm, norm_groups = "group_norm", ref.norm[0].num_groups
+        elif kind == "BatchNorm" and not getattr(ref.norm[0], "kwargs", {}):
+            norm = "batch_norm"
+        elif kind == "AdaIN":
+            norm = "ada_in"
         else:
             raise NotImplementedError(f"FNOBlocks with {kind} normalisation layers has no B200 drop-in")
     rsf = ref.resolution_scaling_factor
@@ -44,7 +48,8 @@ def _convert_fno_blocks(ref: nn.Module) -> FNOBlocks:
         ref.in_channels, ref.out_channels, ref.n_modes, resolution_scaling_factor=rsf, n_layers=ref.n_layers,
         max_n_modes=ref.max_n_modes, fno_block_precision=ref.fno_block_precision, use_channel_mlp=ref.use_channel_mlp,
         channel_mlp_dropout=ref.channel_mlp_dropout, channel_mlp_expansion=ref.channel_mlp_expansion,
-        non_linearity=ref.non_linearity, stabilizer=ref.stabilizer, norm=norm, norm_groups=norm_groups, preactivation=ref.preactivation,
+        non_linearity=ref.non_linearity, stabilizer=ref.stabilizer, norm=norm, norm_groups=norm_groups,
+        ada_in_features=ref.ada_in_features, preactivation=ref.preactivation,
         fno_skip=ref.fno_skip, conv_bias_kernel=ref.conv_bias_kernel, channel_mlp_skip=ref.channel_mlp_skip,
         complex_data=ref.complex_data, separable=ref.separable, factorization=ref.factorization, rank=ref.rank,
         fixed_rank_modes=ref.fixed_rank_modes, implementation=ref.implementation, decomposition_kwargs=ref.decomposition_kwargs,
@@ -56,6 +61,10 @@ def _convert_fno_blocks(ref: nn.Module) -> FNOBlocks:
             parts[-1] = "factor_" + parts[-1]
         state[".".join(parts)] = v
     new.load_state_dict(state)
+    if norm == "ada_in":
+        for ours, theirs in zip(new.norm, ref.norm):
+            ours.embedding = theirs.embedding
+    new.train(ref.training)
     return new
 
 

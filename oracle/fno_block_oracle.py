@@ -54,6 +54,14 @@ def _norm(kind: Optional[str], params: Dict[str, torch.Tensor], prefix: str, x: 
         return F.instance_norm(x)
     if kind == "group_norm":
         return F.group_norm(x, groups, params[prefix + ".weight"], params[prefix + ".bias"])
+    if kind == "batch_norm":      # BatchNorm.forward (normalization_layers.py:146-158) in TRAINING mode: batch statistics
+        return F.batch_norm(x, None, None, params[prefix + ".norm.weight"], params[prefix + ".norm.bias"], training=True, eps=1e-5)
+    if kind == "ada_in":          # AdaIN.forward (:51-57): weight, bias = split(mlp(embedding)); group_norm with C groups
+        e = params["ada_in_embedding"]
+        h = F.gelu(F.linear(e, params[prefix + ".mlp.0.weight"], params[prefix + ".mlp.0.bias"]))
+        wb = F.linear(h, params[prefix + ".mlp.2.weight"], params[prefix + ".mlp.2.bias"])
+        C = x.shape[1]
+        return F.group_norm(x, C, wb[:C], wb[C:], eps=1e-5)
     raise ValueError(kind)
 
 

@@ -60,6 +60,9 @@ CASES = [
     ("block_d3_instance_norm_no_mlp", 1, 4, 4, (6, 8, 10), (4, 4, 4), 2, 0, {"norm": "instance_norm", "use_channel_mlp": False}, {}),
     ("block_d2_group_norm_upsample_softgating", 2, 4, 4, (10, 12), (6, 6), 2, 0,
      {"norm": "group_norm", "resolution_scaling_factor": 2, "fno_skip": "soft-gating"}, {}),
+    ("block_d2_batch_norm_mid", 3, 6, 6, (12, 14), (6, 6), 2, 0, {"norm": "batch_norm"}, {}),
+    ("block_d1_batch_norm_last", 3, 4, 4, (30,), (8,), 2, 1, {"norm": "batch_norm"}, {}),
+    ("block_d2_ada_in_mid", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"norm": "ada_in", "ada_in_features": 5}, {}),
 ]
 
 
@@ -77,11 +80,19 @@ def main():
             for pname, p in blk.named_parameters():
                 if "channel_mlp_skips" in pname or (pname.startswith("fno_skips") and p.ndim == len(grid) + 2) or pname.startswith("norm."):
                     p.add_(0.3 * torch.randn_like(p))
+        embedding = None
+        if ctor.get("norm") == "ada_in":
+            embedding = torch.randn(ctor["ada_in_features"])
+            blk.set_ada_in_embeddings(embedding)
         x = torch.randn(B, Ci, *grid, requires_grad=True)
         y = blk(x, idx, **fkw)
         gy = torch.randn_like(y)
         y.backward(gy)
         arrays = {"x": x.detach().numpy(), "gy": gy.numpy(), "y": y.detach().numpy(), "dx": x.grad.numpy()}
+        if embedding is not None:
+            arrays["ada_in_embedding"] = embedding.numpy()
+        for bname, buf in blk.named_buffers():                   # batch norm: the running statistics AFTER this forward
+            arrays["b__" + bname.replace(".", "__")] = buf.detach().numpy()
         pnames, touched = [], []
         for pname, p in blk.named_parameters():
             key = pname.replace(".", "__")

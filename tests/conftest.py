@@ -123,7 +123,7 @@ def load_block_golden(name):
         elif key.startswith("g__"):
             grads[key[3:].replace("__", ".")] = t
         else:
-            io[key] = t
+            io[key] = t                    # x, gy, y, dx; ada_in_embedding; b__<buffer name>: buffers after the forward pass
     return meta, io, params, grads
 
 

@@ -120,11 +120,16 @@ def test_block_module_matches_reference_golden(host, name):
         for pname, val in params.items():
             assert ours[_our_name(pname)].shape == val.shape, pname
             ours[_our_name(pname)].copy_(val)
+    if "ada_in_embedding" in io:
+        blk.set_ada_in_embeddings(io["ada_in_embedding"])
     x = io["x"].clone().requires_grad_(True)
     kw = {k: tuple(v) for k, v in meta["forward"].items()}
     y = blk(x, meta["index"], **kw)
     assert y.dtype == torch.float32 and list(y.shape[2:]) == meta["out_grid"]
     y.backward(io["gy"])
+    for bname, buf in blk.named_buffers():                       # batch norm: running statistics after this (training-mode) forward
+        want = io["b__" + bname.replace(".", "__")]
+        assert rel_err(buf.float(), want.float()) < 2e-5, bname
     assert rel_err(y, io["y"]) < 2e-5, "y"
     assert rel_err(x.grad, io["dx"]) < 2e-5, "dx"
     for pname in meta["params"]:
@@ -178,7 +183,7 @@ def test_state_dict_round_trip_with_the_reference(host):
 
 
 def test_unsupported_configurations_raise():
-    for kw in (dict(norm="batch_norm"), dict(norm="ada_in"), dict(complex_data=True), dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
+    for kw in (dict(complex_data=True), dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
                dict(non_linearity=torch.nn.functional.relu)):
         with pytest.raises(NotImplementedError):
             nb.FNOBlocks(4, 4, (4, 4), **kw)

@@ -105,12 +105,16 @@ def test_block_module_matches_reference_golden(cuda_device, name):
         for pname, val in params.items():
             assert ours[_our_name(pname)].shape == val.shape, pname
             ours[_our_name(pname)].copy_(val.to(cuda_device))
+    if "ada_in_embedding" in io:
+        blk.set_ada_in_embeddings(io["ada_in_embedding"].to(cuda_device))
     x = io["x"].to(cuda_device).requires_grad_(True)
     kw = {k: tuple(v) for k, v in meta["forward"].items()}
     y = blk(x, meta["index"], **kw)
     assert y.dtype == torch.float32 and list(y.shape[2:]) == meta["out_grid"]
     y.backward(io["gy"].to(cuda_device))
     torch.cuda.synchronize()
+    for bname, buf in blk.named_buffers():                       # batch norm: running statistics after this (training-mode) forward
+        assert rel_err(buf.float(), io["b__" + bname.replace(".", "__")].float()) < REL_TOL, bname
     assert rel_err(y, io["y"]) < REL_TOL, "y"
     assert rel_err(x.grad, io["dx"]) < REL_TOL, "dx"
     for pname in meta["touched"]:

@@ -32,7 +32,8 @@ def test_stacked_drop_ins_match_reference_fno_golden(host, name):  # noqa: F811
                                 dict(n_modes=(10,), in_channels=1, out_channels=1, hidden_channels=4, n_layers=3, stabilizer="tanh",
                                      fno_skip="soft-gating", channel_mlp_skip="linear"),
                                 dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="group_norm"),
-                                dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="instance_norm")])
+                                dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="instance_norm"),
+                                dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="batch_norm")])
 def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
     import sys
     sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
@@ -68,14 +69,15 @@ def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
 
 @pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
 def test_blocks_without_a_drop_in_keep_the_reference_block_and_swap_its_convs(host):  # noqa: F811
-    """norm="batch_norm": the reference FNOBlocks stays (batch norm has no drop-in), the SpectralConvs inside it and the
-    lifting / projection MLPs move over; outputs and gradients are unchanged."""
+    """channel_mlp_dropout > 0: the reference FNOBlocks stays (dropout has no drop-in), the SpectralConvs inside it and the lifting /
+    projection MLPs move over; outputs and gradients are unchanged (eval mode: dropout off)."""
     import sys
     sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
     from make_golden_fno import load_reference_fno
     fno = load_reference_fno()
     torch.manual_seed(5)
-    model = fno.FNO(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=8, n_layers=2, norm="batch_norm", max_n_modes=(10, 8))
+    model = fno.FNO(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=8, n_layers=2, channel_mlp_dropout=0.1, max_n_modes=(10, 8))
+    model.eval()
     x = torch.randn(2, 1, 16, 12)
     xr = x.clone().requires_grad_(True)
     y_ref = model(xr)
