@@ -99,6 +99,30 @@ def test_blocks_without_a_drop_in_keep_the_reference_block_and_swap_its_convs(ho
         assert grad_err(p.grad, ref_grads[k], ref_grads) < 5e-5, k       # (the conv bias in front of a norm has a zero gradient)
 
 
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+def test_batch_norm_eval_mode_uses_the_running_statistics(host):  # noqa: F811
+    import importlib
+    from oracle.load_reference import load_reference_spectral_conv
+    load_reference_spectral_conv()
+    ref_fb = importlib.import_module("neuralop.layers.fno_block")
+    torch.manual_seed(8)
+    ref = ref_fb.FNOBlocks(4, 4, (6, 6), n_layers=2, norm="batch_norm", implementation="reconstructed")
+    ours = nb.FNOBlocks(4, 4, (6, 6), n_layers=2, norm="batch_norm", implementation="reconstructed")
+    ours.load_state_dict(ref.state_dict())
+    x = torch.randn(3, 4, 12, 12)
+    for i in range(2):                                       # two training steps: the running statistics move the same way
+        assert rel_err(ours(x, i), ref(x, i).detach()) < 3e-5
+    for (na, a), (nb_, b) in zip(ours.named_buffers(), ref.named_buffers()):
+        assert na == nb_ and rel_err(a.float(), b.float()) < 1e-5, na
+    ours.eval()
+    ref.eval()
+    x2 = torch.randn(2, 4, 12, 12)
+    with torch.no_grad():
+        assert rel_err(ours(x2, 0), ref(x2, 0)) < 3e-5     # eval: running statistics instead of the batch's
+        assert rel_err(ours(x2, 0), ours.train()(x2, 0)) > 1e-3
+    ours.eval()
+
+
 def test_unsupported_reference_modules_are_reported():
     class ChannelMLP(torch.nn.Module):                     # a reference-like ChannelMLP with dropout
         in_channels = out_channels = hidden_channels = 4
