@@ -232,3 +232,39 @@ def test_whole_layer_epilogue_on_the_host_tiles_matches_reference_ops():
                            ("db2", db2_k, b2.grad), ("dgate", dgate_k, gate.grad.view(-1))]:
         err = (got.double() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-20)
         assert err < 2e-5, (name, err)
+
+
+# ---- randomised extents (hypothesis): every tile edge combination, every option subset ------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=80, deadline=None)
+@given(B=st.integers(1, 3), Ci=st.integers(0, 70), Co=st.integers(1, 70), P=st.integers(1, 300), has_bias=st.booleans(), has_add=st.booleans(),
+       gate_kind=st.sampled_from(["none", "gated", "gate+gated"]), gelu=st.booleans(), seed=st.integers(0, 10_000))
+def test_channel_mix_random_extents_and_options(B, Ci, Co, P, has_bias, has_add, gate_kind, gelu, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Ci, P, generator=g) if Ci else None
+    w = torch.randn(Co, Ci, generator=g) / max(Ci, 1) ** 0.5 if Ci else None
+    bias = torch.randn(Co, generator=g) if has_bias else None
+    add = torch.randn(B, Co, P, generator=g) if has_add else None
+    gated = torch.randn(B, Co, P, generator=g) if gate_kind != "none" else None
+    gate = torch.randn(Co, generator=g) if gate_kind == "gate+gated" else None
+    act = _lib.ACT_GELU if gelu else _lib.ACT_IDENTITY
+    out, pre = host_channel_mix(x, w, Ci, 1, bias, add, gate, gated, act, B, Ci, Co, P)
+    ref_out, ref_pre = ref_channel_mix(x, w, bias, add, gate, gated, act, B, Co, P)
+    assert not torch.isnan(out).any() and not torch.isnan(pre).any()
+    assert (pre.double() - ref_pre).abs().max() < 2e-5 * max(1.0, ref_pre.abs().max().item())
+    assert (out.double() - ref_out).abs().max() < 2e-5 * max(1.0, ref_out.abs().max().item())
+
+
+@settings(max_examples=40, deadline=None)
+@given(B=st.integers(1, 3), Ci=st.integers(1, 70), Co=st.integers(1, 70), P=st.integers(1, 5000), seed=st.integers(0, 10_000))
+def test_weight_grad_random_extents(B, Ci, Co, P, seed):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(seed)
+    gp = torch.randn(B, Co, P, generator=g)
+    x = torch.randn(B, Ci, P, generator=g)
+    dw = torch.full((Co, Ci), float("nan"))
+    assert lib.sc_hostcheck_channel_mix_weight_grad(_p(gp), _p(x), _p(dw), B, Ci, Co, P) == 0
+    ref = torch.einsum("bop,bip->oi", gp.double(), x.double())
+    assert (dw.double() - ref).abs().max() < 3e-5 * max(1.0, ref.abs().max().item()) * (B * P) ** 0.5
