@@ -5,6 +5,7 @@
 
     neuralop.layers.fno_block.FNOBlocks        -> neuraloperator_b200.FNOBlocks   (SpectralConv + fused layer epilogue)
     neuralop.layers.channel_mlp.ChannelMLP     -> neuraloperator_b200.ChannelMLP  (lifting / projection: one fused launch per layer)
+    neuralop.layers.skip_connections.Flattened1dConv / SoftGating -> the same-named drop-ins (stand-alone skips, e.g. UNO's)
     neuralop.layers.spectral_convolution.SpectralConv -> neuraloperator_b200.SpectralConv  (wherever the block around it has no
                                                   drop-in -- norm layers, complex data, dropout: the block stays, its convs move over)
 
@@ -16,7 +17,7 @@ import warnings
 
 from torch import nn
 
-from .fno_block import ChannelMLP, FNOBlocks
+from .fno_block import ChannelMLP, Flattened1dConv, FNOBlocks, SoftGating
 from .spectral_conv import SpectralConv
 
 
@@ -89,7 +90,23 @@ def _convert_spectral_conv(ref: nn.Module) -> SpectralConv:
     return new
 
 
-_CONVERTERS = {"FNOBlocks": _convert_fno_blocks, "ChannelMLP": _convert_channel_mlp, "SpectralConv": _convert_spectral_conv}
+def _convert_flattened_conv(ref: nn.Module) -> Flattened1dConv:
+    """A stand-alone linear skip (skip_connections.py:96-130), e.g. the horizontal skips of UNO."""
+    if tuple(ref.conv.kernel_size) != (1,):
+        raise NotImplementedError("Flattened1dConv with kernel_size != 1 has no B200 drop-in")
+    new = Flattened1dConv(ref.conv.in_channels, ref.conv.out_channels, kernel_size=1, bias=ref.conv.bias is not None)
+    new.load_state_dict(ref.state_dict())
+    return new
+
+
+def _convert_soft_gating(ref: nn.Module) -> SoftGating:
+    new = SoftGating(ref.in_features, ref.out_features, n_dim=ref.weight.ndim - 2, bias=ref.bias is not None)
+    new.load_state_dict(ref.state_dict())
+    return new
+
+
+_CONVERTERS = {"FNOBlocks": _convert_fno_blocks, "ChannelMLP": _convert_channel_mlp, "SpectralConv": _convert_spectral_conv,
+               "Flattened1dConv": _convert_flattened_conv, "SoftGating": _convert_soft_gating}
 
 
 def use_b200_layers(model: nn.Module) -> nn.Module:

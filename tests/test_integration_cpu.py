@@ -100,6 +100,39 @@ def test_blocks_without_a_drop_in_keep_the_reference_block_and_swap_its_convs(ho
 
 
 @pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
+def test_use_b200_layers_on_another_model_family_uno(host):  # noqa: F811
+    """The swap is by module class, not by model: a reference U-shaped neural operator (neuralop/models/uno.py: FNOBlocks with
+    different channel counts / modes / scalings per layer, stand-alone linear skips) ends up without a single reference layer class
+    from this package's list, and computes the same function."""
+    import importlib
+    import sys
+    sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
+    from make_golden_fno import load_reference_fno
+    load_reference_fno()
+    uno = importlib.import_module("neuralop.models.uno")
+    torch.manual_seed(0)
+    model = uno.UNO(in_channels=1, out_channels=1, hidden_channels=8, n_layers=3, uno_out_channels=[8, 8, 8],
+                    uno_n_modes=[[6, 6], [4, 4], [6, 6]], uno_scalings=[[0.5, 0.5], [1, 1], [2, 2]], channel_mlp_skip="linear")
+    x = torch.randn(2, 1, 16, 16)
+    xr = x.clone().requires_grad_(True)
+    y_ref = model(xr)
+    gy = torch.randn_like(y_ref)
+    y_ref.backward(gy)
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters()}
+    dx_ref = xr.grad.clone()
+    model.zero_grad(set_to_none=True)
+    nb.use_b200_layers(model)
+    left = {type(m).__name__ for m in model.modules() if type(m).__module__.startswith("neuralop.")}
+    assert not left & {"FNOBlocks", "SpectralConv", "ChannelMLP", "Flattened1dConv", "SoftGating"}, left
+    xo = x.clone().requires_grad_(True)
+    y = model(xo)
+    y.backward(gy)
+    assert rel_err(y, y_ref.detach()) < 3e-5 and rel_err(xo.grad, dx_ref) < 3e-5
+    for k, p in model.named_parameters():
+        assert grad_err(p.grad, ref_grads[k], ref_grads) < 5e-5, k
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
 def test_batch_norm_eval_mode_uses_the_running_statistics(host):  # noqa: F811
     import importlib
     from oracle.load_reference import load_reference_spectral_conv
