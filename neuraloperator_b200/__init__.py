@@ -10,5 +10,5 @@ from .data_parallel import GradientAllReducer, PeerGradientAllReducer  # noqa: F
 from .integration import use_b200_layers  # noqa: F401
 
 __version__ = "0.1.0"
-from .fno_block import (ChannelMLP, Flattened1dConv, FNOBlocks, SoftGating, channel_mix,  # noqa: F401
+from .fno_block import (ChannelMLP, ComplexValued, Flattened1dConv, FNOBlocks, SoftGating, channel_mix,  # noqa: F401
                         set_tensor_core_mixing, skip_connection, uses_tensor_core_mixing)

@@ -557,6 +557,10 @@ SC_HD float pointwise_elem(int op, const float* a, const float* b, long long i) 
     case SC_POINTWISE_TANH: return tanhf(a[i]);
     case SC_POINTWISE_TANH_BACKWARD: { const float t = b[i]; return a[i] * (1.0f - t * t); }    // a = upstream grad, b = tanh(x)
     case SC_POINTWISE_ROUND_HALF: return __half2float(__float2half_rn(a[i]));                   // x.half() (:436-437), x.chalf() (:451-454)
+    // interleaved complex (re, im) pairs, element i = 2k + parity:  out = a + 1j * b   (apply_complex, neuralop/layers/complex.py:55-62)
+    case SC_POINTWISE_ADD_I_TIMES: return (i & 1) ? a[i] + b[i - 1] : a[i] - b[i + 1];
+    // out = -1j * a   (its gradient with respect to b)
+    case SC_POINTWISE_MUL_NEG_I: return (i & 1) ? -a[i - 1] : a[i + 1];
     default: return a[i];
   }
 }
@@ -689,9 +693,11 @@ int sc_layer_set_tensor_cores(int enable) {
 int sc_layer_uses_tensor_cores(void) { return mix_tc_enabled() ? 1 : 0; }
 
 int sc_pointwise(int op, const float* a, const float* b, float* out, int64_t n, sc_stream stream) {
-  SC_REQUIRE(op == SC_POINTWISE_TANH || op == SC_POINTWISE_TANH_BACKWARD || op == SC_POINTWISE_ROUND_HALF, "sc_pointwise: unknown op");
+  SC_REQUIRE(op >= SC_POINTWISE_TANH && op <= SC_POINTWISE_MUL_NEG_I, "sc_pointwise: unknown op");
   SC_REQUIRE(n == 0 || (a != nullptr && out != nullptr), "sc_pointwise: null argument");
-  SC_REQUIRE(op != SC_POINTWISE_TANH_BACKWARD || n == 0 || b != nullptr, "sc_pointwise: tanh backward needs tanh(x)");
+  SC_REQUIRE((op != SC_POINTWISE_TANH_BACKWARD && op != SC_POINTWISE_ADD_I_TIMES) || n == 0 || b != nullptr, "sc_pointwise: this op needs its second operand");
+  SC_REQUIRE((op != SC_POINTWISE_ADD_I_TIMES && op != SC_POINTWISE_MUL_NEG_I) || ((n & 1) == 0 && a != out && b != out),
+             "sc_pointwise: the complex-pair ops need an even count and an output that aliases no input");
   SC_TRY(launch_pointwise(op, a, b, out, (long long)n, static_cast<cudaStream_t>(stream)));
   return 0;
 }
@@ -735,7 +741,9 @@ int sc_hostcheck_channel_mix_weight_grad(const float* gpre, const float* in, flo
 }
 
 int sc_hostcheck_pointwise(int op, const float* a, const float* b, float* out, int64_t n) {
-  SC_REQUIRE(op == SC_POINTWISE_TANH || op == SC_POINTWISE_TANH_BACKWARD || op == SC_POINTWISE_ROUND_HALF, "sc_hostcheck_pointwise: unknown op");
+  SC_REQUIRE(op >= SC_POINTWISE_TANH && op <= SC_POINTWISE_MUL_NEG_I, "sc_hostcheck_pointwise: unknown op");
+  SC_REQUIRE((op != SC_POINTWISE_ADD_I_TIMES && op != SC_POINTWISE_MUL_NEG_I) || ((n & 1) == 0 && a != out && b != out),
+             "sc_hostcheck_pointwise: the complex-pair ops need an even count and an output that aliases no input");
   // the kernel's own index walk: block, thread, slot
   const long long per = PW_THREADS * PW_PER_THREAD;
   const long long blocks = (n + per - 1) / per;

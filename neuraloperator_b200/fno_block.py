@@ -34,6 +34,13 @@ def _require_device_tensor(t: torch.Tensor, what: str):
         raise TypeError(f"{what} must be float32 (full precision, real data), got {t.dtype}")
 
 
+def _require_complex_input(x: torch.Tensor):
+    if not x.is_cuda:
+        raise RuntimeError(f"neuraloperator_b200 has no CPU path: FNOBlocks input must live on a B200 (got {x.device})")
+    if x.dtype != torch.complex64:
+        raise TypeError(f"FNOBlocks(complex_data=True) expects complex64 input, got {x.dtype}")
+
+
 def set_tensor_core_mixing(enable: bool) -> None:
     """Route `channel_mix` (forward and input gradient; Ci <= 256, Co <= 128) through the tcgen05 bf16x3 kernel instead of the exact
     fp32 SIMT kernel.  OPT-IN: that kernel was written without hardware access (also: SC_MIX_TC=1 in the environment)."""
@@ -407,6 +414,69 @@ class ChannelMLP(nn.Module):
 
 
 # --------------------------------------------------------------------------------------------------
+# complex-valued data at block level (neuralop/layers/complex.py): every layer-epilogue op on the (..., 2) real view of a complex
+# tensor -- the kernels are dimension-agnostic, so the trailing (re, im) axis is just one more grid axis
+# --------------------------------------------------------------------------------------------------
+class _AddITimes(torch.autograd.Function):
+    """view_as_complex(a) + 1j * view_as_complex(b) on real (..., 2) views: how `apply_complex` (complex.py:55-62) recombines."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        lib = _lib.load()
+        _require_device_tensor(a, "complex recombination operand")
+        _require_device_tensor(b, "complex recombination operand")
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        if a.numel():
+            with torch.cuda.device(a.device):
+                _lib.check(lib.sc_pointwise(_lib.POINTWISE_ADD_I_TIMES, _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream_ptr(a.device)),
+                           "sc_pointwise")
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        g = g.contiguous().float()
+        gb = torch.empty_like(g)
+        if g.numel():
+            with torch.cuda.device(g.device):
+                _lib.check(lib.sc_pointwise(_lib.POINTWISE_MUL_NEG_I, _ptr(g), None, _ptr(gb), g.numel(), _stream_ptr(g.device)), "sc_pointwise")
+        return g, gb
+
+
+def _as_real(z: torch.Tensor) -> torch.Tensor:
+    return torch.view_as_real(z.contiguous()) if z.is_complex() else z
+
+
+class ComplexValued(nn.Module):
+    """`ComplexValued(module)` of the reference (complex.py:65-79): a real module applied to complex data as
+    (fr(x.real) - fi(x.imag)) + 1j (fr(x.imag) + fi(x.real)), with `fr` / `fi` two copies of the module (same parameter names).
+    Here each copy runs ONCE on the (..., 2) real view of x -- which yields fr / fi of the real and the imaginary part side by
+    side -- and the two results are recombined as a + 1j * b by one pointwise launch."""
+
+    def __init__(self, module):
+        super().__init__()
+        import copy
+        self.fr = copy.deepcopy(module)
+        self.fi = copy.deepcopy(module)
+
+    def forward(self, x):
+        xv = _as_real(x)
+        return torch.view_as_complex(_AddITimes.apply(self.fr(xv), self.fi(xv)))
+
+
+def _complex_act(z, act):
+    """CGELU (complex.py:12-31): the activation on the real and the imaginary part separately = on the real view."""
+    return z if act == ACT_IDENTITY else torch.view_as_complex(channel_mix(add=_as_real(z), act=act))
+
+
+def _complex_add_act(z1, z2, act):
+    """act(z1 + z2) in one launch on the real views."""
+    return torch.view_as_complex(channel_mix(add=_as_real(z1), gated=_as_real(z2), act=act))
+
+
+# --------------------------------------------------------------------------------------------------
 # FNOBlocks
 # --------------------------------------------------------------------------------------------------
 def _validate_scaling_factor(factor, n_dim, n_layers):
@@ -465,9 +535,11 @@ class FNOBlocks(nn.Module):
         self.n_dim = len(n_modes)
         if norm not in (None, "instance_norm", "group_norm", "batch_norm", "ada_in"):
             raise ValueError(f"Got norm={norm} but expected None or one of [instance_norm, group_norm, batch_norm, ada_in]")
-        if complex_data:
-            raise NotImplementedError("FNOBlocks(complex_data=True): the layer epilogue kernels are real-valued "
-                                      "(SpectralConv itself supports complex data)")
+        if complex_data and norm is not None:
+            raise NotImplementedError("FNOBlocks(complex_data=True) with a normalisation layer is not built")
+        if complex_data and resolution_scaling_factor is not None:
+            raise NotImplementedError("FNOBlocks(complex_data=True) with a resolution change is not built (the reference's `resample` "
+                                      "interpolates real tensors)")
         if non_linearity is not F.gelu:
             raise NotImplementedError("FNOBlocks: the fused epilogue implements F.gelu (exact erf form) only")
         if channel_mlp_dropout:
@@ -534,6 +606,13 @@ class FNOBlocks(nn.Module):
                     for _ in range(n_layers)])
             else:
                 self.channel_mlp_skips = None
+        if self.complex_data:          # fno_block.py:275-276, 293-311: every epilogue module becomes a ComplexValued pair (fr, fi)
+            if self.fno_skips is not None:
+                self.fno_skips = nn.ModuleList([ComplexValued(m) for m in self.fno_skips])
+            if self.use_channel_mlp:
+                self.channel_mlp = nn.ModuleList([ComplexValued(m) for m in self.channel_mlp])
+                if self.channel_mlp_skips is not None:
+                    self.channel_mlp_skips = nn.ModuleList([ComplexValued(m) for m in self.channel_mlp_skips])
 
     def set_ada_in_embeddings(self, *embeddings):
         """Sets the embeddings of the AdaIN layers (fno_block.py:354-369): one for all, or one per norm layer."""
@@ -604,9 +683,32 @@ class FNOBlocks(nn.Module):
 
     # -- forward ------------------------------------------------------------------------------------
     def forward(self, x, index=0, output_shape=None):
+        if self.complex_data:
+            return self._forward_complex(x, index, output_shape)
         if self.preactivation:
             return self.forward_with_preactivation(x, index, output_shape)
         return self.forward_with_postactivation(x, index, output_shape)
+
+    def _forward_complex(self, x, index, output_shape):
+        """Both forward orders for complex data (CGELU, ctanh, ComplexValued skips / MLP; fno_block.py:377-453 with :204-207, :275-311):
+        the same sequence as the real case with every epilogue op on the (..., 2) real view."""
+        _require_complex_input(x)
+        if output_shape is not None and list(output_shape) != list(x.shape[2:]):
+            raise NotImplementedError("FNOBlocks(complex_data=True) with a resolution change is not built")
+        act = ACT_GELU if index < (self.n_layers - 1) else ACT_IDENTITY
+        x = x.contiguous()
+        if self.preactivation:
+            x = _complex_act(x, ACT_GELU)
+        x_skip_fno = self.fno_skips[index](x) if self.fno_skips is not None else None
+        x_skip_mlp = self.channel_mlp_skips[index](x) if self.use_channel_mlp and self.channel_mlp_skips is not None else None
+        xc = torch.view_as_complex(_Tanh.apply(_as_real(x))) if self.stabilizer == "tanh" else x         # ctanh, complex.py:45-52
+        x_fno = self.convs[index](xc, output_shape=output_shape)
+        y = _complex_add_act(x_fno, x_skip_fno, act) if x_skip_fno is not None else _complex_act(x_fno, act)
+        if self.use_channel_mlp:
+            m = self.channel_mlp[index](y)
+            final = ACT_IDENTITY if self.preactivation else act
+            return _complex_add_act(m, x_skip_mlp, final) if x_skip_mlp is not None else _complex_act(m, final)
+        return y if self.preactivation else _complex_act(y, act)
 
     def forward_with_postactivation(self, x, index=0, output_shape=None):
         """fno_block.py:377-414."""

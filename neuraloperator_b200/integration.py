@@ -15,9 +15,10 @@ reference's Python.  Modules are recognised by class NAME and constructor attrib
 """
 import warnings
 
+import torch.nn.functional as F
 from torch import nn
 
-from .fno_block import ChannelMLP, Flattened1dConv, FNOBlocks, SoftGating
+from .fno_block import ChannelMLP, ComplexValued, Flattened1dConv, FNOBlocks, SoftGating
 from .spectral_conv import SpectralConv
 
 
@@ -49,7 +50,8 @@ def _convert_fno_blocks(ref: nn.Module) -> FNOBlocks:
         ref.in_channels, ref.out_channels, ref.n_modes, resolution_scaling_factor=rsf, n_layers=ref.n_layers,
         max_n_modes=ref.max_n_modes, fno_block_precision=ref.fno_block_precision, use_channel_mlp=ref.use_channel_mlp,
         channel_mlp_dropout=ref.channel_mlp_dropout, channel_mlp_expansion=ref.channel_mlp_expansion,
-        non_linearity=ref.non_linearity, stabilizer=ref.stabilizer, norm=norm, norm_groups=norm_groups,
+        # (for complex data the reference replaces whatever activation was passed by CGELU, fno_block.py:204-207: ours does the same)
+        non_linearity=F.gelu if ref.complex_data else ref.non_linearity, stabilizer=ref.stabilizer, norm=norm, norm_groups=norm_groups,
         ada_in_features=ref.ada_in_features, preactivation=ref.preactivation,
         fno_skip=ref.fno_skip, conv_bias_kernel=ref.conv_bias_kernel, channel_mlp_skip=ref.channel_mlp_skip,
         complex_data=ref.complex_data, separable=ref.separable, factorization=ref.factorization, rank=ref.rank,
@@ -105,7 +107,21 @@ def _convert_soft_gating(ref: nn.Module) -> SoftGating:
     return new
 
 
-_CONVERTERS = {"FNOBlocks": _convert_fno_blocks, "ChannelMLP": _convert_channel_mlp, "SpectralConv": _convert_spectral_conv,
+def _convert_complex_valued(ref: nn.Module) -> ComplexValued:
+    """`ComplexValued(module)` (complex.py:65-79, e.g. the lifting / projection of a complex FNO): the pair (fr, fi) of converted
+    modules, evaluated once each on the real view of the input."""
+    parts = []
+    for part in (ref.fr, ref.fi):
+        conv = _CONVERTERS.get(type(part).__name__)
+        if conv is None or type(part).__name__ == "ComplexValued":
+            raise NotImplementedError(f"ComplexValued({type(part).__name__}) has no B200 drop-in")
+        parts.append(conv(part))
+    new = ComplexValued(nn.Identity())
+    new.fr, new.fi = parts
+    return new
+
+
+_CONVERTERS = {"ComplexValued": _convert_complex_valued, "FNOBlocks": _convert_fno_blocks, "ChannelMLP": _convert_channel_mlp, "SpectralConv": _convert_spectral_conv,
                "Flattened1dConv": _convert_flattened_conv, "SoftGating": _convert_soft_gating}
 
 

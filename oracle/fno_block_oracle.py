@@ -129,10 +129,50 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
     return y
 
 
+def _cgelu(z):                                                                  # complex.py:12-31
+    return torch.complex(F.gelu(z.real), F.gelu(z.imag))
+
+
+def _complex_valued(fr, fi, z):                                                 # apply_complex, complex.py:55-62
+    return torch.complex(fr(z.real) - fi(z.imag), fr(z.imag) + fi(z.real))
+
+
+def fno_block_forward_complex(x: torch.Tensor, params: Dict[str, torch.Tensor], index: int, *, n_modes: Sequence[int], n_layers: int,
+                              fno_skip: Optional[str] = "linear", channel_mlp_skip: Optional[str] = "soft-gating",
+                              use_channel_mlp: bool = True, stabilizer: Optional[str] = None, preactivation: bool = False,
+                              max_n_modes: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """`FNOBlocks.forward(x, index)` with complex_data=True (fno_block.py:204-207 CGELU, :275-276 / :293-311 ComplexValued skips and
+    MLP, :386-388 ctanh), dense conv weight, norm=None, no resolution change."""
+    nonlin = index < n_layers - 1
+
+    def cv(kind_fn, prefix):
+        return lambda z: _complex_valued(lambda t: kind_fn(prefix + ".fr", t), lambda t: kind_fn(prefix + ".fi", t), z)
+
+    if preactivation:
+        x = _cgelu(x)
+    x_skip_fno = cv(lambda pre, t: _skip(fno_skip, params, pre, t), f"fno_skips.{index}")(x) if fno_skip is not None else None
+    x_skip_mlp = None
+    if use_channel_mlp and channel_mlp_skip is not None:
+        x_skip_mlp = cv(lambda pre, t: _skip(channel_mlp_skip, params, pre, t), f"channel_mlp_skips.{index}")(x)
+    xc = torch.complex(torch.tanh(x.real), torch.tanh(x.imag)) if stabilizer == "tanh" else x
+    x_fno = O.spectral_conv_forward_complex(xc, params[f"convs.{index}.weight.tensor"], params.get(f"convs.{index}.bias"), list(n_modes),
+                                            max_n_modes=max_n_modes)
+    y = x_fno + x_skip_fno if x_skip_fno is not None else x_fno
+    if nonlin:
+        y = _cgelu(y)
+    if use_channel_mlp:
+        y = cv(lambda pre, t: _channel_mlp(params, pre, t), f"channel_mlp.{index}")(y)
+        if x_skip_mlp is not None:
+            y = y + x_skip_mlp
+    if nonlin and not preactivation:
+        y = _cgelu(y)
+    return y
+
+
 def fno_block_fwd_bwd(x, params, index, grad_y, **kw):
     """Forward + autograd backward. Returns y, dx, {name: grad} for every parameter the layer touched."""
     x = x.detach().clone().requires_grad_(True)
     ps = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
-    y = fno_block_forward(x, ps, index, **kw)
+    y = (fno_block_forward_complex if x.is_complex() else fno_block_forward)(x, ps, index, **kw)
     y.backward(grad_y)
     return y.detach(), x.grad, {k: v.grad for k, v in ps.items() if v.grad is not None}

@@ -63,6 +63,12 @@ CASES = [
     ("block_d2_batch_norm_mid", 3, 6, 6, (12, 14), (6, 6), 2, 0, {"norm": "batch_norm"}, {}),
     ("block_d1_batch_norm_last", 3, 4, 4, (30,), (8,), 2, 1, {"norm": "batch_norm"}, {}),
     ("block_d2_ada_in_mid", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"norm": "ada_in", "ada_in_features": 5}, {}),
+    ("block_cplx_d2_mid", 2, 4, 4, (10, 12), (6, 6), 2, 0, {"complex_data": True}, {}),
+    ("block_cplx_d2_last", 2, 4, 4, (10, 12), (6, 6), 2, 1, {"complex_data": True}, {}),
+    ("block_cplx_d1_tanh_linear_skips", 2, 4, 6, (24,), (8,), 2, 0, {"complex_data": True, "stabilizer": "tanh", "channel_mlp_skip": "linear"}, {}),
+    ("block_cplx_d2_identity_no_mlp", 2, 4, 4, (10, 12), (6, 6), 2, 0, {"complex_data": True, "fno_skip": "identity", "use_channel_mlp": False}, {}),
+    ("block_cplx_d3_preactivation_softgating", 1, 3, 3, (6, 6, 8), (4, 4, 4), 2, 0,
+     {"complex_data": True, "preactivation": True, "fno_skip": "soft-gating"}, {}),
 ]
 
 
@@ -84,11 +90,13 @@ def main():
         if ctor.get("norm") == "ada_in":
             embedding = torch.randn(ctor["ada_in_features"])
             blk.set_ada_in_embeddings(embedding)
-        x = torch.randn(B, Ci, *grid, requires_grad=True)
+        x = torch.randn(B, Ci, *grid, dtype=torch.cfloat if ctor.get("complex_data") else torch.float32, requires_grad=True)
         y = blk(x, idx, **fkw)
         gy = torch.randn_like(y)
         y.backward(gy)
-        arrays = {"x": x.detach().numpy(), "gy": gy.numpy(), "y": y.detach().numpy(), "dx": x.grad.numpy()}
+        arrays = {}
+        for key, val in (("x", x.detach()), ("gy", gy), ("y", y.detach()), ("dx", x.grad)):
+            arrays[key + ("__c" if val.is_complex() else "")] = torch.view_as_real(val).numpy() if val.is_complex() else val.numpy()
         if embedding is not None:
             arrays["ada_in_embedding"] = embedding.numpy()
         for bname, buf in blk.named_buffers():                   # batch norm: the running statistics AFTER this forward

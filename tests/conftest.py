@@ -140,6 +140,8 @@ def block_oracle_kwargs(meta):
         kw["max_n_modes"] = stored_n_modes(ctor["max_n_modes"])
     if "output_shape" in meta["forward"]:
         kw["output_shape"] = meta["forward"]["output_shape"]
+    if ctor.get("complex_data"):           # oracle.fno_block_oracle.fno_block_forward_complex: dense weight, no norm, no resampling
+        kw = {k: kw[k] for k in ("n_modes", "n_layers", "fno_skip", "channel_mlp_skip", "use_channel_mlp", "stabilizer", "preactivation")}
     return kw
 
 

@@ -49,6 +49,9 @@ class _HostLib:
 def _oracle_conv_forward(self, x, output_shape=None):
     """SpectralConv.forward served by the CPU oracle (differentiable through torch.fft), from the module's own parameters."""
     kind = getattr(self.weight, "kind", "dense")
+    if self.complex_data:
+        return O.spectral_conv_forward_complex(x, self.weight.to_tensor(), self.bias, list(self.n_modes), max_n_modes=list(self.max_n_modes),
+                                               output_shape=output_shape, fft_norm=self.fft_norm)
     if kind == "dense":
         w = O.Weight("dense", tensor=self.weight.tensor)
     elif kind == "tucker":
@@ -76,6 +79,7 @@ def host(monkeypatch):
     monkeypatch.setattr(fb._lib, "load", lambda: h)
     monkeypatch.setattr(fb._lib, "check", lambda rc, what: (_ for _ in ()).throw(RuntimeError(f"{what}: {real.sc_last_error()}")) if rc else None)
     monkeypatch.setattr(fb, "_require_device_tensor", lambda t, what: None)
+    monkeypatch.setattr(fb, "_require_complex_input", lambda x: None)
     monkeypatch.setattr(fb, "_stream_ptr", lambda dev: None)
     monkeypatch.setattr(torch.cuda, "device", lambda dev: contextlib.nullcontext())
     monkeypatch.setattr(nb.SpectralConv, "forward", _oracle_conv_forward)
@@ -125,7 +129,7 @@ def test_block_module_matches_reference_golden(host, name):
     x = io["x"].clone().requires_grad_(True)
     kw = {k: tuple(v) for k, v in meta["forward"].items()}
     y = blk(x, meta["index"], **kw)
-    assert y.dtype == torch.float32 and list(y.shape[2:]) == meta["out_grid"]
+    assert y.dtype == (torch.complex64 if meta["ctor"].get("complex_data") else torch.float32) and list(y.shape[2:]) == meta["out_grid"]
     y.backward(io["gy"])
     for bname, buf in blk.named_buffers():                       # batch norm: running statistics after this (training-mode) forward
         want = io["b__" + bname.replace(".", "__")]
@@ -183,7 +187,8 @@ def test_state_dict_round_trip_with_the_reference(host):
 
 
 def test_unsupported_configurations_raise():
-    for kw in (dict(complex_data=True), dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
+    for kw in (dict(complex_data=True, norm="group_norm"), dict(complex_data=True, resolution_scaling_factor=2),
+               dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
                dict(non_linearity=torch.nn.functional.relu)):
         with pytest.raises(NotImplementedError):
             nb.FNOBlocks(4, 4, (4, 4), **kw)

@@ -110,7 +110,7 @@ def test_block_module_matches_reference_golden(cuda_device, name):
     x = io["x"].to(cuda_device).requires_grad_(True)
     kw = {k: tuple(v) for k, v in meta["forward"].items()}
     y = blk(x, meta["index"], **kw)
-    assert y.dtype == torch.float32 and list(y.shape[2:]) == meta["out_grid"]
+    assert y.dtype == (torch.complex64 if meta["ctor"].get("complex_data") else torch.float32) and list(y.shape[2:]) == meta["out_grid"]
     y.backward(io["gy"].to(cuda_device))
     torch.cuda.synchronize()
     for bname, buf in blk.named_buffers():                       # batch norm: running statistics after this (training-mode) forward

@@ -33,7 +33,9 @@ def test_stacked_drop_ins_match_reference_fno_golden(host, name):  # noqa: F811
                                      fno_skip="soft-gating", channel_mlp_skip="linear"),
                                 dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="group_norm"),
                                 dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="instance_norm"),
-                                dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="batch_norm")])
+                                dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="batch_norm"),
+                                dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, complex_data=True,
+                                     positional_embedding=None)])
 def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
     import sys
     sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
@@ -42,7 +44,7 @@ def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
     torch.manual_seed(21)
     model = fno.FNO(**kw)                                  # default positional embedding (grid) + no padding: stays reference code
     grid = (16,) * len(kw["n_modes"])
-    x = torch.randn(2, kw["in_channels"], *grid)
+    x = torch.randn(2, kw["in_channels"], *grid, dtype=torch.cfloat if kw.get("complex_data") else torch.float32)
     gy = None
     xr = x.clone().requires_grad_(True)
     y_ref = model(xr)
@@ -55,7 +57,8 @@ def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
 
     out = nb.use_b200_layers(model)
     assert out is model
-    assert type(model.fno_blocks) is nb.FNOBlocks and type(model.lifting) is nb.ChannelMLP and type(model.projection) is nb.ChannelMLP
+    mlp_type = nb.ComplexValued if kw.get("complex_data") else nb.ChannelMLP
+    assert type(model.fno_blocks) is nb.FNOBlocks and type(model.lifting) is mlp_type and type(model.projection) is mlp_type
     assert sorted(k.replace("factors.factor_", "factors.") for k, _ in model.named_parameters()) == names
     xo = x.clone().requires_grad_(True)
     y = model(xo)
