@@ -233,7 +233,7 @@ int sc_allreduce_p2p(float* const* peer_buffers, uint32_t* const* peer_signal_pa
  *
  * bias, add, gate, gated, pre_out may each be NULL (gate NULL with gated given = coefficient 1: the identity skip); in_channels may
  * be 0 (no mixing term: in / w unused).  pre_out (B, Co, P): the pre-activation, stored for the backward pass when given. */
-enum { SC_ACT_IDENTITY = 0, SC_ACT_GELU = 1 };
+enum { SC_ACT_IDENTITY = 0, SC_ACT_GELU = 1, SC_ACT_RELU = 2, SC_ACT_SILU = 3, SC_ACT_TANH = 4 };   /* non_linearity of the block */
 int sc_channel_mix(const float* in, const float* w, int64_t w_stride_o, int64_t w_stride_i, const float* bias, const float* add,
                    const float* gate, const float* gated, int act, float* out, float* pre_out, int32_t batch, int32_t in_channels,
                    int32_t out_channels, int64_t n_points, sc_stream stream);

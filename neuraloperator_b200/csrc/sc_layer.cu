@@ -37,8 +37,13 @@ namespace sc {
 
 // ---- activations (F.gelu default = exact erf form, torch/nn/functional.py; fno_block.py:150 non_linearity=F.gelu) ------------
 SC_HD float act_apply(int act, float v) {
-  if (act == SC_ACT_GELU) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
-  return v;
+  switch (act) {
+    case SC_ACT_GELU: return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+    case SC_ACT_RELU: return v > 0.f ? v : 0.f;
+    case SC_ACT_SILU: return v / (1.0f + expf(-v));
+    case SC_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
 }
 SC_HD float act_grad(int act, float v) {
   if (act == SC_ACT_GELU) {
@@ -46,6 +51,9 @@ SC_HD float act_grad(int act, float v) {
     const float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
     return cdf + v * pdf;
   }
+  if (act == SC_ACT_RELU) return v > 0.f ? 1.0f : 0.f;              // (zero at the kink, as torch)
+  if (act == SC_ACT_SILU) { const float sg = 1.0f / (1.0f + expf(-v)); return sg * (1.0f + v * (1.0f - sg)); }
+  if (act == SC_ACT_TANH) { const float t = tanhf(v); return 1.0f - t * t; }
   return 1.0f;
 }
 // (d0, d1) += a * (b0, b1) as ONE packed instruction: on sm_100 the scalar FFMA issues every other cycle per sub-partition and
@@ -636,7 +644,7 @@ static int fill_mix(MixArgs& a, const char* who, const float* in, const float* w
   SC_REQUIRE(batch >= 0 && in_channels >= 0 && out_channels >= 0 && n_points >= 0, "sc_channel_mix: negative extent");
   SC_REQUIRE(in_channels == 0 || (in != nullptr && w != nullptr), "sc_channel_mix: in / w are required when in_channels > 0");
   SC_REQUIRE(gate == nullptr || gated != nullptr, "sc_channel_mix: a gate needs the tensor it gates");
-  SC_REQUIRE(act == SC_ACT_IDENTITY || act == SC_ACT_GELU, "sc_channel_mix: unknown activation");
+  SC_REQUIRE(act >= SC_ACT_IDENTITY && act <= SC_ACT_TANH, "sc_channel_mix: unknown activation");
   a = MixArgs{in, w, (long long)w_stride_o, (long long)w_stride_i, bias, add, gate, gated, out, pre_out, act, batch, in_channels,
               out_channels, (long long)n_points};
   return 0;
@@ -647,7 +655,7 @@ static int fill_act_backward(ActBwdArgs& a, const float* gout, const float* pre,
                              int64_t n_points) {
   SC_REQUIRE(gout != nullptr, "sc_channel_mix_act_backward: null upstream gradient");
   SC_REQUIRE(batch >= 0 && channels >= 0 && n_points >= 0, "sc_channel_mix_act_backward: negative extent");
-  SC_REQUIRE(act == SC_ACT_IDENTITY || act == SC_ACT_GELU, "sc_channel_mix_act_backward: unknown activation");
+  SC_REQUIRE(act >= SC_ACT_IDENTITY && act <= SC_ACT_TANH, "sc_channel_mix_act_backward: unknown activation");
   SC_REQUIRE(act == SC_ACT_IDENTITY || pre != nullptr, "sc_channel_mix_act_backward: the activation derivative needs the pre-activation");
   SC_REQUIRE(dgate == nullptr || gated != nullptr, "sc_channel_mix_act_backward: dgate needs the gated tensor");
   a = ActBwdArgs{gout, act == SC_ACT_IDENTITY ? nullptr : pre, act, gate, gated, gpre_out, dgated_out, dbias, dgate, batch, channels,

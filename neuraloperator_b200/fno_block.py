@@ -9,7 +9,7 @@ semantics (fno_block.py:371-453), with everything after the spectral convolution
 
 instead of one tensor pass per torch op (conv1d, add, gelu, mul, add, gelu ...).  No CPU / PyTorch fallback: the modules raise on
 CPU tensors, and configurations the kernels do not cover (complex data, dropout, activations other than GELU, conv_bias_kernel > 1)
-raise `NotImplementedError` at construction.  The four `norm` options are composed from the same kernels (one statistics pass + one
+raise `NotImplementedError` at construction (activations: gelu, relu, silu, tanh; dropout: eval mode only).  The four `norm` options are composed from the same kernels (one statistics pass + one
 fused affine / add / activation launch per normalisation).
 """
 import math
@@ -25,6 +25,17 @@ from .spectral_conv import SpectralConv, _ptr, _stream_ptr
 
 Number = Union[int, float]
 ACT_IDENTITY, ACT_GELU = _lib.ACT_IDENTITY, _lib.ACT_GELU
+
+
+def activation_code(non_linearity) -> int:
+    """The kernels' activation code for a `non_linearity` callable of the reference API (fno_block.py:150, channel_mlp.py:49)."""
+    table = {F.gelu: _lib.ACT_GELU, F.relu: _lib.ACT_RELU, torch.relu: _lib.ACT_RELU, F.silu: _lib.ACT_SILU, torch.tanh: _lib.ACT_TANH,
+             F.tanh: _lib.ACT_TANH}
+    for fn, code in table.items():
+        if non_linearity is fn:
+            return code
+    raise NotImplementedError(f"non_linearity {non_linearity!r}: the fused kernels implement F.gelu (exact erf form), F.relu, F.silu "
+                              "and torch.tanh")
 
 
 def _require_device_tensor(t: torch.Tensor, what: str):
@@ -385,16 +396,14 @@ class ChannelMLP(nn.Module):
 
     def __init__(self, in_channels, out_channels=None, hidden_channels=None, n_layers=2, n_dim=2, non_linearity=F.gelu, dropout=0.0):
         super().__init__()
-        if non_linearity is not F.gelu:
-            raise NotImplementedError("ChannelMLP: the fused kernels implement F.gelu (exact erf form) only")
-        if dropout > 0.0:
-            raise NotImplementedError("ChannelMLP: dropout is not built")
+        self._act = activation_code(non_linearity)
         self.n_layers = n_layers
         self.in_channels = in_channels
         self.out_channels = in_channels if out_channels is None else out_channels
         self.hidden_channels = in_channels if hidden_channels is None else hidden_channels
         self.non_linearity = non_linearity
-        self.dropout = None
+        # dropout: identity in eval mode (F.dropout); the training-mode mask is not built (forward raises there)
+        self.dropout = nn.ModuleList([nn.Dropout(dropout) for _ in range(n_layers)]) if dropout > 0.0 else None
         self.fcs = nn.ModuleList()                                                       # Conv1d modules as parameter containers
         for i in range(n_layers):
             cin = self.in_channels if i == 0 else self.hidden_channels
@@ -402,9 +411,11 @@ class ChannelMLP(nn.Module):
             self.fcs.append(nn.Conv1d(cin, cout, 1))
 
     def _forward_fused(self, x, gate=None, gated=None, final_act=ACT_IDENTITY):
+        if self.dropout is not None and self.training:
+            raise NotImplementedError("ChannelMLP: dropout in training mode is not built (eval mode, where it is the identity, is)")
         for i, fc in enumerate(self.fcs):
             if i < self.n_layers - 1:
-                x = channel_mix(x, fc.weight, fc.bias, act=ACT_GELU)
+                x = channel_mix(x, fc.weight, fc.bias, act=self._act)
             else:
                 x = channel_mix(x, fc.weight, fc.bias, gate=gate, gated=gated, act=final_act)
         return x
@@ -540,10 +551,7 @@ class FNOBlocks(nn.Module):
         if complex_data and resolution_scaling_factor is not None:
             raise NotImplementedError("FNOBlocks(complex_data=True) with a resolution change is not built (the reference's `resample` "
                                       "interpolates real tensors)")
-        if non_linearity is not F.gelu:
-            raise NotImplementedError("FNOBlocks: the fused epilogue implements F.gelu (exact erf form) only")
-        if channel_mlp_dropout:
-            raise NotImplementedError("FNOBlocks: channel_mlp_dropout is not built")
+        self._act = ACT_GELU if complex_data else activation_code(non_linearity)      # (complex data: CGELU whatever was passed, :204-207)
         if conv_bias_kernel != 1:
             raise NotImplementedError("FNOBlocks: conv_bias_kernel > 1 (a local convolution as the skip) is not built")
         if stabilizer not in (None, "tanh"):
@@ -714,7 +722,7 @@ class FNOBlocks(nn.Module):
         """fno_block.py:377-414."""
         _require_device_tensor(x, "FNOBlocks input")
         x = x.contiguous()
-        act = ACT_GELU if index < (self.n_layers - 1) else ACT_IDENTITY
+        act = self._act if index < (self.n_layers - 1) else ACT_IDENTITY
         if self.norm is not None:
             x1 = self._fourier_step(x, index, output_shape, act, norm=self.norm[self.n_norms * index])
             pre = self._mlp_step(x1, x, index, output_shape, ACT_IDENTITY) if self.use_channel_mlp else x1
@@ -729,10 +737,10 @@ class FNOBlocks(nn.Module):
     def forward_with_preactivation(self, x, index=0, output_shape=None):
         """fno_block.py:416-453: activation first, then conv + skip (+ activation unless last), then the channel MLP + skip."""
         _require_device_tensor(x, "FNOBlocks input")
-        x = channel_mix(add=x.contiguous(), act=ACT_GELU)
+        x = channel_mix(add=x.contiguous(), act=self._act)
         if self.norm is not None:                                                                # fno_block.py:421-422
             x = _apply_norm(x, *_norm_scale_shift(self.norm[self.n_norms * index], x))
-        act = ACT_GELU if index < (self.n_layers - 1) else ACT_IDENTITY
+        act = self._act if index < (self.n_layers - 1) else ACT_IDENTITY
         x1 = self._fourier_step(x, index, output_shape, act)
         if self.norm is not None:                                                                # fno_block.py:444-445
             x1 = _apply_norm(x1, *_norm_scale_shift(self.norm[self.n_norms * index + 1], x1))

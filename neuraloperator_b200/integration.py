@@ -23,10 +23,10 @@ from .spectral_conv import SpectralConv
 
 
 def _convert_channel_mlp(ref: nn.Module) -> ChannelMLP:
-    if getattr(ref, "dropout", None) is not None:
-        raise NotImplementedError("ChannelMLP with dropout has no B200 drop-in")
+    drop = ref.dropout[0].p if getattr(ref, "dropout", None) is not None else 0.0      # (eval-mode only on the B200 side)
     new = ChannelMLP(ref.in_channels, out_channels=ref.out_channels, hidden_channels=ref.hidden_channels, n_layers=ref.n_layers,
-                     non_linearity=ref.non_linearity)
+                     non_linearity=ref.non_linearity, dropout=drop)
+    new.train(ref.training)
     new.load_state_dict(ref.state_dict())
     return new
 

@@ -89,8 +89,9 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
                       weight_kind: str = "dense", fno_skip: Optional[str] = "linear", channel_mlp_skip: Optional[str] = "soft-gating",
                       use_channel_mlp: bool = True, stabilizer: Optional[str] = None, preactivation: bool = False,
                       output_shape: Optional[Sequence[int]] = None, resolution_scaling_factor=None,
-                      max_n_modes: Optional[Sequence[int]] = None, norm: Optional[str] = None, norm_groups: int = 1) -> torch.Tensor:
-    """One Fourier layer: `FNOBlocks.forward(x, index, output_shape)` for real data, GELU, norm in {None, instance_norm, group_norm}."""
+                      max_n_modes: Optional[Sequence[int]] = None, norm: Optional[str] = None, norm_groups: int = 1,
+                      non_linearity=F.gelu) -> torch.Tensor:
+    """One Fourier layer: `FNOBlocks.forward(x, index, output_shape)` for real data (the ChannelMLP inside keeps GELU, fno_block.py:280-290)."""
     grid = list(x.shape[2:])
     rsf = resolution_scaling_factor
     if rsf is not None and not isinstance(rsf, (list, tuple)):
@@ -98,7 +99,7 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
     out_grid = O.resolve_output_grid(grid, rsf, output_shape)
     nonlin = index < n_layers - 1
     if preactivation:
-        x = F.gelu(x)                                                           # :419
+        x = non_linearity(x)                                                    # :419
         if norm is not None:
             x = _norm(norm, params, f"norm.{2 * index}", x, norm_groups)         # :421-422
     x_skip_fno = None
@@ -115,7 +116,7 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
         x_fno = _norm(norm, params, f"norm.{2 * index}", x_fno, norm_groups)     # :394-395
     y = x_fno + x_skip_fno if x_skip_fno is not None else x_fno                 # :397
     if nonlin:
-        y = F.gelu(y)                                                           # :399-400
+        y = non_linearity(y)                                                    # :399-400
     if norm is not None and preactivation:
         y = _norm(norm, params, f"norm.{2 * index + 1}", y, norm_groups)         # :444-445
     if use_channel_mlp:                                                         # :402-406
@@ -125,7 +126,7 @@ def fno_block_forward(x: torch.Tensor, params: Dict[str, torch.Tensor], index: i
     if norm is not None and not preactivation:
         y = _norm(norm, params, f"norm.{2 * index + 1}", y, norm_groups)         # :408-409
     if nonlin and not preactivation:                                            # :411-412 (the pre-activation form ends without it)
-        y = F.gelu(y)
+        y = non_linearity(y)
     return y
 
 

@@ -69,7 +69,12 @@ CASES = [
     ("block_cplx_d2_identity_no_mlp", 2, 4, 4, (10, 12), (6, 6), 2, 0, {"complex_data": True, "fno_skip": "identity", "use_channel_mlp": False}, {}),
     ("block_cplx_d3_preactivation_softgating", 1, 3, 3, (6, 6, 8), (4, 4, 4), 2, 0,
      {"complex_data": True, "preactivation": True, "fno_skip": "soft-gating"}, {}),
+    ("block_d2_relu", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"non_linearity": "relu"}, {}),
+    ("block_d2_silu_preactivation", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"non_linearity": "silu", "preactivation": True}, {}),
+    ("block_d1_tanh_activation_no_mlp", 2, 4, 4, (30,), (8,), 2, 0, {"non_linearity": "tanh", "use_channel_mlp": False}, {}),
 ]
+
+ACTIVATIONS = {"relu": torch.nn.functional.relu, "silu": torch.nn.functional.silu, "tanh": torch.tanh}
 
 
 def main():
@@ -81,7 +86,10 @@ def main():
         torch.manual_seed(7000 + seed)
         ctor = dict(implementation="reconstructed")
         ctor.update(ckw)
-        blk = fb.FNOBlocks(Ci, Co, modes, n_layers=n_layers, **ctor)
+        live = dict(ctor)
+        if "non_linearity" in live:
+            live["non_linearity"] = ACTIVATIONS[live["non_linearity"]]
+        blk = fb.FNOBlocks(Ci, Co, modes, n_layers=n_layers, **live)
         with torch.no_grad():                                   # soft-gating weights start at exactly 1: make them matter
             for pname, p in blk.named_parameters():
                 if "channel_mlp_skips" in pname or (pname.startswith("fno_skips") and p.ndim == len(grid) + 2) or pname.startswith("norm."):

@@ -103,6 +103,19 @@ def load_complex_golden(name):
     return meta, out
 
 
+BLOCK_ACTIVATIONS = {"relu": torch.nn.functional.relu, "silu": torch.nn.functional.silu, "tanh": torch.tanh}
+
+
+def block_ctor_kwargs(meta):
+    """Constructor keywords of a block golden with the activation name resolved to the callable."""
+    ctor = dict(meta["ctor"])
+    if "max_n_modes" in ctor:
+        ctor["max_n_modes"] = tuple(ctor["max_n_modes"])
+    if "non_linearity" in ctor:
+        ctor["non_linearity"] = BLOCK_ACTIVATIONS[ctor["non_linearity"]]
+    return ctor
+
+
 def block_golden_index():
     with open(os.path.join(GOLDEN_DIR, "block_index.json")) as f:
         return json.load(f)["cases"]
@@ -135,6 +148,8 @@ def block_oracle_kwargs(meta):
               use_channel_mlp=ctor.get("use_channel_mlp", True), stabilizer=ctor.get("stabilizer"),
               preactivation=ctor.get("preactivation", False), resolution_scaling_factor=ctor.get("resolution_scaling_factor"),
               norm=ctor.get("norm"), norm_groups=ctor.get("norm_groups", 1))
+    if "non_linearity" in ctor:
+        kw["non_linearity"] = BLOCK_ACTIVATIONS[ctor["non_linearity"]]
     if "max_n_modes" in ctor:
         from oracle.spectral_conv_oracle import stored_n_modes
         kw["max_n_modes"] = stored_n_modes(ctor["max_n_modes"])

@@ -12,7 +12,7 @@ import torch
 
 import neuraloperator_b200 as nb
 from neuraloperator_b200 import _lib, fno_block as fb
-from conftest import block_golden_index, load_block_golden
+from conftest import block_ctor_kwargs, block_golden_index, load_block_golden
 from oracle import spectral_conv_oracle as O
 from oracle.load_reference import load_reference_spectral_conv, reference_available
 
@@ -108,9 +108,7 @@ def _our_name(pname):
 
 
 def _build(meta):
-    ctor = dict(meta["ctor"])
-    if "max_n_modes" in ctor:
-        ctor["max_n_modes"] = tuple(ctor["max_n_modes"])
+    ctor = block_ctor_kwargs(meta)
     return nb.FNOBlocks(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), n_layers=meta["n_layers"], **ctor)
 
 
@@ -188,8 +186,7 @@ def test_state_dict_round_trip_with_the_reference(host):
 
 def test_unsupported_configurations_raise():
     for kw in (dict(complex_data=True, norm="group_norm"), dict(complex_data=True, resolution_scaling_factor=2),
-               dict(channel_mlp_dropout=0.1), dict(conv_bias_kernel=3),
-               dict(non_linearity=torch.nn.functional.relu)):
+               dict(conv_bias_kernel=3), dict(non_linearity=torch.nn.functional.elu)):
         with pytest.raises(NotImplementedError):
             nb.FNOBlocks(4, 4, (4, 4), **kw)
     with pytest.raises(ValueError):
@@ -198,6 +195,19 @@ def test_unsupported_configurations_raise():
         nb.FNOBlocks(4, 4, (4, 4), norm="bogus")
     with pytest.raises(ValueError):
         nb.FNOBlocks(4, 6, (4, 4))                       # soft gating needs in == out channels (skip_connections.py:74-79)
+
+
+def test_dropout_is_the_identity_in_eval_mode_and_refused_in_training(host):
+    meta, io, params, _ = load_block_golden("block_d2_default_mid")
+    plain, dropped = _build(meta), nb.FNOBlocks(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), n_layers=2,
+                                                 implementation="reconstructed", channel_mlp_dropout=0.3)
+    dropped.load_state_dict(plain.state_dict())
+    dropped.eval()
+    with torch.no_grad():
+        assert rel_err(dropped(io["x"], 0), plain(io["x"], 0)) == 0.0
+    dropped.train()
+    with pytest.raises(NotImplementedError, match="training mode"):
+        dropped(io["x"], 0)
 
 
 def test_no_cpu_path():

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 import neuraloperator_b200 as nb
 from neuraloperator_b200 import _lib
-from conftest import block_golden_index, load_block_golden
+from conftest import block_ctor_kwargs, block_golden_index, load_block_golden
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]
 REL_TOL = 1e-4
@@ -96,9 +96,7 @@ def _our_name(pname):
 @pytest.mark.parametrize("name", CASES)
 def test_block_module_matches_reference_golden(cuda_device, name):
     meta, io, params, grads = load_block_golden(name)
-    ctor = dict(meta["ctor"])
-    if "max_n_modes" in ctor:
-        ctor["max_n_modes"] = tuple(ctor["max_n_modes"])
+    ctor = block_ctor_kwargs(meta)
     blk = nb.FNOBlocks(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), n_layers=meta["n_layers"], **ctor).to(cuda_device)
     ours = dict(blk.named_parameters())
     with torch.no_grad():

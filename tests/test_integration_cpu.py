@@ -72,15 +72,14 @@ def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
 
 @pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
 def test_blocks_without_a_drop_in_keep_the_reference_block_and_swap_its_convs(host):  # noqa: F811
-    """channel_mlp_dropout > 0: the reference FNOBlocks stays (dropout has no drop-in), the SpectralConvs inside it and the lifting /
-    projection MLPs move over; outputs and gradients are unchanged (eval mode: dropout off)."""
+    """conv_bias_kernel=3 (a local 3x3 convolution as the skip): the reference FNOBlocks stays (no drop-in for that), the SpectralConvs and
+    the ChannelMLPs inside it and the lifting / projection MLPs move over; outputs and gradients are unchanged."""
     import sys
     sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
     from make_golden_fno import load_reference_fno
     fno = load_reference_fno()
     torch.manual_seed(5)
-    model = fno.FNO(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=8, n_layers=2, channel_mlp_dropout=0.1, max_n_modes=(10, 8))
-    model.eval()
+    model = fno.FNO(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=8, n_layers=2, conv_bias_kernel=3, max_n_modes=(10, 8))
     x = torch.randn(2, 1, 16, 12)
     xr = x.clone().requires_grad_(True)
     y_ref = model(xr)
@@ -160,11 +159,11 @@ def test_batch_norm_eval_mode_uses_the_running_statistics(host):  # noqa: F811
 
 
 def test_unsupported_reference_modules_are_reported():
-    class ChannelMLP(torch.nn.Module):                     # a reference-like ChannelMLP with dropout
+    class ChannelMLP(torch.nn.Module):                     # a reference-like ChannelMLP with an activation the kernels do not have
         in_channels = out_channels = hidden_channels = 4
         n_layers = 2
-        non_linearity = staticmethod(torch.nn.functional.gelu)
-        dropout = torch.nn.ModuleList([torch.nn.Dropout(0.1)])
+        non_linearity = staticmethod(torch.nn.functional.elu)
+        dropout = None
     holder = torch.nn.Module()
     holder.mlp = ChannelMLP()
     with pytest.warns(UserWarning, match="stays the reference module"):

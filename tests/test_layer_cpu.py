@@ -85,6 +85,28 @@ def test_channel_mix_without_mixing_term():
     assert (out.double() - ref_out).abs().max() < 1e-5 and (pre.double() - ref_pre).abs().max() < 1e-5
 
 
+TORCH_ACT = {_lib.ACT_IDENTITY: lambda t: t, _lib.ACT_GELU: F.gelu, _lib.ACT_RELU: F.relu, _lib.ACT_SILU: F.silu, _lib.ACT_TANH: torch.tanh}
+
+
+@pytest.mark.parametrize("act", [_lib.ACT_RELU, _lib.ACT_SILU, _lib.ACT_TANH, _lib.ACT_GELU])
+def test_every_activation_forward_and_derivative(act):
+    """out = act(pre) in the mixing kernel and gpre = gout * act'(pre) in the backward kernel against torch's function and autograd."""
+    lib = _lib.load()
+    B, C, P = 2, 5, 333
+    g = torch.Generator().manual_seed(act)
+    add = torch.randn(B, C, P, generator=g) * 2
+    out, pre = host_channel_mix(None, None, 0, 0, None, add, None, None, act, B, 0, C, P)
+    ref_in = add.double().requires_grad_(True)
+    ref = TORCH_ACT[act](ref_in)
+    assert (out.double() - ref.detach()).abs().max() < 1e-6
+    assert torch.equal(pre, add)
+    gout = torch.randn(B, C, P, generator=g)
+    ref.backward(gout.double())
+    gpre = torch.full((B, C, P), float("nan"))
+    assert lib.sc_hostcheck_channel_mix_act_backward(_p(gout), _p(pre), act, None, None, _p(gpre), None, None, None, B, C, P) == 0
+    assert (gpre.double() - ref_in.grad).abs().max() < 2e-6
+
+
 def test_channel_mix_rejects_bad_arguments():
     lib = _lib.load()
     out = torch.empty(1, 1, 1)
