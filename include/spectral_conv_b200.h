@@ -258,9 +258,10 @@ int sc_layer_uses_tensor_cores(void);
  *                                                   (x.half() :436-437, x.chalf() :451-454, chalf output spectrum :456-462)
  *   SC_POINTWISE_ADD_I_TIMES    a + 1j * b          on interleaved complex (re, im) pairs: how `apply_complex` (neuralop/layers/complex.py:
  *                                                   55-62) combines the real and the imaginary module of a ComplexValued layer
- *   SC_POINTWISE_MUL_NEG_I      -1j * a             (the gradient of the above with respect to b); both: n even, out aliases no input */
+ *   SC_POINTWISE_MUL_NEG_I      -1j * a             (the gradient of the above with respect to b); both: n even, out aliases no input
+ *   SC_POINTWISE_MUL            a * b               dropout of the ChannelMLP (channel_mlp.py:54-58, 110-111): b = mask / (1 - p) */
 enum { SC_POINTWISE_TANH = 0, SC_POINTWISE_TANH_BACKWARD = 1, SC_POINTWISE_ROUND_HALF = 2, SC_POINTWISE_ADD_I_TIMES = 3,
-       SC_POINTWISE_MUL_NEG_I = 4 };
+       SC_POINTWISE_MUL_NEG_I = 4, SC_POINTWISE_MUL = 5 };
 int sc_pointwise(int op, const float* a, const float* b, float* out, int64_t n, sc_stream stream);
 /* Host checks of the four kernels above: the kernels are sequences of __host__ __device__ tile functions; these entry points run
  * exactly those functions thread by thread, block by block, on HOST buffers (same arguments, no stream).  They exist so that the CPU

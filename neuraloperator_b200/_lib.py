@@ -13,7 +13,7 @@ SC_MAX_DIMS = 4
 NORMS = {"forward": 0, "backward": 1, "ortho": 2}
 FLAG_RESAMPLE = 1
 ACT_IDENTITY, ACT_GELU, ACT_RELU, ACT_SILU, ACT_TANH = 0, 1, 2, 3, 4
-POINTWISE_TANH, POINTWISE_TANH_BACKWARD, POINTWISE_ROUND_HALF, POINTWISE_ADD_I_TIMES, POINTWISE_MUL_NEG_I = 0, 1, 2, 3, 4
+POINTWISE_TANH, POINTWISE_TANH_BACKWARD, POINTWISE_ROUND_HALF, POINTWISE_ADD_I_TIMES, POINTWISE_MUL_NEG_I, POINTWISE_MUL = 0, 1, 2, 3, 4, 5
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int

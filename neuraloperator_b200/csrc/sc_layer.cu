@@ -569,6 +569,7 @@ SC_HD float pointwise_elem(int op, const float* a, const float* b, long long i) 
     case SC_POINTWISE_ADD_I_TIMES: return (i & 1) ? a[i] + b[i - 1] : a[i] - b[i + 1];
     // out = -1j * a   (its gradient with respect to b)
     case SC_POINTWISE_MUL_NEG_I: return (i & 1) ? -a[i - 1] : a[i + 1];
+    case SC_POINTWISE_MUL: return a[i] * b[i];                                                  // dropout: x * (mask / (1 - p))
     default: return a[i];
   }
 }
@@ -701,9 +702,10 @@ int sc_layer_set_tensor_cores(int enable) {
 int sc_layer_uses_tensor_cores(void) { return mix_tc_enabled() ? 1 : 0; }
 
 int sc_pointwise(int op, const float* a, const float* b, float* out, int64_t n, sc_stream stream) {
-  SC_REQUIRE(op >= SC_POINTWISE_TANH && op <= SC_POINTWISE_MUL_NEG_I, "sc_pointwise: unknown op");
+  SC_REQUIRE(op >= SC_POINTWISE_TANH && op <= SC_POINTWISE_MUL, "sc_pointwise: unknown op");
   SC_REQUIRE(n == 0 || (a != nullptr && out != nullptr), "sc_pointwise: null argument");
-  SC_REQUIRE((op != SC_POINTWISE_TANH_BACKWARD && op != SC_POINTWISE_ADD_I_TIMES) || n == 0 || b != nullptr, "sc_pointwise: this op needs its second operand");
+  SC_REQUIRE((op != SC_POINTWISE_TANH_BACKWARD && op != SC_POINTWISE_ADD_I_TIMES && op != SC_POINTWISE_MUL) || n == 0 || b != nullptr,
+             "sc_pointwise: this op needs its second operand");
   SC_REQUIRE((op != SC_POINTWISE_ADD_I_TIMES && op != SC_POINTWISE_MUL_NEG_I) || ((n & 1) == 0 && a != out && b != out),
              "sc_pointwise: the complex-pair ops need an even count and an output that aliases no input");
   SC_TRY(launch_pointwise(op, a, b, out, (long long)n, static_cast<cudaStream_t>(stream)));
@@ -749,7 +751,7 @@ int sc_hostcheck_channel_mix_weight_grad(const float* gpre, const float* in, flo
 }
 
 int sc_hostcheck_pointwise(int op, const float* a, const float* b, float* out, int64_t n) {
-  SC_REQUIRE(op >= SC_POINTWISE_TANH && op <= SC_POINTWISE_MUL_NEG_I, "sc_hostcheck_pointwise: unknown op");
+  SC_REQUIRE(op >= SC_POINTWISE_TANH && op <= SC_POINTWISE_MUL, "sc_hostcheck_pointwise: unknown op");
   SC_REQUIRE((op != SC_POINTWISE_ADD_I_TIMES && op != SC_POINTWISE_MUL_NEG_I) || ((n & 1) == 0 && a != out && b != out),
              "sc_hostcheck_pointwise: the complex-pair ops need an even count and an output that aliases no input");
   // the kernel's own index walk: block, thread, slot

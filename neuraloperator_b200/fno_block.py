@@ -346,6 +346,34 @@ class InstanceNorm(nn.Module):
         return _apply_norm(x, scale, shift)
 
 
+class _Dropout(torch.autograd.Function):
+    """F.dropout(x, p, training=True) (channel_mlp.py:54-58, 110-111): the Bernoulli mask comes from torch's generator --
+    `F.dropout(ones)` draws exactly the mask `F.dropout(x)` would, so a run seeded like the reference drops the same elements --
+    and is applied (forward and backward) by the pointwise product kernel."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        x = x.contiguous()
+        scaled_mask = F.dropout(torch.ones_like(x), p, True)             # mask / (1 - p)
+        ctx.save_for_backward(scaled_mask)
+        return _Dropout._mul(x, scaled_mask)
+
+    @staticmethod
+    def _mul(a, b):
+        lib = _lib.load()
+        out = torch.empty_like(a)
+        if a.numel():
+            with torch.cuda.device(a.device):
+                _lib.check(lib.sc_pointwise(_lib.POINTWISE_MUL, _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream_ptr(a.device)), "sc_pointwise")
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (scaled_mask,) = ctx.saved_tensors
+        return _Dropout._mul(g.contiguous().float(), scaled_mask), None
+
+
 # --------------------------------------------------------------------------------------------------
 # parameter containers with the reference's names (state-dict compatible) and fused forwards
 # --------------------------------------------------------------------------------------------------
@@ -402,7 +430,6 @@ class ChannelMLP(nn.Module):
         self.out_channels = in_channels if out_channels is None else out_channels
         self.hidden_channels = in_channels if hidden_channels is None else hidden_channels
         self.non_linearity = non_linearity
-        # dropout: identity in eval mode (F.dropout); the training-mode mask is not built (forward raises there)
         self.dropout = nn.ModuleList([nn.Dropout(dropout) for _ in range(n_layers)]) if dropout > 0.0 else None
         self.fcs = nn.ModuleList()                                                       # Conv1d modules as parameter containers
         for i in range(n_layers):
@@ -411,13 +438,21 @@ class ChannelMLP(nn.Module):
             self.fcs.append(nn.Conv1d(cin, cout, 1))
 
     def _forward_fused(self, x, gate=None, gated=None, final_act=ACT_IDENTITY):
-        if self.dropout is not None and self.training:
-            raise NotImplementedError("ChannelMLP: dropout in training mode is not built (eval mode, where it is the identity, is)")
+        dropping = self.dropout is not None and self.training and self.dropout[0].p > 0.0
         for i, fc in enumerate(self.fcs):
-            if i < self.n_layers - 1:
+            last = i == self.n_layers - 1
+            if not last:
                 x = channel_mix(x, fc.weight, fc.bias, act=self._act)
+            elif dropping:
+                # the reference drops the output of the last layer BEFORE the block adds its skip (channel_mlp.py:104-111): the skip
+                # and the final activation get a launch of their own
+                x = channel_mix(x, fc.weight, fc.bias)
             else:
                 x = channel_mix(x, fc.weight, fc.bias, gate=gate, gated=gated, act=final_act)
+            if dropping:
+                x = _Dropout.apply(x, self.dropout[i].p)
+        if dropping and (gated is not None or final_act != ACT_IDENTITY):
+            x = channel_mix(add=x, gate=gate, gated=gated, act=final_act)
         return x
 
     def forward(self, x):

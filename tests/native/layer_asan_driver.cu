@@ -54,6 +54,7 @@ int main(int argc, char** argv) {
           CHECK(sc_hostcheck_pointwise(SC_POINTWISE_TANH, out.p, nullptr, pre.p, (long long)B * Co * P));
           CHECK(sc_hostcheck_pointwise(SC_POINTWISE_TANH_BACKWARD, out.p, pre.p, out.p, (long long)B * Co * P));
           CHECK(sc_hostcheck_pointwise(SC_POINTWISE_ROUND_HALF, out.p, nullptr, out.p, (long long)B * Co * P));
+          CHECK(sc_hostcheck_pointwise(SC_POINTWISE_MUL, out.p, pre.p, out.p, (long long)B * Co * P));
           if ((((long long)B * Co * P) & 1) == 0) {      // the complex-pair ops read the neighbour inside a pair
             CHECK(sc_hostcheck_pointwise(SC_POINTWISE_ADD_I_TIMES, out.p, pre.p, add.p, (long long)B * Co * P));
             CHECK(sc_hostcheck_pointwise(SC_POINTWISE_MUL_NEG_I, out.p, nullptr, add.p, (long long)B * Co * P));

@@ -197,17 +197,42 @@ def test_unsupported_configurations_raise():
         nb.FNOBlocks(4, 6, (4, 4))                       # soft gating needs in == out channels (skip_connections.py:74-79)
 
 
-def test_dropout_is_the_identity_in_eval_mode_and_refused_in_training(host):
+def test_dropout_eval_identity_and_training_masks_like_the_reference(host):
     meta, io, params, _ = load_block_golden("block_d2_default_mid")
     plain, dropped = _build(meta), nb.FNOBlocks(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), n_layers=2,
                                                  implementation="reconstructed", channel_mlp_dropout=0.3)
     dropped.load_state_dict(plain.state_dict())
     dropped.eval()
     with torch.no_grad():
-        assert rel_err(dropped(io["x"], 0), plain(io["x"], 0)) == 0.0
+        assert rel_err(dropped(io["x"], 0), plain(io["x"], 0)) == 0.0            # eval mode: the identity
     dropped.train()
-    with pytest.raises(NotImplementedError, match="training mode"):
-        dropped(io["x"], 0)
+    torch.manual_seed(1)
+    a = dropped(io["x"], 0)
+    torch.manual_seed(2)
+    b = dropped(io["x"], 0)
+    assert rel_err(a, b.detach()) > 1e-2                                          # training mode: a different mask per draw
+    if not reference_available():
+        return
+    # same generator state, same masks: F.dropout(ones) draws what the reference's F.dropout(x) draws (channel_mlp.py:110-111)
+    load_reference_spectral_conv()
+    ref_fb = importlib.import_module("neuralop.layers.fno_block")
+    ref = ref_fb.FNOBlocks(meta["in_channels"], meta["out_channels"], tuple(meta["n_modes"]), n_layers=2, implementation="reconstructed",
+                           channel_mlp_dropout=0.3)
+    ref.load_state_dict(plain.state_dict())
+    for index in (0, 1):
+        x1, x2 = io["x"].clone().requires_grad_(True), io["x"].clone().requires_grad_(True)
+        torch.manual_seed(7)
+        y_ref = ref(x1, index)
+        torch.manual_seed(7)
+        y = dropped(x2, index)
+        y_ref.backward(io["gy"])
+        y.backward(io["gy"])
+        assert rel_err(y, y_ref.detach()) < 2e-5 and rel_err(x2.grad, x1.grad) < 2e-5
+        for (n1, p1), (n2, p2) in zip(dropped.named_parameters(), ref.named_parameters()):
+            if p2.grad is not None:
+                assert n1 == n2 and rel_err(p1.grad, p2.grad) < 5e-5, n1
+        dropped.zero_grad(set_to_none=True)
+        ref.zero_grad(set_to_none=True)
 
 
 def test_no_cpu_path():

@@ -195,6 +195,8 @@ def test_pointwise_ops(n):
     assert lib.sc_hostcheck_pointwise(_lib.POINTWISE_ROUND_HALF, _p(big), None, _p(out2), big.numel()) == 0
     assert torch.equal(out2, big.half().float())           # bit-exact: round-to-nearest-even fp16, as torch's .half()
     assert lib.sc_hostcheck_pointwise(9, _p(a), None, _p(out), n) != 0
+    assert lib.sc_hostcheck_pointwise(_lib.POINTWISE_MUL, _p(a), _p(b), _p(out), n) == 0
+    assert n == 0 or torch.equal(out, a * b)
     if n % 2 == 0 and n:                                     # the complex-pair ops: out = a + 1j * b, out = -1j * a on interleaved pairs
         ac, bc = torch.view_as_complex(a.view(-1, 2)), torch.view_as_complex(b.view(-1, 2).contiguous())
         assert lib.sc_hostcheck_pointwise(_lib.POINTWISE_ADD_I_TIMES, _p(a), _p(b), _p(out), n) == 0
