@@ -9,7 +9,8 @@ semantics (fno_block.py:371-453), with everything after the spectral convolution
 
 instead of one tensor pass per torch op (conv1d, add, gelu, mul, add, gelu ...).  No CPU / PyTorch fallback: the modules raise on
 CPU tensors, and configurations the kernels do not cover (complex data, dropout, activations other than GELU, conv_bias_kernel > 1)
-raise `NotImplementedError` at construction (activations: gelu, relu, silu, tanh; dropout: eval mode only).  The four `norm` options are composed from the same kernels (one statistics pass + one
+raise `NotImplementedError` at construction (activations: gelu, relu, silu, tanh; `conv_bias_kernel > 1` keeps torch's Conv{n}d for
+that skip).  The four `norm` options are composed from the same kernels (one statistics pass + one
 fused affine / add / activation launch per normalisation).
 """
 import math
@@ -587,8 +588,15 @@ class FNOBlocks(nn.Module):
             raise NotImplementedError("FNOBlocks(complex_data=True) with a resolution change is not built (the reference's `resample` "
                                       "interpolates real tensors)")
         self._act = ACT_GELU if complex_data else activation_code(non_linearity)      # (complex data: CGELU whatever was passed, :204-207)
+        if conv_bias_kernel < 1:
+            raise ValueError(f"conv_bias_kernel must be >= 1, got {conv_bias_kernel}")
         if conv_bias_kernel != 1:
-            raise NotImplementedError("FNOBlocks: conv_bias_kernel > 1 (a local convolution as the skip) is not built")
+            if fno_skip is None or fno_skip.lower() != "linear":
+                raise ValueError("conv_bias_kernel can only differ from 1 when fno_skip='linear'.")
+            if self.n_dim > 3:
+                raise NotImplementedError("conv_bias_kernel > 1 is only implemented for 1D, 2D, and 3D FNO blocks.")
+            if complex_data:
+                raise NotImplementedError("FNOBlocks(complex_data=True) with conv_bias_kernel > 1 is not built")
         if stabilizer not in (None, "tanh"):
             raise ValueError(f"unknown stabilizer {stabilizer!r}")
         for name, kind in (("fno_skip", fno_skip), ("channel_mlp_skip", channel_mlp_skip)):
@@ -633,7 +641,13 @@ class FNOBlocks(nn.Module):
             )
             for i in range(n_layers)
         ])
-        if self.fno_skip is not None:
+        if self.fno_skip is not None and conv_bias_kernel != 1:
+            # a LOCAL convolution as the skip (fno_block.py:18-43): the one piece of the block that is a library call here (torch's
+            # Conv{n}d = cuDNN, like the reference); its output joins the fused add + activation launch as a materialised skip
+            self.fno_skips = nn.ModuleList([getattr(nn, f"Conv{self.n_dim}d")(self.in_channels, self.out_channels,
+                                                                               kernel_size=conv_bias_kernel, padding="same", bias=False)
+                                            for _ in range(n_layers)])
+        elif self.fno_skip is not None:
             self.fno_skips = nn.ModuleList([skip_connection(self.in_channels, self.out_channels, skip_type=self.fno_skip, n_dim=self.n_dim)
                                             for _ in range(n_layers)])
         else:
@@ -672,8 +686,8 @@ class FNOBlocks(nn.Module):
     def _skip_terms(kind, module, x):
         """The skip as (x_mix, weight, gate, gated) operands of the fused op, without materialising it."""
         if kind == "linear":
-            if module.conv.bias is not None:
-                return None          # (never built by skip_connection's default bias=False: materialise)
+            if not isinstance(module, Flattened1dConv) or module.conv.bias is not None:
+                return None          # a local convolution (conv_bias_kernel > 1) or a skip with a bias: materialise
             return x, module.conv.weight, None, None
         if kind == "soft-gating":
             if module.bias is not None:

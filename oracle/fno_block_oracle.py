@@ -27,6 +27,8 @@ from . import spectral_conv_oracle as O
 
 
 def _skip(kind: Optional[str], params: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor) -> torch.Tensor:
+    if kind == "linear" and prefix + ".weight" in params:                      # conv_bias_kernel > 1: Conv{n}d, padding="same", no bias (:36-43)
+        return getattr(F, f"conv{x.ndim - 2}d")(x, params[prefix + ".weight"], padding="same")
     if kind == "linear":
         w = params[prefix + ".conv.weight"]                                   # (Co, Ci, 1), no bias (skip_connection default)
         size = list(x.shape)

@@ -72,6 +72,8 @@ CASES = [
     ("block_d2_relu", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"non_linearity": "relu"}, {}),
     ("block_d2_silu_preactivation", 2, 6, 6, (12, 14), (6, 6), 2, 0, {"non_linearity": "silu", "preactivation": True}, {}),
     ("block_d1_tanh_activation_no_mlp", 2, 4, 4, (30,), (8,), 2, 0, {"non_linearity": "tanh", "use_channel_mlp": False}, {}),
+    ("block_d2_conv_bias_kernel_3", 2, 4, 6, (12, 14), (6, 6), 2, 0, {"conv_bias_kernel": 3, "channel_mlp_skip": "linear"}, {}),
+    ("block_d1_conv_bias_kernel_5_upsample", 2, 4, 4, (24,), (8,), 2, 0, {"conv_bias_kernel": 5, "resolution_scaling_factor": 2}, {}),
 ]
 
 ACTIVATIONS = {"relu": torch.nn.functional.relu, "silu": torch.nn.functional.silu, "tanh": torch.tanh}

@@ -186,13 +186,15 @@ def test_state_dict_round_trip_with_the_reference(host):
 
 def test_unsupported_configurations_raise():
     for kw in (dict(complex_data=True, norm="group_norm"), dict(complex_data=True, resolution_scaling_factor=2),
-               dict(conv_bias_kernel=3), dict(non_linearity=torch.nn.functional.elu)):
+               dict(conv_bias_kernel=3, complex_data=True), dict(non_linearity=torch.nn.functional.elu)):
         with pytest.raises(NotImplementedError):
             nb.FNOBlocks(4, 4, (4, 4), **kw)
     with pytest.raises(ValueError):
         nb.FNOBlocks(4, 4, (4, 4), fno_skip="bogus")
     with pytest.raises(ValueError):
         nb.FNOBlocks(4, 4, (4, 4), norm="bogus")
+    with pytest.raises(ValueError):
+        nb.FNOBlocks(4, 4, (4, 4), conv_bias_kernel=3, fno_skip="soft-gating")
     with pytest.raises(ValueError):
         nb.FNOBlocks(4, 6, (4, 4))                       # soft gating needs in == out channels (skip_connections.py:74-79)
 

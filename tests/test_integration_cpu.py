@@ -35,7 +35,9 @@ def test_stacked_drop_ins_match_reference_fno_golden(host, name):  # noqa: F811
                                 dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="instance_norm"),
                                 dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, norm="batch_norm"),
                                 dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, complex_data=True,
-                                     positional_embedding=None)])
+                                     positional_embedding=None),
+                                dict(n_modes=(8, 8), in_channels=1, out_channels=1, hidden_channels=6, n_layers=2, conv_bias_kernel=3,
+                                     channel_mlp_dropout=0.2, non_linearity=torch.nn.functional.silu)])
 def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
     import sys
     sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
@@ -43,6 +45,8 @@ def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
     fno = load_reference_fno()
     torch.manual_seed(21)
     model = fno.FNO(**kw)                                  # default positional embedding (grid) + no padding: stays reference code
+    if kw.get("channel_mlp_dropout"):
+        model.eval()                                       # (training-mode dropout is compared under equal seeds in test_block_host_logic)
     grid = (16,) * len(kw["n_modes"])
     x = torch.randn(2, kw["in_channels"], *grid, dtype=torch.cfloat if kw.get("complex_data") else torch.float32)
     gy = None
@@ -72,14 +76,15 @@ def test_use_b200_layers_on_a_live_reference_model(host, kw):  # noqa: F811
 
 @pytest.mark.skipif(not reference_available(), reason="reference tree not present (GPU box)")
 def test_blocks_without_a_drop_in_keep_the_reference_block_and_swap_its_convs(host):  # noqa: F811
-    """conv_bias_kernel=3 (a local 3x3 convolution as the skip): the reference FNOBlocks stays (no drop-in for that), the SpectralConvs and
-    the ChannelMLPs inside it and the lifting / projection MLPs move over; outputs and gradients are unchanged."""
+    """non_linearity=F.elu (an activation the kernels do not have): the reference FNOBlocks and the lifting / projection MLPs stay, with a
+    warning each; the SpectralConvs and the (GELU) ChannelMLPs inside the block move over; outputs and gradients are unchanged."""
     import sys
     sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__import__("os").path.dirname(__file__)), "oracle"))
     from make_golden_fno import load_reference_fno
     fno = load_reference_fno()
     torch.manual_seed(5)
-    model = fno.FNO(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=8, n_layers=2, conv_bias_kernel=3, max_n_modes=(10, 8))
+    model = fno.FNO(n_modes=(8, 6), in_channels=1, out_channels=1, hidden_channels=8, n_layers=2, non_linearity=torch.nn.functional.elu,
+                    max_n_modes=(10, 8))
     x = torch.randn(2, 1, 16, 12)
     xr = x.clone().requires_grad_(True)
     y_ref = model(xr)
@@ -91,7 +96,8 @@ def test_blocks_without_a_drop_in_keep_the_reference_block_and_swap_its_convs(ho
     nb.use_b200_layers(model)
     assert type(model.fno_blocks).__module__.startswith("neuralop.")                    # the block is still the reference's
     assert all(type(c) is nb.SpectralConv for c in model.fno_blocks.convs)              # ... its convs are ours
-    assert type(model.lifting) is nb.ChannelMLP
+    assert all(type(m) is nb.ChannelMLP for m in model.fno_blocks.channel_mlp)          # ... and its (GELU) channel MLPs
+    assert type(model.lifting).__module__.startswith("neuralop.")                       # an elu MLP has no drop-in
     assert model.fno_blocks.convs[0].n_modes == [8, 4] and list(model.fno_blocks.convs[0].max_n_modes) == [10, 8]
     xo = x.clone().requires_grad_(True)
     y = model(xo)
