@@ -986,10 +986,10 @@ class SpectralConv(BaseSpectralConv):
                              f"to out_channels, but got in_channels={in_channels} and out_channels={out_channels}")
         if fno_block_precision not in ("full", "half", "mixed"):
             raise ValueError(f"Got fno_block_precision={fno_block_precision}, expected 'full', 'half' or 'mixed'")
-        if fno_block_precision != "full" and (complex_data or separable or
-                                              (implementation == "factorized" and factorization not in (None, "dense", "Dense", "ComplexDense"))):
-            raise NotImplementedError("fno_block_precision 'half' / 'mixed' is built for real data and a dense or reconstructed weight "
-                                      "(not for complex_data, separable, or a factor-by-factor contraction)")
+        if fno_block_precision != "full" and (complex_data or separable):
+            raise NotImplementedError("fno_block_precision 'half' / 'mixed' is built for real data and a non-separable weight")
+        # (reduced precision with implementation="factorized": the weight is reconstructed in fp32 and rounded to fp16 ONCE, where the
+        #  reference's einsum_complexhalf rounds after every pairwise contraction of the factors -- fewer roundings, same fp16 noise level)
         if implementation not in ("reconstructed", "factorized"):
             raise ValueError(f'Got implementation={implementation}, expected "reconstructed" or "factorized"')
         if fft_norm not in _lib.NORMS:

@@ -67,8 +67,9 @@ def test_module_contract_dense():
     assert tuple(csep.weight.shape) == (4, 8, 8)
     assert nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half").fno_block_precision == "half"
     assert nb.SpectralConv(4, 4, (8, 8), fno_block_precision="mixed", factorization="tucker", rank=[2, 2, 3, 3]).implementation == "reconstructed"
-    with pytest.raises(NotImplementedError):     # factor-by-factor contraction in reduced precision is not built
-        nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half", factorization="tucker", implementation="factorized")
+    assert nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half", factorization="tucker", implementation="factorized").implementation == "factorized"
+    with pytest.raises(NotImplementedError):
+        nb.SpectralConv(4, 4, (8, 8), fno_block_precision="half", separable=True)
     with pytest.raises(NotImplementedError):
         nb.SpectralConv(4, 4, (8, 8), fno_block_precision="mixed", complex_data=True)
     with pytest.raises(ValueError):
