@@ -208,3 +208,21 @@ def test_complex_contraction_plans_are_valid_problems(lib):
                                   None, 0, ctypes.byref(r), ctypes.byref(c))
         assert rc == 0, (name, lib.sc_last_error())
         assert (r.value, c.value) == (cgrid[-1], 2 * kept[-1]), (name, r.value, c.value)
+
+
+def test_product_package_never_uses_the_test_hooks_or_the_oracle():
+    """The `sc_hostcheck_*` entry points (host execution of the layer kernels' tile functions, dry run of the C chains) and everything
+    under oracle/ are test infrastructure: the package binds the symbols (header == binding == exports) but no product module calls
+    them, imports the oracle, or reaches for torch.fft / cuFFT / Triton / torch.compile."""
+    import glob
+    import re
+    pkg = os.path.join(ROOT, "neuraloperator_b200")
+    for path in glob.glob(os.path.join(pkg, "*.py")):
+        src = open(path).read()
+        code = "\n".join(line.split("#", 1)[0] for line in src.splitlines())        # comments may mention them
+        code = re.sub(r'""".*?"""', "", code, flags=re.S)
+        if not path.endswith("_lib.py"):
+            assert "sc_hostcheck" not in code, path
+        assert not re.search(r"^\s*(from|import)\s+oracle", code, flags=re.M), path
+        for banned in ("torch.fft", "cufft", "triton", "torch.compile"):
+            assert banned not in code, (path, banned)
