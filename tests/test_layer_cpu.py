@@ -271,7 +271,7 @@ def test_whole_layer_epilogue_on_the_host_tiles_matches_reference_ops():
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
 
-@settings(max_examples=80, deadline=None)
+@settings(max_examples=80, deadline=None, derandomize=True)
 @given(B=st.integers(1, 3), Ci=st.integers(0, 70), Co=st.integers(1, 70), P=st.integers(1, 300), has_bias=st.booleans(), has_add=st.booleans(),
        gate_kind=st.sampled_from(["none", "gated", "gate+gated"]), gelu=st.booleans(), seed=st.integers(0, 10_000))
 def test_channel_mix_random_extents_and_options(B, Ci, Co, P, has_bias, has_add, gate_kind, gelu, seed):
@@ -290,7 +290,7 @@ def test_channel_mix_random_extents_and_options(B, Ci, Co, P, has_bias, has_add,
     assert (out.double() - ref_out).abs().max() < 2e-5 * max(1.0, ref_out.abs().max().item())
 
 
-@settings(max_examples=40, deadline=None)
+@settings(max_examples=40, deadline=None, derandomize=True)
 @given(B=st.integers(1, 3), Ci=st.integers(1, 70), Co=st.integers(1, 70), P=st.integers(1, 5000), seed=st.integers(0, 10_000))
 def test_weight_grad_random_extents(B, Ci, Co, P, seed):
     lib = _lib.load()
