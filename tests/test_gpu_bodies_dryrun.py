@@ -131,3 +131,87 @@ def complex_primitives(monkeypatch, no_cuda_calls):
 @pytest.mark.parametrize("name", G_COMPLEX.CASES)
 def test_body_complex_goldens(complex_primitives, name):
     G_COMPLEX.test_complex_module_matches_golden(CPU, name)
+
+
+# ---- CP / TT: Python-orchestrated chain vs the one-C-call entry points (tests/test_gpu_zzzz_factorized_c.py) ---------------------
+import test_gpu_zzzz_factorized_c as G_CHAINS  # noqa: E402
+from test_factorized_host_logic import _pair_reduce  # noqa: E402
+
+
+class _ChainCalls(type(_CHAIN_LIB)):
+    """The per-factor primitives as in test_factorized_host_logic; the one-call entry points with REAL transforms around the oracle's
+    einsum statement of the contraction (their C orchestration is replayed from the launch log in tests/test_factorized_chain_log.py)."""
+
+    @staticmethod
+    def _run(plan, x, bias, contract):
+        m = O.analyze_modes(x, plan.dims, plan.fft_norm)
+        y = O.synthesize_modes(contract(m), plan.dims, plan.out_grid, plan.fft_norm)
+        return y + (bias.reshape(1, -1, *[1] * plan.ndim) if bias is not None else 0)
+
+    def sc_pointwise(self, *a):
+        raise AssertionError("not used here")
+
+    def sc_bias_grad(self, plan, gm, db, B, Co, st):                   # fft_norm "forward": the DC slot of gm is sum_n gy
+        db.copy_(gm[(slice(None), slice(None)) + tuple(p.in_bins.index(0) for p in plan.dims)].real.sum(0))
+        return 0
+
+    def sc_forward_cp(self, plan, x, lam, u_in, u_out, u_modes, bias, y, saved, B, Ci, Co, R, ws, n, st):
+        self._x = x.detach().clone()
+        y.copy_(self._run(plan, x, bias, lambda m: O.contract_cp(m, lam, [u_in, u_out, *u_modes])))
+        return 0
+
+    def sc_backward_cp(self, plan, gy, lam, u_in, u_out, u_modes, saved, dx, d_lam, d_u_in, d_u_out, d_u_modes, dbias, B, Ci, Co, R, ws, n, st):
+        with torch.enable_grad():
+            ps = [t.detach().clone().requires_grad_(True) for t in (self._x, lam, u_in, u_out, *u_modes)]
+            self._run(plan, ps[0], None, lambda m: O.contract_cp(m, ps[1], ps[2:])).backward(gy)
+        for dst, src in zip([dx, d_lam, d_u_in, d_u_out, *d_u_modes], ps):
+            dst.copy_(src.grad)
+        if dbias is not None:
+            dbias.copy_(gy.sum(dim=[0] + list(range(2, gy.ndim))))
+        return 0
+
+    def sc_forward_tt(self, plan, plan_kept, x, g0, g1, cores, bias, y, saved, B, Ci, Co, ranks, ws, n, st):
+        self._x = x.detach().clone()
+        y.copy_(self._run(plan, x, bias, lambda m: O.contract_tt(m, [g0, g1, *cores])))
+        return 0
+
+    def sc_backward_tt(self, plan, plan_kept, gy, g0, g1, cores, saved, dx, d_g0, d_g1, d_cores, dbias, B, Ci, Co, ranks, ws, n, st):
+        with torch.enable_grad():
+            ps = [t.detach().clone().requires_grad_(True) for t in (self._x, g0, g1, *cores)]
+            self._run(plan, ps[0], None, lambda m: O.contract_tt(m, ps[1:])).backward(gy)
+        for dst, src in zip([dx, d_g0, d_g1, *d_cores], ps):
+            dst.copy_(src.grad)
+        if dbias is not None:
+            dbias.copy_(gy.sum(dim=[0] + list(range(2, gy.ndim))))
+        return 0
+
+
+@pytest.fixture
+def chain_primitives(monkeypatch, conv_primitives):
+    lib = _ChainCalls()
+    monkeypatch.setattr(sc._lib, "load", lambda: lib)
+    monkeypatch.setattr(sc._lib, "check", lambda rc, what: None)
+    monkeypatch.setattr(sc._lib, "launch_count", lambda: 0)
+    monkeypatch.setattr(sc, "_ptr", lambda t: t)
+    monkeypatch.setattr(sc, "_ptr_array", lambda ts: list(ts))
+    monkeypatch.setattr(sc, "_table_contract", _table_contract)
+    monkeypatch.setattr(sc, "_pair_reduce", _pair_reduce)
+    monkeypatch.setattr(sc, "_cp_factor_args", lambda us, kept: (list(us), list(kept), len(us)))
+    monkeypatch.setattr(G_CHAINS._lib, "launch_count", iter(range(10 ** 6)).__next__)       # "kernels were launched": any increasing counter
+    return lib
+
+
+@pytest.mark.parametrize("fact,rank,Ci,Co,grid,modes,max_modes", [("cp", 6, 4, 5, (12, 10, 16), (6, 6, 8), None), ("cp", 8, 8, 8, (32, 32), (8, 8), (16, 12)),
+                                                                 ("tt", 0.5, 6, 7, (64,), (20,), None), ("tt", 0.3, 8, 8, (32, 32), (8, 8), (16, 12))])
+def test_body_c_chain_vs_python_chain(chain_primitives, fact, rank, Ci, Co, grid, modes, max_modes):
+    G_CHAINS.test_c_chain_matches_python_chain(CPU, fact, rank, Ci, Co, grid, modes, max_modes)
+
+
+@pytest.mark.parametrize("name", ["d2_cp", "d2_tt"])
+def test_body_c_chain_goldens(chain_primitives, name):
+    old = sc.FACTORIZED_CHAINS_IN_C
+    sc.FACTORIZED_CHAINS_IN_C = True
+    try:
+        G_CHAINS.test_c_chain_matches_reference_golden(CPU, None, name)
+    finally:
+        sc.FACTORIZED_CHAINS_IN_C = old
