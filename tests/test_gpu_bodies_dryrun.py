@@ -215,3 +215,17 @@ def test_body_c_chain_goldens(chain_primitives, name):
         G_CHAINS.test_c_chain_matches_reference_golden(CPU, None, name)
     finally:
         sc.FACTORIZED_CHAINS_IN_C = old
+
+
+# ---- the tensor-core mixing tier: its test LOGIC only (on the CPU both settings run the SIMT tile functions) ------------------------
+import test_gpu_zzzzz_mix_tc as G_TC  # noqa: E402
+
+
+@pytest.mark.parametrize("B,Ci,Co,grid", [(2, 64, 32, (50, 30)), (3, 5, 7, (129,)), (1, 200, 100, (40,))])
+def test_body_tensor_core_tier_logic(host, no_cuda_calls, monkeypatch, B, Ci, Co, grid):  # noqa: F811
+    flag = {"on": False}
+    monkeypatch.setattr(G_TC.nb, "set_tensor_core_mixing", lambda enable: flag.__setitem__("on", bool(enable)))
+    monkeypatch.setattr(G_TC.nb, "uses_tensor_core_mixing", lambda: flag["on"])
+    flag["on"] = True                                           # what the `tensor_cores` fixture of that file does
+    G_TC.test_tensor_core_mix_matches_float64_and_simt(CPU, None, B, Ci, Co, grid)
+    G_TC.test_tensor_core_mix_through_the_block(CPU, None)
