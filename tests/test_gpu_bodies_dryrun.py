@@ -229,3 +229,8 @@ def test_body_tensor_core_tier_logic(host, no_cuda_calls, monkeypatch, B, Ci, Co
     flag["on"] = True                                           # what the `tensor_cores` fixture of that file does
     G_TC.test_tensor_core_mix_matches_float64_and_simt(CPU, None, B, Ci, Co, grid)
     G_TC.test_tensor_core_mix_through_the_block(CPU, None)
+
+
+def test_body_mixed_precision_block_runs(host, no_cuda_calls):  # noqa: F811
+    """(the conv is the full-precision oracle here: this only exercises the test's own logic and the block wiring with tanh)"""
+    G_LAYER.test_block_with_mixed_precision_and_tanh_runs(CPU)
